@@ -1,0 +1,131 @@
+/*
+ * mpa_b200.h -- C ABI of libmpa_b200.so, the B200 (sm_100a) native hot path of
+ * multi_part_assembly.  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *   - every pointer named d_* / without a "_host" suffix in the function name is a
+ *     DEVICE pointer valid on the current CUDA device; functions ending in
+ *     `_host` take HOST pointers and do their own H2D/D2H copies.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream,
+ *     which is what the reference kernels use: chamfer_kernel.cu:147).
+ *   - return value: 0 on success, negative MPA_ERR_* otherwise; the message is
+ *     available from mpa_last_error() (thread-local).  Nothing is printed and
+ *     the process is never exited (contrast pointnet2_ops cuda_utils.h:30-39).
+ *   - workspaces: `ws` may be NULL, in which case the library allocates and frees
+ *     scratch with cudaMallocAsync/cudaFreeAsync on `stream`; otherwise `ws` must
+ *     hold at least the size the matching *_workspace_bytes() returns.
+ *   - all arithmetic is fp32 (the reference force-casts Chamfer and rotations to
+ *     float32: utils/chamfer/chamfer.py:14, utils/rotation.py:141).
+ *
+ * Reference paths are relative to /root/reference/multi_part_assembly.
+ */
+#ifndef MPA_B200_H_
+#define MPA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPA_OK 0
+#define MPA_ERR_INVALID_ARG (-1)
+#define MPA_ERR_CUDA (-2)
+#define MPA_ERR_WORKSPACE (-3)
+#define MPA_ERR_UNSUPPORTED (-4)
+
+/* Chamfer nearest-neighbour search algorithm selector (results are identical
+ * bit for bit; this only picks the kernel). */
+#define MPA_ALGO_AUTO 0
+#define MPA_ALGO_BRUTE 1 /* one thread per query, all pairs, packed FP32x2 math */
+#define MPA_ALGO_GRID 2  /* exact uniform-grid search (counting sort + ring walk) */
+
+const char* mpa_last_error(void);
+int mpa_version(void);
+/* number of kernels this library has launched in this process (bench.py's
+ * `gpu_launches` claim is the difference across the timed region). */
+uint64_t mpa_launch_count(void);
+
+/* ---- Chamfer distance -------------------------------------------------- */
+/* Replaces chamfer_cuda.chamfer_forward (utils/chamfer/cuda/chamfer.cpp:8-11,21;
+ * ChamferForward, chamfer_kernel.cu:116-168).
+ *   xyz1 [B,N1,3], xyz2 [B,N2,3] contiguous fp32
+ *   dist1 [B,N1], dist2 [B,N2] fp32 : squared distance to the nearest neighbour
+ *   idx1 [B,N1], idx2 [B,N2] int64  : its index (lowest index on ties,
+ *                                     chamfer_kernel.cu:82); may be NULL
+ * Both directions run in one launch sequence on `stream`. */
+size_t mpa_chamfer_forward_workspace_bytes(int B, int N1, int N2, int algo);
+int mpa_chamfer_forward(const float* xyz1, const float* xyz2, int B, int N1, int N2,
+                        float* dist1, int64_t* idx1, float* dist2, int64_t* idx2,
+                        int algo, void* ws, size_t ws_bytes, void* stream);
+
+/* Replaces chamfer_cuda.chamfer_backward (chamfer.cpp:13-19,22; ChamferBackward,
+ * chamfer_kernel.cu:224-289).  grad_xyz1 [B,N1,3], grad_xyz2 [B,N2,3] are
+ * OVERWRITTEN (the reference returns freshly zeroed tensors, :252-253).
+ * Accumulates with fp32 atomics like the reference (:203-208), so the
+ * summation order of coincident neighbours is unspecified. */
+int mpa_chamfer_backward(const float* grad_dist1, const float* grad_dist2,
+                         const float* xyz1, const float* xyz2, const int64_t* idx1,
+                         const int64_t* idx2, int B, int N1, int N2, float* grad_xyz1,
+                         float* grad_xyz2, void* stream);
+
+/* Same as mpa_chamfer_forward with HOST buffers: copies inputs H2D, runs, copies
+ * the four outputs D2H, synchronises `stream`.  This is the end-to-end entry the
+ * `e2e` leg of bench.py times. */
+int mpa_chamfer_forward_host(const float* h_xyz1, const float* h_xyz2, int B, int N1,
+                             int N2, float* h_dist1, int64_t* h_idx1, float* h_dist2,
+                             int64_t* h_idx2, int algo, void* stream);
+
+/* ---- SE(3) on part point clouds ---------------------------------------- */
+/* Replaces qrot / qtransform (utils/transforms.py:75-109), i.e.
+ * pytorch3d.transforms.quaternion_apply broadcast over the N points of a part:
+ *   out[p,i,:] = (q_p (x) (0,pts[p,i,:]) (x) conj(q_p))[1:] (+ trans[p,:])
+ * quat [n_parts,4] real part first, trans [n_parts,3] or NULL (rot_pc),
+ * pts/out [n_parts,N,3]. */
+int mpa_se3_transform(const float* quat, const float* trans, const float* pts,
+                      int n_parts, int N, float* out, void* stream);
+/* Backward of the above: grad_pts (always), grad_quat/grad_trans (may be NULL). */
+int mpa_se3_transform_backward(const float* quat, const float* pts, const float* grad_out,
+                               int n_parts, int N, float* grad_pts, float* grad_quat,
+                               float* grad_trans, void* stream);
+
+/* ---- fused pose losses -------------------------------------------------- */
+/* Fused SE(3) + bidirectional Chamfer for the two Chamfer losses of
+ * utils/loss.py.  pts [B,P,N,3]; quat1/quat2 [B,P,4]; trans1/trans2 [B,P,3] or
+ * NULL; valids [B,P] (1.0 valid / 0.0 padded).
+ *
+ * mode MPA_CD_PART  : rot_points_cd_loss (loss.py:113-138): every part is its own
+ *                     cloud.  Padded parts are skipped (their dist is 0).
+ * mode MPA_CD_SHAPE : shape_cd_loss (loss.py:141-202): padded parts are filled
+ *                     with 1e3 (:173-175), all parts of a shape form one cloud
+ *                     of P*N points.  Padded query points get dist 0; padded
+ *                     target parts stay candidates exactly as in the reference.
+ * Outputs (device): dist1/dist2 [B,P,N] fp32, idx1/idx2 [B,P,N] int32 index into
+ * the cloud (part-local for PART, shape-level p*N+i for SHAPE; -1 for skipped),
+ * pts1/pts2 [B,P,N,3] transformed clouds or NULL. */
+#define MPA_CD_PART 0
+#define MPA_CD_SHAPE 1
+size_t mpa_pose_chamfer_workspace_bytes(int B, int P, int N, int mode);
+int mpa_pose_chamfer(const float* pts, const float* quat1, const float* trans1,
+                     const float* quat2, const float* trans2, const float* valids,
+                     int B, int P, int N, int mode, float* dist1, int32_t* idx1,
+                     float* dist2, int32_t* idx2, float* pts1, float* pts2, void* ws,
+                     size_t ws_bytes, void* stream);
+
+/* Backward of mpa_pose_chamfer w.r.t. the two poses (the points carry no
+ * gradient: loss.py:172 detaches them, and part_pcs is data).  Chains
+ * ChamferBackward (chamfer_kernel.cu:175-210) into the SE(3) backward.
+ * grad_quat{1,2} [B,P,4] and grad_trans{1,2} [B,P,3] may be NULL (e.g. the ground-truth pose). */
+size_t mpa_pose_chamfer_backward_workspace_bytes(int B, int P, int N);
+int mpa_pose_chamfer_backward(const float* grad_dist1, const float* grad_dist2, const float* pts,
+                              const float* quat1, const float* quat2, const float* valids,
+                              const float* pts1, const float* pts2, const int32_t* idx1,
+                              const int32_t* idx2, int B, int P, int N, int mode, float* grad_quat1,
+                              float* grad_trans1, float* grad_quat2, float* grad_trans2, void* ws,
+                              size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPA_B200_H_ */

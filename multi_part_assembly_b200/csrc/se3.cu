@@ -1,0 +1,154 @@
+// SE(3) on part point clouds: qrot / qtransform (utils/transforms.py:75-109) and
+// their backward.  One quaternion (+ translation) per part, applied to the N
+// points of the part without materialising the [B,P,N,4] broadcast the
+// reference builds with repeat_interleave (:85, :103).
+#include "mpa_common.cuh"
+
+namespace mpa {
+
+// 4 points (12 floats, three 16-byte vectors) per thread when N % 4 == 0.
+__global__ void __launch_bounds__(256)
+se3_forward_vec4_kernel(const float* __restrict__ quat, const float* __restrict__ trans,
+                        const float4* __restrict__ pts, int n_parts, int N, float4* __restrict__ out) {
+  const int groups_per_part = N >> 2;
+  const long long total = (long long)n_parts * groups_per_part;
+  for (long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; gidx < total;
+       gidx += (long long)gridDim.x * blockDim.x) {
+    const int part = (int)(gidx / groups_per_part);
+    const float4 qv = *reinterpret_cast<const float4*>(quat + 4 * (long long)part);
+    const float q[4] = {qv.x, qv.y, qv.z, qv.w};
+    const float* t = trans ? trans + 3 * (long long)part : nullptr;
+    const float4 a = pts[gidx * 3 + 0], b = pts[gidx * 3 + 1], c = pts[gidx * 3 + 2];
+    const float3 p0 = se3_apply(q, t, make_float3(a.x, a.y, a.z));
+    const float3 p1 = se3_apply(q, t, make_float3(a.w, b.x, b.y));
+    const float3 p2 = se3_apply(q, t, make_float3(b.z, b.w, c.x));
+    const float3 p3 = se3_apply(q, t, make_float3(c.y, c.z, c.w));
+    out[gidx * 3 + 0] = make_float4(p0.x, p0.y, p0.z, p1.x);
+    out[gidx * 3 + 1] = make_float4(p1.y, p1.z, p2.x, p2.y);
+    out[gidx * 3 + 2] = make_float4(p2.z, p3.x, p3.y, p3.z);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+se3_forward_kernel(const float* __restrict__ quat, const float* __restrict__ trans,
+                   const float* __restrict__ pts, int n_parts, int N, float* __restrict__ out) {
+  const long long total = (long long)n_parts * N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long part = i / N;
+    const float q[4] = {quat[4 * part], quat[4 * part + 1], quat[4 * part + 2], quat[4 * part + 3]};
+    const float3 v = se3_apply(q, trans ? trans + 3 * part : nullptr,
+                               make_float3(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]));
+    out[3 * i] = v.x; out[3 * i + 1] = v.y; out[3 * i + 2] = v.z;
+  }
+}
+
+// v' = (w^2 - u.u) v + 2 (u.v) u + 2 w (u x v)   with q = (w, u)
+//   grad_v = (w^2 - u.u) g + 2 (u.g) u - 2 w (u x g)
+//   grad_w = sum_i g . (2 w v + 2 u x v)
+//   grad_u = sum_i [ -2 (g.v) u + 2 (u.v) g + 2 (u.g) v + 2 w (v x g) ]
+//   grad_t = sum_i g
+// One CTA per part; the seven sums are reduced in a fixed order (deterministic).
+__global__ void __launch_bounds__(256)
+se3_backward_kernel(const float* __restrict__ quat, const float* __restrict__ pts,
+                    const float* __restrict__ gout, const float* __restrict__ valids,
+                    int fill_invalid, int N, float* __restrict__ gpts,
+                    float* __restrict__ gquat, float* __restrict__ gtrans) {
+  __shared__ float red[7][8];
+  const int part = blockIdx.x;
+  // shape_cd_loss: a padded part is the constant point (1e3,1e3,1e3) (loss.py:175)
+  const bool filled = fill_invalid && valids != nullptr && valids[part] == 0.0f;
+  const float w = quat[4 * part], ux = quat[4 * part + 1], uy = quat[4 * part + 2], uz = quat[4 * part + 3];
+  const float s = w * w - (ux * ux + uy * uy + uz * uz);
+  float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const long long o = ((long long)part * N + i) * 3;
+    const float gx = gout[o], gy = gout[o + 1], gz = gout[o + 2];
+    if (gpts != nullptr) {
+      const float ug = ux * gx + uy * gy + uz * gz;
+      gpts[o] = s * gx + 2.f * ug * ux - 2.f * w * (uy * gz - uz * gy);
+      gpts[o + 1] = s * gy + 2.f * ug * uy - 2.f * w * (uz * gx - ux * gz);
+      gpts[o + 2] = s * gz + 2.f * ug * uz - 2.f * w * (ux * gy - uy * gx);
+    }
+    if (gquat != nullptr || gtrans != nullptr) {
+      const float vx = filled ? 1e3f : pts[o], vy = filled ? 1e3f : pts[o + 1],
+                  vz = filled ? 1e3f : pts[o + 2];
+      const float gv = gx * vx + gy * vy + gz * vz;
+      const float uv = ux * vx + uy * vy + uz * vz;
+      const float ug = ux * gx + uy * gy + uz * gz;
+      const float cx = uy * vz - uz * vy, cy = uz * vx - ux * vz, cz = ux * vy - uy * vx;  // u x v
+      const float kx = vy * gz - vz * gy, ky = vz * gx - vx * gz, kz = vx * gy - vy * gx;  // v x g
+      acc[0] += 2.f * (w * gv + (gx * cx + gy * cy + gz * cz));
+      acc[1] += 2.f * (-gv * ux + uv * gx + ug * vx + w * kx);
+      acc[2] += 2.f * (-gv * uy + uv * gy + ug * vy + w * ky);
+      acc[3] += 2.f * (-gv * uz + uv * gz + ug * vz + w * kz);
+      acc[4] += gx; acc[5] += gy; acc[6] += gz;
+    }
+  }
+  if (gquat == nullptr && gtrans == nullptr) return;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    float v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) red[k][wid] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 7) {
+    float v = 0.f;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) v += red[threadIdx.x][k];
+    if (threadIdx.x < 4) {
+      if (gquat != nullptr) gquat[4 * part + threadIdx.x] = v;
+    } else if (gtrans != nullptr) {
+      gtrans[3 * part + threadIdx.x - 4] = v;
+    }
+  }
+}
+
+int launch_se3_backward(const float* quat, const float* pts, const float* grad_out,
+                        const float* valids, int fill_invalid, int n_parts, int N, float* grad_pts,
+                        float* grad_quat, float* grad_trans, cudaStream_t stream) {
+  se3_backward_kernel<<<n_parts, 256, 0, stream>>>(quat, pts, grad_out, valids, fill_invalid, N,
+                                                   grad_pts, grad_quat, grad_trans);
+  MPA_LAUNCH_CHECK();
+  return MPA_OK;
+}
+
+}  // namespace mpa
+
+using namespace mpa;
+
+extern "C" {
+
+int mpa_se3_transform(const float* quat, const float* trans, const float* pts, int n_parts, int N,
+                      float* out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MPA_CHECK_ARG(n_parts >= 0 && N >= 0, "se3_transform: negative size");
+  if (n_parts == 0 || N == 0) return MPA_OK;
+  MPA_CHECK_ARG(quat && pts && out, "se3_transform: null pointer");
+  const bool vec = (N % 4 == 0) && (((uintptr_t)pts | (uintptr_t)out | (uintptr_t)quat) % 16 == 0);
+  const long long work = vec ? (long long)n_parts * (N / 4) : (long long)n_parts * N;
+  long long blocks = (work + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (vec)
+    se3_forward_vec4_kernel<<<(unsigned)blocks, 256, 0, stream>>>(
+        quat, trans, (const float4*)pts, n_parts, N, (float4*)out);
+  else
+    se3_forward_kernel<<<(unsigned)blocks, 256, 0, stream>>>(quat, trans, pts, n_parts, N, out);
+  MPA_LAUNCH_CHECK();
+  return MPA_OK;
+}
+
+int mpa_se3_transform_backward(const float* quat, const float* pts, const float* grad_out,
+                               int n_parts, int N, float* grad_pts, float* grad_quat,
+                               float* grad_trans, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MPA_CHECK_ARG(n_parts >= 0 && N >= 0, "se3_transform_backward: negative size");
+  if (n_parts == 0) return MPA_OK;
+  MPA_CHECK_ARG(quat && pts && grad_out, "se3_transform_backward: null pointer");
+  return launch_se3_backward(quat, pts, grad_out, nullptr, 0, n_parts, N, grad_pts, grad_quat,
+                             grad_trans, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,211 @@
+"""Loss terms of the assembly models, reference API of utils/loss.py; every
+function returns a per-shape [B] tensor.
+
+`rot_points_cd_loss` and `shape_cd_loss` (reference :113-202) are the dominant
+cost of a training step.  The reference chains masked_fill / transform_pc x2 /
+chamfer_distance; here both run as ONE fused op (`pose_chamfer`, csrc/chamfer.cu):
+the pose is applied while the clouds are binned into a uniform grid, the two
+nearest-neighbour directions share that grid build, and the backward goes
+straight from d(dist) to d(quat), d(trans).
+"""
+import torch
+
+from .. import _lib
+from .rotation import Rotation3D
+from .transforms import rot_pc, transform_pc
+from .chamfer import chamfer_distance
+
+CD_PART, CD_SHAPE = 0, 1
+
+
+def _valid_mean(loss_per_part, valids):
+    """[B, P] -> [B], mean over the valid parts (reference :7-19)."""
+    valids = valids.float().detach()
+    return (loss_per_part * valids).sum(1) / valids.sum(1)
+
+
+class _PoseChamferFunction(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, pts, quat1, trans1, quat2, trans2, valids, mode):
+        B, P, N, _ = pts.shape
+        dev = pts.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        dist1 = torch.empty(B, P, N, **f32)
+        dist2 = torch.empty(B, P, N, **f32)
+        idx1 = torch.empty(B, P, N, dtype=torch.int32, device=dev)
+        idx2 = torch.empty(B, P, N, dtype=torch.int32, device=dev)
+        pts1 = torch.empty(B, P, N, 3, **f32)
+        pts2 = torch.empty(B, P, N, 3, **f32)
+        L = _lib.lib()
+        ws_bytes = L.mpa_pose_chamfer_workspace_bytes(B, P, N, mode)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = L.mpa_pose_chamfer(
+                _lib.ptr(pts), _lib.ptr(quat1), _lib.ptr(trans1),
+                _lib.ptr(quat2), _lib.ptr(trans2), _lib.ptr(valids), B, P, N,
+                mode, _lib.ptr(dist1), _lib.ptr(idx1), _lib.ptr(dist2),
+                _lib.ptr(idx2), _lib.ptr(pts1), _lib.ptr(pts2), _lib.ptr(ws),
+                ws_bytes, _lib.cuda_stream(dev))
+        _lib.check(rc, 'mpa_pose_chamfer')
+        ctx.save_for_backward(pts, quat1, quat2, valids, pts1, pts2, idx1, idx2)
+        ctx.mode = mode
+        ctx.has_trans = (trans1 is not None, trans2 is not None)
+        ctx.mark_non_differentiable(pts1, pts2)
+        return dist1, dist2, pts1, pts2
+
+    @staticmethod
+    def backward(ctx, g1, g2, _gp1, _gp2):
+        pts, quat1, quat2, valids, pts1, pts2, idx1, idx2 = ctx.saved_tensors
+        B, P, N, _ = pts.shape
+        dev = pts.device
+        need = ctx.needs_input_grad
+        g1 = g1.contiguous().float()
+        g2 = g2.contiguous().float()
+        f32 = dict(dtype=torch.float32, device=dev)
+        gq1 = torch.empty(B, P, 4, **f32) if need[1] else None
+        gt1 = torch.empty(B, P, 3, **f32) if need[2] and ctx.has_trans[0] else None
+        gq2 = torch.empty(B, P, 4, **f32) if need[3] else None
+        gt2 = torch.empty(B, P, 3, **f32) if need[4] and ctx.has_trans[1] else None
+        L = _lib.lib()
+        ws_bytes = L.mpa_pose_chamfer_backward_workspace_bytes(B, P, N)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = L.mpa_pose_chamfer_backward(
+                _lib.ptr(g1), _lib.ptr(g2), _lib.ptr(pts), _lib.ptr(quat1),
+                _lib.ptr(quat2), _lib.ptr(valids), _lib.ptr(pts1),
+                _lib.ptr(pts2), _lib.ptr(idx1), _lib.ptr(idx2), B, P, N,
+                ctx.mode, _lib.ptr(gq1), _lib.ptr(gt1), _lib.ptr(gq2),
+                _lib.ptr(gt2), _lib.ptr(ws), ws_bytes, _lib.cuda_stream(dev))
+        _lib.check(rc, 'mpa_pose_chamfer_backward')
+        return None, gq1, gt1, gq2, gt2, None, None
+
+
+def pose_chamfer(pts, trans1, trans2, quat1, quat2, valids, mode):
+    """Fused SE(3) + bidirectional Chamfer.
+
+    pts [B,P,N,3]; quat* [B,P,4]; trans* [B,P,3] or None; valids [B,P].
+    Returns dist1, dist2 [B,P,N] (0 on padded parts) and the two transformed
+    clouds [B,P,N,3] (no gradient).
+    """
+    _lib.require_cuda(pts, quat1, quat2, trans1, trans2, valids)
+
+    def prep(t):
+        return None if t is None else t.contiguous().float()
+
+    return _PoseChamferFunction.apply(
+        prep(pts.detach()), prep(quat1), prep(trans1), prep(quat2), prep(trans2),
+        prep(valids.detach()), mode)
+
+
+def trans_l2_loss(trans1, trans2, valids):
+    """L2 loss between translations [B, P, 3] (reference :22-35)."""
+    return _valid_mean((trans1 - trans2).pow(2).sum(dim=-1), valids)
+
+
+def rot_l2_loss(rot1, rot2, valids):
+    """L2 loss between quaternions, q == -q (reference :38-56)."""
+    assert rot1.rot_type == rot2.rot_type == 'quat'
+    q1, q2 = rot1.rot, rot2.rot
+    loss = torch.minimum((q1 - q2).pow(2).sum(dim=-1), (q1 + q2).pow(2).sum(dim=-1))
+    return _valid_mean(loss, valids)
+
+
+def rot_cosine_loss(rot1, rot2, valids):
+    """Cosine loss between rotations (reference :59-86)."""
+    assert rot1.rot_type == rot2.rot_type
+    rot_type = rot1.rot_type
+    if rot_type == 'quat':
+        loss = 1. - torch.abs(torch.sum(rot1.rot * rot2.rot, dim=-1))
+    elif rot_type == 'rmat':
+        B = rot1.shape[0]
+        r1, r2 = rot1.rot.view(-1, 3, 3), rot2.rot.view(-1, 3, 3)
+        iden = torch.eye(3).unsqueeze(0).type_as(r1)
+        loss = (iden - torch.bmm(r1.transpose(1, 2), r2)).pow(2).mean(
+            dim=[-1, -2]).view(B, -1)
+    else:
+        raise NotImplementedError(f'cosine loss not supported for {rot_type}')
+    return _valid_mean(loss, valids)
+
+
+def rot_points_l2_loss(pts, rot1, rot2, valids, ret_pts=False):
+    """Per-point L2 between the part rotated by rot1 and by rot2
+    (reference :89-110)."""
+    pts1 = rot_pc(rot1, pts)
+    pts2 = rot_pc(rot2, pts)
+    loss = (pts1 - pts2).pow(2).sum(-1).mean(-1)  # [B, P]
+    loss = _valid_mean(loss, valids)
+    if ret_pts:
+        return loss, pts1, pts2
+    return loss
+
+
+def _both_quat(rot1, rot2):
+    return isinstance(rot1, Rotation3D) and isinstance(rot2, Rotation3D) and \
+        rot1.rot_type == 'quat' and rot2.rot_type == 'quat'
+
+
+def rot_points_cd_loss(pts, rot1, rot2, valids, ret_pts=False):
+    """Chamfer distance between each part rotated by rot1 and by rot2
+    (reference :113-138)."""
+    B = pts.shape[0]
+    if _both_quat(rot1, rot2):
+        dist1, dist2, pts1, pts2 = pose_chamfer(
+            pts, None, None, rot1.rot, rot2.rot, valids, CD_PART)
+        loss = dist1.mean(-1) + dist2.mean(-1)  # [B, P]
+    else:
+        pts1 = rot_pc(rot1, pts)
+        pts2 = rot_pc(rot2, pts)
+        dist1, dist2 = chamfer_distance(pts1.flatten(0, 1), pts2.flatten(0, 1))
+        loss = torch.mean(dist1, dim=1) + torch.mean(dist2, dim=1)
+        loss = loss.view(B, -1)
+    loss = _valid_mean(loss.type_as(pts), valids)
+    if ret_pts:
+        return loss, pts1, pts2
+    return loss
+
+
+def shape_cd_loss(pts, trans1, trans2, rot1, rot2, valids, ret_pts=False,
+                  training=True):
+    """Chamfer distance between the assembled shapes (reference :141-202).
+
+    training=True divides by the padded point count P*N (hard-negative
+    weighting, reference :185-193); False is the per-part mean averaged over
+    the valid parts (:195-198).
+    """
+    B, P, N, _ = pts.shape
+    if _both_quat(rot1, rot2):
+        dist1, dist2, pts1, pts2 = pose_chamfer(
+            pts, trans1, trans2, rot1.rot, rot2.rot, valids, CD_SHAPE)
+        dist1 = dist1.view(B, -1)  # padded points already contribute 0
+        dist2 = dist2.view(B, -1)
+    else:
+        pts = pts.detach().clone()
+        pts = pts.masked_fill(valids[..., None, None] == 0, 1e3)
+        pts1 = transform_pc(trans1, rot1, pts)
+        pts2 = transform_pc(trans2, rot2, pts)
+        dist1, dist2 = chamfer_distance(pts1.flatten(1, 2), pts2.flatten(1, 2))
+        vrep = valids.float().detach().unsqueeze(2).expand(B, P, N).reshape(B, -1)
+        dist1 = dist1 * vrep
+        dist2 = dist2 * vrep
+    valids = valids.float().detach()
+    if training:
+        loss = torch.mean(dist1, dim=1) + torch.mean(dist2, dim=1)
+    else:
+        loss = _valid_mean((dist1 + dist2).view(B, P, N).mean(-1), valids)
+    if ret_pts:
+        return loss, pts1, pts2
+    return loss
+
+
+def repulsion_cd_loss(part_pcs, valids, thre):
+    """Pairwise part Chamfer below `thre` as a repulsion term
+    (reference :205-225)."""
+    B, P, N, _ = part_pcs.shape
+    pts1 = part_pcs.unsqueeze(2).expand(B, P, P, N, 3).flatten(0, 2)
+    pts2 = part_pcs.unsqueeze(1).expand(B, P, P, N, 3).flatten(0, 2)
+    dist1, dist2 = chamfer_distance(pts1, pts2)  # [B*P*P, N]
+    cd = torch.mean(dist1, dim=1) + torch.mean(dist2, dim=1)
+    cd = torch.clamp_min(thre - cd.view(B, P, P), min=0.)
+    mask = valids[:, :, None] * valids[:, None, :]
+    return (cd * mask).sum([1, 2]) / mask.sum([1, 2])

@@ -1,0 +1,219 @@
+/*
+ * mpa_oracle.c -- TEST INFRASTRUCTURE ONLY (never imported by the product path).
+ *
+ * Scalar CPU restatement of the native / third-party arithmetic on the
+ * multi_part_assembly hot path.  Every function cites the reference lines it
+ * follows (paths relative to /root/reference/multi_part_assembly).  Built by
+ * oracle/Makefile into oracle/libmpa_oracle.so, loaded by oracle/cpu.py.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+ * reference legs may call this.
+ *
+ * Compile with -ffp-contract=off: every fused multiply-add below is explicit
+ * (fmaf) so the rounding sequence is the one written, on any host compiler.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* squared distance exactly as nvcc contracts the reference expression
+ *   (x1-x2)*(x1-x2) + (y1-y2)*(y1-y2) + (z1-z2)*(z1-z2)
+ * (utils/chamfer/cuda/chamfer_kernel.cu:80) with default -fmad=true:
+ *   t = dy*dy ; t = fma(dx,dx,t) ; t = fma(dz,dz,t)
+ * (checked with `nvcc -ptx` on that expression for sm_100a). */
+static inline float sqdist_ref(float x1, float y1, float z1,
+                               float x2, float y2, float z2) {
+  float dx = x1 - x2, dy = y1 - y2, dz = z1 - z2;
+  float t = dy * dy;
+  t = fmaf(dx, dx, t);
+  t = fmaf(dz, dz, t);
+  return t;
+}
+
+/* same distance without contraction: the definition in
+ * utils/chamfer/test_chamfer.py:8-18 (diff**2 summed over the last axis). */
+static inline float sqdist_unfused(float x1, float y1, float z1,
+                                   float x2, float y2, float z2) {
+  float dx = x1 - x2, dy = y1 - y2, dz = z1 - z2;
+  float a = dx * dx, b = dy * dy, c = dz * dz;
+  return (a + b) + c;
+}
+
+/* One direction of ChamferForwardKernel (chamfer_kernel.cu:32-95):
+ * for every point of xyz1[b] the squared distance to, and the index of, its
+ * nearest point of xyz2[b]; init min_dist=1e32, min_idx=-1 (:60-61); strict
+ * `d < min_dist` with j ascending so ties keep the lowest index (:81-85). */
+static void nn_one_direction(const float* xyz1, const float* xyz2, int64_t B,
+                             int64_t n1, int64_t n2, float* dist, int64_t* idx,
+                             int fused) {
+#pragma omp parallel for schedule(static)
+  for (int64_t bi = 0; bi < B * n1; ++bi) {
+    int64_t b = bi / n1;
+    const float* p = xyz1 + bi * 3;
+    const float* q = xyz2 + b * n2 * 3;
+    float best = 1e32f;
+    int64_t arg = -1;
+    for (int64_t j = 0; j < n2; ++j) {
+      float d = fused ? sqdist_ref(p[0], p[1], p[2], q[3 * j], q[3 * j + 1], q[3 * j + 2])
+                      : sqdist_unfused(p[0], p[1], p[2], q[3 * j], q[3 * j + 1], q[3 * j + 2]);
+      if (d < best) { best = d; arg = j; }
+    }
+    dist[bi] = best;
+    idx[bi] = arg;
+  }
+}
+
+/* ChamferForward (chamfer_kernel.cu:116-168): both directions. */
+void oracle_chamfer_forward(const float* xyz1, const float* xyz2, int64_t B,
+                            int64_t n1, int64_t n2, float* dist1, int64_t* idx1,
+                            float* dist2, int64_t* idx2, int fused) {
+  nn_one_direction(xyz1, xyz2, B, n1, n2, dist1, idx1, fused);
+  nn_one_direction(xyz2, xyz1, B, n2, n1, dist2, idx2, fused);
+}
+
+/* ChamferBackwardKernel (chamfer_kernel.cu:175-210), one direction:
+ * g = 2*grad_dist[i]; grad_a[i] += g*(a_i - b_idx); grad_b[idx] -= same.
+ * The reference accumulates with float atomics (order unspecified); the
+ * oracle accumulates in double in ascending i and rounds once, which is the
+ * value every float summation order approximates. */
+static void bwd_one_direction(const float* grad_dist, const int64_t* index,
+                              const float* a, const float* b, double* ga,
+                              double* gb, int64_t B, int64_t n1, int64_t n2) {
+  for (int64_t i = 0; i < B * n1; ++i) {
+    int64_t bt = i / n1;
+    int64_t j = bt * n2 + index[i];
+    float g = grad_dist[i] * 2.0f;
+    for (int c = 0; c < 3; ++c) {
+      float gc = g * (a[3 * i + c] - b[3 * j + c]);
+      ga[3 * i + c] += (double)gc;
+      gb[3 * j + c] -= (double)gc;
+    }
+  }
+}
+
+/* ChamferBackward (chamfer_kernel.cu:224-289). */
+void oracle_chamfer_backward(const float* grad_dist1, const float* grad_dist2,
+                             const float* xyz1, const float* xyz2,
+                             const int64_t* idx1, const int64_t* idx2, int64_t B,
+                             int64_t n1, int64_t n2, float* grad_xyz1,
+                             float* grad_xyz2) {
+  double* g1 = (double*)calloc((size_t)(B * n1 * 3), sizeof(double));
+  double* g2 = (double*)calloc((size_t)(B * n2 * 3), sizeof(double));
+  bwd_one_direction(grad_dist1, idx1, xyz1, xyz2, g1, g2, B, n1, n2);
+  bwd_one_direction(grad_dist2, idx2, xyz2, xyz1, g2, g1, B, n2, n1);
+  for (int64_t i = 0; i < B * n1 * 3; ++i) grad_xyz1[i] = (float)g1[i];
+  for (int64_t i = 0; i < B * n2 * 3; ++i) grad_xyz2[i] = (float)g2[i];
+  free(g1);
+  free(g2);
+}
+
+/* Hamilton product, the published pytorch3d.transforms.quaternion_raw_multiply
+ * (third-party, un-vendored and unpinned: setup.py:3-6 lists bare
+ * 'pytorch3d'); real part first.  Each output is evaluated left to right as
+ * the four-term expression of the published source, no contraction (torch
+ * elementwise kernels do not fuse). */
+static inline void qmul_raw(const float a[4], const float b[4], float o[4]) {
+  o[0] = ((a[0] * b[0] - a[1] * b[1]) - a[2] * b[2]) - a[3] * b[3];
+  o[1] = ((a[0] * b[1] + a[1] * b[0]) + a[2] * b[3]) - a[3] * b[2];
+  o[2] = ((a[0] * b[2] - a[1] * b[3]) + a[2] * b[0]) + a[3] * b[1];
+  o[3] = ((a[0] * b[3] + a[1] * b[2]) - a[2] * b[1]) + a[3] * b[0];
+}
+
+/* qrot / qtransform (utils/transforms.py:75-109) over a [n_parts, N, 3] cloud
+ * with one quaternion (and optional translation) per part:
+ *   v' = (q (x) (0,v) (x) conj(q))[1:] (+ t)
+ * = pytorch3d quaternion_apply; conj only, no normalisation, so a non-unit q
+ * scales by |q|^2 exactly as the reference does.  trans may be NULL (rot_pc). */
+void oracle_se3_transform(const float* quat, const float* trans,
+                          const float* pts, int64_t n_parts, int64_t N,
+                          float* out) {
+#pragma omp parallel for schedule(static)
+  for (int64_t p = 0; p < n_parts; ++p) {
+    const float* q = quat + 4 * p;
+    float qc[4] = {q[0], -q[1], -q[2], -q[3]};
+    for (int64_t i = 0; i < N; ++i) {
+      const float* v = pts + (p * N + i) * 3;
+      float pv[4] = {0.0f, v[0], v[1], v[2]};
+      float t1[4], t2[4];
+      qmul_raw(q, pv, t1);
+      qmul_raw(t1, qc, t2);
+      float* o = out + (p * N + i) * 3;
+      for (int c = 0; c < 3; ++c)
+        o[c] = trans ? t2[c + 1] + trans[3 * p + c] : t2[c + 1];
+    }
+  }
+}
+
+/* knn (models/modules/encoder/dgcnn.py:8-15) on x [n, C, N] (channel-major as
+ * the reference passes it): score(i,j) = -|xi|^2 + 2 xi.xj - |xj|^2 in the
+ * expanded form, top-k largest (self included).  The reference's matmul
+ * accumulation order and topk tie order are unspecified, so the oracle fixes
+ * them: sequential-c fp32 dot product, selection by (score desc, index asc),
+ * and the parity contract is the SORTED index set per row.
+ * out_idx: [n, N, k] int64, ascending index order within a row. */
+static int cmp_i64(const void* a, const void* b) {
+  int64_t x = *(const int64_t*)a, y = *(const int64_t*)b;
+  return (x > y) - (x < y);
+}
+void oracle_knn(const float* x, int64_t n, int64_t C, int64_t N, int64_t k,
+                int64_t* out_idx) {
+#pragma omp parallel
+  {
+    float* score = (float*)malloc((size_t)N * sizeof(float));
+    float* xx = (float*)malloc((size_t)N * sizeof(float));
+    char* taken = (char*)malloc((size_t)N);
+#pragma omp for schedule(dynamic, 1)
+    for (int64_t b = 0; b < n; ++b) {
+      const float* xb = x + b * C * N;
+      for (int64_t j = 0; j < N; ++j) {
+        float s = 0.0f;
+        for (int64_t c = 0; c < C; ++c) s += xb[c * N + j] * xb[c * N + j];
+        xx[j] = s;
+      }
+      for (int64_t i = 0; i < N; ++i) {
+        /* dgcnn.py:10-12: inner = -2 x^T x; xx is [B,1,N] so the FIRST term of
+         * `-xx - inner - xx^T` is -|x_j|^2 and the transposed one is -|x_i|^2;
+         * evaluated in the order written: (-xx_j - inner) - xx_i. */
+        for (int64_t j = 0; j < N; ++j) {
+          float dot = 0.0f;
+          for (int64_t c = 0; c < C; ++c) dot += xb[c * N + i] * xb[c * N + j];
+          float inner = -2.0f * dot;
+          score[j] = (-xx[j] - inner) - xx[i];
+        }
+        memset(taken, 0, (size_t)N);
+        int64_t* row = out_idx + (b * N + i) * k;
+        for (int64_t s = 0; s < k; ++s) {
+          int64_t arg = -1;
+          float best = -INFINITY;
+          for (int64_t j = 0; j < N; ++j)
+            if (!taken[j] && (arg < 0 || score[j] > best)) { best = score[j]; arg = j; }
+          taken[arg] = 1;
+          row[s] = arg;
+        }
+        qsort(row, (size_t)k, sizeof(int64_t), cmp_i64);
+      }
+    }
+    free(score);
+    free(xx);
+    free(taken);
+  }
+}
+
+int oracle_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
