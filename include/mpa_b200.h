@@ -47,6 +47,12 @@ int mpa_version(void);
  * `gpu_launches` claim is the difference across the timed region). */
 uint64_t mpa_launch_count(void);
 
+/* Optional per-kernel CUDA-event timing (used by bench.py for the roofline of the
+ * dominant kernel).  mpa_profile_report waits for the recorded events, writes
+ * "kernel launches total_ms" lines into buf and clears the records. */
+void mpa_profile_enable(int on);
+size_t mpa_profile_report(char* buf, size_t cap);
+
 /* ---- Chamfer distance -------------------------------------------------- */
 /* Replaces chamfer_cuda.chamfer_forward (utils/chamfer/cuda/chamfer.cpp:8-11,21;
  * ChamferForward, chamfer_kernel.cu:116-168).

@@ -22,6 +22,8 @@ _SIGNATURES = {
     'mpa_last_error': (ctypes.c_char_p, []),
     'mpa_version': (c_int, []),
     'mpa_launch_count': (ctypes.c_uint64, []),
+    'mpa_profile_enable': (None, [c_int]),
+    'mpa_profile_report': (c_size_t, [ctypes.c_char_p, c_size_t]),
     'mpa_chamfer_forward_workspace_bytes': (c_size_t, [c_int] * 4),
     'mpa_chamfer_forward': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int,
                                     c_void_p, c_void_p, c_void_p, c_void_p,

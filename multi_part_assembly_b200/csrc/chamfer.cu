@@ -535,14 +535,20 @@ static int run_grid(CloudDesc c0, CloudDesc c1, int S, float* dist0, IdxT* idx0,
                                   (int)(sizeof(int) * (GRID_MAX_DIM * GRID_MAX_DIM * GRID_MAX_DIM + 1))));
     attr_set[which] = true;
   }
-  grid_build_kernel<IdxT><<<2 * S, threads, smem, stream>>>(c0, c1, S, s0, s1, cs, L.cs_stride,
-                                                            params, far, dist0, idx0, dist1, idx1);
+  {
+    ProfScope ps(c0.fill_invalid ? "chamfer_grid_build_shape" : (c0.quat ? "chamfer_grid_build_part" : "chamfer_grid_build"), stream);
+    grid_build_kernel<IdxT><<<2 * S, threads, smem, stream>>>(c0, c1, S, s0, s1, cs, L.cs_stride,
+                                                              params, far, dist0, idx0, dist1, idx1);
+  }
   MPA_LAUNCH_CHECK();
   const long long warps = (long long)S * ((c0.Nseg + 31) / 32 + (c1.Nseg + 31) / 32);
   const long long blocks = (warps + 7) / 8;
   if (blocks > 0) {
-    grid_nn_kernel<IdxT><<<(unsigned)blocks, 256, 0, stream>>>(
-        s0, s1, cs, L.cs_stride, params, far, S, c0.Nseg, c1.Nseg, dist0, idx0, dist1, idx1);
+    {
+      ProfScope ps(c0.fill_invalid ? "chamfer_grid_nn_shape" : (c0.quat ? "chamfer_grid_nn_part" : "chamfer_grid_nn"), stream);
+      grid_nn_kernel<IdxT><<<(unsigned)blocks, 256, 0, stream>>>(
+          s0, s1, cs, L.cs_stride, params, far, S, c0.Nseg, c1.Nseg, dist0, idx0, dist1, idx1);
+    }
     MPA_LAUNCH_CHECK();
   }
   return MPA_OK;
@@ -573,7 +579,8 @@ int mpa_chamfer_forward(const float* xyz1, const float* xyz2, int B, int N1, int
   MPA_CHECK_ARG(B >= 0 && N1 >= 0 && N2 >= 0, "chamfer_forward: negative size");
   MPA_CHECK_ARG(algo >= MPA_ALGO_AUTO && algo <= MPA_ALGO_GRID, "chamfer_forward: bad algo %d", algo);
   if (B == 0 || (N1 == 0 && N2 == 0)) return MPA_OK;
-  MPA_CHECK_ARG(xyz1 && xyz2 && dist1 && dist2, "chamfer_forward: null pointer");
+  MPA_CHECK_ARG((N1 == 0 || (xyz1 && dist1)) && (N2 == 0 || (xyz2 && dist2)),
+                "chamfer_forward: null pointer");
   if (N1 > 0 && N2 > 0 && use_grid(algo, N1, N2)) {
     CloudDesc c0{xyz1, nullptr, nullptr, nullptr, nullptr, N1, N1, 0, 0};
     CloudDesc c1{xyz2, nullptr, nullptr, nullptr, nullptr, N2, N2, 0, 0};
@@ -583,8 +590,11 @@ int mpa_chamfer_forward(const float* xyz1, const float* xyz2, int B, int N1, int
   const long long blocks = (long long)B * ((N1 + BF_THREADS - 1) / BF_THREADS +
                                            (N2 + BF_THREADS - 1) / BF_THREADS);
   const long long cap = (long long)num_sms() * 8;
-  chamfer_brute_kernel<long long><<<(unsigned)(blocks < cap ? blocks : cap), BF_THREADS, 0, stream>>>(
-      xyz1, xyz2, B, N1, N2, dist1, (long long*)idx1, dist2, (long long*)idx2);
+  {
+    ProfScope ps("chamfer_brute", stream);
+    chamfer_brute_kernel<long long><<<(unsigned)(blocks < cap ? blocks : cap), BF_THREADS, 0, stream>>>(
+        xyz1, xyz2, B, N1, N2, dist1, (long long*)idx1, dist2, (long long*)idx2);
+  }
   MPA_LAUNCH_CHECK();
   return MPA_OK;
 }
@@ -603,9 +613,12 @@ int mpa_chamfer_backward(const float* grad_dist1, const float* grad_dist2, const
   const long long total = (long long)B * (N1 + N2);
   const long long blocks = (total + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
-  chamfer_backward_kernel<long long><<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, stream>>>(
-      grad_dist1, grad_dist2, xyz1, xyz2, (const long long*)idx1, (const long long*)idx2, B, N1, N2,
-      grad_xyz1, grad_xyz2);
+  {
+    ProfScope ps("chamfer_backward", stream);
+    chamfer_backward_kernel<long long><<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, stream>>>(
+        grad_dist1, grad_dist2, xyz1, xyz2, (const long long*)idx1, (const long long*)idx2, B, N1, N2,
+        grad_xyz1, grad_xyz2);
+  }
   MPA_LAUNCH_CHECK();
   return MPA_OK;
 }
@@ -703,8 +716,11 @@ int mpa_pose_chamfer_backward(const float* grad_dist1, const float* grad_dist2, 
   const long long total = (long long)S * Nseg * 2;
   const long long blocks = (total + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
-  chamfer_backward_kernel<int><<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, stream>>>(
-      grad_dist1, grad_dist2, pts1, pts2, idx1, idx2, S, Nseg, Nseg, gp1, gp2);
+  {
+    ProfScope ps("chamfer_backward", stream);
+    chamfer_backward_kernel<int><<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, stream>>>(
+        grad_dist1, grad_dist2, pts1, pts2, idx1, idx2, S, Nseg, Nseg, gp1, gp2);
+  }
   MPA_LAUNCH_CHECK();
   if (grad_quat1 != nullptr || grad_trans1 != nullptr) {
     rc = launch_se3_backward(quat1, pts, gp1, valids, shape ? 1 : 0, B * P, N, nullptr, grad_quat1,

@@ -13,6 +13,18 @@ void set_error(const char* fmt, ...);
 extern std::atomic<uint64_t> g_launches;
 inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
+// RAII CUDA-event pair around a kernel launch; a no-op unless mpa_profile_enable(1)
+class ProfScope {
+ public:
+  ProfScope(const char* name, cudaStream_t stream);
+  ~ProfScope();
+ private:
+  const char* name_;
+  cudaStream_t stream_;
+  cudaEvent_t a_ = nullptr, b_ = nullptr;
+  bool active_ = false;
+};
+
 #define MPA_CHECK_ARG(cond, ...)            \
   do {                                      \
     if (!(cond)) {                          \

@@ -109,8 +109,11 @@ se3_backward_kernel(const float* __restrict__ quat, const float* __restrict__ pt
 int launch_se3_backward(const float* quat, const float* pts, const float* grad_out,
                         const float* valids, int fill_invalid, int n_parts, int N, float* grad_pts,
                         float* grad_quat, float* grad_trans, cudaStream_t stream) {
-  se3_backward_kernel<<<n_parts, 256, 0, stream>>>(quat, pts, grad_out, valids, fill_invalid, N,
-                                                   grad_pts, grad_quat, grad_trans);
+  {
+    ProfScope ps("se3_backward", stream);
+    se3_backward_kernel<<<n_parts, 256, 0, stream>>>(quat, pts, grad_out, valids, fill_invalid, N,
+                                                     grad_pts, grad_quat, grad_trans);
+  }
   MPA_LAUNCH_CHECK();
   return MPA_OK;
 }
@@ -131,6 +134,7 @@ int mpa_se3_transform(const float* quat, const float* trans, const float* pts, i
   const long long work = vec ? (long long)n_parts * (N / 4) : (long long)n_parts * N;
   long long blocks = (work + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
+  ProfScope ps("se3_forward", stream);
   if (vec)
     se3_forward_vec4_kernel<<<(unsigned)blocks, 256, 0, stream>>>(
         quat, trans, (const float4*)pts, n_parts, N, (float4*)out);

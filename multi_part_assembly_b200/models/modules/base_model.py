@@ -1,0 +1,303 @@
+"""`BaseModel`: the LightningModule-style base class of every assembly model,
+same hook names and semantics as the reference
+(models/modules/base_model.py:17-464): `forward`, `training_step`,
+`validation_step`/`test_step` + `*_epoch_end`, `forward_pass`, `_calc_loss`,
+`loss_function` (Min-of-N), `_match_parts` (Hungarian matching of
+geometrically equivalent parts), `configure_optimizers`.
+
+Differences that do not change results: the loss terms run on the fused CUDA
+ops of utils/loss.py, per-step logging keeps tensors instead of calling
+`.item()` on every term (a host sync per term in the reference, :138), and the
+matching cost matrices of all groups of a batch are computed in one batched
+Chamfer call before a single device->host copy.
+"""
+import numpy as np
+import torch
+import torch.optim as optim
+from scipy.optimize import linear_sum_assignment
+
+from ...compat.lightning import LightningModule
+from ...utils import transform_pc, Rotation3D, filter_wd_parameters
+from ...utils import trans_l2_loss, rot_points_cd_loss, shape_cd_loss, \
+    rot_cosine_loss, rot_points_l2_loss, chamfer_distance
+from ...utils import calc_part_acc, calc_connectivity_acc, trans_metrics, \
+    rot_metrics
+from ...utils.lr import CosineAnnealingWarmupRestarts
+
+
+class BaseModel(LightningModule):
+    """Base class for multi-part assembly models."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+        self._setup()
+
+    def _setup(self):
+        self.rot_type = self.cfg.model.rot_type
+        if self.rot_type == 'quat':
+            self.pose_dim = 3 + 4
+            ones = (0, )
+        elif self.rot_type == 'rmat':
+            self.pose_dim = 3 + 6
+            ones = (0, 4)
+        else:
+            raise NotImplementedError(f'rotation {self.rot_type} is not supported')
+        zero_pose = torch.zeros(1, 1, self.pose_dim)
+        for i in ones:
+            zero_pose[..., i] = 1.
+        self.zero_pose = zero_pose
+
+        self.semantic = (self.cfg.data.dataset != 'geometry')
+        self.max_num_part = self.cfg.data.max_num_part
+        self.pc_feat_dim = self.cfg.model.pc_feat_dim
+        self.use_part_label = 'part_label' in self.cfg.data.data_keys
+        self.sample_iter = self.cfg.loss.get('sample_iter', 1)
+
+    # ------------------------------------------------------------------ hooks
+    def forward(self, data_dict):
+        """Predict poses for each part (implemented by the subclasses)."""
+        raise NotImplementedError
+
+    def training_step(self, data_dict, batch_idx, optimizer_idx=-1):
+        return self.forward_pass(data_dict, mode='train', optimizer_idx=optimizer_idx)['loss']
+
+    def validation_step(self, data_dict, batch_idx):
+        return self.forward_pass(data_dict, mode='val', optimizer_idx=-1)
+
+    def test_step(self, data_dict, batch_idx):
+        return self.forward_pass(data_dict, mode='test', optimizer_idx=-1)
+
+    @staticmethod
+    def _weighted_epoch_mean(outputs, prefix, stack_loss=True):
+        int_bs = isinstance(outputs[0]['batch_size'], int)
+        bs_fn = torch.tensor if int_bs else (torch.stack if stack_loss else torch.cat)
+        loss_fn = torch.stack if (int_bs or stack_loss) else torch.cat
+        batch_sizes = bs_fn([o.pop('batch_size') for o in outputs]).type_as(outputs[0]['loss'])
+        return {
+            f'{prefix}/{k}': (loss_fn([o[k] for o in outputs]) * batch_sizes).sum() / batch_sizes.sum()
+            for k in outputs[0].keys()
+        }
+
+    def validation_epoch_end(self, outputs):
+        self.log_dict(self._weighted_epoch_mean(outputs, 'val'), sync_dist=True)
+
+    def test_epoch_end(self, outputs):
+        avg_loss = self._weighted_epoch_mean(outputs, 'test', stack_loss=False)
+        print('; '.join([f'{k}: {v.item():.6f}' for k, v in avg_loss.items()]))
+        self.test_results = avg_loss
+
+    def forward_pass(self, data_dict, mode, optimizer_idx):
+        """Loss computation and logging for one batch.  `data_dict` follows the
+        dataset schema; like the reference (:130-132)
+        the call replaces `part_quat` by the Rotation3D `part_rot` in place."""
+        part_quat = data_dict.pop('part_quat')
+        data_dict['part_rot'] = Rotation3D(part_quat, rot_type='quat').convert(self.rot_type)
+        loss_dict = self.loss_function(data_dict, optimizer_idx=optimizer_idx)
+
+        if mode == 'train' and self.local_rank == 0:
+            log_dict = {f'{mode}/{k}': v.detach() for k, v in loss_dict.items()}
+            profiler = getattr(getattr(self, 'trainer', None), 'profiler', None)
+            if profiler is not None:
+                names = [k for k in profiler.recorded_durations if 'prepare_data' in k]
+                if names:
+                    log_dict[f'{mode}/data_time'] = profiler.recorded_durations[names[0]][-1]
+            self.log_dict(log_dict, logger=True, sync_dist=False, rank_zero_only=True)
+        return loss_dict
+
+    # --------------------------------------------------------------- matching
+    @torch.no_grad()
+    def _match_cost(self, pts, trans1, rot1, trans2, rot2):
+        """p x p matching cost of one group of equivalent parts: Chamfer
+        distance between part i under pose-1 i and part j ... (reference
+        :162-174).  Returns the [p, p] device tensor."""
+        p, N, _ = pts.shape
+        n = 100
+        sample_idx = torch.randperm(N)[:n].to(pts.device).long()  # CPU RNG, as the reference
+        pts = pts[:, sample_idx]
+        pts1 = transform_pc(trans1, rot1, pts, self.rot_type)
+        pts2 = transform_pc(trans2, rot2, pts, self.rot_type)
+        pts1 = pts1.unsqueeze(1).expand(p, p, n, 3).reshape(-1, n, 3)
+        pts2 = pts2.unsqueeze(0).expand(p, p, n, 3).reshape(-1, n, 3)
+        dist1, dist2 = chamfer_distance(pts1, pts2)
+        return (dist1.mean(1) + dist2.mean(1)).view(p, p)
+
+    @torch.no_grad()
+    def _linear_sum_assignment(self, pts, trans1, rot1, trans2, rot2):
+        """Min-cost matching between two groups of poses (reference :150-179)."""
+        dist_mat = self._match_cost(pts, trans1, rot1, trans2, rot2)
+        rind, cind = linear_sum_assignment(dist_mat.cpu().numpy())
+        rind = torch.from_numpy(rind).to(pts.device).long()
+        cind = torch.from_numpy(cind).to(pts.device).long()
+        return rind, cind
+
+    @torch.no_grad()
+    def _match_parts(self, part_pcs, pred_trans, pred_rot, gt_trans, gt_rot, match_ids):
+        """Semantic assembly: permute the GT poses inside every group of
+        geometrically equivalent parts to the min-cost assignment against the
+        predictions (reference :181-238).  `match_ids` [B, P]: 0 = unique or
+        padded, g > 0 = group id."""
+        match_ids = match_ids.long()
+        new_gt_trans = gt_trans.detach().clone()
+        new_gt_rot_tensor = gt_rot.detach().clone().rot
+        gt_rot_tensor = gt_rot.rot
+        pred_rot_tensor = pred_rot.rot
+
+        # one host copy of the ids instead of a sync per (shape, group)
+        ids_host = match_ids.cpu().numpy()
+        groups = []  # (shape index, part indices)
+        for ind in range(part_pcs.shape[0]):
+            for g in range(1, int(ids_host[ind].max()) + 1):
+                members = np.nonzero(ids_host[ind] == g)[0]
+                groups.append((ind, torch.from_numpy(members).to(part_pcs.device)))
+        # cost matrices in group order (keeps the reference's RNG consumption:
+        # one torch.randperm(N) per group), then one batched host copy
+        costs = [self._match_cost(part_pcs[ind, m], pred_trans[ind, m], pred_rot_tensor[ind, m],
+                                  gt_trans[ind, m], new_gt_rot_tensor[ind, m])
+                 for ind, m in groups]
+        if costs:
+            flat = torch.cat([c.reshape(-1) for c in costs]).cpu().numpy()
+            off = 0
+            for (ind, m), c in zip(groups, costs):
+                p = c.shape[0]
+                _, cind = linear_sum_assignment(flat[off:off + p * p].reshape(p, p))
+                off += p * p
+                cind = torch.from_numpy(cind).to(part_pcs.device).long()
+                new_gt_trans[ind, m] = gt_trans[ind, m][cind]
+                new_gt_rot_tensor[ind, m] = gt_rot_tensor[ind, m][cind]
+        return new_gt_trans, self._wrap_rotation(new_gt_rot_tensor)
+
+    # ------------------------------------------------------------------- loss
+    def _calc_loss(self, out_dict, data_dict):
+        """All loss terms ([B] each) for one prediction; evaluation metrics too
+        when not training (reference :240-314)."""
+        pred_trans, pred_rot = out_dict['trans'], out_dict['rot']
+        part_pcs, valids = data_dict['part_pcs'], data_dict['part_valids']
+        gt_trans, gt_rot = data_dict['part_trans'], data_dict['part_rot']
+        if self.semantic:
+            new_trans, new_rot = self._match_parts(part_pcs, pred_trans, pred_rot, gt_trans,
+                                                   gt_rot, data_dict['match_ids'])
+        else:
+            new_trans, new_rot = gt_trans.detach().clone(), gt_rot.detach().clone()
+
+        trans_loss = trans_l2_loss(pred_trans, new_trans, valids)
+        rot_pt_cd_loss = rot_points_cd_loss(part_pcs, pred_rot, new_rot, valids)
+        transform_pt_cd_loss, pred_trans_pts, gt_trans_pts = shape_cd_loss(
+            part_pcs, pred_trans, new_trans, pred_rot, new_rot, valids, ret_pts=True,
+            # semantic: always divide by the padded part count; geometric: only
+            # while training (reference :264-280)
+            training=self.semantic or self.training)
+        loss_dict = {
+            'trans_loss': trans_loss,
+            'rot_pt_cd_loss': rot_pt_cd_loss,
+            'transform_pt_cd_loss': transform_pt_cd_loss,
+        }
+        if self.cfg.loss.use_rot_loss:
+            loss_dict['rot_loss'] = rot_cosine_loss(pred_rot, new_rot, valids)
+        if self.cfg.loss.use_rot_pt_l2_loss:
+            loss_dict['rot_pt_l2_loss'] = rot_points_l2_loss(part_pcs, pred_rot, new_rot, valids)
+        if not self.training:
+            loss_dict.update(self._calc_metrics(data_dict, out_dict, new_trans, new_rot))
+        out_dict = {
+            'pred_trans': pred_trans,
+            'pred_rot': pred_rot,
+            'gt_trans_pts': gt_trans_pts,
+            'pred_trans_pts': pred_trans_pts,
+        }
+        return loss_dict, out_dict
+
+    @torch.no_grad()
+    def _calc_metrics(self, data_dict, out_dict, gt_trans, gt_rot):
+        """Evaluation metrics (reference :316-339)."""
+        metric_dict = {}
+        part_pcs, valids = data_dict['part_pcs'], data_dict['part_valids']
+        pred_trans, pred_rot = out_dict['trans'], out_dict['rot']
+        metric_dict['part_acc'] = calc_part_acc(part_pcs, pred_trans, gt_trans, pred_rot,
+                                                gt_rot, valids)
+        if self.semantic and 'contact_points' in data_dict.keys():
+            metric_dict['connectivity_acc'] = calc_connectivity_acc(
+                pred_trans, pred_rot, data_dict['contact_points'])
+        if not self.semantic:
+            for metric in ['mse', 'rmse', 'mae']:
+                metric_dict[f'trans_{metric}'] = trans_metrics(pred_trans, gt_trans, valids,
+                                                               metric=metric)
+                metric_dict[f'rot_{metric}'] = rot_metrics(pred_rot, gt_rot, valids, metric=metric)
+        return metric_dict
+
+    def _loss_function(self, data_dict, out_dict={}, optimizer_idx=-1):
+        raise NotImplementedError
+
+    def loss_function(self, data_dict, optimizer_idx):
+        """Min-of-N loss: sample `sample_iter` predictions, keep per shape the
+        one with the lowest weighted total (reference :348-387)."""
+        samples = None
+        out_dict = {}
+        for _ in range(self.sample_iter):
+            sample_loss, out_dict = self._loss_function(data_dict, out_dict,
+                                                        optimizer_idx=optimizer_idx)
+            if samples is None:
+                samples = {k: [] for k in sample_loss.keys()}
+            for k, v in sample_loss.items():
+                samples[k].append(v)
+        loss_dict = {k: torch.stack(v, dim=0) for k, v in samples.items()}
+        total_loss = 0.
+        for k, v in loss_dict.items():
+            if k.endswith('_loss'):  # metrics logged in eval are not part of the loss
+                total_loss = total_loss + v * self.cfg.loss[f'{k}_w']
+        loss_dict['loss'] = total_loss
+        if self.sample_iter == 1:
+            loss_dict = {k: v[0].mean() for k, v in loss_dict.items()}
+        else:
+            min_idx = total_loss.argmin(0)  # [B]
+            batch_idx = torch.arange(min_idx.shape[0]).type_as(min_idx)
+            loss_dict = {k: v[min_idx, batch_idx].mean() for k, v in loss_dict.items()}
+        if not self.training:
+            loss_dict['batch_size'] = total_loss.shape[1]
+        return loss_dict
+
+    # -------------------------------------------------------------- optimiser
+    def configure_optimizers(self):
+        """Adam(W) + optional cosine schedule with warm-up (reference :389-425)."""
+        lr = self.cfg.optimizer.lr
+        wd = self.cfg.optimizer.weight_decay
+        if wd > 0.:
+            groups = filter_wd_parameters(self)
+            optimizer = optim.AdamW([
+                {'params': groups['no_decay'], 'weight_decay': 0.},
+                {'params': groups['decay'], 'weight_decay': wd},
+            ], lr=lr)
+        else:
+            optimizer = optim.Adam(self.parameters(), lr=lr, weight_decay=0.)
+        if self.cfg.optimizer.lr_scheduler:
+            assert self.cfg.optimizer.lr_scheduler in ['cosine']
+            total_epochs = self.cfg.exp.num_epochs
+            warmup_epochs = int(total_epochs * self.cfg.optimizer.warmup_ratio)
+            scheduler = CosineAnnealingWarmupRestarts(
+                optimizer, total_epochs, max_lr=lr,
+                min_lr=lr / self.cfg.optimizer.lr_decay_factor, warmup_steps=warmup_epochs)
+            return [optimizer], [{'scheduler': scheduler, 'interval': 'epoch'}]
+        return optimizer
+
+    @torch.no_grad()
+    def sample_assembly(self, data_dict):
+        """Predicted and GT assembled clouds per shape (reference :427-460),
+        as lists of [p*N, 3] arrays (colouring is left to the caller)."""
+        if 'part_rot' not in data_dict:
+            part_quat = data_dict.pop('part_quat')
+            data_dict['part_rot'] = Rotation3D(part_quat, rot_type='quat').convert(self.rot_type)
+        part_pcs, valids = data_dict['part_pcs'], data_dict['part_valids']
+        gt_pcs = transform_pc(data_dict['part_trans'], data_dict['part_rot'], part_pcs)
+        B = part_pcs.shape[0]
+        pred_pcs_lst, gt_pcs_lst = [[] for _ in range(B)], []
+        for i in range(self.sample_iter):
+            out = self.forward(data_dict)
+            pred_pcs = transform_pc(out['trans'], out['rot'], part_pcs)
+            for j in range(B):
+                valid = valids[j].bool()
+                pred_pcs_lst[j].append(pred_pcs[j][valid].cpu().numpy().reshape(-1, 3))
+                if i == 0:
+                    gt_pcs_lst.append(gt_pcs[j][valid].cpu().numpy().reshape(-1, 3))
+        return gt_pcs_lst, pred_pcs_lst
+
+    def _wrap_rotation(self, rot_tensor):
+        return Rotation3D(rot_tensor, rot_type=self.rot_type)

@@ -1,0 +1,138 @@
+"""Product modules, losses and whole models on the GPU against the golden
+vectors generated from the reference (tests/golden, oracle/make_golden.py).
+Tolerance: north_star asks 1e-5 rel for Chamfer/pose losses given the same
+poses; network outputs accumulate in a different order than the CPU
+reference, so module outputs use 1e-4 rel."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.params import fill_params_, zero_dropout
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+def gold(name):
+    return dict(np.load(os.path.join(GOLD, name + '.npz')))
+
+
+def T(a, dev):
+    return torch.from_numpy(np.asarray(a)).to(dev)
+
+
+def test_pointnet_module(cuda):
+    from multi_part_assembly_b200.models import build_encoder
+    g = gold('pointnet')
+    enc = fill_params_(build_encoder('pointnet', 256), 3).to(cuda).train()
+    x = T(g['x'], cuda)
+    out = enc(x)
+    np.testing.assert_allclose(out.cpu().detach().numpy(), g['out_train'], rtol=1e-4, atol=1e-5)
+    # train-mode side effect: running statistics (momentum 0.1, unbiased var)
+    np.testing.assert_allclose(enc.bn5.running_mean.cpu().numpy(), g['bn5_running_mean'], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(enc.bn5.running_var.cpu().numpy(), g['bn5_running_var'], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(enc.bn1.running_mean.cpu().numpy(), g['bn1_running_mean'], rtol=1e-4, atol=1e-6)
+    enc.eval()
+    np.testing.assert_allclose(enc(x).cpu().detach().numpy(), g['out_eval_after_update'], rtol=1e-4, atol=1e-5)
+    pp = fill_params_(build_encoder('pointnet', 64, global_feat=False), 4).to(cuda).eval()
+    np.testing.assert_allclose(pp(x).cpu().detach().numpy(), g['out_perpoint_eval'], rtol=1e-4, atol=1e-5)
+
+
+def test_dgcnn_module(cuda):
+    from multi_part_assembly_b200.models import build_encoder
+    g = gold('dgcnn')
+    enc = fill_params_(build_encoder('dgcnn', 128), 5).to(cuda).train()
+    x = T(g['x'], cuda)
+    np.testing.assert_allclose(enc(x).cpu().detach().numpy(), g['out_train'], rtol=1e-4, atol=1e-5)
+    enc.eval()
+    np.testing.assert_allclose(enc(x).cpu().detach().numpy(), g['out_eval_after_update'], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize('name,dims,seed', [('transformer', (64, 4, 128, 2), 6),
+                                            ('transformer_full', (256, 8, 1024, 4), 7)])
+def test_transformer_module(cuda, name, dims, seed):
+    from multi_part_assembly_b200.models.pn_transformer import TransformerEncoder
+    g = gold(name)
+    tr = fill_params_(TransformerEncoder(*dims), seed).to(cuda).eval()
+    out = tr(T(g['tokens'], cuda), T(g['valid'], cuda)).cpu().detach().numpy()
+    v = g['valid']
+    np.testing.assert_allclose(out[v], g['out'][v], rtol=1e-4, atol=1e-5)
+    assert np.isfinite(out).all()  # padded slots must stay finite
+
+
+def test_losses(cuda):
+    from multi_part_assembly_b200.datasets import make_batch
+    from multi_part_assembly_b200 import utils as U
+    g = gold('losses')
+    b = make_batch(3, P=6, N=80, num_valid=[6, 3, 1], seed=9, device=cuda)
+    pts, valids, gt = b['part_pcs'], b['part_valids'], b['part_trans']
+    gq = U.Rotation3D(b['part_quat'])
+    pq, pt = U.Rotation3D(T(g['pred_quat'], cuda)), T(g['pred_trans'], cuda)
+    got = {
+        'trans_l2': U.trans_l2_loss(pt, gt, valids), 'rot_l2': U.rot_l2_loss(pq, gq, valids),
+        'rot_cosine': U.rot_cosine_loss(pq, gq, valids),
+        'rot_points_l2': U.rot_points_l2_loss(pts, pq, gq, valids),
+        'rot_points_cd': U.rot_points_cd_loss(pts, pq, gq, valids),
+        'shape_cd_train': U.shape_cd_loss(pts, pt, gt, pq, gq, valids, training=True),
+        'shape_cd_eval': U.shape_cd_loss(pts, pt, gt, pq, gq, valids, training=False),
+        'part_acc': U.calc_part_acc(pts, pt, gt, pq, gq, valids),
+        'part_acc_close': U.calc_part_acc(pts, gt + 0.01, gt, gq, gq, valids),
+        'trans_rmse': U.trans_metrics(pt, gt, valids, 'rmse'),
+        'rot_mae': U.rot_metrics(pq, gq, valids, 'mae'),
+        'rot_rmse': U.rot_metrics(pq, gq, valids, 'rmse'),
+    }
+    for k, v in got.items():
+        tol = 1e-4 if k.startswith('rot_m') or k.startswith('rot_r') else 1e-5
+        np.testing.assert_allclose(v.cpu().numpy(), g[k], rtol=tol, atol=1e-7, err_msg=k)
+
+
+CASES = [
+    ('model_pn_transformer', 'pn_transformer', 'everyday', None, 11, False, 64, (5, 3)),
+    ('model_pn_transformer_semantic', 'pn_transformer', 'partnet_chair', None, 12, True, 128, (7, 4)),
+    ('model_global', 'global', 'everyday', None, 13, False, 64, (5, 3)),
+    ('model_dgl', 'dgl', 'everyday', None, 14, False, 64, (5, 3)),
+    ('model_dgl_dgcnn', 'dgl', 'everyday', 'dgcnn', 15, False, 64, (5, 3)),
+    ('model_pn_transformer_refine', 'pn_transformer_refine', 'everyday', None, 16, False, 64, (5, 3)),
+]
+
+
+@pytest.mark.parametrize('tag,name,dataset,encoder,seed,semantic,N,nv', CASES)
+def test_model_steps_match_reference(cuda, tag, name, dataset, encoder, seed, semantic, N, nv):
+    """training_step / validation_step loss dicts and the gradient norm of the
+    reference model (same weights, same batch, same RNG seed, dropout 0)."""
+    from multi_part_assembly_b200.configs import get_cfg
+    from multi_part_assembly_b200.datasets import make_batch
+    from multi_part_assembly_b200.models import build_model
+    from multi_part_assembly_b200.compat.lightning import Trainer
+    g = gold(tag)
+    cfg = get_cfg(name, dataset)
+    if encoder:
+        cfg.model.encoder = encoder
+    model = zero_dropout(fill_params_(build_model(cfg), seed)).to(cuda)
+    model.trainer = Trainer()
+    for mode in ('train', 'val'):
+        batch = make_batch(2, P=20, N=N, num_valid=list(nv), seed=seed, semantic=semantic)
+        if semantic:
+            cp = torch.zeros(2, 20, 20, 4)
+            cp[:, 0, 1, 0] = cp[:, 1, 0, 0] = 1
+            cp[:, 0, 1, 1:] = 0.1
+            cp[:, 1, 0, 1:] = -0.1
+            batch['contact_points'] = cp
+        batch = {k: v.to(cuda) for k, v in batch.items()}
+        model.train(mode == 'train')
+        torch.manual_seed(100 + seed)
+        with torch.set_grad_enabled(mode == 'train'):
+            ld = model.forward_pass(batch, mode=mode, optimizer_idx=-1)
+        for k, v in ld.items():
+            want = g[f'{mode}/{k}']
+            got = float(v)
+            assert np.isfinite(got), k
+            np.testing.assert_allclose(got, want, rtol=2e-4, atol=1e-6, err_msg=f'{mode}/{k}')
+        if mode == 'train':
+            ld['loss'].backward()
+            gn = torch.sqrt(sum((p.grad.double()**2).sum() for p in model.parameters()
+                                if p.grad is not None))
+            np.testing.assert_allclose(float(gn), g['train/grad_norm'], rtol=2e-3)
+            model.zero_grad()
