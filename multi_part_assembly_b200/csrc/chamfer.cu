@@ -15,6 +15,7 @@
 //           the best distance is provably smaller than the distance to any
 //           unexplored cell.  ~10^2 candidate pairs per query instead of N.
 #include <math.h>
+#include <stdlib.h>
 
 #include "mpa_common.cuh"
 
@@ -126,9 +127,11 @@ struct CloudDesc {
   int ppp;              // points per pose (= N of a part)
   int fill_invalid;     // shape mode: padded parts are the point (1e3,1e3,1e3) (loss.py:175)
   int dmax;             // max cells per axis
+  float occ;            // target points per cell (in the effective volume)
+  int use_eff;          // size cells from the effective (sigma) volume, not the bbox
 };
 
-constexpr int GRID_MAX_DIM = 32;
+constexpr int GRID_MAX_DIM = 38;  // 38^3+1 ints = 214 KB of shared memory in the build kernel
 constexpr int MAX_FAR = 64;  // >= max parts per shape
 
 __device__ __forceinline__ int cell_coord(float x, float o, float inv_h, int dim) {
@@ -177,6 +180,7 @@ __global__ void grid_build_kernel(CloudDesc c0, CloudDesc c1, int S, float4* __r
                                   float* dist1, IdxT* idx1) {
   extern __shared__ int cnt[];
   __shared__ float red[6][32];
+  __shared__ double redm[6][32];
   __shared__ int s_wsum[32];
   __shared__ GridParams gp;
   __shared__ int s_count, s_nfar;
@@ -198,6 +202,7 @@ __global__ void grid_build_kernel(CloudDesc c0, CloudDesc c1, int S, float4* __r
   // ---- pass 1: bbox of the valid points, transformed output, zero-fill ----
   const float inf = __int_as_float(0x7f800000);
   float mnx = inf, mny = inf, mnz = inf, mxx = -inf, mxy = -inf, mxz = -inf;
+  double m1x = 0, m1y = 0, m1z = 0, m2x = 0, m2y = 0, m2z = 0;  // coordinate moments
   int nvalid = 0;
   for (int i = tid; i < n; i += blockDim.x) {
     bool valid;
@@ -209,6 +214,8 @@ __global__ void grid_build_kernel(CloudDesc c0, CloudDesc c1, int S, float4* __r
     if (valid) {
       mnx = fminf(mnx, v.x); mny = fminf(mny, v.y); mnz = fminf(mnz, v.z);
       mxx = fmaxf(mxx, v.x); mxy = fmaxf(mxy, v.y); mxz = fmaxf(mxz, v.z);
+      m1x += v.x; m1y += v.y; m1z += v.z;
+      m2x += (double)v.x * v.x; m2y += (double)v.y * v.y; m2z += (double)v.z * v.z;
       ++nvalid;
     } else if (has_valid) {
       const long long o = (long long)seg * n + i;
@@ -219,9 +226,17 @@ __global__ void grid_build_kernel(CloudDesc c0, CloudDesc c1, int S, float4* __r
   mnx = warp_min(mnx); mny = warp_min(mny); mnz = warp_min(mnz);
   mxx = warp_max(mxx); mxy = warp_max(mxy); mxz = warp_max(mxz);
   nvalid = __reduce_add_sync(0xffffffffu, nvalid);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    m1x += __shfl_xor_sync(0xffffffffu, m1x, o); m1y += __shfl_xor_sync(0xffffffffu, m1y, o);
+    m1z += __shfl_xor_sync(0xffffffffu, m1z, o); m2x += __shfl_xor_sync(0xffffffffu, m2x, o);
+    m2y += __shfl_xor_sync(0xffffffffu, m2y, o); m2z += __shfl_xor_sync(0xffffffffu, m2z, o);
+  }
   if (lane == 0) {
     red[0][wid] = mnx; red[1][wid] = mny; red[2][wid] = mnz;
     red[3][wid] = mxx; red[4][wid] = mxy; red[5][wid] = mxz;
+    redm[0][wid] = m1x; redm[1][wid] = m1y; redm[2][wid] = m1z;
+    redm[3][wid] = m2x; redm[4][wid] = m2y; redm[5][wid] = m2z;
     atomicAdd(&s_count, nvalid);
   }
   // padded parts of a shape cloud: one far candidate each, index = first point
@@ -257,8 +272,20 @@ __global__ void grid_build_kernel(CloudDesc c0, CloudDesc c1, int S, float4* __r
         const float emax = fmaxf(ex, fmaxf(ey, ez));
         const bool finite = (emax < inf) && (emax == emax);
         const float tiny = fmaxf(emax * 1e-3f, 1e-30f);
-        // ~2 points per cell on average, at most dmax cells per axis
-        float h = cbrtf(fmaxf(ex, tiny) * fmaxf(ey, tiny) * fmaxf(ez, tiny) * 2.0f / (float)p.count);
+        // Cell size from the EFFECTIVE volume: per axis min(bbox extent, sqrt(12)*sigma)
+        // (equal for a uniform box, much smaller for a dense core with a sparse halo),
+        // aiming at ~1.5 points per cell where the points actually are.
+        float eff[3] = {ex, ey, ez};
+        for (int ax = 0; ax < 3; ++ax) {
+          double s1 = 0, s2 = 0;
+          for (int w = 0; w < nwarps; ++w) { s1 += redm[ax][w]; s2 += redm[3 + ax][w]; }
+          const double mean = s1 / p.count;
+          const double var = fmax(s2 / p.count - mean * mean, 0.0);
+          const float se = (float)(3.4641016151377544 * sqrt(var));
+          if (c.use_eff && se == se && se < eff[ax]) eff[ax] = se;
+        }
+        float h = cbrtf(fmaxf(eff[0], tiny) * fmaxf(eff[1], tiny) * fmaxf(eff[2], tiny) * c.occ /
+                        (float)p.count);
         h = fmaxf(h, emax / (float)c.dmax * 1.0001f);
         if (!(h > 0.0f) || !(h < inf) || !finite) h = 1.0f;  // all points equal / non-finite cloud
         p.h = h;
@@ -342,18 +369,35 @@ __global__ void grid_build_kernel(CloudDesc c0, CloudDesc c1, int S, float4* __r
   }
 }
 
-__device__ __forceinline__ void scan_range(const float4* __restrict__ T, int s, int e, float qx,
-                                           float qy, float qz, float& best, int& bidx) {
-  for (int p = s; p < e; ++p) {
-    const float4 t = __ldg(&T[p]);
-    const float d = sqdist_ref(qx, qy, qz, t.x, t.y, t.z);
+__device__ __forceinline__ void consider(const float4 t, float qx, float qy, float qz, float& best,
+                                         int& bidx) {
+  const float d = sqdist_ref(qx, qy, qz, t.x, t.y, t.z);
+  if (d <= best) {  // rare after the first few candidates
     const int ti = __float_as_int(t.w);
-    if (d < best || (d == best && ti < bidx)) { best = d; bidx = ti; }
+    if (d < best || ti < bidx) { best = d; bidx = ti; }
   }
 }
 
+__device__ __forceinline__ void scan_range(const float4* __restrict__ T, int s, int e, float qx,
+                                           float qy, float qz, float& best, int& bidx) {
+  int p = s;
+  for (; p + 1 < e; p += 2) {  // two independent loads in flight
+    const float4 t0 = __ldg(&T[p]);
+    const float4 t1 = __ldg(&T[p + 1]);
+    consider(t0, qx, qy, qz, best, bidx);
+    consider(t1, qx, qy, qz, best, bidx);
+  }
+  if (p < e) consider(__ldg(&T[p]), qx, qy, qz, best, bidx);
+}
+
 // K2: one lane per query (queries taken in their own cloud's cell order so a
-// warp touches neighbouring target cells).
+// warp touches neighbouring target cells).  The search walks the rows (fixed
+// y,z cell, contiguous in memory along x) of the (2R+1)^2 window around the
+// query cell, nearest rows first; a row is skipped when its slab is already
+// farther than the best distance, and its x-range is clipped to the cells the
+// sphere of radius sqrt(best) can reach.  After window R the block
+// [c-R, c+R]^3 is proven complete when `best` is smaller than the distance to
+// the block's faces; otherwise R grows (shell only).
 template <typename IdxT>
 __global__ void __launch_bounds__(256)
 grid_nn_kernel(const float4* __restrict__ sorted0, const float4* __restrict__ sorted1,
@@ -380,6 +424,7 @@ grid_nn_kernel(const float4* __restrict__ sorted0, const float4* __restrict__ so
   const float4 q = (dir1 ? sorted1 : sorted0)[(long long)seg * NQ + i];
   const float4* __restrict__ T = (dir1 ? sorted0 : sorted1) + (long long)seg * NT;
   const int* __restrict__ cs = cell_start + (long long)(tc * S + seg) * cs_stride;
+  const float inf = __int_as_float(0x7f800000);
 
   float best = 1e32f;
   int bidx = -1;
@@ -391,25 +436,47 @@ grid_nn_kernel(const float4* __restrict__ sorted0, const float4* __restrict__ so
     const float slack = 1e-5f * (fabsf(q.x) + fabsf(q.y) + fabsf(q.z) + fabsf(g.ox) +
                                  fabsf(g.oy) + fabsf(g.oz) + (float)(g.dx + g.dy + g.dz) * g.h);
     for (int r = 1;; ++r) {
-      const int z0 = max(cz - r, 0), z1 = min(cz + r, g.dz - 1);
-      const int y0 = max(cy - r, 0), y1 = min(cy + r, g.dy - 1);
-      const int x0 = max(cx - r, 0), x1 = min(cx + r, g.dx - 1);
-      for (int zc = z0; zc <= z1; ++zc) {
-        for (int yc = y0; yc <= y1; ++yc) {
+      const int xlo = max(cx - r, 0), xhi = min(cx + r, g.dx - 1);
+      // offsets ordered 0, -1, +1, -2, +2, ... so that the nearest rows come first
+      for (int kz = 0; kz <= 2 * r; ++kz) {
+        const int dz = (kz & 1) ? -((kz + 1) >> 1) : (kz >> 1);
+        const int zc = cz + dz;
+        if (zc < 0 || zc >= g.dz) continue;
+        // distance from the query to the slab of cells zc (0 inside it)
+        float lz = dz == 0 ? 0.f : (dz < 0 ? q.z - (g.oz + (float)(zc + 1) * g.h)
+                                            : (g.oz + (float)zc * g.h) - q.z);
+        lz = fmaxf(lz - slack, 0.f);
+        if (lz * lz > best) continue;
+        for (int ky = 0; ky <= 2 * r; ++ky) {
+          const int dy = (ky & 1) ? -((ky + 1) >> 1) : (ky >> 1);
+          const int yc = cy + dy;
+          if (yc < 0 || yc >= g.dy) continue;
+          const bool shell = (r == 1) || dz == r || dz == -r || dy == r || dy == -r;
+          float ly = dy == 0 ? 0.f : (dy < 0 ? q.y - (g.oy + (float)(yc + 1) * g.h)
+                                              : (g.oy + (float)yc * g.h) - q.y);
+          ly = fmaxf(ly - slack, 0.f);
+          const float rem = best - (ly * ly + lz * lz);  // squared x-reach left
+          if (rem < 0.f) continue;  // strictly farther than best: cannot win or tie
+          int xa = xlo, xb = xhi;
+          if (best < 1e30f) {
+            const float rad = sqrtf(rem) * 1.00001f + slack;
+            xa = max(xa, cell_coord(q.x - rad, g.ox, g.inv_h, g.dx));
+            xb = min(xb, cell_coord(q.x + rad, g.ox, g.inv_h, g.dx));
+          }
           const int row = (zc * g.dy + yc) * g.dx;
-          const bool full = (r == 1) || zc == cz - r || zc == cz + r || yc == cy - r || yc == cy + r;
-          if (full) {
-            scan_range(T, cs[row + x0], cs[row + x1 + 1], q.x, q.y, q.z, best, bidx);
-          } else {
-            if (cx - r >= 0) scan_range(T, cs[row + cx - r], cs[row + cx - r + 1], q.x, q.y, q.z, best, bidx);
-            if (cx + r < g.dx) scan_range(T, cs[row + cx + r], cs[row + cx + r + 1], q.x, q.y, q.z, best, bidx);
+          if (shell) {
+            if (xa <= xb) scan_range(T, cs[row + xa], cs[row + xb + 1], q.x, q.y, q.z, best, bidx);
+          } else {  // interior row of a grown window: only the two new end cells
+            const int xl = cx - r, xr = cx + r;
+            if (xl >= xa && xl <= xb) scan_range(T, cs[row + xl], cs[row + xl + 1], q.x, q.y, q.z, best, bidx);
+            if (xr >= xa && xr <= xb) scan_range(T, cs[row + xr], cs[row + xr + 1], q.x, q.y, q.z, best, bidx);
           }
         }
       }
       const bool covers = (cx - r <= 0) && (cx + r >= g.dx - 1) && (cy - r <= 0) &&
                           (cy + r >= g.dy - 1) && (cz - r <= 0) && (cz + r >= g.dz - 1);
       if (covers) break;
-      float bound = __int_as_float(0x7f800000);
+      float bound = inf;
       if (cx - r > 0) bound = fminf(bound, q.x - (g.ox + (float)(cx - r) * g.h));
       if (cx + r < g.dx - 1) bound = fminf(bound, (g.ox + (float)(cx + r + 1) * g.h) - q.x);
       if (cy - r > 0) bound = fminf(bound, q.y - (g.oy + (float)(cy - r) * g.h));
@@ -423,12 +490,7 @@ grid_nn_kernel(const float4* __restrict__ sorted0, const float4* __restrict__ so
     }
   }
   const float4* __restrict__ F = far + (long long)(tc * S + seg) * MAX_FAR;
-  for (int f = 0; f < g.nfar; ++f) {
-    const float4 t = F[f];
-    const float d = sqdist_ref(q.x, q.y, q.z, t.x, t.y, t.z);
-    const int ti = __float_as_int(t.w);
-    if (d < best || (d == best && ti < bidx)) { best = d; bidx = ti; }
-  }
+  for (int f = 0; f < g.nfar; ++f) consider(F[f], q.x, q.y, q.z, best, bidx);
   const long long o = (long long)seg * NQ + __float_as_int(q.w);
   (dir1 ? dist1 : dist0)[o] = best;
   IdxT* io = dir1 ? idx1 : idx0;
@@ -483,7 +545,9 @@ static int num_sms() {
 }
 
 static int pick_dmax(int n) {
-  int d = (int)ceil(cbrt((double)n / 2.0));
+  // cells per axis the bbox of a uniform cloud needs at ~1 point per cell
+  // (the device code aims at c.occ points per cell), capped by shared memory
+  int d = (int)ceil(cbrt((double)n));
   if (d < 1) d = 1;
   if (d > GRID_MAX_DIM) d = GRID_MAX_DIM;
   return d;
@@ -523,6 +587,18 @@ static int run_grid(CloudDesc c0, CloudDesc c1, int S, float* dist0, IdxT* idx0,
   float4* s1 = (float4*)(base + L.off_sorted1);
   c0.dmax = pick_dmax(c0.Nseg);
   c1.dmax = pick_dmax(c1.Nseg);
+  {
+    static float occ = -1.f;
+    static int use_eff = 1;
+    if (occ < 0.f) {  // tuning knobs (defaults chosen from the sweep in profiles/)
+      const char* e = getenv("MPA_GRID_OCC");
+      occ = e ? (float)atof(e) : 4.0f;
+      const char* u = getenv("MPA_GRID_EFF");
+      use_eff = u ? atoi(u) : 0;
+    }
+    c0.occ = c1.occ = occ;
+    c0.use_eff = c1.use_eff = use_eff;
+  }
 
   const int nmax = c0.Nseg > c1.Nseg ? c0.Nseg : c1.Nseg;
   const int threads = nmax >= 8192 ? 1024 : (nmax >= 2048 ? 512 : 256);
@@ -582,8 +658,8 @@ int mpa_chamfer_forward(const float* xyz1, const float* xyz2, int B, int N1, int
   MPA_CHECK_ARG((N1 == 0 || (xyz1 && dist1)) && (N2 == 0 || (xyz2 && dist2)),
                 "chamfer_forward: null pointer");
   if (N1 > 0 && N2 > 0 && use_grid(algo, N1, N2)) {
-    CloudDesc c0{xyz1, nullptr, nullptr, nullptr, nullptr, N1, N1, 0, 0};
-    CloudDesc c1{xyz2, nullptr, nullptr, nullptr, nullptr, N2, N2, 0, 0};
+    CloudDesc c0{xyz1, nullptr, nullptr, nullptr, nullptr, N1, N1, 0, 0, 0.f, 0};
+    CloudDesc c1{xyz2, nullptr, nullptr, nullptr, nullptr, N2, N2, 0, 0, 0.f, 0};
     return run_grid<long long>(c0, c1, B, dist1, (long long*)idx1, dist2, (long long*)idx2, ws,
                                ws_bytes, stream);
   }
@@ -681,8 +757,8 @@ int mpa_pose_chamfer(const float* pts, const float* quat1, const float* trans1, 
   const bool shape = mode == MPA_CD_SHAPE;
   const int S = shape ? B : B * P;
   const int Nseg = shape ? P * N : N;
-  CloudDesc c0{pts, quat1, trans1, valids, pts1, Nseg, N, shape ? 1 : 0, 0};
-  CloudDesc c1{pts, quat2, trans2, valids, pts2, Nseg, N, shape ? 1 : 0, 0};
+  CloudDesc c0{pts, quat1, trans1, valids, pts1, Nseg, N, shape ? 1 : 0, 0, 0.f, 0};
+  CloudDesc c1{pts, quat2, trans2, valids, pts2, Nseg, N, shape ? 1 : 0, 0, 0.f, 0};
   return run_grid<int>(c0, c1, S, dist1, idx1, dist2, idx2, ws, ws_bytes, stream);
 }
 
