@@ -131,6 +131,24 @@ int mpa_pose_chamfer_backward(const float* grad_dist1, const float* grad_dist2, 
                               float* grad_trans1, float* grad_quat2, float* grad_trans2, void* ws,
                               size_t ws_bytes, void* stream);
 
+/* ---- PointNet part encoder --------------------------------------------- */
+/* Replaces PointNet.forward with global_feat=True (models/modules/encoder/
+ * pointnet.py:29-41) fused with the valid-part selection of _extract_part_feats
+ * (models/pn_transformer/network.py:59-68): pts [n_parts,N,3]; valids [n_parts]
+ * or NULL (padded parts are skipped, excluded from the BatchNorm statistics and
+ * get zero features); conv_w[5] = conv{1..5}.weight ([Cout,Cin] fp32, no bias);
+ * bn_* [5] = bn{1..5}.{weight,bias,running_mean,running_var}; feats [n_parts,F],
+ * F in {128,256}.  training != 0: batch statistics (biased variance) and the
+ * running statistics are updated in place with `momentum`; 0: running statistics.
+ * GEMMs run on tcgen05 tensor cores with bf16 operands and fp32 accumulation
+ * (the reference's --fp16 autocast analogue); BatchNorm math is fp32. */
+size_t mpa_pointnet_workspace_bytes(int n_parts);
+int mpa_pointnet_forward(const float* pts, const float* valids, int n_parts, int N, int F,
+                         const float* const* conv_w, const float* const* bn_gamma,
+                         const float* const* bn_beta, float* const* bn_running_mean,
+                         float* const* bn_running_var, int training, float eps, float momentum,
+                         float* feats, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

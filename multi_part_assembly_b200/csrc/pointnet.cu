@@ -1,0 +1,436 @@
+// Fused PointNet part encoder on the 5th-generation tensor cores (tcgen05).
+//
+// Replaces PointNet.forward (models/modules/encoder/pointnet.py:29-41): five
+// bias-free 1x1 convolutions 3->64->64->64->128->F with BatchNorm1d after each,
+// ReLU after the first four, max over the N points of a part.  The reference
+// runs ~15 cuDNN/elementwise kernels that write and re-read [n, C, N] fp32
+// activations (~9 GB of HBM traffic at n=640, N=1000); here the activations of
+// a 128-point tile never leave the SM:
+//
+//   orientation   D[channel, point] = W[channel, k] * X[point, k]^T, so a TMEM
+//                 lane is a channel and a TMEM column is a point: BatchNorm
+//                 scale/shift are per-thread constants, the batch statistics
+//                 and the max-pool are per-thread reductions over registers.
+//   operands      bf16, K-major, 128-byte swizzle; weights staged once per CTA
+//                 (a pre-swizzled 128 KB image), activations written straight
+//                 from the previous layer's epilogue into the B-operand tile.
+//   accumulators  fp32 in TMEM, read back with tcgen05.ld (32x32b.x32).
+//   training BN   needs the statistics of layer l before layer l+1 can run, so
+//                 the forward is PHASE = 1..5 launches; launch l recomputes
+//                 layers 1..l-1 with their final scale/shift (cheap: input is
+//                 12 B/point) and reduces sum / sum-of-squares of layer l in
+//                 registers.  Launch 5 also keeps per-part max and min, from
+//                 which max_n(BN5(y)) follows for either sign of gamma.
+//   eval BN       one launch (PHASE 5 with running statistics).
+// Two independent 128-thread pipelines per CTA share the weight image and
+// overlap one pipeline's MMA with the other's epilogue.
+#include "mpa_common.cuh"
+#include "tc05.cuh"
+
+namespace mpa {
+
+constexpr int PN_TILE = 128;                  // points per tile = UMMA N
+constexpr int PN_GROUPS = 2;                  // pipelines per CTA
+constexpr int PN_THREADS = 128 * PN_GROUPS;
+constexpr int PN_WTILE = 128 * 128;           // bytes of one [128 rows][64 k] bf16 tile
+// weight image: layer1..4 one tile each (rows = out channels padded to 128),
+// layer 5: [mblock 0..1][kblock 0..1] tiles
+__host__ __device__ constexpr int pn_w_off(int layer0) { return layer0 * PN_WTILE; }
+constexpr int PN_W_BYTES = 8 * PN_WTILE;      // 128 KB
+constexpr int PN_ACT_BYTES = 2 * PN_WTILE;    // per pipeline: two K-blocks of [128 points][64 ch]
+constexpr int PN_SMEM = PN_W_BYTES + PN_GROUPS * PN_ACT_BYTES + 1024;  // + alignment slack
+constexpr int PN_MAXC = 256;
+
+struct PointNetArgs {
+  const float* pts;         // [n_parts, N, 3]
+  const float* valids;      // [n_parts] or nullptr
+  const uint4* wimage;      // pre-swizzled bf16 weights (PN_W_BYTES)
+  const float* scale;       // [5, 256] BN scale of the finished layers
+  const float* shift;       // [5, 256]
+  float* partial;           // [workers, 256, 2] sum / sumsq of layer PHASE
+  unsigned* pmax;           // [n_parts, 256] ordered-uint max of layer-5 pre-activations
+  unsigned* pmin;           // [n_parts, 256]
+  int n_parts, N, F;        // F = channels of layer 5 (128 or 256)
+};
+
+__device__ __forceinline__ int pn_cout(int layer, int F) {  // layer 1..5
+  return layer <= 3 ? 64 : (layer == 4 ? 128 : F);
+}
+
+template <int PHASE>
+__global__ void __launch_bounds__(PN_THREADS, 1) pointnet_phase_kernel(PointNetArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t mbar[PN_GROUPS];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x;
+  const int g = tid >> 7;            // pipeline
+  const int t = tid & 127;           // thread in pipeline = channel (mod 128) = TMEM lane
+  const int wq = t >> 5;             // warp quadrant -> TMEM lanes 32*wq..
+  uint8_t* wsm = smem;
+  uint8_t* act = smem + PN_W_BYTES + g * PN_ACT_BYTES;
+
+  // ---- one-time setup: weights -> smem, mbarriers, TMEM ----
+  {
+    uint4* dst = reinterpret_cast<uint4*>(wsm);
+    for (int i = tid; i < PN_W_BYTES / 16; i += PN_THREADS) dst[i] = a.wimage[i];
+  }
+  if (tid == 0) {
+    for (int i = 0; i < PN_GROUPS; ++i) tc::mbar_init(&mbar[i], 1);
+    tc::fence_barrier_init();
+  }
+  if (tid < 32) tc::tmem_alloc<512>(&tmem_base_s);
+  tc::fence_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_base_s + (uint32_t)(g * 256);       // this pipeline's 256 columns
+  const uint32_t tmem_lane = tmem + ((uint32_t)(wq * 32) << 16);  // this warp's lane quadrant
+
+  // per-thread BN constants of the finished layers (channel t; layer 4 has 128 channels)
+  float sc[4], sh[4];
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    sc[l] = (l + 1 < PHASE) ? a.scale[l * PN_MAXC + t] : 0.f;
+    sh[l] = (l + 1 < PHASE) ? a.shift[l * PN_MAXC + t] : 0.f;
+  }
+  constexpr uint32_t IDESC = tc::make_idesc_bf16(128, PN_TILE);
+  const int mblocks5 = a.F / 128;
+  float ssum[2] = {0.f, 0.f}, ssq[2] = {0.f, 0.f};
+  uint32_t parity = 0;
+
+  const int tiles_per_part = (a.N + PN_TILE - 1) / PN_TILE;
+  const long long n_tiles = (long long)a.n_parts * tiles_per_part;
+  const int worker = blockIdx.x * PN_GROUPS + g;
+  const int n_workers = gridDim.x * PN_GROUPS;
+
+  for (long long tile = worker; tile < n_tiles; tile += n_workers) {
+    const int part = (int)(tile / tiles_per_part);
+    if (a.valids != nullptr && a.valids[part] == 0.0f) continue;  // uniform per pipeline
+    const int p0 = (int)(tile % tiles_per_part) * PN_TILE;
+    const int npts = min(PN_TILE, a.N - p0);
+
+    // ---- layer-1 B operand: row = point, k = (x, y, z, 0 ...) in bf16 ----
+    {
+      float x = 0.f, y = 0.f, z = 0.f;
+      if (t < npts) {
+        const float* p = a.pts + ((long long)part * a.N + p0 + t) * 3;
+        x = p[0]; y = p[1]; z = p[2];
+      }
+      const __nv_bfloat162 xy = __floats2bfloat162_rn(x, y);
+      const __nv_bfloat162 z0 = __floats2bfloat162_rn(z, 0.f);
+      uint4 c0;
+      c0.x = *reinterpret_cast<const uint32_t*>(&xy);
+      c0.y = *reinterpret_cast<const uint32_t*>(&z0);
+      c0.z = 0u; c0.w = 0u;
+      *reinterpret_cast<uint4*>(act + tc::sw128_offset(t, 0)) = c0;
+      *reinterpret_cast<uint4*>(act + tc::sw128_offset(t, 8)) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    tc::group_sync(1 + g, 128);
+
+#pragma unroll
+    for (int layer = 1; layer <= PHASE; ++layer) {
+      const int K = layer == 1 ? 16 : (layer == 5 ? 128 : 64);
+      const int mblocks = layer == 5 ? mblocks5 : 1;
+      // ---- MMA issue (one thread) ----
+      if (t == 0) {
+        tc::fence_after_sync();
+        for (int mb = 0; mb < mblocks; ++mb) {
+          for (int k = 0; k < K; k += 16) {
+            const int kb = k >> 6, ks = k & 63;
+            const uint32_t wa = tc::smem_u32(wsm) + pn_w_off(layer - 1) +
+                                (layer == 5 ? (mb * 2 + kb) * PN_WTILE : 0) + ks * 2;
+            const uint32_t ba = tc::smem_u32(act) + kb * PN_WTILE + ks * 2;
+            tc::mma_bf16(tmem + (uint32_t)(mb * 128), tc::make_desc_sw128(wa),
+                         tc::make_desc_sw128(ba), IDESC, k > 0 ? 1u : 0u);
+          }
+        }
+        tc::mma_commit(&mbar[g]);
+      }
+      tc::mbar_wait(&mbar[g], parity);
+      parity ^= 1u;
+      tc::fence_after_sync();
+
+      // ---- epilogue ----
+      if (layer < PHASE) {
+        // BN + ReLU, bf16, into the B-operand tile of the next layer (this
+        // layer's input tile is dead: its MMA has completed)
+        const int cout = pn_cout(layer, a.F);
+        if (wq * 32 < cout) {
+          const float s = sc[layer - 1], b = sh[layer - 1];
+          uint8_t* dst = act + (t >> 6) * PN_WTILE;  // K-block of channel t
+          const int col = t & 63;
+#pragma unroll 1
+          for (int j0 = 0; j0 < PN_TILE; j0 += 32) {
+            float v[32];
+            tc::tmem_ld32(tmem_lane + (uint32_t)j0, v);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float r = fmaxf(fmaf(v[j], s, b), 0.f);
+              *reinterpret_cast<__nv_bfloat16*>(dst + tc::sw128_offset(j0 + j, col)) =
+                  __float2bfloat16_rn(r);
+            }
+          }
+        }
+        tc::fence_async_smem();
+        tc::fence_before_sync();
+        tc::group_sync(1 + g, 128);
+      } else {
+        // statistics of this layer's pre-activations (+ max/min for layer 5)
+        const int cout = pn_cout(layer, a.F);
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) {
+          if (mb < mblocks && mb * 128 + wq * 32 < cout) {
+            float mx = -3.0e38f, mn = 3.0e38f, s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+            for (int j0 = 0; j0 < PN_TILE; j0 += 32) {
+              float v[32];
+              tc::tmem_ld32(tmem_lane + (uint32_t)(mb * 128 + j0), v);
+              tc::tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (j0 + j < npts) {
+                  s1 += v[j];
+                  s2 = fmaf(v[j], v[j], s2);
+                  if (PHASE == 5) { mx = fmaxf(mx, v[j]); mn = fminf(mn, v[j]); }
+                }
+              }
+            }
+            ssum[mb] += s1;
+            ssq[mb] += s2;
+            if (PHASE == 5) {
+              const long long o = (long long)part * PN_MAXC + mb * 128 + t;
+              atomicMax(a.pmax + o, tc::float_to_ordered(mx));
+              atomicMin(a.pmin + o, tc::float_to_ordered(mn));
+            }
+          }
+        }
+        tc::fence_before_sync();  // TMEM reads done before the next tile's MMA overwrites
+      }
+    }
+  }
+
+  // ---- per-worker partial statistics ----
+#pragma unroll
+  for (int mb = 0; mb < 2; ++mb) {
+    const int c = mb * 128 + t;
+    float* o = a.partial + ((long long)worker * PN_MAXC + c) * 2;
+    o[0] = ssum[mb];
+    o[1] = ssq[mb];
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (tid < 32) tc::tmem_dealloc<512>(tmem_base_s);
+}
+
+// fp32 conv weights [Cout, Cin] -> pre-swizzled bf16 smem image (zero-filled beforehand)
+__global__ void pointnet_fill_weights_kernel(const float* w1, const float* w2, const float* w3,
+                                             const float* w4, const float* w5, int F,
+                                             uint8_t* image) {
+  // one thread per (layer, out channel, in channel)
+  const int cin[5] = {3, 64, 64, 64, 128};
+  const int cout[5] = {64, 64, 64, 128, F};
+  const float* w[5] = {w1, w2, w3, w4, w5};
+  for (int layer = 0; layer < 5; ++layer) {
+    const int n = cin[layer] * cout[layer];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+      const int co = i / cin[layer], ci = i % cin[layer];
+      const int mb = co >> 7, row = co & 127, kb = ci >> 6, col = ci & 63;
+      uint8_t* tile = image + pn_w_off(layer) + (layer == 4 ? (mb * 2 + kb) * PN_WTILE : 0);
+      *reinterpret_cast<__nv_bfloat16*>(tile + tc::sw128_offset(row, col)) =
+          __float2bfloat16_rn(w[layer][i]);
+    }
+  }
+}
+
+// reduce the per-worker partial sums of layer `layer` (0-based) in a fixed order,
+// produce BN scale/shift, update the running statistics (train mode), and for the
+// last layer turn per-part max/min into the pooled features.
+__global__ void pointnet_finalize_kernel(const float* partial, int n_workers, int layer, int C,
+                                         const float* valids, int n_parts, int N,
+                                         const float* gamma, const float* beta, float eps,
+                                         float momentum, float* running_mean, float* running_var,
+                                         float* scale, float* shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int w = 0; w < n_workers; ++w) {
+    s1 += (double)partial[((long long)w * PN_MAXC + c) * 2];
+    s2 += (double)partial[((long long)w * PN_MAXC + c) * 2 + 1];
+  }
+  double cnt = 0.0;
+  for (int p = 0; p < n_parts; ++p) cnt += (valids == nullptr || valids[p] != 0.0f) ? (double)N : 0.0;
+  const double mean = s1 / cnt;
+  const double var = fmax(s2 / cnt - mean * mean, 0.0);
+  const float sc = gamma[c] * (float)(1.0 / sqrt(var + (double)eps));
+  scale[layer * PN_MAXC + c] = sc;
+  shift[layer * PN_MAXC + c] = beta[c] - (float)mean * sc;
+  if (running_mean != nullptr) {
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+    const double unbiased = cnt > 1.0 ? var * cnt / (cnt - 1.0) : var;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+__global__ void pointnet_eval_affine_kernel(const float* gamma, const float* beta,
+                                            const float* running_mean, const float* running_var,
+                                            float eps, int layer, int C, float* scale, float* shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float sc = gamma[c] * rsqrtf(running_var[c] + eps);
+  scale[layer * PN_MAXC + c] = sc;
+  shift[layer * PN_MAXC + c] = beta[c] - running_mean[c] * sc;
+}
+
+__global__ void pointnet_init_minmax_kernel(unsigned* pmax, unsigned* pmin, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    pmax[i] = 0u;           // below every encoded float
+    pmin[i] = 0xffffffffu;  // above every encoded float
+  }
+}
+
+// feats[part, c] = max_n BN5(y)[c] = scale*max + shift (scale >= 0) or scale*min + shift
+__global__ void pointnet_pool_kernel(const unsigned* pmax, const unsigned* pmin, const float* scale,
+                                     const float* shift, const float* valids, int n_parts, int F,
+                                     float* feats) {
+  const long long total = (long long)n_parts * F;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int part = (int)(i / F), c = (int)(i % F);
+    float out = 0.f;
+    if (valids == nullptr || valids[part] != 0.0f) {
+      const float sc = scale[4 * PN_MAXC + c], sh = shift[4 * PN_MAXC + c];
+      const float mx = tc::ordered_to_float(pmax[(long long)part * PN_MAXC + c]);
+      const float mn = tc::ordered_to_float(pmin[(long long)part * PN_MAXC + c]);
+      out = sc >= 0.f ? fmaf(sc, mx, sh) : fmaf(sc, mn, sh);
+    }
+    feats[i] = out;
+  }
+}
+
+template <int PHASE>
+static int launch_phase(const PointNetArgs& a, int grid, cudaStream_t stream) {
+  static bool attr = false;
+  if (!attr) {
+    MPA_CUDA(cudaFuncSetAttribute(pointnet_phase_kernel<PHASE>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, PN_SMEM));
+    attr = true;
+  }
+  {
+    static const char* names[5] = {"pointnet_phase1", "pointnet_phase2", "pointnet_phase3",
+                                   "pointnet_phase4", "pointnet_phase5"};
+    ProfScope ps(names[PHASE - 1], stream);
+    pointnet_phase_kernel<PHASE><<<grid, PN_THREADS, PN_SMEM, stream>>>(a);
+  }
+  MPA_LAUNCH_CHECK();
+  return MPA_OK;
+}
+
+}  // namespace mpa
+
+using namespace mpa;
+
+extern "C" {
+
+size_t mpa_pointnet_workspace_bytes(int n_parts) {
+  if (n_parts <= 0) return 0;
+  size_t o = 0;
+  o += align_up(PN_W_BYTES, 256);                                   // weight image
+  o += align_up(sizeof(float) * 2 * 5 * PN_MAXC, 256);              // scale, shift
+  o += align_up(sizeof(float) * 2 * PN_MAXC * 2 * 160 * PN_GROUPS, 256);  // partial (<=160 CTAs)
+  o += 2 * align_up(sizeof(unsigned) * (size_t)n_parts * PN_MAXC, 256);   // pmax, pmin
+  return o;
+}
+
+int mpa_pointnet_forward(const float* pts, const float* valids, int n_parts, int N, int F,
+                         const float* const* conv_w, const float* const* bn_gamma,
+                         const float* const* bn_beta, float* const* bn_running_mean,
+                         float* const* bn_running_var, int training, float eps, float momentum,
+                         float* feats, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MPA_CHECK_ARG(n_parts >= 0 && N >= 0, "pointnet_forward: negative size");
+  MPA_CHECK_ARG(F == 128 || F == 256, "pointnet_forward: feat_dim must be 128 or 256 (got %d)", F);
+  if (n_parts == 0) return MPA_OK;
+  MPA_CHECK_ARG(N > 0, "pointnet_forward: parts need at least one point");
+  MPA_CHECK_ARG(pts && conv_w && bn_gamma && bn_beta && bn_running_mean && bn_running_var && feats,
+                "pointnet_forward: null pointer");
+  int sms = 0, dev = 0;
+  MPA_CUDA(cudaGetDevice(&dev));
+  MPA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int tiles_per_part = (N + PN_TILE - 1) / PN_TILE;
+  const long long n_tiles = (long long)n_parts * tiles_per_part;
+  int grid = (int)((n_tiles + PN_GROUPS - 1) / PN_GROUPS);
+  if (grid > sms) grid = sms;
+  if (grid > 160) grid = 160;
+  const int n_workers = grid * PN_GROUPS;
+
+  Scratch scratch;
+  const size_t need = mpa_pointnet_workspace_bytes(n_parts);
+  int rc = scratch.acquire(ws, ws_bytes, need, stream);
+  if (rc != MPA_OK) return rc;
+  char* p = (char*)scratch.base;
+  uint8_t* image = (uint8_t*)p; p += align_up(PN_W_BYTES, 256);
+  float* scale = (float*)p;
+  float* shift = scale + 5 * PN_MAXC; p += align_up(sizeof(float) * 2 * 5 * PN_MAXC, 256);
+  float* partial = (float*)p; p += align_up(sizeof(float) * 2 * PN_MAXC * 2 * 160 * PN_GROUPS, 256);
+  unsigned* pmax = (unsigned*)p; p += align_up(sizeof(unsigned) * (size_t)n_parts * PN_MAXC, 256);
+  unsigned* pmin = (unsigned*)p;
+
+  MPA_CUDA(cudaMemsetAsync(image, 0, PN_W_BYTES, stream));
+  {
+    ProfScope ps("pointnet_pack_weights", stream);
+    pointnet_fill_weights_kernel<<<64, 256, 0, stream>>>(conv_w[0], conv_w[1], conv_w[2], conv_w[3],
+                                                         conv_w[4], F, image);
+  }
+  MPA_LAUNCH_CHECK();
+  {
+    ProfScope ps("pointnet_init_minmax", stream);
+    pointnet_init_minmax_kernel<<<256, 256, 0, stream>>>(pmax, pmin, (long long)n_parts * PN_MAXC);
+  }
+  MPA_LAUNCH_CHECK();
+
+  PointNetArgs a{pts, valids, (const uint4*)image, scale, shift, partial, pmax, pmin, n_parts, N, F};
+  const int C[5] = {64, 64, 64, 128, F};
+  if (training) {
+    for (int layer = 0; layer < 5; ++layer) {
+      switch (layer) {
+        case 0: rc = launch_phase<1>(a, grid, stream); break;
+        case 1: rc = launch_phase<2>(a, grid, stream); break;
+        case 2: rc = launch_phase<3>(a, grid, stream); break;
+        case 3: rc = launch_phase<4>(a, grid, stream); break;
+        default: rc = launch_phase<5>(a, grid, stream); break;
+      }
+      if (rc != MPA_OK) return rc;
+      {
+        ProfScope ps("pointnet_bn_finalize", stream);
+        pointnet_finalize_kernel<<<(C[layer] + 127) / 128, 128, 0, stream>>>(
+            partial, n_workers, layer, C[layer], valids, n_parts, N, bn_gamma[layer], bn_beta[layer],
+            eps, momentum, bn_running_mean[layer], bn_running_var[layer], scale, shift);
+      }
+      MPA_LAUNCH_CHECK();
+    }
+  } else {
+    for (int layer = 0; layer < 5; ++layer) {
+      pointnet_eval_affine_kernel<<<(C[layer] + 127) / 128, 128, 0, stream>>>(
+          bn_gamma[layer], bn_beta[layer], bn_running_mean[layer], bn_running_var[layer], eps, layer,
+          C[layer], scale, shift);
+      MPA_LAUNCH_CHECK();
+    }
+    rc = launch_phase<5>(a, grid, stream);
+    if (rc != MPA_OK) return rc;
+  }
+  {
+    ProfScope ps("pointnet_pool", stream);
+    pointnet_pool_kernel<<<(int)(((long long)n_parts * F + 255) / 256), 256, 0, stream>>>(
+        pmax, pmin, scale, shift, valids, n_parts, F, feats);
+  }
+  MPA_LAUNCH_CHECK();
+  return MPA_OK;
+}
+
+}  // extern "C"

@@ -20,7 +20,11 @@ class PointNet(nn.Module):
             setattr(self, f'bn{i + 1}', nn.BatchNorm1d(dims[i + 1]))
         self.global_feat = global_feat
 
-    def forward(self, x):
+    supports_valids = True
+
+    def forward(self, x, valids=None):
+        """x [n, N, 3]; `valids` [n] (extension): parts flagged 0 are skipped on
+        the device (zero features, no BatchNorm contribution)."""
         convs = [getattr(self, f'conv{i}') for i in range(1, 6)]
         bns = [getattr(self, f'bn{i}') for i in range(1, 6)]
-        return kernels.pointnet_forward(x, convs, bns, self.training, self.global_feat)
+        return kernels.pointnet_forward(x, convs, bns, self.training, self.global_feat, valids)

@@ -136,3 +136,61 @@ def test_model_steps_match_reference(cuda, tag, name, dataset, encoder, seed, se
                                 if p.grad is not None))
             np.testing.assert_allclose(float(gn), g['train/grad_norm'], rtol=2e-3)
             model.zero_grad()
+
+
+def _bf16_emulated_pointnet(x, enc, training):
+    """The arithmetic of csrc/pointnet.cu in plain torch: bf16-rounded weights
+    and layer inputs, fp32 accumulation, fp32 BatchNorm on the fp32 conv output."""
+    import torch.nn.functional as F
+    q = lambda t: t.to(torch.bfloat16).float()
+    h = q(x.transpose(2, 1))
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        for i in range(1, 6):
+            conv, bn = getattr(enc, f'conv{i}'), getattr(enc, f'bn{i}')
+            y = F.conv1d(h, q(conv.weight))
+            y = F.batch_norm(y, None if training else bn.running_mean,
+                             None if training else bn.running_var, bn.weight, bn.bias, training, 0.0, bn.eps)
+            h = q(F.relu(y)) if i < 5 else y
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    return h.max(dim=-1)[0]
+
+
+@pytest.mark.parametrize('feat,n,N', [(256, 6, 50), (256, 40, 1000), (128, 9, 333), (128, 3, 128)])
+@pytest.mark.parametrize('training', [True, False])
+def test_pointnet_tcgen05_kernel(cuda, feat, n, N, training):
+    """Native tcgen05 PointNet vs (a) the same bf16 arithmetic in torch (tight)
+    and (b) the fp32 module (loose: bf16 operand rounding)."""
+    import copy
+    from multi_part_assembly_b200 import kernels
+    from multi_part_assembly_b200.models import build_encoder
+    enc = fill_params_(build_encoder('pointnet', feat), 21).to(cuda).train(training)
+    ref = copy.deepcopy(enc)
+    g = torch.Generator().manual_seed(n * N)
+    x = (torch.rand(n, N, 3, generator=g) - 0.5).to(cuda)
+    valids = torch.ones(n, device=cuda)
+    valids[n // 2] = 0
+    kernels.set_precision('bf16')
+    try:
+        out = enc(x, valids=valids)
+    finally:
+        kernels.set_precision('auto')
+    keep = valids.bool()
+    want = _bf16_emulated_pointnet(x[keep], ref, training)
+    np.testing.assert_allclose(out[keep].detach().cpu().numpy(), want.detach().cpu().numpy(), rtol=2e-2, atol=2e-2)
+    assert torch.all(out[~keep] == 0)
+    kernels.set_precision('fp32')
+    try:
+        full = ref(x[keep])
+    finally:
+        kernels.set_precision('auto')
+    err = (out[keep] - full).abs().max().item() / full.abs().max().item()
+    assert err < 5e-2, err
+    if training:  # running statistics updated like nn.BatchNorm1d (momentum 0.1, unbiased var)
+        np.testing.assert_allclose(enc.bn1.running_mean.cpu().numpy(), ref.bn1.running_mean.cpu().numpy(),
+                                   rtol=2e-2, atol=2e-3)
+        np.testing.assert_allclose(enc.bn5.running_var.cpu().numpy(), ref.bn5.running_var.cpu().numpy(),
+                                   rtol=5e-2, atol=5e-3)
+        assert int(enc.bn3.num_batches_tracked) == 1
