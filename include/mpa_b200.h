@@ -149,6 +149,36 @@ int mpa_pointnet_forward(const float* pts, const float* valids, int n_parts, int
                          float* const* bn_running_var, int training, float eps, float momentum,
                          float* feats, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- token-level dense layers on tcgen05 + TMA ---------------------------- */
+/* Y = act(X W^T + bias) (+ residual): X [M,K], W [N,K] (an nn.Linear weight),
+ * bias [N] or NULL, residual [M,N] or NULL, out [M,N]; fp32 in memory, bf16
+ * tensor-core operands with fp32 accumulation.  act: 0 none, 1 ReLU,
+ * 2 LeakyReLU(0.2).  K must be a multiple of 8.  Replaces the cuBLAS GEMMs of
+ * PoseRegressor (models/modules/regressor.py:45-68). */
+size_t mpa_linear_workspace_bytes(int M, int N, int K);
+int mpa_linear_forward(const float* x, const float* w, const float* bias, const float* residual,
+                       int M, int N, int K, int act, float* out, void* ws, size_t ws_bytes,
+                       void* stream);
+
+/* Replaces TransformerEncoder.forward (models/pn_transformer/transformer.py:63-79),
+ * i.e. nn.TransformerEncoder built at :23-34: `layers` pre-LN encoder layers
+ * (MHA with H heads, ReLU FFN of width FF) + final LayerNorm (final_norm_w may be
+ * NULL), key-padding mask `valid` [B*P] bytes (1 = valid; NULL = all valid).
+ * tokens/out [B*P, D] fp32.  Every *_w/*_b argument is an array of `layers`
+ * device pointers laid out as torch stores them (in_proj_weight [3D,D] = [Wq;Wk;Wv]).
+ * Dropout is not applied (eval mode, or p = 0 as in the benchmark). */
+size_t mpa_transformer_workspace_bytes(int B, int P, int D, int FF, int layers);
+int mpa_transformer_forward(const float* tokens, const unsigned char* valid, int B, int P, int D,
+                            int H, int FF, int layers, const float* const* in_proj_w,
+                            const float* const* in_proj_b, const float* const* out_proj_w,
+                            const float* const* out_proj_b, const float* const* lin1_w,
+                            const float* const* lin1_b, const float* const* lin2_w,
+                            const float* const* lin2_b, const float* const* norm1_w,
+                            const float* const* norm1_b, const float* const* norm2_w,
+                            const float* const* norm2_b, const float* final_norm_w,
+                            const float* final_norm_b, float eps, float* out, void* ws,
+                            size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,414 @@
+// Dense token-level contractions of the inter-part transformer (and the pose
+// head) on tcgen05 tensor cores, fed by TMA.
+//
+//   Y[M, N] = epilogue( X[M, K] (bf16) * W[N, K]^T (bf16) + bias[N] )
+//
+// X is a row-major activation matrix (tokens x features), W is an nn.Linear
+// weight as torch stores it ([out, in], K-major) -- both operands are K-major,
+// so TMA boxes of {64 k, 128 rows} with the 128-byte swizzle land in shared
+// memory exactly in the canonical UMMA layout.  One CTA computes one 128 x BN
+// output tile: warp 0 is the TMA producer, warp 1 issues tcgen05.mma into TMEM,
+// warps 2-5 run the epilogue (tcgen05.ld -> bias / activation / residual ->
+// global).  A 4-stage mbarrier ring overlaps the K loop.
+//
+// Replaces the cuBLAS GEMMs inside nn.TransformerEncoderLayer
+// (models/pn_transformer/transformer.py:23-34) and PoseRegressor
+// (models/modules/regressor.py:45-68).
+#include <cuda.h>
+
+#include "mpa_common.cuh"
+#include "tc05.cuh"
+
+namespace mpa {
+
+constexpr int LN_BM = 128;      // rows per tile (UMMA M)
+constexpr int LN_BN = 128;      // columns per tile (UMMA N)
+constexpr int LN_BK = 64;       // k per stage (one 128-byte swizzle span of bf16)
+constexpr int LN_STAGES = 4;
+constexpr int LN_THREADS = 192;  // warp 0: TMA, warp 1: MMA, warps 2-5: epilogue
+constexpr int LN_STAGE_BYTES = (LN_BM + LN_BN) * LN_BK * 2;
+constexpr int LN_SMEM = LN_STAGES * LN_STAGE_BYTES + 1024;
+
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY02 = 2 };
+
+struct LinearEpilogue {
+  const float* bias;       // [N] or nullptr
+  const float* residual;   // [M, N] fp32 added after the activation, or nullptr
+  float* out_f32;          // [M, N] or nullptr
+  __nv_bfloat16* out_bf16; // [M, N] or nullptr
+  int act;
+};
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(tc::smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(tc::smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(LN_THREADS, 1)
+linear_bf16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                   int M, int N, int K, LinearEpilogue ep) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[LN_STAGES], empty_bar[LN_STAGES], done_bar;
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * LN_BM, n0 = blockIdx.y * LN_BN;
+  const int num_k = (K + LN_BK - 1) / LN_BK;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < LN_STAGES; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
+    tc::mbar_init(&done_bar, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc<LN_BN>(&tmem_base_s);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer =====
+      for (int kb = 0; kb < num_k; ++kb) {
+        const int s = kb % LN_STAGES;
+        if (kb >= LN_STAGES) tc::mbar_wait(&empty_bar[s], ((kb / LN_STAGES) - 1) & 1);
+        uint8_t* a_dst = smem + s * LN_STAGE_BYTES;
+        uint8_t* b_dst = a_dst + LN_BM * LN_BK * 2;
+        mbar_expect_tx(&full_bar[s], LN_STAGE_BYTES);
+        tma_load_2d(a_dst, &map_x, kb * LN_BK, m0, &full_bar[s]);
+        tma_load_2d(b_dst, &map_w, kb * LN_BK, n0, &full_bar[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      constexpr uint32_t IDESC = tc::make_idesc_bf16(LN_BM, LN_BN);
+      for (int kb = 0; kb < num_k; ++kb) {
+        const int s = kb % LN_STAGES;
+        tc::mbar_wait(&full_bar[s], (kb / LN_STAGES) & 1);
+        tc::fence_after_sync();
+        const uint32_t a_addr = tc::smem_u32(smem + s * LN_STAGE_BYTES);
+        const uint32_t b_addr = a_addr + LN_BM * LN_BK * 2;
+#pragma unroll
+        for (int k = 0; k < LN_BK; k += 16)
+          tc::mma_bf16(tmem, tc::make_desc_sw128(a_addr + k * 2), tc::make_desc_sw128(b_addr + k * 2),
+                       IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+        tc::mma_commit(&empty_bar[s]);  // frees this stage when the MMAs above retire
+      }
+      tc::mma_commit(&done_bar);
+    }
+  } else {  // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
+    tc::mbar_wait(&done_bar, 0);
+    tc::fence_after_sync();
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int j0 = 0; j0 < LN_BN; j0 += 32) {
+      float v[32];
+      tc::tmem_ld32(taddr + (uint32_t)j0, v);
+      tc::tmem_ld_wait();
+      if (row < M) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = n0 + j0 + j;
+          if (col < N) {
+            float r = v[j] + (ep.bias ? __ldg(ep.bias + col) : 0.f);
+            if (ep.act == ACT_RELU) r = fmaxf(r, 0.f);
+            else if (ep.act == ACT_LEAKY02) r = r > 0.f ? r : 0.2f * r;
+            if (ep.residual) r += ep.residual[(long long)row * N + col];
+            if (ep.out_f32) ep.out_f32[(long long)row * N + col] = r;
+            if (ep.out_bf16) ep.out_bf16[(long long)row * N + col] = __float2bfloat16_rn(r);
+          }
+        }
+      }
+    }
+    tc::fence_before_sync();
+  }
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc<LN_BN>(tmem);
+}
+
+// ---- driver-API entry point for tensor maps, resolved at run time (no -lcuda) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// bf16 row-major [rows, cols] matrix, box = {64 cols, 128 rows}, 128-byte swizzle, zero OOB fill
+static int make_map(CUtensorMap* map, const void* base, int rows, int cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return MPA_ERR_CUDA;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)cols * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)LN_BK, (cuuint32_t)LN_BM};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for a [%d, %d] bf16 matrix", (int)r, rows, cols);
+    return MPA_ERR_CUDA;
+  }
+  return MPA_OK;
+}
+
+int launch_linear(const __nv_bfloat16* x, const __nv_bfloat16* w, int M, int N, int K,
+                  const LinearEpilogue& ep, const char* name, cudaStream_t stream) {
+  MPA_CHECK_ARG(K % 8 == 0, "linear: K must be a multiple of 8 (got %d)", K);
+  CUtensorMap mx, mw;
+  int rc = make_map(&mx, x, M, K);
+  if (rc != MPA_OK) return rc;
+  rc = make_map(&mw, w, N, K);
+  if (rc != MPA_OK) return rc;
+  static bool attr = false;
+  if (!attr) {
+    MPA_CUDA(cudaFuncSetAttribute(linear_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM));
+    attr = true;
+  }
+  dim3 grid((M + LN_BM - 1) / LN_BM, (N + LN_BN - 1) / LN_BN);
+  {
+    ProfScope ps(name, stream);
+    linear_bf16_kernel<<<grid, LN_THREADS, LN_SMEM, stream>>>(mx, mw, M, N, K, ep);
+  }
+  MPA_LAUNCH_CHECK();
+  return MPA_OK;
+}
+
+// ---- small token-level kernels ---------------------------------------------
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16_rn(in[i]);
+}
+
+// LayerNorm over the last dim (D <= 1024, multiple of 32): one warp per row,
+// fp32 statistics (two-pass in registers), output bf16 (GEMM operand) and/or fp32.
+__global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, int rows, int D, float eps,
+                                 __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + (long long)row * D;
+  float v[32];
+  const int per = D / 32;
+  float s = 0.f;
+  for (int i = 0; i < per; ++i) { v[i] = xr[lane + 32 * i]; s += v[i]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)D;
+  float q = 0.f;
+  for (int i = 0; i < per; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)D + eps);
+  for (int i = 0; i < per; ++i) {
+    const int c = lane + 32 * i;
+    const float r = (v[i] - mean) * rstd * gamma[c] + beta[c];
+    if (out_bf16) out_bf16[(long long)row * D + c] = __float2bfloat16_rn(r);
+    if (out_f32) out_f32[(long long)row * D + c] = r;
+  }
+}
+
+// Multi-head self-attention over the P part tokens of one shape with a
+// key-padding mask (nn.MultiheadAttention semantics: softmax over valid keys
+// only; scale 1/sqrt(hd)).  qkv [B*P, 3*D] fp32 (q | k | v), out [B*P, D] bf16.
+// One warp per (shape, head); lane i owns query row i (P <= 32, hd <= 64).
+__global__ void attention_kernel(const float* __restrict__ qkv, const unsigned char* __restrict__ valid,
+                                 int B, int P, int H, int hd, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ float sm[];
+  const int warps_per_block = blockDim.x >> 5;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * warps_per_block + w;
+  float* ks = sm + (size_t)w * 2 * P * hd;
+  float* vs = ks + P * hd;
+  if (gw >= B * H) return;
+  const int b = gw / H, h = gw % H, D = H * hd;
+  for (int i = lane; i < P * hd; i += 32) {
+    const int p = i / hd, c = i % hd;
+    const float* base = qkv + (long long)(b * P + p) * 3 * D + h * hd + c;
+    ks[i] = base[D];
+    vs[i] = base[2 * D];
+  }
+  __syncwarp();
+  if (lane < P) {
+    const float* qp = qkv + (long long)(b * P + lane) * 3 * D + h * hd;
+    float q[64];
+    for (int c = 0; c < hd; ++c) q[c] = qp[c];
+    const float scale = rsqrtf((float)hd);
+    float sc[32];
+    float mx = -3.0e38f;
+    for (int j = 0; j < P; ++j) {
+      float d = 0.f;
+      for (int c = 0; c < hd; ++c) d = fmaf(q[c], ks[j * hd + c], d);
+      const bool ok = valid == nullptr || valid[b * P + j] != 0;
+      sc[j] = ok ? d * scale : -3.0e38f;
+      mx = fmaxf(mx, sc[j]);
+    }
+    float den = 0.f;
+    for (int j = 0; j < P; ++j) {
+      const bool ok = valid == nullptr || valid[b * P + j] != 0;
+      sc[j] = ok ? __expf(sc[j] - mx) : 0.f;
+      den += sc[j];
+    }
+    // a shape without any valid key cannot occur (>= 1 valid part); guard anyway
+    const float inv = den > 0.f ? 1.f / den : 0.f;
+    __nv_bfloat16* op = out + (long long)(b * P + lane) * D + h * hd;
+    for (int c = 0; c < hd; ++c) {
+      float o = 0.f;
+      for (int j = 0; j < P; ++j) o = fmaf(sc[j], vs[j * hd + c], o);
+      op[c] = __float2bfloat16_rn(o * inv);
+    }
+  }
+}
+
+}  // namespace mpa
+
+using namespace mpa;
+
+extern "C" {
+
+/* Y = act(X W^T + b) (+ residual); X [M,K] fp32, W [N,K] fp32 (converted to bf16
+ * operands), out fp32.  Generic entry (pose head, tests). */
+size_t mpa_linear_workspace_bytes(int M, int N, int K) {
+  return align_up((size_t)M * K * 2, 256) + align_up((size_t)N * K * 2, 256);
+}
+
+int mpa_linear_forward(const float* x, const float* w, const float* bias, const float* residual, int M,
+                       int N, int K, int act, float* out, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MPA_CHECK_ARG(M >= 0 && N > 0 && K > 0, "linear_forward: bad sizes %d %d %d", M, N, K);
+  MPA_CHECK_ARG(act >= ACT_NONE && act <= ACT_LEAKY02, "linear_forward: bad activation %d", act);
+  if (M == 0) return MPA_OK;
+  MPA_CHECK_ARG(x && w && out, "linear_forward: null pointer");
+  Scratch scratch;
+  int rc = scratch.acquire(ws, ws_bytes, mpa_linear_workspace_bytes(M, N, K), stream);
+  if (rc != MPA_OK) return rc;
+  __nv_bfloat16* xb = (__nv_bfloat16*)scratch.base;
+  __nv_bfloat16* wb = (__nv_bfloat16*)((char*)scratch.base + align_up((size_t)M * K * 2, 256));
+  f32_to_bf16_kernel<<<148, 256, 0, stream>>>(x, xb, (long long)M * K);
+  MPA_LAUNCH_CHECK();
+  f32_to_bf16_kernel<<<148, 256, 0, stream>>>(w, wb, (long long)N * K);
+  MPA_LAUNCH_CHECK();
+  LinearEpilogue ep{bias, residual, out, nullptr, act};
+  return launch_linear(xb, wb, M, N, K, ep, "linear_bf16", stream);
+}
+
+/* Pre-LN transformer encoder (nn.TransformerEncoder with norm_first=True,
+ * batch_first, ReLU FFN, final LayerNorm; dropout is not applied: eval mode or
+ * p = 0), key-padding mask from `valid`.  tokens/out [B*P, D] fp32.
+ * Per-layer parameter arrays hold `layers` device pointers each. */
+size_t mpa_transformer_workspace_bytes(int B, int P, int D, int FF, int layers) {
+  const size_t T = (size_t)B * P;
+  size_t o = 0;
+  o += align_up((size_t)layers * ((size_t)3 * D * D + (size_t)D * D + 2 * (size_t)FF * D) * 2, 256);  // bf16 weights
+  o += align_up(T * D * 4, 256);       // residual stream x
+  o += align_up(T * D * 2, 256);       // LN output bf16
+  o += align_up(T * 3 * D * 4, 256);   // qkv fp32
+  o += align_up(T * D * 2, 256);       // attention output bf16
+  o += align_up(T * FF * 2, 256);      // FFN hidden bf16
+  return o;
+}
+
+int mpa_transformer_forward(const float* tokens, const unsigned char* valid, int B, int P, int D, int H,
+                            int FF, int layers, const float* const* in_proj_w,
+                            const float* const* in_proj_b, const float* const* out_proj_w,
+                            const float* const* out_proj_b, const float* const* lin1_w,
+                            const float* const* lin1_b, const float* const* lin2_w,
+                            const float* const* lin2_b, const float* const* norm1_w,
+                            const float* const* norm1_b, const float* const* norm2_w,
+                            const float* const* norm2_b, const float* final_norm_w,
+                            const float* final_norm_b, float eps, float* out, void* ws, size_t ws_bytes,
+                            void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MPA_CHECK_ARG(B >= 0 && P > 0 && P <= 32, "transformer_forward: 1 <= P <= 32 parts (got %d)", P);
+  MPA_CHECK_ARG(D % 32 == 0 && D <= 1024 && H > 0 && D % H == 0 && D / H <= 64 && FF % 8 == 0,
+                "transformer_forward: unsupported dims D=%d H=%d FF=%d", D, H, FF);
+  if (B == 0) return MPA_OK;
+  const int T = B * P, hd = D / H;
+  Scratch scratch;
+  int rc = scratch.acquire(ws, ws_bytes, mpa_transformer_workspace_bytes(B, P, D, FF, layers), stream);
+  if (rc != MPA_OK) return rc;
+  char* p = (char*)scratch.base;
+  const size_t per_layer = (size_t)3 * D * D + (size_t)D * D + 2 * (size_t)FF * D;
+  __nv_bfloat16* wts = (__nv_bfloat16*)p; p += align_up((size_t)layers * per_layer * 2, 256);
+  float* x = (float*)p; p += align_up((size_t)T * D * 4, 256);
+  __nv_bfloat16* xn = (__nv_bfloat16*)p; p += align_up((size_t)T * D * 2, 256);
+  float* qkv = (float*)p; p += align_up((size_t)T * 3 * D * 4, 256);
+  __nv_bfloat16* att = (__nv_bfloat16*)p; p += align_up((size_t)T * D * 2, 256);
+  __nv_bfloat16* hid = (__nv_bfloat16*)p;
+
+  {
+    ProfScope ps("transformer_weights_to_bf16", stream);
+    for (int l = 0; l < layers; ++l) {
+      __nv_bfloat16* wl = wts + (size_t)l * per_layer;
+      f32_to_bf16_kernel<<<64, 256, 0, stream>>>(in_proj_w[l], wl, (long long)3 * D * D);
+      f32_to_bf16_kernel<<<64, 256, 0, stream>>>(out_proj_w[l], wl + (size_t)3 * D * D, (long long)D * D);
+      f32_to_bf16_kernel<<<64, 256, 0, stream>>>(lin1_w[l], wl + (size_t)4 * D * D, (long long)FF * D);
+      f32_to_bf16_kernel<<<64, 256, 0, stream>>>(lin2_w[l], wl + (size_t)4 * D * D + (size_t)FF * D,
+                                                 (long long)FF * D);
+      count_launch(4);
+    }
+  }
+  MPA_CUDA(cudaGetLastError());
+  MPA_CUDA(cudaMemcpyAsync(x, tokens, (size_t)T * D * 4, cudaMemcpyDeviceToDevice, stream));
+  const int ln_blocks = (T * 32 + 255) / 256;
+  const int att_warps = 4;
+  const size_t att_smem = (size_t)att_warps * 2 * P * hd * sizeof(float);
+  for (int l = 0; l < layers; ++l) {
+    const __nv_bfloat16* wl = wts + (size_t)l * per_layer;
+    { ProfScope ps("layernorm", stream);
+      layernorm_kernel<<<ln_blocks, 256, 0, stream>>>(x, norm1_w[l], norm1_b[l], T, D, eps, xn, nullptr); }
+    MPA_LAUNCH_CHECK();
+    LinearEpilogue e_qkv{in_proj_b[l], nullptr, qkv, nullptr, ACT_NONE};
+    rc = launch_linear(xn, wl, T, 3 * D, D, e_qkv, "linear_qkv", stream);
+    if (rc != MPA_OK) return rc;
+    { ProfScope ps("attention", stream);
+      attention_kernel<<<(B * H + att_warps - 1) / att_warps, att_warps * 32, att_smem, stream>>>(
+          qkv, valid, B, P, H, hd, att); }
+    MPA_LAUNCH_CHECK();
+    LinearEpilogue e_o{out_proj_b[l], x, x, nullptr, ACT_NONE};
+    rc = launch_linear(att, wl + (size_t)3 * D * D, T, D, D, e_o, "linear_out_proj", stream);
+    if (rc != MPA_OK) return rc;
+    { ProfScope ps("layernorm", stream);
+      layernorm_kernel<<<ln_blocks, 256, 0, stream>>>(x, norm2_w[l], norm2_b[l], T, D, eps, xn, nullptr); }
+    MPA_LAUNCH_CHECK();
+    LinearEpilogue e_f1{lin1_b[l], nullptr, nullptr, hid, ACT_RELU};
+    rc = launch_linear(xn, wl + (size_t)4 * D * D, T, FF, D, e_f1, "linear_ffn1", stream);
+    if (rc != MPA_OK) return rc;
+    LinearEpilogue e_f2{lin2_b[l], x, x, nullptr, ACT_NONE};
+    rc = launch_linear(hid, wl + (size_t)4 * D * D + (size_t)FF * D, T, D, FF, e_f2, "linear_ffn2", stream);
+    if (rc != MPA_OK) return rc;
+  }
+  if (final_norm_w != nullptr) {
+    { ProfScope ps("layernorm", stream);
+      layernorm_kernel<<<ln_blocks, 256, 0, stream>>>(x, final_norm_w, final_norm_b, T, D, eps, nullptr, out); }
+    MPA_LAUNCH_CHECK();
+  } else {
+    MPA_CUDA(cudaMemcpyAsync(out, x, (size_t)T * D * 4, cudaMemcpyDeviceToDevice, stream));
+  }
+  return MPA_OK;
+}
+
+}  // extern "C"

@@ -192,7 +192,78 @@ def dgcnn_forward(x, m, training, k=20):
 # ---------------------------------------------------------------------------
 # Transformer encoder
 # ---------------------------------------------------------------------------
+def _transformer_params(encoder):
+    ls = encoder.layers
+    groups = [
+        [l.self_attn.in_proj_weight for l in ls], [l.self_attn.in_proj_bias for l in ls],
+        [l.self_attn.out_proj.weight for l in ls], [l.self_attn.out_proj.bias for l in ls],
+        [l.linear1.weight for l in ls], [l.linear1.bias for l in ls],
+        [l.linear2.weight for l in ls], [l.linear2.bias for l in ls],
+        [l.norm1.weight for l in ls], [l.norm1.bias for l in ls],
+        [l.norm2.weight for l in ls], [l.norm2.bias for l in ls],
+    ]
+    return groups
+
+
+class _TransformerFunction(torch.autograd.Function):
+    """Forward: tcgen05 + TMA kernels (csrc/linear.cu).  Backward: re-runs the
+    stock nn.TransformerEncoder with autograd (round-1 scope is fwd+loss)."""
+
+    @staticmethod
+    def forward(ctx, tokens, valid, encoder, num_heads, *params):
+        B, P, D = tokens.shape
+        ls = encoder.layers
+        FF = ls[0].linear1.out_features
+        dev = tokens.device
+        out = torch.empty_like(tokens)
+        groups = _transformer_params(encoder)
+        L = _lib.lib()
+        ws_bytes = L.mpa_transformer_workspace_bytes(B, P, D, FF, len(ls))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        vb = None if valid is None else valid.to(torch.uint8).contiguous()
+        fn = encoder.norm
+        with torch.cuda.device(dev):
+            rc = L.mpa_transformer_forward(
+                _lib.ptr(tokens), _lib.ptr(vb), B, P, D, num_heads, FF, len(ls),
+                *[_ptr_array([t.detach() for t in g]) for g in groups],
+                _lib.ptr(fn.weight.detach()) if fn is not None else None,
+                _lib.ptr(fn.bias.detach()) if fn is not None else None,
+                float(ls[0].norm1.eps), _lib.ptr(out), _lib.ptr(ws), ws_bytes,
+                _lib.cuda_stream(dev))
+        _lib.check(rc, 'mpa_transformer_forward')
+        ctx.save_for_backward(tokens, valid if valid is not None else tokens.new_empty(0))
+        ctx.encoder = encoder
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        tokens, valid = ctx.saved_tensors
+        encoder = ctx.encoder
+        params = [p for p in encoder.parameters()]
+        with torch.enable_grad():
+            t = tokens.detach().requires_grad_(True)
+            pad = ~valid if valid.numel() else None
+            out = encoder(t, src_key_padding_mask=pad)
+            grads = torch.autograd.grad(out, [t] + params, grad, allow_unused=True)
+        return (grads[0], None, None, None) + tuple(grads[1:])
+
+
 def transformer_forward(tokens, valid_masks, encoder, num_heads, training, dropout):
+    """tokens [B, P, C], valid_masks [B, P] bool -> [B, P, C]."""
     _lib.require_cuda(tokens)
+    layer0 = encoder.layers[0]
+    native = _use_bf16() and layer0.norm_first and not (training and dropout > 0.) and \
+        tokens.shape[1] <= 32 and tokens.shape[2] % 32 == 0 and \
+        tokens.shape[2] // num_heads <= 64
+    if native:
+        params = [p for p in encoder.parameters()]
+        with torch.autocast('cuda', enabled=False):
+            return _TransformerFunction.apply(tokens.float().contiguous(), valid_masks, encoder,
+                                              num_heads, *params)
     pad = None if valid_masks is None else ~valid_masks
-    return encoder(tokens, src_key_padding_mask=pad)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        return encoder(tokens, src_key_padding_mask=pad)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev

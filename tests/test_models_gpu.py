@@ -194,3 +194,48 @@ def test_pointnet_tcgen05_kernel(cuda, feat, n, N, training):
         np.testing.assert_allclose(enc.bn5.running_var.cpu().numpy(), ref.bn5.running_var.cpu().numpy(),
                                    rtol=5e-2, atol=5e-3)
         assert int(enc.bn3.num_batches_tracked) == 1
+
+
+@pytest.mark.parametrize('M,N,K,act,res', [(640, 768, 256, 0, False), (640, 256, 1024, 0, True),
+                                           (40, 1024, 256, 1, False), (7, 4, 128, 2, False),
+                                           (129, 136, 288, 2, True), (5120, 256, 256, 0, True)])
+def test_linear_tcgen05(cuda, M, N, K, act, res):
+    """TMA-fed tcgen05 GEMM vs the same bf16-operand / fp32-accumulate product in torch."""
+    from multi_part_assembly_b200 import _lib
+    g = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g).to(cuda)
+    w = (torch.randn(N, K, generator=g) / K**0.5).to(cuda)
+    b = torch.randn(N, generator=g).to(cuda)
+    r = torch.randn(M, N, generator=g).to(cuda) if res else None
+    out = torch.empty(M, N, device=cuda)
+    L = _lib.lib()
+    rc = L.mpa_linear_forward(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(r), M, N, K, act,
+                              _lib.ptr(out), None, 0, _lib.cuda_stream(cuda))
+    _lib.check(rc, 'mpa_linear_forward')
+    want = x.to(torch.bfloat16).double() @ w.to(torch.bfloat16).double().T + b.double()
+    if act == 1:
+        want = torch.relu(want)
+    elif act == 2:
+        want = torch.nn.functional.leaky_relu(want, 0.2)
+    if res:
+        want = want + r.double()
+    np.testing.assert_allclose(out.cpu().numpy(), want.float().cpu().numpy(), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize('name,dims,seed', [('transformer', (64, 4, 128, 2), 6),
+                                            ('transformer_full', (256, 8, 1024, 4), 7)])
+def test_transformer_tcgen05(cuda, name, dims, seed):
+    """Native transformer encoder (bf16 tensor-core GEMMs) vs the reference golden output."""
+    from multi_part_assembly_b200 import kernels
+    from multi_part_assembly_b200.models.pn_transformer import TransformerEncoder
+    g = gold(name)
+    tr = fill_params_(TransformerEncoder(*dims), seed).to(cuda).eval()
+    kernels.set_precision('bf16')
+    try:
+        out = tr(T(g['tokens'], cuda), T(g['valid'], cuda)).cpu().detach().numpy()
+    finally:
+        kernels.set_precision('auto')
+    v = g['valid']
+    assert np.isfinite(out).all()
+    err = np.abs(out[v] - g['out'][v]).max() / np.abs(g['out'][v]).max()
+    assert err < 3e-2, err
