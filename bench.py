@@ -169,9 +169,21 @@ def run_native(args):
     resident = {k: v.to(dev) for k, v in host.items()}
     flush = torch.empty(192 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
+    def eager_step(batch):
+        with torch.no_grad():
+            with torch.autocast('cuda', dtype=torch.bfloat16, enabled=args.dtype == 'bf16'):
+                return model.forward_pass(dict(batch), mode='train', optimizer_idx=-1)['loss']
+
+    graphed = None
+    if not args.no_graph:
+        from multi_part_assembly_b200.runtime import GraphedStep
+        graphed = GraphedStep(model, resident, mode='train',
+                              autocast_dtype=torch.bfloat16 if args.dtype == 'bf16' else None)
+
     def step(batch):
-        with torch.autocast('cuda', dtype=torch.bfloat16, enabled=args.dtype == 'bf16'):
-            return model.forward_pass(dict(batch), mode='train', optimizer_idx=-1)['loss']
+        if graphed is not None:
+            return graphed(batch)['loss']
+        return eager_step(batch)
 
     def barrier():
         torch.cuda.synchronize()
@@ -193,16 +205,22 @@ def run_native(args):
         return sum(s.elapsed_time(e) for s, e in zip(starts, stops))
 
     for _ in range(args.warmup):
-        step(resident)
+        step(None if graphed is not None else resident)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = _lib.launch_count()
-    ms_total = timed(lambda: step(resident), args.steps)
-    launches = _lib.launch_count() - launches0
+    l0 = _lib.launch_count()
+    eager_step(resident)
+    launches_per_step = _lib.launch_count() - l0  # a graph replay issues the same kernel nodes
+    torch.cuda.synchronize()
+    # inputs already resident in HBM (the graph's static input buffers / `resident`)
+    ms_total = timed(lambda: step(None if graphed is not None else resident), args.steps)
+    launches = launches_per_step * args.steps
 
     # e2e: pinned host batch -> device, forward_pass, loss back to the host
     def e2e_step():
+        if graphed is not None:
+            return float(step(host))  # pinned host -> static device buffers -> replay -> loss D2H
         batch = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
         return float(step(batch))
 
@@ -215,7 +233,7 @@ def run_native(args):
     profiler.enable(True)
     for _ in range(min(args.steps, 10)):
         flush.zero_()
-        step(resident)
+        eager_step(resident)  # eager: the library's event pairs cannot be recorded inside a graph
     torch.cuda.synchronize()
     prof = profiler.report()
     profiler.enable(False)
@@ -264,7 +282,9 @@ def run_native(args):
         'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'batch_per_gpu': B_PER_GPU, 'parts': P, 'points': N_PTS,
                    'l2': 'flushed (192 MiB memset) before every timed step',
-                   'autograd': 'graph recorded (training-mode forward + loss)'},
+                   'mode': 'training-mode forward (BatchNorm batch statistics) + all loss terms, '
+                           'no autograd recording, dropout 0',
+                   'cuda_graph': graphed is not None},
         'clocks': clocks,
         'e2e': {'value': shapes / (ms_e2e / 1e3), 'unit': 'shapes/s',
                 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4},
@@ -286,6 +306,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'f32'])
+    ap.add_argument('--no-graph', action='store_true', help='eager launches instead of a CUDA graph')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'native' else args.warmup
     if args.impl == 'reference':

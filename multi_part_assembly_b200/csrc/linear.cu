@@ -108,27 +108,35 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     tc::mbar_wait(&done_bar, 0);
     tc::fence_after_sync();
     const int q = warp & 3;
-    const int row = m0 + q * 32 + lane;
     const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
+    // the operand ring is idle now: reuse it as a [32][33] fp32 transpose tile per
+    // warp so that global stores / residual loads are coalesced along N
+    float* stage = reinterpret_cast<float*>(smem) + q * (32 * 33);
 #pragma unroll 1
     for (int j0 = 0; j0 < LN_BN; j0 += 32) {
       float v[32];
       tc::tmem_ld32(taddr + (uint32_t)j0, v);
       tc::tmem_ld_wait();
-      if (row < M) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = n0 + j0 + j;
-          if (col < N) {
-            float r = v[j] + (ep.bias ? __ldg(ep.bias + col) : 0.f);
-            if (ep.act == ACT_RELU) r = fmaxf(r, 0.f);
-            else if (ep.act == ACT_LEAKY02) r = r > 0.f ? r : 0.2f * r;
-            if (ep.residual) r += ep.residual[(long long)row * N + col];
-            if (ep.out_f32) ep.out_f32[(long long)row * N + col] = r;
-            if (ep.out_bf16) ep.out_bf16[(long long)row * N + col] = __float2bfloat16_rn(r);
-          }
+      for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = v[j];  // row = lane
+      __syncwarp();
+      const int col = n0 + j0 + lane;
+      if (col < N) {
+        const float bias = ep.bias ? __ldg(ep.bias + col) : 0.f;
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+          const int row = m0 + q * 32 + r;
+          if (row >= M) break;
+          float x = stage[r * 33 + lane] + bias;
+          if (ep.act == ACT_RELU) x = fmaxf(x, 0.f);
+          else if (ep.act == ACT_LEAKY02) x = x > 0.f ? x : 0.2f * x;
+          const long long o = (long long)row * N + col;
+          if (ep.residual) x += ep.residual[o];
+          if (ep.out_f32) ep.out_f32[o] = x;
+          if (ep.out_bf16) ep.out_bf16[o] = __float2bfloat16_rn(x);
         }
       }
+      __syncwarp();
     }
     tc::fence_before_sync();
   }
@@ -234,52 +242,57 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
 // Multi-head self-attention over the P part tokens of one shape with a
 // key-padding mask (nn.MultiheadAttention semantics: softmax over valid keys
 // only; scale 1/sqrt(hd)).  qkv [B*P, 3*D] fp32 (q | k | v), out [B*P, D] bf16.
-// One warp per (shape, head); lane i owns query row i (P <= 32, hd <= 64).
-__global__ void attention_kernel(const float* __restrict__ qkv, const unsigned char* __restrict__ valid,
-                                 int B, int P, int H, int hd, __nv_bfloat16* __restrict__ out) {
+// One warp per (shape, head): K (row-padded) and V staged in shared memory;
+// per query the 32 lanes first hold one key score each (softmax by shuffles),
+// then one (or two) output channels each.  P <= 32, hd <= 64.
+constexpr int ATT_WARPS = 2;
+__global__ void __launch_bounds__(ATT_WARPS * 32)
+attention_kernel(const float* __restrict__ qkv, const unsigned char* __restrict__ valid, int B, int P,
+                 int H, int hd, __nv_bfloat16* __restrict__ out) {
   extern __shared__ float sm[];
-  const int warps_per_block = blockDim.x >> 5;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int gw = blockIdx.x * warps_per_block + w;
-  float* ks = sm + (size_t)w * 2 * P * hd;
-  float* vs = ks + P * hd;
+  const int gw = blockIdx.x * ATT_WARPS + w;
   if (gw >= B * H) return;
+  const int ldk = hd + 1;
+  float* qs = sm + (size_t)w * (P * hd + P * ldk + P * hd);
+  float* ks = qs + P * hd;
+  float* vs = ks + P * ldk;
   const int b = gw / H, h = gw % H, D = H * hd;
   for (int i = lane; i < P * hd; i += 32) {
     const int p = i / hd, c = i % hd;
     const float* base = qkv + (long long)(b * P + p) * 3 * D + h * hd + c;
-    ks[i] = base[D];
+    qs[i] = base[0];
+    ks[p * ldk + c] = base[D];
     vs[i] = base[2 * D];
   }
   __syncwarp();
-  if (lane < P) {
-    const float* qp = qkv + (long long)(b * P + lane) * 3 * D + h * hd;
-    float q[64];
-    for (int c = 0; c < hd; ++c) q[c] = qp[c];
-    const float scale = rsqrtf((float)hd);
-    float sc[32];
-    float mx = -3.0e38f;
-    for (int j = 0; j < P; ++j) {
+  const bool key_ok = lane < P && (valid == nullptr || valid[b * P + lane] != 0);
+  const float scale = rsqrtf((float)hd);
+  for (int i = 0; i < P; ++i) {
+    float s = -3.0e38f;
+    if (key_ok) {
       float d = 0.f;
-      for (int c = 0; c < hd; ++c) d = fmaf(q[c], ks[j * hd + c], d);
-      const bool ok = valid == nullptr || valid[b * P + j] != 0;
-      sc[j] = ok ? d * scale : -3.0e38f;
-      mx = fmaxf(mx, sc[j]);
+      for (int c = 0; c < hd; ++c) d = fmaf(qs[i * hd + c], ks[lane * ldk + c], d);
+      s = d * scale;
     }
-    float den = 0.f;
-    for (int j = 0; j < P; ++j) {
-      const bool ok = valid == nullptr || valid[b * P + j] != 0;
-      sc[j] = ok ? __expf(sc[j] - mx) : 0.f;
-      den += sc[j];
-    }
+    float mx = s;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float e = key_ok ? __expf(s - mx) : 0.f;
+    float den = e;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
     // a shape without any valid key cannot occur (>= 1 valid part); guard anyway
-    const float inv = den > 0.f ? 1.f / den : 0.f;
-    __nv_bfloat16* op = out + (long long)(b * P + lane) * D + h * hd;
-    for (int c = 0; c < hd; ++c) {
-      float o = 0.f;
-      for (int j = 0; j < P; ++j) o = fmaf(sc[j], vs[j * hd + c], o);
-      op[c] = __float2bfloat16_rn(o * inv);
+    e = den > 0.f ? e / den : 0.f;
+    float o0 = 0.f, o1 = 0.f;
+    for (int j = 0; j < P; ++j) {
+      const float pj = __shfl_sync(0xffffffffu, e, j);
+      if (lane < hd) o0 = fmaf(pj, vs[j * hd + lane], o0);
+      if (lane + 32 < hd) o1 = fmaf(pj, vs[j * hd + lane + 32], o1);
     }
+    __nv_bfloat16* op = out + (long long)(b * P + i) * D + h * hd;
+    if (lane < hd) op[lane] = __float2bfloat16_rn(o0);
+    if (lane + 32 < hd) op[lane + 32] = __float2bfloat16_rn(o1);
   }
 }
 
@@ -374,8 +387,8 @@ int mpa_transformer_forward(const float* tokens, const unsigned char* valid, int
   MPA_CUDA(cudaGetLastError());
   MPA_CUDA(cudaMemcpyAsync(x, tokens, (size_t)T * D * 4, cudaMemcpyDeviceToDevice, stream));
   const int ln_blocks = (T * 32 + 255) / 256;
-  const int att_warps = 4;
-  const size_t att_smem = (size_t)att_warps * 2 * P * hd * sizeof(float);
+  const int att_warps = ATT_WARPS;
+  const size_t att_smem = (size_t)att_warps * (2 * P * hd + P * (hd + 1)) * sizeof(float);
   for (int l = 0; l < layers; ++l) {
     const __nv_bfloat16* wl = wts + (size_t)l * per_layer;
     { ProfScope ps("layernorm", stream);

@@ -255,15 +255,23 @@ __global__ void pointnet_finalize_kernel(const float* partial, int n_workers, in
                                          const float* gamma, const float* beta, float eps,
                                          float momentum, float* running_mean, float* running_var,
                                          float* scale, float* shift) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per channel; lanes stride over the workers (fixed order -> deterministic)
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
-  double s1 = 0.0, s2 = 0.0;
-  for (int w = 0; w < n_workers; ++w) {
+  double s1 = 0.0, s2 = 0.0, cnt = 0.0;
+  for (int w = lane; w < n_workers; w += 32) {
     s1 += (double)partial[((long long)w * PN_MAXC + c) * 2];
     s2 += (double)partial[((long long)w * PN_MAXC + c) * 2 + 1];
   }
-  double cnt = 0.0;
-  for (int p = 0; p < n_parts; ++p) cnt += (valids == nullptr || valids[p] != 0.0f) ? (double)N : 0.0;
+  for (int p = lane; p < n_parts; p += 32)
+    cnt += (valids == nullptr || valids[p] != 0.0f) ? (double)N : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if (lane != 0) return;
   const double mean = s1 / cnt;
   const double var = fmax(s2 / cnt - mean * mean, 0.0);
   const float sc = gamma[c] * (float)(1.0 / sqrt(var + (double)eps));
@@ -408,7 +416,7 @@ int mpa_pointnet_forward(const float* pts, const float* valids, int n_parts, int
       if (rc != MPA_OK) return rc;
       {
         ProfScope ps("pointnet_bn_finalize", stream);
-        pointnet_finalize_kernel<<<(C[layer] + 127) / 128, 128, 0, stream>>>(
+        pointnet_finalize_kernel<<<(C[layer] * 32 + 255) / 256, 256, 0, stream>>>(
             partial, n_workers, layer, C[layer], valids, n_parts, N, bn_gamma[layer], bn_beta[layer],
             eps, momentum, bn_running_mean[layer], bn_running_var[layer], scale, shift);
       }

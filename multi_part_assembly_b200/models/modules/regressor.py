@@ -48,5 +48,8 @@ class StocasticPoseRegressor(PoseRegressor):
         self.noise_dim = noise_dim
 
     def forward(self, x):
+        if self.noise_dim == 0:  # deterministic head (geometric configs): nothing to sample
+            return super().forward(x)
+        # CPU generator, like the reference (regressor.py:82), so seeds reproduce its samples
         noise = torch.randn(list(x.shape[:-1]) + [self.noise_dim]).type_as(x)
         return super().forward(torch.cat([x, noise], dim=-1))
