@@ -123,17 +123,24 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       const int col = n0 + j0 + lane;
       if (col < N) {
         const float bias = ep.bias ? __ldg(ep.bias + col) : 0.f;
-#pragma unroll 4
+        const int row0 = m0 + q * 32;
+        // residual may alias the output (x += f(x)): fetch the whole 32-row slab
+        // before the first store so the loads are not serialised behind stores
+        float res[32];
+#pragma unroll
+        for (int r = 0; r < 32; ++r)
+          res[r] = (ep.residual != nullptr && row0 + r < M) ? ep.residual[(long long)(row0 + r) * N + col] : 0.f;
+#pragma unroll
         for (int r = 0; r < 32; ++r) {
-          const int row = m0 + q * 32 + r;
-          if (row >= M) break;
-          float x = stage[r * 33 + lane] + bias;
-          if (ep.act == ACT_RELU) x = fmaxf(x, 0.f);
-          else if (ep.act == ACT_LEAKY02) x = x > 0.f ? x : 0.2f * x;
-          const long long o = (long long)row * N + col;
-          if (ep.residual) x += ep.residual[o];
-          if (ep.out_f32) ep.out_f32[o] = x;
-          if (ep.out_bf16) ep.out_bf16[o] = __float2bfloat16_rn(x);
+          if (row0 + r < M) {
+            float x = stage[r * 33 + lane] + bias;
+            if (ep.act == ACT_RELU) x = fmaxf(x, 0.f);
+            else if (ep.act == ACT_LEAKY02) x = x > 0.f ? x : 0.2f * x;
+            x += res[r];
+            const long long o = (long long)(row0 + r) * N + col;
+            if (ep.out_f32) ep.out_f32[o] = x;
+            if (ep.out_bf16) ep.out_bf16[o] = __float2bfloat16_rn(x);
+          }
         }
       }
       __syncwarp();
@@ -245,35 +252,38 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
 // One warp per (shape, head): K (row-padded) and V staged in shared memory;
 // per query the 32 lanes first hold one key score each (softmax by shuffles),
 // then one (or two) output channels each.  P <= 32, hd <= 64.
-constexpr int ATT_WARPS = 2;
+constexpr int ATT_WARPS = 4;
 __global__ void __launch_bounds__(ATT_WARPS * 32)
 attention_kernel(const float* __restrict__ qkv, const unsigned char* __restrict__ valid, int B, int P,
                  int H, int hd, __nv_bfloat16* __restrict__ out) {
   extern __shared__ float sm[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int gw = blockIdx.x * ATT_WARPS + w;
-  if (gw >= B * H) return;
+  const int gw = blockIdx.x;  // (shape, head)
   const int ldk = hd + 1;
-  float* qs = sm + (size_t)w * (P * hd + P * ldk + P * hd);
+  float* qs = sm;
   float* ks = qs + P * hd;
   float* vs = ks + P * ldk;
   const int b = gw / H, h = gw % H, D = H * hd;
-  for (int i = lane; i < P * hd; i += 32) {
+  for (int i = threadIdx.x; i < P * hd; i += ATT_WARPS * 32) {
     const int p = i / hd, c = i % hd;
     const float* base = qkv + (long long)(b * P + p) * 3 * D + h * hd + c;
     qs[i] = base[0];
     ks[p * ldk + c] = base[D];
     vs[i] = base[2 * D];
   }
-  __syncwarp();
+  __syncthreads();
   const bool key_ok = lane < P && (valid == nullptr || valid[b * P + lane] != 0);
   const float scale = rsqrtf((float)hd);
-  for (int i = 0; i < P; ++i) {
+  for (int i = w; i < P; i += ATT_WARPS) {
     float s = -3.0e38f;
     if (key_ok) {
-      float d = 0.f;
-      for (int c = 0; c < hd; ++c) d = fmaf(qs[i * hd + c], ks[lane * ldk + c], d);
-      s = d * scale;
+      float d0 = 0.f, d1 = 0.f;
+      for (int c = 0; c + 1 < hd; c += 2) {
+        d0 = fmaf(qs[i * hd + c], ks[lane * ldk + c], d0);
+        d1 = fmaf(qs[i * hd + c + 1], ks[lane * ldk + c + 1], d1);
+      }
+      if (hd & 1) d0 = fmaf(qs[i * hd + hd - 1], ks[lane * ldk + hd - 1], d0);
+      s = (d0 + d1) * scale;
     }
     float mx = s;
 #pragma unroll
@@ -293,6 +303,28 @@ attention_kernel(const float* __restrict__ qkv, const unsigned char* __restrict_
     __nv_bfloat16* op = out + (long long)(b * P + i) * D + h * hd;
     if (lane < hd) op[lane] = __float2bfloat16_rn(o0);
     if (lane + 32 < hd) op[lane + 32] = __float2bfloat16_rn(o1);
+  }
+}
+
+// several fp32 -> bf16 conversions in one launch (blockIdx.y selects the segment)
+struct CvtBatch {
+  const float* src[64];
+  __nv_bfloat16* dst[64];
+  long long n[64];
+};
+__global__ void f32_to_bf16_batch_kernel(CvtBatch cb) {
+  const float* __restrict__ in = cb.src[blockIdx.y];
+  __nv_bfloat16* __restrict__ o = cb.dst[blockIdx.y];
+  const long long n = cb.n[blockIdx.y];
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n;
+       i += (long long)gridDim.x * blockDim.x * 4) {
+    if (i + 3 < n) {
+      const float4 v = *reinterpret_cast<const float4*>(in + i);
+      *reinterpret_cast<__nv_bfloat162*>(o + i) = __floats2bfloat162_rn(v.x, v.y);
+      *reinterpret_cast<__nv_bfloat162*>(o + i + 2) = __floats2bfloat162_rn(v.z, v.w);
+    } else {
+      for (long long k = i; k < n; ++k) o[k] = __float2bfloat16_rn(in[k]);
+    }
   }
 }
 
@@ -372,23 +404,23 @@ int mpa_transformer_forward(const float* tokens, const unsigned char* valid, int
   __nv_bfloat16* att = (__nv_bfloat16*)p; p += align_up((size_t)T * D * 2, 256);
   __nv_bfloat16* hid = (__nv_bfloat16*)p;
 
+  MPA_CHECK_ARG(layers * 4 <= 64, "transformer_forward: at most 16 layers");
   {
     ProfScope ps("transformer_weights_to_bf16", stream);
+    CvtBatch cb;
     for (int l = 0; l < layers; ++l) {
       __nv_bfloat16* wl = wts + (size_t)l * per_layer;
-      f32_to_bf16_kernel<<<64, 256, 0, stream>>>(in_proj_w[l], wl, (long long)3 * D * D);
-      f32_to_bf16_kernel<<<64, 256, 0, stream>>>(out_proj_w[l], wl + (size_t)3 * D * D, (long long)D * D);
-      f32_to_bf16_kernel<<<64, 256, 0, stream>>>(lin1_w[l], wl + (size_t)4 * D * D, (long long)FF * D);
-      f32_to_bf16_kernel<<<64, 256, 0, stream>>>(lin2_w[l], wl + (size_t)4 * D * D + (size_t)FF * D,
-                                                 (long long)FF * D);
-      count_launch(4);
+      cb.src[4 * l + 0] = in_proj_w[l];  cb.dst[4 * l + 0] = wl;                         cb.n[4 * l + 0] = (long long)3 * D * D;
+      cb.src[4 * l + 1] = out_proj_w[l]; cb.dst[4 * l + 1] = wl + (size_t)3 * D * D;     cb.n[4 * l + 1] = (long long)D * D;
+      cb.src[4 * l + 2] = lin1_w[l];     cb.dst[4 * l + 2] = wl + (size_t)4 * D * D;     cb.n[4 * l + 2] = (long long)FF * D;
+      cb.src[4 * l + 3] = lin2_w[l];     cb.dst[4 * l + 3] = wl + (size_t)4 * D * D + (size_t)FF * D; cb.n[4 * l + 3] = (long long)FF * D;
     }
+    f32_to_bf16_batch_kernel<<<dim3(32, layers * 4), 256, 0, stream>>>(cb);
   }
-  MPA_CUDA(cudaGetLastError());
+  MPA_LAUNCH_CHECK();
   MPA_CUDA(cudaMemcpyAsync(x, tokens, (size_t)T * D * 4, cudaMemcpyDeviceToDevice, stream));
   const int ln_blocks = (T * 32 + 255) / 256;
-  const int att_warps = ATT_WARPS;
-  const size_t att_smem = (size_t)att_warps * (2 * P * hd + P * (hd + 1)) * sizeof(float);
+  const size_t att_smem = (size_t)(2 * P * hd + P * (hd + 1)) * sizeof(float);
   for (int l = 0; l < layers; ++l) {
     const __nv_bfloat16* wl = wts + (size_t)l * per_layer;
     { ProfScope ps("layernorm", stream);
@@ -398,7 +430,7 @@ int mpa_transformer_forward(const float* tokens, const unsigned char* valid, int
     rc = launch_linear(xn, wl, T, 3 * D, D, e_qkv, "linear_qkv", stream);
     if (rc != MPA_OK) return rc;
     { ProfScope ps("attention", stream);
-      attention_kernel<<<(B * H + att_warps - 1) / att_warps, att_warps * 32, att_smem, stream>>>(
+      attention_kernel<<<B * H, ATT_WARPS * 32, att_smem, stream>>>(
           qkv, valid, B, P, H, hd, att); }
     MPA_LAUNCH_CHECK();
     LinearEpilogue e_o{out_proj_b[l], x, x, nullptr, ACT_NONE};
