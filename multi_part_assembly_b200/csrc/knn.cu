@@ -1,0 +1,272 @@
+// k-nearest-neighbour graph and EdgeConv aggregation of the DGCNN part encoder.
+//
+// knn: replaces `knn` (models/modules/encoder/dgcnn.py:8-15): for every point
+// the k highest scores  -|x_i|^2 + 2 x_i.x_j - |x_j|^2  (self included), in
+// the reference's expanded form.  The reference materialises the [n, N, N]
+// score tensor with a batched cuBLAS SGEMM and runs a radix-select topk over
+// it; here a CTA owns 32 (or 16) query rows of one part, streams the
+// candidates through a register-tiled fp32 contraction (sequential-k FMA, the
+// oracle's order -> bit-exact scores), keeps the score rows in shared memory
+// and extracts the top k there.  Nothing of size N x N touches HBM.
+//
+// edge_aggregate: replaces get_graph_feature + 1x1 Conv2d + max over k
+// (dgcnn.py:18-38, 81-95) after the algebraic split
+//     W [x_j - x_i ; x_i] = W1 x_j + (W2 - W1) x_i = u_j + v_i,
+// so the [n, 2C, N, k] edge tensor (10+ GB at n=512, C=128) never exists: per
+// point it gathers the k neighbours' u rows (coalesced along channels), and
+// keeps max, min, sum and sum of squares of u_j + v_i -- what BatchNorm2d
+// (batch statistics over n*N*k edges) + LeakyReLU + max-over-k need.
+#include "mpa_common.cuh"
+
+namespace mpa {
+
+constexpr int KNN_THREADS = 256;
+constexpr int KNN_BN = 128;   // candidates per block
+constexpr int KNN_KC = 32;    // channels per chunk
+
+__global__ void sqnorm_kernel(const float* __restrict__ x, long long rows, int C, float* __restrict__ xx) {
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows;
+       r += (long long)gridDim.x * blockDim.x) {
+    const float* p = x + r * C;
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s = __fmaf_rn(p[c], p[c], s);
+    xx[r] = s;
+  }
+}
+
+// x [n, N, C] row-major, xx [n, N]; idx [n, N, k] int32 (best first; ties -> lower index)
+template <int ROWS>
+__global__ void __launch_bounds__(KNN_THREADS)
+knn_kernel(const float* __restrict__ x, const float* __restrict__ xx, int N, int C, int k,
+           int* __restrict__ idx) {
+  extern __shared__ float sm[];
+  const int Cp = ((C + 3) & ~3) + 4;           // padded query row stride
+  float* As = sm;                               // [ROWS][Cp]
+  float* Bs = As + ROWS * Cp;                   // [KNN_BN][KNN_KC + 4]
+  float* S = Bs + KNN_BN * (KNN_KC + 4);        // [ROWS][Np]
+  const int Np = (N + KNN_BN - 1) / KNN_BN * KNN_BN;
+  const int tiles = (N + ROWS - 1) / ROWS;
+  const int part = blockIdx.x / tiles, i0 = (blockIdx.x % tiles) * ROWS;
+  const float* xp = x + (long long)part * N * C;
+  const float* xxp = xx + (long long)part * N;
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  constexpr int RPT = ROWS / 8;                 // rows per thread (8 warps)
+  const float ninf = -__int_as_float(0x7f800000);
+
+  for (int e = tid; e < ROWS * Cp; e += KNN_THREADS) {
+    const int r = e / Cp, c = e % Cp;
+    As[e] = (i0 + r < N && c < C) ? xp[(long long)(i0 + r) * C + c] : 0.f;
+  }
+  for (int j0 = 0; j0 < N; j0 += KNN_BN) {
+    float acc[RPT][4];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+    for (int kc = 0; kc < C; kc += KNN_KC) {
+      __syncthreads();
+      for (int e = tid; e < KNN_BN * KNN_KC; e += KNN_THREADS) {
+        const int col = e / KNN_KC, kk = e % KNN_KC;
+        Bs[col * (KNN_KC + 4) + kk] =
+            (j0 + col < N && kc + kk < C) ? xp[(long long)(j0 + col) * C + kc + kk] : 0.f;
+      }
+      __syncthreads();
+      const int klen = min(KNN_KC, ((C - kc) + 3) & ~3);
+      for (int kk = 0; kk < klen; kk += 4) {
+        float4 a[RPT], b[4];
+#pragma unroll
+        for (int r = 0; r < RPT; ++r)
+          a[r] = *reinterpret_cast<const float4*>(&As[(ty * RPT + r) * Cp + kc + kk]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          b[c] = *reinterpret_cast<const float4*>(&Bs[(tx + 32 * c) * (KNN_KC + 4) + kk]);
+#pragma unroll
+        for (int r = 0; r < RPT; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {  // ascending k, one accumulator: the oracle's order
+            float d = acc[r][c];
+            d = __fmaf_rn(a[r].x, b[c].x, d);
+            d = __fmaf_rn(a[r].y, b[c].y, d);
+            d = __fmaf_rn(a[r].z, b[c].z, d);
+            d = __fmaf_rn(a[r].w, b[c].w, d);
+            acc[r][c] = d;
+          }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      const int row = ty * RPT + r;
+      const float xi = (i0 + row < N) ? xxp[i0 + row] : 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int j = j0 + tx + 32 * c;
+        float s = ninf;
+        if (j < N) {
+          const float inner = __fmul_rn(-2.0f, acc[r][c]);          // dgcnn.py:10
+          s = __fsub_rn(__fsub_rn(-xxp[j], inner), xi);             // dgcnn.py:12
+        }
+        S[row * Np + j] = s;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- top-k per row: each lane caches the best of its strided slice ----
+  for (int row = ty; row < ROWS; row += 8) {
+    if (i0 + row >= N) break;
+    float* Sr = S + row * Np;
+    float best = ninf;
+    int barg = 0x7fffffff;
+    for (int j = tx; j < N; j += 32)
+      if (Sr[j] > best) { best = Sr[j]; barg = j; }
+    int* out = idx + ((long long)part * N + i0 + row) * k;
+    for (int s = 0; s < k; ++s) {
+      float v = best;
+      int a = barg;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, a, o);
+        if (ov > v || (ov == v && oa < a)) { v = ov; a = oa; }
+      }
+      if (tx == 0) out[s] = a;
+      if ((a & 31) == tx && a < N) {  // owner lane: remove and rescan its slice
+        Sr[a] = ninf;
+        best = ninf; barg = 0x7fffffff;
+        for (int j = tx; j < N; j += 32)
+          if (Sr[j] > best) { best = Sr[j]; barg = j; }
+      }
+    }
+  }
+}
+
+// uv [M, 2*Co] (u | v), idx [M, k] (indices local to the part), M = n*N.
+// One CTA per PTS points, thread = channel.  ymax/ymin [M, Co]; partial [gridDim, Co, 2].
+constexpr int EC_PTS = 8;
+__global__ void edge_aggregate_kernel(const float* __restrict__ uv, const int* __restrict__ idx, long long M,
+                                      int N, int Co, int k, float* __restrict__ ymax,
+                                      float* __restrict__ ymin, float* __restrict__ partial) {
+  extern __shared__ int sidx[];  // [EC_PTS][k]
+  const long long p0 = (long long)blockIdx.x * EC_PTS;
+  for (int e = threadIdx.x; e < EC_PTS * k; e += blockDim.x) {
+    const long long p = p0 + e / k;
+    sidx[e] = p < M ? idx[p * k + e % k] : 0;
+  }
+  __syncthreads();
+  const int c = threadIdx.x;
+  float s1 = 0.f, s2 = 0.f;
+  if (c < Co) {
+    for (int q = 0; q < EC_PTS; ++q) {
+      const long long p = p0 + q;
+      if (p >= M) break;
+      const long long base = p / N * N;  // first point of this part
+      const float v = uv[p * 2 * Co + Co + c];
+      float mx = -3.0e38f, mn = 3.0e38f;
+      for (int e = 0; e < k; ++e) {
+        const float y = uv[(base + sidx[q * k + e]) * 2 * Co + c] + v;
+        mx = fmaxf(mx, y); mn = fminf(mn, y);
+        s1 += y; s2 = fmaf(y, y, s2);
+      }
+      ymax[p * Co + c] = mx;
+      ymin[p * Co + c] = mn;
+    }
+    partial[((long long)blockIdx.x * Co + c) * 2] = s1;
+    partial[((long long)blockIdx.x * Co + c) * 2 + 1] = s2;
+  }
+}
+
+// deterministic column sums of partial [rows, Co, 2] -> sums [Co, 2] (double accumulate)
+__global__ void column_sum_kernel(const float* __restrict__ partial, long long rows, int Co,
+                                  double* __restrict__ sums) {
+  const int c = blockIdx.x, lane = threadIdx.x;  // one warp per channel
+  double s1 = 0, s2 = 0;
+  for (long long r = lane; r < rows; r += 32) {
+    s1 += (double)partial[(r * Co + c) * 2];
+    s2 += (double)partial[(r * Co + c) * 2 + 1];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if (lane == 0) { sums[2 * c] = s1; sums[2 * c + 1] = s2; }
+}
+
+}  // namespace mpa
+
+using namespace mpa;
+
+extern "C" {
+
+size_t mpa_knn_workspace_bytes(int n, int N) { return align_up(sizeof(float) * (size_t)n * N, 256); }
+
+int mpa_knn(const float* x, int n, int N, int C, int k, int32_t* idx, void* ws, size_t ws_bytes,
+            void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MPA_CHECK_ARG(n >= 0 && N > 0 && C > 0 && k > 0, "knn: bad sizes n=%d N=%d C=%d k=%d", n, N, C, k);
+  MPA_CHECK_ARG(k <= N, "knn: k=%d exceeds the %d points of a part", k, N);
+  MPA_CHECK_ARG(N <= 2048 && C <= 512, "knn: supports N <= 2048 points and C <= 512 channels");
+  if (n == 0) return MPA_OK;
+  MPA_CHECK_ARG(x && idx, "knn: null pointer");
+  Scratch scratch;
+  int rc = scratch.acquire(ws, ws_bytes, mpa_knn_workspace_bytes(n, N), stream);
+  if (rc != MPA_OK) return rc;
+  float* xx = (float*)scratch.base;
+  {
+    ProfScope ps("knn_sqnorm", stream);
+    sqnorm_kernel<<<592, 256, 0, stream>>>(x, (long long)n * N, C, xx);
+  }
+  MPA_LAUNCH_CHECK();
+  const int rows = N <= 1024 ? 32 : 16;
+  const int Cp = ((C + 3) & ~3) + 4;
+  const int Np = (N + KNN_BN - 1) / KNN_BN * KNN_BN;
+  const size_t smem = sizeof(float) * ((size_t)rows * Cp + KNN_BN * (KNN_KC + 4) + (size_t)rows * Np);
+  const int tiles = (N + rows - 1) / rows;
+  static bool attr = false;
+  if (!attr) {
+    MPA_CUDA(cudaFuncSetAttribute(knn_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MPA_CUDA(cudaFuncSetAttribute(knn_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  MPA_CHECK_ARG(smem <= 227 * 1024, "knn: shared memory need %zu exceeds 227 KB", smem);
+  {
+    ProfScope ps("knn", stream);
+    if (rows == 32) knn_kernel<32><<<n * tiles, KNN_THREADS, smem, stream>>>(x, xx, N, C, k, idx);
+    else knn_kernel<16><<<n * tiles, KNN_THREADS, smem, stream>>>(x, xx, N, C, k, idx);
+  }
+  MPA_LAUNCH_CHECK();
+  return MPA_OK;
+}
+
+size_t mpa_edge_aggregate_workspace_bytes(long long M, int Co) {
+  const long long blocks = (M + EC_PTS - 1) / EC_PTS;
+  return align_up(sizeof(float) * 2 * (size_t)blocks * Co, 256);
+}
+
+int mpa_edge_aggregate(const float* uv, const int32_t* idx, int n, int N, int Co, int k, float* ymax,
+                       float* ymin, double* sums, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MPA_CHECK_ARG(n >= 0 && N > 0 && Co > 0 && Co <= 1024 && k > 0, "edge_aggregate: bad sizes");
+  if (n == 0) return MPA_OK;
+  MPA_CHECK_ARG(uv && idx && ymax && ymin && sums, "edge_aggregate: null pointer");
+  const long long M = (long long)n * N;
+  const long long blocks = (M + EC_PTS - 1) / EC_PTS;
+  Scratch scratch;
+  int rc = scratch.acquire(ws, ws_bytes, mpa_edge_aggregate_workspace_bytes(M, Co), stream);
+  if (rc != MPA_OK) return rc;
+  float* partial = (float*)scratch.base;
+  const int threads = (Co + 31) / 32 * 32;
+  {
+    ProfScope ps("edge_aggregate", stream);
+    edge_aggregate_kernel<<<(unsigned)blocks, threads, sizeof(int) * EC_PTS * k, stream>>>(
+        uv, idx, M, N, Co, k, ymax, ymin, partial);
+  }
+  MPA_LAUNCH_CHECK();
+  {
+    ProfScope ps("edge_column_sum", stream);
+    column_sum_kernel<<<Co, 32, 0, stream>>>(partial, blocks, Co, sums);
+  }
+  MPA_LAUNCH_CHECK();
+  return MPA_OK;
+}
+
+}  // extern "C"

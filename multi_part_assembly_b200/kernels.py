@@ -163,6 +163,123 @@ def pointnet_forward(x, convs, bns, training, global_feat=True, valids=None):
 # ---------------------------------------------------------------------------
 # DGCNN
 # ---------------------------------------------------------------------------
+def knn(x, k=20):
+    """x [n, N, C] (points as rows) -> idx [n, N, k] int32, best first
+    (replaces dgcnn.py:8-15; native kernel csrc/knn.cu)."""
+    _lib.require_cuda(x)
+    x = x.float().contiguous()
+    n, N, C = x.shape
+    idx = torch.empty(n, N, k, dtype=torch.int32, device=x.device)
+    L = _lib.lib()
+    ws_bytes = L.mpa_knn_workspace_bytes(n, N)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = L.mpa_knn(_lib.ptr(x), n, N, C, k, _lib.ptr(idx), _lib.ptr(ws), ws_bytes,
+                       _lib.cuda_stream(x.device))
+    _lib.check(rc, 'mpa_knn')
+    return idx
+
+
+def edge_aggregate(uv, idx, n, N, Co, k):
+    """uv [n*N, 2*Co], idx [n, N, k] -> ymax, ymin [n*N, Co], sums [Co, 2] (fp64)."""
+    dev = uv.device
+    ymax = torch.empty(n * N, Co, dtype=torch.float32, device=dev)
+    ymin = torch.empty_like(ymax)
+    sums = torch.empty(Co, 2, dtype=torch.float64, device=dev)
+    L = _lib.lib()
+    ws_bytes = L.mpa_edge_aggregate_workspace_bytes(n * N, Co)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.mpa_edge_aggregate(_lib.ptr(uv), _lib.ptr(idx), n, N, Co, k, _lib.ptr(ymax),
+                                  _lib.ptr(ymin), _lib.ptr(sums), _lib.ptr(ws), ws_bytes,
+                                  _lib.cuda_stream(dev))
+    _lib.check(rc, 'mpa_edge_aggregate')
+    return ymax, ymin, sums
+
+
+def linear(x, w, bias=None, act=0, residual=None):
+    """act(x @ w.T + bias) (+ residual) on the tcgen05 kernel (bf16 operands)."""
+    M, K = x.shape
+    N = w.shape[0]
+    if K % 8:
+        pad = 8 - K % 8
+        x = F.pad(x, (0, pad))
+        w = F.pad(w, (0, pad))
+        K += pad
+    x = x.float().contiguous()
+    w = w.float().contiguous()
+    out = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    L = _lib.lib()
+    ws_bytes = L.mpa_linear_workspace_bytes(M, N, K)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = L.mpa_linear_forward(_lib.ptr(x), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(residual), M,
+                                  N, K, act, _lib.ptr(out), _lib.ptr(ws), ws_bytes,
+                                  _lib.cuda_stream(x.device))
+    _lib.check(rc, 'mpa_linear_forward')
+    return out
+
+
+def _dense(x, w, bf16):
+    if bf16:
+        return linear(x, w)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        return x @ w.t()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def _bn_affine(bn, mean, var_biased, count, training):
+    """scale/shift of a BatchNorm from batch moments (training: also updates the
+    running statistics like torch, unbiased variance) or running statistics."""
+    if training:
+        with torch.no_grad():
+            m = bn.momentum
+            bn.running_mean.mul_(1 - m).add_(mean.float(), alpha=m)
+            bn.running_var.mul_(1 - m).add_((var_biased * (count / max(count - 1, 1))).float(), alpha=m)
+            bn.num_batches_tracked += 1
+    else:
+        mean, var_biased = bn.running_mean.double(), bn.running_var.double()
+    scale = bn.weight.double() / torch.sqrt(var_biased + bn.eps)
+    return scale.float(), (bn.bias.double() - mean * scale).float()
+
+
+def _dgcnn_native(x, m, training, k, bf16):
+    n, N, _ = x.shape
+    M = n * N
+    h = x.reshape(M, 3).float()
+    feats = []
+    for conv, bn in ((m.conv1, m.bn1), (m.conv2, m.bn2), (m.conv3, m.bn3), (m.conv4, m.bn4)):
+        C = h.shape[1]
+        W = conv[0].weight.reshape(conv[0].weight.shape[0], 2 * C).float()
+        Co = W.shape[0]
+        idx = knn(h.view(n, N, C), k)
+        # W [xj - xi ; xi] = W1 xj + (W2 - W1) xi
+        wcat = torch.cat([W[:, :C], W[:, C:] - W[:, :C]], dim=0)
+        uv = _dense(h, wcat, bf16)
+        ymax, ymin, sums = edge_aggregate(uv, idx, n, N, Co, k)
+        cnt = M * k
+        mean = sums[:, 0] / cnt
+        var = (sums[:, 1] / cnt - mean * mean).clamp_min(0)
+        scale, shift = _bn_affine(bn, mean, var, cnt, training)
+        h = F.leaky_relu(torch.where(scale >= 0, ymax, ymin) * scale + shift, 0.2)
+        feats.append(h)
+    y = _dense(torch.cat(feats, dim=1), m.conv5[0].weight.reshape(m.conv5[0].weight.shape[0], -1).float(), bf16)
+    if training:
+        var, mean = torch.var_mean(y.double(), dim=0, unbiased=False)
+    else:
+        mean = var = None
+    scale, shift = _bn_affine(m.bn5, mean, var, M, training)
+    y = F.leaky_relu(y * scale + shift, 0.2)
+    if not m.global_feat:
+        return y.view(n, N, -1)
+    y = y.view(n, N, -1)
+    g = torch.cat((y.max(dim=1)[0], y.mean(dim=1)), 1)
+    return F.linear(g, m.out_fc.weight, m.out_fc.bias)
+
+
 def _graph_feature(x, k):
     n, C, N = x.shape
     inner = -2 * torch.matmul(x.transpose(2, 1), x)
@@ -174,9 +291,8 @@ def _graph_feature(x, k):
     return torch.cat((nbr - ctr, ctr), dim=3).permute(0, 3, 1, 2).contiguous()
 
 
-def dgcnn_forward(x, m, training, k=20):
-    """x [n, N, 3] -> [n, F] / [n, N, F]; `m` is the DGCNN module."""
-    _lib.require_cuda(x)
+def _dgcnn_torch(x, m, k):
+    """Stock-op formulation (dgcnn.py:77-109), used to differentiate the native forward."""
     h = x.transpose(2, 1).contiguous()
     feats = []
     for conv in (m.conv1, m.conv2, m.conv3, m.conv4):
@@ -187,6 +303,41 @@ def dgcnn_forward(x, m, training, k=20):
         return h.transpose(2, 1).contiguous()
     g = torch.cat((h.max(dim=-1)[0], h.mean(dim=-1)), 1)
     return m.out_fc(g)
+
+
+class _DGCNNFunction(torch.autograd.Function):
+    """Forward: native k-NN + EdgeConv kernels.  Backward (outside the round-1
+    fwd+loss scope): re-runs the stock formulation with autograd; BatchNorm
+    buffers are restored so the running statistics advance only once."""
+
+    @staticmethod
+    def forward(ctx, x, m, training, k, bf16, *params):
+        out = _dgcnn_native(x, m, training, k, bf16)
+        ctx.save_for_backward(x)
+        ctx.m, ctx.k = m, k
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        (x, ) = ctx.saved_tensors
+        m = ctx.m
+        buffers = {n_: b.clone() for n_, b in m.named_buffers()}
+        params = [p for p in m.parameters()]
+        with torch.enable_grad():
+            out = _dgcnn_torch(x.detach(), m, ctx.k)
+            grads = torch.autograd.grad(out, params, grad, allow_unused=True)
+        with torch.no_grad():
+            for n_, b in m.named_buffers():
+                b.copy_(buffers[n_])
+        return (None, None, None, None, None) + tuple(grads)
+
+
+def dgcnn_forward(x, m, training, k=20):
+    """x [n, N, 3] -> [n, F] / [n, N, F]; `m` is the DGCNN module."""
+    _lib.require_cuda(x)
+    params = [p for p in m.parameters()]
+    with torch.autocast('cuda', enabled=False):
+        return _DGCNNFunction.apply(x.float().contiguous(), m, training, k, _use_bf16(), *params)
 
 
 # ---------------------------------------------------------------------------

@@ -152,7 +152,7 @@ void oracle_se3_transform(const float* quat, const float* trans,
  * the reference passes it): score(i,j) = -|xi|^2 + 2 xi.xj - |xj|^2 in the
  * expanded form, top-k largest (self included).  The reference's matmul
  * accumulation order and topk tie order are unspecified, so the oracle fixes
- * them: sequential-c fp32 dot product, selection by (score desc, index asc),
+ * them: sequential-c fp32 FMA dot product, selection by (score desc, index asc),
  * and the parity contract is the SORTED index set per row.
  * out_idx: [n, N, k] int64, ascending index order within a row. */
 static int cmp_i64(const void* a, const void* b) {
@@ -171,7 +171,7 @@ void oracle_knn(const float* x, int64_t n, int64_t C, int64_t N, int64_t k,
       const float* xb = x + b * C * N;
       for (int64_t j = 0; j < N; ++j) {
         float s = 0.0f;
-        for (int64_t c = 0; c < C; ++c) s += xb[c * N + j] * xb[c * N + j];
+        for (int64_t c = 0; c < C; ++c) s = fmaf(xb[c * N + j], xb[c * N + j], s);
         xx[j] = s;
       }
       for (int64_t i = 0; i < N; ++i) {
@@ -180,7 +180,7 @@ void oracle_knn(const float* x, int64_t n, int64_t C, int64_t N, int64_t k,
          * evaluated in the order written: (-xx_j - inner) - xx_i. */
         for (int64_t j = 0; j < N; ++j) {
           float dot = 0.0f;
-          for (int64_t c = 0; c < C; ++c) dot += xb[c * N + i] * xb[c * N + j];
+          for (int64_t c = 0; c < C; ++c) dot = fmaf(xb[c * N + i], xb[c * N + j], dot);
           float inner = -2.0f * dot;
           score[j] = (-xx[j] - inner) - xx[i];
         }

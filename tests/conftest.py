@@ -17,4 +17,8 @@ def cuda():
     import torch
     if not torch.cuda.is_available():
         pytest.skip('no CUDA device')
+    # parity is judged against the fp32 CPU reference: stock torch layers that are
+    # not on the native path (DGL's GNN MLPs, pose heads) must not silently use TF32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     return torch.device('cuda:0')
