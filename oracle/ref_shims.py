@@ -23,8 +23,8 @@ import torch
 REFERENCE_ROOT = '/root/reference'
 
 
-def available():
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, 'multi_part_assembly'))
+def available(root=None):
+    return os.path.isdir(os.path.join(root or REFERENCE_ROOT, 'multi_part_assembly'))
 
 
 def _stub(name, **attrs):
@@ -35,8 +35,16 @@ def _stub(name, **attrs):
     return m
 
 
-def install():
-    """Returns the imported reference package `multi_part_assembly`."""
+def install(root=None, cuda_chamfer=False):
+    """Returns the imported reference package `multi_part_assembly`.
+
+    root: directory holding the package (default /root/reference; the GPU
+    baseline tool passes baseline/_ref, the pip-installed unmodified copy).
+    cuda_chamfer: use the reference's own compiled `chamfer_cuda` extension
+    (must be importable) instead of the CPU oracle stand-in."""
+    global REFERENCE_ROOT
+    if root is not None:
+        REFERENCE_ROOT = root
     if not available():
         raise RuntimeError('reference tree not present')
     if 'multi_part_assembly' in sys.modules and \
@@ -82,7 +90,8 @@ def install():
                                     xyz2.detach().numpy(), idx1.numpy(), idx2.numpy())
         return [torch.from_numpy(a), torch.from_numpy(b)]
 
-    _stub('chamfer_cuda', chamfer_forward=chamfer_forward, chamfer_backward=chamfer_backward)
+    if not cuda_chamfer:
+        _stub('chamfer_cuda', chamfer_forward=chamfer_forward, chamfer_backward=chamfer_backward)
 
     class _Missing:
 
@@ -102,8 +111,9 @@ def install():
     assert ref.__file__.startswith(REFERENCE_ROOT)
     # the reference asserts .is_cuda in its autograd Function (chamfer.py:18);
     # swap in the CPU oracle Function (same forward/backward arithmetic)
-    ch = importlib.import_module('multi_part_assembly.utils.chamfer.chamfer')
-    ch.ChamferDistanceFunction = torch_ref._Chamfer
+    if not cuda_chamfer:
+        ch = importlib.import_module('multi_part_assembly.utils.chamfer.chamfer')
+        ch.ChamferDistanceFunction = torch_ref._Chamfer
     return ref
 
 
