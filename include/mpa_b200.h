@@ -131,6 +131,22 @@ int mpa_pose_chamfer_backward(const float* grad_dist1, const float* grad_dist2, 
                               float* grad_trans1, float* grad_quat2, float* grad_trans2, void* ws,
                               size_t ws_bytes, void* stream);
 
+/* Fused reductions of the geometric loss terms as BaseModel._calc_loss assembles
+ * them (models/modules/base_model.py:256-290; utils/loss.py:22-35, 59-86, 89-110,
+ * 131-134, 185-198), forward only.  part_dist{1,2} and shape_dist{1,2} [B,P,N] are the
+ * outputs of mpa_pose_chamfer in PART / SHAPE mode (0 on padded parts).
+ * weights (DEVICE pointer, 5 floats) = {trans_loss_w, rot_pt_cd_loss_w, transform_pt_cd_loss_w, rot_loss_w,
+ * rot_pt_l2_loss_w} (0 for a disabled term).  terms [6,B] = trans_loss,
+ * rot_pt_cd_loss, transform_pt_cd_loss, rot_loss, rot_pt_l2_loss, weighted total.
+ * training: shape_cd_loss divides by P*N (:185-193), else per-part means (:195-198). */
+size_t mpa_geometric_losses_workspace_bytes(int B, int P);
+int mpa_geometric_losses(const float* pts, const float* quat1, const float* trans1,
+                         const float* quat2, const float* trans2, const float* valids,
+                         const float* part_dist1, const float* part_dist2,
+                         const float* shape_dist1, const float* shape_dist2, int B, int P, int N,
+                         int training, int want_rot_l2, const float* weights, float* terms,
+                         void* ws, size_t ws_bytes, void* stream);
+
 /* ---- PointNet part encoder --------------------------------------------- */
 /* Replaces PointNet.forward with global_feat=True (models/modules/encoder/
  * pointnet.py:29-41) fused with the valid-part selection of _extract_part_feats

@@ -1,0 +1,135 @@
+// Fused reductions of the geometric loss terms (utils/loss.py:7-202 as assembled
+// by BaseModel._calc_loss, models/modules/base_model.py:256-290): one launch for
+// the per-part sums (incl. rot_points_l2_loss, which re-rotates the part twice
+// in the reference) and one for the per-shape terms, instead of ~60 elementwise
+// / reduction kernels.  Forward only (used when autograd is not recording).
+#include "mpa_common.cuh"
+
+namespace mpa {
+
+// per part: sum of part-level dist1, dist2, shape-level dist1, dist2, and
+// sum_i |R1 v_i - R2 v_i|^2.  out [B*P, 5].  One CTA per part.
+__global__ void __launch_bounds__(256)
+loss_part_sums_kernel(const float* __restrict__ pts, const float* __restrict__ q1,
+                      const float* __restrict__ q2, const float* __restrict__ pd1,
+                      const float* __restrict__ pd2, const float* __restrict__ sd1,
+                      const float* __restrict__ sd2, int N, int want_l2, float* __restrict__ out) {
+  __shared__ float red[5][8];
+  const int part = blockIdx.x;
+  float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  float a[4], b[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { a[c] = q1[4 * part + c]; b[c] = q2[4 * part + c]; }
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const long long o = (long long)part * N + i;
+    acc[0] += pd1[o]; acc[1] += pd2[o]; acc[2] += sd1[o]; acc[3] += sd2[o];
+    if (want_l2) {
+      const float3 v = make_float3(pts[3 * o], pts[3 * o + 1], pts[3 * o + 2]);
+      const float3 r1 = se3_apply(a, nullptr, v), r2 = se3_apply(b, nullptr, v);
+      const float dx = r1.x - r2.x, dy = r1.y - r2.y, dz = r1.z - r2.z;
+      acc[4] += dx * dx + dy * dy + dz * dz;
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    float v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) red[k][wid] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    float v = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[threadIdx.x][w];
+    out[(long long)part * 5 + threadIdx.x] = v;
+  }
+}
+
+// per shape: the five loss terms and their weighted total.  One warp per shape.
+// terms [6, B]: trans, rot_pt_cd, transform_pt_cd, rot (cosine), rot_pt_l2, total
+__global__ void loss_shape_terms_kernel(const float* __restrict__ sums, const float* __restrict__ q1,
+                                        const float* __restrict__ t1, const float* __restrict__ q2,
+                                        const float* __restrict__ t2, const float* __restrict__ valids,
+                                        int B, int P, int N, int training,
+                                        const float* __restrict__ weights,  // device [5]
+                                        float* __restrict__ terms) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (b >= B) return;
+  float nv = 0.f, tr = 0.f, cd = 0.f, cs = 0.f, l2 = 0.f, sh_train = 0.f, sh_eval = 0.f;
+  for (int p = lane; p < P; p += 32) {
+    const int g = b * P + p;
+    const float v = valids[g];
+    const float* s = sums + (long long)g * 5;
+    float d = 0.f, dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { const float e = t1[3 * g + c] - t2[3 * g + c]; d += e * e; }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) dot += q1[4 * g + c] * q2[4 * g + c];
+    nv += v;
+    tr += d * v;                                   // trans_l2_loss (loss.py:22-35)
+    cs += (1.f - fabsf(dot)) * v;                  // rot_cosine_loss (:59-86)
+    cd += (s[0] / N + s[1] / N) * v;               // rot_points_cd_loss (:131-134)
+    l2 += (s[4] / N) * v;                          // rot_points_l2_loss (:105-106)
+    sh_train += s[2] + s[3];                       // shape_cd_loss training (:185-193): padded dist is 0
+    sh_eval += ((s[2] + s[3]) / N) * v;            // shape_cd_loss eval (:195-198)
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    nv += __shfl_xor_sync(0xffffffffu, nv, o); tr += __shfl_xor_sync(0xffffffffu, tr, o);
+    cs += __shfl_xor_sync(0xffffffffu, cs, o); cd += __shfl_xor_sync(0xffffffffu, cd, o);
+    l2 += __shfl_xor_sync(0xffffffffu, l2, o); sh_train += __shfl_xor_sync(0xffffffffu, sh_train, o);
+    sh_eval += __shfl_xor_sync(0xffffffffu, sh_eval, o);
+  }
+  if (lane == 0) {
+    const float L_trans = tr / nv, L_cd = cd / nv, L_rot = cs / nv, L_l2 = l2 / nv;
+    const float L_shape = training ? sh_train / (float)(P * N) : sh_eval / nv;
+    terms[0 * B + b] = L_trans;
+    terms[1 * B + b] = L_cd;
+    terms[2 * B + b] = L_shape;
+    terms[3 * B + b] = L_rot;
+    terms[4 * B + b] = L_l2;
+    terms[5 * B + b] = weights[0] * L_trans + weights[1] * L_cd + weights[2] * L_shape +
+                       weights[3] * L_rot + weights[4] * L_l2;
+  }
+}
+
+}  // namespace mpa
+
+using namespace mpa;
+
+extern "C" {
+
+int mpa_geometric_losses(const float* pts, const float* quat1, const float* trans1, const float* quat2,
+                         const float* trans2, const float* valids, const float* part_dist1,
+                         const float* part_dist2, const float* shape_dist1, const float* shape_dist2,
+                         int B, int P, int N, int training, int want_rot_l2, const float* weights,
+                         float* terms, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MPA_CHECK_ARG(B >= 0 && P > 0 && N > 0, "geometric_losses: bad sizes");
+  if (B == 0) return MPA_OK;
+  MPA_CHECK_ARG(pts && quat1 && trans1 && quat2 && trans2 && valids && part_dist1 && part_dist2 &&
+                    shape_dist1 && shape_dist2 && weights && terms,
+                "geometric_losses: null pointer");
+  Scratch scratch;
+  int rc = scratch.acquire(ws, ws_bytes, sizeof(float) * 5 * (size_t)B * P, stream);
+  if (rc != MPA_OK) return rc;
+  float* sums = (float*)scratch.base;
+  {
+    ProfScope ps("loss_part_sums", stream);
+    loss_part_sums_kernel<<<B * P, 256, 0, stream>>>(pts, quat1, quat2, part_dist1, part_dist2,
+                                                     shape_dist1, shape_dist2, N, want_rot_l2, sums);
+  }
+  MPA_LAUNCH_CHECK();
+  {
+    ProfScope ps("loss_shape_terms", stream);
+    loss_shape_terms_kernel<<<(B * 32 + 127) / 128, 128, 0, stream>>>(
+        sums, quat1, trans1, quat2, trans2, valids, B, P, N, training, weights, terms);
+  }
+  MPA_LAUNCH_CHECK();
+  return MPA_OK;
+}
+
+size_t mpa_geometric_losses_workspace_bytes(int B, int P) { return sizeof(float) * 5 * (size_t)B * P; }
+
+}  // extern "C"

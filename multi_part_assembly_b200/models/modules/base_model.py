@@ -22,6 +22,7 @@ from ...utils import trans_l2_loss, rot_points_cd_loss, shape_cd_loss, \
     rot_cosine_loss, rot_points_l2_loss, chamfer_distance
 from ...utils import calc_part_acc, calc_connectivity_acc, trans_metrics, \
     rot_metrics
+from ...utils.loss import fused_geometric_losses
 from ...utils.lr import CosineAnnealingWarmupRestarts
 
 
@@ -180,6 +181,9 @@ class BaseModel(LightningModule):
         else:
             new_trans, new_rot = gt_trans.detach().clone(), gt_rot.detach().clone()
 
+        if self._can_fuse_losses(pred_rot, new_rot):
+            return self._calc_loss_fused(out_dict, data_dict, new_trans, new_rot)
+
         trans_loss = trans_l2_loss(pred_trans, new_trans, valids)
         rot_pt_cd_loss = rot_points_cd_loss(part_pcs, pred_rot, new_rot, valids)
         transform_pt_cd_loss, pred_trans_pts, gt_trans_pts = shape_cd_loss(
@@ -205,6 +209,41 @@ class BaseModel(LightningModule):
             'pred_trans_pts': pred_trans_pts,
         }
         return loss_dict, out_dict
+
+    def _can_fuse_losses(self, pred_rot, gt_rot):
+        """The fused forward-only loss kernels apply when nothing needs a
+        gradient (evaluation, benchmarking, CUDA-graph replay) and both
+        rotations are quaternions."""
+        return (not torch.is_grad_enabled()) and pred_rot.rot_type == 'quat' and \
+            gt_rot.rot_type == 'quat' and pred_rot.rot.is_cuda
+
+    def _loss_weight_tensor(self, device):
+        cache = getattr(self, '_loss_w_cache', None)
+        if cache is None or cache.device != device:
+            c = self.cfg.loss
+            w = [c.trans_loss_w, c.rot_pt_cd_loss_w, c.transform_pt_cd_loss_w,
+                 c.rot_loss_w if c.use_rot_loss else 0.,
+                 c.rot_pt_l2_loss_w if c.use_rot_pt_l2_loss else 0.]
+            cache = torch.tensor(w, dtype=torch.float32, device=device)
+            self._loss_w_cache = cache
+        return cache
+
+    def _calc_loss_fused(self, out_dict, data_dict, new_trans, new_rot):
+        pred_trans, pred_rot = out_dict['trans'], out_dict['rot']
+        part_pcs, valids = data_dict['part_pcs'], data_dict['part_valids']
+        terms, pred_trans_pts, gt_trans_pts = fused_geometric_losses(
+            part_pcs, pred_trans, new_trans, pred_rot, new_rot, valids,
+            self._loss_weight_tensor(part_pcs.device), training=self.semantic or self.training,
+            want_rot_l2=bool(self.cfg.loss.use_rot_pt_l2_loss), ret_pts=True)
+        loss_dict = {k: terms[k] for k in ('trans_loss', 'rot_pt_cd_loss', 'transform_pt_cd_loss')}
+        if self.cfg.loss.use_rot_loss:
+            loss_dict['rot_loss'] = terms['rot_loss']
+        if self.cfg.loss.use_rot_pt_l2_loss:
+            loss_dict['rot_pt_l2_loss'] = terms['rot_pt_l2_loss']
+        if not self.training:
+            loss_dict.update(self._calc_metrics(data_dict, out_dict, new_trans, new_rot))
+        return loss_dict, {'pred_trans': pred_trans, 'pred_rot': pred_rot,
+                           'gt_trans_pts': gt_trans_pts, 'pred_trans_pts': pred_trans_pts}
 
     @torch.no_grad()
     def _calc_metrics(self, data_dict, out_dict, gt_trans, gt_rot):

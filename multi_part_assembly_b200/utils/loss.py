@@ -98,6 +98,44 @@ def pose_chamfer(pts, trans1, trans2, quat1, quat2, valids, mode):
         prep(valids.detach()), mode)
 
 
+def fused_geometric_losses(pts, pred_trans, gt_trans, pred_rot, gt_rot, valids, weights,
+                            training=True, want_rot_l2=True, ret_pts=False):
+    """All geometric loss terms of BaseModel._calc_loss in four launches (two
+    fused pose-Chamfer calls + two reduction kernels), forward only.
+
+    weights: [trans, rot_pt_cd, transform_pt_cd, rot, rot_pt_l2] loss weights.
+    Returns a dict of [B] tensors keyed like the reference's loss_dict plus
+    'loss' (the weighted total), and optionally the two transformed clouds.
+    """
+    B, P, N, _ = pts.shape
+    q1, q2 = pred_rot.rot.contiguous().float(), gt_rot.rot.contiguous().float()
+    t1, t2 = pred_trans.contiguous().float(), gt_trans.contiguous().float()
+    with torch.no_grad():
+        pd1, pd2, _, _ = pose_chamfer(pts, None, None, q1, q2, valids, CD_PART)
+        sd1, sd2, pts1, pts2 = pose_chamfer(pts, t1, t2, q1, q2, valids, CD_SHAPE)
+    dev = pts.device
+    terms = torch.empty(6, B, dtype=torch.float32, device=dev)
+    w = torch.tensor([float(x) for x in weights], dtype=torch.float32).to(dev, non_blocking=True) \
+        if not isinstance(weights, torch.Tensor) else weights
+    L = _lib.lib()
+    ws_bytes = L.mpa_geometric_losses_workspace_bytes(B, P)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    v = valids.contiguous().float()
+    p = pts.contiguous().float()
+    with torch.cuda.device(dev):
+        rc = L.mpa_geometric_losses(
+            _lib.ptr(p), _lib.ptr(q1), _lib.ptr(t1), _lib.ptr(q2), _lib.ptr(t2), _lib.ptr(v),
+            _lib.ptr(pd1), _lib.ptr(pd2), _lib.ptr(sd1), _lib.ptr(sd2), B, P, N,
+            1 if training else 0, 1 if want_rot_l2 else 0, _lib.ptr(w), _lib.ptr(terms),
+            _lib.ptr(ws), ws_bytes, _lib.cuda_stream(dev))
+    _lib.check(rc, 'mpa_geometric_losses')
+    out = {'trans_loss': terms[0], 'rot_pt_cd_loss': terms[1], 'transform_pt_cd_loss': terms[2],
+           'rot_loss': terms[3], 'rot_pt_l2_loss': terms[4], 'loss': terms[5]}
+    if ret_pts:
+        return out, pts1, pts2
+    return out
+
+
 def trans_l2_loss(trans1, trans2, valids):
     """L2 loss between translations [B, P, 3] (reference :22-35)."""
     return _valid_mean((trans1 - trans2).pow(2).sum(dim=-1), valids)

@@ -239,3 +239,28 @@ def test_transformer_tcgen05(cuda, name, dims, seed):
     assert np.isfinite(out).all()
     err = np.abs(out[v] - g['out'][v]).max() / np.abs(g['out'][v]).max()
     assert err < 3e-2, err
+
+
+@pytest.mark.parametrize('tag,name,dataset,seed,semantic,N,nv', [
+    ('model_pn_transformer', 'pn_transformer', 'everyday', 11, False, 64, (5, 3)),
+    ('model_global', 'global', 'everyday', 13, False, 64, (5, 3))])
+def test_fused_loss_path_matches_reference(cuda, tag, name, dataset, seed, semantic, N, nv):
+    """forward_pass without autograd (the benchmark / CUDA-graph path) uses the
+    fused loss kernels; its loss dict must equal the reference's too."""
+    from multi_part_assembly_b200.configs import get_cfg
+    from multi_part_assembly_b200.datasets import make_batch
+    from multi_part_assembly_b200.models import build_model
+    from multi_part_assembly_b200.compat.lightning import Trainer
+    g = gold(tag)
+    model = zero_dropout(fill_params_(build_model(get_cfg(name, dataset)), seed)).to(cuda)
+    model.trainer = Trainer()
+    for mode in ('train', 'val'):
+        batch = {k: v.to(cuda) for k, v in
+                 make_batch(2, P=20, N=N, num_valid=list(nv), seed=seed, semantic=semantic).items()}
+        model.train(mode == 'train')
+        torch.manual_seed(100 + seed)
+        with torch.no_grad():
+            ld = model.forward_pass(batch, mode=mode, optimizer_idx=-1)
+        for k, v in ld.items():
+            np.testing.assert_allclose(float(v), g[f'{mode}/{k}'], rtol=2e-4, atol=1e-6,
+                                       err_msg=f'{mode}/{k}')
