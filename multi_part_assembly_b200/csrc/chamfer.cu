@@ -391,22 +391,33 @@ __device__ __forceinline__ void scan_range(const float4* __restrict__ T, int s, 
 }
 
 // K2: one lane per query (queries taken in their own cloud's cell order so a
-// warp touches neighbouring target cells).  The search walks the rows (fixed
-// y,z cell, contiguous in memory along x) of the (2R+1)^2 window around the
-// query cell, nearest rows first; a row is skipped when its slab is already
-// farther than the best distance, and its x-range is clipped to the cells the
-// sphere of radius sqrt(best) can reach.  After window R the block
-// [c-R, c+R]^3 is proven complete when `best` is smaller than the distance to
-// the block's faces; otherwise R grows (shell only).
+// warp touches neighbouring target cells).
+//   A  scan the query's own cell -> a first `best`;
+//   B  (convergent, no scanning) for the other 26 cells of the 3x3x3 block decide
+//      per row (fixed y,z; contiguous along x) which cells the sphere of radius
+//      sqrt(best) can reach, from the squared distances to the own cell's faces,
+//      and note the candidate ranges (<= 10 per lane) in shared memory;
+//   C  one flat loop over the concatenated ranges: lanes stay converged on the
+//      distance evaluation instead of idling while others walk different rows;
+//   D  the block [c-1, c+1]^3 is proven complete when `best` is smaller than the
+//      distance to the block's faces that have cells beyond them; otherwise
+//      (rare: sparse regions, queries outside the grid) rings R = 2, 3, ... are
+//      walked row by row with the same strict pruning.
+// A cell is skipped only if it is STRICTLY farther than `best` (after a fp32
+// slack), so neither a closer point nor a tie with a lower index can hide in it.
+constexpr int NN_THREADS = 256;
+constexpr int NN_RANGES = 10;
 template <typename IdxT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(NN_THREADS)
 grid_nn_kernel(const float4* __restrict__ sorted0, const float4* __restrict__ sorted1,
                const int* __restrict__ cell_start, int cs_stride,
                const GridParams* __restrict__ params, const float4* __restrict__ far, int S,
                int N0, int N1, float* __restrict__ dist0, IdxT* __restrict__ idx0,
                float* __restrict__ dist1, IdxT* __restrict__ idx1) {
-  const long long wg = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+  __shared__ int rs[NN_RANGES][NN_THREADS], re[NN_RANGES][NN_THREADS];
+  const int tid = threadIdx.x;
+  const long long wg = ((long long)blockIdx.x * blockDim.x + tid) >> 5;
+  const int lane = tid & 31;
   const int per0 = (N0 + 31) >> 5, per1 = (N1 + 31) >> 5;
   const long long total0 = (long long)S * per0;
   const long long total = total0 + (long long)S * per1;
@@ -435,41 +446,100 @@ grid_nn_kernel(const float4* __restrict__ sorted0, const float4* __restrict__ so
     // positional uncertainty of cell planes / cell assignment in fp32
     const float slack = 1e-5f * (fabsf(q.x) + fabsf(q.y) + fabsf(q.z) + fabsf(g.ox) +
                                  fabsf(g.oy) + fabsf(g.oz) + (float)(g.dx + g.dy + g.dz) * g.h);
+    // squared distances from the query to the faces of its own cell (0 = lower side)
+    float X0 = fmaxf(q.x - (g.ox + (float)cx * g.h) - slack, 0.f);
+    float X1 = fmaxf((g.ox + (float)(cx + 1) * g.h) - q.x - slack, 0.f);
+    float Y0 = fmaxf(q.y - (g.oy + (float)cy * g.h) - slack, 0.f);
+    float Y1 = fmaxf((g.oy + (float)(cy + 1) * g.h) - q.y - slack, 0.f);
+    float Z0 = fmaxf(q.z - (g.oz + (float)cz * g.h) - slack, 0.f);
+    float Z1 = fmaxf((g.oz + (float)(cz + 1) * g.h) - q.z - slack, 0.f);
+    X0 *= X0; X1 *= X1; Y0 *= Y0; Y1 *= Y1; Z0 *= Z0; Z1 *= Z1;
+    const bool hasL = cx > 0, hasR = cx < g.dx - 1;
+
+    // ---- A: own cell ----
+    const int c0 = (cz * g.dy + cy) * g.dx + cx;
+    {
+      const int e = cs[c0 + 1];
+      for (int p = cs[c0]; p < e; ++p) consider(__ldg(T + p), q.x, q.y, q.z, best, bidx);
+    }
+    // ---- B: which other cells of the 3x3x3 block can still matter ----
+    int nr = 0;
+    if (hasL && X0 <= best) { rs[nr][tid] = cs[c0 - 1]; re[nr][tid] = cs[c0]; ++nr; }
+    if (hasR && X1 <= best) { rs[nr][tid] = cs[c0 + 1]; re[nr][tid] = cs[c0 + 2]; ++nr; }
+#pragma unroll
+    for (int dz = -1; dz <= 1; ++dz) {
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy) {
+        if (dy == 0 && dz == 0) continue;
+        const int zc = cz + dz, yc = cy + dy;
+        if (zc < 0 || zc >= g.dz || yc < 0 || yc >= g.dy) continue;
+        const float l2 = (dy < 0 ? Y0 : (dy > 0 ? Y1 : 0.f)) + (dz < 0 ? Z0 : (dz > 0 ? Z1 : 0.f));
+        if (l2 > best) continue;
+        const int xa = cx - ((hasL && X0 + l2 <= best) ? 1 : 0);
+        const int xb = cx + ((hasR && X1 + l2 <= best) ? 1 : 0);
+        const int row = (zc * g.dy + yc) * g.dx;
+        rs[nr][tid] = cs[row + xa];
+        re[nr][tid] = cs[row + xb + 1];
+        ++nr;
+      }
+    }
+    // ---- C: flat scan of the noted ranges (two candidates in flight) ----
+    {
+      int k = 0, p = 0, e = 0;
+      if (nr > 0) { p = rs[0][tid]; e = re[0][tid]; }
+      while (k < nr) {
+        if (p >= e) {
+          if (++k < nr) { p = rs[k][tid]; e = re[k][tid]; }
+          continue;
+        }
+        const float4 t0 = __ldg(T + p);
+        if (p + 1 < e) {
+          const float4 t1 = __ldg(T + p + 1);
+          consider(t0, q.x, q.y, q.z, best, bidx);
+          consider(t1, q.x, q.y, q.z, best, bidx);
+          p += 2;
+        } else {
+          consider(t0, q.x, q.y, q.z, best, bidx);
+          ++p;
+        }
+      }
+    }
+    // ---- D: completeness of the block, ring growth ----
     for (int r = 1;; ++r) {
-      const int xlo = max(cx - r, 0), xhi = min(cx + r, g.dx - 1);
-      // offsets ordered 0, -1, +1, -2, +2, ... so that the nearest rows come first
-      for (int kz = 0; kz <= 2 * r; ++kz) {
-        const int dz = (kz & 1) ? -((kz + 1) >> 1) : (kz >> 1);
-        const int zc = cz + dz;
-        if (zc < 0 || zc >= g.dz) continue;
-        // distance from the query to the slab of cells zc (0 inside it)
-        float lz = dz == 0 ? 0.f : (dz < 0 ? q.z - (g.oz + (float)(zc + 1) * g.h)
-                                            : (g.oz + (float)zc * g.h) - q.z);
-        lz = fmaxf(lz - slack, 0.f);
-        if (lz * lz > best) continue;
-        for (int ky = 0; ky <= 2 * r; ++ky) {
-          const int dy = (ky & 1) ? -((ky + 1) >> 1) : (ky >> 1);
-          const int yc = cy + dy;
-          if (yc < 0 || yc >= g.dy) continue;
-          const bool shell = (r == 1) || dz == r || dz == -r || dy == r || dy == -r;
-          float ly = dy == 0 ? 0.f : (dy < 0 ? q.y - (g.oy + (float)(yc + 1) * g.h)
-                                              : (g.oy + (float)yc * g.h) - q.y);
-          ly = fmaxf(ly - slack, 0.f);
-          const float rem = best - (ly * ly + lz * lz);  // squared x-reach left
-          if (rem < 0.f) continue;  // strictly farther than best: cannot win or tie
-          int xa = xlo, xb = xhi;
-          if (best < 1e30f) {
-            const float rad = sqrtf(rem) * 1.00001f + slack;
-            xa = max(xa, cell_coord(q.x - rad, g.ox, g.inv_h, g.dx));
-            xb = min(xb, cell_coord(q.x + rad, g.ox, g.inv_h, g.dx));
-          }
-          const int row = (zc * g.dy + yc) * g.dx;
-          if (shell) {
-            if (xa <= xb) scan_range(T, cs[row + xa], cs[row + xb + 1], q.x, q.y, q.z, best, bidx);
-          } else {  // interior row of a grown window: only the two new end cells
-            const int xl = cx - r, xr = cx + r;
-            if (xl >= xa && xl <= xb) scan_range(T, cs[row + xl], cs[row + xl + 1], q.x, q.y, q.z, best, bidx);
-            if (xr >= xa && xr <= xb) scan_range(T, cs[row + xr], cs[row + xr + 1], q.x, q.y, q.z, best, bidx);
+      if (r > 1) {
+        const int xlo = max(cx - r, 0), xhi = min(cx + r, g.dx - 1);
+        for (int kz = 0; kz <= 2 * r; ++kz) {
+          const int dz = (kz & 1) ? -((kz + 1) >> 1) : (kz >> 1);
+          const int zc = cz + dz;
+          if (zc < 0 || zc >= g.dz) continue;
+          float lz = dz == 0 ? 0.f : (dz < 0 ? q.z - (g.oz + (float)(zc + 1) * g.h)
+                                              : (g.oz + (float)zc * g.h) - q.z);
+          lz = fmaxf(lz - slack, 0.f);
+          if (lz * lz > best) continue;
+          for (int ky = 0; ky <= 2 * r; ++ky) {
+            const int dy = (ky & 1) ? -((ky + 1) >> 1) : (ky >> 1);
+            const int yc = cy + dy;
+            if (yc < 0 || yc >= g.dy) continue;
+            const bool shell = dz == r || dz == -r || dy == r || dy == -r;
+            float ly = dy == 0 ? 0.f : (dy < 0 ? q.y - (g.oy + (float)(yc + 1) * g.h)
+                                                : (g.oy + (float)yc * g.h) - q.y);
+            ly = fmaxf(ly - slack, 0.f);
+            const float rem = best - (ly * ly + lz * lz);  // squared x-reach left
+            if (rem < 0.f) continue;  // strictly farther than best: cannot win or tie
+            int xa = xlo, xb = xhi;
+            if (best < 1e30f) {
+              const float rad = sqrtf(rem) * 1.00001f + slack;
+              xa = max(xa, cell_coord(q.x - rad, g.ox, g.inv_h, g.dx));
+              xb = min(xb, cell_coord(q.x + rad, g.ox, g.inv_h, g.dx));
+            }
+            const int row = (zc * g.dy + yc) * g.dx;
+            if (shell) {
+              if (xa <= xb) scan_range(T, cs[row + xa], cs[row + xb + 1], q.x, q.y, q.z, best, bidx);
+            } else {  // interior row of a grown window: only the two new end cells
+              const int xl = cx - r, xr = cx + r;
+              if (xl >= xa && xl <= xb) scan_range(T, cs[row + xl], cs[row + xl + 1], q.x, q.y, q.z, best, bidx);
+              if (xr >= xa && xr <= xb) scan_range(T, cs[row + xr], cs[row + xr + 1], q.x, q.y, q.z, best, bidx);
+            }
           }
         }
       }
