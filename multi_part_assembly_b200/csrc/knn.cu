@@ -174,12 +174,17 @@ __global__ void edge_aggregate_kernel(const float* __restrict__ uv, const int* _
   }
 }
 
-// deterministic column sums of partial [rows, Co, 2] -> sums [Co, 2] (double accumulate)
-__global__ void column_sum_kernel(const float* __restrict__ partial, long long rows, int Co,
-                                  double* __restrict__ sums) {
-  const int c = blockIdx.x, lane = threadIdx.x;  // one warp per channel
+// deterministic column sums of partial [rows, Co, 2] -> sums [Co, 2] (double accumulate):
+// stage 1 reduces CS_SLICES row slices per channel (one warp each), stage 2 adds the
+// slices in a fixed order.
+constexpr int CS_SLICES = 64;
+__global__ void column_sum_stage1_kernel(const float* __restrict__ partial, long long rows, int Co,
+                                         double* __restrict__ slices) {
+  const int c = blockIdx.x, sl = blockIdx.y, lane = threadIdx.x;
+  const long long per = (rows + CS_SLICES - 1) / CS_SLICES;
+  const long long r0 = sl * per, r1 = min(rows, r0 + per);
   double s1 = 0, s2 = 0;
-  for (long long r = lane; r < rows; r += 32) {
+  for (long long r = r0 + lane; r < r1; r += 32) {
     s1 += (double)partial[(r * Co + c) * 2];
     s2 += (double)partial[(r * Co + c) * 2 + 1];
   }
@@ -188,7 +193,18 @@ __global__ void column_sum_kernel(const float* __restrict__ partial, long long r
     s1 += __shfl_xor_sync(0xffffffffu, s1, o);
     s2 += __shfl_xor_sync(0xffffffffu, s2, o);
   }
-  if (lane == 0) { sums[2 * c] = s1; sums[2 * c + 1] = s2; }
+  if (lane == 0) { slices[((long long)sl * Co + c) * 2] = s1; slices[((long long)sl * Co + c) * 2 + 1] = s2; }
+}
+__global__ void column_sum_stage2_kernel(const double* __restrict__ slices, int Co, double* __restrict__ sums) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Co) return;
+  double s1 = 0, s2 = 0;
+  for (int sl = 0; sl < CS_SLICES; ++sl) {
+    s1 += slices[((long long)sl * Co + c) * 2];
+    s2 += slices[((long long)sl * Co + c) * 2 + 1];
+  }
+  sums[2 * c] = s1;
+  sums[2 * c + 1] = s2;
 }
 
 }  // namespace mpa
@@ -239,7 +255,8 @@ int mpa_knn(const float* x, int n, int N, int C, int k, int32_t* idx, void* ws, 
 
 size_t mpa_edge_aggregate_workspace_bytes(long long M, int Co) {
   const long long blocks = (M + EC_PTS - 1) / EC_PTS;
-  return align_up(sizeof(float) * 2 * (size_t)blocks * Co, 256);
+  return align_up(sizeof(float) * 2 * (size_t)blocks * Co, 256) +
+         align_up(sizeof(double) * 2 * (size_t)CS_SLICES * Co, 256);
 }
 
 int mpa_edge_aggregate(const float* uv, const int32_t* idx, int n, int N, int Co, int k, float* ymax,
@@ -261,10 +278,13 @@ int mpa_edge_aggregate(const float* uv, const int32_t* idx, int n, int N, int Co
         uv, idx, M, N, Co, k, ymax, ymin, partial);
   }
   MPA_LAUNCH_CHECK();
+  double* slices = (double*)((char*)scratch.base + align_up(sizeof(float) * 2 * (size_t)blocks * Co, 256));
   {
     ProfScope ps("edge_column_sum", stream);
-    column_sum_kernel<<<Co, 32, 0, stream>>>(partial, blocks, Co, sums);
+    column_sum_stage1_kernel<<<dim3(Co, CS_SLICES), 32, 0, stream>>>(partial, blocks, Co, slices);
+    column_sum_stage2_kernel<<<(Co + 127) / 128, 128, 0, stream>>>(slices, Co, sums);
   }
+  count_launch();
   MPA_LAUNCH_CHECK();
   return MPA_OK;
 }

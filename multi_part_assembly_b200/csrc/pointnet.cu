@@ -22,24 +22,36 @@
 //                 registers.  Launch 5 also keeps per-part max and min, from
 //                 which max_n(BN5(y)) follows for either sign of gamma.
 //   eval BN       one launch (PHASE 5 with running statistics).
-// Two independent 128-thread pipelines per CTA share the weight image and
-// overlap one pipeline's MMA with the other's epilogue.
+// PN_GROUPS independent 128-thread pipelines per CTA (each on its own 64-point
+// tile and TMEM columns) share the weight image; while one waits for its MMA or
+// its TMEM loads the others run their epilogues.
+#include <stdlib.h>
+
 #include "mpa_common.cuh"
 #include "tc05.cuh"
 
 namespace mpa {
 
-constexpr int PN_TILE = 128;                  // points per tile = UMMA N
-constexpr int PN_GROUPS = 2;                  // pipelines per CTA
+#ifndef MPA_PN_TILE
+#define MPA_PN_TILE 64
+#endif
+#ifndef MPA_PN_GROUPS
+#define MPA_PN_GROUPS 4
+#endif
+constexpr int PN_TILE = MPA_PN_TILE;          // points per tile = UMMA N
+constexpr int PN_GROUPS = MPA_PN_GROUPS;      // pipelines per CTA (GROUPS * 2 * TILE <= 512 TMEM columns)
 constexpr int PN_THREADS = 128 * PN_GROUPS;
 constexpr int PN_WTILE = 128 * 128;           // bytes of one [128 rows][64 k] bf16 tile
 // weight image: layer1..4 one tile each (rows = out channels padded to 128),
 // layer 5: [mblock 0..1][kblock 0..1] tiles
 __host__ __device__ constexpr int pn_w_off(int layer0) { return layer0 * PN_WTILE; }
 constexpr int PN_W_BYTES = 8 * PN_WTILE;      // 128 KB
-constexpr int PN_ACT_BYTES = 2 * PN_WTILE;    // per pipeline: two K-blocks of [128 points][64 ch]
+constexpr int PN_ACT_KB = PN_TILE * 128;      // one K-block of the activation tile: [TILE points][64 ch] bf16
+constexpr int PN_ACT_BYTES = 2 * PN_ACT_KB;   // per pipeline: two K-blocks
 constexpr int PN_SMEM = PN_W_BYTES + PN_GROUPS * PN_ACT_BYTES + 1024;  // + alignment slack
 constexpr int PN_MAXC = 256;
+static_assert(PN_TILE == 64, "the MN-major activation tile is one 64-point swizzle atom wide");
+static_assert(PN_GROUPS * 2 * PN_TILE <= 512, "TMEM has 512 columns");
 
 struct PointNetArgs {
   const float* pts;         // [n_parts, N, 3]
@@ -51,6 +63,7 @@ struct PointNetArgs {
   unsigned* pmax;           // [n_parts, 256] ordered-uint max of layer-5 pre-activations
   unsigned* pmin;           // [n_parts, 256]
   int n_parts, N, F;        // F = channels of layer 5 (128 or 256)
+  long long* dbg;           // optional cycle stamps (MPA_PN_DEBUG), nullptr in production
 };
 
 __device__ __forceinline__ int pn_cout(int layer, int F) {  // layer 1..5
@@ -85,7 +98,7 @@ __global__ void __launch_bounds__(PN_THREADS, 1) pointnet_phase_kernel(PointNetA
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
-  const uint32_t tmem = tmem_base_s + (uint32_t)(g * 256);       // this pipeline's 256 columns
+  const uint32_t tmem = tmem_base_s + (uint32_t)(g * 2 * PN_TILE);  // this pipeline's columns
   const uint32_t tmem_lane = tmem + ((uint32_t)(wq * 32) << 16);  // this warp's lane quadrant
 
   // per-thread BN constants of the finished layers (channel t; layer 4 has 128 channels)
@@ -95,7 +108,7 @@ __global__ void __launch_bounds__(PN_THREADS, 1) pointnet_phase_kernel(PointNetA
     sc[l] = (l + 1 < PHASE) ? a.scale[l * PN_MAXC + t] : 0.f;
     sh[l] = (l + 1 < PHASE) ? a.shift[l * PN_MAXC + t] : 0.f;
   }
-  constexpr uint32_t IDESC = tc::make_idesc_bf16(128, PN_TILE);
+  constexpr uint32_t IDESC = tc::make_idesc_bf16_bmn(128, PN_TILE);  // activations are MN-major
   const int mblocks5 = a.F / 128;
   float ssum[2] = {0.f, 0.f}, ssq[2] = {0.f, 0.f};
   uint32_t parity = 0;
@@ -111,25 +124,34 @@ __global__ void __launch_bounds__(PN_THREADS, 1) pointnet_phase_kernel(PointNetA
     const int p0 = (int)(tile % tiles_per_part) * PN_TILE;
     const int npts = min(PN_TILE, a.N - p0);
 
-    // ---- layer-1 B operand: row = point, k = (x, y, z, 0 ...) in bf16 ----
+    const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && tid == 0 && tile < 8 * n_workers;
+    long long* dbg = a.dbg + (tile / n_workers) * 16;
+    if (dbg_on) dbg[0] = clock64();
+    // ---- layer-1 B operand, MN-major: row k = coordinate k of the TILE points
+    // (rows 3..15 zero).  Thread i fills one 16-byte chunk: row i>>3, points 8*(i&7).. ----
     {
-      float x = 0.f, y = 0.f, z = 0.f;
-      if (t < npts) {
-        const float* p = a.pts + ((long long)part * a.N + p0 + t) * 3;
-        x = p[0]; y = p[1]; z = p[2];
+      const int row = t >> 3, chunk = t & 7;
+      uint32_t w[4] = {0u, 0u, 0u, 0u};
+      if (row < 3) {
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const int pa = chunk * 8 + 2 * h, pb = pa + 1;
+          const float va = pa < npts ? a.pts[((long long)part * a.N + p0 + pa) * 3 + row] : 0.f;
+          const float vb = pb < npts ? a.pts[((long long)part * a.N + p0 + pb) * 3 + row] : 0.f;
+          const __nv_bfloat162 pk = __floats2bfloat162_rn(va, vb);
+          w[h] = *reinterpret_cast<const uint32_t*>(&pk);
+        }
       }
-      const __nv_bfloat162 xy = __floats2bfloat162_rn(x, y);
-      const __nv_bfloat162 z0 = __floats2bfloat162_rn(z, 0.f);
-      uint4 c0;
-      c0.x = *reinterpret_cast<const uint32_t*>(&xy);
-      c0.y = *reinterpret_cast<const uint32_t*>(&z0);
-      c0.z = 0u; c0.w = 0u;
-      *reinterpret_cast<uint4*>(act + tc::sw128_offset(t, 0)) = c0;
-      *reinterpret_cast<uint4*>(act + tc::sw128_offset(t, 8)) = make_uint4(0u, 0u, 0u, 0u);
+      if (row < 16 && chunk * 8 < PN_TILE)
+        *reinterpret_cast<uint4*>(act + row * 128 + (((chunk ^ row) & 7) << 4)) =
+            make_uint4(w[0], w[1], w[2], w[3]);
     }
+    if (dbg_on) dbg[1] = clock64();
     tc::fence_async_smem();
+    if (dbg_on) dbg[2] = clock64();
     tc::fence_before_sync();
     tc::group_sync(1 + g, 128);
+    if (dbg_on) dbg[3] = clock64();
 
 #pragma unroll
     for (int layer = 1; layer <= PHASE; ++layer) {
@@ -143,16 +165,18 @@ __global__ void __launch_bounds__(PN_THREADS, 1) pointnet_phase_kernel(PointNetA
             const int kb = k >> 6, ks = k & 63;
             const uint32_t wa = tc::smem_u32(wsm) + pn_w_off(layer - 1) +
                                 (layer == 5 ? (mb * 2 + kb) * PN_WTILE : 0) + ks * 2;
-            const uint32_t ba = tc::smem_u32(act) + kb * PN_WTILE + ks * 2;
-            tc::mma_bf16(tmem + (uint32_t)(mb * 128), tc::make_desc_sw128(wa),
-                         tc::make_desc_sw128(ba), IDESC, k > 0 ? 1u : 0u);
+            const uint32_t ba = tc::smem_u32(act) + k * 128;  // 16 channel rows per K step
+            tc::mma_bf16(tmem + (uint32_t)(mb * PN_TILE), tc::make_desc_sw128(wa),
+                         tc::make_desc_sw128_mn(ba, 128 * 128), IDESC, k > 0 ? 1u : 0u);
           }
         }
         tc::mma_commit(&mbar[g]);
       }
+      if (dbg_on && layer == 1) dbg[4] = clock64();
       tc::mbar_wait(&mbar[g], parity);
       parity ^= 1u;
       tc::fence_after_sync();
+      if (dbg_on && layer == 1) dbg[5] = clock64();
 
       // ---- epilogue ----
       if (layer < PHASE) {
@@ -161,18 +185,24 @@ __global__ void __launch_bounds__(PN_THREADS, 1) pointnet_phase_kernel(PointNetA
         const int cout = pn_cout(layer, a.F);
         if (wq * 32 < cout) {
           const float s = sc[layer - 1], b = sh[layer - 1];
-          uint8_t* dst = act + (t >> 6) * PN_WTILE;  // K-block of channel t
-          const int col = t & 63;
+          uint8_t* dst = act + t * 128;  // channel row of the MN-major tile (TILE points = 128 B)
 #pragma unroll 1
           for (int j0 = 0; j0 < PN_TILE; j0 += 32) {
             float v[32];
             tc::tmem_ld32(tmem_lane + (uint32_t)j0, v);
             tc::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float r = fmaxf(fmaf(v[j], s, b), 0.f);
-              *reinterpret_cast<__nv_bfloat16*>(dst + tc::sw128_offset(j0 + j, col)) =
-                  __float2bfloat16_rn(r);
+            for (int jj = 0; jj < 32; jj += 8) {
+              uint32_t w[4];
+#pragma unroll
+              for (int h = 0; h < 4; ++h) {
+                const float r0 = fmaxf(fmaf(v[jj + 2 * h], s, b), 0.f);
+                const float r1 = fmaxf(fmaf(v[jj + 2 * h + 1], s, b), 0.f);
+                const __nv_bfloat162 pk = __floats2bfloat162_rn(r0, r1);
+                w[h] = *reinterpret_cast<const uint32_t*>(&pk);
+              }
+              const int chunk = (j0 + jj) >> 3;
+              *reinterpret_cast<uint4*>(dst + (((chunk ^ t) & 7) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
           }
         }
@@ -189,14 +219,23 @@ __global__ void __launch_bounds__(PN_THREADS, 1) pointnet_phase_kernel(PointNetA
 #pragma unroll 1
             for (int j0 = 0; j0 < PN_TILE; j0 += 32) {
               float v[32];
-              tc::tmem_ld32(tmem_lane + (uint32_t)(mb * 128 + j0), v);
+              tc::tmem_ld32(tmem_lane + (uint32_t)(mb * PN_TILE + j0), v);
               tc::tmem_ld_wait();
+              if (npts == PN_TILE) {  // full tile: no per-point predicate
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if (j0 + j < npts) {
+                for (int j = 0; j < 32; ++j) {
                   s1 += v[j];
                   s2 = fmaf(v[j], v[j], s2);
                   if (PHASE == 5) { mx = fmaxf(mx, v[j]); mn = fminf(mn, v[j]); }
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  if (j0 + j < npts) {
+                    s1 += v[j];
+                    s2 = fmaf(v[j], v[j], s2);
+                    if (PHASE == 5) { mx = fmaxf(mx, v[j]); mn = fminf(mn, v[j]); }
+                  }
                 }
               }
             }
@@ -211,7 +250,9 @@ __global__ void __launch_bounds__(PN_THREADS, 1) pointnet_phase_kernel(PointNetA
         }
         tc::fence_before_sync();  // TMEM reads done before the next tile's MMA overwrites
       }
+      if (dbg_on && layer == 1) dbg[6] = clock64();
     }
+    if (dbg_on) dbg[7] = clock64();
   }
 
   // ---- per-worker partial statistics ----
@@ -402,7 +443,13 @@ int mpa_pointnet_forward(const float* pts, const float* valids, int n_parts, int
   }
   MPA_LAUNCH_CHECK();
 
-  PointNetArgs a{pts, valids, (const uint4*)image, scale, shift, partial, pmax, pmin, n_parts, N, F};
+  long long* dbg = nullptr;
+  static const bool want_dbg = getenv("MPA_PN_DEBUG") != nullptr;
+  if (want_dbg) {
+    MPA_CUDA(cudaMalloc((void**)&dbg, sizeof(long long) * 16 * 8));
+    MPA_CUDA(cudaMemset(dbg, 0, sizeof(long long) * 16 * 8));
+  }
+  PointNetArgs a{pts, valids, (const uint4*)image, scale, shift, partial, pmax, pmin, n_parts, N, F, dbg};
   const int C[5] = {64, 64, 64, 128, F};
   if (training) {
     for (int layer = 0; layer < 5; ++layer) {
@@ -414,6 +461,17 @@ int mpa_pointnet_forward(const float* pts, const float* valids, int n_parts, int
         default: rc = launch_phase<5>(a, grid, stream); break;
       }
       if (rc != MPA_OK) return rc;
+      if (want_dbg) {  // debug: cycle stamps of CTA 0 / pipeline 0, first 8 tiles
+        long long h[16 * 8];
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        for (int t = 0; t < 8; ++t) {
+          fprintf(stderr, "[pn phase %d tile %d]", layer + 1, t);
+          for (int k = 1; k < 8; ++k) fprintf(stderr, " %lld", h[t * 16 + k] ? h[t * 16 + k] - h[t * 16] : -1);
+          fprintf(stderr, "  (next tile +%lld)\n", t < 7 ? h[(t + 1) * 16] - h[t * 16] : 0);
+        }
+        cudaMemset(dbg, 0, sizeof(h));
+      }
       {
         ProfScope ps("pointnet_bn_finalize", stream);
         pointnet_finalize_kernel<<<(C[layer] * 32 + 255) / 256, 256, 0, stream>>>(

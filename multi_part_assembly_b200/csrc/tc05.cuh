@@ -44,6 +44,22 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
          ((uint32_t)(M >> 4) << 24);
 }
 
+// Same with the B operand MN-major (its N index contiguous in shared memory)
+__host__ __device__ constexpr uint32_t make_idesc_bf16_bmn(int M, int N) {
+  return make_idesc_bf16(M, N) | (1u << 16);
+}
+// MN-major operand, SWIZZLE_128B: atoms of 64 (MN) x 8 (K) elements; `lbo_bytes` =
+// distance between 64-wide atoms along MN, 8-k groups are 1024 B apart.
+__device__ __forceinline__ uint64_t make_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread
 __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
                                          uint32_t idesc, uint32_t accumulate) {

@@ -336,8 +336,9 @@ def dgcnn_forward(x, m, training, k=20):
     """x [n, N, 3] -> [n, F] / [n, N, F]; `m` is the DGCNN module."""
     _lib.require_cuda(x)
     params = [p for p in m.parameters()]
+    bf16 = _use_bf16()  # read the autocast state before leaving it
     with torch.autocast('cuda', enabled=False):
-        return _DGCNNFunction.apply(x.float().contiguous(), m, training, k, _use_bf16(), *params)
+        return _DGCNNFunction.apply(x.float().contiguous(), m, training, k, bf16, *params)
 
 
 # ---------------------------------------------------------------------------
