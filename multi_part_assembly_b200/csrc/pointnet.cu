@@ -59,7 +59,15 @@ struct PointNetArgs {
   const uint4* wimage;      // pre-swizzled bf16 weights (PN_W_BYTES)
   const float* scale;       // [5, 256] BN scale of the finished layers
   const float* shift;       // [5, 256]
-  float* partial;           // [workers, 256, 2] sum / sumsq of layer PHASE
+  float* scale_out;         // same arrays, written by CTA 0 for the layer finished here
+  float* shift_out;
+  const float* partial_in;  // [ctas, 256, 2] sum / sumsq of layer PHASE-1 (previous launch)
+  float* partial;           // [ctas, 256, 2] sum / sumsq of layer PHASE
+  const float* gamma_prev;  // BatchNorm parameters of layer PHASE-1 (fused finalize) or nullptr
+  const float* beta_prev;
+  float* rmean_prev;        // running statistics of layer PHASE-1 (updated by CTA 0) or nullptr
+  float* rvar_prev;
+  float eps, momentum;
   unsigned* pmax;           // [n_parts, 256] ordered-uint max of layer-5 pre-activations
   unsigned* pmin;           // [n_parts, 256]
   int n_parts, N, F;        // F = channels of layer 5 (128 or 256)
@@ -75,8 +83,14 @@ __global__ void __launch_bounds__(PN_THREADS, 1) pointnet_phase_kernel(PointNetA
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t mbar[PN_GROUPS];
+  __shared__ uint64_t wbar;  // weight image arrival
   __shared__ uint32_t tmem_base_s;
+  __shared__ double dred[PN_GROUPS][128][2];
+  __shared__ float fred[PN_GROUPS][PN_MAXC][2];
+  __shared__ double s_count;
+  __shared__ float s_prev[2][128];
 
+  const long long t_entry = clock64();
   const int tid = threadIdx.x;
   const int g = tid >> 7;            // pipeline
   const int t = tid & 127;           // thread in pipeline = channel (mod 128) = TMEM lane
@@ -84,17 +98,73 @@ __global__ void __launch_bounds__(PN_THREADS, 1) pointnet_phase_kernel(PointNetA
   uint8_t* wsm = smem;
   uint8_t* act = smem + PN_W_BYTES + g * PN_ACT_BYTES;
 
-  // ---- one-time setup: weights -> smem, mbarriers, TMEM ----
-  {
-    uint4* dst = reinterpret_cast<uint4*>(wsm);
-    for (int i = tid; i < PN_W_BYTES / 16; i += PN_THREADS) dst[i] = a.wimage[i];
-  }
+  // ---- one-time setup: mbarriers, weights (bulk async copy), TMEM ----
+  constexpr uint32_t W_BYTES = (PHASE < 5 ? PHASE : 8) * PN_WTILE;  // only the layers this phase runs
   if (tid == 0) {
     for (int i = 0; i < PN_GROUPS; ++i) tc::mbar_init(&mbar[i], 1);
+    tc::mbar_init(&wbar, 1);
     tc::fence_barrier_init();
   }
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(&wbar)),
+                 "r"(W_BYTES)
+                 : "memory");
+    for (uint32_t off = 0; off < W_BYTES; off += PN_WTILE)
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+              tc::smem_u32(wsm + off)),
+          "l"(reinterpret_cast<const uint8_t*>(a.wimage) + off), "r"((uint32_t)PN_WTILE),
+          "r"(tc::smem_u32(&wbar))
+          : "memory");
+  }
   if (tid < 32) tc::tmem_alloc<512>(&tmem_base_s);
-  tc::fence_async_smem();
+
+  // ---- fused BatchNorm finalize of the previous layer (training) ----
+  float sc_prev = 0.f, sh_prev = 0.f;
+  if (PHASE >= 2 && a.gamma_prev != nullptr) {
+    constexpr int CP = PHASE <= 4 ? 64 : 128;  // channels of layer PHASE-1
+    // number of valid points
+    if (tid == 0) s_count = 0.0;
+    double cnt = 0.0;
+    for (int p = tid; p < a.n_parts; p += PN_THREADS)
+      cnt += (a.valids == nullptr || a.valids[p] != 0.0f) ? (double)a.N : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    __syncthreads();
+    if ((tid & 31) == 0) atomicAdd(&s_count, cnt);  // integers: exact in any order
+    // per-CTA partial sums of the previous launch: group g adds CTAs g, g+GROUPS, ...
+    double s1 = 0.0, s2 = 0.0;
+    if (t < CP) {
+      for (int b = g; b < (int)gridDim.x; b += PN_GROUPS) {
+        s1 += (double)a.partial_in[((long long)b * PN_MAXC + t) * 2];
+        s2 += (double)a.partial_in[((long long)b * PN_MAXC + t) * 2 + 1];
+      }
+      dred[g][t][0] = s1;
+      dred[g][t][1] = s2;
+    }
+    __syncthreads();
+    if (t < CP) {
+      s1 = 0.0; s2 = 0.0;
+#pragma unroll
+      for (int k = 0; k < PN_GROUPS; ++k) { s1 += dred[k][t][0]; s2 += dred[k][t][1]; }
+      const double n = s_count;
+      const double mean = s1 / n;
+      const double var = fmax(s2 / n - mean * mean, 0.0);
+      sc_prev = a.gamma_prev[t] * (float)(1.0 / sqrt(var + (double)a.eps));
+      sh_prev = a.beta_prev[t] - (float)mean * sc_prev;
+      if (g == 0) { s_prev[0][t] = sc_prev; s_prev[1][t] = sh_prev; }
+      if (blockIdx.x == 0 && g == 0) {
+        a.scale_out[(PHASE - 2) * PN_MAXC + t] = sc_prev;
+        a.shift_out[(PHASE - 2) * PN_MAXC + t] = sh_prev;
+        if (a.rmean_prev != nullptr) {
+          a.rmean_prev[t] = (1.f - a.momentum) * a.rmean_prev[t] + a.momentum * (float)mean;
+          const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
+          a.rvar_prev[t] = (1.f - a.momentum) * a.rvar_prev[t] + a.momentum * (float)unbiased;
+        }
+      }
+    }
+  }
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -105,9 +175,16 @@ __global__ void __launch_bounds__(PN_THREADS, 1) pointnet_phase_kernel(PointNetA
   float sc[4], sh[4];
 #pragma unroll
   for (int l = 0; l < 4; ++l) {
-    sc[l] = (l + 1 < PHASE) ? a.scale[l * PN_MAXC + t] : 0.f;
-    sh[l] = (l + 1 < PHASE) ? a.shift[l * PN_MAXC + t] : 0.f;
+    // layers 1-3 have 64 channels whose accumulator rows are duplicated in TMEM lanes
+    // 64..127 (duplicated weight rows), so lane t works on channel t & 63
+    const int ch = l < 3 ? (t & 63) : t;
+    const bool fused_here = (l + 2 == PHASE) && a.gamma_prev != nullptr;
+    sc[l] = fused_here ? s_prev[0][ch] : ((l + 1 < PHASE) ? a.scale[l * PN_MAXC + ch] : 0.f);
+    sh[l] = fused_here ? s_prev[1][ch] : ((l + 1 < PHASE) ? a.shift[l * PN_MAXC + ch] : 0.f);
   }
+  const long long t_setup = clock64();
+  tc::mbar_wait(&wbar, 0);  // weight image has landed
+  const long long t_weights = clock64();
   constexpr uint32_t IDESC = tc::make_idesc_bf16_bmn(128, PN_TILE);  // activations are MN-major
   const int mblocks5 = a.F / 128;
   float ssum[2] = {0.f, 0.f}, ssq[2] = {0.f, 0.f};
@@ -179,63 +256,65 @@ __global__ void __launch_bounds__(PN_THREADS, 1) pointnet_phase_kernel(PointNetA
       if (dbg_on && layer == 1) dbg[5] = clock64();
 
       // ---- epilogue ----
+      // 64-channel layers: lanes 64..127 hold a copy of rows 0..63, so warps 2,3 take
+      // the points 32..63 of the same channels and all four warps stay busy.
+      const bool narrow = layer <= 3;
       if (layer < PHASE) {
-        // BN + ReLU, bf16, into the B-operand tile of the next layer (this
-        // layer's input tile is dead: its MMA has completed)
-        const int cout = pn_cout(layer, a.F);
-        if (wq * 32 < cout) {
-          const float s = sc[layer - 1], b = sh[layer - 1];
-          uint8_t* dst = act + t * 128;  // channel row of the MN-major tile (TILE points = 128 B)
-#pragma unroll 1
-          for (int j0 = 0; j0 < PN_TILE; j0 += 32) {
-            float v[32];
-            tc::tmem_ld32(tmem_lane + (uint32_t)j0, v);
-            tc::tmem_ld_wait();
+        // BN + ReLU, bf16, into the B-operand tile of the next layer (this layer's
+        // input tile is dead: its MMA has completed)
+        const float s = sc[layer - 1], b = sh[layer - 1];
+        const int ch = narrow ? (t & 63) : t;
+        uint8_t* dst = act + ch * 128;  // channel row of the MN-major tile (TILE points = 128 B)
+        const int jbeg = narrow ? (t >> 6) * 32 : 0;
+        float v[64];
+        tc::tmem_ld32(tmem_lane + (uint32_t)jbeg, v);
+        if (!narrow) tc::tmem_ld32(tmem_lane + 32u, v + 32);
+        tc::tmem_ld_wait();
 #pragma unroll
-            for (int jj = 0; jj < 32; jj += 8) {
-              uint32_t w[4];
+        for (int jj = 0; jj < 64; jj += 8) {
+          if (narrow && jj >= 32) break;
+          uint32_t w[4];
 #pragma unroll
-              for (int h = 0; h < 4; ++h) {
-                const float r0 = fmaxf(fmaf(v[jj + 2 * h], s, b), 0.f);
-                const float r1 = fmaxf(fmaf(v[jj + 2 * h + 1], s, b), 0.f);
-                const __nv_bfloat162 pk = __floats2bfloat162_rn(r0, r1);
-                w[h] = *reinterpret_cast<const uint32_t*>(&pk);
-              }
-              const int chunk = (j0 + jj) >> 3;
-              *reinterpret_cast<uint4*>(dst + (((chunk ^ t) & 7) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-            }
+          for (int h = 0; h < 4; ++h) {
+            const float r0 = fmaxf(fmaf(v[jj + 2 * h], s, b), 0.f);
+            const float r1 = fmaxf(fmaf(v[jj + 2 * h + 1], s, b), 0.f);
+            const __nv_bfloat162 pk = __floats2bfloat162_rn(r0, r1);
+            w[h] = *reinterpret_cast<const uint32_t*>(&pk);
           }
+          const int chunk = (jbeg + jj) >> 3;
+          *reinterpret_cast<uint4*>(dst + (((chunk ^ ch) & 7) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
         tc::fence_async_smem();
         tc::fence_before_sync();
         tc::group_sync(1 + g, 128);
       } else {
         // statistics of this layer's pre-activations (+ max/min for layer 5)
-        const int cout = pn_cout(layer, a.F);
 #pragma unroll
         for (int mb = 0; mb < 2; ++mb) {
-          if (mb < mblocks && mb * 128 + wq * 32 < cout) {
+          if (mb < mblocks) {
+            const int jbeg = narrow ? (t >> 6) * 32 : 0;
+            const int jn = narrow ? 32 : 64;
+            float v[64];
+            tc::tmem_ld32(tmem_lane + (uint32_t)(mb * PN_TILE + jbeg), v);
+            if (!narrow) tc::tmem_ld32(tmem_lane + (uint32_t)(mb * PN_TILE + 32), v + 32);
+            tc::tmem_ld_wait();
             float mx = -3.0e38f, mn = 3.0e38f, s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-            for (int j0 = 0; j0 < PN_TILE; j0 += 32) {
-              float v[32];
-              tc::tmem_ld32(tmem_lane + (uint32_t)(mb * PN_TILE + j0), v);
-              tc::tmem_ld_wait();
-              if (npts == PN_TILE) {  // full tile: no per-point predicate
+            if (npts == PN_TILE) {  // full tile: no per-point predicate
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
+              for (int j = 0; j < 64; ++j) {
+                if (j < jn) {
                   s1 += v[j];
                   s2 = fmaf(v[j], v[j], s2);
                   if (PHASE == 5) { mx = fmaxf(mx, v[j]); mn = fminf(mn, v[j]); }
                 }
-              } else {
+              }
+            } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  if (j0 + j < npts) {
-                    s1 += v[j];
-                    s2 = fmaf(v[j], v[j], s2);
-                    if (PHASE == 5) { mx = fmaxf(mx, v[j]); mn = fminf(mn, v[j]); }
-                  }
+              for (int j = 0; j < 64; ++j) {
+                if (j < jn && jbeg + j < npts) {
+                  s1 += v[j];
+                  s2 = fmaf(v[j], v[j], s2);
+                  if (PHASE == 5) { mx = fmaxf(mx, v[j]); mn = fminf(mn, v[j]); }
                 }
               }
             }
@@ -255,13 +334,26 @@ __global__ void __launch_bounds__(PN_THREADS, 1) pointnet_phase_kernel(PointNetA
     if (dbg_on) dbg[7] = clock64();
   }
 
-  // ---- per-worker partial statistics ----
+  if (a.dbg != nullptr && blockIdx.x == 0 && tid == 0) {
+    a.dbg[8] = t_setup - t_entry; a.dbg[9] = t_weights - t_entry; a.dbg[10] = clock64() - t_entry;
+  }
+  // ---- per-CTA partial statistics (groups combined in a fixed order) ----
 #pragma unroll
   for (int mb = 0; mb < 2; ++mb) {
-    const int c = mb * 128 + t;
-    float* o = a.partial + ((long long)worker * PN_MAXC + c) * 2;
-    o[0] = ssum[mb];
-    o[1] = ssq[mb];
+    fred[g][mb * 128 + t][0] = ssum[mb];
+    fred[g][mb * 128 + t][1] = ssq[mb];
+  }
+  __syncthreads();
+  if (tid < PN_MAXC) {
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < PN_GROUPS; ++k) {
+      s1 += fred[k][tid][0]; s2 += fred[k][tid][1];
+      if (PHASE <= 3 && tid < 64) { s1 += fred[k][tid + 64][0]; s2 += fred[k][tid + 64][1]; }
+    }
+    float* o = a.partial + ((long long)blockIdx.x * PN_MAXC + tid) * 2;
+    o[0] = s1;
+    o[1] = s2;
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -282,13 +374,15 @@ __global__ void pointnet_fill_weights_kernel(const float* w1, const float* w2, c
       const int co = i / cin[layer], ci = i % cin[layer];
       const int mb = co >> 7, row = co & 127, kb = ci >> 6, col = ci & 63;
       uint8_t* tile = image + pn_w_off(layer) + (layer == 4 ? (mb * 2 + kb) * PN_WTILE : 0);
-      *reinterpret_cast<__nv_bfloat16*>(tile + tc::sw128_offset(row, col)) =
-          __float2bfloat16_rn(w[layer][i]);
+      const __nv_bfloat16 v = __float2bfloat16_rn(w[layer][i]);
+      *reinterpret_cast<__nv_bfloat16*>(tile + tc::sw128_offset(row, col)) = v;
+      if (layer < 3)  // 64-channel layers: rows 64..127 repeat rows 0..63 (see the epilogue)
+        *reinterpret_cast<__nv_bfloat16*>(tile + tc::sw128_offset(row + 64, col)) = v;
     }
   }
 }
 
-// reduce the per-worker partial sums of layer `layer` (0-based) in a fixed order,
+// reduce the per-CTA partial sums of layer `layer` (0-based) in a fixed order,
 // produce BN scale/shift, update the running statistics (train mode), and for the
 // last layer turn per-part max/min into the pooled features.
 __global__ void pointnet_finalize_kernel(const float* partial, int n_workers, int layer, int C,
@@ -416,8 +510,6 @@ int mpa_pointnet_forward(const float* pts, const float* valids, int n_parts, int
   int grid = (int)((n_tiles + PN_GROUPS - 1) / PN_GROUPS);
   if (grid > sms) grid = sms;
   if (grid > 160) grid = 160;
-  const int n_workers = grid * PN_GROUPS;
-
   Scratch scratch;
   const size_t need = mpa_pointnet_workspace_bytes(n_parts);
   int rc = scratch.acquire(ws, ws_bytes, need, stream);
@@ -449,10 +541,23 @@ int mpa_pointnet_forward(const float* pts, const float* valids, int n_parts, int
     MPA_CUDA(cudaMalloc((void**)&dbg, sizeof(long long) * 16 * 8));
     MPA_CUDA(cudaMemset(dbg, 0, sizeof(long long) * 16 * 8));
   }
-  PointNetArgs a{pts, valids, (const uint4*)image, scale, shift, partial, pmax, pmin, n_parts, N, F, dbg};
+  // per-CTA partial sums, double buffered: launch l reads what launch l-1 wrote
+  float* partial_buf[2] = {partial, partial + (size_t)2 * PN_MAXC * 160};
+  PointNetArgs a{};
+  a.pts = pts; a.valids = valids; a.wimage = (const uint4*)image;
+  a.scale = scale; a.shift = shift; a.scale_out = scale; a.shift_out = shift;
+  a.pmax = pmax; a.pmin = pmin; a.n_parts = n_parts; a.N = N; a.F = F; a.dbg = dbg;
+  a.eps = eps; a.momentum = momentum;
   const int C[5] = {64, 64, 64, 128, F};
   if (training) {
     for (int layer = 0; layer < 5; ++layer) {
+      a.partial = partial_buf[layer & 1];
+      a.partial_in = partial_buf[(layer + 1) & 1];
+      // launch `layer` finalizes the BatchNorm of layer-1 in its prologue
+      a.gamma_prev = layer > 0 ? bn_gamma[layer - 1] : nullptr;
+      a.beta_prev = layer > 0 ? bn_beta[layer - 1] : nullptr;
+      a.rmean_prev = layer > 0 ? bn_running_mean[layer - 1] : nullptr;
+      a.rvar_prev = layer > 0 ? bn_running_var[layer - 1] : nullptr;
       switch (layer) {
         case 0: rc = launch_phase<1>(a, grid, stream); break;
         case 1: rc = launch_phase<2>(a, grid, stream); break;
@@ -466,20 +571,21 @@ int mpa_pointnet_forward(const float* pts, const float* valids, int n_parts, int
         cudaStreamSynchronize(stream);
         cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
         for (int t = 0; t < 8; ++t) {
+          if (t == 0) fprintf(stderr, "[pn phase %d] setup %lld weights %lld loop-end %lld cycles\n", layer + 1, h[8], h[9], h[10]);
           fprintf(stderr, "[pn phase %d tile %d]", layer + 1, t);
           for (int k = 1; k < 8; ++k) fprintf(stderr, " %lld", h[t * 16 + k] ? h[t * 16 + k] - h[t * 16] : -1);
           fprintf(stderr, "  (next tile +%lld)\n", t < 7 ? h[(t + 1) * 16] - h[t * 16] : 0);
         }
         cudaMemset(dbg, 0, sizeof(h));
       }
-      {
-        ProfScope ps("pointnet_bn_finalize", stream);
-        pointnet_finalize_kernel<<<(C[layer] * 32 + 255) / 256, 256, 0, stream>>>(
-            partial, n_workers, layer, C[layer], valids, n_parts, N, bn_gamma[layer], bn_beta[layer],
-            eps, momentum, bn_running_mean[layer], bn_running_var[layer], scale, shift);
-      }
-      MPA_LAUNCH_CHECK();
     }
+    {  // the last layer's statistics feed the pooling kernel
+      ProfScope ps("pointnet_bn_finalize", stream);
+      pointnet_finalize_kernel<<<(C[4] * 32 + 255) / 256, 256, 0, stream>>>(
+          partial_buf[0], grid, 4, C[4], valids, n_parts, N, bn_gamma[4], bn_beta[4], eps, momentum,
+          bn_running_mean[4], bn_running_var[4], scale, shift);
+    }
+    MPA_LAUNCH_CHECK();
   } else {
     for (int layer = 0; layer < 5; ++layer) {
       pointnet_eval_affine_kernel<<<(C[layer] + 127) / 128, 128, 0, stream>>>(
@@ -487,6 +593,8 @@ int mpa_pointnet_forward(const float* pts, const float* valids, int n_parts, int
           C[layer], scale, shift);
       MPA_LAUNCH_CHECK();
     }
+    a.partial = partial_buf[0];
+    a.partial_in = partial_buf[1];
     rc = launch_phase<5>(a, grid, stream);
     if (rc != MPA_OK) return rc;
   }
