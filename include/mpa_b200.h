@@ -176,6 +176,13 @@ int mpa_linear_forward(const float* x, const float* w, const float* bias, const 
                        int M, int N, int K, int act, float* out, void* ws, size_t ws_bytes,
                        void* stream);
 
+/* Output rows of PoseRegressor (models/modules/regressor.py:61-67): rot [T,4] =
+ * rot_head(feats) (L2-normalised when `normalize`), trans [T,3] = trans_head(feats);
+ * feats [T,K] fp32, weights as nn.Linear stores them.  Forward only. */
+int mpa_pose_outputs(const float* feats, int T, int K, const float* rot_w, const float* rot_b,
+                     const float* trans_w, const float* trans_b, int normalize, float* rot,
+                     float* trans, void* stream);
+
 /* Replaces TransformerEncoder.forward (models/pn_transformer/transformer.py:63-79),
  * i.e. nn.TransformerEncoder built at :23-34: `layers` pre-LN encoder layers
  * (MHA with H heads, ReLU FFN of width FF) + final LayerNorm (final_norm_w may be

@@ -94,6 +94,41 @@ __global__ void loss_shape_terms_kernel(const float* __restrict__ sums, const fl
   }
 }
 
+// rot = normalize(W_r f + b_r), trans = W_t f + b_t for every token; one warp per token
+__global__ void pose_outputs_kernel(const float* __restrict__ f, int T, int K,
+                                    const float* __restrict__ wr, const float* __restrict__ br,
+                                    const float* __restrict__ wt, const float* __restrict__ bt,
+                                    int normalize, float* __restrict__ rot, float* __restrict__ trans) {
+  const int tok = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (tok >= T) return;
+  float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int k = lane; k < K; k += 32) {
+    const float x = f[(long long)tok * K + k];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) acc[o] = fmaf(x, wr[o * K + k], acc[o]);
+#pragma unroll
+    for (int o = 0; o < 3; ++o) acc[4 + o] = fmaf(x, wt[o * K + k], acc[4 + o]);
+  }
+#pragma unroll
+  for (int o = 0; o < 7; ++o)
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], s);
+  if (lane == 0) {
+    float q[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) q[o] = acc[o] + br[o];
+    if (normalize) {  // F.normalize(p=2, dim=-1, eps=1e-12)
+      const float n = fmaxf(sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]), 1e-12f);
+#pragma unroll
+      for (int o = 0; o < 4; ++o) q[o] /= n;
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o) rot[(long long)tok * 4 + o] = q[o];
+#pragma unroll
+    for (int o = 0; o < 3; ++o) trans[(long long)tok * 3 + o] = acc[4 + o] + bt[o];
+  }
+}
+
 }  // namespace mpa
 
 using namespace mpa;
@@ -131,5 +166,21 @@ int mpa_geometric_losses(const float* pts, const float* quat1, const float* tran
 }
 
 size_t mpa_geometric_losses_workspace_bytes(int B, int P) { return sizeof(float) * 5 * (size_t)B * P; }
+
+int mpa_pose_outputs(const float* feats, int T, int K, const float* rot_w, const float* rot_b,
+                     const float* trans_w, const float* trans_b, int normalize, float* rot,
+                     float* trans, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MPA_CHECK_ARG(T >= 0 && K > 0, "pose_outputs: bad sizes");
+  if (T == 0) return MPA_OK;
+  MPA_CHECK_ARG(feats && rot_w && rot_b && trans_w && trans_b && rot && trans, "pose_outputs: null pointer");
+  {
+    ProfScope ps("pose_outputs", stream);
+    pose_outputs_kernel<<<(T * 32 + 255) / 256, 256, 0, stream>>>(feats, T, K, rot_w, rot_b, trans_w,
+                                                                  trans_b, normalize, rot, trans);
+  }
+  MPA_LAUNCH_CHECK();
+  return MPA_OK;
+}
 
 }  // extern "C"

@@ -220,6 +220,28 @@ def linear(x, w, bias=None, act=0, residual=None):
     return out
 
 
+def pose_head_forward(x, head):
+    """PoseRegressor.forward (models/modules/regressor.py:58-68) for the
+    quaternion head without autograd: the two hidden layers on the tcgen05
+    linear kernel (LeakyReLU fused), the 4+3 output rows and the quaternion
+    normalisation in one small kernel."""
+    shape = x.shape[:-1]
+    h = x.reshape(-1, x.shape[-1])
+    fc0, fc2 = head.fc_layers[0], head.fc_layers[2]
+    h = linear(h, fc0.weight, fc0.bias, act=2)
+    h = linear(h, fc2.weight, fc2.bias, act=2)
+    T = h.shape[0]
+    rot = torch.empty(T, 4, dtype=torch.float32, device=h.device)
+    trans = torch.empty(T, 3, dtype=torch.float32, device=h.device)
+    with torch.cuda.device(h.device):
+        rc = _lib.lib().mpa_pose_outputs(
+            _lib.ptr(h), T, h.shape[1], _lib.ptr(head.rot_head.weight), _lib.ptr(head.rot_head.bias),
+            _lib.ptr(head.trans_head.weight), _lib.ptr(head.trans_head.bias),
+            1 if head.norm_rot else 0, _lib.ptr(rot), _lib.ptr(trans), _lib.cuda_stream(h.device))
+    _lib.check(rc, 'mpa_pose_outputs')
+    return rot.view(*shape, 4), trans.view(*shape, 3)
+
+
 def _dense(x, w, bf16):
     if bf16:
         return linear(x, w)

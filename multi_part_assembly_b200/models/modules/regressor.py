@@ -32,6 +32,10 @@ class PoseRegressor(nn.Module):
         self.trans_head = nn.Linear(128, 3)
 
     def forward(self, x):
+        from ... import kernels
+        if self.rot_type == 'quat' and x.is_cuda and not torch.is_grad_enabled() and \
+                kernels._use_bf16():
+            return kernels.pose_head_forward(x, self)  # native, forward only
         f = self.fc_layers(x)
         rot = self.rot_head(f)
         if self.norm_rot:

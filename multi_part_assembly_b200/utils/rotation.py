@@ -62,11 +62,19 @@ _CONVERT = {
 }
 
 
-def _delegate(name):
-    """Tensor method applied to the wrapped rotation, re-wrapped."""
+def _delegate(name, revalidate=True):
+    """Tensor method applied to the wrapped rotation, re-wrapped.  Methods that
+    keep values, dtype and the trailing representation axis (detach, clone,
+    contiguous, cuda) skip the validity pass: the source was validated already
+    (the reference re-runs it, ~5 small kernels per call, with the same result)."""
 
     def method(self, *args, **kwargs):
-        return type(self)(getattr(self._rot, name)(*args, **kwargs), self._rot_type)
+        out = getattr(self._rot, name)(*args, **kwargs)
+        if revalidate:
+            return type(self)(out, self._rot_type)
+        new = object.__new__(type(self))
+        new._rot, new._rot_type = out, self._rot_type
+        return new
 
     method.__name__ = name
     return method
@@ -180,13 +188,13 @@ class Rotation3D:
     unflatten = _delegate('unflatten')
     transpose = _delegate('transpose')
     permute = _delegate('permute')
-    contiguous = _delegate('contiguous')
+    contiguous = _delegate('contiguous', revalidate=False)
     to = _delegate('to')
-    cuda = _delegate('cuda')
+    cuda = _delegate('cuda', revalidate=False)
     type = _delegate('type')
     type_as = _delegate('type_as')
-    detach = _delegate('detach')
-    clone = _delegate('clone')
+    detach = _delegate('detach', revalidate=False)
+    clone = _delegate('clone', revalidate=False)
 
     def squeeze(self, dim=None):
         r = self._rot.squeeze() if dim is None else self._rot.squeeze(dim)

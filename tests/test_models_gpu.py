@@ -264,3 +264,20 @@ def test_fused_loss_path_matches_reference(cuda, tag, name, dataset, seed, seman
         for k, v in ld.items():
             np.testing.assert_allclose(float(v), g[f'{mode}/{k}'], rtol=2e-4, atol=1e-6,
                                        err_msg=f'{mode}/{k}')
+
+
+def test_pose_head_native(cuda):
+    """Native pose head (tcgen05 hidden layers + fused output kernel) vs the golden reference output."""
+    from multi_part_assembly_b200 import kernels
+    from multi_part_assembly_b200.models import StocasticPoseRegressor
+    g = gold('regressor')
+    head = fill_params_(StocasticPoseRegressor(256, 0), 8).to(cuda)
+    kernels.set_precision('bf16')
+    try:
+        with torch.no_grad():
+            rot, trans = head(T(g['feats'], cuda))
+    finally:
+        kernels.set_precision('auto')
+    np.testing.assert_allclose(rot.cpu().numpy(), g['rot'], rtol=0, atol=2e-2)
+    np.testing.assert_allclose(trans.cpu().numpy(), g['trans'], rtol=0, atol=2e-2)
+    np.testing.assert_allclose(rot.norm(dim=-1).cpu().numpy(), 1.0, rtol=1e-5)
