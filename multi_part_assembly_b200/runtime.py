@@ -53,3 +53,38 @@ class GraphedStep:
                 dst.copy_(batch[k], non_blocking=True)
         self.graph.replay()
         return self.static_out
+
+    # ---- input prefetch: hide the host->device copy of the NEXT batch behind the
+    # current step (what a data loader with a prefetch queue does) -------------
+    def prefetch(self, batch):
+        """Start copying `batch` (pinned host tensors) into a staging buffer on a
+        side stream.  Call `run_prefetched()` afterwards to step on it."""
+        if not hasattr(self, '_copy_stream'):
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._staging = [{k: torch.empty_like(v) for k, v in self.static_in.items()}
+                             for _ in range(2)]
+            self._staged = [None, None]
+            self._slot = 0
+        slot = self._slot
+        self._slot ^= 1
+        ev_free = self._staged[slot]
+        with torch.cuda.stream(self._copy_stream):
+            if ev_free is not None:  # the step that consumed this slot must be done with it
+                self._copy_stream.wait_event(ev_free)
+            for k, dst in self._staging[slot].items():
+                dst.copy_(batch[k], non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self._copy_stream)
+        self._pending = (slot, ready)
+
+    def run_prefetched(self):
+        slot, ready = self._pending
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ready)
+        for k, dst in self.static_in.items():
+            dst.copy_(self._staging[slot][k], non_blocking=True)  # device-to-device, a few us
+        consumed = torch.cuda.Event()
+        consumed.record(cur)
+        self._staged[slot] = consumed
+        self.graph.replay()
+        return self.static_out
