@@ -232,7 +232,8 @@ int mpa_knn(const float* x, int n, int N, int C, int k, int32_t* idx, void* ws, 
     sqnorm_kernel<<<592, 256, 0, stream>>>(x, (long long)n * N, C, xx);
   }
   MPA_LAUNCH_CHECK();
-  const int rows = N <= 1024 ? 32 : 16;
+  static const int rows_env = getenv("MPA_KNN_ROWS") ? atoi(getenv("MPA_KNN_ROWS")) : 0;
+  const int rows = rows_env ? rows_env : 16;  // 16 rows: 2 CTAs per SM (profiles/: 42.0 -> 33.5 ms at cfg D)
   const int Cp = ((C + 3) & ~3) + 4;
   const int Np = (N + KNN_BN - 1) / KNN_BN * KNN_BN;
   const size_t smem = sizeof(float) * ((size_t)rows * Cp + KNN_BN * (KNN_KC + 4) + (size_t)rows * Np);
