@@ -240,6 +240,9 @@ class BaseModel(LightningModule):
             loss_dict['rot_loss'] = terms['rot_loss']
         if self.cfg.loss.use_rot_pt_l2_loss:
             loss_dict['rot_pt_l2_loss'] = terms['rot_pt_l2_loss']
+        # the packed [6, B] tensor (terms + weighted total) lets loss_function reduce
+        # everything with one kernel when there is a single sample
+        self._fused_packed = (terms.packed, tuple(loss_dict.keys()))
         if not self.training:
             loss_dict.update(self._calc_metrics(data_dict, out_dict, new_trans, new_rot))
         return loss_dict, {'pred_trans': pred_trans, 'pred_rot': pred_rot,
@@ -271,6 +274,7 @@ class BaseModel(LightningModule):
         one with the lowest weighted total (reference :348-387)."""
         samples = None
         out_dict = {}
+        self._fused_packed = None
         for _ in range(self.sample_iter):
             sample_loss, out_dict = self._loss_function(data_dict, out_dict,
                                                         optimizer_idx=optimizer_idx)
@@ -278,6 +282,22 @@ class BaseModel(LightningModule):
                 samples = {k: [] for k in sample_loss.keys()}
             for k, v in sample_loss.items():
                 samples[k].append(v)
+        packed = self._fused_packed
+        if self.sample_iter == 1 and packed is not None and \
+                tuple(k for k in samples.keys() if k.endswith('_loss')) == packed[1]:
+            # single sample straight from the fused loss kernels: one mean over [6, B]
+            terms, keys = packed
+            means = terms.mean(dim=1)
+            order = ('trans_loss', 'rot_pt_cd_loss', 'transform_pt_cd_loss', 'rot_loss',
+                     'rot_pt_l2_loss')
+            loss_dict = {k: means[order.index(k)] for k in keys}
+            for k, v in samples.items():  # evaluation metrics computed next to the loss terms
+                if k not in loss_dict:
+                    loss_dict[k] = v[0].mean()
+            loss_dict['loss'] = means[5]
+            if not self.training:
+                loss_dict['batch_size'] = terms.shape[1]
+            return loss_dict
         loss_dict = {k: torch.stack(v, dim=0) for k, v in samples.items()}
         total_loss = 0.
         for k, v in loss_dict.items():

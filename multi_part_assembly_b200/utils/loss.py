@@ -98,6 +98,18 @@ def pose_chamfer(pts, trans1, trans2, quat1, quat2, valids, mode):
         prep(valids.detach()), mode)
 
 
+class FusedLossTerms(dict):
+    """dict of the [B] loss terms that also keeps the packed [6, B] tensor they are
+    views of (order: trans, rot_pt_cd, transform_pt_cd, rot, rot_pt_l2, weighted
+    total), so a caller can reduce all of them with one kernel."""
+    KEYS = ('trans_loss', 'rot_pt_cd_loss', 'transform_pt_cd_loss', 'rot_loss',
+            'rot_pt_l2_loss', 'loss')
+
+    def __init__(self, terms):
+        super().__init__({k: terms[i] for i, k in enumerate(self.KEYS)})
+        self.packed = terms
+
+
 def fused_geometric_losses(pts, pred_trans, gt_trans, pred_rot, gt_rot, valids, weights,
                             training=True, want_rot_l2=True, ret_pts=False):
     """All geometric loss terms of BaseModel._calc_loss in four launches (two
@@ -129,8 +141,7 @@ def fused_geometric_losses(pts, pred_trans, gt_trans, pred_rot, gt_rot, valids, 
             1 if training else 0, 1 if want_rot_l2 else 0, _lib.ptr(w), _lib.ptr(terms),
             _lib.ptr(ws), ws_bytes, _lib.cuda_stream(dev))
     _lib.check(rc, 'mpa_geometric_losses')
-    out = {'trans_loss': terms[0], 'rot_pt_cd_loss': terms[1], 'transform_pt_cd_loss': terms[2],
-           'rot_loss': terms[3], 'rot_pt_l2_loss': terms[4], 'loss': terms[5]}
+    out = FusedLossTerms(terms)
     if ret_pts:
         return out, pts1, pts2
     return out
