@@ -183,6 +183,15 @@ int mpa_pose_outputs(const float* feats, int T, int K, const float* rot_w, const
                      const float* trans_w, const float* trans_b, int normalize, float* rot,
                      float* trans, void* stream);
 
+/* The whole PoseRegressor.forward (models/modules/regressor.py:58-68) in one launch,
+ * fp32: feats [T,K0] -> LeakyReLU(fc0: K0->H1) -> LeakyReLU(fc1: H1->H2) -> rot [T,4]
+ * (rot_head, L2-normalised when `normalize`) and trans [T,3] (trans_head).  Weights as
+ * nn.Linear stores them ([out,in]).  Forward only. */
+int mpa_pose_head_forward(const float* feats, int T, int K0, const float* fc0_w, const float* fc0_b,
+                          int H1, const float* fc1_w, const float* fc1_b, int H2, const float* rot_w,
+                          const float* rot_b, const float* trans_w, const float* trans_b, int normalize,
+                          float* rot, float* trans, void* stream);
+
 /* Replaces TransformerEncoder.forward (models/pn_transformer/transformer.py:63-79),
  * i.e. nn.TransformerEncoder built at :23-34: `layers` pre-LN encoder layers
  * (MHA with H heads, ReLU FFN of width FF) + final LayerNorm (final_norm_w may be

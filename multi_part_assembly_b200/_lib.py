@@ -44,6 +44,8 @@ _SIGNATURES = {
                              [c_int, ctypes.c_float, ctypes.c_float, c_void_p, c_void_p, c_size_t,
                               c_void_p]),
     'mpa_pose_outputs': (c_int, [c_void_p, c_int, c_int] + [c_void_p] * 4 + [c_int] + [c_void_p] * 3),
+    'mpa_pose_head_forward': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                      c_int] + [c_void_p] * 4 + [c_int] + [c_void_p] * 3),
     'mpa_linear_workspace_bytes': (c_size_t, [c_int] * 3),
     'mpa_linear_forward': (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p, c_void_p, c_size_t, c_void_p]),
     'mpa_transformer_workspace_bytes': (c_size_t, [c_int] * 5),

@@ -133,6 +133,7 @@ struct CloudDesc {
 
 constexpr int GRID_MAX_DIM = 38;  // 38^3+1 ints = 214 KB of shared memory in the build kernel
 constexpr int MAX_FAR = 64;  // >= max parts per shape
+constexpr int CB = 4;        // cells per axis of a coarse block (second grid level)
 
 __device__ __forceinline__ int cell_coord(float x, float o, float inv_h, int dim) {
   int c = (int)floorf((x - o) * inv_h);
@@ -176,8 +177,8 @@ template <typename IdxT>
 __global__ void grid_build_kernel(CloudDesc c0, CloudDesc c1, int S, float4* __restrict__ sorted0,
                                   float4* __restrict__ sorted1, int* __restrict__ cell_start,
                                   int cs_stride, GridParams* __restrict__ params,
-                                  float4* __restrict__ far, float* dist0, IdxT* idx0,
-                                  float* dist1, IdxT* idx1) {
+                                  float4* __restrict__ far, float4* __restrict__ reps, int cb_stride,
+                                  float* dist0, IdxT* idx0, float* dist1, IdxT* idx1) {
   extern __shared__ int cnt[];
   __shared__ float red[6][32];
   __shared__ double redm[6][32];
@@ -367,6 +368,25 @@ __global__ void grid_build_kernel(CloudDesc c0, CloudDesc c1, int S, float4* __r
       sorted[pos] = make_float4(v.x, v.y, v.z, __int_as_float(i));
     }
   }
+  __syncthreads();
+
+  // ---- coarse level: one representative target per block of 4x4x4 cells (w = -1: empty) ----
+  {
+    const int bx = (g.dx + CB - 1) / CB, by = (g.dy + CB - 1) / CB, bz = (g.dz + CB - 1) / CB;
+    float4* rp = reps + (long long)(cloud * S + seg) * cb_stride;
+    for (int cb = tid; cb < bx * by * bz; cb += blockDim.x) {
+      const int x0 = (cb % bx) * CB, y0 = ((cb / bx) % by) * CB, z0 = (cb / (bx * by)) * CB;
+      const int x1 = min(x0 + CB, g.dx), y1 = min(y0 + CB, g.dy), z1 = min(z0 + CB, g.dz);
+      int first = -1;
+      for (int zc = z0; zc < z1 && first < 0; ++zc)
+        for (int yc = y0; yc < y1 && first < 0; ++yc) {
+          const int row = (zc * g.dy + yc) * g.dx;
+          const int a = row + x0 == 0 ? 0 : cnt[row + x0 - 1];  // cursors now hold the cell ends
+          if (cnt[row + x1 - 1] > a) first = a;
+        }
+      rp[cb] = first >= 0 ? __ldcg(&sorted[first]) : make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+    }
+  }
 }
 
 __device__ __forceinline__ void consider(const float4 t, float qx, float qy, float qz, float& best,
@@ -400,9 +420,11 @@ __device__ __forceinline__ void scan_range(const float4* __restrict__ T, int s, 
 //   C  one flat loop over the concatenated ranges: lanes stay converged on the
 //      distance evaluation instead of idling while others walk different rows;
 //   D  the block [c-1, c+1]^3 is proven complete when `best` is smaller than the
-//      distance to the block's faces that have cells beyond them; otherwise
-//      (rare: sparse regions, queries outside the grid) rings R = 2, 3, ... are
-//      walked row by row with the same strict pruning.
+//      distance to the block's faces that have cells beyond them;
+//   E  otherwise (sparse regions, queries outside the target cloud) a second grid
+//      level of 4x4x4-cell blocks is searched: a converged loop over one representative
+//      point per occupied block bounds `best`, the nearest block is opened first, then
+//      every block (slab, row, cell range) that is not strictly farther than `best`.
 // A cell is skipped only if it is STRICTLY farther than `best` (after a fp32
 // slack), so neither a closer point nor a tie with a lower index can hide in it.
 constexpr int NN_THREADS = 256;
@@ -411,7 +433,8 @@ template <typename IdxT>
 __global__ void __launch_bounds__(NN_THREADS)
 grid_nn_kernel(const float4* __restrict__ sorted0, const float4* __restrict__ sorted1,
                const int* __restrict__ cell_start, int cs_stride,
-               const GridParams* __restrict__ params, const float4* __restrict__ far, int S,
+               const GridParams* __restrict__ params, const float4* __restrict__ far,
+               const float4* __restrict__ reps, int cb_stride, int S,
                int N0, int N1, float* __restrict__ dist0, IdxT* __restrict__ idx0,
                float* __restrict__ dist1, IdxT* __restrict__ idx1) {
   __shared__ int rs[NN_RANGES][NN_THREADS], re[NN_RANGES][NN_THREADS];
@@ -504,59 +527,93 @@ grid_nn_kernel(const float4* __restrict__ sorted0, const float4* __restrict__ so
         }
       }
     }
-    // ---- D: completeness of the block, ring growth ----
-    for (int r = 1;; ++r) {
-      if (r > 1) {
-        const int xlo = max(cx - r, 0), xhi = min(cx + r, g.dx - 1);
-        for (int kz = 0; kz <= 2 * r; ++kz) {
-          const int dz = (kz & 1) ? -((kz + 1) >> 1) : (kz >> 1);
-          const int zc = cz + dz;
-          if (zc < 0 || zc >= g.dz) continue;
-          float lz = dz == 0 ? 0.f : (dz < 0 ? q.z - (g.oz + (float)(zc + 1) * g.h)
-                                              : (g.oz + (float)zc * g.h) - q.z);
-          lz = fmaxf(lz - slack, 0.f);
+    // ---- D: is the 3x3x3 block provably complete? ----
+    bool done = (cx - 1 <= 0) && (cx + 1 >= g.dx - 1) && (cy - 1 <= 0) && (cy + 1 >= g.dy - 1) &&
+                (cz - 1 <= 0) && (cz + 1 >= g.dz - 1);
+    if (!done) {
+      float bound = inf;
+      if (cx - 1 > 0) bound = fminf(bound, q.x - (g.ox + (float)(cx - 1) * g.h));
+      if (cx + 1 < g.dx - 1) bound = fminf(bound, (g.ox + (float)(cx + 2) * g.h) - q.x);
+      if (cy - 1 > 0) bound = fminf(bound, q.y - (g.oy + (float)(cy - 1) * g.h));
+      if (cy + 1 < g.dy - 1) bound = fminf(bound, (g.oy + (float)(cy + 2) * g.h) - q.y);
+      if (cz - 1 > 0) bound = fminf(bound, q.z - (g.oz + (float)(cz - 1) * g.h));
+      if (cz + 1 < g.dz - 1) bound = fminf(bound, (g.oz + (float)(cz + 2) * g.h) - q.z);
+      bound = (bound - slack) * 0.99999f;
+      // every unexplored target is farther than `bound`: strict so that a tie with
+      // a lower index cannot hide outside the block
+      done = bound > 0.0f && best < bound * bound;
+    }
+    // ---- E: (sparse regions, queries outside the target cloud) two-level search ----
+    // over blocks of CB^3 cells: one representative point per occupied block gives an
+    // upper bound in a converged loop; the nearest block is opened first, then every
+    // block whose box is not strictly farther than `best`.
+    if (!done) {
+      const int bx = (g.dx + CB - 1) / CB, by = (g.dy + CB - 1) / CB, bz = (g.dz + CB - 1) / CB;
+      const int ncb = bx * by * bz;
+      const float4* __restrict__ R = reps + (long long)(tc * S + seg) * cb_stride;
+      float rbest = inf;
+      int rcb = -1;
+      for (int cb = 0; cb < ncb; ++cb) {
+        const float4 t = __ldg(R + cb);
+        if (__float_as_int(t.w) < 0) continue;
+        const float d = sqdist_ref(q.x, q.y, q.z, t.x, t.y, t.z);
+        if (d < rbest) { rbest = d; rcb = cb; }
+        if (d <= best) {
+          const int ti = __float_as_int(t.w);
+          if (d < best || ti < bidx) { best = d; bidx = ti; }
+        }
+      }
+      // open one block: rows pruned by their slab distance, x range clipped to the reach left
+      auto open_block = [&](int cbx, int cby, int cbz) {
+        const int x0 = cbx * CB, y0 = cby * CB, z0 = cbz * CB;
+        const int x1 = min(x0 + CB, g.dx) - 1, y1 = min(y0 + CB, g.dy) - 1, z1 = min(z0 + CB, g.dz) - 1;
+        for (int zc = z0; zc <= z1; ++zc) {
+          const float lz = fmaxf(fmaxf((g.oz + (float)zc * g.h) - q.z, q.z - (g.oz + (float)(zc + 1) * g.h)) - slack, 0.f);
           if (lz * lz > best) continue;
-          for (int ky = 0; ky <= 2 * r; ++ky) {
-            const int dy = (ky & 1) ? -((ky + 1) >> 1) : (ky >> 1);
-            const int yc = cy + dy;
-            if (yc < 0 || yc >= g.dy) continue;
-            const bool shell = dz == r || dz == -r || dy == r || dy == -r;
-            float ly = dy == 0 ? 0.f : (dy < 0 ? q.y - (g.oy + (float)(yc + 1) * g.h)
-                                                : (g.oy + (float)yc * g.h) - q.y);
-            ly = fmaxf(ly - slack, 0.f);
+          for (int yc = y0; yc <= y1; ++yc) {
+            const float ly = fmaxf(fmaxf((g.oy + (float)yc * g.h) - q.y, q.y - (g.oy + (float)(yc + 1) * g.h)) - slack, 0.f);
             const float rem = best - (ly * ly + lz * lz);  // squared x-reach left
-            if (rem < 0.f) continue;  // strictly farther than best: cannot win or tie
-            int xa = xlo, xb = xhi;
+            if (rem < 0.f) continue;
+            int xa = x0, xb = x1;
             if (best < 1e30f) {
               const float rad = sqrtf(rem) * 1.00001f + slack;
               xa = max(xa, cell_coord(q.x - rad, g.ox, g.inv_h, g.dx));
               xb = min(xb, cell_coord(q.x + rad, g.ox, g.inv_h, g.dx));
             }
+            if (xa > xb) continue;
             const int row = (zc * g.dy + yc) * g.dx;
-            if (shell) {
-              if (xa <= xb) scan_range(T, cs[row + xa], cs[row + xb + 1], q.x, q.y, q.z, best, bidx);
-            } else {  // interior row of a grown window: only the two new end cells
-              const int xl = cx - r, xr = cx + r;
-              if (xl >= xa && xl <= xb) scan_range(T, cs[row + xl], cs[row + xl + 1], q.x, q.y, q.z, best, bidx);
-              if (xr >= xa && xr <= xb) scan_range(T, cs[row + xr], cs[row + xr + 1], q.x, q.y, q.z, best, bidx);
+            const bool seen = zc >= cz - 1 && zc <= cz + 1 && yc >= cy - 1 && yc <= cy + 1;
+            if (!seen) {
+              scan_range(T, cs[row + xa], cs[row + xb + 1], q.x, q.y, q.z, best, bidx);
+            } else {  // cells cx-1..cx+1 of this row were handled (scanned or pruned) in A-C
+              const int l1 = min(xb, cx - 2), r0 = max(xa, cx + 2);
+              if (xa <= l1) scan_range(T, cs[row + xa], cs[row + l1 + 1], q.x, q.y, q.z, best, bidx);
+              if (r0 <= xb) scan_range(T, cs[row + r0], cs[row + xb + 1], q.x, q.y, q.z, best, bidx);
             }
           }
         }
+      };
+      if (rcb >= 0) open_block(rcb % bx, (rcb / bx) % by, rcb / (bx * by));
+      // lower bound of the distance to a block's box, per axis (0 inside its slab)
+      for (int cbz = 0; cbz < bz; ++cbz) {
+        const float bzl = fmaxf(fmaxf((g.oz + (float)(cbz * CB) * g.h) - q.z,
+                                      q.z - (g.oz + (float)min(cbz * CB + CB, g.dz) * g.h)) - slack, 0.f);
+        if (bzl * bzl > best) continue;  // strictly farther: cannot win or tie
+        for (int cby = 0; cby < by; ++cby) {
+          const float byl = fmaxf(fmaxf((g.oy + (float)(cby * CB) * g.h) - q.y,
+                                        q.y - (g.oy + (float)min(cby * CB + CB, g.dy) * g.h)) - slack, 0.f);
+          const float yz = byl * byl + bzl * bzl;
+          if (yz > best) continue;
+          for (int cbx = 0; cbx < bx; ++cbx) {
+            const float bxl = fmaxf(fmaxf((g.ox + (float)(cbx * CB) * g.h) - q.x,
+                                          q.x - (g.ox + (float)min(cbx * CB + CB, g.dx) * g.h)) - slack, 0.f);
+            if (bxl * bxl + yz > best) continue;
+            const int cb = (cbz * by + cby) * bx + cbx;
+            if (cb == rcb || __float_as_int(__ldg(R + cb).w) < 0) continue;
+            open_block(cbx, cby, cbz);
+          }
+        }
       }
-      const bool covers = (cx - r <= 0) && (cx + r >= g.dx - 1) && (cy - r <= 0) &&
-                          (cy + r >= g.dy - 1) && (cz - r <= 0) && (cz + r >= g.dz - 1);
-      if (covers) break;
-      float bound = inf;
-      if (cx - r > 0) bound = fminf(bound, q.x - (g.ox + (float)(cx - r) * g.h));
-      if (cx + r < g.dx - 1) bound = fminf(bound, (g.ox + (float)(cx + r + 1) * g.h) - q.x);
-      if (cy - r > 0) bound = fminf(bound, q.y - (g.oy + (float)(cy - r) * g.h));
-      if (cy + r < g.dy - 1) bound = fminf(bound, (g.oy + (float)(cy + r + 1) * g.h) - q.y);
-      if (cz - r > 0) bound = fminf(bound, q.z - (g.oz + (float)(cz - r) * g.h));
-      if (cz + r < g.dz - 1) bound = fminf(bound, (g.oz + (float)(cz + r + 1) * g.h) - q.z);
-      bound = (bound - slack) * 0.99999f;
-      // every unexplored target is farther than `bound`: strict so that a tie with
-      // a lower index cannot hide outside the block
-      if (bound > 0.0f && best < bound * bound) break;
     }
   }
   const float4* __restrict__ F = far + (long long)(tc * S + seg) * MAX_FAR;
@@ -624,8 +681,8 @@ static int pick_dmax(int n) {
 }
 
 struct GridLayout {
-  size_t off_params, off_far, off_cs, off_sorted0, off_sorted1, total;
-  int cs_stride;
+  size_t off_params, off_far, off_reps, off_cs, off_sorted0, off_sorted1, total;
+  int cs_stride, cb_stride;
 };
 
 static GridLayout grid_layout(int S, int N0, int N1) {
@@ -635,6 +692,9 @@ static GridLayout grid_layout(int S, int N0, int N1) {
   size_t o = 0;
   L.off_params = o; o = align_up(o + sizeof(GridParams) * 2 * (size_t)S, 256);
   L.off_far = o; o = align_up(o + sizeof(float4) * 2 * (size_t)S * MAX_FAR, 256);
+  const int db = (d + CB - 1) / CB;
+  L.cb_stride = db * db * db;
+  L.off_reps = o; o = align_up(o + sizeof(float4) * 2 * (size_t)S * L.cb_stride, 256);
   L.off_cs = o; o = align_up(o + sizeof(int) * 2 * (size_t)S * L.cs_stride, 256);
   L.off_sorted0 = o; o = align_up(o + sizeof(float4) * (size_t)S * (N0 > 0 ? N0 : 1), 256);
   L.off_sorted1 = o; o = align_up(o + sizeof(float4) * (size_t)S * (N1 > 0 ? N1 : 1), 256);
@@ -652,6 +712,7 @@ static int run_grid(CloudDesc c0, CloudDesc c1, int S, float* dist0, IdxT* idx0,
   char* base = (char*)scratch.base;
   GridParams* params = (GridParams*)(base + L.off_params);
   float4* far = (float4*)(base + L.off_far);
+  float4* reps = (float4*)(base + L.off_reps);
   int* cs = (int*)(base + L.off_cs);
   float4* s0 = (float4*)(base + L.off_sorted0);
   float4* s1 = (float4*)(base + L.off_sorted1);
@@ -684,7 +745,8 @@ static int run_grid(CloudDesc c0, CloudDesc c1, int S, float* dist0, IdxT* idx0,
   {
     ProfScope ps(c0.fill_invalid ? "chamfer_grid_build_shape" : (c0.quat ? "chamfer_grid_build_part" : "chamfer_grid_build"), stream);
     grid_build_kernel<IdxT><<<2 * S, threads, smem, stream>>>(c0, c1, S, s0, s1, cs, L.cs_stride,
-                                                              params, far, dist0, idx0, dist1, idx1);
+                                                              params, far, reps, L.cb_stride, dist0, idx0,
+                                                              dist1, idx1);
   }
   MPA_LAUNCH_CHECK();
   const long long warps = (long long)S * ((c0.Nseg + 31) / 32 + (c1.Nseg + 31) / 32);
@@ -693,7 +755,8 @@ static int run_grid(CloudDesc c0, CloudDesc c1, int S, float* dist0, IdxT* idx0,
     {
       ProfScope ps(c0.fill_invalid ? "chamfer_grid_nn_shape" : (c0.quat ? "chamfer_grid_nn_part" : "chamfer_grid_nn"), stream);
       grid_nn_kernel<IdxT><<<(unsigned)blocks, 256, 0, stream>>>(
-          s0, s1, cs, L.cs_stride, params, far, S, c0.Nseg, c1.Nseg, dist0, idx0, dist1, idx1);
+          s0, s1, cs, L.cs_stride, params, far, reps, L.cb_stride, S, c0.Nseg, c1.Nseg, dist0, idx0, dist1,
+          idx1);
     }
     MPA_LAUNCH_CHECK();
   }

@@ -22,12 +22,12 @@
 namespace mpa {
 
 constexpr int LN_BM = 128;      // rows per tile (UMMA M)
-constexpr int LN_BN = 128;      // columns per tile (UMMA N)
 constexpr int LN_BK = 64;       // k per stage (one 128-byte swizzle span of bf16)
 constexpr int LN_STAGES = 4;
-constexpr int LN_THREADS = 192;  // warp 0: TMA, warp 1: MMA, warps 2-5: epilogue
-constexpr int LN_STAGE_BYTES = (LN_BM + LN_BN) * LN_BK * 2;
-constexpr int LN_SMEM = LN_STAGES * LN_STAGE_BYTES + 1024;
+constexpr int LN_EPI_WARPS = 8;  // two warps per TMEM lane quadrant, each takes half of the columns
+constexpr int LN_THREADS = 64 + 32 * LN_EPI_WARPS;  // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue
+__host__ __device__ constexpr int ln_stage_bytes(int bn) { return (LN_BM + bn) * LN_BK * 2; }
+__host__ __device__ constexpr int ln_smem_bytes(int bn) { return LN_STAGES * ln_stage_bytes(bn) + 1024; }
 
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY02 = 2 };
 
@@ -37,6 +37,13 @@ struct LinearEpilogue {
   float* out_f32;          // [M, N] or nullptr
   __nv_bfloat16* out_bf16; // [M, N] or nullptr
   int act;
+  // fused LayerNorm of the finished row (only when one tile spans the row: N == tile width)
+  const float* ln_gamma = nullptr;
+  const float* ln_beta = nullptr;
+  float ln_eps = 0.f;
+  __nv_bfloat16* ln_out_bf16 = nullptr;  // LayerNorm(out) as the next GEMM's operand
+  float* ln_out_f32 = nullptr;           // ... and/or in fp32 (final encoder norm)
+  int vec = 0;                           // rows are 16-byte aligned: packed loads / stores
 };
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1,
@@ -52,6 +59,65 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
                : "memory");
 }
 
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == ACT_RELU) return fmaxf(x, 0.f);
+  if (act == ACT_LEAKY02) return x > 0.f ? x : 0.2f * x;
+  return x;
+}
+
+// v[32] (one row, columns col0 .. col0+31, all inside N) <- act(v + bias) + residual
+__device__ __forceinline__ void epilogue_math_vec(float* v, const LinearEpilogue& ep, const float* res_row,
+                                                  int col0, bool row_ok) {
+  if (ep.bias != nullptr) {
+    const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = __ldg(b4 + j);
+      v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+    }
+  }
+  if (ep.act != ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
+  }
+  if (res_row != nullptr && row_ok) {
+    float4 r[8];
+    const float4* r4 = reinterpret_cast<const float4*>(res_row + col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = r4[j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[4 * j + 0] += r[j].x; v[4 * j + 1] += r[j].y; v[4 * j + 2] += r[j].z; v[4 * j + 3] += r[j].w;
+    }
+  }
+}
+__device__ __forceinline__ void store_f32_vec(float* dst, const float* v) {
+  float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+__device__ __forceinline__ void store_bf16_vec(__nv_bfloat16* dst, const float* v) {
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[8 * j + 0], v[8 * j + 1]);
+    __nv_bfloat162 b = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+    __nv_bfloat162 d = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+    u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
+    d4[j] = u;
+  }
+}
+
+// One CTA = one 128 x BN output tile.  Epilogue thread = one output row (its TMEM
+// lane) and half of the tile's columns, 32 at a time straight from tcgen05.ld: the
+// row segment is contiguous in memory, so bias / residual / output move as 16-byte
+// packets without a shared-memory transpose.  FUSE_LN (BN == N): the finished row
+// (residual stream) is parked back in TMEM and LayerNorm-ed from there in two more
+// passes (mean, then centred variance), the two half-row warps meeting in shared memory.
+template <int BN, bool FUSE_LN>
 __global__ void __launch_bounds__(LN_THREADS, 1)
 linear_bf16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                    int M, int N, int K, LinearEpilogue ep) {
@@ -59,9 +125,11 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t full_bar[LN_STAGES], empty_bar[LN_STAGES], done_bar;
   __shared__ uint32_t tmem_base_s;
+  __shared__ float ln_part[2][2][LN_BM];
+  constexpr int STAGE = ln_stage_bytes(BN);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * LN_BM, n0 = blockIdx.y * LN_BN;
+  const int m0 = blockIdx.x * LN_BM, n0 = blockIdx.y * BN;
   const int num_k = (K + LN_BK - 1) / LN_BK;
 
   if (threadIdx.x == 0) {
@@ -69,7 +137,7 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     tc::mbar_init(&done_bar, 1);
     tc::fence_barrier_init();
   }
-  if (warp == 1) tc::tmem_alloc<LN_BN>(&tmem_base_s);
+  if (warp == 1) tc::tmem_alloc<BN>(&tmem_base_s);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -80,21 +148,21 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       for (int kb = 0; kb < num_k; ++kb) {
         const int s = kb % LN_STAGES;
         if (kb >= LN_STAGES) tc::mbar_wait(&empty_bar[s], ((kb / LN_STAGES) - 1) & 1);
-        uint8_t* a_dst = smem + s * LN_STAGE_BYTES;
+        uint8_t* a_dst = smem + s * STAGE;
         uint8_t* b_dst = a_dst + LN_BM * LN_BK * 2;
-        mbar_expect_tx(&full_bar[s], LN_STAGE_BYTES);
+        mbar_expect_tx(&full_bar[s], STAGE);
         tma_load_2d(a_dst, &map_x, kb * LN_BK, m0, &full_bar[s]);
         tma_load_2d(b_dst, &map_w, kb * LN_BK, n0, &full_bar[s]);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {  // ===== MMA issuer =====
-      constexpr uint32_t IDESC = tc::make_idesc_bf16(LN_BM, LN_BN);
+      constexpr uint32_t IDESC = tc::make_idesc_bf16(LN_BM, BN);
       for (int kb = 0; kb < num_k; ++kb) {
         const int s = kb % LN_STAGES;
         tc::mbar_wait(&full_bar[s], (kb / LN_STAGES) & 1);
         tc::fence_after_sync();
-        const uint32_t a_addr = tc::smem_u32(smem + s * LN_STAGE_BYTES);
+        const uint32_t a_addr = tc::smem_u32(smem + s * STAGE);
         const uint32_t b_addr = a_addr + LN_BM * LN_BK * 2;
 #pragma unroll
         for (int k = 0; k < LN_BK; k += 16)
@@ -104,51 +172,100 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       }
       tc::mma_commit(&done_bar);
     }
-  } else {  // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
+  } else {  // ===== epilogue: warps 2..9, TMEM lane quadrant = warp % 4 =====
     tc::mbar_wait(&done_bar, 0);
     tc::fence_after_sync();
-    const int q = warp & 3;
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int row_local = q * 32 + lane;
+    const int row = m0 + row_local;
+    const bool row_ok = row < M;
     const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
-    // the operand ring is idle now: reuse it as a [32][33] fp32 transpose tile per
-    // warp so that global stores / residual loads are coalesced along N
-    float* stage = reinterpret_cast<float*>(smem) + q * (32 * 33);
+    const int c_begin = half * (BN / 2), c_end = c_begin + BN / 2;
+    const long long rowoff = (long long)row * N;
+    if (!FUSE_LN) {
 #pragma unroll 1
-    for (int j0 = 0; j0 < LN_BN; j0 += 32) {
-      float v[32];
-      tc::tmem_ld32(taddr + (uint32_t)j0, v);
-      tc::tmem_ld_wait();
+      for (int j0 = c_begin; j0 < c_end; j0 += 32) {
+        const int col0 = n0 + j0;
+        if (col0 >= N) break;  // warp-uniform
+        float v[32];
+        tc::tmem_ld32(taddr + (uint32_t)j0, v);
+        tc::tmem_ld_wait();
+        if (ep.vec && col0 + 32 <= N) {
+          epilogue_math_vec(v, ep, ep.residual ? ep.residual + rowoff : nullptr, col0, row_ok);
+          if (row_ok) {
+            if (ep.out_f32) store_f32_vec(ep.out_f32 + rowoff + col0, v);
+            if (ep.out_bf16) store_bf16_vec(ep.out_bf16 + rowoff + col0, v);
+          }
+        } else if (row_ok) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = v[j];  // row = lane
-      __syncwarp();
-      const int col = n0 + j0 + lane;
-      if (col < N) {
-        const float bias = ep.bias ? __ldg(ep.bias + col) : 0.f;
-        const int row0 = m0 + q * 32;
-        // residual may alias the output (x += f(x)): fetch the whole 32-row slab
-        // before the first store so the loads are not serialised behind stores
-        float res[32];
-#pragma unroll
-        for (int r = 0; r < 32; ++r)
-          res[r] = (ep.residual != nullptr && row0 + r < M) ? ep.residual[(long long)(row0 + r) * N + col] : 0.f;
-#pragma unroll
-        for (int r = 0; r < 32; ++r) {
-          if (row0 + r < M) {
-            float x = stage[r * 33 + lane] + bias;
-            if (ep.act == ACT_RELU) x = fmaxf(x, 0.f);
-            else if (ep.act == ACT_LEAKY02) x = x > 0.f ? x : 0.2f * x;
-            x += res[r];
-            const long long o = (long long)(row0 + r) * N + col;
-            if (ep.out_f32) ep.out_f32[o] = x;
-            if (ep.out_bf16) ep.out_bf16[o] = __float2bfloat16_rn(x);
+          for (int j = 0; j < 32; ++j) {
+            const int col = col0 + j;
+            if (col >= N) continue;
+            float x = v[j] + (ep.bias ? __ldg(ep.bias + col) : 0.f);
+            x = apply_act(x, ep.act);
+            if (ep.residual) x += ep.residual[rowoff + col];
+            if (ep.out_f32) ep.out_f32[rowoff + col] = x;
+            if (ep.out_bf16) ep.out_bf16[rowoff + col] = __float2bfloat16_rn(x);
           }
         }
       }
-      __syncwarp();
+    } else {
+      // pass 1: finished row -> fp32 output + back into TMEM; row sum
+      float sum = 0.f;
+#pragma unroll 1
+      for (int j0 = c_begin; j0 < c_end; j0 += 32) {
+        float v[32];
+        tc::tmem_ld32(taddr + (uint32_t)j0, v);
+        tc::tmem_ld_wait();
+        epilogue_math_vec(v, ep, ep.residual ? ep.residual + rowoff : nullptr, j0, row_ok);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sum += v[j];
+        if (row_ok && ep.out_f32) store_f32_vec(ep.out_f32 + rowoff + j0, v);
+        tc::tmem_st32(taddr + (uint32_t)j0, v);
+      }
+      tc::tmem_st_wait();
+      ln_part[0][half][row_local] = sum;
+      tc::group_sync(1, LN_EPI_WARPS * 32);
+      const float mean = (ln_part[0][0][row_local] + ln_part[0][1][row_local]) / (float)N;
+      // pass 2: centred sum of squares
+      float sq = 0.f;
+#pragma unroll 1
+      for (int j0 = c_begin; j0 < c_end; j0 += 32) {
+        float v[32];
+        tc::tmem_ld32(taddr + (uint32_t)j0, v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { const float d = v[j] - mean; sq = fmaf(d, d, sq); }
+      }
+      ln_part[1][half][row_local] = sq;
+      tc::group_sync(1, LN_EPI_WARPS * 32);
+      const float rstd = rsqrtf((ln_part[1][0][row_local] + ln_part[1][1][row_local]) / (float)N + ep.ln_eps);
+      // pass 3: normalise, scale, shift
+#pragma unroll 1
+      for (int j0 = c_begin; j0 < c_end; j0 += 32) {
+        float v[32];
+        tc::tmem_ld32(taddr + (uint32_t)j0, v);
+        tc::tmem_ld_wait();
+        const float4* g4 = reinterpret_cast<const float4*>(ep.ln_gamma + j0);
+        const float4* b4 = reinterpret_cast<const float4*>(ep.ln_beta + j0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 g = __ldg(g4 + j), b = __ldg(b4 + j);
+          v[4 * j + 0] = (v[4 * j + 0] - mean) * rstd * g.x + b.x;
+          v[4 * j + 1] = (v[4 * j + 1] - mean) * rstd * g.y + b.y;
+          v[4 * j + 2] = (v[4 * j + 2] - mean) * rstd * g.z + b.z;
+          v[4 * j + 3] = (v[4 * j + 3] - mean) * rstd * g.w + b.w;
+        }
+        if (row_ok) {
+          if (ep.ln_out_bf16) store_bf16_vec(ep.ln_out_bf16 + rowoff + j0, v);
+          if (ep.ln_out_f32) store_f32_vec(ep.ln_out_f32 + rowoff + j0, v);
+        }
+      }
     }
     tc::fence_before_sync();
   }
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc<LN_BN>(tmem);
+  if (warp == 1) tc::tmem_dealloc<BN>(tmem);
 }
 
 // ---- driver-API entry point for tensor maps, resolved at run time (no -lcuda) ----
@@ -168,8 +285,8 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// bf16 row-major [rows, cols] matrix, box = {64 cols, 128 rows}, 128-byte swizzle, zero OOB fill
-static int make_map(CUtensorMap* map, const void* base, int rows, int cols) {
+// bf16 row-major [rows, cols] matrix, box = {64 cols, box_rows rows}, 128-byte swizzle, zero OOB fill
+static int make_map(CUtensorMap* map, const void* base, int rows, int cols, int box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -177,7 +294,7 @@ static int make_map(CUtensorMap* map, const void* base, int rows, int cols) {
   }
   const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t gstride[1] = {(cuuint64_t)cols * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)LN_BK, (cuuint32_t)LN_BM};
+  const cuuint32_t box[2] = {(cuuint32_t)LN_BK, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box,
                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -189,23 +306,42 @@ static int make_map(CUtensorMap* map, const void* base, int rows, int cols) {
   return MPA_OK;
 }
 
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+constexpr int LN_FUSED_WIDTH = 256;  // row width the fused-LayerNorm tile supports (d_model of the reference)
+
 int launch_linear(const __nv_bfloat16* x, const __nv_bfloat16* w, int M, int N, int K,
-                  const LinearEpilogue& ep, const char* name, cudaStream_t stream) {
+                  LinearEpilogue ep, const char* name, cudaStream_t stream) {
   MPA_CHECK_ARG(K % 8 == 0, "linear: K must be a multiple of 8 (got %d)", K);
+  const bool fuse_ln = ep.ln_gamma != nullptr;
+  ep.vec = (N % 8 == 0) && aligned16(ep.bias) && aligned16(ep.residual) && aligned16(ep.out_f32) &&
+           aligned16(ep.out_bf16) && aligned16(ep.ln_gamma) && aligned16(ep.ln_beta) &&
+           aligned16(ep.ln_out_bf16) && aligned16(ep.ln_out_f32);
+  if (fuse_ln)
+    MPA_CHECK_ARG(N == LN_FUSED_WIDTH && ep.vec && ep.ln_beta != nullptr,
+                  "linear: fused LayerNorm needs N == %d and 16-byte aligned rows", LN_FUSED_WIDTH);
+  const int bn = fuse_ln ? LN_FUSED_WIDTH : 128;
   CUtensorMap mx, mw;
-  int rc = make_map(&mx, x, M, K);
+  int rc = make_map(&mx, x, M, K, LN_BM);
   if (rc != MPA_OK) return rc;
-  rc = make_map(&mw, w, N, K);
+  rc = make_map(&mw, w, N, K, bn);
   if (rc != MPA_OK) return rc;
   static bool attr = false;
   if (!attr) {
-    MPA_CUDA(cudaFuncSetAttribute(linear_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM));
+    MPA_CUDA(cudaFuncSetAttribute(linear_bf16_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  ln_smem_bytes(128)));
+    MPA_CUDA(cudaFuncSetAttribute(linear_bf16_kernel<LN_FUSED_WIDTH, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, ln_smem_bytes(LN_FUSED_WIDTH)));
     attr = true;
   }
-  dim3 grid((M + LN_BM - 1) / LN_BM, (N + LN_BN - 1) / LN_BN);
+  dim3 grid((M + LN_BM - 1) / LN_BM, (N + bn - 1) / bn);
   {
     ProfScope ps(name, stream);
-    linear_bf16_kernel<<<grid, LN_THREADS, LN_SMEM, stream>>>(mx, mw, M, N, K, ep);
+    if (fuse_ln)
+      linear_bf16_kernel<LN_FUSED_WIDTH, true><<<grid, LN_THREADS, ln_smem_bytes(LN_FUSED_WIDTH), stream>>>(
+          mx, mw, M, N, K, ep);
+    else
+      linear_bf16_kernel<128, false><<<grid, LN_THREADS, ln_smem_bytes(128), stream>>>(mx, mw, M, N, K, ep);
   }
   MPA_LAUNCH_CHECK();
   return MPA_OK;
@@ -352,9 +488,13 @@ int mpa_linear_forward(const float* x, const float* w, const float* bias, const 
   if (rc != MPA_OK) return rc;
   __nv_bfloat16* xb = (__nv_bfloat16*)scratch.base;
   __nv_bfloat16* wb = (__nv_bfloat16*)((char*)scratch.base + align_up((size_t)M * K * 2, 256));
-  f32_to_bf16_kernel<<<148, 256, 0, stream>>>(x, xb, (long long)M * K);
-  MPA_LAUNCH_CHECK();
-  f32_to_bf16_kernel<<<148, 256, 0, stream>>>(w, wb, (long long)N * K);
+  {
+    ProfScope ps("linear_operands_to_bf16", stream);
+    CvtBatch cb;
+    cb.src[0] = x; cb.dst[0] = xb; cb.n[0] = (long long)M * K;
+    cb.src[1] = w; cb.dst[1] = wb; cb.n[1] = (long long)N * K;
+    f32_to_bf16_batch_kernel<<<dim3(64, 2), 256, 0, stream>>>(cb);
+  }
   MPA_LAUNCH_CHECK();
   LinearEpilogue ep{bias, residual, out, nullptr, act};
   return launch_linear(xb, wb, M, N, K, ep, "linear_bf16", stream);
@@ -418,14 +558,24 @@ int mpa_transformer_forward(const float* tokens, const unsigned char* valid, int
     f32_to_bf16_batch_kernel<<<dim3(32, layers * 4), 256, 0, stream>>>(cb);
   }
   MPA_LAUNCH_CHECK();
-  MPA_CUDA(cudaMemcpyAsync(x, tokens, (size_t)T * D * 4, cudaMemcpyDeviceToDevice, stream));
   const int ln_blocks = (T * 32 + 255) / 256;
   const size_t att_smem = (size_t)(2 * P * hd + P * (hd + 1)) * sizeof(float);
+  // D == 256 (the reference's d_model): the two GEMMs that finish a residual-stream row
+  // (out_proj, FFN2) apply the NEXT LayerNorm in their epilogue -> 5 launches per layer
+  const bool fused = D == LN_FUSED_WIDTH;
+  if (!fused) MPA_CUDA(cudaMemcpyAsync(x, tokens, (size_t)T * D * 4, cudaMemcpyDeviceToDevice, stream));
+  if (fused && layers > 0) {
+    ProfScope ps("layernorm", stream);
+    layernorm_kernel<<<ln_blocks, 256, 0, stream>>>(tokens, norm1_w[0], norm1_b[0], T, D, eps, xn, nullptr);
+    MPA_LAUNCH_CHECK();
+  }
   for (int l = 0; l < layers; ++l) {
     const __nv_bfloat16* wl = wts + (size_t)l * per_layer;
-    { ProfScope ps("layernorm", stream);
-      layernorm_kernel<<<ln_blocks, 256, 0, stream>>>(x, norm1_w[l], norm1_b[l], T, D, eps, xn, nullptr); }
-    MPA_LAUNCH_CHECK();
+    if (!fused) {
+      { ProfScope ps("layernorm", stream);
+        layernorm_kernel<<<ln_blocks, 256, 0, stream>>>(x, norm1_w[l], norm1_b[l], T, D, eps, xn, nullptr); }
+      MPA_LAUNCH_CHECK();
+    }
     LinearEpilogue e_qkv{in_proj_b[l], nullptr, qkv, nullptr, ACT_NONE};
     rc = launch_linear(xn, wl, T, 3 * D, D, e_qkv, "linear_qkv", stream);
     if (rc != MPA_OK) return rc;
@@ -433,25 +583,38 @@ int mpa_transformer_forward(const float* tokens, const unsigned char* valid, int
       attention_kernel<<<B * H, ATT_WARPS * 32, att_smem, stream>>>(
           qkv, valid, B, P, H, hd, att); }
     MPA_LAUNCH_CHECK();
-    LinearEpilogue e_o{out_proj_b[l], x, x, nullptr, ACT_NONE};
+    // x <- x + out_proj(att)  [+ xn <- LayerNorm2(x)]
+    LinearEpilogue e_o{out_proj_b[l], (fused && l == 0) ? tokens : x, x, nullptr, ACT_NONE};
+    if (fused) { e_o.ln_gamma = norm2_w[l]; e_o.ln_beta = norm2_b[l]; e_o.ln_eps = eps; e_o.ln_out_bf16 = xn; }
     rc = launch_linear(att, wl + (size_t)3 * D * D, T, D, D, e_o, "linear_out_proj", stream);
     if (rc != MPA_OK) return rc;
-    { ProfScope ps("layernorm", stream);
-      layernorm_kernel<<<ln_blocks, 256, 0, stream>>>(x, norm2_w[l], norm2_b[l], T, D, eps, xn, nullptr); }
-    MPA_LAUNCH_CHECK();
+    if (!fused) {
+      { ProfScope ps("layernorm", stream);
+        layernorm_kernel<<<ln_blocks, 256, 0, stream>>>(x, norm2_w[l], norm2_b[l], T, D, eps, xn, nullptr); }
+      MPA_LAUNCH_CHECK();
+    }
     LinearEpilogue e_f1{lin1_b[l], nullptr, nullptr, hid, ACT_RELU};
     rc = launch_linear(xn, wl + (size_t)4 * D * D, T, FF, D, e_f1, "linear_ffn1", stream);
     if (rc != MPA_OK) return rc;
-    LinearEpilogue e_f2{lin2_b[l], x, x, nullptr, ACT_NONE};
+    // x <- x + FFN2(hid)  [+ LayerNorm1 of the next layer, or the final encoder norm]
+    const bool last = l + 1 == layers;
+    LinearEpilogue e_f2{lin2_b[l], x, (fused && last) ? (final_norm_w == nullptr ? out : nullptr) : x, nullptr, ACT_NONE};
+    if (fused && !last) {
+      e_f2.ln_gamma = norm1_w[l + 1]; e_f2.ln_beta = norm1_b[l + 1]; e_f2.ln_eps = eps; e_f2.ln_out_bf16 = xn;
+    } else if (fused && final_norm_w != nullptr) {
+      e_f2.ln_gamma = final_norm_w; e_f2.ln_beta = final_norm_b; e_f2.ln_eps = eps; e_f2.ln_out_f32 = out;
+    }
     rc = launch_linear(hid, wl + (size_t)4 * D * D + (size_t)FF * D, T, D, FF, e_f2, "linear_ffn2", stream);
     if (rc != MPA_OK) return rc;
   }
+  if (fused && layers > 0) return MPA_OK;
   if (final_norm_w != nullptr) {
     { ProfScope ps("layernorm", stream);
-      layernorm_kernel<<<ln_blocks, 256, 0, stream>>>(x, final_norm_w, final_norm_b, T, D, eps, nullptr, out); }
+      layernorm_kernel<<<ln_blocks, 256, 0, stream>>>(layers > 0 ? x : tokens, final_norm_w, final_norm_b, T, D,
+                                                      eps, nullptr, out); }
     MPA_LAUNCH_CHECK();
   } else {
-    MPA_CUDA(cudaMemcpyAsync(out, x, (size_t)T * D * 4, cudaMemcpyDeviceToDevice, stream));
+    MPA_CUDA(cudaMemcpyAsync(out, layers > 0 ? x : tokens, (size_t)T * D * 4, cudaMemcpyDeviceToDevice, stream));
   }
   return MPA_OK;
 }

@@ -129,6 +129,121 @@ __global__ void pose_outputs_kernel(const float* __restrict__ f, int T, int K,
   }
 }
 
+
+// ---- whole pose head in one launch ------------------------------------------
+// PoseRegressor.forward (models/modules/regressor.py:58-68): fc(K0->H1) LeakyReLU
+// fc(H1->H2) LeakyReLU, rot_head(H2->4) (+ L2 normalisation), trans_head(H2->3), fp32
+// on the CUDA cores (0.1 MMAC per token: the cost is reading the weights, once per CTA
+// of PH_TOK tokens, with coalesced row reads).  A warp owns an output channel: lanes
+// split k, the 8 per-token partial sums are folded with a transposing butterfly
+// (9 shuffles) so that lane 4t ends up with token t's total.
+constexpr int PH_TOK = 8;
+constexpr int PH_THREADS = 512;
+
+__device__ __forceinline__ float fold8(const float (&a)[8], int lane) {
+  float b[4], c[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool hi = lane & 16;
+    const float recv = __shfl_xor_sync(0xffffffffu, hi ? a[i] : a[i + 4], 16);
+    b[i] = (hi ? a[i + 4] : a[i]) + recv;
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const bool hi = lane & 8;
+    const float recv = __shfl_xor_sync(0xffffffffu, hi ? b[i] : b[i + 2], 8);
+    c[i] = (hi ? b[i + 2] : b[i]) + recv;
+  }
+  const bool hi = lane & 4;
+  float d = (hi ? c[1] : c[0]) + __shfl_xor_sync(0xffffffffu, hi ? c[0] : c[1], 4);
+  d += __shfl_xor_sync(0xffffffffu, d, 2);
+  d += __shfl_xor_sync(0xffffffffu, d, 1);
+  return d;  // token (lane >> 2), complete in every lane of its group of 4
+}
+
+// hout[t][j] = act(b[j] + sum_k W[j][k] xin[t][k]) for the CTA's PH_TOK tokens (all in shared memory)
+__device__ void ph_layer(const float* __restrict__ xin, int K, const float* __restrict__ W,
+                         const float* __restrict__ b, int J, int act, float* __restrict__ hout) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int kc = 0; kc < K; kc += 256) {
+    float xr[PH_TOK][8];
+#pragma unroll
+    for (int t = 0; t < PH_TOK; ++t)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = kc + lane + 32 * i;
+        xr[t][i] = k < K ? xin[t * K + k] : 0.f;
+      }
+    for (int j = warp; j < J; j += nwarps) {
+      float wv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = kc + lane + 32 * i;
+        wv[i] = k < K ? __ldg(W + (long long)j * K + k) : 0.f;
+      }
+      float a[PH_TOK];
+#pragma unroll
+      for (int t = 0; t < PH_TOK; ++t) {
+        a[t] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[t] = fmaf(wv[i], xr[t][i], a[t]);
+      }
+      const float d = fold8(a, lane);
+      if ((lane & 3) == 0) {
+        float* o = hout + (lane >> 2) * J + j;
+        *o = (kc == 0) ? d + __ldg(b + j) : *o + d;
+      }
+    }
+  }
+  __syncthreads();
+  if (act == 2) {
+    for (int i = threadIdx.x; i < PH_TOK * J; i += blockDim.x) {
+      const float v = hout[i];
+      hout[i] = v > 0.f ? v : 0.2f * v;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(PH_THREADS)
+pose_head_kernel(const float* __restrict__ x, int T, int K0, const float* __restrict__ w0,
+                 const float* __restrict__ b0, int H1, const float* __restrict__ w1,
+                 const float* __restrict__ b1, int H2, const float* __restrict__ wr,
+                 const float* __restrict__ br, const float* __restrict__ wt,
+                 const float* __restrict__ bt, int normalize, float* __restrict__ rot,
+                 float* __restrict__ trans) {
+  extern __shared__ float ph_smem[];
+  float* xs = ph_smem;                 // [PH_TOK][K0]
+  float* h1 = xs + PH_TOK * K0;        // [PH_TOK][H1]
+  float* h2 = h1 + PH_TOK * H1;        // [PH_TOK][H2]
+  float* hq = h2 + PH_TOK * H2;        // [PH_TOK][4]
+  float* ht = hq + PH_TOK * 4;         // [PH_TOK][3]
+  const int tok0 = blockIdx.x * PH_TOK;
+  for (int i = threadIdx.x; i < PH_TOK * K0; i += blockDim.x) {
+    const int t = tok0 + i / K0;
+    xs[i] = t < T ? x[(long long)t * K0 + i % K0] : 0.f;
+  }
+  __syncthreads();
+  ph_layer(xs, K0, w0, b0, H1, 2, h1);
+  ph_layer(h1, H1, w1, b1, H2, 2, h2);
+  ph_layer(h2, H2, wr, br, 4, 0, hq);
+  ph_layer(h2, H2, wt, bt, 3, 0, ht);
+  if (threadIdx.x < PH_TOK && tok0 + threadIdx.x < T) {
+    const int t = threadIdx.x;
+    float q[4] = {hq[t * 4], hq[t * 4 + 1], hq[t * 4 + 2], hq[t * 4 + 3]};
+    if (normalize) {  // F.normalize(p=2, dim=-1, eps=1e-12)
+      const float n = fmaxf(sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]), 1e-12f);
+#pragma unroll
+      for (int o = 0; o < 4; ++o) q[o] /= n;
+    }
+    const long long tok = tok0 + t;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) rot[tok * 4 + o] = q[o];
+#pragma unroll
+    for (int o = 0; o < 3; ++o) trans[tok * 3 + o] = ht[t * 3 + o];
+  }
+}
+
 }  // namespace mpa
 
 using namespace mpa;
@@ -178,6 +293,32 @@ int mpa_pose_outputs(const float* feats, int T, int K, const float* rot_w, const
     ProfScope ps("pose_outputs", stream);
     pose_outputs_kernel<<<(T * 32 + 255) / 256, 256, 0, stream>>>(feats, T, K, rot_w, rot_b, trans_w,
                                                                   trans_b, normalize, rot, trans);
+  }
+  MPA_LAUNCH_CHECK();
+  return MPA_OK;
+}
+
+int mpa_pose_head_forward(const float* feats, int T, int K0, const float* fc0_w, const float* fc0_b,
+                          int H1, const float* fc1_w, const float* fc1_b, int H2, const float* rot_w,
+                          const float* rot_b, const float* trans_w, const float* trans_b, int normalize,
+                          float* rot, float* trans, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MPA_CHECK_ARG(T >= 0 && K0 > 0 && H1 > 0 && H2 > 0, "pose_head_forward: bad sizes");
+  if (T == 0) return MPA_OK;
+  MPA_CHECK_ARG(feats && fc0_w && fc0_b && fc1_w && fc1_b && rot_w && rot_b && trans_w && trans_b && rot &&
+                    trans, "pose_head_forward: null pointer");
+  const size_t smem = sizeof(float) * PH_TOK * ((size_t)K0 + H1 + H2 + 7);
+  MPA_CHECK_ARG(smem <= 200 * 1024, "pose_head_forward: layer widths too large (%d, %d, %d)", K0, H1, H2);
+  static size_t attr_smem = 48 * 1024;
+  if (smem > attr_smem) {
+    MPA_CUDA(cudaFuncSetAttribute(pose_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  {
+    ProfScope ps("pose_head", stream);
+    pose_head_kernel<<<(T + PH_TOK - 1) / PH_TOK, PH_THREADS, smem, stream>>>(
+        feats, T, K0, fc0_w, fc0_b, H1, fc1_w, fc1_b, H2, rot_w, rot_b, trans_w, trans_b, normalize, rot,
+        trans);
   }
   MPA_LAUNCH_CHECK();
   return MPA_OK;

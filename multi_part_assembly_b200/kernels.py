@@ -106,9 +106,8 @@ class _PointNetFunction(torch.autograd.Function):
                 float(bns[0].eps), float(bns[0].momentum), _lib.ptr(feats), _lib.ptr(ws),
                 ws_bytes, _lib.cuda_stream(dev))
         _lib.check(rc, 'mpa_pointnet_forward')
-        if training:
-            for b in bns:
-                b.num_batches_tracked += 1
+        if training:  # one multi-tensor launch instead of five scalar adds
+            torch._foreach_add_([b.num_batches_tracked for b in bns], 1)
         ctx.save_for_backward(x, valids if valids is not None else x.new_empty(0))
         ctx.modules = modules
         ctx.training = training
@@ -222,23 +221,22 @@ def linear(x, w, bias=None, act=0, residual=None):
 
 def pose_head_forward(x, head):
     """PoseRegressor.forward (models/modules/regressor.py:58-68) for the
-    quaternion head without autograd: the two hidden layers on the tcgen05
-    linear kernel (LeakyReLU fused), the 4+3 output rows and the quaternion
-    normalisation in one small kernel."""
+    quaternion head without autograd: both hidden layers, the 4+3 output rows
+    and the quaternion normalisation in one fp32 kernel (csrc/loss.cu)."""
     shape = x.shape[:-1]
-    h = x.reshape(-1, x.shape[-1])
-    fc0, fc2 = head.fc_layers[0], head.fc_layers[2]
-    h = linear(h, fc0.weight, fc0.bias, act=2)
-    h = linear(h, fc2.weight, fc2.bias, act=2)
+    h = x.reshape(-1, x.shape[-1]).float().contiguous()
+    fc0, fc1 = head.fc_layers[0], head.fc_layers[2]
     T = h.shape[0]
     rot = torch.empty(T, 4, dtype=torch.float32, device=h.device)
     trans = torch.empty(T, 3, dtype=torch.float32, device=h.device)
     with torch.cuda.device(h.device):
-        rc = _lib.lib().mpa_pose_outputs(
-            _lib.ptr(h), T, h.shape[1], _lib.ptr(head.rot_head.weight), _lib.ptr(head.rot_head.bias),
+        rc = _lib.lib().mpa_pose_head_forward(
+            _lib.ptr(h), T, h.shape[1], _lib.ptr(fc0.weight), _lib.ptr(fc0.bias), fc0.out_features,
+            _lib.ptr(fc1.weight), _lib.ptr(fc1.bias), fc1.out_features,
+            _lib.ptr(head.rot_head.weight), _lib.ptr(head.rot_head.bias),
             _lib.ptr(head.trans_head.weight), _lib.ptr(head.trans_head.bias),
             1 if head.norm_rot else 0, _lib.ptr(rot), _lib.ptr(trans), _lib.cuda_stream(h.device))
-    _lib.check(rc, 'mpa_pose_outputs')
+    _lib.check(rc, 'mpa_pose_head_forward')
     return rot.view(*shape, 4), trans.view(*shape, 3)
 
 

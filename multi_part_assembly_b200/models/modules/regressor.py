@@ -33,9 +33,8 @@ class PoseRegressor(nn.Module):
 
     def forward(self, x):
         from ... import kernels
-        if self.rot_type == 'quat' and x.is_cuda and not torch.is_grad_enabled() and \
-                kernels._use_bf16():
-            return kernels.pose_head_forward(x, self)  # native, forward only
+        if self.rot_type == 'quat' and x.is_cuda and not torch.is_grad_enabled():
+            return kernels.pose_head_forward(x, self)  # native (fp32), forward only
         f = self.fc_layers(x)
         rot = self.rot_head(f)
         if self.norm_rot:

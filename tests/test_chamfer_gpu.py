@@ -111,6 +111,24 @@ def test_grid_equals_brute_full_size(cuda):
     np.testing.assert_array_equal(a[3][:1], j2)
 
 
+@pytest.mark.parametrize('n,offset', [(20000, 0.0), (20000, 1.5), (1000, 0.0), (1000, 4.0), (3000, 0.7)])
+def test_grid_far_queries(cuda, n, offset):
+    """Dense blob vs. a cloud spread over a much larger box (an untrained model's
+    assembly vs. the ground truth): most queries of one direction lie far outside the
+    target cloud and take the two-level block search; results must still equal the
+    brute force bit for bit."""
+    rng = np.random.default_rng(n + int(offset * 10))
+    blob = (rng.random((3, n, 3)) - 0.5).astype(np.float32)
+    parts = (rng.random((3, 20, 1, 3)) - 0.5) * 2.0
+    spread = ((rng.random((3, 20, n // 20, 3)) - 0.5) + parts).reshape(3, -1, 3).astype(np.float32)
+    spread += np.float32(offset)
+    spread[0, :5] = 50.0  # a few extreme outliers stretch the bounding box
+    a = _fwd(blob, spread, 'grid', cuda)
+    b = _fwd(blob, spread, 'brute', cuda)
+    for u, v in zip(a, b):
+        np.testing.assert_array_equal(u, v)
+
+
 def test_empty_inputs(cuda):
     from multi_part_assembly_b200.utils.chamfer import chamfer_forward
     d1, i1, d2, i2 = chamfer_forward(torch.zeros(0, 10, 3, device=cuda),

@@ -1,0 +1,17 @@
+#!/bin/bash
+# One GPU box visit: parity tests, bench, launch list of one graph replay, optional extras.
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.max.sm --format=csv,noheader > gpurun_out/gpu.txt
+nproc >> gpurun_out/gpu.txt
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+tail -15 gpurun_out/pytest_gpu.log
+timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 2500 gpurun_out/bench.json; tail -3 gpurun_out/bench.err
+timeout 300 ncu --profile-from-start off --graph-profiling node --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_graph_step.csv python tools/profile_graph_step.py > gpurun_out/launches.log 2>&1
+python tools/summarize_launches.py gpurun_out/launches_graph_step.csv 1 > gpurun_out/launches_graph_step_summary.txt; head -24 gpurun_out/launches_graph_step_summary.txt
+for extra in "$@"; do
+  case $extra in
+    configs) timeout 900 python tools/bench_configs.py > gpurun_out/configs.log 2>&1; tail -12 gpurun_out/configs.log;;
+    ncu) timeout 400 ncu --profile-from-start off --graph-profiling node --set full --clock-control none --import-source on -k regex:'grid_nn_kernel|pointnet_phase_kernel|linear_bf16_kernel|grid_build_kernel|attention_kernel|pose_head' -o gpurun_out/top_full -f python tools/profile_graph_step.py > gpurun_out/ncu_full.log 2>&1; tail -2 gpurun_out/ncu_full.log;;
+    refbench) timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; cat gpurun_out/bench_reference.json;;
+  esac
+done
