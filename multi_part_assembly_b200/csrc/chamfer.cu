@@ -553,7 +553,9 @@ grid_nn_kernel(const float4* __restrict__ sorted0, const float4* __restrict__ so
       const float4* __restrict__ R = reps + (long long)(tc * S + seg) * cb_stride;
       float rbest = inf;
       int rcb = -1;
-      for (int cb = 0; cb < ncb; ++cb) {
+      // (only when the 3x3x3 block was empty: otherwise `best` already limits the reach to
+      // a few cells and the block loop below prunes everything else)
+      for (int cb = 0; cb < (bidx < 0 ? ncb : 0); ++cb) {
         const float4 t = __ldg(R + cb);
         if (__float_as_int(t.w) < 0) continue;
         const float d = sqdist_ref(q.x, q.y, q.z, t.x, t.y, t.z);
@@ -674,7 +676,12 @@ static int num_sms() {
 static int pick_dmax(int n) {
   // cells per axis the bbox of a uniform cloud needs at ~1 point per cell
   // (the device code aims at c.occ points per cell), capped by shared memory
-  int d = (int)ceil(cbrt((double)n));
+  static double fine = -1.0;
+  if (fine < 0.0) {  // tuning knob: cells-per-axis budget relative to cbrt(n)
+    const char* e = getenv("MPA_GRID_FINE");
+    fine = e ? atof(e) : 1.0;
+  }
+  int d = (int)ceil(cbrt((double)n) * fine);
   if (d < 1) d = 1;
   if (d > GRID_MAX_DIM) d = GRID_MAX_DIM;
   return d;

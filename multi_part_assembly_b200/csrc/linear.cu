@@ -65,58 +65,59 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
-// v[32] (one row, columns col0 .. col0+31, all inside N) <- act(v + bias) + residual
-__device__ __forceinline__ void epilogue_math_vec(float* v, const LinearEpilogue& ep, const float* res_row,
-                                                  int col0, bool row_ok) {
-  if (ep.bias != nullptr) {
-    const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
+// ---- epilogue building blocks -------------------------------------------------
+// A TMEM lane is an output row, so after tcgen05.ld a thread holds 32 consecutive
+// columns of ITS row, while a coalesced global access wants a warp instruction to
+// cover whole rows.  Each epilogue warp therefore owns a [32 rows][32 cols] fp32
+// staging tile in the (idle) operand ring, row pitch 36 floats:
+//   put_row : thread r writes its row as 8 x 16 B       (conflict-free: pitch 144 B)
+//   quad i  : lane l holds 4 consecutive columns 4*(l&7).. of row (l>>3)+4i, i.e. one
+//             instruction moves 4 rows x 128 contiguous bytes to / from global memory
+constexpr int EP_PITCH = 36;
+constexpr int EP_TILE_FLOATS = 32 * EP_PITCH;
+
+__device__ __forceinline__ void tile_put_row(float* tile, int lane, const float* v) {
+  float4* d = reinterpret_cast<float4*>(tile + lane * EP_PITCH);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) d[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+__device__ __forceinline__ void tile_get_row(const float* tile, int lane, float* v) {
+  const float4* d = reinterpret_cast<const float4*>(tile + lane * EP_PITCH);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 t = d[j];
+    v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+  }
+}
+__device__ __forceinline__ float4* tile_quad(float* tile, int lane, int i) {
+  return reinterpret_cast<float4*>(tile + ((lane >> 3) + 4 * i) * EP_PITCH + 4 * (lane & 7));
+}
+__device__ __forceinline__ void add_bias_act(float* v, const float* bias, int col0, int act) {
+  if (bias != nullptr) {
+    const float4* b4 = reinterpret_cast<const float4*>(bias + col0);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float4 b = __ldg(b4 + j);
+      const float4 b = __ldg(b4 + j);  // same address in every lane: one broadcast wavefront
       v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
     }
   }
-  if (ep.act != ACT_NONE) {
+  if (act != ACT_NONE) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
-  }
-  if (res_row != nullptr && row_ok) {
-    float4 r[8];
-    const float4* r4 = reinterpret_cast<const float4*>(res_row + col0);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = r4[j];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      v[4 * j + 0] += r[j].x; v[4 * j + 1] += r[j].y; v[4 * j + 2] += r[j].z; v[4 * j + 3] += r[j].w;
-    }
+    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], act);
   }
 }
-__device__ __forceinline__ void store_f32_vec(float* dst, const float* v) {
-  float4* d4 = reinterpret_cast<float4*>(dst);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-}
-__device__ __forceinline__ void store_bf16_vec(__nv_bfloat16* dst, const float* v) {
-  uint4* d4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    __nv_bfloat162 a = __floats2bfloat162_rn(v[8 * j + 0], v[8 * j + 1]);
-    __nv_bfloat162 b = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
-    __nv_bfloat162 c = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
-    __nv_bfloat162 d = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
-    uint4 u;
-    u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
-    u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
-    d4[j] = u;
-  }
+__device__ __forceinline__ uint2 pack_bf16x4(float4 q) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(q.x, q.y), b = __floats2bfloat162_rn(q.z, q.w);
+  uint2 u;
+  u.x = *reinterpret_cast<const uint32_t*>(&a);
+  u.y = *reinterpret_cast<const uint32_t*>(&b);
+  return u;
 }
 
-// One CTA = one 128 x BN output tile.  Epilogue thread = one output row (its TMEM
-// lane) and half of the tile's columns, 32 at a time straight from tcgen05.ld: the
-// row segment is contiguous in memory, so bias / residual / output move as 16-byte
-// packets without a shared-memory transpose.  FUSE_LN (BN == N): the finished row
-// (residual stream) is parked back in TMEM and LayerNorm-ed from there in two more
-// passes (mean, then centred variance), the two half-row warps meeting in shared memory.
+// One CTA = one 128 x BN output tile; 8 epilogue warps = 4 TMEM lane quadrants x 2
+// column halves.  FUSE_LN (BN == N): the finished row (residual stream) is parked back
+// in TMEM and LayerNorm-ed from there in two more passes (mean, then centred variance),
+// the two half-row warps meeting in shared memory.
 template <int BN, bool FUSE_LN>
 __global__ void __launch_bounds__(LN_THREADS, 1)
 linear_bf16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
@@ -127,6 +128,7 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   __shared__ uint32_t tmem_base_s;
   __shared__ float ln_part[2][2][LN_BM];
   constexpr int STAGE = ln_stage_bytes(BN);
+  static_assert(LN_EPI_WARPS * EP_TILE_FLOATS * 4 <= LN_STAGES * ln_stage_bytes(BN), "staging tiles live in the ring");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * LN_BM, n0 = blockIdx.y * BN;
@@ -173,15 +175,15 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       tc::mma_commit(&done_bar);
     }
   } else {  // ===== epilogue: warps 2..9, TMEM lane quadrant = warp % 4 =====
-    tc::mbar_wait(&done_bar, 0);
+    tc::mbar_wait(&done_bar, 0);  // every MMA has retired: accumulator final, operand ring idle
     tc::fence_after_sync();
     const int q = warp & 3, half = (warp - 2) >> 2;
     const int row_local = q * 32 + lane;
-    const int row = m0 + row_local;
-    const bool row_ok = row < M;
     const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
     const int c_begin = half * (BN / 2), c_end = c_begin + BN / 2;
-    const long long rowoff = (long long)row * N;
+    float* tile = reinterpret_cast<float*>(smem) + (warp - 2) * EP_TILE_FLOATS;
+    const int qrow0 = m0 + q * 32 + (lane >> 3);  // global row of this lane's quad i = 0
+    const int qcol = 4 * (lane & 7);
     if (!FUSE_LN) {
 #pragma unroll 1
       for (int j0 = c_begin; j0 < c_end; j0 += 32) {
@@ -191,12 +193,33 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         tc::tmem_ld32(taddr + (uint32_t)j0, v);
         tc::tmem_ld_wait();
         if (ep.vec && col0 + 32 <= N) {
-          epilogue_math_vec(v, ep, ep.residual ? ep.residual + rowoff : nullptr, col0, row_ok);
-          if (row_ok) {
-            if (ep.out_f32) store_f32_vec(ep.out_f32 + rowoff + col0, v);
-            if (ep.out_bf16) store_bf16_vec(ep.out_bf16 + rowoff + col0, v);
+          // the residual may alias the output (x += f(x)): fetch the whole slab before the
+          // first store, or every load would be ordered behind the previous store
+          float4 res[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = qrow0 + 4 * i;
+            res[i] = (ep.residual != nullptr && row < M)
+                         ? *reinterpret_cast<const float4*>(ep.residual + (long long)row * N + col0 + qcol)
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
           }
-        } else if (row_ok) {
+          add_bias_act(v, ep.bias, col0, ep.act);
+          tile_put_row(tile, lane, v);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = qrow0 + 4 * i;
+            if (row < M) {
+              float4 x = *tile_quad(tile, lane, i);
+              const long long o = (long long)row * N + col0 + qcol;
+              x.x += res[i].x; x.y += res[i].y; x.z += res[i].z; x.w += res[i].w;
+              if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + o) = x;
+              if (ep.out_bf16) *reinterpret_cast<uint2*>(ep.out_bf16 + o) = pack_bf16x4(x);
+            }
+          }
+          __syncwarp();
+        } else if (m0 + row_local < M) {
+          const long long rowoff = (long long)(m0 + row_local) * N;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int col = col0 + j;
@@ -210,17 +233,41 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         }
       }
     } else {
-      // pass 1: finished row -> fp32 output + back into TMEM; row sum
+      // pass 1: x = act(acc + bias) + residual -> fp32 output and back into TMEM; row sum
       float sum = 0.f;
 #pragma unroll 1
       for (int j0 = c_begin; j0 < c_end; j0 += 32) {
+        float4 res[8];  // whole residual slab first (it aliases the output, see above)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = qrow0 + 4 * i;
+          res[i] = (ep.residual != nullptr && row < M)
+                       ? *reinterpret_cast<const float4*>(ep.residual + (long long)row * N + j0 + qcol)
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         float v[32];
         tc::tmem_ld32(taddr + (uint32_t)j0, v);
         tc::tmem_ld_wait();
-        epilogue_math_vec(v, ep, ep.residual ? ep.residual + rowoff : nullptr, j0, row_ok);
+        add_bias_act(v, ep.bias, j0, ep.act);
+        tile_put_row(tile, lane, v);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = qrow0 + 4 * i;
+          float4* tq = tile_quad(tile, lane, i);
+          if (row < M) {
+            float4 x = *tq;
+            const long long o = (long long)row * N + j0 + qcol;
+            x.x += res[i].x; x.y += res[i].y; x.z += res[i].z; x.w += res[i].w;
+            if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + o) = x;
+            *tq = x;
+          }
+        }
+        __syncwarp();
+        tile_get_row(tile, lane, v);
+        __syncwarp();
 #pragma unroll
         for (int j = 0; j < 32; ++j) sum += v[j];
-        if (row_ok && ep.out_f32) store_f32_vec(ep.out_f32 + rowoff + j0, v);
         tc::tmem_st32(taddr + (uint32_t)j0, v);
       }
       tc::tmem_st_wait();
@@ -256,10 +303,19 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           v[4 * j + 2] = (v[4 * j + 2] - mean) * rstd * g.z + b.z;
           v[4 * j + 3] = (v[4 * j + 3] - mean) * rstd * g.w + b.w;
         }
-        if (row_ok) {
-          if (ep.ln_out_bf16) store_bf16_vec(ep.ln_out_bf16 + rowoff + j0, v);
-          if (ep.ln_out_f32) store_f32_vec(ep.ln_out_f32 + rowoff + j0, v);
+        tile_put_row(tile, lane, v);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = qrow0 + 4 * i;
+          if (row < M) {
+            const float4 y = *tile_quad(tile, lane, i);
+            const long long o = (long long)row * N + j0 + qcol;
+            if (ep.ln_out_bf16) *reinterpret_cast<uint2*>(ep.ln_out_bf16 + o) = pack_bf16x4(y);
+            if (ep.ln_out_f32) *reinterpret_cast<float4*>(ep.ln_out_f32 + o) = y;
+          }
         }
+        __syncwarp();
       }
     }
     tc::fence_before_sync();

@@ -117,7 +117,8 @@ class _PointNetFunction(torch.autograd.Function):
     def backward(ctx, grad):
         x, valids = ctx.saved_tensors
         convs, bns = ctx.modules
-        with torch.enable_grad():
+        # same operand precision as the forward kernels (bf16 GEMMs, fp32 BatchNorm)
+        with torch.enable_grad(), torch.autocast('cuda', dtype=torch.bfloat16):
             params = [c.weight for c in convs] + [b.weight for b in bns] + [b.bias for b in bns]
             if valids.numel():
                 idx = (valids != 0).nonzero(as_tuple=True)[0]
@@ -127,7 +128,7 @@ class _PointNetFunction(torch.autograd.Function):
             else:
                 out = _pointnet_torch(x, convs, bns, ctx.training, True, track=False)
                 g = grad
-            grads = torch.autograd.grad(out, params, g, allow_unused=True)
+            grads = torch.autograd.grad(out, params, g.to(out.dtype), allow_unused=True)
         return (None, None, None, None) + tuple(grads)
 
 
@@ -412,11 +413,11 @@ class _TransformerFunction(torch.autograd.Function):
         tokens, valid = ctx.saved_tensors
         encoder = ctx.encoder
         params = [p for p in encoder.parameters()]
-        with torch.enable_grad():
+        with torch.enable_grad(), torch.autocast('cuda', dtype=torch.bfloat16):
             t = tokens.detach().requires_grad_(True)
             pad = ~valid if valid.numel() else None
             out = encoder(t, src_key_padding_mask=pad)
-            grads = torch.autograd.grad(out, [t] + params, grad, allow_unused=True)
+            grads = torch.autograd.grad(out, [t] + params, grad.to(out.dtype), allow_unused=True)
         return (grads[0], None, None, None) + tuple(grads[1:])
 
 
