@@ -429,133 +429,83 @@ __device__ __forceinline__ void scan_range(const float4* __restrict__ T, int s, 
 // slack), so neither a closer point nor a tie with a lower index can hide in it.
 constexpr int NN_THREADS = 256;
 constexpr int NN_RANGES = 10;
-template <typename IdxT>
-__global__ void __launch_bounds__(NN_THREADS)
-grid_nn_kernel(const float4* __restrict__ sorted0, const float4* __restrict__ sorted1,
-               const int* __restrict__ cell_start, int cs_stride,
-               const GridParams* __restrict__ params, const float4* __restrict__ far,
-               const float4* __restrict__ reps, int cb_stride, int S,
-               int N0, int N1, float* __restrict__ dist0, IdxT* __restrict__ idx0,
-               float* __restrict__ dist1, IdxT* __restrict__ idx1) {
-  __shared__ int rs[NN_RANGES][NN_THREADS], re[NN_RANGES][NN_THREADS];
-  const int tid = threadIdx.x;
-  const long long wg = ((long long)blockIdx.x * blockDim.x + tid) >> 5;
-  const int lane = tid & 31;
+
+// everything a lane needs to search the target grid for one query
+struct NNQuery {
+  float4 q;                       // x, y, z, original index (bits)
+  GridParams g;                   // target grid
+  const float4* __restrict__ T;   // targets in cell order
+  const int* __restrict__ cs;     // cell starts
+  const float4* __restrict__ R;   // block representatives
+  const float4* __restrict__ F;   // far candidates (padded parts)
+  long long out;                  // output slot
+  int cx, cy, cz;
+  float slack;
+  bool dir1, valid;
+};
+
+__device__ __forceinline__ NNQuery nn_setup(long long gid, const float4* __restrict__ sorted0,
+                                            const float4* __restrict__ sorted1,
+                                            const int* __restrict__ cell_start, int cs_stride,
+                                            const GridParams* __restrict__ params,
+                                            const float4* __restrict__ far,
+                                            const float4* __restrict__ reps, int cb_stride, int S, int N0,
+                                            int N1) {
+  NNQuery c;
+  c.valid = false;
+  const long long wg = gid >> 5;
+  const int lane = (int)(gid & 31);
   const int per0 = (N0 + 31) >> 5, per1 = (N1 + 31) >> 5;
   const long long total0 = (long long)S * per0;
   const long long total = total0 + (long long)S * per1;
-  if (wg >= total) return;
-  const bool dir1 = wg >= total0;  // queries from cloud 1, targets cloud 0
-  const long long ww = dir1 ? wg - total0 : wg;
-  const int per = dir1 ? per1 : per0;
+  if (wg >= total) return c;
+  c.dir1 = wg >= total0;  // queries from cloud 1, targets cloud 0
+  const long long ww = c.dir1 ? wg - total0 : wg;
+  const int per = c.dir1 ? per1 : per0;
   const int seg = (int)(ww / per);
   const int i = (int)(ww % per) * 32 + lane;
-  const int qc = dir1 ? 1 : 0, tc = dir1 ? 0 : 1;
-  const int NQ = dir1 ? N1 : N0, NT = dir1 ? N0 : N1;
-  const int qcount = params[qc * S + seg].count;
-  if (i >= qcount) return;
-  const GridParams g = params[tc * S + seg];
-  const float4 q = (dir1 ? sorted1 : sorted0)[(long long)seg * NQ + i];
-  const float4* __restrict__ T = (dir1 ? sorted0 : sorted1) + (long long)seg * NT;
-  const int* __restrict__ cs = cell_start + (long long)(tc * S + seg) * cs_stride;
+  const int qc = c.dir1 ? 1 : 0, tc = c.dir1 ? 0 : 1;
+  const int NQ = c.dir1 ? N1 : N0, NT = c.dir1 ? N0 : N1;
+  if (i >= params[qc * S + seg].count) return c;
+  c.valid = true;
+  c.g = params[tc * S + seg];
+  c.q = (c.dir1 ? sorted1 : sorted0)[(long long)seg * NQ + i];
+  c.T = (c.dir1 ? sorted0 : sorted1) + (long long)seg * NT;
+  c.cs = cell_start + (long long)(tc * S + seg) * cs_stride;
+  c.R = reps + (long long)(tc * S + seg) * cb_stride;
+  c.F = far + (long long)(tc * S + seg) * MAX_FAR;
+  c.out = (long long)seg * NQ + __float_as_int(c.q.w);
+  const GridParams& g = c.g;
+  c.cx = cell_coord(c.q.x, g.ox, g.inv_h, g.dx);
+  c.cy = cell_coord(c.q.y, g.oy, g.inv_h, g.dy);
+  c.cz = cell_coord(c.q.z, g.oz, g.inv_h, g.dz);
+  // positional uncertainty of cell planes / cell assignment in fp32
+  c.slack = 1e-5f * (fabsf(c.q.x) + fabsf(c.q.y) + fabsf(c.q.z) + fabsf(g.ox) + fabsf(g.oy) +
+                     fabsf(g.oz) + (float)(g.dx + g.dy + g.dz) * g.h);
+  return c;
+}
+
+// phase E: two-level search over blocks of CB^3 cells (see the kernel comment)
+__device__ __forceinline__ void nn_block_search(const NNQuery& c, float& best, int& bidx) {
+  const GridParams& g = c.g;
+  const float4 q = c.q;
+  const float4* __restrict__ T = c.T;
+  const int* __restrict__ cs = c.cs;
+  const float4* __restrict__ R = c.R;
+  const int cx = c.cx, cy = c.cy, cz = c.cz;
+  const float slack = c.slack;
   const float inf = __int_as_float(0x7f800000);
-
-  float best = 1e32f;
-  int bidx = -1;
-  if (g.count > 0) {
-    const int cx = cell_coord(q.x, g.ox, g.inv_h, g.dx);
-    const int cy = cell_coord(q.y, g.oy, g.inv_h, g.dy);
-    const int cz = cell_coord(q.z, g.oz, g.inv_h, g.dz);
-    // positional uncertainty of cell planes / cell assignment in fp32
-    const float slack = 1e-5f * (fabsf(q.x) + fabsf(q.y) + fabsf(q.z) + fabsf(g.ox) +
-                                 fabsf(g.oy) + fabsf(g.oz) + (float)(g.dx + g.dy + g.dz) * g.h);
-    // squared distances from the query to the faces of its own cell (0 = lower side)
-    float X0 = fmaxf(q.x - (g.ox + (float)cx * g.h) - slack, 0.f);
-    float X1 = fmaxf((g.ox + (float)(cx + 1) * g.h) - q.x - slack, 0.f);
-    float Y0 = fmaxf(q.y - (g.oy + (float)cy * g.h) - slack, 0.f);
-    float Y1 = fmaxf((g.oy + (float)(cy + 1) * g.h) - q.y - slack, 0.f);
-    float Z0 = fmaxf(q.z - (g.oz + (float)cz * g.h) - slack, 0.f);
-    float Z1 = fmaxf((g.oz + (float)(cz + 1) * g.h) - q.z - slack, 0.f);
-    X0 *= X0; X1 *= X1; Y0 *= Y0; Y1 *= Y1; Z0 *= Z0; Z1 *= Z1;
-    const bool hasL = cx > 0, hasR = cx < g.dx - 1;
-
-    // ---- A: own cell ----
-    const int c0 = (cz * g.dy + cy) * g.dx + cx;
-    {
-      const int e = cs[c0 + 1];
-      for (int p = cs[c0]; p < e; ++p) consider(__ldg(T + p), q.x, q.y, q.z, best, bidx);
-    }
-    // ---- B: which other cells of the 3x3x3 block can still matter ----
-    int nr = 0;
-    if (hasL && X0 <= best) { rs[nr][tid] = cs[c0 - 1]; re[nr][tid] = cs[c0]; ++nr; }
-    if (hasR && X1 <= best) { rs[nr][tid] = cs[c0 + 1]; re[nr][tid] = cs[c0 + 2]; ++nr; }
-#pragma unroll
-    for (int dz = -1; dz <= 1; ++dz) {
-#pragma unroll
-      for (int dy = -1; dy <= 1; ++dy) {
-        if (dy == 0 && dz == 0) continue;
-        const int zc = cz + dz, yc = cy + dy;
-        if (zc < 0 || zc >= g.dz || yc < 0 || yc >= g.dy) continue;
-        const float l2 = (dy < 0 ? Y0 : (dy > 0 ? Y1 : 0.f)) + (dz < 0 ? Z0 : (dz > 0 ? Z1 : 0.f));
-        if (l2 > best) continue;
-        const int xa = cx - ((hasL && X0 + l2 <= best) ? 1 : 0);
-        const int xb = cx + ((hasR && X1 + l2 <= best) ? 1 : 0);
-        const int row = (zc * g.dy + yc) * g.dx;
-        rs[nr][tid] = cs[row + xa];
-        re[nr][tid] = cs[row + xb + 1];
-        ++nr;
-      }
-    }
-    // ---- C: flat scan of the noted ranges (two candidates in flight) ----
-    {
-      int k = 0, p = 0, e = 0;
-      if (nr > 0) { p = rs[0][tid]; e = re[0][tid]; }
-      while (k < nr) {
-        if (p >= e) {
-          if (++k < nr) { p = rs[k][tid]; e = re[k][tid]; }
-          continue;
-        }
-        const float4 t0 = __ldg(T + p);
-        if (p + 1 < e) {
-          const float4 t1 = __ldg(T + p + 1);
-          consider(t0, q.x, q.y, q.z, best, bidx);
-          consider(t1, q.x, q.y, q.z, best, bidx);
-          p += 2;
-        } else {
-          consider(t0, q.x, q.y, q.z, best, bidx);
-          ++p;
-        }
-      }
-    }
-    // ---- D: is the 3x3x3 block provably complete? ----
-    bool done = (cx - 1 <= 0) && (cx + 1 >= g.dx - 1) && (cy - 1 <= 0) && (cy + 1 >= g.dy - 1) &&
-                (cz - 1 <= 0) && (cz + 1 >= g.dz - 1);
-    if (!done) {
-      float bound = inf;
-      if (cx - 1 > 0) bound = fminf(bound, q.x - (g.ox + (float)(cx - 1) * g.h));
-      if (cx + 1 < g.dx - 1) bound = fminf(bound, (g.ox + (float)(cx + 2) * g.h) - q.x);
-      if (cy - 1 > 0) bound = fminf(bound, q.y - (g.oy + (float)(cy - 1) * g.h));
-      if (cy + 1 < g.dy - 1) bound = fminf(bound, (g.oy + (float)(cy + 2) * g.h) - q.y);
-      if (cz - 1 > 0) bound = fminf(bound, q.z - (g.oz + (float)(cz - 1) * g.h));
-      if (cz + 1 < g.dz - 1) bound = fminf(bound, (g.oz + (float)(cz + 2) * g.h) - q.z);
-      bound = (bound - slack) * 0.99999f;
-      // every unexplored target is farther than `bound`: strict so that a tie with
-      // a lower index cannot hide outside the block
-      done = bound > 0.0f && best < bound * bound;
-    }
+  {
     // ---- E: (sparse regions, queries outside the target cloud) two-level search ----
     // over blocks of CB^3 cells: one representative point per occupied block gives an
     // upper bound in a converged loop; the nearest block is opened first, then every
     // block whose box is not strictly farther than `best`.
-    if (!done) {
+    {
       const int bx = (g.dx + CB - 1) / CB, by = (g.dy + CB - 1) / CB, bz = (g.dz + CB - 1) / CB;
       const int ncb = bx * by * bz;
-      const float4* __restrict__ R = reps + (long long)(tc * S + seg) * cb_stride;
       float rbest = inf;
       int rcb = -1;
-      // (only when the 3x3x3 block was empty: otherwise `best` already limits the reach to
-      // a few cells and the block loop below prunes everything else)
-      for (int cb = 0; cb < (bidx < 0 ? ncb : 0); ++cb) {
+      for (int cb = 0; cb < ncb; ++cb) {
         const float4 t = __ldg(R + cb);
         if (__float_as_int(t.w) < 0) continue;
         const float d = sqdist_ref(q.x, q.y, q.z, t.x, t.y, t.z);
@@ -618,12 +568,145 @@ grid_nn_kernel(const float4* __restrict__ sorted0, const float4* __restrict__ so
       }
     }
   }
-  const float4* __restrict__ F = far + (long long)(tc * S + seg) * MAX_FAR;
-  for (int f = 0; f < g.nfar; ++f) consider(F[f], q.x, q.y, q.z, best, bidx);
-  const long long o = (long long)seg * NQ + __float_as_int(q.w);
-  (dir1 ? dist1 : dist0)[o] = best;
-  IdxT* io = dir1 ? idx1 : idx0;
-  if (io != nullptr) io[o] = (IdxT)bidx;
+}
+
+template <typename IdxT>
+__device__ __forceinline__ void nn_finish(const NNQuery& c, float best, int bidx, float* __restrict__ dist0,
+                                          IdxT* __restrict__ idx0, float* __restrict__ dist1,
+                                          IdxT* __restrict__ idx1) {
+  for (int f = 0; f < c.g.nfar; ++f) consider(c.F[f], c.q.x, c.q.y, c.q.z, best, bidx);
+  (c.dir1 ? dist1 : dist0)[c.out] = best;
+  IdxT* io = c.dir1 ? idx1 : idx0;
+  if (io != nullptr) io[c.out] = (IdxT)bidx;
+}
+
+// Round 1: every lane runs A-D for its own query.  Queries that need phase E are
+// queued in shared memory and re-dealt to the first lanes of the CTA in round 2, so
+// the (long, divergent) block search runs in full warps instead of a few lanes each.
+template <typename IdxT>
+__global__ void __launch_bounds__(NN_THREADS)
+grid_nn_kernel(const float4* __restrict__ sorted0, const float4* __restrict__ sorted1,
+               const int* __restrict__ cell_start, int cs_stride,
+               const GridParams* __restrict__ params, const float4* __restrict__ far,
+               const float4* __restrict__ reps, int cb_stride, int S,
+               int N0, int N1, float* __restrict__ dist0, IdxT* __restrict__ idx0,
+               float* __restrict__ dist1, IdxT* __restrict__ idx1) {
+  __shared__ int rs[NN_RANGES][NN_THREADS], re[NN_RANGES][NN_THREADS];
+  __shared__ int hq[3][NN_THREADS];  // round-2 queue: lane, best (bits), bidx
+  __shared__ int n_hard;
+  const int tid = threadIdx.x;
+  if (tid == 0) n_hard = 0;
+  __syncthreads();
+  const long long gid0 = (long long)blockIdx.x * NN_THREADS;
+  {
+    const NNQuery c = nn_setup(gid0 + tid, sorted0, sorted1, cell_start, cs_stride, params, far, reps,
+                               cb_stride, S, N0, N1);
+    if (c.valid) {
+      const GridParams& g = c.g;
+      const float4 q = c.q;
+      const float4* __restrict__ T = c.T;
+      const int* __restrict__ cs = c.cs;
+      const int cx = c.cx, cy = c.cy, cz = c.cz;
+      const float slack = c.slack;
+      const float inf = __int_as_float(0x7f800000);
+      float best = 1e32f;
+      int bidx = -1;
+      bool done = true;
+      if (g.count > 0) {
+        // squared distances from the query to the faces of its own cell (0 = lower side)
+        float X0 = fmaxf(q.x - (g.ox + (float)cx * g.h) - slack, 0.f);
+        float X1 = fmaxf((g.ox + (float)(cx + 1) * g.h) - q.x - slack, 0.f);
+        float Y0 = fmaxf(q.y - (g.oy + (float)cy * g.h) - slack, 0.f);
+        float Y1 = fmaxf((g.oy + (float)(cy + 1) * g.h) - q.y - slack, 0.f);
+        float Z0 = fmaxf(q.z - (g.oz + (float)cz * g.h) - slack, 0.f);
+        float Z1 = fmaxf((g.oz + (float)(cz + 1) * g.h) - q.z - slack, 0.f);
+        X0 *= X0; X1 *= X1; Y0 *= Y0; Y1 *= Y1; Z0 *= Z0; Z1 *= Z1;
+        const bool hasL = cx > 0, hasR = cx < g.dx - 1;
+
+        // ---- A: own cell ----
+        const int c0 = (cz * g.dy + cy) * g.dx + cx;
+        {
+          const int e = cs[c0 + 1];
+          for (int p = cs[c0]; p < e; ++p) consider(__ldg(T + p), q.x, q.y, q.z, best, bidx);
+        }
+        // ---- B: which other cells of the 3x3x3 block can still matter ----
+        int nr = 0;
+        if (hasL && X0 <= best) { rs[nr][tid] = cs[c0 - 1]; re[nr][tid] = cs[c0]; ++nr; }
+        if (hasR && X1 <= best) { rs[nr][tid] = cs[c0 + 1]; re[nr][tid] = cs[c0 + 2]; ++nr; }
+    #pragma unroll
+        for (int dz = -1; dz <= 1; ++dz) {
+    #pragma unroll
+          for (int dy = -1; dy <= 1; ++dy) {
+            if (dy == 0 && dz == 0) continue;
+            const int zc = cz + dz, yc = cy + dy;
+            if (zc < 0 || zc >= g.dz || yc < 0 || yc >= g.dy) continue;
+            const float l2 = (dy < 0 ? Y0 : (dy > 0 ? Y1 : 0.f)) + (dz < 0 ? Z0 : (dz > 0 ? Z1 : 0.f));
+            if (l2 > best) continue;
+            const int xa = cx - ((hasL && X0 + l2 <= best) ? 1 : 0);
+            const int xb = cx + ((hasR && X1 + l2 <= best) ? 1 : 0);
+            const int row = (zc * g.dy + yc) * g.dx;
+            rs[nr][tid] = cs[row + xa];
+            re[nr][tid] = cs[row + xb + 1];
+            ++nr;
+          }
+        }
+        // ---- C: flat scan of the noted ranges (two candidates in flight) ----
+        {
+          int k = 0, p = 0, e = 0;
+          if (nr > 0) { p = rs[0][tid]; e = re[0][tid]; }
+          while (k < nr) {
+            if (p >= e) {
+              if (++k < nr) { p = rs[k][tid]; e = re[k][tid]; }
+              continue;
+            }
+            const float4 t0 = __ldg(T + p);
+            if (p + 1 < e) {
+              const float4 t1 = __ldg(T + p + 1);
+              consider(t0, q.x, q.y, q.z, best, bidx);
+              consider(t1, q.x, q.y, q.z, best, bidx);
+              p += 2;
+            } else {
+              consider(t0, q.x, q.y, q.z, best, bidx);
+              ++p;
+            }
+          }
+        }
+        // ---- D: is the 3x3x3 block provably complete? ----
+        done = (cx - 1 <= 0) && (cx + 1 >= g.dx - 1) && (cy - 1 <= 0) && (cy + 1 >= g.dy - 1) &&
+                    (cz - 1 <= 0) && (cz + 1 >= g.dz - 1);
+        if (!done) {
+          float bound = inf;
+          if (cx - 1 > 0) bound = fminf(bound, q.x - (g.ox + (float)(cx - 1) * g.h));
+          if (cx + 1 < g.dx - 1) bound = fminf(bound, (g.ox + (float)(cx + 2) * g.h) - q.x);
+          if (cy - 1 > 0) bound = fminf(bound, q.y - (g.oy + (float)(cy - 1) * g.h));
+          if (cy + 1 < g.dy - 1) bound = fminf(bound, (g.oy + (float)(cy + 2) * g.h) - q.y);
+          if (cz - 1 > 0) bound = fminf(bound, q.z - (g.oz + (float)(cz - 1) * g.h));
+          if (cz + 1 < g.dz - 1) bound = fminf(bound, (g.oz + (float)(cz + 2) * g.h) - q.z);
+          bound = (bound - slack) * 0.99999f;
+          // every unexplored target is farther than `bound`: strict so that a tie with
+          // a lower index cannot hide outside the block
+          done = bound > 0.0f && best < bound * bound;
+        }
+      }
+      if (done) {
+        nn_finish<IdxT>(c, best, bidx, dist0, idx0, dist1, idx1);
+      } else {  // queue for round 2
+        const int slot = atomicAdd(&n_hard, 1);
+        hq[0][slot] = tid;
+        hq[1][slot] = __float_as_int(best);
+        hq[2][slot] = bidx;
+      }
+    }
+  }
+  __syncthreads();
+  if (tid < n_hard) {
+    const NNQuery c = nn_setup(gid0 + hq[0][tid], sorted0, sorted1, cell_start, cs_stride, params, far, reps,
+                               cb_stride, S, N0, N1);
+    float best = __int_as_float(hq[1][tid]);
+    int bidx = hq[2][tid];
+    nn_block_search(c, best, bidx);
+    nn_finish<IdxT>(c, best, bidx, dist0, idx0, dist1, idx1);
+  }
 }
 
 // ======================================================================

@@ -92,12 +92,13 @@ __device__ __forceinline__ void tile_get_row(const float* tile, int lane, float*
 __device__ __forceinline__ float4* tile_quad(float* tile, int lane, int i) {
   return reinterpret_cast<float4*>(tile + ((lane >> 3) + 4 * i) * EP_PITCH + 4 * (lane & 7));
 }
+// `bias` points at the CTA's shared-memory copy of the tile's bias slice (or is nullptr)
 __device__ __forceinline__ void add_bias_act(float* v, const float* bias, int col0, int act) {
   if (bias != nullptr) {
     const float4* b4 = reinterpret_cast<const float4*>(bias + col0);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float4 b = __ldg(b4 + j);  // same address in every lane: one broadcast wavefront
+      const float4 b = b4[j];  // same address in every lane: a broadcast
       v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
     }
   }
@@ -127,6 +128,7 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   __shared__ uint64_t full_bar[LN_STAGES], empty_bar[LN_STAGES], done_bar;
   __shared__ uint32_t tmem_base_s;
   __shared__ float ln_part[2][2][LN_BM];
+  __shared__ __align__(16) float s_vec[3][BN];  // bias, LayerNorm gamma, beta of this tile's columns
   constexpr int STAGE = ln_stage_bytes(BN);
   static_assert(LN_EPI_WARPS * EP_TILE_FLOATS * 4 <= LN_STAGES * ln_stage_bytes(BN), "staging tiles live in the ring");
 
@@ -175,8 +177,6 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       tc::mma_commit(&done_bar);
     }
   } else {  // ===== epilogue: warps 2..9, TMEM lane quadrant = warp % 4 =====
-    tc::mbar_wait(&done_bar, 0);  // every MMA has retired: accumulator final, operand ring idle
-    tc::fence_after_sync();
     const int q = warp & 3, half = (warp - 2) >> 2;
     const int row_local = q * 32 + lane;
     const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
@@ -184,6 +184,29 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     float* tile = reinterpret_cast<float*>(smem) + (warp - 2) * EP_TILE_FLOATS;
     const int qrow0 = m0 + q * 32 + (lane >> 3);  // global row of this lane's quad i = 0
     const int qcol = 4 * (lane & 7);
+    // while the K loop runs: per-column vectors into shared memory, first residual slab into registers
+    for (int c = threadIdx.x - 64; c < BN; c += LN_EPI_WARPS * 32) {
+      const bool in = n0 + c < N;
+      s_vec[0][c] = (ep.bias != nullptr && in) ? __ldg(ep.bias + n0 + c) : 0.f;
+      if (FUSE_LN) {
+        s_vec[1][c] = in ? __ldg(ep.ln_gamma + n0 + c) : 0.f;
+        s_vec[2][c] = in ? __ldg(ep.ln_beta + n0 + c) : 0.f;
+      }
+    }
+    const float* sbias = ep.bias != nullptr ? s_vec[0] : nullptr;
+    float4 res[8];
+    if (FUSE_LN) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = qrow0 + 4 * i;
+        res[i] = (ep.residual != nullptr && row < M)
+                     ? *reinterpret_cast<const float4*>(ep.residual + (long long)row * N + c_begin + qcol)
+                     : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    tc::group_sync(1, LN_EPI_WARPS * 32);  // s_vec complete
+    tc::mbar_wait(&done_bar, 0);  // every MMA has retired: accumulator final, operand ring idle
+    tc::fence_after_sync();
     if (!FUSE_LN) {
 #pragma unroll 1
       for (int j0 = c_begin; j0 < c_end; j0 += 32) {
@@ -195,7 +218,6 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         if (ep.vec && col0 + 32 <= N) {
           // the residual may alias the output (x += f(x)): fetch the whole slab before the
           // first store, or every load would be ordered behind the previous store
-          float4 res[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int row = qrow0 + 4 * i;
@@ -203,7 +225,7 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                          ? *reinterpret_cast<const float4*>(ep.residual + (long long)row * N + col0 + qcol)
                          : make_float4(0.f, 0.f, 0.f, 0.f);
           }
-          add_bias_act(v, ep.bias, col0, ep.act);
+          add_bias_act(v, sbias, j0, ep.act);
           tile_put_row(tile, lane, v);
           __syncwarp();
 #pragma unroll
@@ -237,28 +259,37 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       float sum = 0.f;
 #pragma unroll 1
       for (int j0 = c_begin; j0 < c_end; j0 += 32) {
-        float4 res[8];  // whole residual slab first (it aliases the output, see above)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = qrow0 + 4 * i;
-          res[i] = (ep.residual != nullptr && row < M)
-                       ? *reinterpret_cast<const float4*>(ep.residual + (long long)row * N + j0 + qcol)
-                       : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        // `res` holds this chunk's residual slab (it aliases the output, so it has to be
+        // in registers before the first store); the next chunk's is fetched below, ahead
+        // of this chunk's stores, and lands while this chunk is processed
         float v[32];
         tc::tmem_ld32(taddr + (uint32_t)j0, v);
         tc::tmem_ld_wait();
-        add_bias_act(v, ep.bias, j0, ep.act);
+        add_bias_act(v, sbias, j0, ep.act);
         tile_put_row(tile, lane, v);
         __syncwarp();
+        float4 xq[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 a = *tile_quad(tile, lane, i);
+          xq[i] = make_float4(a.x + res[i].x, a.y + res[i].y, a.z + res[i].z, a.w + res[i].w);
+        }
+        if (j0 + 32 < c_end) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = qrow0 + 4 * i;
+            res[i] = (ep.residual != nullptr && row < M)
+                         ? *reinterpret_cast<const float4*>(ep.residual + (long long)row * N + j0 + 32 + qcol)
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int row = qrow0 + 4 * i;
           float4* tq = tile_quad(tile, lane, i);
           if (row < M) {
-            float4 x = *tq;
+            const float4 x = xq[i];
             const long long o = (long long)row * N + j0 + qcol;
-            x.x += res[i].x; x.y += res[i].y; x.z += res[i].z; x.w += res[i].w;
             if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + o) = x;
             *tq = x;
           }
@@ -293,11 +324,11 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         float v[32];
         tc::tmem_ld32(taddr + (uint32_t)j0, v);
         tc::tmem_ld_wait();
-        const float4* g4 = reinterpret_cast<const float4*>(ep.ln_gamma + j0);
-        const float4* b4 = reinterpret_cast<const float4*>(ep.ln_beta + j0);
+        const float4* g4 = reinterpret_cast<const float4*>(s_vec[1] + j0);
+        const float4* b4 = reinterpret_cast<const float4*>(s_vec[2] + j0);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 g = __ldg(g4 + j), b = __ldg(b4 + j);
+          const float4 g = g4[j], b = b4[j];
           v[4 * j + 0] = (v[4 * j + 0] - mean) * rstd * g.x + b.x;
           v[4 * j + 1] = (v[4 * j + 1] - mean) * rstd * g.y + b.y;
           v[4 * j + 2] = (v[4 * j + 2] - mean) * rstd * g.z + b.z;

@@ -136,32 +136,40 @@ __global__ void pose_outputs_kernel(const float* __restrict__ f, int T, int K,
 // on the CUDA cores (0.1 MMAC per token: the cost is reading the weights, once per CTA
 // of PH_TOK tokens, with coalesced row reads).  A warp owns an output channel: lanes
 // split k, the per-token partial sums are folded with a transposing butterfly so that
-// lane 8t ends up with token t's total.
-constexpr int PH_TOK = 4;
-constexpr int PH_THREADS = 512;
+// lane 4t ends up with token t's total.
+constexpr int PH_TOK = 8;
+constexpr int PH_THREADS = 384;
+constexpr int PH_OUTS = 4;  // output channels per warp iteration: 32 weight loads in flight per lane
 
-// per-lane partial sums of PH_TOK tokens -> token (lane >> 3)'s total in every lane of its group of 8
-__device__ __forceinline__ float fold4(const float (&a)[4], int lane) {
-  float b[2];
+// per-lane partial sums of 8 tokens -> token (lane >> 2)'s total in every lane of its group of 4
+__device__ __forceinline__ float fold8(const float (&a)[8], int lane) {
+  float b[4], c[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool hi = lane & 16;
+    const float recv = __shfl_xor_sync(0xffffffffu, hi ? a[i] : a[i + 4], 16);
+    b[i] = (hi ? a[i + 4] : a[i]) + recv;
+  }
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
-    const bool hi = lane & 16;
-    const float recv = __shfl_xor_sync(0xffffffffu, hi ? a[i] : a[i + 2], 16);
-    b[i] = (hi ? a[i + 2] : a[i]) + recv;
+    const bool hi = lane & 8;
+    const float recv = __shfl_xor_sync(0xffffffffu, hi ? b[i] : b[i + 2], 8);
+    c[i] = (hi ? b[i + 2] : b[i]) + recv;
   }
-  const bool hi = lane & 8;
-  float d = (hi ? b[1] : b[0]) + __shfl_xor_sync(0xffffffffu, hi ? b[0] : b[1], 8);
-  d += __shfl_xor_sync(0xffffffffu, d, 4);
+  const bool hi = lane & 4;
+  float d = (hi ? c[1] : c[0]) + __shfl_xor_sync(0xffffffffu, hi ? c[0] : c[1], 4);
   d += __shfl_xor_sync(0xffffffffu, d, 2);
   d += __shfl_xor_sync(0xffffffffu, d, 1);
   return d;
 }
 
-// hout[t][j] = act(b[j] + sum_k W[j][k] xin[t][k]) for the CTA's PH_TOK tokens (all in shared
-// memory).  Two output channels per iteration keep 16 weight loads in flight per lane.
+// hout[t][j] = act(b[j] + sum_k W[j][k] xin[t][k]) for the CTA's PH_TOK tokens (all in shared memory)
 __device__ void ph_layer(const float* __restrict__ xin, int K, const float* __restrict__ W,
                          const float* __restrict__ b, int J, int act, float* __restrict__ hout) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  // every CTA streams the same weight matrix: start each one at a different row so that
+  // they do not all hit the same L2 slice at the same moment
+  const int rot = (int)((blockIdx.x * 37u) % (unsigned)J);
   for (int kc = 0; kc < K; kc += 256) {
     float xr[PH_TOK][8];
 #pragma unroll
@@ -171,32 +179,39 @@ __device__ void ph_layer(const float* __restrict__ xin, int K, const float* __re
         const int k = kc + lane + 32 * i;
         xr[t][i] = k < K ? xin[t * K + k] : 0.f;
       }
-    for (int j = warp; j < J; j += 2 * nwarps) {
-      const int j2 = j + nwarps;
-      float w0[8], w1[8];
+    for (int j0 = warp; j0 < J; j0 += PH_OUTS * nwarps) {
+      float w[PH_OUTS][8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int k = kc + lane + 32 * i;
-        w0[i] = k < K ? __ldg(W + (long long)j * K + k) : 0.f;
-        w1[i] = (k < K && j2 < J) ? __ldg(W + (long long)j2 * K + k) : 0.f;
-      }
-      float a0[PH_TOK], a1[PH_TOK];
-#pragma unroll
-      for (int t = 0; t < PH_TOK; ++t) {
-        a0[t] = 0.f; a1[t] = 0.f;
+      for (int o = 0; o < PH_OUTS; ++o) {
+        const int jl = j0 + o * nwarps;
+        const int j = jl + rot < J ? jl + rot : jl + rot - J;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          a0[t] = fmaf(w0[i], xr[t][i], a0[t]);
-          a1[t] = fmaf(w1[i], xr[t][i], a1[t]);
+          const int k = kc + lane + 32 * i;
+          w[o][i] = (k < K && jl < J) ? __ldg(W + (long long)j * K + k) : 0.f;
         }
       }
-      const float d0 = fold4(a0, lane), d1 = fold4(a1, lane);
-      if ((lane & 7) == 0) {
-        float* o = hout + (lane >> 3) * J + j;
-        *o = (kc == 0) ? d0 + __ldg(b + j) : *o + d0;
-        if (j2 < J) {
-          float* o2 = hout + (lane >> 3) * J + j2;
-          *o2 = (kc == 0) ? d1 + __ldg(b + j2) : *o2 + d1;
+      float d[PH_OUTS];
+#pragma unroll
+      for (int o = 0; o < PH_OUTS; ++o) {
+        float a[PH_TOK];
+#pragma unroll
+        for (int t = 0; t < PH_TOK; ++t) {
+          a[t] = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a[t] = fmaf(w[o][i], xr[t][i], a[t]);
+        }
+        d[o] = fold8(a, lane);
+      }
+      if ((lane & 3) == 0) {
+#pragma unroll
+        for (int o = 0; o < PH_OUTS; ++o) {
+          const int jl = j0 + o * nwarps;
+          const int j = jl + rot < J ? jl + rot : jl + rot - J;
+          if (jl < J) {
+            float* dst = hout + (lane >> 2) * J + j;
+            *dst = (kc == 0) ? d[o] + __ldg(b + j) : *dst + d[o];
+          }
         }
       }
     }

@@ -110,6 +110,16 @@ class FusedLossTerms(dict):
         self.packed = terms
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev):
+    s = _SIDE_STREAMS.get(dev)
+    if s is None:
+        s = _SIDE_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    return s
+
+
 def fused_geometric_losses(pts, pred_trans, gt_trans, pred_rot, gt_rot, valids, weights,
                             training=True, want_rot_l2=True, ret_pts=False):
     """All geometric loss terms of BaseModel._calc_loss in four launches (two
@@ -122,10 +132,20 @@ def fused_geometric_losses(pts, pred_trans, gt_trans, pred_rot, gt_rot, valids, 
     B, P, N, _ = pts.shape
     q1, q2 = pred_rot.rot.contiguous().float(), gt_rot.rot.contiguous().float()
     t1, t2 = pred_trans.contiguous().float(), gt_trans.contiguous().float()
-    with torch.no_grad():
-        pd1, pd2, _, _ = pose_chamfer(pts, None, None, q1, q2, valids, CD_PART)
-        sd1, sd2, pts1, pts2 = pose_chamfer(pts, t1, t2, q1, q2, valids, CD_SHAPE)
     dev = pts.device
+    with torch.no_grad():
+        # The two searches are independent and each ends in a long tail of slow warps:
+        # run the per-part one on a side stream so that it fills the SMs the shape-level
+        # one leaves idle (a fork/join that CUDA-graph capture records as parallel branches).
+        cur = torch.cuda.current_stream(dev)
+        side = _side_stream(dev)
+        side.wait_stream(cur)
+        sd1, sd2, pts1, pts2 = pose_chamfer(pts, t1, t2, q1, q2, valids, CD_SHAPE)
+        with torch.cuda.stream(side):
+            pd1, pd2, _, _ = pose_chamfer(pts, None, None, q1, q2, valids, CD_PART)
+        cur.wait_stream(side)
+        for t in (pd1, pd2):
+            t.record_stream(cur)
     terms = torch.empty(6, B, dtype=torch.float32, device=dev)
     w = torch.tensor([float(x) for x in weights], dtype=torch.float32).to(dev, non_blocking=True) \
         if not isinstance(weights, torch.Tensor) else weights

@@ -9,6 +9,7 @@ from multi_part_assembly_b200.models import build_model
 from multi_part_assembly_b200.compat.lightning import Trainer
 from multi_part_assembly_b200.runtime import GraphedStep
 dev = torch.device('cuda:0')
+torch.manual_seed(0)  # same weights (hence predicted poses) as bench.py rank 0
 model = build_model(get_cfg('pn_transformer')).to(dev).train()
 model.trainer = Trainer()
 for m in model.modules():
