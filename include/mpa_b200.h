@@ -165,6 +165,35 @@ int mpa_pointnet_forward(const float* pts, const float* valids, int n_parts, int
                          float* const* bn_running_var, int training, float eps, float momentum,
                          float* feats, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- PointNet backward: BatchNorm / ReLU / max-pool between the GEMMs ---------- */
+/* Training-step backward of PointNet.forward (models/modules/encoder/pointnet.py:29-41,
+ * i.e. what autograd derives from nn.Conv1d/BatchNorm1d/ReLU/torch.max there) on
+ * point-major activations: z, a, da, dz are [M = n_parts*N, C] bf16 with C contiguous
+ * (C in {64,128,256}), so the convolutions and their two backward products are plain
+ * GEMMs done by the caller.  valids [n_parts] or NULL: rows of padded parts are left
+ * out of every statistic and get zero outputs.
+ *   mpa_bn_stats     sums[0..C) = sum z, sums[C..2C) = sum z^2   (fp64, device)
+ *   mpa_bn_finalize  -> mean, rstd, scale = gamma*rstd, shift = beta - mean*scale, count
+ *   mpa_bn_act       a = relu?(z*scale + shift)
+ *   mpa_bn_backward  dz = gamma*rstd*(dy - S1/count - zhat*S2/count); sums receives
+ *                    S1 = sum dy (= d beta), S2 = sum dy*zhat (= d gamma).  dy is
+ *                    da * [z*scale+shift > 0] when `da` is given (ReLU layers), else the
+ *                    max-pool scatter g[part,c] * [arg[part,c] == point] (last layer).
+ *   mpa_pool_argmax  arg[part,c] = first point maximising BN(z)[.,c] over the part */
+int mpa_bn_stats(const void* z, long long M, int C, int N, const float* valids, double* sums,
+                 void* stream);
+int mpa_bn_finalize(const double* sums, int C, int n_parts, int N, const float* valids,
+                    const float* gamma, const float* beta, float eps, float* mean, float* rstd,
+                    float* scale, float* shift, float* count, void* stream);
+int mpa_bn_act(const void* z, const float* scale, const float* shift, int relu, long long M, int C,
+               int N, const float* valids, void* a, void* stream);
+int mpa_bn_backward(const void* da, const float* g, const int32_t* arg, const void* z,
+                    const float* mean, const float* rstd, const float* gamma, const float* beta,
+                    const float* count, long long M, int C, int N, const float* valids, double* sums,
+                    void* dz, void* stream);
+int mpa_pool_argmax(const void* z, const float* scale, int n_parts, int N, int C, int32_t* arg,
+                    void* stream);
+
 /* ---- token-level dense layers on tcgen05 + TMA ---------------------------- */
 /* Y = act(X W^T + bias) (+ residual): X [M,K], W [N,K] (an nn.Linear weight),
  * bias [N] or NULL, residual [M,N] or NULL, out [M,N]; fp32 in memory, bf16

@@ -46,6 +46,12 @@ _SIGNATURES = {
     'mpa_pose_outputs': (c_int, [c_void_p, c_int, c_int] + [c_void_p] * 4 + [c_int] + [c_void_p] * 3),
     'mpa_pose_head_forward': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                       c_int] + [c_void_p] * 4 + [c_int] + [c_void_p] * 3),
+    'mpa_bn_stats': (c_int, [c_void_p, ctypes.c_longlong, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'mpa_bn_finalize': (c_int, [c_void_p, c_int, c_int, c_int] + [c_void_p] * 3 + [ctypes.c_float] +
+                        [c_void_p] * 6),
+    'mpa_bn_act': (c_int, [c_void_p] * 3 + [c_int, ctypes.c_longlong, c_int, c_int] + [c_void_p] * 3),
+    'mpa_bn_backward': (c_int, [c_void_p] * 9 + [ctypes.c_longlong, c_int, c_int] + [c_void_p] * 4),
+    'mpa_pool_argmax': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     'mpa_linear_workspace_bytes': (c_size_t, [c_int] * 3),
     'mpa_linear_forward': (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p, c_void_p, c_size_t, c_void_p]),
     'mpa_transformer_workspace_bytes': (c_size_t, [c_int] * 5),

@@ -401,11 +401,22 @@ __device__ __forceinline__ void consider(const float4 t, float qx, float qy, flo
 __device__ __forceinline__ void scan_range(const float4* __restrict__ T, int s, int e, float qx,
                                            float qy, float qz, float& best, int& bidx) {
   int p = s;
-  for (; p + 1 < e; p += 2) {  // two independent loads in flight
+  for (; p + 3 < e; p += 4) {  // four independent loads in flight
+    const float4 t0 = __ldg(&T[p]);
+    const float4 t1 = __ldg(&T[p + 1]);
+    const float4 t2 = __ldg(&T[p + 2]);
+    const float4 t3 = __ldg(&T[p + 3]);
+    consider(t0, qx, qy, qz, best, bidx);
+    consider(t1, qx, qy, qz, best, bidx);
+    consider(t2, qx, qy, qz, best, bidx);
+    consider(t3, qx, qy, qz, best, bidx);
+  }
+  if (p + 1 < e) {
     const float4 t0 = __ldg(&T[p]);
     const float4 t1 = __ldg(&T[p + 1]);
     consider(t0, qx, qy, qz, best, bidx);
     consider(t1, qx, qy, qz, best, bidx);
+    p += 2;
   }
   if (p < e) consider(__ldg(&T[p]), qx, qy, qz, best, bidx);
 }
@@ -592,6 +603,7 @@ grid_nn_kernel(const float4* __restrict__ sorted0, const float4* __restrict__ so
                int N0, int N1, float* __restrict__ dist0, IdxT* __restrict__ idx0,
                float* __restrict__ dist1, IdxT* __restrict__ idx1) {
   __shared__ int rs[NN_RANGES][NN_THREADS], re[NN_RANGES][NN_THREADS];
+  __shared__ float rl[NN_RANGES][NN_THREADS];  // squared distance to each noted range's slab
   __shared__ int hq[3][NN_THREADS];  // round-2 queue: lane, best (bits), bidx
   __shared__ int n_hard;
   const int tid = threadIdx.x;
@@ -625,42 +637,51 @@ grid_nn_kernel(const float4* __restrict__ sorted0, const float4* __restrict__ so
 
         // ---- A: own cell ----
         const int c0 = (cz * g.dy + cy) * g.dx + cx;
-        {
-          const int e = cs[c0 + 1];
-          for (int p = cs[c0]; p < e; ++p) consider(__ldg(T + p), q.x, q.y, q.z, best, bidx);
-        }
-        // ---- B: which other cells of the 3x3x3 block can still matter ----
+        scan_range(T, cs[c0], cs[c0 + 1], q.x, q.y, q.z, best, bidx);
+        // ---- B: which other cells of the 3x3x3 block can still matter (nearest rows first) ----
         int nr = 0;
-        if (hasL && X0 <= best) { rs[nr][tid] = cs[c0 - 1]; re[nr][tid] = cs[c0]; ++nr; }
-        if (hasR && X1 <= best) { rs[nr][tid] = cs[c0 + 1]; re[nr][tid] = cs[c0 + 2]; ++nr; }
+        if (hasL && X0 <= best) { rs[nr][tid] = cs[c0 - 1]; re[nr][tid] = cs[c0]; rl[nr][tid] = X0; ++nr; }
+        if (hasR && X1 <= best) { rs[nr][tid] = cs[c0 + 1]; re[nr][tid] = cs[c0 + 2]; rl[nr][tid] = X1; ++nr; }
     #pragma unroll
-        for (int dz = -1; dz <= 1; ++dz) {
-    #pragma unroll
-          for (int dy = -1; dy <= 1; ++dy) {
-            if (dy == 0 && dz == 0) continue;
-            const int zc = cz + dz, yc = cy + dy;
-            if (zc < 0 || zc >= g.dz || yc < 0 || yc >= g.dy) continue;
-            const float l2 = (dy < 0 ? Y0 : (dy > 0 ? Y1 : 0.f)) + (dz < 0 ? Z0 : (dz > 0 ? Z1 : 0.f));
-            if (l2 > best) continue;
-            const int xa = cx - ((hasL && X0 + l2 <= best) ? 1 : 0);
-            const int xb = cx + ((hasR && X1 + l2 <= best) ? 1 : 0);
-            const int row = (zc * g.dy + yc) * g.dx;
-            rs[nr][tid] = cs[row + xa];
-            re[nr][tid] = cs[row + xb + 1];
-            ++nr;
-          }
+        for (int o = 0; o < 8; ++o) {
+          // face rows (one of dy, dz zero) before the four edge rows
+          const int dy = o < 2 ? (o == 0 ? -1 : 1) : (o < 4 ? 0 : ((o & 1) ? 1 : -1));
+          const int dz = o < 2 ? 0 : (o < 4 ? (o == 2 ? -1 : 1) : (o < 6 ? -1 : 1));
+          const int zc = cz + dz, yc = cy + dy;
+          if (zc < 0 || zc >= g.dz || yc < 0 || yc >= g.dy) continue;
+          const float l2 = (dy < 0 ? Y0 : (dy > 0 ? Y1 : 0.f)) + (dz < 0 ? Z0 : (dz > 0 ? Z1 : 0.f));
+          if (l2 > best) continue;
+          const int xa = cx - ((hasL && X0 + l2 <= best) ? 1 : 0);
+          const int xb = cx + ((hasR && X1 + l2 <= best) ? 1 : 0);
+          const int row = (zc * g.dy + yc) * g.dx;
+          rs[nr][tid] = cs[row + xa];
+          re[nr][tid] = cs[row + xb + 1];
+          rl[nr][tid] = l2;
+          ++nr;
         }
-        // ---- C: flat scan of the noted ranges (two candidates in flight) ----
+        // ---- C: flat scan of the noted ranges (two candidates in flight); a range whose
+        // slab has meanwhile become strictly farther than `best` is dropped unscanned ----
         {
-          int k = 0, p = 0, e = 0;
-          if (nr > 0) { p = rs[0][tid]; e = re[0][tid]; }
-          while (k < nr) {
+          int k = -1, p = 0, e = 0;
+          while (true) {
             if (p >= e) {
-              if (++k < nr) { p = rs[k][tid]; e = re[k][tid]; }
+              if (++k >= nr) break;
+              if (rl[k][tid] > best) continue;
+              p = rs[k][tid];
+              e = re[k][tid];
               continue;
             }
             const float4 t0 = __ldg(T + p);
-            if (p + 1 < e) {
+            if (p + 3 < e) {
+              const float4 t1 = __ldg(T + p + 1);
+              const float4 t2 = __ldg(T + p + 2);
+              const float4 t3 = __ldg(T + p + 3);
+              consider(t0, q.x, q.y, q.z, best, bidx);
+              consider(t1, q.x, q.y, q.z, best, bidx);
+              consider(t2, q.x, q.y, q.z, best, bidx);
+              consider(t3, q.x, q.y, q.z, best, bidx);
+              p += 4;
+            } else if (p + 1 < e) {
               const float4 t1 = __ldg(T + p + 1);
               consider(t0, q.x, q.y, q.z, best, bidx);
               consider(t1, q.x, q.y, q.z, best, bidx);

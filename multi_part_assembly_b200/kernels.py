@@ -46,6 +46,9 @@ def encode_parts(encoder, part_pcs, part_valids, feat_dim):
 # PointNet
 # ---------------------------------------------------------------------------
 _PRECISION = {'mode': 'auto'}
+# backward of the native encoders: hand-written streaming kernels + library GEMMs
+# (True) or the stock formulation re-run under autograd (False; kept for comparison)
+_NATIVE_BACKWARD = {'pointnet': True}
 
 
 def set_precision(mode):
@@ -78,6 +81,85 @@ def _pointnet_torch(x, convs, bns, training, global_feat, track=True):
         if i < 4:
             h = F.relu(h)
     return h.max(dim=-1)[0] if global_feat else h.transpose(2, 1).contiguous()
+
+
+def _mm_f32(a, b):
+    """bf16 x bf16 -> fp32 GEMM (fp32 accumulate and output where the library offers it)."""
+    try:
+        return torch.mm(a, b, out_dtype=torch.float32)
+    except (TypeError, RuntimeError, NotImplementedError):
+        return torch.mm(a, b).float()
+
+
+def _pointnet_backward_native(x, valids, grad, convs, bns):
+    """Gradients of PointNet.forward (global_feat=True, train-mode BatchNorm) w.r.t.
+    conv / BatchNorm parameters (reference: autograd through
+    models/modules/encoder/pointnet.py:29-41).
+
+    Point-major bf16 activations [M = n*N, C]: the 1x1 convolutions and their backward
+    products are row-major library GEMMs; BatchNorm statistics / ReLU / max-pool and
+    their backward are the streaming kernels of csrc/pointnet_bwd.cu (two passes per
+    layer and direction).  No host synchronisation: padded parts are masked on the
+    device.  Returns (conv weight grads, bn weight grads, bn bias grads)."""
+    n, N, _ = x.shape
+    M = n * N
+    dev = x.device
+    L = _lib.lib()
+    st = _lib.cuda_stream(dev)
+    ptr = _lib.ptr
+    bf = torch.bfloat16
+    f32 = dict(dtype=torch.float32, device=dev)
+    v = None if (valids is None or valids.numel() == 0) else valids.float().contiguous()
+    eps = float(bns[0].eps)
+    with torch.cuda.device(dev):
+        a0 = torch.zeros(M, 8, dtype=bf, device=dev)  # xyz padded to one 16-byte packet per point
+        a0[:, :3] = x.reshape(M, 3)
+        Ws = []
+        for i, c in enumerate(convs):
+            w = c.weight.detach().reshape(c.weight.shape[0], -1)
+            Ws.append((F.pad(w, (0, 5)) if i == 0 else w).to(bf))
+        acts, zs, consts = [a0], [], []
+        sums = torch.empty(2 * 256, dtype=torch.float64, device=dev)
+        count = torch.empty(1, **f32)
+        for i in range(5):
+            z = acts[i] @ Ws[i].t()
+            C = z.shape[1]
+            _lib.check(L.mpa_bn_stats(ptr(z), M, C, N, ptr(v), ptr(sums), st), 'mpa_bn_stats')
+            cst = torch.empty(4, C, **f32)  # mean, rstd, scale, shift
+            _lib.check(L.mpa_bn_finalize(ptr(sums), C, n, N, ptr(v), ptr(bns[i].weight.detach()),
+                                         ptr(bns[i].bias.detach()), eps, ptr(cst[0]), ptr(cst[1]),
+                                         ptr(cst[2]), ptr(cst[3]), ptr(count), st), 'mpa_bn_finalize')
+            zs.append(z)
+            consts.append(cst)
+            if i < 4:
+                a = torch.empty_like(z)
+                _lib.check(L.mpa_bn_act(ptr(z), ptr(cst[2]), ptr(cst[3]), 1, M, C, N, ptr(v), ptr(a), st),
+                           'mpa_bn_act')
+                acts.append(a)
+        Fdim = zs[4].shape[1]
+        arg = torch.empty(n, Fdim, dtype=torch.int32, device=dev)
+        _lib.check(L.mpa_pool_argmax(ptr(zs[4]), ptr(consts[4][2]), n, N, Fdim, ptr(arg), st),
+                   'mpa_pool_argmax')
+        g = grad.float().contiguous()
+        gW, gG, gB = [None] * 5, [None] * 5, [None] * 5
+        da = None
+        for i in (4, 3, 2, 1, 0):
+            z, cst = zs[i], consts[i]
+            C = z.shape[1]
+            dz = torch.empty_like(z)
+            s2 = torch.empty(2 * C, dtype=torch.float64, device=dev)
+            _lib.check(L.mpa_bn_backward(
+                ptr(da) if i < 4 else None, ptr(g) if i == 4 else None, ptr(arg) if i == 4 else None,
+                ptr(z), ptr(cst[0]), ptr(cst[1]), ptr(bns[i].weight.detach()), ptr(bns[i].bias.detach()),
+                ptr(count), M, C, N, ptr(v), ptr(s2), ptr(dz), st), 'mpa_bn_backward')
+            gB[i] = s2[:C].float()
+            gG[i] = s2[C:].float()
+            gw = _mm_f32(dz.t(), acts[i])
+            gW[i] = (gw[:, :3] if i == 0 else gw).reshape(convs[i].weight.shape).contiguous()
+            if i > 0:
+                da = dz @ Ws[i]
+            del zs[i], dz
+    return gW, gG, gB
 
 
 class _PointNetFunction(torch.autograd.Function):
@@ -117,6 +199,9 @@ class _PointNetFunction(torch.autograd.Function):
     def backward(ctx, grad):
         x, valids = ctx.saved_tensors
         convs, bns = ctx.modules
+        if ctx.training and _NATIVE_BACKWARD['pointnet']:
+            gW, gG, gB = _pointnet_backward_native(x, valids, grad, convs, bns)
+            return (None, None, None, None) + tuple(gW) + tuple(gG) + tuple(gB)
         # same operand precision as the forward kernels (bf16 GEMMs, fp32 BatchNorm)
         with torch.enable_grad(), torch.autocast('cuda', dtype=torch.bfloat16):
             params = [c.weight for c in convs] + [b.weight for b in bns] + [b.bias for b in bns]

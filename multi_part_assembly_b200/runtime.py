@@ -88,3 +88,62 @@ class GraphedStep:
         self._staged[slot] = consumed
         self.graph.replay()
         return self.static_out
+
+
+class GraphedTrainStep:
+    """Whole training step -- forward, loss, backward, optimizer -- as one CUDA graph.
+
+    Eager PyTorch needs ~15-20 ms of host time to issue the ~1500 launches of one
+    pn_transformer training step, several times what the GPU needs to run them.  The
+    step is captured once for a fixed batch shape (the optimizer must keep its state on
+    the device: Adam/AdamW are switched to `capturable`) and replayed per batch; inputs
+    go through static buffers like `GraphedStep`.  Reference loop being replaced: the
+    PL training loop around `BaseModel.training_step` (models/modules/base_model.py:60-63)
+    with automatic optimisation and `--fp16` autocast (scripts/train.py:88).
+    """
+
+    def __init__(self, model, optimizer, example_batch, autocast_dtype=torch.bfloat16, warmup=3):
+        self.model = model
+        self.optimizer = optimizer
+        self.autocast_dtype = autocast_dtype
+        dev = next(model.parameters()).device
+        self.device = dev
+        for group in optimizer.param_groups:
+            if 'capturable' in group:
+                group['capturable'] = True
+        self.static_in = {k: v.to(dev).clone() for k, v in example_batch.items()}
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._eager_step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self.graph):
+            self.static_loss = self._fwd_bwd()
+            optimizer.step()
+        torch.cuda.synchronize(dev)
+
+    def _fwd_bwd(self):
+        with torch.autocast('cuda', dtype=self.autocast_dtype or torch.bfloat16,
+                            enabled=self.autocast_dtype is not None):
+            loss = self.model.training_step(dict(self.static_in), 0)
+        loss.backward()
+        return loss.detach()
+
+    def _eager_step(self):
+        self.optimizer.zero_grad(set_to_none=True)
+        loss = self._fwd_bwd()
+        self.optimizer.step()
+        return loss
+
+    def __call__(self, batch=None):
+        """One optimisation step on `batch` (host or device tensors; None = the static
+        buffers as they are).  Returns the (static) loss tensor."""
+        if batch is not None:
+            for k, dst in self.static_in.items():
+                dst.copy_(batch[k], non_blocking=True)
+        self.graph.replay()  # gradients live in the graph's private pool and are rewritten in place
+        return self.static_loss
