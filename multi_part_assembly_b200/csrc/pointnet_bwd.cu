@@ -39,6 +39,21 @@ __device__ __forceinline__ Bf8 load_bf8(const __nv_bfloat16* p) {
   }
   return r;
 }
+constexpr int PB_UNROLL = 4;  // rows (16-byte packets) a thread keeps in flight
+__device__ __forceinline__ uint4 ld_packet(const __nv_bfloat16* p) {
+  return *reinterpret_cast<const uint4*>(p);
+}
+__device__ __forceinline__ Bf8 unpack_bf8(const uint4& u) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+  Bf8 r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    r.v[2 * i] = f.x;
+    r.v[2 * i + 1] = f.y;
+  }
+  return r;
+}
 __device__ __forceinline__ void store_bf8(__nv_bfloat16* p, const Bf8& r) {
   uint4 u;
   __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
@@ -89,12 +104,22 @@ bn_stats_kernel(const __nv_bfloat16* __restrict__ z, long long M, int C, int N,
                 const float* __restrict__ valids, double* __restrict__ sums) {
   const int tpr = C >> 3, col = threadIdx.x % tpr, rows_per_iter = PB_THREADS / tpr;
   float acc[2][8] = {};
-  for (long long m = (long long)blockIdx.x * rows_per_iter + threadIdx.x / tpr; m < M;
-       m += (long long)gridDim.x * rows_per_iter) {
-    if (valids != nullptr && valids[m / N] == 0.f) continue;
-    const Bf8 v = load_bf8(z + m * C + col * 8);
+  const long long stride = (long long)gridDim.x * rows_per_iter;
+  for (long long m0 = (long long)blockIdx.x * rows_per_iter + threadIdx.x / tpr; m0 < M; m0 += PB_UNROLL * stride) {
+    uint4 raw[PB_UNROLL];
+    bool ok[PB_UNROLL];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { acc[0][i] += v.v[i]; acc[1][i] = fmaf(v.v[i], v.v[i], acc[1][i]); }
+    for (int u = 0; u < PB_UNROLL; ++u) {  // all loads first: PB_UNROLL packets in flight per thread
+      const long long m = m0 + u * stride;
+      ok[u] = m < M && (valids == nullptr || valids[m / N] != 0.f);
+      raw[u] = ok[u] ? ld_packet(z + m * C + col * 8) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < PB_UNROLL; ++u) {
+      const Bf8 v = unpack_bf8(raw[u]);  // zeros for skipped rows
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { acc[0][i] += v.v[i]; acc[1][i] = fmaf(v.v[i], v.v[i], acc[1][i]); }
+    }
   }
   cta_column_reduce<2>(acc, C, sums);
 }
@@ -135,30 +160,42 @@ bn_act_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ sca
   float sc[8], sh[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { sc[i] = scale[col * 8 + i]; sh[i] = shift[col * 8 + i]; }
-  for (long long m = (long long)blockIdx.x * rows_per_iter + threadIdx.x / tpr; m < M;
-       m += (long long)gridDim.x * rows_per_iter) {
-    Bf8 v = load_bf8(z + m * C + col * 8);
-    const bool ok = valids == nullptr || valids[m / N] != 0.f;
+  const long long stride = (long long)gridDim.x * rows_per_iter;
+  for (long long m0 = (long long)blockIdx.x * rows_per_iter + threadIdx.x / tpr; m0 < M; m0 += PB_UNROLL * stride) {
+    uint4 raw[PB_UNROLL];
+    bool ok[PB_UNROLL];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float y = fmaf(v.v[i], sc[i], sh[i]);
-      if (relu) y = fmaxf(y, 0.f);
-      v.v[i] = ok ? y : 0.f;
+    for (int u = 0; u < PB_UNROLL; ++u) {
+      const long long m = m0 + u * stride;
+      ok[u] = m < M && (valids == nullptr || valids[m / N] != 0.f);
+      raw[u] = ok[u] ? ld_packet(z + m * C + col * 8) : make_uint4(0u, 0u, 0u, 0u);
     }
-    store_bf8(a + m * C + col * 8, v);
+#pragma unroll
+    for (int u = 0; u < PB_UNROLL; ++u) {
+      const long long m = m0 + u * stride;
+      if (m >= M) break;
+      Bf8 v = unpack_bf8(raw[u]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float y = fmaf(v.v[i], sc[i], sh[i]);
+        if (relu) y = fmaxf(y, 0.f);
+        v.v[i] = ok[u] ? y : 0.f;
+      }
+      store_bf8(a + m * C + col * 8, v);
+    }
   }
 }
 
 // incoming gradient of the BatchNorm output at (row m, channels col*8..):
 //   da != nullptr : dy = da * [z*scale+shift > 0]   (ReLU layers)
 //   else          : dy = g[part, c] where arg[part, c] == m - part*N   (max-pool, layer 5)
-__device__ __forceinline__ Bf8 incoming_grad(const __nv_bfloat16* __restrict__ da,
+__device__ __forceinline__ Bf8 incoming_grad(bool has_da, const uint4& da_raw,
                                              const float* __restrict__ g, const int* __restrict__ arg,
                                              const Bf8& zv, const float (&sc)[8], const float (&sh)[8],
                                              long long m, int C, int N, int col) {
   Bf8 dy;
-  if (da != nullptr) {
-    dy = load_bf8(da + m * C + col * 8);
+  if (has_da) {
+    dy = unpack_bf8(da_raw);
 #pragma unroll
     for (int i = 0; i < 8; ++i)
       if (!(fmaf(zv.v[i], sc[i], sh[i]) > 0.f)) dy.v[i] = 0.f;
@@ -192,15 +229,28 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ da, const float* __restri
     sc[i] = bn.gamma[c] * rs[i]; sh[i] = bn.beta[c] - mu[i] * sc[i];
   }
   float acc[2][8] = {};
-  for (long long m = (long long)blockIdx.x * rows_per_iter + threadIdx.x / tpr; m < M;
-       m += (long long)gridDim.x * rows_per_iter) {
-    if (valids != nullptr && valids[m / N] == 0.f) continue;
-    const Bf8 zv = load_bf8(z + m * C + col * 8);
-    const Bf8 dy = incoming_grad(da, g, arg, zv, sc, sh, m, C, N, col);
+  const long long stride = (long long)gridDim.x * rows_per_iter;
+  for (long long m0 = (long long)blockIdx.x * rows_per_iter + threadIdx.x / tpr; m0 < M; m0 += PB_UNROLL * stride) {
+    uint4 zr[PB_UNROLL], dr[PB_UNROLL];
+    bool ok[PB_UNROLL];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      acc[0][i] += dy.v[i];
-      acc[1][i] = fmaf(dy.v[i], (zv.v[i] - mu[i]) * rs[i], acc[1][i]);
+    for (int u = 0; u < PB_UNROLL; ++u) {
+      const long long m = m0 + u * stride;
+      ok[u] = m < M && (valids == nullptr || valids[m / N] != 0.f);
+      zr[u] = ok[u] ? ld_packet(z + m * C + col * 8) : make_uint4(0u, 0u, 0u, 0u);
+      dr[u] = (ok[u] && da != nullptr) ? ld_packet(da + m * C + col * 8) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < PB_UNROLL; ++u) {
+      if (!ok[u]) continue;
+      const long long m = m0 + u * stride;
+      const Bf8 zv = unpack_bf8(zr[u]);
+      const Bf8 dy = incoming_grad(da != nullptr, dr[u], g, arg, zv, sc, sh, m, C, N, col);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[0][i] += dy.v[i];
+        acc[1][i] = fmaf(dy.v[i], (zv.v[i] - mu[i]) * rs[i], acc[1][i]);
+      }
     }
   }
   cta_column_reduce<2>(acc, C, sums);
@@ -223,22 +273,36 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ da, const float* __restric
     k1[i] = (float)sums[c] * inv_n;
     k2[i] = (float)sums[C + c] * inv_n;
   }
-  for (long long m = (long long)blockIdx.x * rows_per_iter + threadIdx.x / tpr; m < M;
-       m += (long long)gridDim.x * rows_per_iter) {
-    Bf8 out;
-    if (valids != nullptr && valids[m / N] == 0.f) {
+  const long long stride = (long long)gridDim.x * rows_per_iter;
+  for (long long m0 = (long long)blockIdx.x * rows_per_iter + threadIdx.x / tpr; m0 < M; m0 += PB_UNROLL * stride) {
+    uint4 zr[PB_UNROLL], dr[PB_UNROLL];
+    bool ok[PB_UNROLL];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) out.v[i] = 0.f;
-    } else {
-      const Bf8 zv = load_bf8(z + m * C + col * 8);
-      const Bf8 dy = incoming_grad(da, g, arg, zv, sc, sh, m, C, N, col);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float zhat = (zv.v[i] - mu[i]) * rs[i];
-        out.v[i] = sc[i] * (dy.v[i] - k1[i] - zhat * k2[i]);
-      }
+    for (int u = 0; u < PB_UNROLL; ++u) {
+      const long long m = m0 + u * stride;
+      ok[u] = m < M && (valids == nullptr || valids[m / N] != 0.f);
+      zr[u] = ok[u] ? ld_packet(z + m * C + col * 8) : make_uint4(0u, 0u, 0u, 0u);
+      dr[u] = (ok[u] && da != nullptr) ? ld_packet(da + m * C + col * 8) : make_uint4(0u, 0u, 0u, 0u);
     }
-    store_bf8(dz + m * C + col * 8, out);
+#pragma unroll
+    for (int u = 0; u < PB_UNROLL; ++u) {
+      const long long m = m0 + u * stride;
+      if (m >= M) break;
+      Bf8 out;
+      if (!ok[u]) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) out.v[i] = 0.f;
+      } else {
+        const Bf8 zv = unpack_bf8(zr[u]);
+        const Bf8 dy = incoming_grad(da != nullptr, dr[u], g, arg, zv, sc, sh, m, C, N, col);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float zhat = (zv.v[i] - mu[i]) * rs[i];
+          out.v[i] = sc[i] * (dy.v[i] - k1[i] - zhat * k2[i]);
+        }
+      }
+      store_bf8(dz + m * C + col * 8, out);
+    }
   }
 }
 
@@ -288,7 +352,7 @@ pool_argmax_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict_
 static int pb_grid(long long M, int C) {
   const int rows_per_iter = PB_THREADS / (C >> 3);
   long long blocks = (M + rows_per_iter - 1) / rows_per_iter;
-  const long long cap = 148LL * 8;  // 8 resident CTAs of 256 threads per SM
+  const long long cap = 148LL * 4;  // a multiple of the SM count; bounds the fp64 atomics per channel
   return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
 }
 
