@@ -265,10 +265,35 @@ def run_native(args):
     prof = profiler.report()
     profiler.enable(False)
 
-    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    # secondary figure: the whole training step -- forward, loss, backward,
+    # gradient all-reduce over the ranks (the path's one collective), Adam -- as one CUDA graph
+    train = None
+    ms_train = 0.0
+    if not args.no_train:
+        try:
+            from multi_part_assembly_b200.runtime import GraphedTrainStep
+            opt = model.configure_optimizers()
+            if isinstance(opt, tuple):
+                opt = opt[0][0]
+            gts = GraphedTrainStep(model, opt, resident,
+                                   autocast_dtype=torch.bfloat16 if args.dtype == 'bf16' else None)
+            k_train = max(3, min(args.steps, 50))
+            for _ in range(3):
+                gts()
+            ms_train = timed(lambda: gts(), k_train)
+            train = {'steps': k_train, 'cuda_graph': True,
+                     'includes': 'forward + loss + backward + gradient all-reduce (N > 1) + Adam'}
+        except Exception as e:  # keep the headline line even if the capture fails on this box
+            train = {'error': repr(e)[:300]}
+            torch.cuda.synchronize()
+
+    t = torch.tensor([ms_total, ms_e2e, ms_train], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e = t.tolist()
+    ms_total, ms_e2e, ms_train = t.tolist()
+    if train is not None and 'error' not in train:
+        train['ms_per_step'] = ms_train / train['steps']
+        train['shapes_per_s'] = B_PER_GPU * world * train['steps'] / (ms_train / 1e3)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -316,6 +341,7 @@ def run_native(args):
         'e2e': {'value': shapes / (ms_e2e / 1e3), 'unit': 'shapes/s',
                 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4},
         'gpu_launches': launches,
+        'train_step': train,
         'roofline': roof,
         'cpu_baseline': {'value': cpu_B / cpu_t, 'unit': 'shapes/s', 'cores': threads,
                          'kind': 'port',
@@ -334,6 +360,7 @@ def main():
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'f32'])
     ap.add_argument('--no-graph', action='store_true', help='eager launches instead of a CUDA graph')
+    ap.add_argument('--no-train', action='store_true', help='skip the secondary training-step figure')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'native' else args.warmup
     if args.impl == 'reference':

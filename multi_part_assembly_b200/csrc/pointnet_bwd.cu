@@ -214,34 +214,38 @@ __device__ __forceinline__ Bf8 incoming_grad(bool has_da, const uint4& da_raw,
   return dy;
 }
 
-// sums[0][c] = sum dy, sums[1][c] = sum dy * zhat  (= d beta, d gamma)
-__global__ void __launch_bounds__(PB_THREADS)
+// Pass 1 of the BatchNorm backward: sums[0][c] = sum dy, sums[1][c] = sum dy * z (raw z:
+// the centring and 1/sigma are applied in fp64 by bn_bwd_fix_kernel, which keeps this
+// kernel's per-thread state to the 16 mask constants and 16 accumulators).
+constexpr int PB_BWD_UNROLL = 2;
+__global__ void __launch_bounds__(PB_THREADS, 3)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ da, const float* __restrict__ g,
                      const int* __restrict__ arg, const __nv_bfloat16* __restrict__ z, BnConst bn,
                      long long M, int C, int N, const float* __restrict__ valids,
                      double* __restrict__ sums) {
   const int tpr = C >> 3, col = threadIdx.x % tpr, rows_per_iter = PB_THREADS / tpr;
-  float sc[8], sh[8], mu[8], rs[8];
+  float sc[8], sh[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int c = col * 8 + i;
-    mu[i] = bn.mean[c]; rs[i] = bn.rstd[c];
-    sc[i] = bn.gamma[c] * rs[i]; sh[i] = bn.beta[c] - mu[i] * sc[i];
+    sc[i] = bn.gamma[c] * bn.rstd[c];
+    sh[i] = bn.beta[c] - bn.mean[c] * sc[i];
   }
   float acc[2][8] = {};
   const long long stride = (long long)gridDim.x * rows_per_iter;
-  for (long long m0 = (long long)blockIdx.x * rows_per_iter + threadIdx.x / tpr; m0 < M; m0 += PB_UNROLL * stride) {
-    uint4 zr[PB_UNROLL], dr[PB_UNROLL];
-    bool ok[PB_UNROLL];
+  for (long long m0 = (long long)blockIdx.x * rows_per_iter + threadIdx.x / tpr; m0 < M;
+       m0 += PB_BWD_UNROLL * stride) {
+    uint4 zr[PB_BWD_UNROLL], dr[PB_BWD_UNROLL];
+    bool ok[PB_BWD_UNROLL];
 #pragma unroll
-    for (int u = 0; u < PB_UNROLL; ++u) {
+    for (int u = 0; u < PB_BWD_UNROLL; ++u) {
       const long long m = m0 + u * stride;
       ok[u] = m < M && (valids == nullptr || valids[m / N] != 0.f);
       zr[u] = ok[u] ? ld_packet(z + m * C + col * 8) : make_uint4(0u, 0u, 0u, 0u);
       dr[u] = (ok[u] && da != nullptr) ? ld_packet(da + m * C + col * 8) : make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
-    for (int u = 0; u < PB_UNROLL; ++u) {
+    for (int u = 0; u < PB_BWD_UNROLL; ++u) {
       if (!ok[u]) continue;
       const long long m = m0 + u * stride;
       const Bf8 zv = unpack_bf8(zr[u]);
@@ -249,43 +253,53 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ da, const float* __restri
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         acc[0][i] += dy.v[i];
-        acc[1][i] = fmaf(dy.v[i], (zv.v[i] - mu[i]) * rs[i], acc[1][i]);
+        acc[1][i] = fmaf(dy.v[i], zv.v[i], acc[1][i]);
       }
     }
   }
   cta_column_reduce<2>(acc, C, sums);
 }
 
-// dz = gamma * rstd * (dy - S1/count - zhat * S2/count), bf16; zero rows for padded parts
-__global__ void __launch_bounds__(PB_THREADS)
+// sums[1][c] <- rstd * (sum dy*z - mean * sum dy) = sum dy * zhat  (= d gamma), in fp64
+__global__ void bn_bwd_fix_kernel(double* __restrict__ sums, int C, const float* __restrict__ mean,
+                                  const float* __restrict__ rstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) sums[C + c] = (double)rstd[c] * (sums[C + c] - (double)mean[c] * sums[c]);
+}
+
+// Pass 2: dz = gamma*rstd*(dy - S1/n - zhat*S2/n) = A*dy + B + D*z with per-channel
+// A = gamma*rstd, D = -A*rstd*S2/n, B = -A*S1/n - D*mean; bf16; zero rows for padded parts
+__global__ void __launch_bounds__(PB_THREADS, 3)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ da, const float* __restrict__ g,
                     const int* __restrict__ arg, const __nv_bfloat16* __restrict__ z, BnConst bn,
                     const double* __restrict__ sums, const float* __restrict__ count, long long M,
                     int C, int N, const float* __restrict__ valids, __nv_bfloat16* __restrict__ dz) {
   const int tpr = C >> 3, col = threadIdx.x % tpr, rows_per_iter = PB_THREADS / tpr;
-  float sc[8], sh[8], mu[8], rs[8], k1[8], k2[8];
+  float sc[8], sh[8], kb[8], kd[8];
   const float inv_n = 1.f / fmaxf(*count, 1.f);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int c = col * 8 + i;
-    mu[i] = bn.mean[c]; rs[i] = bn.rstd[c];
-    sc[i] = bn.gamma[c] * rs[i]; sh[i] = bn.beta[c] - mu[i] * sc[i];
-    k1[i] = (float)sums[c] * inv_n;
-    k2[i] = (float)sums[C + c] * inv_n;
+    const float mu = bn.mean[c], rs = bn.rstd[c];
+    sc[i] = bn.gamma[c] * rs;
+    sh[i] = bn.beta[c] - mu * sc[i];
+    kd[i] = -sc[i] * rs * ((float)sums[C + c] * inv_n);
+    kb[i] = -sc[i] * ((float)sums[c] * inv_n) - kd[i] * mu;
   }
   const long long stride = (long long)gridDim.x * rows_per_iter;
-  for (long long m0 = (long long)blockIdx.x * rows_per_iter + threadIdx.x / tpr; m0 < M; m0 += PB_UNROLL * stride) {
-    uint4 zr[PB_UNROLL], dr[PB_UNROLL];
-    bool ok[PB_UNROLL];
+  for (long long m0 = (long long)blockIdx.x * rows_per_iter + threadIdx.x / tpr; m0 < M;
+       m0 += PB_BWD_UNROLL * stride) {
+    uint4 zr[PB_BWD_UNROLL], dr[PB_BWD_UNROLL];
+    bool ok[PB_BWD_UNROLL];
 #pragma unroll
-    for (int u = 0; u < PB_UNROLL; ++u) {
+    for (int u = 0; u < PB_BWD_UNROLL; ++u) {
       const long long m = m0 + u * stride;
       ok[u] = m < M && (valids == nullptr || valids[m / N] != 0.f);
       zr[u] = ok[u] ? ld_packet(z + m * C + col * 8) : make_uint4(0u, 0u, 0u, 0u);
       dr[u] = (ok[u] && da != nullptr) ? ld_packet(da + m * C + col * 8) : make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
-    for (int u = 0; u < PB_UNROLL; ++u) {
+    for (int u = 0; u < PB_BWD_UNROLL; ++u) {
       const long long m = m0 + u * stride;
       if (m >= M) break;
       Bf8 out;
@@ -296,10 +310,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ da, const float* __restric
         const Bf8 zv = unpack_bf8(zr[u]);
         const Bf8 dy = incoming_grad(da != nullptr, dr[u], g, arg, zv, sc, sh, m, C, N, col);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float zhat = (zv.v[i] - mu[i]) * rs[i];
-          out.v[i] = sc[i] * (dy.v[i] - k1[i] - zhat * k2[i]);
-        }
+        for (int i = 0; i < 8; ++i) out.v[i] = fmaf(sc[i], dy.v[i], fmaf(kd[i], zv.v[i], kb[i]));
       }
       store_bf8(dz + m * C + col * 8, out);
     }
@@ -352,7 +363,7 @@ pool_argmax_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict_
 static int pb_grid(long long M, int C) {
   const int rows_per_iter = PB_THREADS / (C >> 3);
   long long blocks = (M + rows_per_iter - 1) / rows_per_iter;
-  const long long cap = 148LL * 4;  // a multiple of the SM count; bounds the fp64 atomics per channel
+  const long long cap = 148LL * 3;  // one wave at 3 CTAs per SM; bounds the fp64 atomics per channel
   return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
 }
 
@@ -429,6 +440,8 @@ int mpa_bn_backward(const void* da, const float* g, const int32_t* arg, const vo
     bn_bwd_reduce_kernel<<<pb_grid(M, C), PB_THREADS, 0, stream>>>(
         (const __nv_bfloat16*)da, g, arg, (const __nv_bfloat16*)z, bn, M, C, N, valids, sums);
   }
+  MPA_LAUNCH_CHECK();
+  bn_bwd_fix_kernel<<<(C + 127) / 128, 128, 0, stream>>>(sums, C, mean, rstd);
   MPA_LAUNCH_CHECK();
   {
     ProfScope ps("bn_bwd_apply", stream);

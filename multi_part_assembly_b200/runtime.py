@@ -90,6 +90,32 @@ class GraphedStep:
         return self.static_out
 
 
+def allreduce_gradients(params, group=None):
+    """Average the gradients of `params` over the ranks of `group`: the one data-path
+    collective of data-parallel training (the reference gets it implicitly from DDP,
+    scripts/train.py:85,141).  One flat fp32 buffer, ONE all-reduce (3.3 M elements =
+    13 MB for pn_transformer: latency-bound on NVLink, so no bucketing), scattered back
+    with a multi-tensor copy.  Safe to record into a CUDA graph (NCCL)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return
+    world = dist.get_world_size(group)
+    if world == 1:
+        return
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1).float() for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat.div_(world)
+    views, off = [], 0
+    for g in grads:
+        n = g.numel()
+        views.append(flat[off:off + n].view_as(g))
+        off += n
+    torch._foreach_copy_(grads, views)
+
+
 class GraphedTrainStep:
     """Whole training step -- forward, loss, backward, optimizer -- as one CUDA graph.
 
@@ -97,15 +123,19 @@ class GraphedTrainStep:
     pn_transformer training step, several times what the GPU needs to run them.  The
     step is captured once for a fixed batch shape (the optimizer must keep its state on
     the device: Adam/AdamW are switched to `capturable`) and replayed per batch; inputs
-    go through static buffers like `GraphedStep`.  Reference loop being replaced: the
+    go through static buffers like `GraphedStep`.  With torch.distributed initialised the
+    gradient all-reduce of data-parallel training is part of the graph.  Reference loop being replaced: the
     PL training loop around `BaseModel.training_step` (models/modules/base_model.py:60-63)
     with automatic optimisation and `--fp16` autocast (scripts/train.py:88).
     """
 
-    def __init__(self, model, optimizer, example_batch, autocast_dtype=torch.bfloat16, warmup=3):
+    def __init__(self, model, optimizer, example_batch, autocast_dtype=torch.bfloat16, warmup=3,
+                 group=None):
         self.model = model
         self.optimizer = optimizer
         self.autocast_dtype = autocast_dtype
+        self.group = group
+        self._params = [p for p in model.parameters() if p.requires_grad]
         dev = next(model.parameters()).device
         self.device = dev
         for group in optimizer.param_groups:
@@ -131,6 +161,7 @@ class GraphedTrainStep:
                             enabled=self.autocast_dtype is not None):
             loss = self.model.training_step(dict(self.static_in), 0)
         loss.backward()
+        allreduce_gradients(self._params, self.group)  # no-op on a single rank
         return loss.detach()
 
     def _eager_step(self):

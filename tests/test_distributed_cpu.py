@@ -58,3 +58,41 @@ def test_sync_dist_mean_and_sharding():
     assert abs(logged['val/loss'] - 3.0) < 1e-6
     assert abs(logged['val/part_acc'] - 0.25) < 1e-6
     assert ids == list(range(8))
+
+
+def _grad_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank),
+                      LOCAL_RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from multi_part_assembly_b200.runtime import allreduce_gradients
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3))  # same init on both ranks
+    unused = torch.nn.Parameter(torch.zeros(4))                             # a parameter without grad
+    x = torch.full((2, 5), float(rank + 1))
+    net(x).sum().backward()
+    local = [p.grad.clone() for p in net.parameters()]
+    allreduce_gradients(list(net.parameters()) + [unused])
+    gathered = [[torch.zeros_like(g) for _ in range(world)] for g in local]
+    for g, bufs in zip(local, gathered):
+        dist.all_gather(bufs, g)
+    ok = all(torch.allclose(p.grad, torch.stack(bufs).mean(0), atol=1e-6)
+             for p, bufs in zip(net.parameters(), gathered)) and unused.grad is None
+    if rank == 0:
+        out.put(bool(ok))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_averages_over_ranks():
+    """Data-parallel training: one flat all-reduce averages every gradient (the
+    reference's implicit DDP reduction, scripts/train.py:85,141)."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert ok

@@ -15,6 +15,7 @@ for extra in "$@"; do
     occ) bash tools/sweep_occ.sh "1.0 1.4" "1 1.5 2 3 4 6" > gpurun_out/sweep_occ.txt 2>&1; cat gpurun_out/sweep_occ.txt;;
     train) timeout 600 python tools/bench_train_step.py > gpurun_out/train_step.log 2>&1; tail -4 gpurun_out/train_step.log;;
     trainprof) timeout 600 python tools/profile_train_step.py > gpurun_out/train_profile.txt 2>&1; head -45 gpurun_out/train_profile.txt | cut -c1-200;;
+    smoke) timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log;;
     refbench) timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; cat gpurun_out/bench_reference.json;;
   esac
 done
