@@ -11,7 +11,7 @@ python tools/summarize_launches.py gpurun_out/launches_graph_step.csv 1 > gpurun
 for extra in "$@"; do
   case $extra in
     configs) timeout 900 python tools/bench_configs.py > gpurun_out/configs.log 2>&1; tail -12 gpurun_out/configs.log;;
-    ncu) timeout 400 ncu --profile-from-start off --graph-profiling node --set full --clock-control none --import-source on -k regex:'linear_bf16_kernel|pose_head|grid_nn_kernel' -o gpurun_out/top_full -f python tools/profile_graph_step.py > gpurun_out/ncu_full.log 2>&1; tail -2 gpurun_out/ncu_full.log;;
+    ncu) timeout 400 ncu --profile-from-start off --graph-profiling node --set full --clock-control none --import-source on -k regex:'grid_nn_kernel|grid_build_kernel|pointnet_phase_kernel|linear_bf16_kernel|attention_kernel|pose_head_kernel' -o gpurun_out/top_full -f python tools/profile_graph_step.py > gpurun_out/ncu_full.log 2>&1; tail -2 gpurun_out/ncu_full.log;;
     occ) bash tools/sweep_occ.sh "1.0 1.4" "1 1.5 2 3 4 6" > gpurun_out/sweep_occ.txt 2>&1; cat gpurun_out/sweep_occ.txt;;
     train) timeout 600 python tools/bench_train_step.py > gpurun_out/train_step.log 2>&1; tail -4 gpurun_out/train_step.log;;
     trainprof) timeout 600 python tools/profile_train_step.py > gpurun_out/train_profile.txt 2>&1; head -45 gpurun_out/train_profile.txt | cut -c1-200;;
