@@ -316,8 +316,16 @@ def run_native(args):
         # clouds (12 read + 4 dist + 8 idx as the reference writes them), SURVEY.md 8d
         alg_bytes = d.get('alg_bytes_per_launch', 24.0 * B_PER_GPU * 2 * P * N_PTS)
         achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
+        # DRAM bytes of one launch of that kernel from the committed `ncu --set full` capture
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'r01_ncu_traffic.json'))).get(dom)
+            if tr is not None:
+                traffic = tr['dram_bytes_read'] + tr['dram_bytes_write']
+        except (OSError, ValueError, KeyError):
+            pass
         roof = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': hbm_peak,
-                'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': None,
+                'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': traffic,
                 'avg_launch_ms': avg_ms, 'share_of_step': d['ms_total'] / sum(
                     v['ms_total'] for v in prof.values()),
                 'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback 6650 GB/s',
