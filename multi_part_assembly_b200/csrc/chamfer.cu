@@ -834,7 +834,7 @@ static int run_grid(CloudDesc c0, CloudDesc c1, int S, float* dist0, IdxT* idx0,
     static int use_eff = 1;
     if (occ < 0.f) {  // tuning knobs (defaults chosen from the sweep in profiles/)
       const char* e = getenv("MPA_GRID_OCC");
-      occ = e ? (float)atof(e) : 4.0f;
+      occ = e ? (float)atof(e) : 3.0f;
       const char* u = getenv("MPA_GRID_EFF");
       use_eff = u ? atoi(u) : 0;
     }

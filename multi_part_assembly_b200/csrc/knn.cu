@@ -139,6 +139,176 @@ knn_kernel(const float* __restrict__ x, const float* __restrict__ xx, int N, int
   }
 }
 
+// ---- register-tiled variant (k <= 32) ------------------------------------------
+// One CTA = 128 query rows of one part; candidates stream through in blocks of 128.
+// The 128 x 128 score block is an 8 x 8 register tile per thread (64 FMAs per 4
+// 16-byte shared-memory loads: FMA-issue bound instead of LDS bound), accumulated
+// over the channels in ascending order with one accumulator per pair -- the oracle's
+// order, so the scores are bit-identical to knn_kernel's.  The next operand chunk is
+// prefetched into registers while the current one is multiplied.  Each finished block
+// goes through shared memory once; a warp then merges it into its rows' running top-k
+// lists (lane l holds the l-th best; a candidate is inserted with one ballot and one
+// shuffle), so only k entries per row survive a block and nothing N x N exists.
+constexpr int KT = 128;        // query rows per CTA = candidates per block
+constexpr int KT_KC = 32;      // channels per chunk
+constexpr int KT_THREADS = 256;
+constexpr int KT_SP = KT + 4;  // score tile pitch (floats)
+constexpr int KT_SMEM = sizeof(float) * (2 * KT_KC * KT + KT * KT_SP) + sizeof(float) * KT * 32 +
+                        sizeof(int) * KT * 32;
+
+__global__ void __launch_bounds__(KT_THREADS, 1)
+knn_tile_kernel(const float* __restrict__ x, const float* __restrict__ xx, int N, int C, int k,
+                int* __restrict__ idx) {
+  extern __shared__ float sm[];
+  float* As = sm;                       // [KT_KC][KT]  queries, channel-major
+  float* Bs = As + KT_KC * KT;          // [KT_KC][KT]  candidates
+  float* S = Bs + KT_KC * KT;           // [KT][KT_SP]  score block
+  float* topv = S + KT * KT_SP;         // [KT][32]
+  int* topi = reinterpret_cast<int*>(topv + KT * 32);  // [KT][32]
+  const int tiles = (N + KT - 1) / KT;
+  const int part = blockIdx.x / tiles, i0 = (blockIdx.x % tiles) * KT;
+  const float* xp = x + (long long)part * N * C;
+  const float* xxp = xx + (long long)part * N;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads; rows {4ty+r, 64+4ty+r}, cols {4tx+c, 64+4tx+c}
+  const float ninf = -__int_as_float(0x7f800000);
+  const int nchunks = (C + KT_KC - 1) / KT_KC;
+  const int nblocks = (N + KT - 1) / KT;
+
+  for (int e = tid; e < KT * 32; e += KT_THREADS) { topv[e] = ninf; topi[e] = 0x7fffffff; }
+
+  // loader role: row lr of the tile, channel quads lq, lq+2, lq+4, lq+6 of the chunk
+  const int lr = tid & 127, lq = tid >> 7;
+  float4 pa[4], pb[4];
+  auto fetch = [&](int j0, int kc) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = kc + 4 * (lq + 2 * i);
+      const int ra = i0 + lr, rb = j0 + lr;
+      pa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      pb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c + 3 < C) {
+        if ((C & 3) == 0) {
+          if (ra < N) pa[i] = *reinterpret_cast<const float4*>(xp + (long long)ra * C + c);
+          if (rb < N) pb[i] = *reinterpret_cast<const float4*>(xp + (long long)rb * C + c);
+        } else {
+          if (ra < N) { const float* p = xp + (long long)ra * C + c; pa[i] = make_float4(p[0], p[1], p[2], p[3]); }
+          if (rb < N) { const float* p = xp + (long long)rb * C + c; pb[i] = make_float4(p[0], p[1], p[2], p[3]); }
+        }
+      } else if (c < C) {  // ragged channel tail
+        float ta[4] = {0.f, 0.f, 0.f, 0.f}, tb[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int e = 0; e < 4 && c + e < C; ++e) {
+          if (ra < N) ta[e] = xp[(long long)ra * C + c + e];
+          if (rb < N) tb[e] = xp[(long long)rb * C + c + e];
+        }
+        pa[i] = make_float4(ta[0], ta[1], ta[2], ta[3]);
+        pb[i] = make_float4(tb[0], tb[1], tb[2], tb[3]);
+      }
+    }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int kk = 4 * (lq + 2 * i);
+      As[(kk + 0) * KT + lr] = pa[i].x; As[(kk + 1) * KT + lr] = pa[i].y;
+      As[(kk + 2) * KT + lr] = pa[i].z; As[(kk + 3) * KT + lr] = pa[i].w;
+      Bs[(kk + 0) * KT + lr] = pb[i].x; Bs[(kk + 1) * KT + lr] = pb[i].y;
+      Bs[(kk + 2) * KT + lr] = pb[i].z; Bs[(kk + 3) * KT + lr] = pb[i].w;
+    }
+  };
+
+  fetch(0, 0);
+  for (int jb = 0; jb < nblocks; ++jb) {
+    const int j0 = jb * KT;
+    float acc[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const int kc = ch * KT_KC;
+      __syncthreads();  // previous chunk's multiplies (and the previous block's selection) are done
+      stash();
+      __syncthreads();
+      // prefetch the next chunk (next channel slice, or the first slice of the next block)
+      if (ch + 1 < nchunks) fetch(j0, kc + KT_KC);
+      else if (jb + 1 < nblocks) fetch(j0 + KT, 0);
+      const int klen = min(KT_KC, ((C - kc) + 3) & ~3);
+#pragma unroll 4
+      for (int kk = 0; kk < klen; ++kk) {
+        const float4 a0 = *reinterpret_cast<const float4*>(&As[kk * KT + 4 * ty]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&As[kk * KT + 64 + 4 * ty]);
+        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk * KT + 4 * tx]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk * KT + 64 + 4 * tx]);
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[r][c] = __fmaf_rn(a[r], b[c], acc[r][c]);  // ascending channel
+      }
+    }
+    // ---- scores of this block -> shared memory ----
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int row = (r < 4 ? 0 : 60) + 4 * ty + r;  // 4ty+r or 64+4ty+(r-4)
+      const float xi = (i0 + row < N) ? xxp[i0 + row] : 0.f;
+      float sv[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int j = j0 + (c < 4 ? 0 : 60) + 4 * tx + c;
+        float s = ninf;
+        if (j < N) {
+          const float inner = __fmul_rn(-2.0f, acc[r][c]);          // dgcnn.py:10
+          s = __fsub_rn(__fsub_rn(-xxp[j], inner), xi);             // dgcnn.py:12
+        }
+        sv[c] = s;
+      }
+      *reinterpret_cast<float4*>(&S[row * KT_SP + 4 * tx]) = make_float4(sv[0], sv[1], sv[2], sv[3]);
+      *reinterpret_cast<float4*>(&S[row * KT_SP + 64 + 4 * tx]) = make_float4(sv[4], sv[5], sv[6], sv[7]);
+    }
+    __syncthreads();
+    // ---- merge into the rows' top-k lists: warp w owns rows 16w .. 16w+15 ----
+    for (int rr = 0; rr < 16; ++rr) {
+      const int row = warp * 16 + rr;
+      if (i0 + row >= N) break;
+      float lv = topv[row * 32 + lane];
+      int li = topi[row * 32 + lane];
+      float thr = __shfl_sync(0xffffffffu, lv, k - 1);
+      int ithr = __shfl_sync(0xffffffffu, li, k - 1);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int j = j0 + lane + 32 * c;
+        const float v = S[row * KT_SP + lane + 32 * c];
+        unsigned m = __ballot_sync(0xffffffffu, j < N && (v > thr || (v == thr && j < ithr)));
+        while (m) {
+          const int src = __ffs(m) - 1;
+          m &= m - 1;
+          const float vn = __shfl_sync(0xffffffffu, v, src);
+          const int in = j0 + src + 32 * c;
+          if (!(vn > thr || (vn == thr && in < ithr))) continue;  // the list moved on meanwhile
+          const bool better = lv > vn || (lv == vn && li < in);
+          const int pos = __popc(__ballot_sync(0xffffffffu, better && lane < k));
+          const float uv_ = __shfl_up_sync(0xffffffffu, lv, 1);
+          const int ui = __shfl_up_sync(0xffffffffu, li, 1);
+          if (lane > pos) { lv = uv_; li = ui; }
+          else if (lane == pos) { lv = vn; li = in; }
+          thr = __shfl_sync(0xffffffffu, lv, k - 1);
+          ithr = __shfl_sync(0xffffffffu, li, k - 1);
+        }
+      }
+      topv[row * 32 + lane] = lv;
+      topi[row * 32 + lane] = li;
+    }
+    // (the next iteration's first __syncthreads orders this selection before S is rewritten)
+  }
+  __syncthreads();
+  for (int e = tid; e < KT * k; e += KT_THREADS) {
+    const int row = e / k, s_ = e % k;
+    if (i0 + row < N) idx[((long long)part * N + i0 + row) * k + s_] = topi[row * 32 + s_];
+  }
+}
+
 // uv [M, 2*Co] (u | v), idx [M, k] (indices local to the part), M = n*N.
 // One CTA per PTS points, thread = channel.  ymax/ymin [M, Co]; partial [gridDim, Co, 2].
 constexpr int EC_PTS = 8;
@@ -232,6 +402,20 @@ int mpa_knn(const float* x, int n, int N, int C, int k, int32_t* idx, void* ws, 
     sqnorm_kernel<<<592, 256, 0, stream>>>(x, (long long)n * N, C, xx);
   }
   MPA_LAUNCH_CHECK();
+  static const int legacy = getenv("MPA_KNN_LEGACY") ? atoi(getenv("MPA_KNN_LEGACY")) : 0;
+  if (k <= 32 && !legacy) {
+    static bool attr_t = false;
+    if (!attr_t) {
+      MPA_CUDA(cudaFuncSetAttribute(knn_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KT_SMEM));
+      attr_t = true;
+    }
+    {
+      ProfScope ps("knn", stream);
+      knn_tile_kernel<<<n * ((N + KT - 1) / KT), KT_THREADS, KT_SMEM, stream>>>(x, xx, N, C, k, idx);
+    }
+    MPA_LAUNCH_CHECK();
+    return MPA_OK;
+  }
   static const int rows_env = getenv("MPA_KNN_ROWS") ? atoi(getenv("MPA_KNN_ROWS")) : 0;
   const int rows = rows_env ? rows_env : 16;  // 16 rows: 2 CTAs per SM (profiles/: 42.0 -> 33.5 ms at cfg D)
   const int Cp = ((C + 3) & ~3) + 4;

@@ -223,12 +223,9 @@ __global__ void __launch_bounds__(PN_THREADS, 1) pointnet_phase_kernel(PointNetA
         *reinterpret_cast<uint4*>(act + row * 128 + (((chunk ^ row) & 7) << 4)) =
             make_uint4(w[0], w[1], w[2], w[3]);
     }
-    if (dbg_on) dbg[1] = clock64();
     tc::fence_async_smem();
-    if (dbg_on) dbg[2] = clock64();
     tc::fence_before_sync();
     tc::group_sync(1 + g, 128);
-    if (dbg_on) dbg[3] = clock64();
 
 #pragma unroll
     for (int layer = 1; layer <= PHASE; ++layer) {
@@ -249,11 +246,11 @@ __global__ void __launch_bounds__(PN_THREADS, 1) pointnet_phase_kernel(PointNetA
         }
         tc::mma_commit(&mbar[g]);
       }
-      if (dbg_on && layer == 1) dbg[4] = clock64();
+      if (dbg_on) dbg[3 * (layer - 1) + 1] = clock64();  // operand ready + MMAs issued
       tc::mbar_wait(&mbar[g], parity);
       parity ^= 1u;
       tc::fence_after_sync();
-      if (dbg_on && layer == 1) dbg[5] = clock64();
+      if (dbg_on) dbg[3 * (layer - 1) + 2] = clock64();  // accumulator complete
 
       // ---- epilogue ----
       // 64-channel layers: lanes 64..127 hold a copy of rows 0..63, so warps 2,3 take
@@ -329,13 +326,12 @@ __global__ void __launch_bounds__(PN_THREADS, 1) pointnet_phase_kernel(PointNetA
         }
         tc::fence_before_sync();  // TMEM reads done before the next tile's MMA overwrites
       }
-      if (dbg_on && layer == 1) dbg[6] = clock64();
+      if (dbg_on) dbg[3 * (layer - 1) + 3] = clock64();  // epilogue done
     }
-    if (dbg_on) dbg[7] = clock64();
   }
 
   if (a.dbg != nullptr && blockIdx.x == 0 && tid == 0) {
-    a.dbg[8] = t_setup - t_entry; a.dbg[9] = t_weights - t_entry; a.dbg[10] = clock64() - t_entry;
+    a.dbg[128] = t_setup - t_entry; a.dbg[129] = t_weights - t_entry; a.dbg[130] = clock64() - t_entry;
   }
   // ---- per-CTA partial statistics (groups combined in a fixed order) ----
 #pragma unroll
@@ -538,8 +534,8 @@ int mpa_pointnet_forward(const float* pts, const float* valids, int n_parts, int
   long long* dbg = nullptr;
   static const bool want_dbg = getenv("MPA_PN_DEBUG") != nullptr;
   if (want_dbg) {
-    MPA_CUDA(cudaMalloc((void**)&dbg, sizeof(long long) * 16 * 8));
-    MPA_CUDA(cudaMemset(dbg, 0, sizeof(long long) * 16 * 8));
+    MPA_CUDA(cudaMalloc((void**)&dbg, sizeof(long long) * 16 * 9));
+    MPA_CUDA(cudaMemset(dbg, 0, sizeof(long long) * 16 * 9));
   }
   // per-CTA partial sums, double buffered: launch l reads what launch l-1 wrote
   float* partial_buf[2] = {partial, partial + (size_t)2 * PN_MAXC * 160};
@@ -567,13 +563,13 @@ int mpa_pointnet_forward(const float* pts, const float* valids, int n_parts, int
       }
       if (rc != MPA_OK) return rc;
       if (want_dbg) {  // debug: cycle stamps of CTA 0 / pipeline 0, first 8 tiles
-        long long h[16 * 8];
+        long long h[16 * 9];
         cudaStreamSynchronize(stream);
         cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
         for (int t = 0; t < 8; ++t) {
-          if (t == 0) fprintf(stderr, "[pn phase %d] setup %lld weights %lld loop-end %lld cycles\n", layer + 1, h[8], h[9], h[10]);
-          fprintf(stderr, "[pn phase %d tile %d]", layer + 1, t);
-          for (int k = 1; k < 8; ++k) fprintf(stderr, " %lld", h[t * 16 + k] ? h[t * 16 + k] - h[t * 16] : -1);
+          if (t == 0) fprintf(stderr, "[pn phase %d] setup %lld weights %lld loop-end %lld cycles\n", layer + 1, h[128], h[129], h[130]);
+          fprintf(stderr, "[pn phase %d tile %d] (issued, mma done, epilogue done) per layer:", layer + 1, t);
+          for (int k = 1; k < 16; ++k) fprintf(stderr, "%s%lld", (k % 3 == 1) ? " | " : " ", h[t * 16 + k] ? h[t * 16 + k] - h[t * 16] : -1);
           fprintf(stderr, "  (next tile +%lld)\n", t < 7 ? h[(t + 1) * 16] - h[t * 16] : 0);
         }
         cudaMemset(dbg, 0, sizeof(h));

@@ -16,6 +16,8 @@ for extra in "$@"; do
     train) timeout 600 python tools/bench_train_step.py > gpurun_out/train_step.log 2>&1; tail -4 gpurun_out/train_step.log;;
     trainprof) timeout 600 python tools/profile_train_step.py > gpurun_out/train_profile.txt 2>&1; head -45 gpurun_out/train_profile.txt | cut -c1-200;;
     smoke) timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log;;
+    dgcnn) timeout 600 python tools/run_dgl_dgcnn.py 32 3 > gpurun_out/dgl_dgcnn.txt 2>&1; grep -v Warn gpurun_out/dgl_dgcnn.txt | head -40;;
+    pndebug) MPA_PN_DEBUG=1 timeout 300 python tools/pn_debug.py > gpurun_out/pn_debug.txt 2>&1; grep "pn phase 5" gpurun_out/pn_debug.txt | tail -9;;
     refbench) timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; cat gpurun_out/bench_reference.json;;
   esac
 done
