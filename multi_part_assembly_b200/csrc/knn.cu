@@ -147,14 +147,45 @@ knn_kernel(const float* __restrict__ x, const float* __restrict__ xx, int N, int
 // order, so the scores are bit-identical to knn_kernel's.  The next operand chunk is
 // prefetched into registers while the current one is multiplied.  Each finished block
 // goes through shared memory once; a warp then merges it into its rows' running top-k
-// lists (lane l holds the l-th best; a candidate is inserted with one ballot and one
-// shuffle), so only k entries per row survive a block and nothing N x N exists.
+// state: 32 sorted best keys + up to 32 pending candidates per row ((score, index)
+// packed into one ordered 64-bit key).  Candidates that beat the current k-th best are
+// appended with one ballot; when the pending half would overflow, a 64-key bitonic sort
+// (shuffles) folds it into the sorted half.  Nothing of size N x N exists.
 constexpr int KT = 128;        // query rows per CTA = candidates per block
 constexpr int KT_KC = 32;      // channels per chunk
 constexpr int KT_THREADS = 256;
 constexpr int KT_SP = KT + 4;  // score tile pitch (floats)
-constexpr int KT_SMEM = sizeof(float) * (2 * KT_KC * KT + KT * KT_SP) + sizeof(float) * KT * 32 +
-                        sizeof(int) * KT * 32;
+constexpr int KT_IL = 2;       // rows a warp merges at a time (independent shuffle chains)
+constexpr int KT_SMEM = sizeof(float) * (2 * KT_KC * KT + KT * KT_SP) + 2 * sizeof(unsigned long long) * KT * 32 +
+                        sizeof(int) * KT;
+
+// (score, index) as one unsigned key: larger = better (higher score, then lower index)
+__device__ __forceinline__ unsigned long long knn_key(float v, int j) {
+  const unsigned b = __float_as_uint(v);
+  const unsigned o = (b & 0x80000000u) ? ~b : (b | 0x80000000u);  // order-preserving float -> uint
+  return ((unsigned long long)o << 32) | (unsigned long long)(~(unsigned)j);
+}
+// bitonic sort of the 64 keys (a of lane l = element l, b = element 32 + l) into descending order
+__device__ __forceinline__ void knn_sort64(unsigned long long& a, unsigned long long& b, int lane) {
+#pragma unroll
+  for (int kk = 2; kk <= 64; kk <<= 1) {
+#pragma unroll
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      if (j == 32) {  // partner is the other register of the same lane; kk == 64: descending
+        const unsigned long long hi = a > b ? a : b, lo = a > b ? b : a;
+        a = hi; b = lo;
+      } else {
+        const unsigned long long pa = __shfl_xor_sync(0xffffffffu, a, j);
+        const unsigned long long pb = __shfl_xor_sync(0xffffffffu, b, j);
+        const bool lower = (lane & j) == 0;
+        const bool desc_a = (lane & kk) == 0;          // element index = lane
+        const bool desc_b = ((32 + lane) & kk) == 0;   // element index = 32 + lane
+        a = (lower == desc_a) ? (a > pa ? a : pa) : (a > pa ? pa : a);
+        b = (lower == desc_b) ? (b > pb ? b : pb) : (b > pb ? pb : b);
+      }
+    }
+  }
+}
 
 __global__ void __launch_bounds__(KT_THREADS, 1)
 knn_tile_kernel(const float* __restrict__ x, const float* __restrict__ xx, int N, int C, int k,
@@ -163,8 +194,9 @@ knn_tile_kernel(const float* __restrict__ x, const float* __restrict__ xx, int N
   float* As = sm;                       // [KT_KC][KT]  queries, channel-major
   float* Bs = As + KT_KC * KT;          // [KT_KC][KT]  candidates
   float* S = Bs + KT_KC * KT;           // [KT][KT_SP]  score block
-  float* topv = S + KT * KT_SP;         // [KT][32]
-  int* topi = reinterpret_cast<int*>(topv + KT * 32);  // [KT][32]
+  unsigned long long* topk = reinterpret_cast<unsigned long long*>(S + KT * KT_SP);  // [KT][32] sorted best
+  unsigned long long* pend = topk + KT * 32;                                         // [KT][32] pending
+  int* pcnt = reinterpret_cast<int*>(pend + KT * 32);                                // [KT]
   const int tiles = (N + KT - 1) / KT;
   const int part = blockIdx.x / tiles, i0 = (blockIdx.x % tiles) * KT;
   const float* xp = x + (long long)part * N * C;
@@ -175,7 +207,8 @@ knn_tile_kernel(const float* __restrict__ x, const float* __restrict__ xx, int N
   const int nchunks = (C + KT_KC - 1) / KT_KC;
   const int nblocks = (N + KT - 1) / KT;
 
-  for (int e = tid; e < KT * 32; e += KT_THREADS) { topv[e] = ninf; topi[e] = 0x7fffffff; }
+  for (int e = tid; e < KT * 32; e += KT_THREADS) { topk[e] = 0ull; pend[e] = 0ull; }
+  if (tid < KT) pcnt[tid] = 0;
 
   // loader role: row lr of the tile, channel quads lq, lq+2, lq+4, lq+6 of the chunk
   const int lr = tid & 127, lq = tid >> 7;
@@ -268,44 +301,68 @@ knn_tile_kernel(const float* __restrict__ x, const float* __restrict__ xx, int N
       *reinterpret_cast<float4*>(&S[row * KT_SP + 64 + 4 * tx]) = make_float4(sv[4], sv[5], sv[6], sv[7]);
     }
     __syncthreads();
-    // ---- merge into the rows' top-k lists: warp w owns rows 16w .. 16w+15 ----
-    for (int rr = 0; rr < 16; ++rr) {
-      const int row = warp * 16 + rr;
-      if (i0 + row >= N) break;
-      float lv = topv[row * 32 + lane];
-      int li = topi[row * 32 + lane];
-      float thr = __shfl_sync(0xffffffffu, lv, k - 1);
-      int ithr = __shfl_sync(0xffffffffu, li, k - 1);
+    // ---- merge into the rows' top-k state: warp w owns rows 16w .. 16w+15, two at a time ----
+    for (int rr = 0; rr < 16; rr += KT_IL) {
+      const int row0 = warp * 16 + rr;
+      if (i0 + row0 >= N) break;
+      unsigned long long r0[KT_IL], r1[KT_IL], tau[KT_IL];
+      int cnt[KT_IL];
+#pragma unroll
+      for (int u = 0; u < KT_IL; ++u) {
+        r0[u] = topk[(row0 + u) * 32 + lane];
+        r1[u] = pend[(row0 + u) * 32 + lane];
+        cnt[u] = pcnt[row0 + u];
+        tau[u] = __shfl_sync(0xffffffffu, r0[u], k - 1);
+      }
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         const int j = j0 + lane + 32 * c;
-        const float v = S[row * KT_SP + lane + 32 * c];
-        unsigned m = __ballot_sync(0xffffffffu, j < N && (v > thr || (v == thr && j < ithr)));
-        while (m) {
-          const int src = __ffs(m) - 1;
-          m &= m - 1;
-          const float vn = __shfl_sync(0xffffffffu, v, src);
-          const int in = j0 + src + 32 * c;
-          if (!(vn > thr || (vn == thr && in < ithr))) continue;  // the list moved on meanwhile
-          const bool better = lv > vn || (lv == vn && li < in);
-          const int pos = __popc(__ballot_sync(0xffffffffu, better && lane < k));
-          const float uv_ = __shfl_up_sync(0xffffffffu, lv, 1);
-          const int ui = __shfl_up_sync(0xffffffffu, li, 1);
-          if (lane > pos) { lv = uv_; li = ui; }
-          else if (lane == pos) { lv = vn; li = in; }
-          thr = __shfl_sync(0xffffffffu, lv, k - 1);
-          ithr = __shfl_sync(0xffffffffu, li, k - 1);
+        unsigned long long key[KT_IL];
+        unsigned m[KT_IL];
+        bool overflow = false;
+#pragma unroll
+        for (int u = 0; u < KT_IL; ++u) {
+          key[u] = knn_key(S[(row0 + u) * KT_SP + lane + 32 * c], j);
+          m[u] = __ballot_sync(0xffffffffu, j < N && key[u] > tau[u]);
+          overflow |= cnt[u] + __popc(m[u]) > 32;
+        }
+        if (overflow) {  // fold the pending candidates into the sorted top list (both rows: uniform)
+#pragma unroll
+          for (int u = 0; u < KT_IL; ++u) {
+            knn_sort64(r0[u], r1[u], lane);
+            r1[u] = 0ull;
+            cnt[u] = 0;
+            tau[u] = __shfl_sync(0xffffffffu, r0[u], k - 1);
+            m[u] = __ballot_sync(0xffffffffu, j < N && key[u] > tau[u]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < KT_IL; ++u) {  // append the passing candidates behind the pending ones
+          const int n_new = __popc(m[u]);
+          const int d = lane - cnt[u];
+          const bool take = d >= 0 && d < n_new;
+          const int src = take ? (int)__fns(m[u], 0, d + 1) : 0;
+          const unsigned long long kk = __shfl_sync(0xffffffffu, key[u], src);
+          if (take) r1[u] = kk;
+          cnt[u] += n_new;
         }
       }
-      topv[row * 32 + lane] = lv;
-      topi[row * 32 + lane] = li;
+#pragma unroll
+      for (int u = 0; u < KT_IL; ++u) {
+        topk[(row0 + u) * 32 + lane] = r0[u];
+        pend[(row0 + u) * 32 + lane] = r1[u];
+        if (lane == 0) pcnt[row0 + u] = cnt[u];
+      }
     }
     // (the next iteration's first __syncthreads orders this selection before S is rewritten)
   }
-  __syncthreads();
-  for (int e = tid; e < KT * k; e += KT_THREADS) {
-    const int row = e / k, s_ = e % k;
-    if (i0 + row < N) idx[((long long)part * N + i0 + row) * k + s_] = topi[row * 32 + s_];
+  // ---- final fold of the pending candidates, then the k best indices, best first ----
+  for (int rr = 0; rr < 16; ++rr) {
+    const int row = warp * 16 + rr;
+    if (i0 + row >= N) break;
+    unsigned long long r0 = topk[row * 32 + lane], r1 = pend[row * 32 + lane];
+    knn_sort64(r0, r1, lane);
+    if (lane < k) idx[((long long)part * N + i0 + row) * k + lane] = (int)(~(unsigned)(r0 & 0xffffffffull));
   }
 }
 
