@@ -155,7 +155,7 @@ constexpr int KT = 128;        // query rows per CTA = candidates per block
 constexpr int KT_KC = 32;      // channels per chunk
 constexpr int KT_THREADS = 256;
 constexpr int KT_SP = KT + 4;  // score tile pitch (floats)
-constexpr int KT_IL = 2;       // rows a warp merges at a time (independent shuffle chains)
+constexpr int KT_IL = 4;       // rows a warp merges at a time (independent shuffle chains)
 constexpr int KT_SMEM = sizeof(float) * (2 * KT_KC * KT + KT * KT_SP) + 2 * sizeof(unsigned long long) * KT * 32 +
                         sizeof(int) * KT;
 
@@ -207,7 +207,7 @@ knn_tile_kernel(const float* __restrict__ x, const float* __restrict__ xx, int N
   const int nchunks = (C + KT_KC - 1) / KT_KC;
   const int nblocks = (N + KT - 1) / KT;
 
-  for (int e = tid; e < KT * 32; e += KT_THREADS) { topk[e] = 0ull; pend[e] = 0ull; }
+  for (int e = tid; e < KT * 32; e += KT_THREADS) topk[e] = 0ull;
   if (tid < KT) pcnt[tid] = 0;
 
   // loader role: row lr of the tile, channel quads lq, lq+2, lq+4, lq+6 of the chunk
@@ -305,12 +305,11 @@ knn_tile_kernel(const float* __restrict__ x, const float* __restrict__ xx, int N
     for (int rr = 0; rr < 16; rr += KT_IL) {
       const int row0 = warp * 16 + rr;
       if (i0 + row0 >= N) break;
-      unsigned long long r0[KT_IL], r1[KT_IL], tau[KT_IL];
+      unsigned long long r0[KT_IL], tau[KT_IL];  // sorted best keys; the pending ones stay in shared memory
       int cnt[KT_IL];
 #pragma unroll
       for (int u = 0; u < KT_IL; ++u) {
         r0[u] = topk[(row0 + u) * 32 + lane];
-        r1[u] = pend[(row0 + u) * 32 + lane];
         cnt[u] = pcnt[row0 + u];
         tau[u] = __shfl_sync(0xffffffffu, r0[u], k - 1);
       }
@@ -326,41 +325,42 @@ knn_tile_kernel(const float* __restrict__ x, const float* __restrict__ xx, int N
           m[u] = __ballot_sync(0xffffffffu, j < N && key[u] > tau[u]);
           overflow |= cnt[u] + __popc(m[u]) > 32;
         }
-        if (overflow) {  // fold the pending candidates into the sorted top list (both rows: uniform)
+        if (overflow) {  // fold the pending candidates into the sorted top list (all rows: uniform)
+          __syncwarp();
+          unsigned long long r1[KT_IL];
+#pragma unroll
+          for (int u = 0; u < KT_IL; ++u) r1[u] = lane < cnt[u] ? pend[(row0 + u) * 32 + lane] : 0ull;
+#pragma unroll
+          for (int u = 0; u < KT_IL; ++u) knn_sort64(r0[u], r1[u], lane);
 #pragma unroll
           for (int u = 0; u < KT_IL; ++u) {
-            knn_sort64(r0[u], r1[u], lane);
-            r1[u] = 0ull;
             cnt[u] = 0;
             tau[u] = __shfl_sync(0xffffffffu, r0[u], k - 1);
             m[u] = __ballot_sync(0xffffffffu, j < N && key[u] > tau[u]);
           }
+          __syncwarp();
         }
 #pragma unroll
         for (int u = 0; u < KT_IL; ++u) {  // append the passing candidates behind the pending ones
-          const int n_new = __popc(m[u]);
-          const int d = lane - cnt[u];
-          const bool take = d >= 0 && d < n_new;
-          const int src = take ? (int)__fns(m[u], 0, d + 1) : 0;
-          const unsigned long long kk = __shfl_sync(0xffffffffu, key[u], src);
-          if (take) r1[u] = kk;
-          cnt[u] += n_new;
+          if ((m[u] >> lane) & 1u)
+            pend[(row0 + u) * 32 + cnt[u] + __popc(m[u] & ((1u << lane) - 1u))] = key[u];
+          cnt[u] += __popc(m[u]);
         }
       }
 #pragma unroll
       for (int u = 0; u < KT_IL; ++u) {
         topk[(row0 + u) * 32 + lane] = r0[u];
-        pend[(row0 + u) * 32 + lane] = r1[u];
         if (lane == 0) pcnt[row0 + u] = cnt[u];
       }
     }
     // (the next iteration's first __syncthreads orders this selection before S is rewritten)
   }
   // ---- final fold of the pending candidates, then the k best indices, best first ----
+  __syncwarp();  // rows stay with their warp: its own shared-memory writes are all that matter
   for (int rr = 0; rr < 16; ++rr) {
     const int row = warp * 16 + rr;
     if (i0 + row >= N) break;
-    unsigned long long r0 = topk[row * 32 + lane], r1 = pend[row * 32 + lane];
+    unsigned long long r0 = topk[row * 32 + lane], r1 = lane < pcnt[row] ? pend[row * 32 + lane] : 0ull;
     knn_sort64(r0, r1, lane);
     if (lane < k) idx[((long long)part * N + i0 + row) * k + lane] = (int)(~(unsigned)(r0 & 0xffffffffull));
   }
