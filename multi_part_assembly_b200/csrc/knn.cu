@@ -140,30 +140,47 @@ knn_kernel(const float* __restrict__ x, const float* __restrict__ xx, int N, int
 }
 
 // ---- register-tiled variant (k <= 32) ------------------------------------------
-// One CTA = 128 query rows of one part; candidates stream through in blocks of 128.
-// The 128 x 128 score block is an 8 x 8 register tile per thread (64 FMAs per 4
-// 16-byte shared-memory loads: FMA-issue bound instead of LDS bound), accumulated
-// over the channels in ascending order with one accumulator per pair -- the oracle's
-// order, so the scores are bit-identical to knn_kernel's.  The next operand chunk is
-// prefetched into registers while the current one is multiplied.  Each finished block
-// goes through shared memory once; a warp then merges it into its rows' running top-k
-// state: 32 sorted best keys + up to 32 pending candidates per row ((score, index)
-// packed into one ordered 64-bit key).  Candidates that beat the current k-th best are
-// appended with one ballot; when the pending half would overflow, a 64-key bitonic sort
-// (shuffles) folds it into the sorted half.  Nothing of size N x N exists.
-constexpr int KT = 128;        // query rows per CTA = candidates per block
+// A CTA takes 128 query rows of one part at a time (persistent over the work list);
+// candidates stream through in blocks of 128.  The 128 x 128 score block is an 8 x 8
+// register tile per thread (64 FMAs per 4 16-byte shared-memory loads: FMA-issue bound
+// instead of LDS bound), accumulated over the channels in ascending order with one
+// accumulator per pair -- the oracle's order, so the scores are bit-identical to
+// knn_kernel's.  The next operand chunk is prefetched into registers while the current
+// one is multiplied.  Finished score rows go to a per-CTA scratch slab (128 x Np fp32,
+// 512 KB: it lives in the 126 MB L2, never in HBM for long) and are selected from once
+// the row is complete:
+//   each lane takes the maximum of its 32-strided slice; the k-th largest of the 32
+//   lane maxima (one 32-key bitonic sort by shuffles) is a lower bound T0 of the k-th
+//   best score, typically passed by only ~k..2k candidates; those are compacted (ballot-
+//   free: per-lane counts + warp scan) and one 64-key bitonic sort orders them.  Keys are
+//   (score, index) packed into an order-preserving 64-bit integer, so ties resolve to the
+//   lower index exactly as in the oracle.  More than 64 survivors (adversarial layouts)
+//   fall back to k rounds of warp arg-max.
+constexpr int KT = 128;        // query rows per work item = candidates per block
 constexpr int KT_KC = 32;      // channels per chunk
 constexpr int KT_THREADS = 256;
-constexpr int KT_SP = KT + 4;  // score tile pitch (floats)
-constexpr int KT_IL = 4;       // rows a warp merges at a time (independent shuffle chains)
-constexpr int KT_SMEM = sizeof(float) * (2 * KT_KC * KT + KT * KT_SP) + 2 * sizeof(unsigned long long) * KT * 32 +
-                        sizeof(int) * KT;
+constexpr int KT_SMEM = sizeof(float) * (2 * KT_KC * KT) + sizeof(unsigned long long) * 8 * 64;
 
 // (score, index) as one unsigned key: larger = better (higher score, then lower index)
 __device__ __forceinline__ unsigned long long knn_key(float v, int j) {
   const unsigned b = __float_as_uint(v);
   const unsigned o = (b & 0x80000000u) ? ~b : (b | 0x80000000u);  // order-preserving float -> uint
   return ((unsigned long long)o << 32) | (unsigned long long)(~(unsigned)j);
+}
+__device__ __forceinline__ unsigned long long u64max(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
+__device__ __forceinline__ unsigned long long u64min(unsigned long long a, unsigned long long b) { return a > b ? b : a; }
+// bitonic sort of 32 keys (one per lane) into descending order
+__device__ __forceinline__ void knn_sort32(unsigned long long& a, int lane) {
+#pragma unroll
+  for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      const unsigned long long pa = __shfl_xor_sync(0xffffffffu, a, j);
+      const bool lower = (lane & j) == 0;
+      const bool desc = (lane & kk) == 0 || kk == 32;
+      a = (lower == desc) ? u64max(a, pa) : u64min(a, pa);
+    }
+  }
 }
 // bitonic sort of the 64 keys (a of lane l = element l, b = element 32 + l) into descending order
 __device__ __forceinline__ void knn_sort64(unsigned long long& a, unsigned long long& b, int lane) {
@@ -172,7 +189,7 @@ __device__ __forceinline__ void knn_sort64(unsigned long long& a, unsigned long 
 #pragma unroll
     for (int j = kk >> 1; j > 0; j >>= 1) {
       if (j == 32) {  // partner is the other register of the same lane; kk == 64: descending
-        const unsigned long long hi = a > b ? a : b, lo = a > b ? b : a;
+        const unsigned long long hi = u64max(a, b), lo = u64min(a, b);
         a = hi; b = lo;
       } else {
         const unsigned long long pa = __shfl_xor_sync(0xffffffffu, a, j);
@@ -180,189 +197,196 @@ __device__ __forceinline__ void knn_sort64(unsigned long long& a, unsigned long 
         const bool lower = (lane & j) == 0;
         const bool desc_a = (lane & kk) == 0;          // element index = lane
         const bool desc_b = ((32 + lane) & kk) == 0;   // element index = 32 + lane
-        a = (lower == desc_a) ? (a > pa ? a : pa) : (a > pa ? pa : a);
-        b = (lower == desc_b) ? (b > pb ? b : pb) : (b > pb ? pb : b);
+        a = (lower == desc_a) ? u64max(a, pa) : u64min(a, pa);
+        b = (lower == desc_b) ? u64max(b, pb) : u64min(b, pb);
       }
     }
   }
 }
 
 __global__ void __launch_bounds__(KT_THREADS, 1)
-knn_tile_kernel(const float* __restrict__ x, const float* __restrict__ xx, int N, int C, int k,
-                int* __restrict__ idx) {
+knn_tile_kernel(const float* __restrict__ x, const float* __restrict__ xx, int n_parts, int N, int C,
+                int k, float* __restrict__ scratch, int* __restrict__ idx) {
   extern __shared__ float sm[];
   float* As = sm;                       // [KT_KC][KT]  queries, channel-major
   float* Bs = As + KT_KC * KT;          // [KT_KC][KT]  candidates
-  float* S = Bs + KT_KC * KT;           // [KT][KT_SP]  score block
-  unsigned long long* topk = reinterpret_cast<unsigned long long*>(S + KT * KT_SP);  // [KT][32] sorted best
-  unsigned long long* pend = topk + KT * 32;                                         // [KT][32] pending
-  int* pcnt = reinterpret_cast<int*>(pend + KT * 32);                                // [KT]
+  unsigned long long* cbuf = reinterpret_cast<unsigned long long*>(Bs + KT_KC * KT);  // [8 warps][64]
   const int tiles = (N + KT - 1) / KT;
-  const int part = blockIdx.x / tiles, i0 = (blockIdx.x % tiles) * KT;
-  const float* xp = x + (long long)part * N * C;
-  const float* xxp = xx + (long long)part * N;
+  const int Np = tiles * KT;
+  float* S = scratch + (size_t)blockIdx.x * KT * Np;  // this CTA's score slab [KT][Np]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads; rows {4ty+r, 64+4ty+r}, cols {4tx+c, 64+4tx+c}
   const float ninf = -__int_as_float(0x7f800000);
   const int nchunks = (C + KT_KC - 1) / KT_KC;
-  const int nblocks = (N + KT - 1) / KT;
+  const int lr = tid & 127, lq = tid >> 7;  // loader role: tile row, channel quads lq, lq+2, lq+4, lq+6
 
-  for (int e = tid; e < KT * 32; e += KT_THREADS) topk[e] = 0ull;
-  if (tid < KT) pcnt[tid] = 0;
-
-  // loader role: row lr of the tile, channel quads lq, lq+2, lq+4, lq+6 of the chunk
-  const int lr = tid & 127, lq = tid >> 7;
-  float4 pa[4], pb[4];
-  auto fetch = [&](int j0, int kc) {
+  for (int work = blockIdx.x; work < n_parts * tiles; work += gridDim.x) {
+    const int part = work / tiles, i0 = (work % tiles) * KT;
+    const float* xp = x + (long long)part * N * C;
+    const float* xxp = xx + (long long)part * N;
+    float4 pa[4], pb[4];
+    auto fetch = [&](int j0, int kc) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int c = kc + 4 * (lq + 2 * i);
-      const int ra = i0 + lr, rb = j0 + lr;
-      pa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      pb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c + 3 < C) {
-        if ((C & 3) == 0) {
+      for (int i = 0; i < 4; ++i) {
+        const int c = kc + 4 * (lq + 2 * i);
+        const int ra = i0 + lr, rb = j0 + lr;
+        pa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        pb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c + 3 < C && (C & 3) == 0) {
           if (ra < N) pa[i] = *reinterpret_cast<const float4*>(xp + (long long)ra * C + c);
           if (rb < N) pb[i] = *reinterpret_cast<const float4*>(xp + (long long)rb * C + c);
-        } else {
-          if (ra < N) { const float* p = xp + (long long)ra * C + c; pa[i] = make_float4(p[0], p[1], p[2], p[3]); }
-          if (rb < N) { const float* p = xp + (long long)rb * C + c; pb[i] = make_float4(p[0], p[1], p[2], p[3]); }
-        }
-      } else if (c < C) {  // ragged channel tail
-        float ta[4] = {0.f, 0.f, 0.f, 0.f}, tb[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int e = 0; e < 4 && c + e < C; ++e) {
-          if (ra < N) ta[e] = xp[(long long)ra * C + c + e];
-          if (rb < N) tb[e] = xp[(long long)rb * C + c + e];
-        }
-        pa[i] = make_float4(ta[0], ta[1], ta[2], ta[3]);
-        pb[i] = make_float4(tb[0], tb[1], tb[2], tb[3]);
-      }
-    }
-  };
-  auto stash = [&]() {
+        } else if (c < C) {  // unaligned rows / ragged channel tail
+          float ta[4] = {0.f, 0.f, 0.f, 0.f}, tb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int kk = 4 * (lq + 2 * i);
-      As[(kk + 0) * KT + lr] = pa[i].x; As[(kk + 1) * KT + lr] = pa[i].y;
-      As[(kk + 2) * KT + lr] = pa[i].z; As[(kk + 3) * KT + lr] = pa[i].w;
-      Bs[(kk + 0) * KT + lr] = pb[i].x; Bs[(kk + 1) * KT + lr] = pb[i].y;
-      Bs[(kk + 2) * KT + lr] = pb[i].z; Bs[(kk + 3) * KT + lr] = pb[i].w;
-    }
-  };
-
-  fetch(0, 0);
-  for (int jb = 0; jb < nblocks; ++jb) {
-    const int j0 = jb * KT;
-    float acc[8][8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r)
-#pragma unroll
-      for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
-    for (int ch = 0; ch < nchunks; ++ch) {
-      const int kc = ch * KT_KC;
-      __syncthreads();  // previous chunk's multiplies (and the previous block's selection) are done
-      stash();
-      __syncthreads();
-      // prefetch the next chunk (next channel slice, or the first slice of the next block)
-      if (ch + 1 < nchunks) fetch(j0, kc + KT_KC);
-      else if (jb + 1 < nblocks) fetch(j0 + KT, 0);
-      const int klen = min(KT_KC, ((C - kc) + 3) & ~3);
-#pragma unroll 4
-      for (int kk = 0; kk < klen; ++kk) {
-        const float4 a0 = *reinterpret_cast<const float4*>(&As[kk * KT + 4 * ty]);
-        const float4 a1 = *reinterpret_cast<const float4*>(&As[kk * KT + 64 + 4 * ty]);
-        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk * KT + 4 * tx]);
-        const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk * KT + 64 + 4 * tx]);
-        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-        for (int r = 0; r < 8; ++r)
-#pragma unroll
-          for (int c = 0; c < 8; ++c) acc[r][c] = __fmaf_rn(a[r], b[c], acc[r][c]);  // ascending channel
-      }
-    }
-    // ---- scores of this block -> shared memory ----
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const int row = (r < 4 ? 0 : 60) + 4 * ty + r;  // 4ty+r or 64+4ty+(r-4)
-      const float xi = (i0 + row < N) ? xxp[i0 + row] : 0.f;
-      float sv[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const int j = j0 + (c < 4 ? 0 : 60) + 4 * tx + c;
-        float s = ninf;
-        if (j < N) {
-          const float inner = __fmul_rn(-2.0f, acc[r][c]);          // dgcnn.py:10
-          s = __fsub_rn(__fsub_rn(-xxp[j], inner), xi);             // dgcnn.py:12
-        }
-        sv[c] = s;
-      }
-      *reinterpret_cast<float4*>(&S[row * KT_SP + 4 * tx]) = make_float4(sv[0], sv[1], sv[2], sv[3]);
-      *reinterpret_cast<float4*>(&S[row * KT_SP + 64 + 4 * tx]) = make_float4(sv[4], sv[5], sv[6], sv[7]);
-    }
-    __syncthreads();
-    // ---- merge into the rows' top-k state: warp w owns rows 16w .. 16w+15, two at a time ----
-    for (int rr = 0; rr < 16; rr += KT_IL) {
-      const int row0 = warp * 16 + rr;
-      if (i0 + row0 >= N) break;
-      unsigned long long r0[KT_IL], tau[KT_IL];  // sorted best keys; the pending ones stay in shared memory
-      int cnt[KT_IL];
-#pragma unroll
-      for (int u = 0; u < KT_IL; ++u) {
-        r0[u] = topk[(row0 + u) * 32 + lane];
-        cnt[u] = pcnt[row0 + u];
-        tau[u] = __shfl_sync(0xffffffffu, r0[u], k - 1);
-      }
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        const int j = j0 + lane + 32 * c;
-        unsigned long long key[KT_IL];
-        unsigned m[KT_IL];
-        bool overflow = false;
-#pragma unroll
-        for (int u = 0; u < KT_IL; ++u) {
-          key[u] = knn_key(S[(row0 + u) * KT_SP + lane + 32 * c], j);
-          m[u] = __ballot_sync(0xffffffffu, j < N && key[u] > tau[u]);
-          overflow |= cnt[u] + __popc(m[u]) > 32;
-        }
-        if (overflow) {  // fold the pending candidates into the sorted top list (all rows: uniform)
-          __syncwarp();
-          unsigned long long r1[KT_IL];
-#pragma unroll
-          for (int u = 0; u < KT_IL; ++u) r1[u] = lane < cnt[u] ? pend[(row0 + u) * 32 + lane] : 0ull;
-#pragma unroll
-          for (int u = 0; u < KT_IL; ++u) knn_sort64(r0[u], r1[u], lane);
-#pragma unroll
-          for (int u = 0; u < KT_IL; ++u) {
-            cnt[u] = 0;
-            tau[u] = __shfl_sync(0xffffffffu, r0[u], k - 1);
-            m[u] = __ballot_sync(0xffffffffu, j < N && key[u] > tau[u]);
+          for (int e = 0; e < 4; ++e) {
+            if (c + e < C) {
+              if (ra < N) ta[e] = xp[(long long)ra * C + c + e];
+              if (rb < N) tb[e] = xp[(long long)rb * C + c + e];
+            }
           }
-          __syncwarp();
-        }
-#pragma unroll
-        for (int u = 0; u < KT_IL; ++u) {  // append the passing candidates behind the pending ones
-          if ((m[u] >> lane) & 1u)
-            pend[(row0 + u) * 32 + cnt[u] + __popc(m[u] & ((1u << lane) - 1u))] = key[u];
-          cnt[u] += __popc(m[u]);
+          pa[i] = make_float4(ta[0], ta[1], ta[2], ta[3]);
+          pb[i] = make_float4(tb[0], tb[1], tb[2], tb[3]);
         }
       }
+    };
+    auto stash = [&]() {
 #pragma unroll
-      for (int u = 0; u < KT_IL; ++u) {
-        topk[(row0 + u) * 32 + lane] = r0[u];
-        if (lane == 0) pcnt[row0 + u] = cnt[u];
+      for (int i = 0; i < 4; ++i) {
+        const int kk = 4 * (lq + 2 * i);
+        As[(kk + 0) * KT + lr] = pa[i].x; As[(kk + 1) * KT + lr] = pa[i].y;
+        As[(kk + 2) * KT + lr] = pa[i].z; As[(kk + 3) * KT + lr] = pa[i].w;
+        Bs[(kk + 0) * KT + lr] = pb[i].x; Bs[(kk + 1) * KT + lr] = pb[i].y;
+        Bs[(kk + 2) * KT + lr] = pb[i].z; Bs[(kk + 3) * KT + lr] = pb[i].w;
+      }
+    };
+
+    fetch(0, 0);
+    for (int jb = 0; jb < tiles; ++jb) {
+      const int j0 = jb * KT;
+      float acc[8][8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+      for (int ch = 0; ch < nchunks; ++ch) {
+        const int kc = ch * KT_KC;
+        __syncthreads();  // the previous chunk's multiplies are done
+        stash();
+        __syncthreads();
+        // prefetch the next chunk (next channel slice, or the first slice of the next block)
+        if (ch + 1 < nchunks) fetch(j0, kc + KT_KC);
+        else if (jb + 1 < tiles) fetch(j0 + KT, 0);
+        const int klen = min(KT_KC, ((C - kc) + 3) & ~3);
+#pragma unroll 4
+        for (int kk = 0; kk < klen; ++kk) {
+          const float4 a0 = *reinterpret_cast<const float4*>(&As[kk * KT + 4 * ty]);
+          const float4 a1 = *reinterpret_cast<const float4*>(&As[kk * KT + 64 + 4 * ty]);
+          const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk * KT + 4 * tx]);
+          const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk * KT + 64 + 4 * tx]);
+          const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+          const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[r][c] = __fmaf_rn(a[r], b[c], acc[r][c]);  // ascending channel
+        }
+      }
+      // ---- scores of this block -> the CTA's slab (L2) ----
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int row = (r < 4 ? 0 : 60) + 4 * ty + r;  // 4ty+r or 64+4ty+(r-4)
+        const float xi = (i0 + row < N) ? xxp[i0 + row] : 0.f;
+        float sv[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int j = j0 + (c < 4 ? 0 : 60) + 4 * tx + c;
+          float sc = ninf;
+          if (j < N) {
+            const float inner = __fmul_rn(-2.0f, acc[r][c]);          // dgcnn.py:10
+            sc = __fsub_rn(__fsub_rn(-xxp[j], inner), xi);            // dgcnn.py:12
+          }
+          sv[c] = sc;
+        }
+        float* dst = S + (size_t)row * Np + j0;
+        *reinterpret_cast<float4*>(dst + 4 * tx) = make_float4(sv[0], sv[1], sv[2], sv[3]);
+        *reinterpret_cast<float4*>(dst + 64 + 4 * tx) = make_float4(sv[4], sv[5], sv[6], sv[7]);
       }
     }
-    // (the next iteration's first __syncthreads orders this selection before S is rewritten)
-  }
-  // ---- final fold of the pending candidates, then the k best indices, best first ----
-  __syncwarp();  // rows stay with their warp: its own shared-memory writes are all that matter
-  for (int rr = 0; rr < 16; ++rr) {
-    const int row = warp * 16 + rr;
-    if (i0 + row >= N) break;
-    unsigned long long r0 = topk[row * 32 + lane], r1 = lane < pcnt[row] ? pend[row * 32 + lane] : 0ull;
-    knn_sort64(r0, r1, lane);
-    if (lane < k) idx[((long long)part * N + i0 + row) * k + lane] = (int)(~(unsigned)(r0 & 0xffffffffull));
+    __syncthreads();  // all score rows of this work item are written (same CTA: visible after the barrier)
+
+    // ---- top-k per row: warp w owns rows 16w .. 16w+15 ----
+    unsigned long long* wb = cbuf + warp * 64;
+    for (int rr = 0; rr < 16; ++rr) {
+      const int row = warp * 16 + rr;
+      if (i0 + row >= N) break;
+      const float* Sr = S + (size_t)row * Np;
+      float v[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const int j = lane + 32 * c;
+        v[c] = j < Np ? __ldcg(Sr + j) : ninf;  // columns >= N hold -inf already
+      }
+      // lane maximum of the strided slice (first maximum = lowest index)
+      float mv = v[0];
+      int mc = 0;
+#pragma unroll
+      for (int c = 1; c < 32; ++c)
+        if (v[c] > mv) { mv = v[c]; mc = c; }
+      unsigned long long t = (lane + 32 * mc < N) ? knn_key(mv, lane + 32 * mc) : 0ull;
+      knn_sort32(t, lane);
+      const unsigned long long T0 = __shfl_sync(0xffffffffu, t, k - 1);  // <= the k-th best key
+      int cnt = 0;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const int j = lane + 32 * c;
+        cnt += (j < N && knn_key(v[c], j) >= T0) ? 1 : 0;
+      }
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      int* out = idx + ((long long)part * N + i0 + row) * k;
+      if (total <= 64) {
+        int off = incl - cnt;
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const int j = lane + 32 * c;
+          const unsigned long long key = knn_key(v[c], j);
+          if (j < N && key >= T0) wb[off++] = key;
+        }
+        __syncwarp();
+        unsigned long long r0 = lane < total ? wb[lane] : 0ull;
+        unsigned long long r1 = lane + 32 < total ? wb[lane + 32] : 0ull;
+        knn_sort64(r0, r1, lane);
+        if (lane < k) out[lane] = (int)(~(unsigned)(r0 & 0xffffffffull));
+      } else {
+        // fallback: k rounds of warp arg-max over the lanes' slices
+        for (int s_ = 0; s_ < k; ++s_) {
+          unsigned long long best = 0ull;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const int j = lane + 32 * c;
+            const unsigned long long key = j < N ? knn_key(v[c], j) : 0ull;
+            best = u64max(best, key);
+          }
+          unsigned long long wbest = best;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) wbest = u64max(wbest, __shfl_xor_sync(0xffffffffu, wbest, o));
+          const int j = (int)(~(unsigned)(wbest & 0xffffffffull));
+          if (lane == 0) out[s_] = j;
+          if ((j & 31) == lane) {  // owner removes it
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (c == (j >> 5)) v[c] = ninf;
+          }
+        }
+      }
+    }
+    __syncthreads();  // selection done before the next work item overwrites the slab
   }
 }
 
@@ -440,7 +464,22 @@ using namespace mpa;
 
 extern "C" {
 
-size_t mpa_knn_workspace_bytes(int n, int N) { return align_up(sizeof(float) * (size_t)n * N, 256); }
+static int knn_tile_ctas() {  // one persistent CTA (and one 128 x Np score slab) per SM
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+size_t mpa_knn_workspace_bytes(int n, int N) {
+  const size_t Np = (size_t)((N + KT - 1) / KT) * KT;
+  return align_up(sizeof(float) * (size_t)n * N, 256) +       // squared norms
+         sizeof(float) * (size_t)knn_tile_ctas() * KT * Np;   // per-CTA score slabs (L2-resident)
+}
 
 int mpa_knn(const float* x, int n, int N, int C, int k, int32_t* idx, void* ws, size_t ws_bytes,
             void* stream_) {
@@ -460,15 +499,19 @@ int mpa_knn(const float* x, int n, int N, int C, int k, int32_t* idx, void* ws, 
   }
   MPA_LAUNCH_CHECK();
   static const int legacy = getenv("MPA_KNN_LEGACY") ? atoi(getenv("MPA_KNN_LEGACY")) : 0;
-  if (k <= 32 && !legacy) {
+  if (k <= 32 && N <= 1024 && !legacy) {
     static bool attr_t = false;
     if (!attr_t) {
       MPA_CUDA(cudaFuncSetAttribute(knn_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KT_SMEM));
       attr_t = true;
     }
+    const int tiles = (N + KT - 1) / KT;
+    int ctas = knn_tile_ctas();
+    if (ctas > n * tiles) ctas = n * tiles;
+    float* slab = (float*)((char*)scratch.base + align_up(sizeof(float) * (size_t)n * N, 256));
     {
       ProfScope ps("knn", stream);
-      knn_tile_kernel<<<n * ((N + KT - 1) / KT), KT_THREADS, KT_SMEM, stream>>>(x, xx, N, C, k, idx);
+      knn_tile_kernel<<<ctas, KT_THREADS, KT_SMEM, stream>>>(x, xx, n, N, C, k, slab, idx);
     }
     MPA_LAUNCH_CHECK();
     return MPA_OK;
