@@ -263,13 +263,11 @@ knn_tile_kernel(const float* __restrict__ x, const float* __restrict__ xx, int n
     fetch(0, 0);
     for (int jb = 0; jb < tiles; ++jb) {
       const int j0 = jb * KT;
-      // accumulators as packed pairs (columns 2c, 2c+1): one FFMA2 per pair and channel; each
-      // half is an IEEE fma, so the values equal the scalar sequential-channel recurrence
-      unsigned long long acc2[8][4];
+      float acc[8][8];
 #pragma unroll
       for (int r = 0; r < 8; ++r)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc2[r][c] = 0ull;
+        for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
       for (int ch = 0; ch < nchunks; ++ch) {
         const int kc = ch * KT_KC;
         __syncthreads();  // the previous chunk's multiplies are done
@@ -286,14 +284,11 @@ knn_tile_kernel(const float* __restrict__ x, const float* __restrict__ xx, int n
           const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk * KT + 4 * tx]);
           const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk * KT + 64 + 4 * tx]);
           const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-          const unsigned long long b2[4] = {f2_as_u64(make_float2(b0.x, b0.y)), f2_as_u64(make_float2(b0.z, b0.w)),
-                                            f2_as_u64(make_float2(b1.x, b1.y)), f2_as_u64(make_float2(b1.z, b1.w))};
+          const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            const unsigned long long a2 = f2_as_u64(make_float2(a[r], a[r]));
+          for (int r = 0; r < 8; ++r)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) acc2[r][c] = fma2(a2, b2[c], acc2[r][c]);  // ascending channel
-          }
+            for (int c = 0; c < 8; ++c) acc[r][c] = __fmaf_rn(a[r], b[c], acc[r][c]);  // ascending channel
         }
       }
       // ---- scores of this block -> the CTA's slab (L2) ----
@@ -305,11 +300,9 @@ knn_tile_kernel(const float* __restrict__ x, const float* __restrict__ xx, int n
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const int j = j0 + (c < 4 ? 0 : 60) + 4 * tx + c;
-          const float2 pr = u64_as_f2(acc2[r][c >> 1]);
-          const float accv = (c & 1) ? pr.y : pr.x;
           float sc = ninf;
           if (j < N) {
-            const float inner = __fmul_rn(-2.0f, accv);               // dgcnn.py:10
+            const float inner = __fmul_rn(-2.0f, acc[r][c]);          // dgcnn.py:10
             sc = __fsub_rn(__fsub_rn(-xxp[j], inner), xi);            // dgcnn.py:12
           }
           sv[c] = sc;
