@@ -294,9 +294,14 @@ def run_native(args):
     if train is not None and 'error' not in train:
         train['ms_per_step'] = ms_train / train['steps']
         train['shapes_per_s'] = B_PER_GPU * world * train['steps'] / (ms_train / 1e3)
+    if world > 1:
+        # last collective done.  The captured graphs hold NCCL resources and tearing the
+        # process group down around them can block: ranks leave without the teardown.
+        torch.cuda.synchronize()
+        if rank != 0:
+            sys.stdout.flush()
+            os._exit(0)
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
 
     shapes = B_PER_GPU * world * args.steps
@@ -357,7 +362,8 @@ def run_native(args):
     }
     print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def main():
