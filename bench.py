@@ -153,6 +153,7 @@ def run_native(args):
     dev = torch.device('cuda', local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')  # stdout carries the one JSON line only
         dist.init_process_group('nccl', device_id=dev)
 
     torch.manual_seed(rank)
