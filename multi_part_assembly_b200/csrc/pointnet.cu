@@ -89,11 +89,6 @@ __global__ void __launch_bounds__(PN_THREADS, 1) pointnet_phase_kernel(PointNetA
   __shared__ float fred[PN_GROUPS][PN_MAXC][2];
   __shared__ double s_count;
   __shared__ float s_prev[2][128];
-  // UMMA operand descriptors in issue order: tile-invariant, so they are built once --
-  // building them per MMA cost the single issuing thread ~180 cycles per instruction
-  // while the other 127 threads of the pipeline waited (6 of 11.5 k cycles per tile)
-  __shared__ uint64_t s_wdesc[32];              // weights: layer 1 (1), 2-4 (4 each), 5 ([mblock][8])
-  __shared__ uint64_t s_bdesc[PN_GROUPS][8];    // this pipeline's activation tile, per 16-channel K step
 
   const long long t_entry = clock64();
   const int tid = threadIdx.x;
@@ -124,24 +119,6 @@ __global__ void __launch_bounds__(PN_THREADS, 1) pointnet_phase_kernel(PointNetA
           : "memory");
   }
   if (tid < 32) tc::tmem_alloc<512>(&tmem_base_s);
-  if (t == 0) {
-#pragma unroll
-    for (int k16 = 0; k16 < 8; ++k16)
-      s_bdesc[g][k16] = tc::make_desc_sw128_mn(tc::smem_u32(act) + k16 * 16 * 128, 128 * 128);
-  }
-  if (tid == 32) {
-    int n = 0;
-    for (int layer = 1; layer <= 5; ++layer) {
-      const int K = layer == 1 ? 16 : (layer == 5 ? 128 : 64);
-      const int mblocks = layer == 5 ? 2 : 1;
-      for (int mb = 0; mb < mblocks; ++mb)
-        for (int k = 0; k < K; k += 16) {
-          const int kb = k >> 6, ks = k & 63;
-          s_wdesc[n++] = tc::make_desc_sw128(tc::smem_u32(wsm) + pn_w_off(layer - 1) +
-                                             (layer == 5 ? (mb * 2 + kb) * PN_WTILE : 0) + ks * 2);
-        }
-    }
-  }
 
   // ---- fused BatchNorm finalize of the previous layer (training) ----
   float sc_prev = 0.f, sh_prev = 0.f;
@@ -257,13 +234,14 @@ __global__ void __launch_bounds__(PN_THREADS, 1) pointnet_phase_kernel(PointNetA
       // ---- MMA issue (one thread) ----
       if (t == 0) {
         tc::fence_after_sync();
-        const int dbase = layer == 1 ? 0 : (layer == 5 ? 13 : 1 + 4 * (layer - 2));
         for (int mb = 0; mb < mblocks; ++mb) {
-#pragma unroll
-          for (int k16 = 0; k16 < 8; ++k16) {  // 16 channel rows of the activation tile per K step
-            if (k16 * 16 < K)
-              tc::mma_bf16(tmem + (uint32_t)(mb * PN_TILE), s_wdesc[dbase + mb * 8 + k16], s_bdesc[g][k16],
-                           IDESC, k16 > 0 ? 1u : 0u);
+          for (int k = 0; k < K; k += 16) {
+            const int kb = k >> 6, ks = k & 63;
+            const uint32_t wa = tc::smem_u32(wsm) + pn_w_off(layer - 1) +
+                                (layer == 5 ? (mb * 2 + kb) * PN_WTILE : 0) + ks * 2;
+            const uint32_t ba = tc::smem_u32(act) + k * 128;  // 16 channel rows per K step
+            tc::mma_bf16(tmem + (uint32_t)(mb * PN_TILE), tc::make_desc_sw128(wa),
+                         tc::make_desc_sw128_mn(ba, 128 * 128), IDESC, k > 0 ? 1u : 0u);
           }
         }
         tc::mma_commit(&mbar[g]);
