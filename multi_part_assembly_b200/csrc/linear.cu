@@ -580,7 +580,10 @@ int mpa_linear_forward(const float* x, const float* w, const float* bias, const 
     CvtBatch cb;
     cb.src[0] = x; cb.dst[0] = xb; cb.n[0] = (long long)M * K;
     cb.src[1] = w; cb.dst[1] = wb; cb.n[1] = (long long)N * K;
-    f32_to_bf16_batch_kernel<<<dim3(64, 2), 256, 0, stream>>>(cb);
+    // enough CTAs to stream a [512 k, 512] activation matrix (DGCNN) at HBM speed
+    const long long quads = ((long long)M * K + 1023) / 1024;
+    const int gx = (int)(quads < 64 ? 64 : (quads > 148 * 8 ? 148 * 8 : quads));
+    f32_to_bf16_batch_kernel<<<dim3(gx, 2), 256, 0, stream>>>(cb);
   }
   MPA_LAUNCH_CHECK();
   LinearEpilogue ep{bias, residual, out, nullptr, act};

@@ -78,3 +78,17 @@ def test_dgcnn_bf16_mode(cuda):
     finally:
         kernels.set_precision('auto')
     assert np.isfinite(out).all()
+
+
+def test_knn_clustered_in_few_lanes(cuda):
+    """Neighbours that all sit at indices j % 32 in {0,1,2}: the lane-maximum threshold of
+    the tiled kernel then lets more than 64 candidates through and the slow exact path
+    (warp arg-max rounds) must take over.  Still bit-exact."""
+    from multi_part_assembly_b200 import kernels
+    j = np.arange(1024)
+    near = (j % 32) < 3
+    x = np.where(near, j * 1e-3, 1000.0 + j).astype(np.float32).reshape(1, 1024, 1)
+    x = np.concatenate([x, x[:, ::-1]], 0)  # second part: same values, reversed order
+    got = kernels.knn(torch.from_numpy(np.ascontiguousarray(x)).to(cuda), 20).cpu().numpy().astype(np.int64)
+    want = oracle.knn(np.ascontiguousarray(x.transpose(0, 2, 1)), 20)
+    np.testing.assert_array_equal(np.sort(got, -1), want)
