@@ -11,7 +11,8 @@ from multi_part_assembly_b200 import profiler
 dev = torch.device('cuda:0')
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-cfg = get_cfg('dgl', 'everyday', encoder='dgcnn')
+enc = sys.argv[3] if len(sys.argv) > 3 else 'dgcnn'
+cfg = get_cfg('dgl', 'everyday', encoder=enc)
 model = build_model(cfg).to(dev).train()
 model.trainer = Trainer()
 batch = make_batch(B, P=20, N=1000, num_valid=16, seed=0, device=dev)
