@@ -93,7 +93,7 @@ class DGLModel(BaseModel):
         part_label = data_dict['part_label'].type_as(part_feats)
         instance_label = data_dict['instance_label'].type_as(part_feats)
         B, P = instance_label.shape[:2]
-        pred_pose = self.zero_pose.repeat(B, P, 1).type_as(part_feats).detach()
+        pred_pose = self._zero_pose_like(part_feats, B, P)
         class_list = self._gather_same_class(data_dict)
 
         all_rot, all_trans = [], []

@@ -47,7 +47,8 @@ class BaseModel(LightningModule):
         zero_pose = torch.zeros(1, 1, self.pose_dim)
         for i in ones:
             zero_pose[..., i] = 1.
-        self.zero_pose = zero_pose
+        self.zero_pose = zero_pose  # plain attribute like the reference (not in the state dict)
+        self._zero_pose_cache = {}
 
         self.semantic = (self.cfg.data.dataset != 'geometry')
         self.max_num_part = self.cfg.data.max_num_part
@@ -59,6 +60,16 @@ class BaseModel(LightningModule):
     def forward(self, data_dict):
         """Predict poses for each part (implemented by the subclasses)."""
         raise NotImplementedError
+
+    def _zero_pose_like(self, ref, B, P):
+        """[B, P, pose_dim] identity poses on ref's device/dtype.  The reference moves the
+        host constant with `.type_as` on every forward (a pageable host-to-device copy, which
+        also cannot be captured into a CUDA graph); here the device copy is made once."""
+        key = (ref.device, ref.dtype)
+        z = self._zero_pose_cache.get(key)
+        if z is None:
+            z = self._zero_pose_cache[key] = self.zero_pose.to(device=ref.device, dtype=ref.dtype)
+        return z.repeat(B, P, 1).detach()
 
     def training_step(self, data_dict, batch_idx, optimizer_idx=-1):
         return self.forward_pass(data_dict, mode='train', optimizer_idx=optimizer_idx)['loss']

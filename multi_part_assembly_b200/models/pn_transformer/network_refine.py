@@ -57,7 +57,7 @@ class PNTransformerRefine(PNTransformer):
         part_label = data_dict['part_label'].type_as(pc_feats)
         inst_label = data_dict['instance_label'].type_as(pc_feats)
         B, P, _ = inst_label.shape
-        pose = self.zero_pose.repeat(B, P, 1).type_as(part_feats).detach()
+        pose = self._zero_pose_like(part_feats, B, P)
         valid_mask = part_valids == 1
         pred_rot, pred_trans = [], []
         for i in range(self.refine_steps):
