@@ -18,6 +18,9 @@ Keys beyond the base contract:
   cpu_baseline the CPU oracle (port of the reference path) on the host cores
   e2e          same metric through BaseModel.forward_pass with the batch in
                pinned HOST memory: H2D of the batch + D2H of the loss per step
+  train_step   secondary figure: forward + loss + backward + gradient
+               all-reduce over the ranks + Adam as one CUDA graph (runtime.GraphedTrainStep),
+               same batch, timed like the headline; `--no-train` skips it
 `--impl reference` times the CPU restatement of the reference path (the
 reference has no CPU Chamfer of its own: chamfer.py:18 asserts CUDA) with all
 host threads on a bounded sample per step.
@@ -335,6 +338,9 @@ def run_native(args):
                 'avg_launch_ms': avg_ms, 'share_of_step': d['ms_total'] / sum(
                     v['ms_total'] for v in prof.values()),
                 'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback 6650 GB/s',
+                'note': 'the search is paced by lane divergence and L2/L1 load latency, not by HBM '
+                        '(DESIGN.md 4a); HBM-bound kernels of the path: the BatchNorm passes of the '
+                        'PointNet backward (35-60 % of peak, DESIGN.md 4)',
                 'kernels_ms_per_step': {k: v['ms_total'] / min(args.steps, 10) for k, v in prof.items()}}
 
     threads = os.cpu_count() or 1
