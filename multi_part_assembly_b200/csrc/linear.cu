@@ -475,8 +475,8 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
 // One warp per (shape, head): K (row-padded) and V staged in shared memory;
 // per query the 32 lanes first hold one key score each (softmax by shuffles),
 // then one (or two) output channels each.  P <= 32, hd <= 64.
-constexpr int ATT_WARPS = 4;
-__global__ void __launch_bounds__(ATT_WARPS * 32)
+constexpr int ATT_MAX_WARPS = 32;  // one warp per query row (P <= 32): the rows run concurrently
+__global__ void __launch_bounds__(ATT_MAX_WARPS * 32, 1)
 attention_kernel(const float* __restrict__ qkv, const unsigned char* __restrict__ valid, int B, int P,
                  int H, int hd, __nv_bfloat16* __restrict__ out) {
   extern __shared__ float sm[];
@@ -487,7 +487,7 @@ attention_kernel(const float* __restrict__ qkv, const unsigned char* __restrict_
   float* ks = qs + P * hd;
   float* vs = ks + P * ldk;
   const int b = gw / H, h = gw % H, D = H * hd;
-  for (int i = threadIdx.x; i < P * hd; i += ATT_WARPS * 32) {
+  for (int i = threadIdx.x; i < P * hd; i += blockDim.x) {
     const int p = i / hd, c = i % hd;
     const float* base = qkv + (long long)(b * P + p) * 3 * D + h * hd + c;
     qs[i] = base[0];
@@ -497,7 +497,7 @@ attention_kernel(const float* __restrict__ qkv, const unsigned char* __restrict_
   __syncthreads();
   const bool key_ok = lane < P && (valid == nullptr || valid[b * P + lane] != 0);
   const float scale = rsqrtf((float)hd);
-  for (int i = w; i < P; i += ATT_WARPS) {
+  for (int i = w; i < P; i += (int)(blockDim.x >> 5)) {
     float s = -3.0e38f;
     if (key_ok) {
       float d0 = 0.f, d1 = 0.f;
@@ -670,7 +670,7 @@ int mpa_transformer_forward(const float* tokens, const unsigned char* valid, int
     rc = launch_linear(xn, wl, T, 3 * D, D, e_qkv, "linear_qkv", stream);
     if (rc != MPA_OK) return rc;
     { ProfScope ps("attention", stream);
-      attention_kernel<<<B * H, ATT_WARPS * 32, att_smem, stream>>>(
+      attention_kernel<<<B * H, 32 * (P < ATT_MAX_WARPS ? P : ATT_MAX_WARPS), att_smem, stream>>>(
           qkv, valid, B, P, H, hd, att); }
     MPA_LAUNCH_CHECK();
     // x <- x + out_proj(att)  [+ xn <- LayerNorm2(x)]
