@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, 'csrc', 'libmpa_b200.so')
+_SO = os.environ.get('MPA_B200_LIB') or os.path.join(_HERE, 'csrc', 'libmpa_b200.so')  # override: kernel experiments
 _LIB = None
 
 c_void_p = ctypes.c_void_p

@@ -594,8 +594,11 @@ __device__ __forceinline__ void nn_finish(const NNQuery& c, float best, int bidx
 // Round 1: every lane runs A-D for its own query.  Queries that need phase E are
 // queued in shared memory and re-dealt to the first lanes of the CTA in round 2, so
 // the (long, divergent) block search runs in full warps instead of a few lanes each.
+#ifndef MPA_NN_MIN_CTAS
+#define MPA_NN_MIN_CTAS 4
+#endif
 template <typename IdxT>
-__global__ void __launch_bounds__(NN_THREADS)
+__global__ void __launch_bounds__(NN_THREADS, MPA_NN_MIN_CTAS)
 grid_nn_kernel(const float4* __restrict__ sorted0, const float4* __restrict__ sorted1,
                const int* __restrict__ cell_start, int cs_stride,
                const GridParams* __restrict__ params, const float4* __restrict__ far,
