@@ -88,7 +88,7 @@ def run_reference(args):
         'e2e': {'value': value, 'unit': 'shapes/s', 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
     }
-    print(json.dumps(line))
+    args.emit(line)
 
 
 # --------------------------------------------------------------------------
@@ -367,7 +367,7 @@ def run_native(args):
                          'kind': 'port',
                          'sample': f'1 step of {cpu_B} shapes (same P, N), oracle/ C+torch port'},
     }
-    print(json.dumps(line))
+    args.emit(line)
     if world > 1:
         sys.stdout.flush()
         os._exit(0)
@@ -384,6 +384,20 @@ def main():
     ap.add_argument('--no-train', action='store_true', help='skip the secondary training-step figure')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'native' else args.warmup
+    # stdout carries exactly one JSON line: while the benchmark runs, file descriptor 1 points
+    # at stderr, so that banners printed by libraries (NCCL prints its version to stdout on
+    # some boxes) cannot get in front of it; `emit` restores it for the final line.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        sys.stdout.write(json.dumps(line) + '\n')
+        sys.stdout.flush()
+
+    args.emit = emit
     if args.impl == 'reference':
         run_reference(args)
     else:
