@@ -435,12 +435,6 @@ int launch_linear(const __nv_bfloat16* x, const __nv_bfloat16* w, int M, int N, 
 }
 
 // ---- small token-level kernels ---------------------------------------------
-__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x)
-    out[i] = __float2bfloat16_rn(in[i]);
-}
-
 // LayerNorm over the last dim (D <= 1024, multiple of 32): one warp per row,
 // fp32 statistics (two-pass in registers), output bf16 (GEMM operand) and/or fp32.
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,

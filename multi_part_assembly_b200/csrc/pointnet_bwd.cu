@@ -99,20 +99,23 @@ __device__ __forceinline__ void cta_column_reduce(float (&acc)[NACC][8], int C, 
 }
 
 // sums[0][c] = sum_m z[m,c], sums[1][c] = sum_m z[m,c]^2 over the valid rows
-__global__ void __launch_bounds__(PB_THREADS)
+__global__ void __launch_bounds__(PB_THREADS, 4)
 bn_stats_kernel(const __nv_bfloat16* __restrict__ z, long long M, int C, int N,
                 const float* __restrict__ valids, double* __restrict__ sums) {
   const int tpr = C >> 3, col = threadIdx.x % tpr, rows_per_iter = PB_THREADS / tpr;
   float acc[2][8] = {};
   const long long stride = (long long)gridDim.x * rows_per_iter;
-  for (long long m0 = (long long)blockIdx.x * rows_per_iter + threadIdx.x / tpr; m0 < M; m0 += PB_UNROLL * stride) {
+  const long long rstride = stride * C;
+  long long base = ((long long)blockIdx.x * rows_per_iter + threadIdx.x / tpr) * C + col * 8;
+  for (long long m0 = (long long)blockIdx.x * rows_per_iter + threadIdx.x / tpr; m0 < M;
+       m0 += PB_UNROLL * stride, base += PB_UNROLL * rstride) {
     uint4 raw[PB_UNROLL];
     bool ok[PB_UNROLL];
 #pragma unroll
     for (int u = 0; u < PB_UNROLL; ++u) {  // all loads first: PB_UNROLL packets in flight per thread
       const long long m = m0 + u * stride;
       ok[u] = m < M && (valids == nullptr || valids[m / N] != 0.f);
-      raw[u] = ok[u] ? ld_packet(z + m * C + col * 8) : make_uint4(0u, 0u, 0u, 0u);
+      raw[u] = ok[u] ? ld_packet(z + (base + u * rstride)) : make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
     for (int u = 0; u < PB_UNROLL; ++u) {
@@ -152,7 +155,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int C, int n
 }
 
 // a = relu?(z * scale + shift), bf16 (rows of padded parts are written as zeros)
-__global__ void __launch_bounds__(PB_THREADS)
+__global__ void __launch_bounds__(PB_THREADS, 4)
 bn_act_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ scale,
               const float* __restrict__ shift, int relu, long long M, int C, int N,
               const float* __restrict__ valids, __nv_bfloat16* __restrict__ a) {
@@ -161,14 +164,17 @@ bn_act_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ sca
 #pragma unroll
   for (int i = 0; i < 8; ++i) { sc[i] = scale[col * 8 + i]; sh[i] = shift[col * 8 + i]; }
   const long long stride = (long long)gridDim.x * rows_per_iter;
-  for (long long m0 = (long long)blockIdx.x * rows_per_iter + threadIdx.x / tpr; m0 < M; m0 += PB_UNROLL * stride) {
+  const long long rstride = stride * C;
+  long long base = ((long long)blockIdx.x * rows_per_iter + threadIdx.x / tpr) * C + col * 8;
+  for (long long m0 = (long long)blockIdx.x * rows_per_iter + threadIdx.x / tpr; m0 < M;
+       m0 += PB_UNROLL * stride, base += PB_UNROLL * rstride) {
     uint4 raw[PB_UNROLL];
     bool ok[PB_UNROLL];
 #pragma unroll
     for (int u = 0; u < PB_UNROLL; ++u) {
       const long long m = m0 + u * stride;
       ok[u] = m < M && (valids == nullptr || valids[m / N] != 0.f);
-      raw[u] = ok[u] ? ld_packet(z + m * C + col * 8) : make_uint4(0u, 0u, 0u, 0u);
+      raw[u] = ok[u] ? ld_packet(z + (base + u * rstride)) : make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
     for (int u = 0; u < PB_UNROLL; ++u) {
@@ -181,7 +187,7 @@ bn_act_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ sca
         if (relu) y = fmaxf(y, 0.f);
         v.v[i] = ok[u] ? y : 0.f;
       }
-      store_bf8(a + m * C + col * 8, v);
+      store_bf8(a + (base + u * rstride), v);
     }
   }
 }
@@ -233,16 +239,18 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ da, const float* __restri
   }
   float acc[2][8] = {};
   const long long stride = (long long)gridDim.x * rows_per_iter;
+  const long long rstride = stride * C;
+  long long base = ((long long)blockIdx.x * rows_per_iter + threadIdx.x / tpr) * C + col * 8;
   for (long long m0 = (long long)blockIdx.x * rows_per_iter + threadIdx.x / tpr; m0 < M;
-       m0 += PB_BWD_UNROLL * stride) {
+       m0 += PB_BWD_UNROLL * stride, base += PB_BWD_UNROLL * rstride) {
     uint4 zr[PB_BWD_UNROLL], dr[PB_BWD_UNROLL];
     bool ok[PB_BWD_UNROLL];
 #pragma unroll
     for (int u = 0; u < PB_BWD_UNROLL; ++u) {
       const long long m = m0 + u * stride;
       ok[u] = m < M && (valids == nullptr || valids[m / N] != 0.f);
-      zr[u] = ok[u] ? ld_packet(z + m * C + col * 8) : make_uint4(0u, 0u, 0u, 0u);
-      dr[u] = (ok[u] && da != nullptr) ? ld_packet(da + m * C + col * 8) : make_uint4(0u, 0u, 0u, 0u);
+      zr[u] = ok[u] ? ld_packet(z + (base + u * rstride)) : make_uint4(0u, 0u, 0u, 0u);
+      dr[u] = (ok[u] && da != nullptr) ? ld_packet(da + (base + u * rstride)) : make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
     for (int u = 0; u < PB_BWD_UNROLL; ++u) {
@@ -287,16 +295,18 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ da, const float* __restric
     kb[i] = -sc[i] * ((float)sums[c] * inv_n) - kd[i] * mu;
   }
   const long long stride = (long long)gridDim.x * rows_per_iter;
+  const long long rstride = stride * C;
+  long long base = ((long long)blockIdx.x * rows_per_iter + threadIdx.x / tpr) * C + col * 8;
   for (long long m0 = (long long)blockIdx.x * rows_per_iter + threadIdx.x / tpr; m0 < M;
-       m0 += PB_BWD_UNROLL * stride) {
+       m0 += PB_BWD_UNROLL * stride, base += PB_BWD_UNROLL * rstride) {
     uint4 zr[PB_BWD_UNROLL], dr[PB_BWD_UNROLL];
     bool ok[PB_BWD_UNROLL];
 #pragma unroll
     for (int u = 0; u < PB_BWD_UNROLL; ++u) {
       const long long m = m0 + u * stride;
       ok[u] = m < M && (valids == nullptr || valids[m / N] != 0.f);
-      zr[u] = ok[u] ? ld_packet(z + m * C + col * 8) : make_uint4(0u, 0u, 0u, 0u);
-      dr[u] = (ok[u] && da != nullptr) ? ld_packet(da + m * C + col * 8) : make_uint4(0u, 0u, 0u, 0u);
+      zr[u] = ok[u] ? ld_packet(z + (base + u * rstride)) : make_uint4(0u, 0u, 0u, 0u);
+      dr[u] = (ok[u] && da != nullptr) ? ld_packet(da + (base + u * rstride)) : make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
     for (int u = 0; u < PB_BWD_UNROLL; ++u) {
@@ -312,7 +322,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ da, const float* __restric
 #pragma unroll
         for (int i = 0; i < 8; ++i) out.v[i] = fmaf(sc[i], dy.v[i], fmaf(kd[i], zv.v[i], kb[i]));
       }
-      store_bf8(dz + m * C + col * 8, out);
+      store_bf8(dz + (base + u * rstride), out);
     }
   }
 }
@@ -360,10 +370,10 @@ pool_argmax_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict_
   }
 }
 
-static int pb_grid(long long M, int C) {
+static int pb_grid(long long M, int C, int ctas_per_sm) {
   const int rows_per_iter = PB_THREADS / (C >> 3);
   long long blocks = (M + rows_per_iter - 1) / rows_per_iter;
-  const long long cap = 148LL * 3;  // one wave at 3 CTAs per SM; bounds the fp64 atomics per channel
+  const long long cap = 148LL * ctas_per_sm;  // one resident wave; bounds the fp64 atomics per channel
   return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
 }
 
@@ -386,7 +396,7 @@ int mpa_bn_stats(const void* z, long long M, int C, int N, const float* valids, 
   if (M == 0) return MPA_OK;
   {
     ProfScope ps("bn_stats", stream);
-    bn_stats_kernel<<<pb_grid(M, C), PB_THREADS, 0, stream>>>((const __nv_bfloat16*)z, M, C, N, valids, sums);
+    bn_stats_kernel<<<pb_grid(M, C, 4), PB_THREADS, 0, stream>>>((const __nv_bfloat16*)z, M, C, N, valids, sums);
   }
   MPA_LAUNCH_CHECK();
   return MPA_OK;
@@ -415,7 +425,7 @@ int mpa_bn_act(const void* z, const float* scale, const float* shift, int relu, 
   MPA_CHECK_ARG(z && scale && shift && a, "bn_act: null pointer");
   {
     ProfScope ps("bn_act", stream);
-    bn_act_kernel<<<pb_grid(M, C), PB_THREADS, 0, stream>>>((const __nv_bfloat16*)z, scale, shift, relu, M, C,
+    bn_act_kernel<<<pb_grid(M, C, 4), PB_THREADS, 0, stream>>>((const __nv_bfloat16*)z, scale, shift, relu, M, C,
                                                            N, valids, (__nv_bfloat16*)a);
   }
   MPA_LAUNCH_CHECK();
@@ -437,7 +447,7 @@ int mpa_bn_backward(const void* da, const float* g, const int32_t* arg, const vo
   const BnConst bn{mean, rstd, gamma, beta};
   {
     ProfScope ps("bn_bwd_reduce", stream);
-    bn_bwd_reduce_kernel<<<pb_grid(M, C), PB_THREADS, 0, stream>>>(
+    bn_bwd_reduce_kernel<<<pb_grid(M, C, 3), PB_THREADS, 0, stream>>>(
         (const __nv_bfloat16*)da, g, arg, (const __nv_bfloat16*)z, bn, M, C, N, valids, sums);
   }
   MPA_LAUNCH_CHECK();
@@ -445,7 +455,7 @@ int mpa_bn_backward(const void* da, const float* g, const int32_t* arg, const vo
   MPA_LAUNCH_CHECK();
   {
     ProfScope ps("bn_bwd_apply", stream);
-    bn_bwd_apply_kernel<<<pb_grid(M, C), PB_THREADS, 0, stream>>>(
+    bn_bwd_apply_kernel<<<pb_grid(M, C, 3), PB_THREADS, 0, stream>>>(
         (const __nv_bfloat16*)da, g, arg, (const __nv_bfloat16*)z, bn, sums, count, M, C, N, valids,
         (__nv_bfloat16*)dz);
   }
