@@ -133,14 +133,15 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int C, int n
                                    const float* __restrict__ beta, float eps, float* __restrict__ mean,
                                    float* __restrict__ rstd, float* __restrict__ scale,
                                    float* __restrict__ shift, float* __restrict__ count_out) {
-  __shared__ double s_cnt;
-  if (threadIdx.x == 0) {
-    double cnt = 0.0;
-    for (int p = 0; p < n_parts; ++p) cnt += (valids == nullptr || valids[p] != 0.f) ? (double)N : 0.0;
-    s_cnt = cnt;
-    if (count_out != nullptr && blockIdx.x == 0) *count_out = (float)cnt;
-  }
+  __shared__ int s_valid;
+  if (threadIdx.x == 0) s_valid = 0;
   __syncthreads();
+  int nv = 0;
+  for (int p = threadIdx.x; p < n_parts; p += blockDim.x) nv += (valids == nullptr || valids[p] != 0.f) ? 1 : 0;
+  if (nv) atomicAdd(&s_valid, nv);  // integers: exact in any order
+  __syncthreads();
+  const double s_cnt = (double)s_valid * (double)N;
+  if (count_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *count_out = (float)s_cnt;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double n = s_cnt > 0.0 ? s_cnt : 1.0;
