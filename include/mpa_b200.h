@@ -147,6 +147,19 @@ int mpa_geometric_losses(const float* pts, const float* quat1, const float* tran
                          int training, int want_rot_l2, const float* weights, float* terms,
                          void* ws, size_t ws_bytes, void* stream);
 
+/* ---- Hungarian matching of equivalent parts -------------------------------- */
+/* Replaces the SciPy call of BaseModel._linear_sum_assignment (models/modules/
+ * base_model.py:175-176): `n_problems` square min-cost assignment problems in one launch.
+ * costs: the row-major fp32 cost matrices back to back (problem g starts at
+ * cost_offsets[g], is sizes[g] x sizes[g]); col_of_row[out_offsets[g] + r] = column
+ * assigned to row r (SciPy's col_ind; row_ind is 0..p-1).  All pointers are device
+ * pointers.  Same algorithm as SciPy's rectangular_lsap (Crouse 2016), float64 duals, so
+ * the assignment is identical; sizes[g] <= max_size <= 64.  Matrices with non-finite
+ * entries that make a problem infeasible yield the identity. */
+int mpa_lsap_batched(const float* costs, const int32_t* cost_offsets, const int32_t* sizes,
+                     const int32_t* out_offsets, int n_problems, int max_size, int32_t* col_of_row,
+                     void* stream);
+
 /* ---- PointNet part encoder --------------------------------------------- */
 /* Replaces PointNet.forward with global_feat=True (models/modules/encoder/
  * pointnet.py:29-41) fused with the valid-part selection of _extract_part_feats

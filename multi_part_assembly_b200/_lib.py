@@ -52,6 +52,7 @@ _SIGNATURES = {
     'mpa_bn_act': (c_int, [c_void_p] * 3 + [c_int, ctypes.c_longlong, c_int, c_int] + [c_void_p] * 3),
     'mpa_bn_backward': (c_int, [c_void_p] * 9 + [ctypes.c_longlong, c_int, c_int] + [c_void_p] * 4),
     'mpa_pool_argmax': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'mpa_lsap_batched': (c_int, [c_void_p] * 4 + [c_int, c_int, c_void_p, c_void_p]),
     'mpa_linear_workspace_bytes': (c_size_t, [c_int] * 3),
     'mpa_linear_forward': (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p, c_void_p, c_size_t, c_void_p]),
     'mpa_transformer_workspace_bytes': (c_size_t, [c_int] * 5),

@@ -265,6 +265,79 @@ pose_head_kernel(const float* __restrict__ x, int T, int K0, const float* __rest
   }
 }
 
+
+// ---- batched linear sum assignment (Hungarian matching of equivalent parts) ----
+// BaseModel._linear_sum_assignment (models/modules/base_model.py:150-179) hands the p x p
+// Chamfer cost matrix of a group of geometrically equivalent parts to SciPy's
+// linear_sum_assignment.  SciPy (scipy/optimize/rectangular_lsap, not part of the
+// reference tree; the reference pins no version) implements the shortest augmenting path
+// algorithm of D. F. Crouse, "On implementing 2D rectangular assignment algorithms", IEEE
+// TAES 52(4), 2016; this kernel restates that algorithm step for step -- float64 duals,
+// columns visited in descending index order, ties towards an unassigned column -- so the
+// assignment is the same one, without the device-to-host copy per batch.  One thread per
+// problem (p <= 64; the data sets have p <= 20).
+constexpr int LSAP_MAX = 64;
+
+__global__ void lsap_kernel(const float* __restrict__ costs, const int* __restrict__ cost_off,
+                            const int* __restrict__ sizes, const int* __restrict__ out_off, int G,
+                            int* __restrict__ col4row_out) {
+  const int gidx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gidx >= G) return;
+  const int n = sizes[gidx];
+  const float* __restrict__ cost = costs + cost_off[gidx];
+  int* out = col4row_out + out_off[gidx];
+  double u[LSAP_MAX], v[LSAP_MAX], spc[LSAP_MAX];
+  int path[LSAP_MAX], col4row[LSAP_MAX], row4col[LSAP_MAX], remaining[LSAP_MAX];
+  bool SR[LSAP_MAX], SC[LSAP_MAX];
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+  for (int i = 0; i < n; ++i) { u[i] = 0.0; v[i] = 0.0; path[i] = -1; col4row[i] = -1; row4col[i] = -1; }
+  for (int cur = 0; cur < n; ++cur) {
+    // ---- shortest augmenting path from row `cur` ----
+    double minVal = 0.0;
+    int num_remaining = n;
+    for (int it = 0; it < n; ++it) { remaining[it] = n - it - 1; SR[it] = false; SC[it] = false; spc[it] = inf; }
+    int sink = -1, i = cur;
+    while (sink == -1) {
+      int index = -1;
+      double lowest = inf;
+      SR[i] = true;
+      for (int it = 0; it < num_remaining; ++it) {
+        const int j = remaining[it];
+        const double r = minVal + (double)cost[i * n + j] - u[i] - v[j];
+        if (r < spc[j]) { path[j] = i; spc[j] = r; }
+        if (spc[j] < lowest || (spc[j] == lowest && row4col[j] == -1)) { lowest = spc[j]; index = it; }
+      }
+      minVal = lowest;
+      if (index < 0 || minVal == inf) break;  // infeasible (non-finite costs): leave the identity
+      const int j = remaining[index];
+      if (row4col[j] == -1) sink = j; else i = row4col[j];
+      SC[j] = true;
+      remaining[index] = remaining[--num_remaining];
+    }
+    if (sink < 0) {
+      for (int r = 0; r < n; ++r) out[r] = r;
+      return;
+    }
+    // ---- dual update ----
+    u[cur] += minVal;
+    for (int r = 0; r < n; ++r)
+      if (SR[r] && r != cur) u[r] += minVal - spc[col4row[r]];
+    for (int j = 0; j < n; ++j)
+      if (SC[j]) v[j] -= minVal - spc[j];
+    // ---- augment ----
+    int j = sink;
+    while (true) {
+      const int r = path[j];
+      row4col[j] = r;
+      const int t = col4row[r];
+      col4row[r] = j;
+      j = t;
+      if (r == cur) break;
+    }
+  }
+  for (int r = 0; r < n; ++r) out[r] = col4row[r];
+}
+
 }  // namespace mpa
 
 using namespace mpa;
@@ -340,6 +413,24 @@ int mpa_pose_head_forward(const float* feats, int T, int K0, const float* fc0_w,
     pose_head_kernel<<<(T + PH_TOK - 1) / PH_TOK, PH_THREADS, smem, stream>>>(
         feats, T, K0, fc0_w, fc0_b, H1, fc1_w, fc1_b, H2, rot_w, rot_b, trans_w, trans_b, normalize, rot,
         trans);
+  }
+  MPA_LAUNCH_CHECK();
+  return MPA_OK;
+}
+
+int mpa_lsap_batched(const float* costs, const int32_t* cost_offsets, const int32_t* sizes,
+                     const int32_t* out_offsets, int n_problems, int max_size, int32_t* col_of_row,
+                     void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MPA_CHECK_ARG(n_problems >= 0, "lsap_batched: negative problem count");
+  MPA_CHECK_ARG(max_size >= 0 && max_size <= LSAP_MAX, "lsap_batched: at most %d rows per problem (got %d)",
+                LSAP_MAX, max_size);
+  if (n_problems == 0) return MPA_OK;
+  MPA_CHECK_ARG(costs && cost_offsets && sizes && out_offsets && col_of_row, "lsap_batched: null pointer");
+  {
+    ProfScope ps("lsap", stream);
+    lsap_kernel<<<(n_problems + 31) / 32, 32, 0, stream>>>(costs, cost_offsets, sizes, out_offsets, n_problems,
+                                                           col_of_row);
   }
   MPA_LAUNCH_CHECK();
   return MPA_OK;

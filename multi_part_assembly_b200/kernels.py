@@ -326,6 +326,34 @@ def pose_head_forward(x, head):
     return rot.view(*shape, 4), trans.view(*shape, 3)
 
 
+def lsap_batched(costs):
+    """Min-cost assignment of a list of square cost matrices ([p_g, p_g] CUDA tensors) in
+    one launch (csrc/loss.cu::lsap_kernel, the algorithm SciPy's linear_sum_assignment
+    implements).  Returns a list of int64 device tensors `col_ind` (row r -> column),
+    without a device-to-host copy of the costs."""
+    if not costs:
+        return []
+    dev = costs[0].device
+    _lib.require_cuda(*costs)
+    sizes = [int(c.shape[0]) for c in costs]
+    flat = torch.cat([c.reshape(-1).float() for c in costs])
+    coff, ooff, a, b = [], [], 0, 0
+    for p in sizes:
+        coff.append(a)
+        ooff.append(b)
+        a += p * p
+        b += p
+    meta = torch.tensor([coff, sizes, ooff], dtype=torch.int32).to(dev, non_blocking=True)
+    out = torch.empty(b, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().mpa_lsap_batched(_lib.ptr(flat), _lib.ptr(meta[0]), _lib.ptr(meta[1]),
+                                         _lib.ptr(meta[2]), len(sizes), max(sizes), _lib.ptr(out),
+                                         _lib.cuda_stream(dev))
+    _lib.check(rc, 'mpa_lsap_batched')
+    out = out.long()
+    return [out[o:o + p] for o, p in zip(ooff, sizes)]
+
+
 def _dense(x, w, bf16):
     if bf16:
         return linear(x, w)

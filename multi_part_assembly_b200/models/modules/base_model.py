@@ -8,13 +8,12 @@ geometrically equivalent parts), `configure_optimizers`.
 Differences that do not change results: the loss terms run on the fused CUDA
 ops of utils/loss.py, per-step logging keeps tensors instead of calling
 `.item()` on every term (a host sync per term in the reference, :138), and the
-matching cost matrices of all groups of a batch are computed in one batched
-Chamfer call before a single device->host copy.
+matching cost matrices of all groups of a batch are solved by one batched
+assignment kernel on the device (no device->host copy of the costs).
 """
 import numpy as np
 import torch
 import torch.optim as optim
-from scipy.optimize import linear_sum_assignment
 
 from ...compat.lightning import LightningModule
 from ...utils import transform_pc, Rotation3D, filter_wd_parameters
@@ -137,11 +136,10 @@ class BaseModel(LightningModule):
     @torch.no_grad()
     def _linear_sum_assignment(self, pts, trans1, rot1, trans2, rot2):
         """Min-cost matching between two groups of poses (reference :150-179)."""
+        from ... import kernels
         dist_mat = self._match_cost(pts, trans1, rot1, trans2, rot2)
-        rind, cind = linear_sum_assignment(dist_mat.cpu().numpy())
-        rind = torch.from_numpy(rind).to(pts.device).long()
-        cind = torch.from_numpy(cind).to(pts.device).long()
-        return rind, cind
+        cind = kernels.lsap_batched([dist_mat])[0]
+        return torch.arange(cind.shape[0], device=cind.device), cind
 
     @torch.no_grad()
     def _match_parts(self, part_pcs, pred_trans, pred_rot, gt_trans, gt_rot, match_ids):
@@ -168,13 +166,11 @@ class BaseModel(LightningModule):
                                   gt_trans[ind, m], new_gt_rot_tensor[ind, m])
                  for ind, m in groups]
         if costs:
-            flat = torch.cat([c.reshape(-1) for c in costs]).cpu().numpy()
-            off = 0
-            for (ind, m), c in zip(groups, costs):
-                p = c.shape[0]
-                _, cind = linear_sum_assignment(flat[off:off + p * p].reshape(p, p))
-                off += p * p
-                cind = torch.from_numpy(cind).to(part_pcs.device).long()
+            # all assignments in one launch on the device (same algorithm as SciPy's
+            # linear_sum_assignment: oracle/lsap.py is pinned against it); no cost matrix
+            # travels to the host
+            from ... import kernels
+            for (ind, m), cind in zip(groups, kernels.lsap_batched(costs)):
                 new_gt_trans[ind, m] = gt_trans[ind, m][cind]
                 new_gt_rot_tensor[ind, m] = gt_rot_tensor[ind, m][cind]
         return new_gt_trans, self._wrap_rotation(new_gt_rot_tensor)

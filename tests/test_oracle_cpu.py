@@ -178,3 +178,26 @@ def test_c_abi_library_exports_every_declared_symbol():
         assert hasattr(handle, name), name
     assert declared == set(_lib._SIGNATURES), declared ^ set(_lib._SIGNATURES)
     assert _lib.lib().mpa_version() >= 100
+
+
+def test_lsap_restatement_matches_scipy():
+    """oracle/lsap.py (the algorithm the CUDA assignment kernel follows) is pinned against the
+    installed SciPy's linear_sum_assignment -- the call the reference makes
+    (base_model.py:175-176) -- on random, tie-heavy and constant cost matrices."""
+    from scipy.optimize import linear_sum_assignment
+    from oracle.lsap import linear_sum_assignment_square
+    rng = np.random.default_rng(0)
+    for trial in range(600):
+        n = int(rng.integers(1, 21))
+        kind = trial % 4
+        if kind == 0:
+            c = rng.random((n, n)).astype(np.float32)
+        elif kind == 1:
+            c = rng.integers(0, 4, (n, n)).astype(np.float32)
+        elif kind == 2:
+            c = np.full((n, n), 0.5, np.float32)
+        else:
+            c = (rng.random((n, n)) * 1e-3 + rng.integers(0, 2, (n, n))).astype(np.float32)
+        want = linear_sum_assignment(c)[1]
+        got = linear_sum_assignment_square(c.astype(np.float64))
+        assert list(want) == list(got), (trial, n)

@@ -141,3 +141,28 @@ def test_shape_mode_far_part_can_win(cuda):
     assert np.all(j1[0, :N] == 2 * N)  # lowest index of the padded part
     np.testing.assert_array_equal(got['i1'].reshape(B, -1)[0, :N], j1[0, :N])
     np.testing.assert_array_equal(got['d1'].reshape(B, -1)[0, :N], e1[0, :N])
+
+
+def test_lsap_kernel_matches_scipy(cuda):
+    """Batched assignment kernel vs SciPy's linear_sum_assignment (the reference's call,
+    base_model.py:175-176): identical column assignment, including tie-heavy matrices."""
+    from scipy.optimize import linear_sum_assignment
+    from multi_part_assembly_b200 import kernels
+    rng = np.random.default_rng(1)
+    mats = []
+    for trial in range(400):
+        n = int(rng.integers(1, 21))
+        kind = trial % 4
+        if kind == 0:
+            c = rng.random((n, n))
+        elif kind == 1:
+            c = rng.integers(0, 4, (n, n))
+        elif kind == 2:
+            c = np.full((n, n), 0.5)
+        else:
+            c = rng.random((n, n)) * 1e-3 + rng.integers(0, 2, (n, n))
+        mats.append(c.astype(np.float32))
+    mats.append(rng.random((64, 64)).astype(np.float32))
+    got = kernels.lsap_batched([torch.from_numpy(m).to(cuda) for m in mats])
+    for m, g in zip(mats, got):
+        np.testing.assert_array_equal(g.cpu().numpy(), linear_sum_assignment(m)[1])
