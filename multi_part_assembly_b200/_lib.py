@@ -78,10 +78,13 @@ def lib():
     global _LIB
     if _LIB is not None:
         return _LIB
-    if not os.path.exists(_SO):
-        # build in-tree; raises if nvcc is missing or compilation fails
-        from .csrc.build import build
-        build()
+    if 'MPA_B200_LIB' not in os.environ:
+        # build in-tree when the library is missing or older than its sources (mtime check
+        # and file lock inside build()); raises if compilation fails.  A box without nvcc
+        # (the GPU box) loads the prebuilt library as it is.
+        from .csrc.build import build, NVCC
+        if os.path.exists(NVCC) or not os.path.exists(_SO):
+            build()
     try:
         handle = ctypes.CDLL(_SO)
     except OSError as e:  # pragma: no cover

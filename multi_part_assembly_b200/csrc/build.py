@@ -18,17 +18,43 @@ FLAGS = [
 FLAGS = [f for f in FLAGS if not f.startswith('--use_fast_math')]
 
 
+def _source_hash():
+    import hashlib
+    h = hashlib.sha256(' '.join(FLAGS).encode())
+    for d in SOURCES + HEADERS:
+        with open(os.path.join(HERE, d), 'rb') as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+STAMP = os.path.join(HERE, 'build', '.srchash')
+
+
 def _stale():
-    if not os.path.exists(TARGET):
+    """True when the library is missing or was built from other sources.  Content hash,
+    not mtimes: the snapshot that carries the tree to a GPU box does not keep them."""
+    if not os.path.exists(TARGET) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(TARGET)
-    deps = [os.path.join(HERE, s) for s in SOURCES + HEADERS] + [__file__]
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(STAMP) as f:
+        return f.read().strip() != _source_hash()
 
 
 def build(force=False, verbose=False):
+    """Compile when the library is missing or older than a source.  Concurrent callers
+    (ranks of one torchrun) serialise on a file lock; the library is written to a
+    temporary name and renamed, so a reader never maps a partial file."""
     if not force and not _stale():
         return TARGET
+    import fcntl
+    os.makedirs(os.path.join(HERE, 'build'), exist_ok=True)
+    with open(os.path.join(HERE, 'build', '.lock'), 'w') as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not _stale():  # another process built it while we waited
+            return TARGET
+        return _build_locked(verbose)
+
+
+def _build_locked(verbose):
     objs = []
     procs = []
     for s in SOURCES:
@@ -46,8 +72,12 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError('nvcc failed building libmpa_b200.so')
-    subprocess.check_call([NVCC, '-shared', '-o', TARGET] + objs +
+    tmp = TARGET + f'.tmp{os.getpid()}'
+    subprocess.check_call([NVCC, '-shared', '-o', tmp] + objs +
                           ['-gencode', 'arch=compute_100a,code=sm_100a'])
+    os.replace(tmp, TARGET)
+    with open(STAMP, 'w') as f:
+        f.write(_source_hash())
     return TARGET
 
 

@@ -769,16 +769,7 @@ __global__ void chamfer_backward_kernel(const float* __restrict__ g1, const floa
 // ======================================================================
 // host side
 // ======================================================================
-static int num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
-  return sms;
-}
+static int num_sms() { return device_sms(); }
 
 static int pick_dmax(int n) {
   // cells per axis the bbox of a uniform cloud needs at ~1 point per cell
@@ -848,13 +839,13 @@ static int run_grid(CloudDesc c0, CloudDesc c1, int S, float* dist0, IdxT* idx0,
   const int nmax = c0.Nseg > c1.Nseg ? c0.Nseg : c1.Nseg;
   const int threads = nmax >= 8192 ? 1024 : (nmax >= 2048 ? 512 : 256);
   const size_t smem = sizeof(int) * (size_t)L.cs_stride;
-  static bool attr_set[2] = {false, false};
+  static DeviceOnce attr_set[2];
   const int which = sizeof(IdxT) == 8 ? 1 : 0;
-  if (!attr_set[which]) {
+  if (attr_set[which].pending()) {
     MPA_CUDA(cudaFuncSetAttribute(grid_build_kernel<IdxT>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(sizeof(int) * (GRID_MAX_DIM * GRID_MAX_DIM * GRID_MAX_DIM + 1))));
-    attr_set[which] = true;
+    attr_set[which].done();
   }
   {
     ProfScope ps(c0.fill_invalid ? "chamfer_grid_build_shape" : (c0.quat ? "chamfer_grid_build_part" : "chamfer_grid_build"), stream);

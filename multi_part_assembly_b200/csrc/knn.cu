@@ -465,14 +465,7 @@ using namespace mpa;
 extern "C" {
 
 static int knn_tile_ctas() {  // one persistent CTA (and one 128 x Np score slab) per SM
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
-  return sms;
+  return device_sms();
 }
 
 size_t mpa_knn_workspace_bytes(int n, int N) {
@@ -500,10 +493,10 @@ int mpa_knn(const float* x, int n, int N, int C, int k, int32_t* idx, void* ws, 
   MPA_LAUNCH_CHECK();
   static const int legacy = getenv("MPA_KNN_LEGACY") ? atoi(getenv("MPA_KNN_LEGACY")) : 0;
   if (k <= 32 && N <= 1024 && !legacy) {
-    static bool attr_t = false;
-    if (!attr_t) {
+    static DeviceOnce attr_t;
+    if (attr_t.pending()) {
       MPA_CUDA(cudaFuncSetAttribute(knn_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KT_SMEM));
-      attr_t = true;
+      attr_t.done();
     }
     const int tiles = (N + KT - 1) / KT;
     int ctas = knn_tile_ctas();
@@ -522,11 +515,11 @@ int mpa_knn(const float* x, int n, int N, int C, int k, int32_t* idx, void* ws, 
   const int Np = (N + KNN_BN - 1) / KNN_BN * KNN_BN;
   const size_t smem = sizeof(float) * ((size_t)rows * Cp + KNN_BN * (KNN_KC + 4) + (size_t)rows * Np);
   const int tiles = (N + rows - 1) / rows;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.pending()) {
     MPA_CUDA(cudaFuncSetAttribute(knn_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     MPA_CUDA(cudaFuncSetAttribute(knn_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
+    attr.done();
   }
   MPA_CHECK_ARG(smem <= 227 * 1024, "knn: shared memory need %zu exceeds 227 KB", smem);
   {

@@ -413,13 +413,13 @@ int launch_linear(const __nv_bfloat16* x, const __nv_bfloat16* w, int M, int N, 
   if (rc != MPA_OK) return rc;
   rc = make_map(&mw, w, N, K, bn);
   if (rc != MPA_OK) return rc;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.pending()) {
     MPA_CUDA(cudaFuncSetAttribute(linear_bf16_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   ln_smem_bytes(128)));
     MPA_CUDA(cudaFuncSetAttribute(linear_bf16_kernel<LN_FUSED_WIDTH, true>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, ln_smem_bytes(LN_FUSED_WIDTH)));
-    attr = true;
+    attr.done();
   }
   dim3 grid((M + LN_BM - 1) / LN_BM, (N + bn - 1) / bn);
   {

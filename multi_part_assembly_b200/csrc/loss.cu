@@ -403,10 +403,10 @@ int mpa_pose_head_forward(const float* feats, int T, int K0, const float* fc0_w,
                     trans, "pose_head_forward: null pointer");
   const size_t smem = sizeof(float) * PH_TOK * ((size_t)K0 + H1 + H2 + 7);
   MPA_CHECK_ARG(smem <= 200 * 1024, "pose_head_forward: layer widths too large (%d, %d, %d)", K0, H1, H2);
-  static size_t attr_smem = 48 * 1024;
-  if (smem > attr_smem) {
-    MPA_CUDA(cudaFuncSetAttribute(pose_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
+  static DeviceOnce attr;  // the limit is per device: raise it to the checked maximum once on each
+  if (smem > 48 * 1024 && attr.pending()) {
+    MPA_CUDA(cudaFuncSetAttribute(pose_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr.done();
   }
   {
     ProfScope ps("pose_head", stream);

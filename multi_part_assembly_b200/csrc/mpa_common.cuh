@@ -55,6 +55,32 @@ int launch_se3_backward(const float* quat, const float* pts, const float* grad_o
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Function attributes (dynamic shared memory limits) and the SM count are PER DEVICE: a
+// process that drives a second GPU must set / query them again.  `DeviceOnce` remembers, per
+// call site, on which devices the one-time setup already ran (idempotent, so a race between
+// two host threads only repeats it).
+inline int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d;
+}
+struct DeviceOnce {
+  std::atomic<uint64_t> mask{0};
+  bool pending() const { return (mask.load(std::memory_order_acquire) >> (current_device() & 63) & 1ull) == 0; }
+  void done() { mask.fetch_or(1ull << (current_device() & 63), std::memory_order_release); }
+};
+inline int device_sms() {
+  static std::atomic<int> cache[64];
+  const int d = current_device() & 63;
+  int s = cache[d].load(std::memory_order_relaxed);
+  if (s == 0) {
+    cudaDeviceGetAttribute(&s, cudaDevAttrMultiProcessorCount, d);
+    if (s <= 0) s = 148;
+    cache[d].store(s, std::memory_order_relaxed);
+  }
+  return s;
+}
+
 // scratch: caller-provided workspace or stream-ordered allocation
 struct Scratch {
   void* base = nullptr;

@@ -454,11 +454,11 @@ __global__ void pointnet_pool_kernel(const unsigned* pmax, const unsigned* pmin,
 
 template <int PHASE>
 static int launch_phase(const PointNetArgs& a, int grid, cudaStream_t stream) {
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.pending()) {
     MPA_CUDA(cudaFuncSetAttribute(pointnet_phase_kernel<PHASE>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, PN_SMEM));
-    attr = true;
+    attr.done();
   }
   {
     static const char* names[5] = {"pointnet_phase1", "pointnet_phase2", "pointnet_phase3",

@@ -179,6 +179,9 @@ class BaseModel(LightningModule):
     def _calc_loss(self, out_dict, data_dict):
         """All loss terms ([B] each) for one prediction; evaluation metrics too
         when not training (reference :240-314)."""
+        # the single-kernel reduction of loss_function is only valid when ONE prediction
+        # was scored (DGL / refine models score every GNN / refine iteration)
+        self._calc_loss_calls = getattr(self, '_calc_loss_calls', 0) + 1
         pred_trans, pred_rot = out_dict['trans'], out_dict['rot']
         part_pcs, valids = data_dict['part_pcs'], data_dict['part_valids']
         gt_trans, gt_rot = data_dict['part_trans'], data_dict['part_rot']
@@ -282,6 +285,7 @@ class BaseModel(LightningModule):
         samples = None
         out_dict = {}
         self._fused_packed = None
+        self._calc_loss_calls = 0
         for _ in range(self.sample_iter):
             sample_loss, out_dict = self._loss_function(data_dict, out_dict,
                                                         optimizer_idx=optimizer_idx)
@@ -290,7 +294,7 @@ class BaseModel(LightningModule):
             for k, v in sample_loss.items():
                 samples[k].append(v)
         packed = self._fused_packed
-        if self.sample_iter == 1 and packed is not None and \
+        if self.sample_iter == 1 and packed is not None and self._calc_loss_calls == 1 and \
                 tuple(k for k in samples.keys() if k.endswith('_loss')) == packed[1]:
             # single sample straight from the fused loss kernels: one mean over [6, B]
             terms, keys = packed

@@ -14,10 +14,27 @@ of BASELINE.json's metric); training steps use the eager path.
 import torch
 
 
+def _check_capturable(model):
+    """A CUDA graph replays fixed device work: anything the step draws from the CPU
+    generator or reads back on the host would be frozen into the graph.  The semantic
+    (PartNet) models do both -- `torch.randperm` per matching group and a host read of
+    `match_ids` (models/modules/base_model.py `_match_parts`), `torch.randn` pose noise
+    (models/modules/regressor.py) -- so Min-of-N sampling would silently repeat one
+    sample.  They take the eager path."""
+    if getattr(model, 'semantic', False):
+        raise ValueError('Graphed steps do not support semantic (Hungarian-matching) models: '
+                         'the matching draws CPU random numbers and reads match_ids on the host')
+    for m in model.modules():
+        if getattr(m, 'noise_dim', 0):
+            raise ValueError('Graphed steps do not support pose heads with noise_dim > 0: the noise '
+                             'is drawn from the CPU generator and would be baked into the graph')
+
+
 class GraphedStep:
 
     def __init__(self, model, example_batch, mode='train', autocast_dtype=torch.bfloat16,
                  warmup=3):
+        _check_capturable(model)
         self.model = model
         self.mode = mode
         self.autocast_dtype = autocast_dtype
@@ -102,7 +119,13 @@ def allreduce_gradients(params, group=None):
     world = dist.get_world_size(group)
     if world == 1:
         return
-    grads = [p.grad for p in params if p.grad is not None]
+    # every rank must reduce the same buffer: a parameter without a gradient on this rank
+    # (unused in this step) contributes zeros instead of shortening the buffer
+    params = [p for p in params if p.requires_grad]
+    for p in params:
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+    grads = [p.grad for p in params]
     if not grads:
         return
     flat = torch.cat([g.reshape(-1).float() for g in grads])
@@ -131,6 +154,7 @@ class GraphedTrainStep:
 
     def __init__(self, model, optimizer, example_batch, autocast_dtype=torch.bfloat16, warmup=3,
                  group=None):
+        _check_capturable(model)
         self.model = model
         self.optimizer = optimizer
         self.autocast_dtype = autocast_dtype

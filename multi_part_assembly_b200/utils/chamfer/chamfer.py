@@ -72,13 +72,16 @@ class ChamferDistanceFunction(torch.autograd.Function):
     @staticmethod
     @custom_fwd(device_type='cuda', cast_inputs=torch.float32)
     def forward(ctx, xyz1, xyz2):
-        xyz1 = xyz1.contiguous()
-        xyz2 = xyz2.contiguous()
-        if xyz1.dtype == torch.float64:
+        if xyz1.dtype == torch.float64 or xyz2.dtype == torch.float64:
             raise RuntimeError(
                 'chamfer_distance: float64 is not supported by the sm_100a '
                 'kernels (the reference only uses it in its gradcheck test)')
-        dist1, idx1, dist2, idx2 = chamfer_forward(xyz1.float(), xyz2.float())
+        ctx.in_dtypes = (xyz1.dtype, xyz2.dtype)
+        # the kernels read fp32: cast ONCE and save the cast tensors, so that the
+        # backward never hands half-precision buffers to a float* entry point
+        xyz1 = xyz1.contiguous().float()
+        xyz2 = xyz2.contiguous().float()
+        dist1, idx1, dist2, idx2 = chamfer_forward(xyz1, xyz2)
         ctx.save_for_backward(xyz1, xyz2, idx1, idx2)
         ctx.mark_non_differentiable(idx1, idx2)
         return dist1, dist2
@@ -89,7 +92,8 @@ class ChamferDistanceFunction(torch.autograd.Function):
         xyz1, xyz2, idx1, idx2 = ctx.saved_tensors
         grad_dist1 = grad_dist1.contiguous().float()
         grad_dist2 = grad_dist2.contiguous().float()
-        return chamfer_backward(grad_dist1, grad_dist2, xyz1, xyz2, idx1, idx2)
+        g1, g2 = chamfer_backward(grad_dist1, grad_dist2, xyz1, xyz2, idx1, idx2)
+        return g1.to(ctx.in_dtypes[0]), g2.to(ctx.in_dtypes[1])
 
 
 def chamfer_distance(xyz1, xyz2, transpose=False, sqrt=False, eps=1e-12):

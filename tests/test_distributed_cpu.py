@@ -67,16 +67,22 @@ def _grad_worker(rank, world, port, out):
     from multi_part_assembly_b200.runtime import allreduce_gradients
     torch.manual_seed(0)
     net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3))  # same init on both ranks
-    unused = torch.nn.Parameter(torch.zeros(4))                             # a parameter without grad
+    # a parameter that only rank 0 uses in this step: rank 1 has no gradient for it and must
+    # contribute zeros, so that both ranks reduce buffers of the same length
+    unused = torch.nn.Parameter(torch.zeros(4))
     x = torch.full((2, 5), float(rank + 1))
-    net(x).sum().backward()
+    loss = net(x).sum()
+    if rank == 0:
+        loss = loss + 3.0 * unused.sum()
+    loss.backward()
     local = [p.grad.clone() for p in net.parameters()]
     allreduce_gradients(list(net.parameters()) + [unused])
     gathered = [[torch.zeros_like(g) for _ in range(world)] for g in local]
     for g, bufs in zip(local, gathered):
         dist.all_gather(bufs, g)
     ok = all(torch.allclose(p.grad, torch.stack(bufs).mean(0), atol=1e-6)
-             for p, bufs in zip(net.parameters(), gathered)) and unused.grad is None
+             for p, bufs in zip(net.parameters(), gathered)) and \
+        unused.grad is not None and torch.allclose(unused.grad, torch.full((4, ), 1.5))
     if rank == 0:
         out.put(bool(ok))
     dist.destroy_process_group()

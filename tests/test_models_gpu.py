@@ -243,7 +243,11 @@ def test_transformer_tcgen05(cuda, name, dims, seed):
 
 @pytest.mark.parametrize('tag,name,dataset,seed,semantic,N,nv', [
     ('model_pn_transformer', 'pn_transformer', 'everyday', 11, False, 64, (5, 3)),
-    ('model_global', 'global', 'everyday', 13, False, 64, (5, 3))])
+    ('model_global', 'global', 'everyday', 13, False, 64, (5, 3)),
+    # models that score several predictions per step (GNN / refine iterations): the totals
+    # are sums over the iterations, which the single-prediction shortcut must not replace
+    ('model_dgl', 'dgl', 'everyday', 14, False, 64, (5, 3)),
+    ('model_pn_transformer_refine', 'pn_transformer_refine', 'everyday', 16, False, 64, (5, 3))])
 def test_fused_loss_path_matches_reference(cuda, tag, name, dataset, seed, semantic, N, nv):
     """forward_pass without autograd (the benchmark / CUDA-graph path) uses the
     fused loss kernels; its loss dict must equal the reference's too."""
