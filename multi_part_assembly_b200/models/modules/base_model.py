@@ -183,6 +183,9 @@ class BaseModel(LightningModule):
         # was scored (DGL / refine models score every GNN / refine iteration)
         self._calc_loss_calls = getattr(self, '_calc_loss_calls', 0) + 1
         pred_trans, pred_rot = out_dict['trans'], out_dict['rot']
+        # last scored prediction (references, no copies): lets a CUDA-graph replay expose
+        # the poses next to the losses (runtime.GraphedStep.static_pred)
+        self._last_pred = (pred_trans, pred_rot.rot)
         part_pcs, valids = data_dict['part_pcs'], data_dict['part_valids']
         gt_trans, gt_rot = data_dict['part_trans'], data_dict['part_rot']
         if self.semantic:

@@ -51,6 +51,9 @@ class GraphedStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.static_out = self._step()
+            # the poses the losses were computed from ([B, P, 3], [B, P, 4]); static graph
+            # buffers like the losses: valid until the next replay
+            self.static_pred = getattr(model, '_last_pred', None)
         torch.cuda.synchronize(dev)
 
     def _step(self):

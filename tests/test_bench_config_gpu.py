@@ -1,0 +1,210 @@
+"""Parity of the paths bench.py actually times, at the sizes it times them (P = 20 slots,
+N = 1000 points), against the CPU oracle.
+
+The model-step golden tests (test_models_gpu.py) run fp32 at N = 64/128, where PointNet and the
+transformer take the fp32 route.  Here the step runs the way the headline number is
+measured -- `runtime.GraphedStep`, bf16 tensor-core kernels, Chamfer/SE(3) in fp32 -- and is
+checked in two stages:
+
+  1. poses: the graph's own poses vs `oracle.torch_ref.pn_transformer_forward` (fp32 CPU, same
+     weights and batch) at the bf16 bar (<= 3e-2 of the largest pose component);
+  2. losses: every loss term of the graph vs `oracle.torch_ref.geometric_losses` evaluated ON
+     THE GPU'S OWN POSES, at north_star's 1e-5 relative bar (brute-force C Chamfer underneath,
+     2 x 20000^2 pair evaluations per shape).
+
+Same scheme for the DGCNN encoder at cfg D's part size (k-NN sets of the first layer bit-exact)
+and for one semantic batch (Hungarian matching vs SciPy on the GPU's poses, Min-of-N)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cpu as oracle_cpu
+from oracle import torch_ref
+from oracle.params import fill_params_, zero_dropout
+
+pytestmark = pytest.mark.gpu
+
+
+def _cpu_batch(batch):
+    return {k: v.detach().cpu() for k, v in batch.items()}
+
+
+def _state(model):
+    return {k: v.detach().cpu() for k, v in model.state_dict().items()}
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+@pytest.mark.parametrize('nv', [[20, 20, 20, 20], [20, 7, 2, 13]])
+def test_graphed_bf16_step_at_bench_size(cuda, nv):
+    from multi_part_assembly_b200.configs import get_cfg
+    from multi_part_assembly_b200.datasets import make_batch
+    from multi_part_assembly_b200.models import build_model
+    from multi_part_assembly_b200.compat.lightning import Trainer
+    from multi_part_assembly_b200.runtime import GraphedStep
+    from multi_part_assembly_b200 import _lib
+    B, P, N = len(nv), 20, 1000
+    model = zero_dropout(fill_params_(build_model(get_cfg('pn_transformer', 'everyday')), 41))
+    model = model.to(cuda).train()
+    model.trainer = Trainer()
+    sd = _state(model)  # BatchNorm running statistics are not used in train mode
+    host = make_batch(B, P=P, N=N, num_valid=nv, seed=5)
+    dev_batch = {k: v.to(cuda) for k, v in host.items()}
+    l0 = _lib.launch_count()
+    step = GraphedStep(model, dev_batch, mode='train', autocast_dtype=torch.bfloat16)
+    assert _lib.launch_count() > l0  # the capture issued kernels of libmpa_b200.so
+    out = {k: float(v) for k, v in step(dev_batch).items()}
+    pred_trans, pred_quat = [t.detach().float().cpu() for t in step.static_pred]
+
+    # stage 1: poses at the bf16 bar
+    want_rot, want_trans = torch_ref.pn_transformer_forward(host, sd, training=True)
+    valid = host['part_valids'] == 1
+    assert torch.isfinite(pred_quat).all() and torch.isfinite(pred_trans).all()
+    assert _rel(pred_quat[valid], want_rot[valid]) < 3e-2
+    assert _rel(pred_trans[valid], want_trans[valid]) < 3e-2
+
+    # stage 2: losses on the GPU's own poses, 1e-5 relative (north_star)
+    want, _ = torch_ref.geometric_losses(host, torch_ref.process_zero_quat(pred_quat), pred_trans,
+                                         training=True)
+    for k, w in want.items():
+        np.testing.assert_allclose(out[k], float(w), rtol=1e-5, atol=1e-7, err_msg=k)
+
+    # the replay is deterministic and equals the eager path it was captured from
+    again = {k: float(v) for k, v in step(dev_batch).items()}
+    assert again == out
+    with torch.no_grad(), torch.autocast('cuda', dtype=torch.bfloat16):
+        eager = model.forward_pass(dict(dev_batch), mode='train', optimizer_idx=-1)
+    for k, v in eager.items():
+        np.testing.assert_allclose(float(v), out[k], rtol=1e-6, atol=1e-8, err_msg=k)
+
+
+@pytest.mark.parametrize('precision,bar', [('fp32', 2e-4), ('bf16', 5e-2)])
+def test_dgcnn_encoder_at_cfg_d_part_size(cuda, precision, bar):
+    """DGCNN on parts of N = 1000 points (cfg D's size; 25 parts so the CPU oracle finishes in
+    seconds): first-layer k-NN sets bit-exact vs the C oracle, features vs the fp32 torch
+    restatement (fp32 mode: accumulation order only; bf16 mode: bf16 operand rounding)."""
+    from multi_part_assembly_b200 import kernels
+    from multi_part_assembly_b200.models import build_encoder
+    enc = fill_params_(build_encoder('dgcnn', 128), 5).to(cuda).train()
+    sd = _state(enc)
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(25, 1000, 3, generator=g) - 0.5
+    x = x - x.mean(1, keepdim=True)
+    got_idx = kernels.knn(x.to(cuda), 20).cpu().numpy().astype(np.int64)
+    want_idx = oracle_cpu.knn(np.ascontiguousarray(x.numpy().transpose(0, 2, 1)), 20)
+    np.testing.assert_array_equal(np.sort(got_idx, -1), want_idx)
+    kernels.set_precision(precision)
+    try:
+        with torch.no_grad():
+            out = enc(x.to(cuda)).float().cpu().numpy()
+    finally:
+        kernels.set_precision('auto')
+    want = torch_ref.dgcnn_forward(x, sd, training=True).numpy()
+    assert np.isfinite(out).all()
+    assert _rel(out, want) < bar, _rel(out, want)
+
+
+def test_dgl_dgcnn_losses_on_own_poses(cuda):
+    """cfg D model (DGL GNN + DGCNN encoder), 16 valid parts x 1000 points: the loss terms of
+    the last GNN iteration equal the oracle's on the GPU's own poses (1e-5)."""
+    from multi_part_assembly_b200.configs import get_cfg
+    from multi_part_assembly_b200.datasets import make_batch
+    from multi_part_assembly_b200.models import build_model
+    from multi_part_assembly_b200.compat.lightning import Trainer
+    cfg = get_cfg('dgl', 'everyday')
+    cfg.model.encoder = 'dgcnn'
+    model = zero_dropout(fill_params_(build_model(cfg), 15)).to(cuda).eval()
+    model.trainer = Trainer()
+    host = make_batch(2, P=20, N=1000, num_valid=[16, 9], seed=8)
+    dev_batch = {k: v.to(cuda) for k, v in host.items()}
+    with torch.no_grad():
+        ld = model.forward_pass(dict(dev_batch), mode='val', optimizer_idx=-1)
+    pred_trans, pred_quat = [t.detach().float().cpu() for t in model._last_pred]
+    want, _ = torch_ref.geometric_losses(host, torch_ref.process_zero_quat(pred_quat), pred_trans,
+                                         training=False)
+    # validation scores the final iteration only (dgl/network.py:284-297 in the reference)
+    for k in ('trans_loss', 'rot_pt_cd_loss', 'transform_pt_cd_loss', 'rot_loss', 'rot_pt_l2_loss'):
+        np.testing.assert_allclose(float(ld[k]), float(want[k]), rtol=1e-5, atol=1e-7, err_msg=k)
+    np.testing.assert_allclose(float(ld['loss']), float(want['loss']), rtol=1e-5)
+
+
+def test_semantic_batch_matching_and_mon(cuda):
+    """Semantic (PartNet-style) batch at N = 1000 under bf16: every Hungarian matching of the step
+    equals SciPy's on the GPU's own poses and the same CPU random subsample, and the
+    Min-of-N loss dict equals the oracle's recomputation from the per-sample poses."""
+    from scipy.optimize import linear_sum_assignment
+    from multi_part_assembly_b200.configs import get_cfg
+    from multi_part_assembly_b200.datasets import make_batch
+    from multi_part_assembly_b200.models import build_model
+    from multi_part_assembly_b200.compat.lightning import Trainer
+    cfg = get_cfg('pn_transformer', 'partnet_chair')
+    model = zero_dropout(fill_params_(build_model(cfg), 12)).to(cuda).train()
+    model.trainer = Trainer()
+    B, P, N = 2, 20, 1000
+    host = make_batch(B, P=P, N=N, num_valid=[7, 4], seed=12, semantic=True)
+    dev_batch = {k: v.to(cuda) for k, v in host.items()}
+
+    calls = []
+    orig = model._match_parts
+
+    def spy(part_pcs, pred_trans, pred_rot, gt_trans, gt_rot, match_ids):
+        state = torch.get_rng_state()
+        new_t, new_r = orig(part_pcs, pred_trans, pred_rot, gt_trans, gt_rot, match_ids)
+        calls.append(dict(state=state, pred_t=pred_trans.detach().float().cpu(),
+                          pred_q=pred_rot.rot.detach().float().cpu(),
+                          new_t=new_t.detach().cpu(), new_q=new_r.rot.detach().cpu()))
+        return new_t, new_r
+
+    model._match_parts = spy
+    torch.manual_seed(112)
+    with torch.no_grad(), torch.autocast('cuda', dtype=torch.bfloat16):
+        ld = model.forward_pass(dict(dev_batch), mode='train', optimizer_idx=-1)
+    assert len(calls) == cfg.loss.sample_iter
+
+    pcs, valids = host['part_pcs'], host['part_valids']
+    gt_t, gt_q = host['part_trans'], torch_ref.process_zero_quat(host['part_quat'])
+    ids = host['match_ids'].long().numpy()
+    keep = torch.get_rng_state()
+    totals, terms_all = [], []
+    for c in calls:
+        # ---- the matching, restated (base_model.py:150-238) with SciPy as the reference does
+        torch.set_rng_state(c['state'])
+        want_t, want_q = gt_t.clone(), gt_q.clone()
+        for b in range(B):
+            for g in range(1, int(ids[b].max()) + 1):
+                m = np.nonzero(ids[b] == g)[0]
+                sample = torch.randperm(N)[:100]
+                pts = pcs[b, m][:, sample]
+                p = len(m)
+                a = torch_ref.qtransform(c['pred_t'][b, m], c['pred_q'][b, m], pts)
+                bb = torch_ref.qtransform(gt_t[b, m], gt_q[b, m], pts)
+                a = a.unsqueeze(1).expand(p, p, 100, 3).reshape(-1, 100, 3)
+                bb = bb.unsqueeze(0).expand(p, p, 100, 3).reshape(-1, 100, 3)
+                d1, d2 = torch_ref.chamfer_distance(a, bb)
+                cost = (d1.mean(1) + d2.mean(1)).view(p, p).numpy()
+                rind, cind = linear_sum_assignment(cost)
+                want_t[b, m[rind]] = gt_t[b, m[cind]]
+                want_q[b, m[rind]] = gt_q[b, m[cind]]
+        np.testing.assert_array_equal(c['new_t'].numpy(), want_t.numpy())
+        np.testing.assert_array_equal(c['new_q'].numpy(), want_q.numpy())
+        # ---- this sample's loss terms on the matched ground truth
+        pq = torch_ref.process_zero_quat(c['pred_q'])
+        terms = {
+            'trans_loss': torch_ref.trans_l2_loss(c['pred_t'], want_t, valids),
+            'rot_pt_cd_loss': torch_ref.rot_points_cd_loss(pcs, pq, want_q, valids),
+            'transform_pt_cd_loss': torch_ref.shape_cd_loss(pcs, c['pred_t'], want_t, pq, want_q,
+                                                            valids, training=True),
+        }
+        terms_all.append(terms)
+        totals.append(sum(terms[k] * cfg.loss[f'{k}_w'] for k in terms))
+    torch.set_rng_state(keep)
+    total = torch.stack(totals)                     # [samples, B]
+    pick = total.argmin(0)
+    ar = torch.arange(B)
+    for k in terms_all[0]:
+        want = torch.stack([t[k] for t in terms_all])[pick, ar].mean()
+        np.testing.assert_allclose(float(ld[k]), float(want), rtol=1e-5, atol=1e-7, err_msg=k)
+    np.testing.assert_allclose(float(ld['loss']), float(total[pick, ar].mean()), rtol=1e-5)
