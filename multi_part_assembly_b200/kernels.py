@@ -380,6 +380,10 @@ def _bn_affine(bn, mean, var_biased, count, training):
     return scale.float(), (bn.bias.double() - mean * scale).float()
 
 
+# tests set this to a list to receive the k-NN graph of every EdgeConv layer
+_DGCNN_TRACE = None
+
+
 def _dgcnn_native(x, m, training, k, bf16):
     n, N, _ = x.shape
     M = n * N
@@ -390,6 +394,8 @@ def _dgcnn_native(x, m, training, k, bf16):
         W = conv[0].weight.reshape(conv[0].weight.shape[0], 2 * C).float()
         Co = W.shape[0]
         idx = knn(h.view(n, N, C), k)
+        if _DGCNN_TRACE is not None:
+            _DGCNN_TRACE.append(idx)
         # W [xj - xi ; xi] = W1 xj + (W2 - W1) xi
         wcat = torch.cat([W[:, :C], W[:, C:] - W[:, :C]], dim=0)
         uv = _dense(h, wcat, bf16)

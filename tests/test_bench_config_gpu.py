@@ -81,11 +81,16 @@ def test_graphed_bf16_step_at_bench_size(cuda, nv):
         np.testing.assert_allclose(float(v), out[k], rtol=1e-6, atol=1e-8, err_msg=k)
 
 
-@pytest.mark.parametrize('precision,bar', [('fp32', 2e-4), ('bf16', 5e-2)])
-def test_dgcnn_encoder_at_cfg_d_part_size(cuda, precision, bar):
+@pytest.mark.parametrize('precision,bar,knn_tol', [('fp32', 2e-4, 1e-5), ('bf16', 5e-2, 5e-2)])
+def test_dgcnn_encoder_at_cfg_d_part_size(cuda, precision, bar, knn_tol):
     """DGCNN on parts of N = 1000 points (cfg D's size; 25 parts so the CPU oracle finishes in
-    seconds): first-layer k-NN sets bit-exact vs the C oracle, features vs the fp32 torch
-    restatement (fp32 mode: accumulation order only; bf16 mode: bf16 operand rounding)."""
+    seconds).  Layer 1 (identical input): k-NN sets bit-exact vs the C oracle.  Layers 2-4 work
+    on features that differ from the oracle's in the last bits, so near-ties between the k-th
+    and (k+1)-th neighbour may resolve differently ("bit-exact k-NN indices"):
+    there the GPU's set must be a valid top-k of the ORACLE's score matrix up to `knn_tol`,
+    and the oracle then continues on the GPU's graph, so that the features are compared on
+    the same graph: fp32 mode at 2e-4 (accumulation order only), bf16 mode at the bf16 bar."""
+    import torch.nn.functional as F
     from multi_part_assembly_b200 import kernels
     from multi_part_assembly_b200.models import build_encoder
     enc = fill_params_(build_encoder('dgcnn', 128), 5).to(cuda).train()
@@ -93,17 +98,38 @@ def test_dgcnn_encoder_at_cfg_d_part_size(cuda, precision, bar):
     g = torch.Generator().manual_seed(3)
     x = torch.rand(25, 1000, 3, generator=g) - 0.5
     x = x - x.mean(1, keepdim=True)
-    got_idx = kernels.knn(x.to(cuda), 20).cpu().numpy().astype(np.int64)
-    want_idx = oracle_cpu.knn(np.ascontiguousarray(x.numpy().transpose(0, 2, 1)), 20)
-    np.testing.assert_array_equal(np.sort(got_idx, -1), want_idx)
+    k = 20
     kernels.set_precision(precision)
+    kernels._DGCNN_TRACE = trace = []
     try:
         with torch.no_grad():
             out = enc(x.to(cuda)).float().cpu().numpy()
     finally:
         kernels.set_precision('auto')
-    want = torch_ref.dgcnn_forward(x, sd, training=True).numpy()
-    assert np.isfinite(out).all()
+        kernels._DGCNN_TRACE = None
+    assert len(trace) == 4 and np.isfinite(out).all()
+    idxs = [t.long().cpu() for t in trace]
+    want_idx = oracle_cpu.knn(np.ascontiguousarray(x.numpy().transpose(0, 2, 1)), k)
+    np.testing.assert_array_equal(np.sort(idxs[0].numpy(), -1), want_idx)
+
+    h = x.transpose(2, 1).contiguous()
+    feats = []
+    for i in range(1, 5):
+        scores = torch_ref.knn_scores(h)                     # [n, N, N], the reference's form
+        kth = scores.topk(k, dim=-1)[0][..., -1]             # oracle's k-th best score per row
+        worst = torch.gather(scores, 2, idxs[i - 1]).min(-1)[0]
+        scale = scores.abs().amax(-1)
+        assert bool((worst >= kth - knn_tol * scale).all()), f'layer {i}: not a top-{k} set'
+        assert bool((idxs[i - 1].sort(-1)[0].diff(dim=-1) > 0).all())  # k distinct neighbours
+        e = torch_ref.graph_feature(h, k, idxs[i - 1])
+        e = F.conv2d(e, sd[f'conv{i}.0.weight'])
+        e = F.leaky_relu(torch_ref._bn(e, sd, f'bn{i}', True), 0.2)
+        h = e.max(dim=-1)[0]
+        feats.append(h)
+    h = F.conv1d(torch.cat(feats, dim=1), sd['conv5.0.weight'])
+    h = F.leaky_relu(torch_ref._bn(h, sd, 'bn5', True), 0.2)
+    want = F.linear(torch.cat((h.max(dim=-1)[0], h.mean(dim=-1)), 1), sd['out_fc.weight'],
+                    sd['out_fc.bias']).numpy()
     assert _rel(out, want) < bar, _rel(out, want)
 
 

@@ -67,17 +67,22 @@ def test_edge_aggregate_vs_torch(cuda):
 
 
 def test_dgcnn_bf16_mode(cuda):
-    """bf16 tensor-core GEMMs inside DGCNN: same graph, outputs within bf16 tolerance."""
+    """bf16 tensor-core GEMMs inside DGCNN vs the reference's fp32 golden output: same
+    first-layer graph, features within bf16 operand rounding (5e-2 of the largest feature;
+    tests/test_bench_config_gpu.py holds the N = 1000 version with the graph check)."""
     from multi_part_assembly_b200 import kernels
     from multi_part_assembly_b200.models import build_encoder
     g = dict(np.load(os.path.join(GOLD, 'dgcnn.npz')))
-    enc = fill_params_(build_encoder('dgcnn', 128), 5).to(cuda).eval()
+    enc = fill_params_(build_encoder('dgcnn', 128), 5).to(cuda).train()
     kernels.set_precision('bf16')
     try:
-        out = enc(torch.from_numpy(g['x']).to(cuda)).detach().cpu().numpy()
+        with torch.no_grad():
+            out = enc(torch.from_numpy(g['x']).to(cuda)).detach().float().cpu().numpy()
     finally:
         kernels.set_precision('auto')
     assert np.isfinite(out).all()
+    err = np.abs(out - g['out_train']).max() / np.abs(g['out_train']).max()
+    assert err < 5e-2, err
 
 
 def test_knn_clustered_in_few_lanes(cuda):
