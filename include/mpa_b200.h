@@ -258,21 +258,25 @@ int mpa_transformer_forward(const float* tokens, const unsigned char* valid, int
  * points of a part as ROWS (the reference passes [n,C,N]; transpose first);
  * idx [n,N,k] int32, indices local to the part, best score first, ties to the
  * lower index.  Scores are the reference's expanded form evaluated in fp32 with
- * a sequential-channel FMA dot product (the oracle's order).  N <= 2048. */
+ * a sequential-channel FMA dot product (the oracle's order).  N <= 2048.
+ * valids [n] (nullable): parts flagged 0 (padding) are skipped on the device --
+ * their idx rows are left untouched -- so the caller never compacts on the host
+ * (the reference's boolean-mask gather, models/dgl/network.py:90-99). */
 size_t mpa_knn_workspace_bytes(int n, int N);
-int mpa_knn(const float* x, int n, int N, int C, int k, int32_t* idx, void* ws, size_t ws_bytes,
-            void* stream);
+int mpa_knn(const float* x, const float* valids, int n, int N, int C, int k, int32_t* idx, void* ws,
+            size_t ws_bytes, void* stream);
 
 /* EdgeConv after the split W [xj-xi ; xi] = W1 xj + (W2-W1) xi (dgcnn.py:18-38,
  * 81-95): uv [n*N, 2*Co] holds u = W1 x in the first Co columns and
  * v = (W2-W1) x in the last Co; idx [n*N,k] from mpa_knn.  Writes the max and
  * min over the k edges of u_j + v_i (ymax/ymin [n*N,Co]) and sums [Co,2] =
  * (sum, sum of squares) over all n*N*k edges in fp64 -- the inputs of
- * BatchNorm2d batch statistics + LeakyReLU + max over k. */
+ * BatchNorm2d batch statistics + LeakyReLU + max over k.  valids [n] (nullable):
+ * points of parts flagged 0 get ymax = ymin = 0 and stay out of the sums. */
 size_t mpa_edge_aggregate_workspace_bytes(long long M, int Co);
-int mpa_edge_aggregate(const float* uv, const int32_t* idx, int n, int N, int Co, int k,
-                       float* ymax, float* ymin, double* sums, void* ws, size_t ws_bytes,
-                       void* stream);
+int mpa_edge_aggregate(const float* uv, const int32_t* idx, const float* valids, int n, int N,
+                       int Co, int k, float* ymax, float* ymin, double* sums, void* ws,
+                       size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

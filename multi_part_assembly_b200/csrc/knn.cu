@@ -37,8 +37,8 @@ __global__ void sqnorm_kernel(const float* __restrict__ x, long long rows, int C
 // x [n, N, C] row-major, xx [n, N]; idx [n, N, k] int32 (best first; ties -> lower index)
 template <int ROWS>
 __global__ void __launch_bounds__(KNN_THREADS)
-knn_kernel(const float* __restrict__ x, const float* __restrict__ xx, int N, int C, int k,
-           int* __restrict__ idx) {
+knn_kernel(const float* __restrict__ x, const float* __restrict__ xx, const float* __restrict__ valids,
+           int N, int C, int k, int* __restrict__ idx) {
   extern __shared__ float sm[];
   const int Cp = ((C + 3) & ~3) + 4;           // padded query row stride
   float* As = sm;                               // [ROWS][Cp]
@@ -47,6 +47,7 @@ knn_kernel(const float* __restrict__ x, const float* __restrict__ xx, int N, int
   const int Np = (N + KNN_BN - 1) / KNN_BN * KNN_BN;
   const int tiles = (N + ROWS - 1) / ROWS;
   const int part = blockIdx.x / tiles, i0 = (blockIdx.x % tiles) * ROWS;
+  if (valids != nullptr && valids[part] == 0.0f) return;  // padded part: no graph (CTA-uniform)
   const float* xp = x + (long long)part * N * C;
   const float* xxp = xx + (long long)part * N;
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
@@ -223,7 +224,8 @@ __device__ __noinline__ void knn_select_slow(const float* __restrict__ Sr, int N
 }
 
 __global__ void __launch_bounds__(KT_THREADS, 1)
-knn_tile_kernel(const float* __restrict__ x, const float* __restrict__ xx, int n_parts, int N, int C,
+knn_tile_kernel(const float* __restrict__ x, const float* __restrict__ xx,
+                const float* __restrict__ valids, int n_parts, int N, int C,
                 int k, float* __restrict__ scratch, int* __restrict__ idx) {
   extern __shared__ float sm[];
   float* As = sm;                       // [KT_KC][KT]  queries, channel-major
@@ -240,6 +242,7 @@ knn_tile_kernel(const float* __restrict__ x, const float* __restrict__ xx, int n
 
   for (int work = blockIdx.x; work < n_parts * tiles; work += gridDim.x) {
     const int part = work / tiles, i0 = (work % tiles) * KT;
+    if (valids != nullptr && valids[part] == 0.0f) continue;  // padded part (CTA-uniform)
     const float* xp = x + (long long)part * N * C;
     const float* xxp = xx + (long long)part * N;
     float4 pa[4], pb[4];
@@ -393,14 +396,17 @@ knn_tile_kernel(const float* __restrict__ x, const float* __restrict__ xx, int n
 // uv [M, 2*Co] (u | v), idx [M, k] (indices local to the part), M = n*N.
 // One CTA per PTS points, thread = channel.  ymax/ymin [M, Co]; partial [gridDim, Co, 2].
 constexpr int EC_PTS = 8;
-__global__ void edge_aggregate_kernel(const float* __restrict__ uv, const int* __restrict__ idx, long long M,
+__global__ void edge_aggregate_kernel(const float* __restrict__ uv, const int* __restrict__ idx,
+                                      const float* __restrict__ valids, long long M,
                                       int N, int Co, int k, float* __restrict__ ymax,
                                       float* __restrict__ ymin, float* __restrict__ partial) {
   extern __shared__ int sidx[];  // [EC_PTS][k]
   const long long p0 = (long long)blockIdx.x * EC_PTS;
   for (int e = threadIdx.x; e < EC_PTS * k; e += blockDim.x) {
     const long long p = p0 + e / k;
-    sidx[e] = p < M ? idx[p * k + e % k] : 0;
+    // padded parts have no graph (mpa_knn skipped them): never dereference their slots
+    const bool live = p < M && (valids == nullptr || valids[p / N] != 0.0f);
+    sidx[e] = live ? idx[p * k + e % k] : -1;
   }
   __syncthreads();
   const int c = threadIdx.x;
@@ -409,6 +415,11 @@ __global__ void edge_aggregate_kernel(const float* __restrict__ uv, const int* _
     for (int q = 0; q < EC_PTS; ++q) {
       const long long p = p0 + q;
       if (p >= M) break;
+      if (sidx[q * k] < 0) {  // point of a padded part: zero features, no BatchNorm contribution
+        ymax[p * Co + c] = 0.f;
+        ymin[p * Co + c] = 0.f;
+        continue;
+      }
       const long long base = p / N * N;  // first point of this part
       const float v = uv[p * 2 * Co + Co + c];
       float mx = -3.0e38f, mn = 3.0e38f;
@@ -474,8 +485,8 @@ size_t mpa_knn_workspace_bytes(int n, int N) {
          sizeof(float) * (size_t)knn_tile_ctas() * KT * Np;   // per-CTA score slabs (L2-resident)
 }
 
-int mpa_knn(const float* x, int n, int N, int C, int k, int32_t* idx, void* ws, size_t ws_bytes,
-            void* stream_) {
+int mpa_knn(const float* x, const float* valids, int n, int N, int C, int k, int32_t* idx, void* ws,
+            size_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   MPA_CHECK_ARG(n >= 0 && N > 0 && C > 0 && k > 0, "knn: bad sizes n=%d N=%d C=%d k=%d", n, N, C, k);
   MPA_CHECK_ARG(k <= N, "knn: k=%d exceeds the %d points of a part", k, N);
@@ -504,7 +515,7 @@ int mpa_knn(const float* x, int n, int N, int C, int k, int32_t* idx, void* ws, 
     float* slab = (float*)((char*)scratch.base + align_up(sizeof(float) * (size_t)n * N, 256));
     {
       ProfScope ps("knn", stream);
-      knn_tile_kernel<<<ctas, KT_THREADS, KT_SMEM, stream>>>(x, xx, n, N, C, k, slab, idx);
+      knn_tile_kernel<<<ctas, KT_THREADS, KT_SMEM, stream>>>(x, xx, valids, n, N, C, k, slab, idx);
     }
     MPA_LAUNCH_CHECK();
     return MPA_OK;
@@ -524,8 +535,8 @@ int mpa_knn(const float* x, int n, int N, int C, int k, int32_t* idx, void* ws, 
   MPA_CHECK_ARG(smem <= 227 * 1024, "knn: shared memory need %zu exceeds 227 KB", smem);
   {
     ProfScope ps("knn", stream);
-    if (rows == 32) knn_kernel<32><<<n * tiles, KNN_THREADS, smem, stream>>>(x, xx, N, C, k, idx);
-    else knn_kernel<16><<<n * tiles, KNN_THREADS, smem, stream>>>(x, xx, N, C, k, idx);
+    if (rows == 32) knn_kernel<32><<<n * tiles, KNN_THREADS, smem, stream>>>(x, xx, valids, N, C, k, idx);
+    else knn_kernel<16><<<n * tiles, KNN_THREADS, smem, stream>>>(x, xx, valids, N, C, k, idx);
   }
   MPA_LAUNCH_CHECK();
   return MPA_OK;
@@ -537,8 +548,9 @@ size_t mpa_edge_aggregate_workspace_bytes(long long M, int Co) {
          align_up(sizeof(double) * 2 * (size_t)CS_SLICES * Co, 256);
 }
 
-int mpa_edge_aggregate(const float* uv, const int32_t* idx, int n, int N, int Co, int k, float* ymax,
-                       float* ymin, double* sums, void* ws, size_t ws_bytes, void* stream_) {
+int mpa_edge_aggregate(const float* uv, const int32_t* idx, const float* valids, int n, int N, int Co,
+                       int k, float* ymax, float* ymin, double* sums, void* ws, size_t ws_bytes,
+                       void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   MPA_CHECK_ARG(n >= 0 && N > 0 && Co > 0 && Co <= 1024 && k > 0, "edge_aggregate: bad sizes");
   if (n == 0) return MPA_OK;
@@ -553,7 +565,7 @@ int mpa_edge_aggregate(const float* uv, const int32_t* idx, int n, int N, int Co
   {
     ProfScope ps("edge_aggregate", stream);
     edge_aggregate_kernel<<<(unsigned)blocks, threads, sizeof(int) * EC_PTS * k, stream>>>(
-        uv, idx, M, N, Co, k, ymax, ymin, partial);
+        uv, idx, valids, M, N, Co, k, ymax, ymin, partial);
   }
   MPA_LAUNCH_CHECK();
   double* slices = (double*)((char*)scratch.base + align_up(sizeof(float) * 2 * (size_t)blocks * Co, 256));

@@ -248,25 +248,28 @@ def pointnet_forward(x, convs, bns, training, global_feat=True, valids=None):
 # ---------------------------------------------------------------------------
 # DGCNN
 # ---------------------------------------------------------------------------
-def knn(x, k=20):
+def knn(x, k=20, valids=None):
     """x [n, N, C] (points as rows) -> idx [n, N, k] int32, best first
-    (replaces dgcnn.py:8-15; native kernel csrc/knn.cu)."""
+    (replaces dgcnn.py:8-15; native kernel csrc/knn.cu).  `valids` [n]: parts flagged 0
+    are skipped on the device (their rows of idx are zeros)."""
     _lib.require_cuda(x)
     x = x.float().contiguous()
     n, N, C = x.shape
-    idx = torch.empty(n, N, k, dtype=torch.int32, device=x.device)
+    idx = (torch.zeros if valids is not None else torch.empty)(
+        n, N, k, dtype=torch.int32, device=x.device)
     L = _lib.lib()
     ws_bytes = L.mpa_knn_workspace_bytes(n, N)
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=x.device)
     with torch.cuda.device(x.device):
-        rc = L.mpa_knn(_lib.ptr(x), n, N, C, k, _lib.ptr(idx), _lib.ptr(ws), ws_bytes,
-                       _lib.cuda_stream(x.device))
+        rc = L.mpa_knn(_lib.ptr(x), _lib.ptr(valids), n, N, C, k, _lib.ptr(idx), _lib.ptr(ws),
+                       ws_bytes, _lib.cuda_stream(x.device))
     _lib.check(rc, 'mpa_knn')
     return idx
 
 
-def edge_aggregate(uv, idx, n, N, Co, k):
-    """uv [n*N, 2*Co], idx [n, N, k] -> ymax, ymin [n*N, Co], sums [Co, 2] (fp64)."""
+def edge_aggregate(uv, idx, n, N, Co, k, valids=None):
+    """uv [n*N, 2*Co], idx [n, N, k] -> ymax, ymin [n*N, Co], sums [Co, 2] (fp64).
+    `valids` [n]: padded parts give zero rows and stay out of the sums."""
     dev = uv.device
     ymax = torch.empty(n * N, Co, dtype=torch.float32, device=dev)
     ymin = torch.empty_like(ymax)
@@ -275,7 +278,7 @@ def edge_aggregate(uv, idx, n, N, Co, k):
     ws_bytes = L.mpa_edge_aggregate_workspace_bytes(n * N, Co)
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        rc = L.mpa_edge_aggregate(_lib.ptr(uv), _lib.ptr(idx), n, N, Co, k, _lib.ptr(ymax),
+        rc = L.mpa_edge_aggregate(_lib.ptr(uv), _lib.ptr(idx), _lib.ptr(valids), n, N, Co, k, _lib.ptr(ymax),
                                   _lib.ptr(ymin), _lib.ptr(sums), _lib.ptr(ws), ws_bytes,
                                   _lib.cuda_stream(dev))
     _lib.check(rc, 'mpa_edge_aggregate')
@@ -367,12 +370,17 @@ def _dense(x, w, bf16):
 
 def _bn_affine(bn, mean, var_biased, count, training):
     """scale/shift of a BatchNorm from batch moments (training: also updates the
-    running statistics like torch, unbiased variance) or running statistics."""
+    running statistics like torch, unbiased variance) or running statistics.
+    `count` may be a python number or a device scalar (masked batches)."""
     if training:
         with torch.no_grad():
             m = bn.momentum
+            if isinstance(count, torch.Tensor):
+                unbias = count / (count - 1).clamp_min(1)
+            else:
+                unbias = count / max(count - 1, 1)
             bn.running_mean.mul_(1 - m).add_(mean.float(), alpha=m)
-            bn.running_var.mul_(1 - m).add_((var_biased * (count / max(count - 1, 1))).float(), alpha=m)
+            bn.running_var.mul_(1 - m).add_((var_biased * unbias).float(), alpha=m)
             bn.num_batches_tracked += 1
     else:
         mean, var_biased = bn.running_mean.double(), bn.running_var.double()
@@ -380,44 +388,55 @@ def _bn_affine(bn, mean, var_biased, count, training):
     return scale.float(), (bn.bias.double() - mean * scale).float()
 
 
-# tests set this to a list to receive the k-NN graph of every EdgeConv layer
-_DGCNN_TRACE = None
-
-
-def _dgcnn_native(x, m, training, k, bf16):
+def _dgcnn_native(x, m, training, k, bf16, valids=None):
+    """`valids` [n] float (optional): padded parts are skipped by the k-NN / EdgeConv kernels
+    on the device, kept out of every BatchNorm statistic and get zero features -- the
+    semantics of the reference's mask gather + scatter (models/dgl/network.py:90-99)
+    without its host synchronisation."""
     n, N, _ = x.shape
     M = n * N
     h = x.reshape(M, 3).float()
     feats = []
+    nv = None if valids is None else valids.double().sum()  # device scalar: number of valid parts
     for conv, bn in ((m.conv1, m.bn1), (m.conv2, m.bn2), (m.conv3, m.bn3), (m.conv4, m.bn4)):
         C = h.shape[1]
         W = conv[0].weight.reshape(conv[0].weight.shape[0], 2 * C).float()
         Co = W.shape[0]
-        idx = knn(h.view(n, N, C), k)
+        idx = knn(h.view(n, N, C), k, valids)
         if _DGCNN_TRACE is not None:
             _DGCNN_TRACE.append(idx)
         # W [xj - xi ; xi] = W1 xj + (W2 - W1) xi
         wcat = torch.cat([W[:, :C], W[:, C:] - W[:, :C]], dim=0)
         uv = _dense(h, wcat, bf16)
-        ymax, ymin, sums = edge_aggregate(uv, idx, n, N, Co, k)
-        cnt = M * k
+        ymax, ymin, sums = edge_aggregate(uv, idx, n, N, Co, k, valids)
+        cnt = M * k if nv is None else nv * (N * k)
         mean = sums[:, 0] / cnt
         var = (sums[:, 1] / cnt - mean * mean).clamp_min(0)
         scale, shift = _bn_affine(bn, mean, var, cnt, training)
         h = F.leaky_relu(torch.where(scale >= 0, ymax, ymin) * scale + shift, 0.2)
         feats.append(h)
     y = _dense(torch.cat(feats, dim=1), m.conv5[0].weight.reshape(m.conv5[0].weight.shape[0], -1).float(), bf16)
+    cnt5 = M
     if training:
-        var, mean = torch.var_mean(y.double(), dim=0, unbiased=False)
+        if valids is None:
+            var, mean = torch.var_mean(y.double(), dim=0, unbiased=False)
+        else:
+            w = valids.double().repeat_interleave(N).unsqueeze(1)  # [M, 1]
+            cnt5 = nv * N
+            yd = y.double()
+            mean = (yd * w).sum(0) / cnt5
+            var = ((yd * yd * w).sum(0) / cnt5 - mean * mean).clamp_min(0)
     else:
         mean = var = None
-    scale, shift = _bn_affine(m.bn5, mean, var, M, training)
+    scale, shift = _bn_affine(m.bn5, mean, var, cnt5, training)
     y = F.leaky_relu(y * scale + shift, 0.2)
     if not m.global_feat:
-        return y.view(n, N, -1)
+        y = y.view(n, N, -1)
+        return y if valids is None else y * valids.view(n, 1, 1)
     y = y.view(n, N, -1)
     g = torch.cat((y.max(dim=1)[0], y.mean(dim=1)), 1)
-    return F.linear(g, m.out_fc.weight, m.out_fc.bias)
+    out = F.linear(g, m.out_fc.weight, m.out_fc.bias)
+    return out if valids is None else out * valids.view(n, 1)
 
 
 def _graph_feature(x, k):
@@ -451,34 +470,41 @@ class _DGCNNFunction(torch.autograd.Function):
     buffers are restored so the running statistics advance only once."""
 
     @staticmethod
-    def forward(ctx, x, m, training, k, bf16, *params):
-        out = _dgcnn_native(x, m, training, k, bf16)
-        ctx.save_for_backward(x)
+    def forward(ctx, x, valids, m, training, k, bf16, *params):
+        out = _dgcnn_native(x, m, training, k, bf16, valids)
+        ctx.save_for_backward(x, valids if valids is not None else x.new_empty(0))
         ctx.m, ctx.k = m, k
         return out
 
     @staticmethod
     def backward(ctx, grad):
-        (x, ) = ctx.saved_tensors
+        x, valids = ctx.saved_tensors
         m = ctx.m
         buffers = {n_: b.clone() for n_, b in m.named_buffers()}
         params = [p for p in m.parameters()]
+        x = x.detach()
+        if valids.numel():  # the stock formulation has no mask: compact like the reference
+            keep = (valids != 0).nonzero(as_tuple=True)[0]
+            x, grad = x.index_select(0, keep), grad.index_select(0, keep)
         with torch.enable_grad():
-            out = _dgcnn_torch(x.detach(), m, ctx.k)
+            out = _dgcnn_torch(x, m, ctx.k)
             grads = torch.autograd.grad(out, params, grad, allow_unused=True)
         with torch.no_grad():
             for n_, b in m.named_buffers():
                 b.copy_(buffers[n_])
-        return (None, None, None, None, None) + tuple(grads)
+        return (None, None, None, None, None, None) + tuple(grads)
 
 
-def dgcnn_forward(x, m, training, k=20):
-    """x [n, N, 3] -> [n, F] / [n, N, F]; `m` is the DGCNN module."""
+def dgcnn_forward(x, m, training, k=20, valids=None):
+    """x [n, N, 3] -> [n, F] / [n, N, F]; `m` is the DGCNN module; `valids` [n]: padded
+    parts are masked on the device (zero features, outside the BatchNorm statistics)."""
     _lib.require_cuda(x)
     params = [p for p in m.parameters()]
     bf16 = _use_bf16()  # read the autocast state before leaving it
     with torch.autocast('cuda', enabled=False):
-        return _DGCNNFunction.apply(x.float().contiguous(), m, training, k, bf16, *params)
+        return _DGCNNFunction.apply(x.float().contiguous(),
+                                    None if valids is None else valids.float().contiguous(),
+                                    m, training, k, bf16, *params)
 
 
 # ---------------------------------------------------------------------------

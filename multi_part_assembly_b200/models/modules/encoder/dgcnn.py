@@ -30,5 +30,9 @@ class DGCNN(nn.Module):
         if global_feat:
             self.out_fc = nn.Linear(feat_dim * 2, feat_dim)
 
-    def forward(self, x):
-        return kernels.dgcnn_forward(x, self, self.training, self.K)
+    supports_valids = True
+
+    def forward(self, x, valids=None):
+        """x [n, N, 3]; `valids` [n] (extension): parts flagged 0 are masked on the device
+        (zero features, no BatchNorm contribution) instead of being compacted on the host."""
+        return kernels.dgcnn_forward(x, self, self.training, self.K, valids)

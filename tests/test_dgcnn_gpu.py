@@ -97,3 +97,29 @@ def test_knn_clustered_in_few_lanes(cuda):
     got = kernels.knn(torch.from_numpy(np.ascontiguousarray(x)).to(cuda), 20).cpu().numpy().astype(np.int64)
     want = oracle.knn(np.ascontiguousarray(x.transpose(0, 2, 1)), 20)
     np.testing.assert_array_equal(np.sort(got, -1), want)
+
+
+@pytest.mark.parametrize('global_feat', [True, False])
+def test_dgcnn_valids_mask_equals_compaction(cuda, global_feat):
+    """Masking padded parts on the device (`valids`) gives what the reference's gather ->
+    encoder -> scatter gives (models/dgl/network.py:90-99): same features on the valid parts,
+    zeros on the padding, same BatchNorm running statistics -- with no host sync, so the step
+    can be captured in a CUDA graph."""
+    import copy
+    from multi_part_assembly_b200.models import build_encoder
+    enc = fill_params_(build_encoder('dgcnn', 128, global_feat=global_feat), 5).to(cuda).train()
+    ref = copy.deepcopy(enc)
+    g = torch.Generator().manual_seed(11)
+    x = (torch.rand(7, 300, 3, generator=g) - 0.5).to(cuda)
+    valids = torch.tensor([1, 1, 0, 1, 0, 0, 1.], device=cuda)
+    x = x * valids.view(-1, 1, 1)  # padded parts are all-zero clouds, as the dataset pads them
+    keep = valids.bool()
+    with torch.no_grad():
+        got = enc(x, valids=valids)
+        want = ref(x[keep])
+    np.testing.assert_allclose(got[keep].cpu().numpy(), want.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    assert torch.all(got[~keep] == 0)
+    for name in ('bn1', 'bn4', 'bn5'):
+        a, b = getattr(enc, name), getattr(ref, name)
+        np.testing.assert_allclose(a.running_mean.cpu().numpy(), b.running_mean.cpu().numpy(), rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(a.running_var.cpu().numpy(), b.running_var.cpu().numpy(), rtol=1e-5, atol=1e-7)
