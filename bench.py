@@ -1,29 +1,41 @@
 """Benchmark of the B200-native multi_part_assembly hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config B|C|D|E] [--points N]
+                    [--impl native|reference]
 
-Metric (BASELINE.json): shapes/sec of pn_transformer forward + loss on synthetic
-[B=32, P=20 valid parts, N=1000 points] Breaking-Bad-like shapes
-(configs/pn_transformer ... everyday), bf16 autocast for the encoder /
-attention GEMMs, Chamfer and SE(3) always fp32 -- BASELINE config C.
+Metric (BASELINE.json): shapes/sec of forward + loss on synthetic Breaking-Bad-like shapes.
+The default, `--config C`, is the configuration the metric is quoted on (`configs[2]`:
+pn_transformer, B=32 shapes x P=20 valid parts x N=1000 points per GPU, bf16 tensor-core
+GEMMs, Chamfer / SE(3) always fp32).  The other BASELINE.json configs are selectable:
 
-One process per GPU (torchrun for N > 1): every rank steps its own batch of 32
-shapes (weak scaling, no data-path collective -- fwd+loss has none, SURVEY.md
-8e); the timed region is bracketed by barrier + synchronize, timed with CUDA
-events, max over ranks.
+    B  configs[1]  global PointNet encoder model, B=32, 8 valid parts, N=1000      (weak)
+    C  configs[2]  pn_transformer, B=32 per GPU, 20 valid parts, N=1000            (weak)
+    D  configs[3]  dgl + DGCNN (k=20 EdgeConv), B=32 per GPU, 16 valid parts, fp32 (weak)
+    E  configs[4]  pn_transformer, GLOBAL batch 256 split over the ranks,
+                   N = --points in {512, 1000, 2048}                               (strong)
+
+One process per GPU (torchrun for N > 1).  fwd+loss has no data-path collective (SURVEY.md
+8e); the timed region is bracketed by barrier + synchronize, timed with CUDA events, max over
+ranks; `ms_per_step_ranks` lists every rank's own time.
 
 Keys beyond the base contract:
-  roofline     dominant kernel (Chamfer grid search of shape_cd_loss): achieved
-               algorithmic GB/s from CUDA events inside the library
-  cpu_baseline the CPU oracle (port of the reference path) on the host cores
-  e2e          same metric through BaseModel.forward_pass with the batch in
-               pinned HOST memory: H2D of the batch + D2H of the loss per step
-  train_step   secondary figure: forward + loss + backward + gradient
-               all-reduce over the ranks + Adam as one CUDA graph (runtime.GraphedTrainStep),
-               same batch, timed like the headline; `--no-train` skips it
-`--impl reference` times the CPU restatement of the reference path (the
-reference has no CPU Chamfer of its own: chamfer.py:18 asserts CUDA) with all
-host threads on a bounded sample per step.
+  roofline       dominant kernel: algorithmic GB/s from CUDA events inside the library vs the
+                 measured HBM peak (the BASELINE metric), `bound` says what really bounds it
+  roofline_fp32  the same kernel in SURVEY.md 8d's units: candidate pair evaluations per
+                 second vs the FP32 issue peak (37.2e12 slots/s / 9 slots per pair)
+  cpu_baseline   the CPU oracle (port of the reference path) on the host cores
+  e2e            same metric through forward_pass with the batch in pinned HOST memory:
+                 H2D of the batch + D2H of the loss every step
+  reference_gpu_build  (rank 0) the north_star's target denominator: the UNMODIFIED reference
+                 Python + its own Chamfer CUDA kernels built for sm_100a (baseline/_ref),
+                 same batch, same harness, in a child process -- a baseline leg like
+                 cpu_baseline, none of this repo's kernels on it
+  cfg_e_strong   (config C only) cfg E at this N: global batch 256 split over the ranks for
+                 512 / 1000 / 2048 points -- strong scaling = value(N) / value(1)
+  train_step     secondary figure: forward + loss + backward + gradient
+                 all-reduce + Adam as one CUDA graph; `--no-train` skips it
+`--impl reference` times the CPU restatement of the reference path (the reference has no CPU
+Chamfer of its own: chamfer.py:18 asserts CUDA) with all host threads on a bounded sample.
 """
 import argparse
 import json
@@ -37,13 +49,34 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-B_PER_GPU, P, N_PTS = 32, 20, 1000
-WORKLOAD = 'configs[2]: configs/pn_transformer everyday, B=32 x P=20 valid parts x N=1000 pts, fwd+loss'
+P = 20
+CONFIGS = {
+    'B': dict(model='global', encoder='pointnet', batch=32, valid=8, points=1000, dtype='bf16',
+              scaling='weak', ref='configs[1]: configs/global PointNet encoder model'),
+    'C': dict(model='pn_transformer', encoder='pointnet', batch=32, valid=20, points=1000,
+              dtype='bf16', scaling='weak', ref='configs[2]: configs/pn_transformer everyday'),
+    'D': dict(model='dgl', encoder='dgcnn', batch=32, valid=16, points=1000, dtype='f32',
+              scaling='weak', ref='configs[3]: configs/dgl with DGCNN k=20 EdgeConv encoder + GNN'),
+    'E': dict(model='pn_transformer', encoder='pointnet', batch=256, valid=20, points=1000,
+              dtype='bf16', scaling='strong',
+              ref='configs[4]: pn_transformer, global batch 256 split over the ranks'),
+}
+FP32_PAIR_PEAK = 148 * 128 * 1.965e9 / 9.0  # pair evaluations / s at 9 FP32 issue slots each
+
+
+def workload(c, world, points):
+    per = c['batch'] // world if c['scaling'] == 'strong' else c['batch']
+    return (f"{c['ref']}, B={per} per GPU x P={P} slots ({c['valid']} valid) x N={points} pts, "
+            f"fwd+loss")
+
+
+def metric_name(c):
+    return f"shapes_per_sec_{c['model']}_fwd_loss"
 
 
 # --------------------------------------------------------------------------
-def cpu_step(B, seed, threads):
-    """One forward+loss of the CPU oracle on B shapes; returns seconds."""
+def cpu_step(B, seed, threads, points=1000, valid=20):
+    """One forward+loss of the CPU oracle (pn_transformer) on B shapes; returns seconds."""
     import torch
     from oracle import torch_ref, cpu as ocpu
     from oracle.params import fill_params_
@@ -55,7 +88,7 @@ def cpu_step(B, seed, threads):
     if not hasattr(cpu_step, 'sd'):
         model = fill_params_(build_model(get_cfg('pn_transformer')), 0)
         cpu_step.sd = {k: v.detach() for k, v in model.state_dict().items()}
-    batch = make_batch(B, P=P, N=N_PTS, num_valid=P, seed=seed)
+    batch = make_batch(B, P=P, N=points, num_valid=valid, seed=seed)
     t0 = time.perf_counter()
     with torch.no_grad():
         rot, trans = torch_ref.pn_transformer_forward(batch, cpu_step.sd, training=True)
@@ -69,19 +102,25 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
+    c = CONFIGS[args.config]
+    if c['model'] != 'pn_transformer':
+        args.emit({'impl': 'reference', 'unavailable':
+                   f"the CPU port covers pn_transformer (configs C, E); config {args.config} has none"})
+        return
     threads = os.cpu_count() or 1
     Bs = 4  # bounded sample per step
     for i in range(args.warmup):
-        cpu_step(Bs, i, threads)
-    t = [cpu_step(Bs, 100 + i, threads) for i in range(args.steps)]
+        cpu_step(Bs, i, threads, args.points, c['valid'])
+    t = [cpu_step(Bs, 100 + i, threads, args.points, c['valid']) for i in range(args.steps)]
     total = sum(t)
     value = Bs * args.steps / total
     line = {
-        'impl': 'reference', 'metric': 'shapes_per_sec_pn_transformer_fwd_loss', 'value': value,
+        'impl': 'reference', 'metric': metric_name(c), 'value': value,
         'unit': 'shapes/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': 1e3 * total / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'sample': f'{Bs} shapes per step (same P, N)'},
+        'ms_per_step': 1e3 * total / args.steps, 'higher_is_better': True,
+        'scaling': c['scaling'], 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': workload(c, args.gpus, args.points), 'name': args.config,
+                   'sample': f'{Bs} shapes per step (same P, N)'},
         'cpu_baseline': {'value': value, 'unit': 'shapes/s', 'cores': threads, 'kind': 'port',
                          'sample': f'{args.steps} steps x {Bs} shapes, oracle/ C+torch port, '
                                    f'{threads} threads'},
@@ -89,6 +128,92 @@ def run_reference(args):
                 'd2h_bytes_per_step': 0},
     }
     args.emit(line)
+
+
+# --------------------------------------------------------------------------
+def run_reference_gpu(args):
+    """Child-process leg behind `reference_gpu_build`: the unmodified reference package from
+    baseline/_ref (pip-installed copy) with its own chamfer_cuda extension, stock torch kernels
+    everywhere else, same synthetic batch and timing harness as the native arm."""
+    ref = os.path.join(ROOT, 'baseline', '_ref')
+    if not (os.path.exists(os.path.join(ref, 'chamfer_cuda.so')) and
+            os.path.isdir(os.path.join(ref, 'multi_part_assembly'))):
+        args.emit({'unavailable': 'baseline/_ref (reference package + chamfer_cuda.so) not present'})
+        return
+    sys.path.insert(0, ref)
+    import torch
+    from oracle import ref_shims  # third-party stand-ins (pytorch3d / lightning / yacs) only
+    ref_shims.install(root=ref, cuda_chamfer=True)
+    from multi_part_assembly.models import build_model as ref_build_model
+    from multi_part_assembly_b200.configs import get_cfg
+    from multi_part_assembly_b200.datasets import make_batch
+    from multi_part_assembly_b200.compat.lightning import Trainer
+    c = CONFIGS[args.config]
+    dev = torch.device('cuda', args.device)
+    torch.cuda.set_device(dev)
+    B = args.batch or c['batch']
+    cfg = get_cfg(c['model'], 'everyday', encoder=c['encoder'])
+    torch.manual_seed(0)
+    model = ref_build_model(cfg).to(dev).train()
+    model.trainer = Trainer()
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+        if isinstance(m, torch.nn.MultiheadAttention):
+            m.dropout = 0.0
+    batch = make_batch(B, P=P, N=args.points, num_valid=c['valid'], seed=0, device=dev)
+    flush = torch.empty(192 << 20, dtype=torch.uint8, device=dev)
+    out = {'batch': B, 'points': args.points}
+    for name, amp in (('fp32', None), ('fp16', torch.float16)):
+        def step():
+            with torch.no_grad(), torch.autocast('cuda', dtype=amp or torch.float16,
+                                                 enabled=amp is not None):
+                return model.forward_pass(dict(batch), mode='train', optimizer_idx=-1)['loss']
+        try:
+            for _ in range(3):
+                step()
+            ts = []
+            for _ in range(max(5, min(args.steps, 15))):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); step(); b.record(); torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            ts.sort()
+            out[f'{name}_ms_per_step'] = ts[len(ts) // 2]
+        except Exception as e:  # e.g. out of memory for DGCNN at full batch
+            out[f'{name}_error'] = repr(e)[:200]
+            torch.cuda.empty_cache()
+    good = [out[k] for k in ('fp32_ms_per_step', 'fp16_ms_per_step') if k in out]
+    if good:
+        out['ms_per_step'] = min(good)
+        out['value'] = B / min(good) * 1e3
+        out['unit'] = 'shapes/s'
+    out['peak_mem_gib'] = torch.cuda.max_memory_allocated() / 2**30
+    args.emit(out)
+
+
+def reference_gpu_build(config, points, batch, device, steps):
+    """Run the leg above in a child process (a fresh interpreter: the reference package and
+    the product alias cannot share one) and return its JSON."""
+    env = {k: v for k, v in os.environ.items()
+           if k not in ('RANK', 'LOCAL_RANK', 'WORLD_SIZE', 'MASTER_ADDR', 'MASTER_PORT',
+                        'TORCHELASTIC_RUN_ID', 'GROUP_RANK', 'LOCAL_WORLD_SIZE', 'ROLE_RANK')}
+    cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference_gpu', '--config', config,
+           '--points', str(points), '--batch', str(batch), '--device', str(device),
+           '--steps', str(steps)]
+    try:
+        p = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                           timeout=600)
+        lines = [l for l in p.stdout.splitlines() if l.startswith('{')]
+        if p.returncode != 0 or not lines:
+            return {'unavailable': f'child failed (rc {p.returncode}): {p.stderr[-300:]}'}
+        out = json.loads(lines[-1])
+    except Exception as e:
+        return {'unavailable': repr(e)[:300]}
+    out['what'] = ('unmodified reference Python (baseline/_ref) + its chamfer_kernel.cu built for '
+                   'sm_100a + stock torch kernels; forward+loss, no autograd, dropout 0, faster of '
+                   'fp32 / fp16 autocast; same batch and timing harness, child process')
+    return out
 
 
 # --------------------------------------------------------------------------
@@ -137,6 +262,19 @@ class ClockSampler:
                 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
+def no_dropout(model):
+    """Dropout off on both arms for comparability."""
+    import torch
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+        if isinstance(m, torch.nn.MultiheadAttention):
+            m.dropout = 0.0
+        if hasattr(m, 'dropout') and isinstance(m.dropout, float):
+            m.dropout = 0.0
+    return model
+
+
 def run_native(args):
     import torch
     import torch.distributed as dist
@@ -159,35 +297,10 @@ def run_native(args):
         os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')  # stdout carries the one JSON line only
         dist.init_process_group('nccl', device_id=dev)
 
-    torch.manual_seed(rank)
-    cfg = get_cfg('pn_transformer', 'everyday')
-    model = build_model(cfg).to(dev).train()
-    model.trainer = Trainer()
-    for m in model.modules():  # dropout off on both arms for comparability
-        if isinstance(m, torch.nn.Dropout):
-            m.p = 0.0
-        if hasattr(m, 'dropout') and isinstance(m.dropout, float):
-            m.dropout = 0.0
-    host = make_batch(B_PER_GPU, P=P, N=N_PTS, num_valid=P, seed=rank, pin_memory=True)
-    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
-    resident = {k: v.to(dev) for k, v in host.items()}
+    c = CONFIGS[args.config]
+    dtype = args.dtype or c['dtype']
+    amp = torch.bfloat16 if dtype == 'bf16' else None
     flush = torch.empty(192 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-
-    def eager_step(batch):
-        with torch.no_grad():
-            with torch.autocast('cuda', dtype=torch.bfloat16, enabled=args.dtype == 'bf16'):
-                return model.forward_pass(dict(batch), mode='train', optimizer_idx=-1)['loss']
-
-    graphed = None
-    if not args.no_graph:
-        from multi_part_assembly_b200.runtime import GraphedStep
-        graphed = GraphedStep(model, resident, mode='train',
-                              autocast_dtype=torch.bfloat16 if args.dtype == 'bf16' else None)
-
-    def step(batch):
-        if graphed is not None:
-            return graphed(batch)['loss']
-        return eager_step(batch)
 
     def barrier():
         torch.cuda.synchronize()
@@ -208,8 +321,55 @@ def run_native(args):
         barrier()
         return sum(s.elapsed_time(e) for s, e in zip(starts, stops))
 
+    def max_over_ranks(values):
+        """(max over ranks, per-rank lists) of a few host floats."""
+        t = torch.tensor(values, dtype=torch.float64, device=dev)
+        if world == 1:
+            return list(values), [[v] for v in values]
+        allv = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allv, t)
+        stack = torch.stack(allv)  # [world, len]
+        return stack.max(0)[0].tolist(), stack.t().tolist()
+
+    def setup(model_name, encoder, per_gpu, valid, points, seed):
+        """Model + pinned host batches + the stepping functions for one workload."""
+        torch.manual_seed(seed)
+        cfg = get_cfg(model_name, 'everyday', encoder=encoder)
+        model = no_dropout(build_model(cfg)).to(dev).train()
+        model.trainer = Trainer()
+        hosts = [make_batch(per_gpu, P=P, N=points, num_valid=valid, seed=seed + 1000 * i,
+                            pin_memory=True) for i in range(2)]
+        resident = {k: v.to(dev) for k, v in hosts[0].items()}
+
+        def eager_step(batch):
+            with torch.no_grad():
+                with torch.autocast('cuda', dtype=torch.bfloat16, enabled=amp is not None):
+                    return model.forward_pass(dict(batch), mode='train', optimizer_idx=-1)['loss']
+
+        graphed, graph_error = None, None
+        if not args.no_graph:
+            from multi_part_assembly_b200.runtime import GraphedStep
+            try:
+                graphed = GraphedStep(model, resident, mode='train', autocast_dtype=amp)
+            except Exception as e:  # a host sync inside the step: fall back to eager launches
+                graph_error = repr(e)[:200]
+                torch.cuda.synchronize()
+
+        def step():
+            return graphed()['loss'] if graphed is not None else eager_step(resident)
+
+        return dict(model=model, hosts=hosts, resident=resident, eager_step=eager_step,
+                    graphed=graphed, graph_error=graph_error, step=step, per_gpu=per_gpu)
+
+    per_gpu = c['batch'] // world if c['scaling'] == 'strong' else c['batch']
+    assert per_gpu >= 1, 'more ranks than shapes'
+    w = setup(c['model'], c['encoder'], per_gpu, c['valid'], args.points, rank)
+    model, hosts, resident, graphed = w['model'], w['hosts'], w['resident'], w['graphed']
+    eager_step, step, graph_error = w['eager_step'], w['step'], w['graph_error']
+    h2d_bytes = sum(v.numel() * v.element_size() for v in hosts[0].values())
+
     for _ in range(args.warmup):
-        step(None if graphed is not None else resident)
+        step()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -218,16 +378,12 @@ def run_native(args):
     launches_per_step = _lib.launch_count() - l0  # a graph replay issues the same kernel nodes
     torch.cuda.synchronize()
     # inputs already resident in HBM (the graph's static input buffers / `resident`)
-    ms_total = timed(lambda: step(None if graphed is not None else resident), args.steps)
+    ms_total = timed(step, args.steps)
     launches = launches_per_step * args.steps
 
-    # e2e: pinned host batch -> device, forward_pass, loss back to the host
     # e2e: every step copies ITS batch from pinned host memory and reads its loss back.
     # With the graph runtime the copy of batch k+1 is issued before step k runs (input
     # prefetch on a side stream, as a data loader does), so it overlaps the compute.
-    host2 = make_batch(B_PER_GPU, P=P, N=N_PTS, num_valid=P, seed=rank + 1000, pin_memory=True)
-    host_batches = [host, host2]
-
     def e2e_loop(steps):
         """K end-to-end steps; returns the summed CUDA-event time of the steps."""
         starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
@@ -236,12 +392,12 @@ def run_native(args):
         if graphed is not None:
             flush.zero_()
             starts[0].record()
-            graphed.prefetch(host_batches[0])
+            graphed.prefetch(hosts[0])
             for i in range(steps):
                 out = graphed.run_prefetched()
                 if i + 1 < steps:
-                    graphed.prefetch(host_batches[(i + 1) % 2])  # next batch's H2D overlaps this step
-                loss = float(out['loss'])                          # D2H of this step's result
+                    graphed.prefetch(hosts[(i + 1) % 2])  # next batch's H2D overlaps this step
+                float(out['loss'])                         # D2H of this step's result
                 stops[i].record()
                 if i + 1 < steps:
                     flush.zero_()
@@ -250,8 +406,8 @@ def run_native(args):
             for i in range(steps):
                 flush.zero_()
                 starts[i].record()
-                batch = {k: v.to(dev, non_blocking=True) for k, v in host_batches[i % 2].items()}
-                loss = float(eager_step(batch))
+                batch = {k: v.to(dev, non_blocking=True) for k, v in hosts[i % 2].items()}
+                float(eager_step(batch))
                 stops[i].record()
         barrier()
         return sum(s.elapsed_time(e) for s, e in zip(starts, stops))
@@ -261,26 +417,27 @@ def run_native(args):
     clocks = sampler.stop() if rank == 0 else None
 
     # roofline of the dominant kernel: same steps with the library's per-kernel events on
+    n_prof = min(args.steps, 10)
     profiler.enable(True)
-    for _ in range(min(args.steps, 10)):
+    for _ in range(n_prof):
         flush.zero_()
         eager_step(resident)  # eager: the library's event pairs cannot be recorded inside a graph
     torch.cuda.synchronize()
     prof = profiler.report()
     profiler.enable(False)
+    pair_stats = profiler.pair_stats(lambda: eager_step(resident)) \
+        if hasattr(profiler, 'pair_stats') else None
 
-    # secondary figure: the whole training step -- forward, loss, backward,
-    # gradient all-reduce over the ranks (the path's one collective), Adam -- as one CUDA graph
+    # secondary figure: the whole training step as one CUDA graph
     train = None
     ms_train = 0.0
-    if not args.no_train:
+    if not args.no_train and c['model'] == 'pn_transformer':
         try:
             from multi_part_assembly_b200.runtime import GraphedTrainStep
             opt = model.configure_optimizers()
             if isinstance(opt, tuple):
                 opt = opt[0][0]
-            gts = GraphedTrainStep(model, opt, resident,
-                                   autocast_dtype=torch.bfloat16 if args.dtype == 'bf16' else None)
+            gts = GraphedTrainStep(model, opt, resident, autocast_dtype=amp)
             k_train = max(3, min(args.steps, 50))
             for _ in range(3):
                 gts()
@@ -291,13 +448,32 @@ def run_native(args):
             train = {'error': repr(e)[:300]}
             torch.cuda.synchronize()
 
-    t = torch.tensor([ms_total, ms_e2e, ms_train], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e, ms_train = t.tolist()
+    # cfg E at this N (strong scaling): global batch 256 split over the ranks, three cloud sizes
+    strong = None
+    strong_ms = []
+    if args.config == 'C' and not args.no_extra and 256 % world == 0:
+        strong = []
+        k_e = max(5, min(args.steps, 30))
+        for pts in (512, 1000, 2048):
+            we = setup('pn_transformer', 'pointnet', 256 // world, 20, pts, rank)
+            for _ in range(3):
+                we['step']()
+            strong_ms.append(timed(we['step'], k_e) / k_e)
+            strong.append({'points': pts, 'global_batch': 256, 'batch_per_gpu': 256 // world,
+                           'steps': k_e, 'cuda_graph': we['graphed'] is not None})
+            del we
+            torch.cuda.empty_cache()
+
+    mx, per_rank = max_over_ranks([ms_total, ms_e2e, ms_train] + strong_ms)
+    ms_total, ms_e2e, ms_train = mx[:3]
     if train is not None and 'error' not in train:
         train['ms_per_step'] = ms_train / train['steps']
-        train['shapes_per_s'] = B_PER_GPU * world * train['steps'] / (ms_train / 1e3)
+        train['shapes_per_s'] = per_gpu * world * train['steps'] / (ms_train / 1e3)
+    if strong is not None:
+        for e, ms, ranks in zip(strong, mx[3:], per_rank[3:]):
+            e['ms_per_step'] = ms
+            e['ms_per_step_ranks'] = ranks
+            e['shapes_per_s'] = 256 / (ms / 1e3)
     if world > 1:
         # last collective done.  The captured graphs hold NCCL resources and tearing the
         # process group down around them can block: ranks leave without the teardown.
@@ -308,7 +484,7 @@ def run_native(args):
     if rank != 0:
         return
 
-    shapes = B_PER_GPU * world * args.steps
+    shapes = per_gpu * world * args.steps
     value = shapes / (ms_total / 1e3)
     peaks = {}
     try:
@@ -317,55 +493,90 @@ def run_native(args):
         pass
     hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
     dom = max(prof.items(), key=lambda kv: kv[1]['ms_total'])[0] if prof else None
-    roof = None
+    roof, roof32 = None, None
     if dom is not None:
         d = prof[dom]
         avg_ms = d['ms_total'] / d['launches']
-        # algorithmic bytes of one shape-level Chamfer launch: 24 B per point of both
-        # clouds (12 read + 4 dist + 8 idx as the reference writes them), SURVEY.md 8d
-        alg_bytes = d.get('alg_bytes_per_launch', 24.0 * B_PER_GPU * 2 * P * N_PTS)
+        n_clouds = per_gpu * 2 * P * args.points  # points of both clouds of one Chamfer call
+        # algorithmic bytes of one Chamfer launch: 24 B per point of both clouds (12 read +
+        # 4 dist + 8 idx as the reference writes them), SURVEY.md 8d
+        alg_bytes = 24.0 * n_clouds
         achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
-        # DRAM bytes of one launch of that kernel from the committed `ncu --set full` capture
         traffic = None
-        try:
-            tr = json.load(open(os.path.join(ROOT, 'profiles', 'r01_ncu_traffic.json'))).get(dom)
-            if tr is not None:
-                traffic = tr['dram_bytes_read'] + tr['dram_bytes_write']
+        try:  # DRAM bytes of one launch of that kernel from the committed `ncu --set full` capture
+            for name in ('r02_ncu_traffic.json', 'r01_ncu_traffic.json'):
+                path = os.path.join(ROOT, 'profiles', name)
+                if os.path.exists(path):
+                    tr = json.load(open(path)).get(dom)
+                    if tr is not None:
+                        traffic = tr['dram_bytes_read'] + tr['dram_bytes_write']
+                        break
         except (OSError, ValueError, KeyError):
             pass
-        roof = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': hbm_peak,
+        is_search = dom.startswith('chamfer')
+        step_ms = sum(v['ms_total'] for v in prof.values()) / n_prof
+        roof = {'bound': 'fp32-issue/latency (not hbm: see roofline_fp32)' if is_search else 'hbm',
+                'kernel': dom, 'achieved': achieved, 'peak': hbm_peak,
                 'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': traffic,
-                'avg_launch_ms': avg_ms, 'share_of_step': d['ms_total'] / sum(
-                    v['ms_total'] for v in prof.values()),
+                'avg_launch_ms': avg_ms,
+                'share_of_summed_kernel_time': d['ms_total'] / sum(v['ms_total'] for v in prof.values()),
+                'summed_kernel_ms_per_step': step_ms,
                 'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback 6650 GB/s',
-                'note': 'the search is paced by lane divergence and L2/L1 load latency, not by HBM '
-                        '(DESIGN.md 4a); HBM-bound kernels of the path: the BatchNorm passes of the '
-                        'PointNet backward (35-60 % of peak, DESIGN.md 4)',
-                'kernels_ms_per_step': {k: v['ms_total'] / min(args.steps, 10) for k, v in prof.items()}}
+                'note': 'algorithmic bytes = 24 B x points of both clouds (SURVEY.md 8d); the exact '
+                        'search is bounded by FP32 issue / load latency, so the HBM fraction is '
+                        'small by construction; kernels on parallel graph branches overlap, so '
+                        'summed kernel time exceeds the step',
+                'kernels_ms_per_step': {k: v['ms_total'] / n_prof for k, v in prof.items()}}
+        if is_search and pair_stats and pair_stats.get(dom):
+            pairs = pair_stats[dom]  # candidate pairs actually evaluated by one launch
+            brute = float(per_gpu) * (P * args.points) ** 2 * 2 if dom.endswith('shape') else \
+                float(per_gpu * P) * args.points ** 2 * 2
+            rate = pairs / (avg_ms * 1e-3)
+            roof32 = {'bound': 'fp32-issue', 'kernel': dom, 'achieved': rate,
+                      'peak': FP32_PAIR_PEAK, 'unit': 'pair-evals/s', 'frac': rate / FP32_PAIR_PEAK,
+                      'pairs_evaluated_per_launch': pairs, 'brute_force_pairs_per_launch': brute,
+                      'pruning_factor': brute / max(pairs, 1.0),
+                      'brute_force_equivalent_rate': brute / (avg_ms * 1e-3),
+                      'peak_source': '148 SMs x 128 lanes x 1.965 GHz / 9 issue slots per pair '
+                                     '(SURVEY.md 8d)'}
 
     threads = os.cpu_count() or 1
-    cpu_B = 8
-    cpu_step(2, 0, threads)
-    cpu_t = cpu_step(cpu_B, 1, threads)
+    cpu = None
+    if c['model'] == 'pn_transformer':
+        cpu_B = 8
+        cpu_step(2, 0, threads, args.points)
+        cpu_t = cpu_step(cpu_B, 1, threads, args.points)
+        cpu = {'value': cpu_B / cpu_t, 'unit': 'shapes/s', 'cores': threads, 'kind': 'port',
+               'sample': f'1 step of {cpu_B} shapes (same P, N), oracle/ C+torch port'}
+    ref_gpu = None
+    if not args.no_extra:
+        ref_gpu = reference_gpu_build(args.config, args.points, per_gpu, local_rank, 15)
+        if 'value' in ref_gpu:
+            ref_gpu['native_over_reference'] = (per_gpu / (ms_total / args.steps) * 1e3) / ref_gpu['value']
     line = {
-        'metric': 'shapes_per_sec_pn_transformer_fwd_loss', 'value': value, 'unit': 'shapes/s',
+        'metric': metric_name(c), 'value': value, 'unit': 'shapes/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'batch_per_gpu': B_PER_GPU, 'parts': P, 'points': N_PTS,
+        'ms_per_step': ms_total / args.steps,
+        'ms_per_step_ranks': [v / args.steps for v in per_rank[0]],
+        'higher_is_better': True, 'scaling': c['scaling'],
+        'vs_baseline': None, 'dtype': dtype, 'data': 'synthetic',
+        'config': {'workload': workload(c, world, args.points), 'name': args.config,
+                   'batch_per_gpu': per_gpu, 'global_batch': per_gpu * world, 'parts': P,
+                   'valid_parts': c['valid'], 'points': args.points,
                    'l2': 'flushed (192 MiB memset) before every timed step',
                    'mode': 'training-mode forward (BatchNorm batch statistics) + all loss terms, '
                            'no autograd recording, dropout 0',
-                   'cuda_graph': graphed is not None},
+                   'cuda_graph': graphed is not None, 'graph_error': graph_error},
         'clocks': clocks,
         'e2e': {'value': shapes / (ms_e2e / 1e3), 'unit': 'shapes/s',
                 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4},
         'gpu_launches': launches,
         'train_step': train,
         'roofline': roof,
-        'cpu_baseline': {'value': cpu_B / cpu_t, 'unit': 'shapes/s', 'cores': threads,
-                         'kind': 'port',
-                         'sample': f'1 step of {cpu_B} shapes (same P, N), oracle/ C+torch port'},
+        'roofline_fp32': roof32,
+        'cpu_baseline': cpu,
+        'reference_gpu_build': ref_gpu,
+        'cfg_e_strong': strong,
     }
     args.emit(line)
     if world > 1:
@@ -378,11 +589,19 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=300)
     ap.add_argument('--warmup', type=int, default=10)
-    ap.add_argument('--impl', default='native', choices=['native', 'reference'])
-    ap.add_argument('--dtype', default='bf16', choices=['bf16', 'f32'])
+    ap.add_argument('--impl', default='native', choices=['native', 'reference', 'reference_gpu'])
+    ap.add_argument('--config', default='C', choices=sorted(CONFIGS))
+    ap.add_argument('--points', type=int, default=None, help='points per part (config E sweep)')
+    ap.add_argument('--dtype', default=None, choices=['bf16', 'f32'])
+    ap.add_argument('--batch', type=int, default=0, help=argparse.SUPPRESS)
+    ap.add_argument('--device', type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument('--no-graph', action='store_true', help='eager launches instead of a CUDA graph')
     ap.add_argument('--no-train', action='store_true', help='skip the secondary training-step figure')
+    ap.add_argument('--no-extra', action='store_true',
+                    help='skip the reference-GPU-build leg and the cfg E strong-scaling sweep')
     args = ap.parse_args()
+    if args.points is None:
+        args.points = CONFIGS[args.config]['points']
     args.warmup = max(args.warmup, 3) if args.impl == 'native' else args.warmup
     # stdout carries exactly one JSON line: while the benchmark runs, file descriptor 1 points
     # at stderr, so that banners printed by libraries (NCCL prints its version to stdout on
@@ -400,6 +619,8 @@ def main():
     args.emit = emit
     if args.impl == 'reference':
         run_reference(args)
+    elif args.impl == 'reference_gpu':
+        run_reference_gpu(args)
     else:
         run_native(args)
 
