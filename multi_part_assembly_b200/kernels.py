@@ -388,6 +388,10 @@ def _bn_affine(bn, mean, var_biased, count, training):
     return scale.float(), (bn.bias.double() - mean * scale).float()
 
 
+# tests set this to a list to receive the k-NN graph of every EdgeConv layer
+_DGCNN_TRACE = None
+
+
 def _dgcnn_native(x, m, training, k, bf16, valids=None):
     """`valids` [n] float (optional): padded parts are skipped by the k-NN / EdgeConv kernels
     on the device, kept out of every BatchNorm statistic and get zero features -- the

@@ -117,7 +117,7 @@ def test_dgcnn_valids_mask_equals_compaction(cuda, global_feat):
     with torch.no_grad():
         got = enc(x, valids=valids)
         want = ref(x[keep])
-    np.testing.assert_allclose(got[keep].cpu().numpy(), want.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(got[keep].cpu().numpy(), want.cpu().numpy(), rtol=1e-4, atol=2e-5)
     assert torch.all(got[~keep] == 0)
     for name in ('bn1', 'bn4', 'bn5'):
         a, b = getattr(enc, name), getattr(ref, name)
