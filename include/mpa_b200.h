@@ -54,6 +54,13 @@ void mpa_profile_enable(int on);
 size_t mpa_profile_report(char* buf, size_t cap);
 
 /* ---- Chamfer distance -------------------------------------------------- */
+/* Instrumentation for bench.py's roofline_fp32 (SURVEY.md 8d asks for pair evaluations per
+ * second next to the GB/s figure): on != 0 switches the exact grid searches to an instantiation
+ * that counts the candidate pairs it evaluates; out[3] (nullable) receives and clears the
+ * counters of the current device {per-part pose search, shape-level pose search, plain clouds}.
+ * No reference counterpart. */
+int mpa_chamfer_pair_count(int on, unsigned long long* out);
+
 /* Replaces chamfer_cuda.chamfer_forward (utils/chamfer/cuda/chamfer.cpp:8-11,21;
  * ChamferForward, chamfer_kernel.cu:116-168).
  *   xyz1 [B,N1,3], xyz2 [B,N2,3] contiguous fp32

@@ -24,6 +24,7 @@ _SIGNATURES = {
     'mpa_launch_count': (ctypes.c_uint64, []),
     'mpa_profile_enable': (None, [c_int]),
     'mpa_profile_report': (c_size_t, [ctypes.c_char_p, c_size_t]),
+    'mpa_chamfer_pair_count': (c_int, [c_int, c_void_p]),
     'mpa_chamfer_forward_workspace_bytes': (c_size_t, [c_int] * 4),
     'mpa_chamfer_forward': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int,
                                     c_void_p, c_void_p, c_void_p, c_void_p,

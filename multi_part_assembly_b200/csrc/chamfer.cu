@@ -133,7 +133,40 @@ struct CloudDesc {
 
 constexpr int GRID_MAX_DIM = 38;  // 38^3+1 ints = 214 KB of shared memory in the build kernel
 constexpr int MAX_FAR = 64;  // >= max parts per shape
-constexpr int CB = 4;        // cells per axis of a coarse block (second grid level)
+
+// Occupancy pyramid over the cell grid (second stage of the search): level L >= 1 holds, per
+// node of (2^L)^3 cells, the number of targets inside.  Level dimensions follow the host-side
+// cell budget `dmax` (D[L] = ceil(dmax / 2^L) per axis), not the actual grid, so that every
+// cloud of a launch shares one layout; nodes beyond the actual grid hold 0.
+constexpr int PYR_MAX_LEVELS = 8;
+struct PyrLayout {
+  int top;                  // root level: D[top] == 1
+  int D[PYR_MAX_LEVELS];    // nodes per axis at level L (D[0] = dmax, unused)
+  int off[PYR_MAX_LEVELS];  // offset of level L in a cloud's pyramid (off[0] unused)
+  int stride;               // ints per cloud
+};
+static PyrLayout make_pyr_layout(int dmax) {
+  PyrLayout p;
+  p.D[0] = dmax;
+  p.off[0] = 0;
+  int o = 0, L = 0;
+  while (p.D[L] > 1 && L + 1 < PYR_MAX_LEVELS) {
+    ++L;
+    p.D[L] = (p.D[L - 1] + 1) / 2;
+    p.off[L] = o;
+    o += p.D[L] * p.D[L] * p.D[L];
+  }
+  if (L == 0) {  // a single cell: still give the search a root above it
+    L = 1;
+    p.D[1] = 1;
+    p.off[1] = 0;
+    o = 1;
+  }
+  p.top = L;
+  for (int l = L + 1; l < PYR_MAX_LEVELS; ++l) { p.D[l] = 1; p.off[l] = 0; }
+  p.stride = o;
+  return p;
+}
 
 __device__ __forceinline__ int cell_coord(float x, float o, float inv_h, int dim) {
   int c = (int)floorf((x - o) * inv_h);
@@ -177,7 +210,7 @@ template <typename IdxT>
 __global__ void grid_build_kernel(CloudDesc c0, CloudDesc c1, int S, float4* __restrict__ sorted0,
                                   float4* __restrict__ sorted1, int* __restrict__ cell_start,
                                   int cs_stride, GridParams* __restrict__ params,
-                                  float4* __restrict__ far, float4* __restrict__ reps, int cb_stride,
+                                  float4* __restrict__ far, int* pyr_base, PyrLayout pl,
                                   float* dist0, IdxT* idx0, float* dist1, IdxT* idx1) {
   extern __shared__ int cnt[];
   __shared__ float red[6][32];
@@ -370,21 +403,42 @@ __global__ void grid_build_kernel(CloudDesc c0, CloudDesc c1, int S, float4* __r
   }
   __syncthreads();
 
-  // ---- coarse level: one representative target per block of 4x4x4 cells (w = -1: empty) ----
+  // ---- occupancy pyramid (cnt[] now holds the cell ENDS): level 1 from the cells, each
+  // further level from the one below (global memory written by this CTA, made visible to
+  // it by __syncthreads) ----
   {
-    const int bx = (g.dx + CB - 1) / CB, by = (g.dy + CB - 1) / CB, bz = (g.dz + CB - 1) / CB;
-    float4* rp = reps + (long long)(cloud * S + seg) * cb_stride;
-    for (int cb = tid; cb < bx * by * bz; cb += blockDim.x) {
-      const int x0 = (cb % bx) * CB, y0 = ((cb / bx) % by) * CB, z0 = (cb / (bx * by)) * CB;
-      const int x1 = min(x0 + CB, g.dx), y1 = min(y0 + CB, g.dy), z1 = min(z0 + CB, g.dz);
-      int first = -1;
-      for (int zc = z0; zc < z1 && first < 0; ++zc)
-        for (int yc = y0; yc < y1 && first < 0; ++yc) {
-          const int row = (zc * g.dy + yc) * g.dx;
-          const int a = row + x0 == 0 ? 0 : cnt[row + x0 - 1];  // cursors now hold the cell ends
-          if (cnt[row + x1 - 1] > a) first = a;
+    int* pyr = pyr_base + (long long)(cloud * S + seg) * pl.stride;
+    {
+      const int D = pl.D[1];
+      int* lv = pyr + pl.off[1];
+      for (int i = tid; i < D * D * D; i += blockDim.x) {
+        const int x = i % D, y = (i / D) % D, z = i / (D * D);
+        int sum = 0;
+        const int xa = 2 * x, xb = min(2 * x + 1, g.dx - 1);
+        if (xa < g.dx) {
+          for (int zc = 2 * z; zc <= min(2 * z + 1, g.dz - 1); ++zc)
+            for (int yc = 2 * y; yc <= min(2 * y + 1, g.dy - 1); ++yc) {
+              const int row = (zc * g.dy + yc) * g.dx;
+              sum += cnt[row + xb] - (row + xa == 0 ? 0 : cnt[row + xa - 1]);
+            }
         }
-      rp[cb] = first >= 0 ? __ldcg(&sorted[first]) : make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+        lv[i] = sum;
+      }
+    }
+    for (int L = 2; L <= pl.top; ++L) {
+      __syncthreads();
+      const int D = pl.D[L], Dc = pl.D[L - 1];
+      const int* lc = pyr + pl.off[L - 1];
+      int* lv = pyr + pl.off[L];
+      for (int i = tid; i < D * D * D; i += blockDim.x) {
+        const int x = i % D, y = (i / D) % D, z = i / (D * D);
+        int sum = 0;
+        for (int zc = 2 * z; zc <= min(2 * z + 1, Dc - 1); ++zc)
+          for (int yc = 2 * y; yc <= min(2 * y + 1, Dc - 1); ++yc)
+            for (int xc = 2 * x; xc <= min(2 * x + 1, Dc - 1); ++xc)
+              sum += lc[(zc * Dc + yc) * Dc + xc];
+        lv[i] = sum;
+      }
     }
   }
 }
@@ -447,7 +501,7 @@ struct NNQuery {
   GridParams g;                   // target grid
   const float4* __restrict__ T;   // targets in cell order
   const int* __restrict__ cs;     // cell starts
-  const float4* __restrict__ R;   // block representatives
+  const int* __restrict__ pyr;    // occupancy pyramid of the target grid
   const float4* __restrict__ F;   // far candidates (padded parts)
   long long out;                  // output slot
   int cx, cy, cz;
@@ -460,8 +514,8 @@ __device__ __forceinline__ NNQuery nn_setup(long long gid, const float4* __restr
                                             const int* __restrict__ cell_start, int cs_stride,
                                             const GridParams* __restrict__ params,
                                             const float4* __restrict__ far,
-                                            const float4* __restrict__ reps, int cb_stride, int S, int N0,
-                                            int N1) {
+                                            const int* __restrict__ pyr_base, int pyr_stride, int S,
+                                            int N0, int N1) {
   NNQuery c;
   c.valid = false;
   const long long wg = gid >> 5;
@@ -483,7 +537,7 @@ __device__ __forceinline__ NNQuery nn_setup(long long gid, const float4* __restr
   c.q = (c.dir1 ? sorted1 : sorted0)[(long long)seg * NQ + i];
   c.T = (c.dir1 ? sorted0 : sorted1) + (long long)seg * NT;
   c.cs = cell_start + (long long)(tc * S + seg) * cs_stride;
-  c.R = reps + (long long)(tc * S + seg) * cb_stride;
+  c.pyr = pyr_base + (long long)(tc * S + seg) * pyr_stride;
   c.F = far + (long long)(tc * S + seg) * MAX_FAR;
   c.out = (long long)seg * NQ + __float_as_int(c.q.w);
   const GridParams& g = c.g;
@@ -496,87 +550,76 @@ __device__ __forceinline__ NNQuery nn_setup(long long gid, const float4* __restr
   return c;
 }
 
-// phase E: two-level search over blocks of CB^3 cells (see the kernel comment)
-__device__ __forceinline__ void nn_block_search(const NNQuery& c, float& best, int& bidx) {
+// phase E: best-first descent of the occupancy pyramid (see the kernel comment).  Depth-first
+// with an explicit stack (local memory, <= 7 pending siblings per level); the children of a
+// node are pushed farthest first in the XOR order of the child nearest to the query, so the
+// nearest one is opened next.  A node is dropped only if the squared distance to its box
+// (after the fp32 slack) is STRICTLY larger than `best`, or if it holds no target.
+constexpr int PYR_STACK = 7 * (PYR_MAX_LEVELS - 1) + 2;
+
+// squared gap between q and the slab [cc << L, min((cc + 1) << L, dim)) of cells along one axis
+__device__ __forceinline__ float axis_gap2(float q, float o, float h, int cc, int L, int dim,
+                                           float slack) {
+  const int c0 = cc << L;
+  if (c0 >= dim) return __int_as_float(0x7f800000);  // outside the grid: never opened
+  const float lo = o + (float)c0 * h, hi = o + (float)min((cc + 1) << L, dim) * h;
+  const float gpos = fmaxf(fmaxf(lo - q, q - hi) - slack, 0.f);
+  return gpos * gpos;
+}
+
+template <bool COUNT>
+__device__ __forceinline__ void nn_pyramid_search(const NNQuery& c, const PyrLayout& pl, float& best,
+                                                  int& bidx, unsigned& ncand) {
   const GridParams& g = c.g;
   const float4 q = c.q;
   const float4* __restrict__ T = c.T;
   const int* __restrict__ cs = c.cs;
-  const float4* __restrict__ R = c.R;
+  const int* __restrict__ pyr = c.pyr;
   const int cx = c.cx, cy = c.cy, cz = c.cz;
   const float slack = c.slack;
-  const float inf = __int_as_float(0x7f800000);
-  {
-    // ---- E: (sparse regions, queries outside the target cloud) two-level search ----
-    // over blocks of CB^3 cells: one representative point per occupied block gives an
-    // upper bound in a converged loop; the nearest block is opened first, then every
-    // block whose box is not strictly farther than `best`.
-    {
-      const int bx = (g.dx + CB - 1) / CB, by = (g.dy + CB - 1) / CB, bz = (g.dz + CB - 1) / CB;
-      const int ncb = bx * by * bz;
-      float rbest = inf;
-      int rcb = -1;
-      for (int cb = 0; cb < ncb; ++cb) {
-        const float4 t = __ldg(R + cb);
-        if (__float_as_int(t.w) < 0) continue;
-        const float d = sqdist_ref(q.x, q.y, q.z, t.x, t.y, t.z);
-        if (d < rbest) { rbest = d; rcb = cb; }
-        if (d <= best) {
-          const int ti = __float_as_int(t.w);
-          if (d < best || ti < bidx) { best = d; bidx = ti; }
-        }
+  int stack[PYR_STACK];
+  int sp = 0;
+  stack[sp++] = pl.top << 18;  // the root
+  while (sp > 0) {
+    const int e = stack[--sp];
+    const int L = e >> 18, z = (e >> 12) & 63, y = (e >> 6) & 63, x = e & 63;
+    if (L == 0) {  // a cell; those of the 3x3x3 block were handled (scanned or pruned) in A-C
+      if (x >= cx - 1 && x <= cx + 1 && y >= cy - 1 && y <= cy + 1 && z >= cz - 1 && z <= cz + 1) continue;
+      const float lb = axis_gap2(q.x, g.ox, g.h, x, 0, g.dx, slack) + axis_gap2(q.y, g.oy, g.h, y, 0, g.dy, slack) +
+                       axis_gap2(q.z, g.oz, g.h, z, 0, g.dz, slack);
+      if (lb > best) continue;  // `best` may have improved since the push
+      const int ci = (z * g.dy + y) * g.dx + x;
+      const int s0 = cs[ci], s1 = cs[ci + 1];
+      if (COUNT) ncand += (unsigned)(s1 - s0);
+      scan_range(T, s0, s1, q.x, q.y, q.z, best, bidx);
+      continue;
+    }
+    const int Lc = L - 1;
+    // squared gaps to the two halves of the node along every axis
+    const float gx0 = axis_gap2(q.x, g.ox, g.h, 2 * x, Lc, g.dx, slack);
+    const float gx1 = axis_gap2(q.x, g.ox, g.h, 2 * x + 1, Lc, g.dx, slack);
+    const float gy0 = axis_gap2(q.y, g.oy, g.h, 2 * y, Lc, g.dy, slack);
+    const float gy1 = axis_gap2(q.y, g.oy, g.h, 2 * y + 1, Lc, g.dy, slack);
+    const float gz0 = axis_gap2(q.z, g.oz, g.h, 2 * z, Lc, g.dz, slack);
+    const float gz1 = axis_gap2(q.z, g.oz, g.h, 2 * z + 1, Lc, g.dz, slack);
+    if (fminf(gx0, gx1) + fminf(gy0, gy1) + fminf(gz0, gz1) > best) continue;  // whole node out of reach
+    const int near = (gx1 < gx0 ? 1 : 0) | (gy1 < gy0 ? 2 : 0) | (gz1 < gz0 ? 4 : 0);
+    const int Dc = pl.D[Lc];
+    const int* __restrict__ lv = pyr + pl.off[Lc];
+#pragma unroll
+    for (int o = 7; o >= 0; --o) {  // farthest first: the nearest child ends on top of the stack
+      const int b = o ^ near;
+      const int xc = 2 * x + (b & 1), yc = 2 * y + ((b >> 1) & 1), zc = 2 * z + (b >> 2);
+      const float lb = ((b & 1) ? gx1 : gx0) + ((b & 2) ? gy1 : gy0) + ((b & 4) ? gz1 : gz0);
+      if (lb > best) continue;  // also drops children outside the grid (infinite gap)
+      int occ;
+      if (Lc == 0) {
+        const int ci = (zc * g.dy + yc) * g.dx + xc;
+        occ = cs[ci + 1] - cs[ci];
+      } else {
+        occ = lv[(zc * Dc + yc) * Dc + xc];
       }
-      // open one block: rows pruned by their slab distance, x range clipped to the reach left
-      auto open_block = [&](int cbx, int cby, int cbz) {
-        const int x0 = cbx * CB, y0 = cby * CB, z0 = cbz * CB;
-        const int x1 = min(x0 + CB, g.dx) - 1, y1 = min(y0 + CB, g.dy) - 1, z1 = min(z0 + CB, g.dz) - 1;
-        for (int zc = z0; zc <= z1; ++zc) {
-          const float lz = fmaxf(fmaxf((g.oz + (float)zc * g.h) - q.z, q.z - (g.oz + (float)(zc + 1) * g.h)) - slack, 0.f);
-          if (lz * lz > best) continue;
-          for (int yc = y0; yc <= y1; ++yc) {
-            const float ly = fmaxf(fmaxf((g.oy + (float)yc * g.h) - q.y, q.y - (g.oy + (float)(yc + 1) * g.h)) - slack, 0.f);
-            const float rem = best - (ly * ly + lz * lz);  // squared x-reach left
-            if (rem < 0.f) continue;
-            int xa = x0, xb = x1;
-            if (best < 1e30f) {
-              const float rad = sqrtf(rem) * 1.00001f + slack;
-              xa = max(xa, cell_coord(q.x - rad, g.ox, g.inv_h, g.dx));
-              xb = min(xb, cell_coord(q.x + rad, g.ox, g.inv_h, g.dx));
-            }
-            if (xa > xb) continue;
-            const int row = (zc * g.dy + yc) * g.dx;
-            const bool seen = zc >= cz - 1 && zc <= cz + 1 && yc >= cy - 1 && yc <= cy + 1;
-            if (!seen) {
-              scan_range(T, cs[row + xa], cs[row + xb + 1], q.x, q.y, q.z, best, bidx);
-            } else {  // cells cx-1..cx+1 of this row were handled (scanned or pruned) in A-C
-              const int l1 = min(xb, cx - 2), r0 = max(xa, cx + 2);
-              if (xa <= l1) scan_range(T, cs[row + xa], cs[row + l1 + 1], q.x, q.y, q.z, best, bidx);
-              if (r0 <= xb) scan_range(T, cs[row + r0], cs[row + xb + 1], q.x, q.y, q.z, best, bidx);
-            }
-          }
-        }
-      };
-      if (rcb >= 0) open_block(rcb % bx, (rcb / bx) % by, rcb / (bx * by));
-      // lower bound of the distance to a block's box, per axis (0 inside its slab)
-      for (int cbz = 0; cbz < bz; ++cbz) {
-        const float bzl = fmaxf(fmaxf((g.oz + (float)(cbz * CB) * g.h) - q.z,
-                                      q.z - (g.oz + (float)min(cbz * CB + CB, g.dz) * g.h)) - slack, 0.f);
-        if (bzl * bzl > best) continue;  // strictly farther: cannot win or tie
-        for (int cby = 0; cby < by; ++cby) {
-          const float byl = fmaxf(fmaxf((g.oy + (float)(cby * CB) * g.h) - q.y,
-                                        q.y - (g.oy + (float)min(cby * CB + CB, g.dy) * g.h)) - slack, 0.f);
-          const float yz = byl * byl + bzl * bzl;
-          if (yz > best) continue;
-          for (int cbx = 0; cbx < bx; ++cbx) {
-            const float bxl = fmaxf(fmaxf((g.ox + (float)(cbx * CB) * g.h) - q.x,
-                                          q.x - (g.ox + (float)min(cbx * CB + CB, g.dx) * g.h)) - slack, 0.f);
-            if (bxl * bxl + yz > best) continue;
-            const int cb = (cbz * by + cby) * bx + cbx;
-            if (cb == rcb || __float_as_int(__ldg(R + cb).w) < 0) continue;
-            open_block(cbx, cby, cbz);
-          }
-        }
-      }
+      if (occ > 0) stack[sp++] = (Lc << 18) | (zc << 12) | (yc << 6) | xc;
     }
   }
 }
@@ -597,14 +640,15 @@ __device__ __forceinline__ void nn_finish(const NNQuery& c, float best, int bidx
 #ifndef MPA_NN_MIN_CTAS
 #define MPA_NN_MIN_CTAS 4
 #endif
-template <typename IdxT>
+template <typename IdxT, bool COUNT>
 __global__ void __launch_bounds__(NN_THREADS, MPA_NN_MIN_CTAS)
 grid_nn_kernel(const float4* __restrict__ sorted0, const float4* __restrict__ sorted1,
                const int* __restrict__ cell_start, int cs_stride,
                const GridParams* __restrict__ params, const float4* __restrict__ far,
-               const float4* __restrict__ reps, int cb_stride, int S,
+               const int* __restrict__ pyr_base, const PyrLayout pl, int S,
                int N0, int N1, float* __restrict__ dist0, IdxT* __restrict__ idx0,
-               float* __restrict__ dist1, IdxT* __restrict__ idx1) {
+               float* __restrict__ dist1, IdxT* __restrict__ idx1,
+               unsigned long long* __restrict__ pair_counter) {
   __shared__ int rs[NN_RANGES][NN_THREADS], re[NN_RANGES][NN_THREADS];
   __shared__ float rl[NN_RANGES][NN_THREADS];  // squared distance to each noted range's slab
   __shared__ int hq[3][NN_THREADS];  // round-2 queue: lane, best (bits), bidx
@@ -613,9 +657,10 @@ grid_nn_kernel(const float4* __restrict__ sorted0, const float4* __restrict__ so
   if (tid == 0) n_hard = 0;
   __syncthreads();
   const long long gid0 = (long long)blockIdx.x * NN_THREADS;
+  unsigned ncand = 0;  // candidate pairs this lane evaluated (COUNT instantiation only)
   {
-    const NNQuery c = nn_setup(gid0 + tid, sorted0, sorted1, cell_start, cs_stride, params, far, reps,
-                               cb_stride, S, N0, N1);
+    const NNQuery c = nn_setup(gid0 + tid, sorted0, sorted1, cell_start, cs_stride, params, far, pyr_base,
+                               pl.stride, S, N0, N1);
     if (c.valid) {
       const GridParams& g = c.g;
       const float4 q = c.q;
@@ -640,6 +685,7 @@ grid_nn_kernel(const float4* __restrict__ sorted0, const float4* __restrict__ so
 
         // ---- A: own cell ----
         const int c0 = (cz * g.dy + cy) * g.dx + cx;
+        if (COUNT) ncand += (unsigned)(cs[c0 + 1] - cs[c0]);
         scan_range(T, cs[c0], cs[c0 + 1], q.x, q.y, q.z, best, bidx);
         // ---- B: which other cells of the 3x3x3 block can still matter (nearest rows first) ----
         int nr = 0;
@@ -672,6 +718,7 @@ grid_nn_kernel(const float4* __restrict__ sorted0, const float4* __restrict__ so
               if (rl[k][tid] > best) continue;
               p = rs[k][tid];
               e = re[k][tid];
+              if (COUNT) ncand += (unsigned)(e - p);
               continue;
             }
             const float4 t0 = __ldg(T + p);
@@ -724,12 +771,16 @@ grid_nn_kernel(const float4* __restrict__ sorted0, const float4* __restrict__ so
   }
   __syncthreads();
   if (tid < n_hard) {
-    const NNQuery c = nn_setup(gid0 + hq[0][tid], sorted0, sorted1, cell_start, cs_stride, params, far, reps,
-                               cb_stride, S, N0, N1);
+    const NNQuery c = nn_setup(gid0 + hq[0][tid], sorted0, sorted1, cell_start, cs_stride, params, far,
+                               pyr_base, pl.stride, S, N0, N1);
     float best = __int_as_float(hq[1][tid]);
     int bidx = hq[2][tid];
-    nn_block_search(c, best, bidx);
+    nn_pyramid_search<COUNT>(c, pl, best, bidx, ncand);
     nn_finish<IdxT>(c, best, bidx, dist0, idx0, dist1, idx1);
+  }
+  if (COUNT) {
+    const unsigned long long w = (unsigned long long)__reduce_add_sync(0xffffffffu, ncand);
+    if ((tid & 31) == 0 && w) atomicAdd(pair_counter, w);
   }
 }
 
@@ -785,9 +836,28 @@ static int pick_dmax(int n) {
   return d;
 }
 
+// ---- optional instrumentation (bench.py roofline_fp32): candidate pairs evaluated ----
+// One device counter per launch kind (0 per-part pose search, 1 shape-level, 2 plain clouds),
+// allocated on first use on the current device; enabled by mpa_chamfer_pair_count(1, ...).
+static std::atomic<int> g_pair_count_on{0};
+static unsigned long long* g_pair_counters[64] = {nullptr};
+static bool pair_count_enabled() { return g_pair_count_on.load(std::memory_order_relaxed) != 0; }
+static unsigned long long* pair_counter_device(int which) {
+  const int d = current_device() & 63;
+  if (g_pair_counters[d] == nullptr) {
+    if (cudaMalloc((void**)&g_pair_counters[d], 3 * sizeof(unsigned long long)) != cudaSuccess) {
+      set_error("pair counter: cudaMalloc failed");
+      return nullptr;
+    }
+    cudaMemset(g_pair_counters[d], 0, 3 * sizeof(unsigned long long));
+  }
+  return g_pair_counters[d] + which;
+}
+
 struct GridLayout {
-  size_t off_params, off_far, off_reps, off_cs, off_sorted0, off_sorted1, total;
-  int cs_stride, cb_stride;
+  size_t off_params, off_far, off_pyr, off_cs, off_sorted0, off_sorted1, total;
+  int cs_stride;
+  PyrLayout pyr;
 };
 
 static GridLayout grid_layout(int S, int N0, int N1) {
@@ -797,9 +867,8 @@ static GridLayout grid_layout(int S, int N0, int N1) {
   size_t o = 0;
   L.off_params = o; o = align_up(o + sizeof(GridParams) * 2 * (size_t)S, 256);
   L.off_far = o; o = align_up(o + sizeof(float4) * 2 * (size_t)S * MAX_FAR, 256);
-  const int db = (d + CB - 1) / CB;
-  L.cb_stride = db * db * db;
-  L.off_reps = o; o = align_up(o + sizeof(float4) * 2 * (size_t)S * L.cb_stride, 256);
+  L.pyr = make_pyr_layout(d);
+  L.off_pyr = o; o = align_up(o + sizeof(int) * 2 * (size_t)S * L.pyr.stride, 256);
   L.off_cs = o; o = align_up(o + sizeof(int) * 2 * (size_t)S * L.cs_stride, 256);
   L.off_sorted0 = o; o = align_up(o + sizeof(float4) * (size_t)S * (N0 > 0 ? N0 : 1), 256);
   L.off_sorted1 = o; o = align_up(o + sizeof(float4) * (size_t)S * (N1 > 0 ? N1 : 1), 256);
@@ -817,7 +886,7 @@ static int run_grid(CloudDesc c0, CloudDesc c1, int S, float* dist0, IdxT* idx0,
   char* base = (char*)scratch.base;
   GridParams* params = (GridParams*)(base + L.off_params);
   float4* far = (float4*)(base + L.off_far);
-  float4* reps = (float4*)(base + L.off_reps);
+  int* pyr = (int*)(base + L.off_pyr);
   int* cs = (int*)(base + L.off_cs);
   float4* s0 = (float4*)(base + L.off_sorted0);
   float4* s1 = (float4*)(base + L.off_sorted1);
@@ -850,7 +919,7 @@ static int run_grid(CloudDesc c0, CloudDesc c1, int S, float* dist0, IdxT* idx0,
   {
     ProfScope ps(c0.fill_invalid ? "chamfer_grid_build_shape" : (c0.quat ? "chamfer_grid_build_part" : "chamfer_grid_build"), stream);
     grid_build_kernel<IdxT><<<2 * S, threads, smem, stream>>>(c0, c1, S, s0, s1, cs, L.cs_stride,
-                                                              params, far, reps, L.cb_stride, dist0, idx0,
+                                                              params, far, pyr, L.pyr, dist0, idx0,
                                                               dist1, idx1);
   }
   MPA_LAUNCH_CHECK();
@@ -858,10 +927,19 @@ static int run_grid(CloudDesc c0, CloudDesc c1, int S, float* dist0, IdxT* idx0,
   const long long blocks = (warps + 7) / 8;
   if (blocks > 0) {
     {
+      const int which_counter = c0.fill_invalid ? 1 : (c0.quat ? 0 : 2);
       ProfScope ps(c0.fill_invalid ? "chamfer_grid_nn_shape" : (c0.quat ? "chamfer_grid_nn_part" : "chamfer_grid_nn"), stream);
-      grid_nn_kernel<IdxT><<<(unsigned)blocks, 256, 0, stream>>>(
-          s0, s1, cs, L.cs_stride, params, far, reps, L.cb_stride, S, c0.Nseg, c1.Nseg, dist0, idx0, dist1,
-          idx1);
+      if (pair_count_enabled()) {
+        unsigned long long* ctr = pair_counter_device(which_counter);
+        if (ctr == nullptr) return MPA_ERR_CUDA;
+        grid_nn_kernel<IdxT, true><<<(unsigned)blocks, 256, 0, stream>>>(
+            s0, s1, cs, L.cs_stride, params, far, pyr, L.pyr, S, c0.Nseg, c1.Nseg, dist0, idx0, dist1, idx1,
+            ctr);
+      } else {
+        grid_nn_kernel<IdxT, false><<<(unsigned)blocks, 256, 0, stream>>>(
+            s0, s1, cs, L.cs_stride, params, far, pyr, L.pyr, S, c0.Nseg, c1.Nseg, dist0, idx0, dist1, idx1,
+            nullptr);
+      }
     }
     MPA_LAUNCH_CHECK();
   }
@@ -879,6 +957,21 @@ static bool use_grid(int algo, int N1, int N2) {
 using namespace mpa;
 
 extern "C" {
+
+/* Instrumentation: on != 0 makes the grid searches count the candidate pairs they evaluate
+ * (slower instantiation); out[3] (nullable) receives and clears the counters of the current
+ * device: {per-part pose search, shape-level pose search, plain clouds}.  Synchronises. */
+int mpa_chamfer_pair_count(int on, unsigned long long* out) {
+  g_pair_count_on.store(on ? 1 : 0);
+  if (out != nullptr) {
+    unsigned long long* ctr = pair_counter_device(0);
+    if (ctr == nullptr) return MPA_ERR_CUDA;
+    MPA_CUDA(cudaDeviceSynchronize());
+    MPA_CUDA(cudaMemcpy(out, ctr, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    MPA_CUDA(cudaMemset(ctr, 0, 3 * sizeof(unsigned long long)));
+  }
+  return MPA_OK;
+}
 
 size_t mpa_chamfer_forward_workspace_bytes(int B, int N1, int N2, int algo) {
   if (B <= 0 || N1 <= 0 || N2 <= 0) return 0;

@@ -127,6 +127,32 @@ def test_pose_chamfer_shape_mode(cuda, B, P, N, n_valid):
         assert np.all(g[~m] == (0 if g.dtype == np.float32 else -1))
 
 
+@pytest.mark.parametrize('spread', [0.0, 0.02, 3.0])
+def test_pose_chamfer_blob_vs_spread(cuda, spread):
+    """The distribution the benchmark feeds the search: an untrained model puts
+    every part under nearly the same pose (a dense blob of 20 000 points) while the ground truth
+    is spread over a box several times larger, so ~40 % of the ground-truth queries lie far
+    outside the target grid and take the pyramid descent.  spread = 3: clouds that do not
+    overlap at all (every query is a far query).  Bit-exact vs the brute-force oracle."""
+    B, P, N = 2, 20, 1000
+    pts, valids, q1, t1, q2, t2 = _pose_inputs(B, P, N, [20, 13], 23)
+    rng = np.random.default_rng(5)
+    base = _rand_quat(rng, (B, 1))
+    q1 = base + 0.03 * rng.standard_normal((B, P, 4)).astype(np.float32)
+    q1 = (q1 / np.linalg.norm(q1, axis=-1, keepdims=True)).astype(np.float32)
+    t1 = (0.2 + 0.02 * rng.standard_normal((B, P, 3)) + spread).astype(np.float32)
+    if spread == 0.0:
+        t1[:] = 0.25  # all predicted translations identical
+    got = _pose_chamfer_gpu(pts, valids, q1, t1, q2, t2, 1, cuda)
+    filled = pts.copy(); filled[valids == 0] = 1e3
+    p1 = oracle.se3_transform(q1, t1, filled); p2 = oracle.se3_transform(q2, t2, filled)
+    e1, j1, e2, j2 = oracle.chamfer_forward(p1.reshape(B, P * N, 3), p2.reshape(B, P * N, 3))
+    m = np.repeat(valids.reshape(B, P, 1), N, 2).reshape(B, P * N) == 1
+    for g, e in ((got['d1'], e1), (got['d2'], e2), (got['i1'], j1), (got['i2'], j2)):
+        g = g.reshape(B, P * N)
+        np.testing.assert_array_equal(g[m], e[m].astype(g.dtype))
+
+
 def test_shape_mode_far_part_can_win(cuda):
     """A valid query that sits next to a padded part's 1e3 point must report it,
     exactly as the reference's brute force would."""
