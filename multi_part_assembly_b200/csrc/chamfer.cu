@@ -211,7 +211,8 @@ __global__ void grid_build_kernel(CloudDesc c0, CloudDesc c1, int S, float4* __r
                                   float4* __restrict__ sorted1, int* __restrict__ cell_start,
                                   int cs_stride, GridParams* __restrict__ params,
                                   float4* __restrict__ far, int* pyr_base, PyrLayout pl,
-                                  float* dist0, IdxT* idx0, float* dist1, IdxT* idx1) {
+                                  int* hard_count, float* dist0, IdxT* idx0, float* dist1,
+                                  IdxT* idx1) {
   extern __shared__ int cnt[];
   __shared__ float red[6][32];
   __shared__ double redm[6][32];
@@ -231,6 +232,7 @@ __global__ void grid_build_kernel(CloudDesc c0, CloudDesc c1, int S, float4* __r
   const bool has_valid = c.valids != nullptr;
 
   if (tid == 0) { s_count = 0; s_nfar = 0; }
+  if (blockIdx.x == 0 && tid == 0) *hard_count = 0;  // the search kernels' append list starts empty
   __syncthreads();
 
   // ---- pass 1: bbox of the valid points, transformed output, zero-fill ----
@@ -634,9 +636,11 @@ __device__ __forceinline__ void nn_finish(const NNQuery& c, float best, int bidx
   if (io != nullptr) io[c.out] = (IdxT)bidx;
 }
 
-// Round 1: every lane runs A-D for its own query.  Queries that need phase E are
-// queued in shared memory and re-dealt to the first lanes of the CTA in round 2, so
-// the (long, divergent) block search runs in full warps instead of a few lanes each.
+// Kernel 1: every lane runs A-D for its own query.  Queries that need phase E are appended
+// to a global list (one atomic per warp, no CTA barrier: the CTA leaves as soon as its
+// slowest easy query is done) and kernel 2 (`grid_nn_hard_kernel`) deals them out densely,
+// 32 per warp, to a persistent grid -- the long, divergent pyramid descent neither idles the
+// lanes of easy queries nor holds their CTA slots.
 #ifndef MPA_NN_MIN_CTAS
 #define MPA_NN_MIN_CTAS 4
 #endif
@@ -648,16 +652,16 @@ grid_nn_kernel(const float4* __restrict__ sorted0, const float4* __restrict__ so
                const int* __restrict__ pyr_base, const PyrLayout pl, int S,
                int N0, int N1, float* __restrict__ dist0, IdxT* __restrict__ idx0,
                float* __restrict__ dist1, IdxT* __restrict__ idx1,
+               int* __restrict__ hard_count, int4* __restrict__ hard_list,
                unsigned long long* __restrict__ pair_counter) {
   __shared__ int rs[NN_RANGES][NN_THREADS], re[NN_RANGES][NN_THREADS];
   __shared__ float rl[NN_RANGES][NN_THREADS];  // squared distance to each noted range's slab
-  __shared__ int hq[3][NN_THREADS];  // round-2 queue: lane, best (bits), bidx
-  __shared__ int n_hard;
   const int tid = threadIdx.x;
-  if (tid == 0) n_hard = 0;
-  __syncthreads();
   const long long gid0 = (long long)blockIdx.x * NN_THREADS;
   unsigned ncand = 0;  // candidate pairs this lane evaluated (COUNT instantiation only)
+  bool hard = false;
+  float hbest = 0.f;
+  int hbidx = -1;
   {
     const NNQuery c = nn_setup(gid0 + tid, sorted0, sorted1, cell_start, cs_stride, params, far, pyr_base,
                                pl.stride, S, N0, N1);
@@ -761,27 +765,55 @@ grid_nn_kernel(const float4* __restrict__ sorted0, const float4* __restrict__ so
       }
       if (done) {
         nn_finish<IdxT>(c, best, bidx, dist0, idx0, dist1, idx1);
-      } else {  // queue for round 2
-        const int slot = atomicAdd(&n_hard, 1);
-        hq[0][slot] = tid;
-        hq[1][slot] = __float_as_int(best);
-        hq[2][slot] = bidx;
+      } else {
+        hard = true;
+        hbest = best;
+        hbidx = bidx;
       }
     }
   }
-  __syncthreads();
-  if (tid < n_hard) {
-    const NNQuery c = nn_setup(gid0 + hq[0][tid], sorted0, sorted1, cell_start, cs_stride, params, far,
-                               pyr_base, pl.stride, S, N0, N1);
-    float best = __int_as_float(hq[1][tid]);
-    int bidx = hq[2][tid];
-    nn_pyramid_search<COUNT>(c, pl, best, bidx, ncand);
-    nn_finish<IdxT>(c, best, bidx, dist0, idx0, dist1, idx1);
+  // warp-aggregated append of the unfinished queries (all lanes reconverge here)
+  {
+    const unsigned m = __ballot_sync(0xffffffffu, hard);
+    if (m != 0u) {
+      const int lane = tid & 31;
+      int base = 0;
+      if (lane == 0) base = atomicAdd(hard_count, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (hard)
+        hard_list[base + __popc(m & ((1u << lane) - 1u))] =
+            make_int4((int)(gid0 + tid), __float_as_int(hbest), hbidx, 0);
+    }
   }
   if (COUNT) {
     const unsigned long long w = (unsigned long long)__reduce_add_sync(0xffffffffu, ncand);
     if ((tid & 31) == 0 && w) atomicAdd(pair_counter, w);
   }
+}
+
+// Kernel 2: phase E for the queries kernel 1 could not finish, 32 per warp.
+constexpr int NNH_THREADS = 128;
+template <typename IdxT, bool COUNT>
+__global__ void __launch_bounds__(NNH_THREADS)
+grid_nn_hard_kernel(const float4* __restrict__ sorted0, const float4* __restrict__ sorted1,
+                    const int* __restrict__ cell_start, int cs_stride,
+                    const GridParams* __restrict__ params, const float4* __restrict__ far,
+                    const int* __restrict__ pyr_base, const PyrLayout pl, int S, int N0, int N1,
+                    float* __restrict__ dist0, IdxT* __restrict__ idx0, float* __restrict__ dist1,
+                    IdxT* __restrict__ idx1, const int* __restrict__ hard_count,
+                    const int4* __restrict__ hard_list, unsigned long long* __restrict__ pair_counter) {
+  const int n = *hard_count;
+  unsigned ncand = 0;
+  for (int i = blockIdx.x * NNH_THREADS + threadIdx.x; i < n; i += gridDim.x * NNH_THREADS) {
+    const int4 h = hard_list[i];
+    const NNQuery c = nn_setup((long long)h.x, sorted0, sorted1, cell_start, cs_stride, params, far, pyr_base,
+                               pl.stride, S, N0, N1);
+    float best = __int_as_float(h.y);
+    int bidx = h.z;
+    nn_pyramid_search<COUNT>(c, pl, best, bidx, ncand);
+    nn_finish<IdxT>(c, best, bidx, dist0, idx0, dist1, idx1);
+  }
+  if (COUNT && ncand) atomicAdd(pair_counter, (unsigned long long)ncand);
 }
 
 // ======================================================================
@@ -855,7 +887,7 @@ static unsigned long long* pair_counter_device(int which) {
 }
 
 struct GridLayout {
-  size_t off_params, off_far, off_pyr, off_cs, off_sorted0, off_sorted1, total;
+  size_t off_params, off_far, off_pyr, off_cs, off_sorted0, off_sorted1, off_hard, total;
   int cs_stride;
   PyrLayout pyr;
 };
@@ -872,6 +904,9 @@ static GridLayout grid_layout(int S, int N0, int N1) {
   L.off_cs = o; o = align_up(o + sizeof(int) * 2 * (size_t)S * L.cs_stride, 256);
   L.off_sorted0 = o; o = align_up(o + sizeof(float4) * (size_t)S * (N0 > 0 ? N0 : 1), 256);
   L.off_sorted1 = o; o = align_up(o + sizeof(float4) * (size_t)S * (N1 > 0 ? N1 : 1), 256);
+  // counter (first 256 bytes) + one int4 per query of either direction (worst case: all unfinished)
+  const size_t nq = (size_t)S * ((size_t)((N0 + 31) / 32) + (size_t)((N1 + 31) / 32)) * 32;
+  L.off_hard = o; o = align_up(o + 256 + sizeof(int4) * nq, 256);
   L.total = o;
   return L;
 }
@@ -890,6 +925,8 @@ static int run_grid(CloudDesc c0, CloudDesc c1, int S, float* dist0, IdxT* idx0,
   int* cs = (int*)(base + L.off_cs);
   float4* s0 = (float4*)(base + L.off_sorted0);
   float4* s1 = (float4*)(base + L.off_sorted1);
+  int* hard_count = (int*)(base + L.off_hard);
+  int4* hard_list = (int4*)(base + L.off_hard + 256);
   c0.dmax = pick_dmax(c0.Nseg);
   c1.dmax = pick_dmax(c1.Nseg);
   {
@@ -919,8 +956,8 @@ static int run_grid(CloudDesc c0, CloudDesc c1, int S, float* dist0, IdxT* idx0,
   {
     ProfScope ps(c0.fill_invalid ? "chamfer_grid_build_shape" : (c0.quat ? "chamfer_grid_build_part" : "chamfer_grid_build"), stream);
     grid_build_kernel<IdxT><<<2 * S, threads, smem, stream>>>(c0, c1, S, s0, s1, cs, L.cs_stride,
-                                                              params, far, pyr, L.pyr, dist0, idx0,
-                                                              dist1, idx1);
+                                                              params, far, pyr, L.pyr, hard_count, dist0,
+                                                              idx0, dist1, idx1);
   }
   MPA_LAUNCH_CHECK();
   const long long warps = (long long)S * ((c0.Nseg + 31) / 32 + (c1.Nseg + 31) / 32);
@@ -929,17 +966,25 @@ static int run_grid(CloudDesc c0, CloudDesc c1, int S, float* dist0, IdxT* idx0,
     {
       const int which_counter = c0.fill_invalid ? 1 : (c0.quat ? 0 : 2);
       ProfScope ps(c0.fill_invalid ? "chamfer_grid_nn_shape" : (c0.quat ? "chamfer_grid_nn_part" : "chamfer_grid_nn"), stream);
+      const int hard_ctas = num_sms() * 8;  // persistent: 8 CTAs of 128 threads per SM
       if (pair_count_enabled()) {
         unsigned long long* ctr = pair_counter_device(which_counter);
         if (ctr == nullptr) return MPA_ERR_CUDA;
         grid_nn_kernel<IdxT, true><<<(unsigned)blocks, 256, 0, stream>>>(
             s0, s1, cs, L.cs_stride, params, far, pyr, L.pyr, S, c0.Nseg, c1.Nseg, dist0, idx0, dist1, idx1,
-            ctr);
+            hard_count, hard_list, ctr);
+        grid_nn_hard_kernel<IdxT, true><<<hard_ctas, NNH_THREADS, 0, stream>>>(
+            s0, s1, cs, L.cs_stride, params, far, pyr, L.pyr, S, c0.Nseg, c1.Nseg, dist0, idx0, dist1, idx1,
+            hard_count, hard_list, ctr);
       } else {
         grid_nn_kernel<IdxT, false><<<(unsigned)blocks, 256, 0, stream>>>(
             s0, s1, cs, L.cs_stride, params, far, pyr, L.pyr, S, c0.Nseg, c1.Nseg, dist0, idx0, dist1, idx1,
-            nullptr);
+            hard_count, hard_list, nullptr);
+        grid_nn_hard_kernel<IdxT, false><<<hard_ctas, NNH_THREADS, 0, stream>>>(
+            s0, s1, cs, L.cs_stride, params, far, pyr, L.pyr, S, c0.Nseg, c1.Nseg, dist0, idx0, dist1, idx1,
+            hard_count, hard_list, nullptr);
       }
+      count_launch();
     }
     MPA_LAUNCH_CHECK();
   }
