@@ -232,7 +232,7 @@ __global__ void grid_build_kernel(CloudDesc c0, CloudDesc c1, int S, float4* __r
   const bool has_valid = c.valids != nullptr;
 
   if (tid == 0) { s_count = 0; s_nfar = 0; }
-  if (blockIdx.x == 0 && tid == 0) *hard_count = 0;  // the search kernels' append list starts empty
+  if (blockIdx.x == 0 && tid == 0) { hard_count[0] = 0; hard_count[1] = 0; }  // append list + its read cursor
   __syncthreads();
 
   // ---- pass 1: bbox of the valid points, transformed output, zero-fill ----
@@ -569,60 +569,54 @@ __device__ __forceinline__ float axis_gap2(float q, float o, float h, int cc, in
   return gpos * gpos;
 }
 
+// one stack entry: scan a cell or expand a node (pushes <= 8 children)
 template <bool COUNT>
-__device__ __forceinline__ void nn_pyramid_search(const NNQuery& c, const PyrLayout& pl, float& best,
-                                                  int& bidx, unsigned& ncand) {
+__device__ __forceinline__ void nn_pyramid_step(const NNQuery& c, const PyrLayout& pl, int* stack, int& sp,
+                                                float& best, int& bidx, unsigned& ncand) {
   const GridParams& g = c.g;
   const float4 q = c.q;
-  const float4* __restrict__ T = c.T;
   const int* __restrict__ cs = c.cs;
-  const int* __restrict__ pyr = c.pyr;
-  const int cx = c.cx, cy = c.cy, cz = c.cz;
   const float slack = c.slack;
-  int stack[PYR_STACK];
-  int sp = 0;
-  stack[sp++] = pl.top << 18;  // the root
-  while (sp > 0) {
-    const int e = stack[--sp];
-    const int L = e >> 18, z = (e >> 12) & 63, y = (e >> 6) & 63, x = e & 63;
-    if (L == 0) {  // a cell; those of the 3x3x3 block were handled (scanned or pruned) in A-C
-      if (x >= cx - 1 && x <= cx + 1 && y >= cy - 1 && y <= cy + 1 && z >= cz - 1 && z <= cz + 1) continue;
-      const float lb = axis_gap2(q.x, g.ox, g.h, x, 0, g.dx, slack) + axis_gap2(q.y, g.oy, g.h, y, 0, g.dy, slack) +
-                       axis_gap2(q.z, g.oz, g.h, z, 0, g.dz, slack);
-      if (lb > best) continue;  // `best` may have improved since the push
-      const int ci = (z * g.dy + y) * g.dx + x;
-      const int s0 = cs[ci], s1 = cs[ci + 1];
-      if (COUNT) ncand += (unsigned)(s1 - s0);
-      scan_range(T, s0, s1, q.x, q.y, q.z, best, bidx);
-      continue;
-    }
-    const int Lc = L - 1;
-    // squared gaps to the two halves of the node along every axis
-    const float gx0 = axis_gap2(q.x, g.ox, g.h, 2 * x, Lc, g.dx, slack);
-    const float gx1 = axis_gap2(q.x, g.ox, g.h, 2 * x + 1, Lc, g.dx, slack);
-    const float gy0 = axis_gap2(q.y, g.oy, g.h, 2 * y, Lc, g.dy, slack);
-    const float gy1 = axis_gap2(q.y, g.oy, g.h, 2 * y + 1, Lc, g.dy, slack);
-    const float gz0 = axis_gap2(q.z, g.oz, g.h, 2 * z, Lc, g.dz, slack);
-    const float gz1 = axis_gap2(q.z, g.oz, g.h, 2 * z + 1, Lc, g.dz, slack);
-    if (fminf(gx0, gx1) + fminf(gy0, gy1) + fminf(gz0, gz1) > best) continue;  // whole node out of reach
-    const int near = (gx1 < gx0 ? 1 : 0) | (gy1 < gy0 ? 2 : 0) | (gz1 < gz0 ? 4 : 0);
-    const int Dc = pl.D[Lc];
-    const int* __restrict__ lv = pyr + pl.off[Lc];
+  const int e = stack[--sp];
+  const int L = e >> 18, z = (e >> 12) & 63, y = (e >> 6) & 63, x = e & 63;
+  if (L == 0) {  // a cell; those of the 3x3x3 block were handled (scanned or pruned) in A-C
+    if (x >= c.cx - 1 && x <= c.cx + 1 && y >= c.cy - 1 && y <= c.cy + 1 && z >= c.cz - 1 && z <= c.cz + 1)
+      return;
+    const float lb = axis_gap2(q.x, g.ox, g.h, x, 0, g.dx, slack) + axis_gap2(q.y, g.oy, g.h, y, 0, g.dy, slack) +
+                     axis_gap2(q.z, g.oz, g.h, z, 0, g.dz, slack);
+    if (lb > best) return;  // `best` may have improved since the push
+    const int ci = (z * g.dy + y) * g.dx + x;
+    const int s0 = cs[ci], s1 = cs[ci + 1];
+    if (COUNT) ncand += (unsigned)(s1 - s0);
+    scan_range(c.T, s0, s1, q.x, q.y, q.z, best, bidx);
+    return;
+  }
+  const int Lc = L - 1;
+  // squared gaps to the two halves of the node along every axis
+  const float gx0 = axis_gap2(q.x, g.ox, g.h, 2 * x, Lc, g.dx, slack);
+  const float gx1 = axis_gap2(q.x, g.ox, g.h, 2 * x + 1, Lc, g.dx, slack);
+  const float gy0 = axis_gap2(q.y, g.oy, g.h, 2 * y, Lc, g.dy, slack);
+  const float gy1 = axis_gap2(q.y, g.oy, g.h, 2 * y + 1, Lc, g.dy, slack);
+  const float gz0 = axis_gap2(q.z, g.oz, g.h, 2 * z, Lc, g.dz, slack);
+  const float gz1 = axis_gap2(q.z, g.oz, g.h, 2 * z + 1, Lc, g.dz, slack);
+  if (fminf(gx0, gx1) + fminf(gy0, gy1) + fminf(gz0, gz1) > best) return;  // whole node out of reach
+  const int near = (gx1 < gx0 ? 1 : 0) | (gy1 < gy0 ? 2 : 0) | (gz1 < gz0 ? 4 : 0);
+  const int Dc = pl.D[Lc];
+  const int* __restrict__ lv = c.pyr + pl.off[Lc];
 #pragma unroll
-    for (int o = 7; o >= 0; --o) {  // farthest first: the nearest child ends on top of the stack
-      const int b = o ^ near;
-      const int xc = 2 * x + (b & 1), yc = 2 * y + ((b >> 1) & 1), zc = 2 * z + (b >> 2);
-      const float lb = ((b & 1) ? gx1 : gx0) + ((b & 2) ? gy1 : gy0) + ((b & 4) ? gz1 : gz0);
-      if (lb > best) continue;  // also drops children outside the grid (infinite gap)
-      int occ;
-      if (Lc == 0) {
-        const int ci = (zc * g.dy + yc) * g.dx + xc;
-        occ = cs[ci + 1] - cs[ci];
-      } else {
-        occ = lv[(zc * Dc + yc) * Dc + xc];
-      }
-      if (occ > 0) stack[sp++] = (Lc << 18) | (zc << 12) | (yc << 6) | xc;
+  for (int o = 7; o >= 0; --o) {  // farthest first: the nearest child ends on top of the stack
+    const int b = o ^ near;
+    const int xc = 2 * x + (b & 1), yc = 2 * y + ((b >> 1) & 1), zc = 2 * z + (b >> 2);
+    const float lb = ((b & 1) ? gx1 : gx0) + ((b & 2) ? gy1 : gy0) + ((b & 4) ? gz1 : gz0);
+    if (lb > best) continue;  // also drops children outside the grid (infinite gap)
+    int occ;
+    if (Lc == 0) {
+      const int ci = (zc * g.dy + yc) * g.dx + xc;
+      occ = cs[ci + 1] - cs[ci];
+    } else {
+      occ = lv[(zc * Dc + yc) * Dc + xc];
     }
+    if (occ > 0) stack[sp++] = (Lc << 18) | (zc << 12) | (yc << 6) | xc;
   }
 }
 
@@ -791,8 +785,15 @@ grid_nn_kernel(const float4* __restrict__ sorted0, const float4* __restrict__ so
   }
 }
 
-// Kernel 2: phase E for the queries kernel 1 could not finish, 32 per warp.
+// Kernel 2: phase E for the queries kernel 1 could not finish.  Persistent lanes: the descent is
+// one flat loop whose body handles ONE stack entry (a cell to scan or a node to expand), so the
+// lanes of a warp stay converged on it whatever query each works on; a lane whose stack runs
+// empty writes its result and waits until a quarter of the warp is idle (or nothing else is
+// running), then the idle lanes draw new queries together (one atomic per refill) -- the
+// descent lengths differ ~3x between neighbouring queries, which left 2/3 of the lanes idle
+// when every warp simply took 32 queries.
 constexpr int NNH_THREADS = 128;
+constexpr int NNH_REFILL = 8;  // idle lanes that trigger a refill
 template <typename IdxT, bool COUNT>
 __global__ void __launch_bounds__(NNH_THREADS)
 grid_nn_hard_kernel(const float4* __restrict__ sorted0, const float4* __restrict__ sorted1,
@@ -801,17 +802,47 @@ grid_nn_hard_kernel(const float4* __restrict__ sorted0, const float4* __restrict
                     const int* __restrict__ pyr_base, const PyrLayout pl, int S, int N0, int N1,
                     float* __restrict__ dist0, IdxT* __restrict__ idx0, float* __restrict__ dist1,
                     IdxT* __restrict__ idx1, const int* __restrict__ hard_count,
-                    const int4* __restrict__ hard_list, unsigned long long* __restrict__ pair_counter) {
+                    int* __restrict__ hard_cursor, const int4* __restrict__ hard_list,
+                    unsigned long long* __restrict__ pair_counter) {
   const int n = *hard_count;
+  const int lane = threadIdx.x & 31;
   unsigned ncand = 0;
-  for (int i = blockIdx.x * NNH_THREADS + threadIdx.x; i < n; i += gridDim.x * NNH_THREADS) {
-    const int4 h = hard_list[i];
-    const NNQuery c = nn_setup((long long)h.x, sorted0, sorted1, cell_start, cs_stride, params, far, pyr_base,
-                               pl.stride, S, N0, N1);
-    float best = __int_as_float(h.y);
-    int bidx = h.z;
-    nn_pyramid_search<COUNT>(c, pl, best, bidx, ncand);
-    nn_finish<IdxT>(c, best, bidx, dist0, idx0, dist1, idx1);
+  int stack[PYR_STACK];
+  int sp = 0;
+  bool have = false;      // this lane holds a query
+  bool drained = false;   // the list is exhausted: no more refills
+  NNQuery c;
+  float best = 0.f;
+  int bidx = -1;
+  while (true) {
+    const unsigned idle = __ballot_sync(0xffffffffu, sp == 0);
+    if (idle == 0xffffffffu || (!drained && __popc(idle) >= NNH_REFILL)) {
+      // ---- idle lanes retire their query and draw the next ones together ----
+      if (sp == 0 && have) {
+        nn_finish<IdxT>(c, best, bidx, dist0, idx0, dist1, idx1);
+        have = false;
+      }
+      if (drained) break;  // every stack is empty and nothing is left
+      int base = 0;
+      if (lane == 0) base = atomicAdd(hard_cursor, __popc(idle));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base + __popc(idle) >= n) drained = true;  // warp-uniform
+      if (sp == 0) {
+        const int i = base + __popc(idle & ((1u << lane) - 1u));
+        if (i < n) {
+          const int4 h = hard_list[i];
+          c = nn_setup((long long)h.x, sorted0, sorted1, cell_start, cs_stride, params, far, pyr_base,
+                       pl.stride, S, N0, N1);
+          best = __int_as_float(h.y);
+          bidx = h.z;
+          have = true;
+          stack[0] = pl.top << 18;  // the root
+          sp = 1;
+        }
+      }
+      continue;
+    }
+    if (sp > 0) nn_pyramid_step<COUNT>(c, pl, stack, sp, best, bidx, ncand);
   }
   if (COUNT && ncand) atomicAdd(pair_counter, (unsigned long long)ncand);
 }
@@ -975,14 +1006,14 @@ static int run_grid(CloudDesc c0, CloudDesc c1, int S, float* dist0, IdxT* idx0,
             hard_count, hard_list, ctr);
         grid_nn_hard_kernel<IdxT, true><<<hard_ctas, NNH_THREADS, 0, stream>>>(
             s0, s1, cs, L.cs_stride, params, far, pyr, L.pyr, S, c0.Nseg, c1.Nseg, dist0, idx0, dist1, idx1,
-            hard_count, hard_list, ctr);
+            hard_count, hard_count + 1, hard_list, ctr);
       } else {
         grid_nn_kernel<IdxT, false><<<(unsigned)blocks, 256, 0, stream>>>(
             s0, s1, cs, L.cs_stride, params, far, pyr, L.pyr, S, c0.Nseg, c1.Nseg, dist0, idx0, dist1, idx1,
             hard_count, hard_list, nullptr);
         grid_nn_hard_kernel<IdxT, false><<<hard_ctas, NNH_THREADS, 0, stream>>>(
             s0, s1, cs, L.cs_stride, params, far, pyr, L.pyr, S, c0.Nseg, c1.Nseg, dist0, idx0, dist1, idx1,
-            hard_count, hard_list, nullptr);
+            hard_count, hard_count + 1, hard_list, nullptr);
       }
       count_launch();
     }
