@@ -247,8 +247,14 @@ int mpa_pose_head_forward(const float* feats, int T, int K0, const float* fc0_w,
  * NULL), key-padding mask `valid` [B*P] bytes (1 = valid; NULL = all valid).
  * tokens/out [B*P, D] fp32.  Every *_w/*_b argument is an array of `layers`
  * device pointers laid out as torch stores them (in_proj_weight [3D,D] = [Wq;Wk;Wv]).
- * Dropout is not applied (eval mode, or p = 0 as in the benchmark). */
+ * Training-mode dropout (the reference trains with p = 0.1, transformer.py:10,47): with
+ * dropout_p > 0, rng_state (device, two 64-bit key words the caller draws for THIS forward)
+ * keys an in-kernel Philox4x32-10 at the four dropout sites of nn.TransformerEncoderLayer
+ * (attention probabilities, after out_proj, FFN hidden, after linear2); `masks` (nullable,
+ * mpa_transformer_mask_bytes, per layer [B,H,P,P | T,D | T,FF | T,D] keep bytes) receives the
+ * masks for the backward pass.  dropout_p = 0: eval. */
 size_t mpa_transformer_workspace_bytes(int B, int P, int D, int FF, int layers);
+size_t mpa_transformer_mask_bytes(int B, int P, int D, int H, int FF, int layers);
 int mpa_transformer_forward(const float* tokens, const unsigned char* valid, int B, int P, int D,
                             int H, int FF, int layers, const float* const* in_proj_w,
                             const float* const* in_proj_b, const float* const* out_proj_w,
@@ -257,8 +263,9 @@ int mpa_transformer_forward(const float* tokens, const unsigned char* valid, int
                             const float* const* lin2_b, const float* const* norm1_w,
                             const float* const* norm1_b, const float* const* norm2_w,
                             const float* const* norm2_b, const float* final_norm_w,
-                            const float* final_norm_b, float eps, float* out, void* ws,
-                            size_t ws_bytes, void* stream);
+                            const float* final_norm_b, float eps, float dropout_p,
+                            unsigned long long* rng_state, unsigned char* masks, float* out,
+                            void* ws, size_t ws_bytes, void* stream);
 
 /* ---- DGCNN: k-NN graph and EdgeConv aggregation -------------------------- */
 /* Replaces knn (models/modules/encoder/dgcnn.py:8-15).  x [n,N,C] fp32 with the

@@ -31,6 +31,53 @@ __host__ __device__ constexpr int ln_smem_bytes(int bn) { return LN_STAGES * ln_
 
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY02 = 2 };
 
+// Inverted dropout (torch semantics: keep with probability 1 - p, scale kept values by
+// 1 / (1 - p)) drawn from a counter-based generator: Philox4x32-10 keyed by `rng[0]` (seed) with
+// the counter (element quad, row, site, rng[1] = number of forward calls so far).  The keep mask
+// is written out (one byte per element) so that the backward pass applies the same mask.
+struct DropoutSpec {
+  const unsigned long long* rng = nullptr;  // device: two key words of this forward; nullptr = no dropout
+  float p = 0.f;
+  unsigned site = 0;                        // distinguishes the dropout sites of a forward
+  unsigned char* mask = nullptr;            // [rows, cols] keep mask out (nullable)
+};
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned lo0 = 0xD2511F53u * ctr.x, hi0 = __umulhi(0xD2511F53u, ctr.x);
+    const unsigned lo1 = 0xCD9E8D57u * ctr.z, hi1 = __umulhi(0xCD9E8D57u, ctr.z);
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+// keep decisions of the 4 elements (row, 4*quad .. 4*quad+3) of dropout site `site`
+__device__ __forceinline__ uint4 dropout_quad(const unsigned long long* rng, unsigned site, unsigned row,
+                                              unsigned quad, float p) {
+  const unsigned long long seed = rng[0], calls = rng[1];
+  const uint4 r = philox4x32_10(make_uint4(quad, row, site, (unsigned)calls),
+                                make_uint2((unsigned)seed, (unsigned)(seed >> 32) ^ (unsigned)(calls >> 32)));
+  const unsigned thr = (unsigned)(p * 16777216.0f);  // keep iff the top 24 bits >= p * 2^24
+  return make_uint4((r.x >> 8) >= thr, (r.y >> 8) >= thr, (r.z >> 8) >= thr, (r.w >> 8) >= thr);
+}
+// dropout of the 32 consecutive columns col0.. of `row` held in v[]
+__device__ __forceinline__ void dropout32(float* v, const DropoutSpec& d, int row, int col0, int ncols) {
+  const float scale = 1.0f / (1.0f - d.p);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint4 k = dropout_quad(d.rng, d.site, (unsigned)row, (unsigned)((col0 >> 2) + j), d.p);
+    v[4 * j + 0] = k.x ? v[4 * j + 0] * scale : 0.f;
+    v[4 * j + 1] = k.y ? v[4 * j + 1] * scale : 0.f;
+    v[4 * j + 2] = k.z ? v[4 * j + 2] * scale : 0.f;
+    v[4 * j + 3] = k.w ? v[4 * j + 3] * scale : 0.f;
+    if (d.mask != nullptr && col0 + 4 * j + 3 < ncols)
+      *reinterpret_cast<uchar4*>(d.mask + (long long)row * ncols + col0 + 4 * j) =
+          make_uchar4((unsigned char)k.x, (unsigned char)k.y, (unsigned char)k.z, (unsigned char)k.w);
+  }
+}
+
 struct LinearEpilogue {
   const float* bias;       // [N] or nullptr
   const float* residual;   // [M, N] fp32 added after the activation, or nullptr
@@ -44,6 +91,7 @@ struct LinearEpilogue {
   __nv_bfloat16* ln_out_bf16 = nullptr;  // LayerNorm(out) as the next GEMM's operand
   float* ln_out_f32 = nullptr;           // ... and/or in fp32 (final encoder norm)
   int vec = 0;                           // rows are 16-byte aligned: packed loads / stores
+  DropoutSpec drop;                      // applied to act(acc + bias), before the residual add
 };
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1,
@@ -226,6 +274,7 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                          : make_float4(0.f, 0.f, 0.f, 0.f);
           }
           add_bias_act(v, sbias, j0, ep.act);
+          if (ep.drop.rng != nullptr && m0 + row_local < M) dropout32(v, ep.drop, m0 + row_local, col0, N);
           tile_put_row(tile, lane, v);
           __syncwarp();
 #pragma unroll
@@ -266,6 +315,7 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         tc::tmem_ld32(taddr + (uint32_t)j0, v);
         tc::tmem_ld_wait();
         add_bias_act(v, sbias, j0, ep.act);
+        if (ep.drop.rng != nullptr && m0 + row_local < M) dropout32(v, ep.drop, m0 + row_local, j0, N);
         tile_put_row(tile, lane, v);
         __syncwarp();
         float4 xq[8];
@@ -472,7 +522,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
 constexpr int ATT_MAX_WARPS = 32;  // one warp per query row (P <= 32): the rows run concurrently
 __global__ void __launch_bounds__(ATT_MAX_WARPS * 32, 1)
 attention_kernel(const float* __restrict__ qkv, const unsigned char* __restrict__ valid, int B, int P,
-                 int H, int hd, __nv_bfloat16* __restrict__ out) {
+                 int H, int hd, __nv_bfloat16* __restrict__ out, DropoutSpec drop) {
   extern __shared__ float sm[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gw = blockIdx.x;  // (shape, head)
@@ -511,6 +561,12 @@ attention_kernel(const float* __restrict__ qkv, const unsigned char* __restrict_
     for (int o = 16; o > 0; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
     // a shape without any valid key cannot occur (>= 1 valid part); guard anyway
     e = den > 0.f ? e / den : 0.f;
+    if (drop.rng != nullptr) {  // dropout on the attention probabilities (nn.MultiheadAttention)
+      const unsigned el = (unsigned)((gw * P + i) * P + lane);  // [B, H, P, P] element
+      const bool keep = lane < P ? dropout_quad(drop.rng, drop.site, 0u, el, drop.p).x != 0u : false;
+      e = keep ? e / (1.0f - drop.p) : 0.f;
+      if (drop.mask != nullptr && lane < P) drop.mask[el] = keep ? 1 : 0;
+    }
     float o0 = 0.f, o1 = 0.f;
     for (int j = 0; j < P; ++j) {
       const float pj = __shfl_sync(0xffffffffu, e, j);
@@ -585,9 +641,19 @@ int mpa_linear_forward(const float* x, const float* w, const float* bias, const 
 }
 
 /* Pre-LN transformer encoder (nn.TransformerEncoder with norm_first=True,
- * batch_first, ReLU FFN, final LayerNorm; dropout is not applied: eval mode or
- * p = 0), key-padding mask from `valid`.  tokens/out [B*P, D] fp32.
- * Per-layer parameter arrays hold `layers` device pointers each. */
+ * batch_first, ReLU FFN, final LayerNorm), key-padding mask from `valid`.
+ * tokens/out [B*P, D] fp32.  Per-layer parameter arrays hold `layers` device pointers each.
+ * Training-mode dropout (the reference trains with p = 0.1, transformer.py:10,47): with
+ * dropout_p > 0, `rng_state` (device, two 64-bit words the caller draws per forward) keys an
+ * in-kernel Philox4x32-10 at the four sites of nn.TransformerEncoderLayer -- attention
+ * probabilities, after out_proj, FFN hidden, after linear2 -- and `masks` receives the keep
+ * masks per layer (mpa_transformer_mask_bytes) for the backward pass. */
+size_t mpa_transformer_mask_bytes(int B, int P, int D, int H, int FF, int layers) {
+  const size_t T = (size_t)B * P;
+  return (size_t)layers * ((size_t)B * H * P * P + 2 * T * D + T * FF);
+}
+
+
 size_t mpa_transformer_workspace_bytes(int B, int P, int D, int FF, int layers) {
   const size_t T = (size_t)B * P;
   size_t o = 0;
@@ -608,10 +674,15 @@ int mpa_transformer_forward(const float* tokens, const unsigned char* valid, int
                             const float* const* lin2_b, const float* const* norm1_w,
                             const float* const* norm1_b, const float* const* norm2_w,
                             const float* const* norm2_b, const float* final_norm_w,
-                            const float* final_norm_b, float eps, float* out, void* ws, size_t ws_bytes,
-                            void* stream_) {
+                            const float* final_norm_b, float eps, float dropout_p,
+                            unsigned long long* rng_state, unsigned char* masks, float* out, void* ws,
+                            size_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   MPA_CHECK_ARG(B >= 0 && P > 0 && P <= 32, "transformer_forward: 1 <= P <= 32 parts (got %d)", P);
+  MPA_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "transformer_forward: dropout %f", dropout_p);
+  const bool drop = dropout_p > 0.f;
+  MPA_CHECK_ARG(!drop || (rng_state != nullptr && D % 32 == 0 && FF % 32 == 0),
+                "transformer_forward: dropout needs rng_state and D, FF multiples of 32");
   MPA_CHECK_ARG(D % 32 == 0 && D <= 1024 && H > 0 && D % H == 0 && D / H <= 64 && FF % 8 == 0,
                 "transformer_forward: unsupported dims D=%d H=%d FF=%d", D, H, FF);
   if (B == 0) return MPA_OK;
@@ -653,6 +724,21 @@ int mpa_transformer_forward(const float* tokens, const unsigned char* valid, int
     layernorm_kernel<<<ln_blocks, 256, 0, stream>>>(tokens, norm1_w[0], norm1_b[0], T, D, eps, xn, nullptr);
     MPA_LAUNCH_CHECK();
   }
+  const size_t mask_layer = (size_t)B * H * P * P + 2 * (size_t)T * D + (size_t)T * FF;
+  auto site = [&](int l, int k) {  // k: 0 attention, 1 after out_proj, 2 FFN hidden, 3 after linear2
+    DropoutSpec d;
+    if (!drop) return d;
+    d.rng = rng_state;
+    d.p = dropout_p;
+    d.site = (unsigned)(4 * l + k);
+    if (masks != nullptr) {
+      unsigned char* m = masks + (size_t)l * mask_layer;
+      const size_t offs[4] = {0, (size_t)B * H * P * P, (size_t)B * H * P * P + (size_t)T * D,
+                              (size_t)B * H * P * P + (size_t)T * D + (size_t)T * FF};
+      d.mask = m + offs[k];
+    }
+    return d;
+  };
   for (int l = 0; l < layers; ++l) {
     const __nv_bfloat16* wl = wts + (size_t)l * per_layer;
     if (!fused) {
@@ -665,10 +751,11 @@ int mpa_transformer_forward(const float* tokens, const unsigned char* valid, int
     if (rc != MPA_OK) return rc;
     { ProfScope ps("attention", stream);
       attention_kernel<<<B * H, 32 * (P < ATT_MAX_WARPS ? P : ATT_MAX_WARPS), att_smem, stream>>>(
-          qkv, valid, B, P, H, hd, att); }
+          qkv, valid, B, P, H, hd, att, site(l, 0)); }
     MPA_LAUNCH_CHECK();
-    // x <- x + out_proj(att)  [+ xn <- LayerNorm2(x)]
+    // x <- x + dropout1(out_proj(att))  [+ xn <- LayerNorm2(x)]
     LinearEpilogue e_o{out_proj_b[l], (fused && l == 0) ? tokens : x, x, nullptr, ACT_NONE};
+    e_o.drop = site(l, 1);
     if (fused) { e_o.ln_gamma = norm2_w[l]; e_o.ln_beta = norm2_b[l]; e_o.ln_eps = eps; e_o.ln_out_bf16 = xn; }
     rc = launch_linear(att, wl + (size_t)3 * D * D, T, D, D, e_o, "linear_out_proj", stream);
     if (rc != MPA_OK) return rc;
@@ -678,11 +765,13 @@ int mpa_transformer_forward(const float* tokens, const unsigned char* valid, int
       MPA_LAUNCH_CHECK();
     }
     LinearEpilogue e_f1{lin1_b[l], nullptr, nullptr, hid, ACT_RELU};
+    e_f1.drop = site(l, 2);
     rc = launch_linear(xn, wl + (size_t)4 * D * D, T, FF, D, e_f1, "linear_ffn1", stream);
     if (rc != MPA_OK) return rc;
     // x <- x + FFN2(hid)  [+ LayerNorm1 of the next layer, or the final encoder norm]
     const bool last = l + 1 == layers;
     LinearEpilogue e_f2{lin2_b[l], x, (fused && last) ? (final_norm_w == nullptr ? out : nullptr) : x, nullptr, ACT_NONE};
+    e_f2.drop = site(l, 3);
     if (fused && !last) {
       e_f2.ln_gamma = norm1_w[l + 1]; e_f2.ln_beta = norm1_b[l + 1]; e_f2.ln_eps = eps; e_f2.ln_out_bf16 = xn;
     } else if (fused && final_norm_w != nullptr) {

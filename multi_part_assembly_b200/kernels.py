@@ -527,12 +527,75 @@ def _transformer_params(encoder):
     return groups
 
 
+def _rng_state(dev):
+    """{seed, stream} of the in-kernel dropout generator for ONE forward, drawn from torch's
+    CUDA generator: torch.manual_seed reproduces a run, and inside a CUDA graph torch's
+    graph-safe generator advances per replay, so every replay draws fresh masks."""
+    return torch.randint(0, 2**62, (2, ), dtype=torch.int64, device=dev)
+
+
+def _transformer_masked_torch(tokens, valid, encoder, num_heads, masks, p):
+    """The encoder in plain torch ops with EXPLICIT dropout keep masks (per layer: attention
+    probabilities [B,H,P,P], after out_proj [B,P,D], FFN hidden [B,P,FF], after linear2 [B,P,D];
+    None = no dropout) -- nn.TransformerEncoderLayer(norm_first=True) semantics.  Used to
+    differentiate the native forward (same masks as the kernels drew) and by the tests."""
+    B, P, D = tokens.shape
+    hd = D // num_heads
+    keep = 1.0 / (1.0 - p) if masks is not None else 1.0
+    neg = None
+    if valid is not None and valid.numel():
+        neg = torch.zeros(B, 1, 1, P, dtype=tokens.dtype, device=tokens.device)
+        neg = neg.masked_fill(~valid.view(B, 1, 1, P), float('-inf'))
+    x = tokens
+    for l, layer in enumerate(encoder.layers):
+        m = masks[l] if masks is not None else (None, None, None, None)
+        h = F.layer_norm(x, (D, ), layer.norm1.weight, layer.norm1.bias, layer.norm1.eps)
+        qkv = F.linear(h, layer.self_attn.in_proj_weight, layer.self_attn.in_proj_bias)
+        q, k, v = qkv.view(B, P, 3, num_heads, hd).permute(2, 0, 3, 1, 4)
+        sc = torch.matmul(q, k.transpose(-1, -2)) / (hd**0.5)
+        if neg is not None:
+            sc = sc + neg
+        pr = torch.softmax(sc.float(), dim=-1).to(sc.dtype)
+        if m[0] is not None:
+            pr = pr * (m[0].to(pr.dtype) * keep)
+        o = torch.matmul(pr, v).permute(0, 2, 1, 3).reshape(B, P, D)
+        o = F.linear(o, layer.self_attn.out_proj.weight, layer.self_attn.out_proj.bias)
+        if m[1] is not None:
+            o = o * (m[1].to(o.dtype) * keep)
+        x = x + o
+        h = F.layer_norm(x, (D, ), layer.norm2.weight, layer.norm2.bias, layer.norm2.eps)
+        f = F.relu(F.linear(h, layer.linear1.weight, layer.linear1.bias))
+        if m[2] is not None:
+            f = f * (m[2].to(f.dtype) * keep)
+        f = F.linear(f, layer.linear2.weight, layer.linear2.bias)
+        if m[3] is not None:
+            f = f * (m[3].to(f.dtype) * keep)
+        x = x + f
+    if encoder.norm is not None:
+        x = F.layer_norm(x, (D, ), encoder.norm.weight, encoder.norm.bias, encoder.norm.eps)
+    return x
+
+
+def split_transformer_masks(masks, B, P, D, H, FF, layers):
+    """Flat keep-mask buffer of mpa_transformer_forward -> per layer (attn, d1, hid, d2) views."""
+    out, o = [], 0
+    T = B * P
+    for _ in range(layers):
+        a = masks[o:o + B * H * P * P].view(B, H, P, P); o += B * H * P * P
+        d1 = masks[o:o + T * D].view(B, P, D); o += T * D
+        hm = masks[o:o + T * FF].view(B, P, FF); o += T * FF
+        d2 = masks[o:o + T * D].view(B, P, D); o += T * D
+        out.append((a, d1, hm, d2))
+    return out
+
+
 class _TransformerFunction(torch.autograd.Function):
-    """Forward: tcgen05 + TMA kernels (csrc/linear.cu).  Backward: re-runs the
-    stock nn.TransformerEncoder with autograd (round-1 scope is fwd+loss)."""
+    """Forward: tcgen05 + TMA kernels (csrc/linear.cu), dropout drawn in-kernel (Philox) when
+    training with p > 0.  Backward: autograd through the same layer chain in torch ops, with
+    the keep masks the kernels wrote (or the stock module when there is no dropout)."""
 
     @staticmethod
-    def forward(ctx, tokens, valid, encoder, num_heads, *params):
+    def forward(ctx, tokens, valid, encoder, num_heads, dropout_p, *params):
         B, P, D = tokens.shape
         ls = encoder.layers
         FF = ls[0].linear1.out_features
@@ -544,44 +607,71 @@ class _TransformerFunction(torch.autograd.Function):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         vb = None if valid is None else valid.to(torch.uint8).contiguous()
         fn = encoder.norm
+        masks, rng = None, None
+        if dropout_p > 0.:
+            rng = _rng_state(dev)
+            masks = torch.empty(L.mpa_transformer_mask_bytes(B, P, D, num_heads, FF, len(ls)),
+                                dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             rc = L.mpa_transformer_forward(
                 _lib.ptr(tokens), _lib.ptr(vb), B, P, D, num_heads, FF, len(ls),
                 *[_ptr_array([t.detach() for t in g]) for g in groups],
                 _lib.ptr(fn.weight.detach()) if fn is not None else None,
                 _lib.ptr(fn.bias.detach()) if fn is not None else None,
-                float(ls[0].norm1.eps), _lib.ptr(out), _lib.ptr(ws), ws_bytes,
-                _lib.cuda_stream(dev))
+                float(ls[0].norm1.eps), float(dropout_p), _lib.ptr(rng), _lib.ptr(masks),
+                _lib.ptr(out), _lib.ptr(ws), ws_bytes, _lib.cuda_stream(dev))
         _lib.check(rc, 'mpa_transformer_forward')
-        ctx.save_for_backward(tokens, valid if valid is not None else tokens.new_empty(0))
+        ctx.save_for_backward(tokens, valid if valid is not None else tokens.new_empty(0),
+                              masks if masks is not None else tokens.new_empty(0))
         ctx.encoder = encoder
+        ctx.num_heads = num_heads
+        ctx.dropout_p = dropout_p
+        if _TRANSFORMER_TRACE is not None:
+            _TRANSFORMER_TRACE.append(masks)
         return out
 
     @staticmethod
     def backward(ctx, grad):
-        tokens, valid = ctx.saved_tensors
+        tokens, valid, masks = ctx.saved_tensors
         encoder = ctx.encoder
         params = [p for p in encoder.parameters()]
+        B, P, D = tokens.shape
         with torch.enable_grad(), torch.autocast('cuda', dtype=torch.bfloat16):
             t = tokens.detach().requires_grad_(True)
-            pad = ~valid if valid.numel() else None
-            out = encoder(t, src_key_padding_mask=pad)
+            if ctx.dropout_p > 0.:
+                FF = encoder.layers[0].linear1.out_features
+                ms = split_transformer_masks(masks, B, P, D, ctx.num_heads, FF, len(encoder.layers))
+                out = _transformer_masked_torch(t, valid if valid.numel() else None, encoder,
+                                                ctx.num_heads, ms, ctx.dropout_p)
+            else:
+                pad = ~valid if valid.numel() else None
+                out = encoder(t, src_key_padding_mask=pad)
             grads = torch.autograd.grad(out, [t] + params, grad.to(out.dtype), allow_unused=True)
-        return (grads[0], None, None, None) + tuple(grads[1:])
+        return (grads[0], None, None, None, None) + tuple(grads[1:])
+
+
+# tests set this to a list to receive the dropout keep masks of every native forward
+_TRANSFORMER_TRACE = None
 
 
 def transformer_forward(tokens, valid_masks, encoder, num_heads, training, dropout):
     """tokens [B, P, C], valid_masks [B, P] bool -> [B, P, C]."""
     _lib.require_cuda(tokens)
     layer0 = encoder.layers[0]
-    native = _use_bf16() and layer0.norm_first and not (training and dropout > 0.) and \
+    # the modules' own rates (tests and the benchmark zero them); the kernels draw one rate for
+    # the four sites of a layer, as nn.TransformerEncoderLayer(dropout=p) builds them
+    rates = {float(r) for l in encoder.layers
+             for r in (l.dropout.p, l.dropout1.p, l.dropout2.p, l.self_attn.dropout)}
+    p = rates.pop() if (training and len(rates) == 1) else 0.0
+    ff = layer0.linear1.out_features
+    native = _use_bf16() and layer0.norm_first and (not training or len(rates) == 0) and \
         tokens.shape[1] <= 32 and tokens.shape[2] % 32 == 0 and \
-        tokens.shape[2] // num_heads <= 64
+        tokens.shape[2] // num_heads <= 64 and (p == 0. or ff % 32 == 0)
     if native:
-        params = [p for p in encoder.parameters()]
+        params = [p_ for p_ in encoder.parameters()]
         with torch.autocast('cuda', enabled=False):
             return _TransformerFunction.apply(tokens.float().contiguous(), valid_masks, encoder,
-                                              num_heads, *params)
+                                              num_heads, p, *params)
     pad = None if valid_masks is None else ~valid_masks
     prev = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = False

@@ -386,3 +386,80 @@ def test_graphed_train_step_matches_eager(cuda):
     got = [float(g()) for _ in range(2)]
     np.testing.assert_allclose(got, want[3:5], rtol=5e-3)
     assert all(np.isfinite(got))
+
+
+def test_transformer_native_dropout(cuda):
+    """Training with the reference's dropout 0.1 (transformer.py:10,47) stays on the native
+    kernels: the Philox masks drawn in-kernel are returned, so the forward can be checked
+    against the same layer chain in fp32 torch WITH THOSE MASKS (bf16 bar), the keep rate
+    against 1 - p, reseeding against reproducibility, and the backward against fp32 autograd."""
+    from multi_part_assembly_b200 import kernels
+    from multi_part_assembly_b200.models.pn_transformer import TransformerEncoder
+    B, P, D, H, FF, Lyr, p = 6, 20, 256, 8, 1024, 4, 0.1
+    tr = fill_params_(TransformerEncoder(D, H, FF, Lyr), 7).to(cuda).train()
+    g = torch.Generator().manual_seed(3)
+    tokens = torch.randn(B, P, D, generator=g).to(cuda).requires_grad_(True)
+    valid = torch.ones(B, P, dtype=torch.bool, device=cuda)
+    valid[1, 7:] = False
+    valid[4, 2:] = False
+
+    def run(seed):
+        torch.manual_seed(seed)
+        kernels._TRANSFORMER_TRACE = trace = []
+        kernels.set_precision('bf16')
+        try:
+            out = tr(tokens, valid)
+        finally:
+            kernels.set_precision('auto')
+            kernels._TRANSFORMER_TRACE = None
+        assert len(trace) == 1 and trace[0] is not None  # the native path ran and drew masks
+        return out, trace[0]
+
+    out, masks = run(5)
+    ms = kernels.split_transformer_masks(masks, B, P, D, H, FF, Lyr)
+    for layer in ms:
+        for m in layer:
+            assert abs(float(m.float().mean()) - (1 - p)) < 0.02
+    enc = tr.transformer_encoder
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        tok32 = tokens.detach().clone().requires_grad_(True)
+        want = kernels._transformer_masked_torch(tok32, valid, enc, H, ms, p)
+        w = torch.randn(B, P, D, generator=g).to(cuda) * valid[..., None]
+        (want * w).sum().backward()
+        want_grads = [tok32.grad] + [q.grad.clone() for q in enc.parameters()]
+        enc.zero_grad()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    v = valid.cpu().numpy()
+    a, b = out.detach().cpu().numpy(), want.detach().cpu().numpy()
+    assert np.isfinite(a).all()
+    assert np.abs(a[v] - b[v]).max() / np.abs(b[v]).max() < 3e-2
+    # backward through the saved masks vs fp32 autograd with the same masks
+    (out * w).sum().backward()
+    got_grads = [tokens.grad] + [q.grad for q in enc.parameters()]
+    for gg, ww in zip(got_grads, want_grads):
+        rel = float((gg.double() - ww.double()).norm() / ww.double().norm().clamp_min(1e-12))
+        assert rel < 6e-2, rel
+    # a second forward draws new masks; re-seeding reproduces the first ones
+    _, masks2 = run(5)
+    assert torch.equal(masks, masks2)
+    kernels._TRANSFORMER_TRACE = trace = []
+    kernels.set_precision('bf16')
+    try:
+        tr(tokens, valid)
+    finally:
+        kernels.set_precision('auto')
+        kernels._TRANSFORMER_TRACE = None
+    assert not torch.equal(trace[0], masks)
+    # eval mode: no dropout, no masks
+    tr.eval()
+    kernels._TRANSFORMER_TRACE = trace = []
+    kernels.set_precision('bf16')
+    try:
+        tr(tokens, valid)
+    finally:
+        kernels.set_precision('auto')
+        kernels._TRANSFORMER_TRACE = None
+    assert trace == [None]
