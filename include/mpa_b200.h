@@ -220,7 +220,16 @@ int mpa_pool_argmax(const void* z, const float* scale, int n_parts, int N, int C
  * tensor-core operands with fp32 accumulation.  act: 0 none, 1 ReLU,
  * 2 LeakyReLU(0.2).  K must be a multiple of 8.  Replaces the cuBLAS GEMMs of
  * PoseRegressor (models/modules/regressor.py:45-68). */
+#define MPA_PRECISION_BF16 0 /* bf16 operands, fp32 accumulation */
+#define MPA_PRECISION_FP32 1 /* fp32-accurate: 3 bf16 planes per operand, 6 tensor-core products per k-step */
 size_t mpa_linear_workspace_bytes(int M, int N, int K);
+/* Same with a precision selector: MPA_PRECISION_FP32 replaces the fp32 cuBLAS/cuDNN GEMMs
+ * of the reference's default (non --fp16) mode, e.g. the 1x1 convolutions of DGCNN
+ * (models/modules/encoder/dgcnn.py:51-68). */
+size_t mpa_linear_workspace_bytes_ex(int M, int N, int K, int precision);
+int mpa_linear_forward_ex(const float* x, const float* w, const float* bias, const float* residual,
+                          int M, int N, int K, int act, int precision, float* out, void* ws,
+                          size_t ws_bytes, void* stream);
 int mpa_linear_forward(const float* x, const float* w, const float* bias, const float* residual,
                        int M, int N, int K, int act, float* out, void* ws, size_t ws_bytes,
                        void* stream);
@@ -252,7 +261,10 @@ int mpa_pose_head_forward(const float* feats, int T, int K0, const float* fc0_w,
  * keys an in-kernel Philox4x32-10 at the four dropout sites of nn.TransformerEncoderLayer
  * (attention probabilities, after out_proj, FFN hidden, after linear2); `masks` (nullable,
  * mpa_transformer_mask_bytes, per layer [B,H,P,P | T,D | T,FF | T,D] keep bytes) receives the
- * masks for the backward pass.  dropout_p = 0: eval. */
+ * masks for the backward pass.  dropout_p = 0: eval.  precision: MPA_PRECISION_BF16 (bf16
+ * operands, the analogue of the reference's --fp16 autocast) or MPA_PRECISION_FP32 (the
+ * reference default, scripts/train.py:88: every operand is carried as three bf16 planes and
+ * six tensor-core products per k-step reproduce an fp32 GEMM to ~1e-6). */
 size_t mpa_transformer_workspace_bytes(int B, int P, int D, int FF, int layers);
 size_t mpa_transformer_mask_bytes(int B, int P, int D, int H, int FF, int layers);
 int mpa_transformer_forward(const float* tokens, const unsigned char* valid, int B, int P, int D,
@@ -264,8 +276,8 @@ int mpa_transformer_forward(const float* tokens, const unsigned char* valid, int
                             const float* const* norm1_b, const float* const* norm2_w,
                             const float* const* norm2_b, const float* final_norm_w,
                             const float* final_norm_b, float eps, float dropout_p,
-                            unsigned long long* rng_state, unsigned char* masks, float* out,
-                            void* ws, size_t ws_bytes, void* stream);
+                            unsigned long long* rng_state, unsigned char* masks, int precision,
+                            float* out, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- DGCNN: k-NN graph and EdgeConv aggregation -------------------------- */
 /* Replaces knn (models/modules/encoder/dgcnn.py:8-15).  x [n,N,C] fp32 with the

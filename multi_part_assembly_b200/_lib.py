@@ -55,11 +55,13 @@ _SIGNATURES = {
     'mpa_pool_argmax': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     'mpa_lsap_batched': (c_int, [c_void_p] * 4 + [c_int, c_int, c_void_p, c_void_p]),
     'mpa_linear_workspace_bytes': (c_size_t, [c_int] * 3),
+    'mpa_linear_workspace_bytes_ex': (c_size_t, [c_int] * 4),
+    'mpa_linear_forward_ex': (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p, c_void_p, c_size_t, c_void_p]),
     'mpa_linear_forward': (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p, c_void_p, c_size_t, c_void_p]),
     'mpa_transformer_workspace_bytes': (c_size_t, [c_int] * 5),
     'mpa_transformer_mask_bytes': (c_size_t, [c_int] * 6),
     'mpa_transformer_forward': (c_int, [c_void_p, c_void_p] + [c_int] * 6 + [c_void_p] * 14 +
-                                [ctypes.c_float, ctypes.c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                                [ctypes.c_float, ctypes.c_float, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                  c_size_t, c_void_p]),
     'mpa_knn_workspace_bytes': (c_size_t, [c_int] * 2),
     'mpa_knn': (c_int, [c_void_p, c_void_p] + [c_int] * 4 + [c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -23,11 +23,17 @@ namespace mpa {
 
 constexpr int LN_BM = 128;      // rows per tile (UMMA M)
 constexpr int LN_BK = 64;       // k per stage (one 128-byte swizzle span of bf16)
-constexpr int LN_STAGES = 4;
 constexpr int LN_EPI_WARPS = 8;  // two warps per TMEM lane quadrant, each takes half of the columns
 constexpr int LN_THREADS = 64 + 32 * LN_EPI_WARPS;  // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue
-__host__ __device__ constexpr int ln_stage_bytes(int bn) { return (LN_BM + bn) * LN_BK * 2; }
-__host__ __device__ constexpr int ln_smem_bytes(int bn) { return LN_STAGES * ln_stage_bytes(bn) + 1024; }
+// SPLIT = 1: bf16 operands.  SPLIT = 3: fp32-accurate mode -- every fp32 operand is carried as
+// three bf16 planes (hi, mid, lo: 3 x 8 mantissa bits) and a k-step issues the six products
+// whose weight is >= 2^-16 (hi.hi, hi.mid, mid.hi, hi.lo, lo.hi, mid.mid) into the same fp32
+// accumulator: the result agrees with an fp32 GEMM to ~1e-6 relative, on the tensor cores.
+__host__ __device__ constexpr int ln_stage_bytes(int bn, int split = 1) { return (LN_BM + bn) * LN_BK * 2 * split; }
+__host__ __device__ constexpr int ln_stages(int bn, int split) { return split == 1 ? 4 : (bn > 128 ? 1 : 2); }
+__host__ __device__ constexpr int ln_smem_bytes(int bn, int split = 1) {
+  return ln_stages(bn, split) * ln_stage_bytes(bn, split) + 1024;
+}
 
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY02 = 2 };
 
@@ -92,6 +98,8 @@ struct LinearEpilogue {
   float* ln_out_f32 = nullptr;           // ... and/or in fp32 (final encoder norm)
   int vec = 0;                           // rows are 16-byte aligned: packed loads / stores
   DropoutSpec drop;                      // applied to act(acc + bias), before the residual add
+  long long plane = 0;                   // SPLIT = 3: elements between the hi / mid / lo planes of
+                                         // out_bf16 and ln_out_bf16 (0 = plain bf16 output)
 };
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1,
@@ -163,22 +171,49 @@ __device__ __forceinline__ uint2 pack_bf16x4(float4 q) {
   return u;
 }
 
+// fp32 quad -> bf16 operand: one plane, or the hi / mid / lo planes of the fp32-accurate mode
+__device__ __forceinline__ void store_operand4(__nv_bfloat16* base, long long o, long long plane, float4 x) {
+  *reinterpret_cast<uint2*>(base + o) = pack_bf16x4(x);
+  if (plane != 0) {
+    float r[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int s = 1; s < 3; ++s) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r[j] -= __bfloat162float(__float2bfloat16_rn(r[j]));
+      *reinterpret_cast<uint2*>(base + (long long)s * plane + o) = pack_bf16x4(make_float4(r[0], r[1], r[2], r[3]));
+    }
+  }
+}
+__device__ __forceinline__ void store_operand1(__nv_bfloat16* base, long long o, long long plane, float x) {
+  __nv_bfloat16 h = __float2bfloat16_rn(x);
+  base[o] = h;
+  if (plane != 0) {
+    x -= __bfloat162float(h);
+    h = __float2bfloat16_rn(x);
+    base[plane + o] = h;
+    x -= __bfloat162float(h);
+    base[2 * plane + o] = __float2bfloat16_rn(x);
+  }
+}
+
 // One CTA = one 128 x BN output tile; 8 epilogue warps = 4 TMEM lane quadrants x 2
 // column halves.  FUSE_LN (BN == N): the finished row (residual stream) is parked back
 // in TMEM and LayerNorm-ed from there in two more passes (mean, then centred variance),
 // the two half-row warps meeting in shared memory.
-template <int BN, bool FUSE_LN>
+template <int BN, bool FUSE_LN, int SPLIT>
 __global__ void __launch_bounds__(LN_THREADS, 1)
 linear_bf16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-                   int M, int N, int K, LinearEpilogue ep) {
+                   int M, int N, int K, int x_plane_rows, int w_plane_rows, LinearEpilogue ep) {
+  constexpr int LN_STAGES = ln_stages(BN, SPLIT);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t full_bar[LN_STAGES], empty_bar[LN_STAGES], done_bar;
   __shared__ uint32_t tmem_base_s;
   __shared__ float ln_part[2][2][LN_BM];
   __shared__ __align__(16) float s_vec[3][BN];  // bias, LayerNorm gamma, beta of this tile's columns
-  constexpr int STAGE = ln_stage_bytes(BN);
-  static_assert(LN_EPI_WARPS * EP_TILE_FLOATS * 4 <= LN_STAGES * ln_stage_bytes(BN), "staging tiles live in the ring");
+  constexpr int STAGE = ln_stage_bytes(BN, SPLIT);
+  constexpr int A_TILE = LN_BM * LN_BK * 2, B_TILE = BN * LN_BK * 2;  // one plane of a stage
+  static_assert(LN_EPI_WARPS * EP_TILE_FLOATS * 4 <= LN_STAGES * ln_stage_bytes(BN, SPLIT), "staging tiles live in the ring");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * LN_BM, n0 = blockIdx.y * BN;
@@ -200,11 +235,14 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       for (int kb = 0; kb < num_k; ++kb) {
         const int s = kb % LN_STAGES;
         if (kb >= LN_STAGES) tc::mbar_wait(&empty_bar[s], ((kb / LN_STAGES) - 1) & 1);
-        uint8_t* a_dst = smem + s * STAGE;
-        uint8_t* b_dst = a_dst + LN_BM * LN_BK * 2;
+        uint8_t* a_dst = smem + s * STAGE;            // stage = SPLIT A planes, then SPLIT B planes
+        uint8_t* b_dst = a_dst + SPLIT * A_TILE;
         mbar_expect_tx(&full_bar[s], STAGE);
-        tma_load_2d(a_dst, &map_x, kb * LN_BK, m0, &full_bar[s]);
-        tma_load_2d(b_dst, &map_w, kb * LN_BK, n0, &full_bar[s]);
+#pragma unroll
+        for (int pl = 0; pl < SPLIT; ++pl) {  // plane pl of an operand starts pl * plane_rows rows down
+          tma_load_2d(a_dst + pl * A_TILE, &map_x, kb * LN_BK, pl * x_plane_rows + m0, &full_bar[s]);
+          tma_load_2d(b_dst + pl * B_TILE, &map_w, kb * LN_BK, pl * w_plane_rows + n0, &full_bar[s]);
+        }
       }
     }
   } else if (warp == 1) {
@@ -215,11 +253,22 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         tc::mbar_wait(&full_bar[s], (kb / LN_STAGES) & 1);
         tc::fence_after_sync();
         const uint32_t a_addr = tc::smem_u32(smem + s * STAGE);
-        const uint32_t b_addr = a_addr + LN_BM * LN_BK * 2;
+        const uint32_t b_addr = a_addr + SPLIT * A_TILE;
 #pragma unroll
-        for (int k = 0; k < LN_BK; k += 16)
-          tc::mma_bf16(tmem, tc::make_desc_sw128(a_addr + k * 2), tc::make_desc_sw128(b_addr + k * 2),
-                       IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < LN_BK; k += 16) {
+          if (SPLIT == 1) {
+            tc::mma_bf16(tmem, tc::make_desc_sw128(a_addr + k * 2), tc::make_desc_sw128(b_addr + k * 2),
+                         IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+          } else {
+            // smallest terms first; (plane of A, plane of B)
+            constexpr int PA[6] = {1, 2, 0, 1, 0, 0}, PB[6] = {1, 0, 2, 0, 1, 0};
+#pragma unroll
+            for (int t = 0; t < 6; ++t)
+              tc::mma_bf16(tmem, tc::make_desc_sw128(a_addr + PA[t] * A_TILE + k * 2),
+                           tc::make_desc_sw128(b_addr + PB[t] * B_TILE + k * 2), IDESC,
+                           (kb > 0 || k > 0 || t > 0) ? 1u : 0u);
+          }
+        }
         tc::mma_commit(&empty_bar[s]);  // frees this stage when the MMAs above retire
       }
       tc::mma_commit(&done_bar);
@@ -285,7 +334,7 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
               const long long o = (long long)row * N + col0 + qcol;
               x.x += res[i].x; x.y += res[i].y; x.z += res[i].z; x.w += res[i].w;
               if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + o) = x;
-              if (ep.out_bf16) *reinterpret_cast<uint2*>(ep.out_bf16 + o) = pack_bf16x4(x);
+              if (ep.out_bf16) store_operand4(ep.out_bf16, o, ep.plane, x);
             }
           }
           __syncwarp();
@@ -299,7 +348,7 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             x = apply_act(x, ep.act);
             if (ep.residual) x += ep.residual[rowoff + col];
             if (ep.out_f32) ep.out_f32[rowoff + col] = x;
-            if (ep.out_bf16) ep.out_bf16[rowoff + col] = __float2bfloat16_rn(x);
+            if (ep.out_bf16) store_operand1(ep.out_bf16, rowoff + col, ep.plane, x);
           }
         }
       }
@@ -392,7 +441,7 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           if (row < M) {
             const float4 y = *tile_quad(tile, lane, i);
             const long long o = (long long)row * N + j0 + qcol;
-            if (ep.ln_out_bf16) *reinterpret_cast<uint2*>(ep.ln_out_bf16 + o) = pack_bf16x4(y);
+            if (ep.ln_out_bf16) store_operand4(ep.ln_out_bf16, o, ep.plane, y);
             if (ep.ln_out_f32) *reinterpret_cast<float4*>(ep.ln_out_f32 + o) = y;
           }
         }
@@ -447,38 +496,54 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 constexpr int LN_FUSED_WIDTH = 256;  // row width the fused-LayerNorm tile supports (d_model of the reference)
 
+// x: [split, M, K] bf16 planes, w: [split, N, K] (split = 1: plain bf16 operands)
 int launch_linear(const __nv_bfloat16* x, const __nv_bfloat16* w, int M, int N, int K,
-                  LinearEpilogue ep, const char* name, cudaStream_t stream) {
+                  LinearEpilogue ep, const char* name, cudaStream_t stream, int split = 1) {
   MPA_CHECK_ARG(K % 8 == 0, "linear: K must be a multiple of 8 (got %d)", K);
+  MPA_CHECK_ARG(split == 1 || split == 3, "linear: split must be 1 or 3");
   const bool fuse_ln = ep.ln_gamma != nullptr;
   ep.vec = (N % 8 == 0) && aligned16(ep.bias) && aligned16(ep.residual) && aligned16(ep.out_f32) &&
            aligned16(ep.out_bf16) && aligned16(ep.ln_gamma) && aligned16(ep.ln_beta) &&
-           aligned16(ep.ln_out_bf16) && aligned16(ep.ln_out_f32);
+           aligned16(ep.ln_out_bf16) && aligned16(ep.ln_out_f32) && (ep.plane % 8 == 0);
   if (fuse_ln)
     MPA_CHECK_ARG(N == LN_FUSED_WIDTH && ep.vec && ep.ln_beta != nullptr,
                   "linear: fused LayerNorm needs N == %d and 16-byte aligned rows", LN_FUSED_WIDTH);
   const int bn = fuse_ln ? LN_FUSED_WIDTH : 128;
   CUtensorMap mx, mw;
-  int rc = make_map(&mx, x, M, K, LN_BM);
+  int rc = make_map(&mx, x, split * M, K, LN_BM);
   if (rc != MPA_OK) return rc;
-  rc = make_map(&mw, w, N, K, bn);
+  rc = make_map(&mw, w, split * N, K, bn);
   if (rc != MPA_OK) return rc;
   static DeviceOnce attr;
   if (attr.pending()) {
-    MPA_CUDA(cudaFuncSetAttribute(linear_bf16_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  ln_smem_bytes(128)));
-    MPA_CUDA(cudaFuncSetAttribute(linear_bf16_kernel<LN_FUSED_WIDTH, true>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, ln_smem_bytes(LN_FUSED_WIDTH)));
+    MPA_CUDA(cudaFuncSetAttribute(linear_bf16_kernel<128, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  ln_smem_bytes(128, 1)));
+    MPA_CUDA(cudaFuncSetAttribute(linear_bf16_kernel<LN_FUSED_WIDTH, true, 1>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, ln_smem_bytes(LN_FUSED_WIDTH, 1)));
+    MPA_CUDA(cudaFuncSetAttribute(linear_bf16_kernel<128, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  ln_smem_bytes(128, 3)));
+    MPA_CUDA(cudaFuncSetAttribute(linear_bf16_kernel<LN_FUSED_WIDTH, true, 3>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, ln_smem_bytes(LN_FUSED_WIDTH, 3)));
     attr.done();
   }
   dim3 grid((M + LN_BM - 1) / LN_BM, (N + bn - 1) / bn);
   {
     ProfScope ps(name, stream);
-    if (fuse_ln)
-      linear_bf16_kernel<LN_FUSED_WIDTH, true><<<grid, LN_THREADS, ln_smem_bytes(LN_FUSED_WIDTH), stream>>>(
-          mx, mw, M, N, K, ep);
-    else
-      linear_bf16_kernel<128, false><<<grid, LN_THREADS, ln_smem_bytes(128), stream>>>(mx, mw, M, N, K, ep);
+    if (split == 1) {
+      if (fuse_ln)
+        linear_bf16_kernel<LN_FUSED_WIDTH, true, 1><<<grid, LN_THREADS, ln_smem_bytes(LN_FUSED_WIDTH, 1), stream>>>(
+            mx, mw, M, N, K, M, N, ep);
+      else
+        linear_bf16_kernel<128, false, 1><<<grid, LN_THREADS, ln_smem_bytes(128, 1), stream>>>(mx, mw, M, N, K, M,
+                                                                                             N, ep);
+    } else {
+      if (fuse_ln)
+        linear_bf16_kernel<LN_FUSED_WIDTH, true, 3><<<grid, LN_THREADS, ln_smem_bytes(LN_FUSED_WIDTH, 3), stream>>>(
+            mx, mw, M, N, K, M, N, ep);
+      else
+        linear_bf16_kernel<128, false, 3><<<grid, LN_THREADS, ln_smem_bytes(128, 3), stream>>>(mx, mw, M, N, K, M,
+                                                                                             N, ep);
+    }
   }
   MPA_LAUNCH_CHECK();
   return MPA_OK;
@@ -489,7 +554,8 @@ int launch_linear(const __nv_bfloat16* x, const __nv_bfloat16* w, int M, int N, 
 // fp32 statistics (two-pass in registers), output bf16 (GEMM operand) and/or fp32.
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, int rows, int D, float eps,
-                                 __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32) {
+                                 __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32,
+                                 long long plane) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= rows) return;
   const float* xr = x + (long long)row * D;
@@ -508,7 +574,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
   for (int i = 0; i < per; ++i) {
     const int c = lane + 32 * i;
     const float r = (v[i] - mean) * rstd * gamma[c] + beta[c];
-    if (out_bf16) out_bf16[(long long)row * D + c] = __float2bfloat16_rn(r);
+    if (out_bf16) store_operand1(out_bf16, (long long)row * D + c, plane, r);
     if (out_f32) out_f32[(long long)row * D + c] = r;
   }
 }
@@ -522,7 +588,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
 constexpr int ATT_MAX_WARPS = 32;  // one warp per query row (P <= 32): the rows run concurrently
 __global__ void __launch_bounds__(ATT_MAX_WARPS * 32, 1)
 attention_kernel(const float* __restrict__ qkv, const unsigned char* __restrict__ valid, int B, int P,
-                 int H, int hd, __nv_bfloat16* __restrict__ out, DropoutSpec drop) {
+                 int H, int hd, __nv_bfloat16* __restrict__ out, long long plane, DropoutSpec drop) {
   extern __shared__ float sm[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gw = blockIdx.x;  // (shape, head)
@@ -573,9 +639,9 @@ attention_kernel(const float* __restrict__ qkv, const unsigned char* __restrict_
       if (lane < hd) o0 = fmaf(pj, vs[j * hd + lane], o0);
       if (lane + 32 < hd) o1 = fmaf(pj, vs[j * hd + lane + 32], o1);
     }
-    __nv_bfloat16* op = out + (long long)(b * P + i) * D + h * hd;
-    if (lane < hd) op[lane] = __float2bfloat16_rn(o0);
-    if (lane + 32 < hd) op[lane + 32] = __float2bfloat16_rn(o1);
+    const long long ob = (long long)(b * P + i) * D + h * hd;
+    if (lane < hd) store_operand1(out, ob + lane, plane, o0);
+    if (lane + 32 < hd) store_operand1(out, ob + lane + 32, plane, o1);
   }
 }
 
@@ -584,19 +650,18 @@ struct CvtBatch {
   const float* src[64];
   __nv_bfloat16* dst[64];
   long long n[64];
+  long long plane[64];  // 0: one bf16 plane; else hi / mid / lo planes this many elements apart
 };
 __global__ void f32_to_bf16_batch_kernel(CvtBatch cb) {
   const float* __restrict__ in = cb.src[blockIdx.y];
   __nv_bfloat16* __restrict__ o = cb.dst[blockIdx.y];
-  const long long n = cb.n[blockIdx.y];
+  const long long n = cb.n[blockIdx.y], plane = cb.plane[blockIdx.y];
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n;
        i += (long long)gridDim.x * blockDim.x * 4) {
-    if (i + 3 < n) {
-      const float4 v = *reinterpret_cast<const float4*>(in + i);
-      *reinterpret_cast<__nv_bfloat162*>(o + i) = __floats2bfloat162_rn(v.x, v.y);
-      *reinterpret_cast<__nv_bfloat162*>(o + i + 2) = __floats2bfloat162_rn(v.z, v.w);
+    if (i + 3 < n && (plane & 3) == 0) {
+      store_operand4(o, i, plane, *reinterpret_cast<const float4*>(in + i));
     } else {
-      for (long long k = i; k < n; ++k) o[k] = __float2bfloat16_rn(in[k]);
+      for (long long k = i; k < n && k < i + 4; ++k) store_operand1(o, k, plane, in[k]);
     }
   }
 }
@@ -609,27 +674,33 @@ extern "C" {
 
 /* Y = act(X W^T + b) (+ residual); X [M,K] fp32, W [N,K] fp32 (converted to bf16
  * operands), out fp32.  Generic entry (pose head, tests). */
-size_t mpa_linear_workspace_bytes(int M, int N, int K) {
-  return align_up((size_t)M * K * 2, 256) + align_up((size_t)N * K * 2, 256);
+size_t mpa_linear_workspace_bytes_ex(int M, int N, int K, int precision) {
+  const size_t planes = precision == MPA_PRECISION_FP32 ? 3 : 1;
+  return align_up(planes * (size_t)M * K * 2, 256) + align_up(planes * (size_t)N * K * 2, 256);
 }
+size_t mpa_linear_workspace_bytes(int M, int N, int K) { return mpa_linear_workspace_bytes_ex(M, N, K, MPA_PRECISION_BF16); }
 
-int mpa_linear_forward(const float* x, const float* w, const float* bias, const float* residual, int M,
-                       int N, int K, int act, float* out, void* ws, size_t ws_bytes, void* stream_) {
+int mpa_linear_forward_ex(const float* x, const float* w, const float* bias, const float* residual, int M,
+                          int N, int K, int act, int precision, float* out, void* ws, size_t ws_bytes,
+                          void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   MPA_CHECK_ARG(M >= 0 && N > 0 && K > 0, "linear_forward: bad sizes %d %d %d", M, N, K);
   MPA_CHECK_ARG(act >= ACT_NONE && act <= ACT_LEAKY02, "linear_forward: bad activation %d", act);
+  MPA_CHECK_ARG(precision == MPA_PRECISION_BF16 || precision == MPA_PRECISION_FP32,
+                "linear_forward: bad precision %d", precision);
   if (M == 0) return MPA_OK;
   MPA_CHECK_ARG(x && w && out, "linear_forward: null pointer");
+  const int split = precision == MPA_PRECISION_FP32 ? 3 : 1;
   Scratch scratch;
-  int rc = scratch.acquire(ws, ws_bytes, mpa_linear_workspace_bytes(M, N, K), stream);
+  int rc = scratch.acquire(ws, ws_bytes, mpa_linear_workspace_bytes_ex(M, N, K, precision), stream);
   if (rc != MPA_OK) return rc;
   __nv_bfloat16* xb = (__nv_bfloat16*)scratch.base;
-  __nv_bfloat16* wb = (__nv_bfloat16*)((char*)scratch.base + align_up((size_t)M * K * 2, 256));
+  __nv_bfloat16* wb = (__nv_bfloat16*)((char*)scratch.base + align_up((size_t)split * M * K * 2, 256));
   {
     ProfScope ps("linear_operands_to_bf16", stream);
     CvtBatch cb;
-    cb.src[0] = x; cb.dst[0] = xb; cb.n[0] = (long long)M * K;
-    cb.src[1] = w; cb.dst[1] = wb; cb.n[1] = (long long)N * K;
+    cb.src[0] = x; cb.dst[0] = xb; cb.n[0] = (long long)M * K; cb.plane[0] = split == 3 ? (long long)M * K : 0;
+    cb.src[1] = w; cb.dst[1] = wb; cb.n[1] = (long long)N * K; cb.plane[1] = split == 3 ? (long long)N * K : 0;
     // enough CTAs to stream a [512 k, 512] activation matrix (DGCNN) at HBM speed
     const long long quads = ((long long)M * K + 1023) / 1024;
     const int gx = (int)(quads < 64 ? 64 : (quads > 148 * 8 ? 148 * 8 : quads));
@@ -637,7 +708,13 @@ int mpa_linear_forward(const float* x, const float* w, const float* bias, const 
   }
   MPA_LAUNCH_CHECK();
   LinearEpilogue ep{bias, residual, out, nullptr, act};
-  return launch_linear(xb, wb, M, N, K, ep, "linear_bf16", stream);
+  return launch_linear(xb, wb, M, N, K, ep, split == 3 ? "linear_fp32x3" : "linear_bf16", stream, split);
+}
+
+int mpa_linear_forward(const float* x, const float* w, const float* bias, const float* residual, int M,
+                       int N, int K, int act, float* out, void* ws, size_t ws_bytes, void* stream_) {
+  return mpa_linear_forward_ex(x, w, bias, residual, M, N, K, act, MPA_PRECISION_BF16, out, ws, ws_bytes,
+                               stream_);
 }
 
 /* Pre-LN transformer encoder (nn.TransformerEncoder with norm_first=True,
@@ -656,13 +733,14 @@ size_t mpa_transformer_mask_bytes(int B, int P, int D, int H, int FF, int layers
 
 size_t mpa_transformer_workspace_bytes(int B, int P, int D, int FF, int layers) {
   const size_t T = (size_t)B * P;
+  const size_t planes = 3;  // sized for the fp32-accurate mode (hi / mid / lo operand planes)
   size_t o = 0;
-  o += align_up((size_t)layers * ((size_t)3 * D * D + (size_t)D * D + 2 * (size_t)FF * D) * 2, 256);  // bf16 weights
-  o += align_up(T * D * 4, 256);       // residual stream x
-  o += align_up(T * D * 2, 256);       // LN output bf16
-  o += align_up(T * 3 * D * 4, 256);   // qkv fp32
-  o += align_up(T * D * 2, 256);       // attention output bf16
-  o += align_up(T * FF * 2, 256);      // FFN hidden bf16
+  o += align_up(planes * (size_t)layers * ((size_t)3 * D * D + (size_t)D * D + 2 * (size_t)FF * D) * 2, 256);  // weights
+  o += align_up(T * D * 4, 256);                // residual stream x
+  o += align_up(planes * T * D * 2, 256);       // LN output (operand)
+  o += align_up(T * 3 * D * 4, 256);            // qkv fp32
+  o += align_up(planes * T * D * 2, 256);       // attention output (operand)
+  o += align_up(planes * T * FF * 2, 256);      // FFN hidden (operand)
   return o;
 }
 
@@ -675,9 +753,12 @@ int mpa_transformer_forward(const float* tokens, const unsigned char* valid, int
                             const float* const* norm1_b, const float* const* norm2_w,
                             const float* const* norm2_b, const float* final_norm_w,
                             const float* final_norm_b, float eps, float dropout_p,
-                            unsigned long long* rng_state, unsigned char* masks, float* out, void* ws,
-                            size_t ws_bytes, void* stream_) {
+                            unsigned long long* rng_state, unsigned char* masks, int precision,
+                            float* out, void* ws, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  MPA_CHECK_ARG(precision == MPA_PRECISION_BF16 || precision == MPA_PRECISION_FP32,
+                "transformer_forward: bad precision %d", precision);
+  const int split = precision == MPA_PRECISION_FP32 ? 3 : 1;
   MPA_CHECK_ARG(B >= 0 && P > 0 && P <= 32, "transformer_forward: 1 <= P <= 32 parts (got %d)", P);
   MPA_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "transformer_forward: dropout %f", dropout_p);
   const bool drop = dropout_p > 0.f;
@@ -691,13 +772,17 @@ int mpa_transformer_forward(const float* tokens, const unsigned char* valid, int
   int rc = scratch.acquire(ws, ws_bytes, mpa_transformer_workspace_bytes(B, P, D, FF, layers), stream);
   if (rc != MPA_OK) return rc;
   char* p = (char*)scratch.base;
-  const size_t per_layer = (size_t)3 * D * D + (size_t)D * D + 2 * (size_t)FF * D;
-  __nv_bfloat16* wts = (__nv_bfloat16*)p; p += align_up((size_t)layers * per_layer * 2, 256);
+  // every weight matrix is stored as `split` consecutive planes [split][rows][cols]
+  const size_t per_layer = ((size_t)3 * D * D + (size_t)D * D + 2 * (size_t)FF * D) * split;
+  __nv_bfloat16* wts = (__nv_bfloat16*)p; p += align_up(3 * (size_t)layers * (per_layer / split) * 2, 256);
   float* x = (float*)p; p += align_up((size_t)T * D * 4, 256);
-  __nv_bfloat16* xn = (__nv_bfloat16*)p; p += align_up((size_t)T * D * 2, 256);
+  __nv_bfloat16* xn = (__nv_bfloat16*)p; p += align_up(3 * (size_t)T * D * 2, 256);
   float* qkv = (float*)p; p += align_up((size_t)T * 3 * D * 4, 256);
-  __nv_bfloat16* att = (__nv_bfloat16*)p; p += align_up((size_t)T * D * 2, 256);
+  __nv_bfloat16* att = (__nv_bfloat16*)p; p += align_up(3 * (size_t)T * D * 2, 256);
   __nv_bfloat16* hid = (__nv_bfloat16*)p;
+  const long long pl_TD = split == 3 ? (long long)T * D : 0, pl_TF = split == 3 ? (long long)T * FF : 0;
+  const size_t o_out = (size_t)3 * D * D * split, o_l1 = o_out + (size_t)D * D * split,
+               o_l2 = o_l1 + (size_t)FF * D * split;  // offsets of out_proj / linear1 / linear2 in a layer
 
   MPA_CHECK_ARG(layers * 4 <= 64, "transformer_forward: at most 16 layers");
   {
@@ -705,10 +790,11 @@ int mpa_transformer_forward(const float* tokens, const unsigned char* valid, int
     CvtBatch cb;
     for (int l = 0; l < layers; ++l) {
       __nv_bfloat16* wl = wts + (size_t)l * per_layer;
-      cb.src[4 * l + 0] = in_proj_w[l];  cb.dst[4 * l + 0] = wl;                         cb.n[4 * l + 0] = (long long)3 * D * D;
-      cb.src[4 * l + 1] = out_proj_w[l]; cb.dst[4 * l + 1] = wl + (size_t)3 * D * D;     cb.n[4 * l + 1] = (long long)D * D;
-      cb.src[4 * l + 2] = lin1_w[l];     cb.dst[4 * l + 2] = wl + (size_t)4 * D * D;     cb.n[4 * l + 2] = (long long)FF * D;
-      cb.src[4 * l + 3] = lin2_w[l];     cb.dst[4 * l + 3] = wl + (size_t)4 * D * D + (size_t)FF * D; cb.n[4 * l + 3] = (long long)FF * D;
+      cb.src[4 * l + 0] = in_proj_w[l];  cb.dst[4 * l + 0] = wl;         cb.n[4 * l + 0] = (long long)3 * D * D;
+      cb.src[4 * l + 1] = out_proj_w[l]; cb.dst[4 * l + 1] = wl + o_out; cb.n[4 * l + 1] = (long long)D * D;
+      cb.src[4 * l + 2] = lin1_w[l];     cb.dst[4 * l + 2] = wl + o_l1;  cb.n[4 * l + 2] = (long long)FF * D;
+      cb.src[4 * l + 3] = lin2_w[l];     cb.dst[4 * l + 3] = wl + o_l2;  cb.n[4 * l + 3] = (long long)FF * D;
+      for (int k = 0; k < 4; ++k) cb.plane[4 * l + k] = split == 3 ? cb.n[4 * l + k] : 0;
     }
     f32_to_bf16_batch_kernel<<<dim3(32, layers * 4), 256, 0, stream>>>(cb);
   }
@@ -721,7 +807,7 @@ int mpa_transformer_forward(const float* tokens, const unsigned char* valid, int
   if (!fused) MPA_CUDA(cudaMemcpyAsync(x, tokens, (size_t)T * D * 4, cudaMemcpyDeviceToDevice, stream));
   if (fused && layers > 0) {
     ProfScope ps("layernorm", stream);
-    layernorm_kernel<<<ln_blocks, 256, 0, stream>>>(tokens, norm1_w[0], norm1_b[0], T, D, eps, xn, nullptr);
+    layernorm_kernel<<<ln_blocks, 256, 0, stream>>>(tokens, norm1_w[0], norm1_b[0], T, D, eps, xn, nullptr, pl_TD);
     MPA_LAUNCH_CHECK();
   }
   const size_t mask_layer = (size_t)B * H * P * P + 2 * (size_t)T * D + (size_t)T * FF;
@@ -743,30 +829,32 @@ int mpa_transformer_forward(const float* tokens, const unsigned char* valid, int
     const __nv_bfloat16* wl = wts + (size_t)l * per_layer;
     if (!fused) {
       { ProfScope ps("layernorm", stream);
-        layernorm_kernel<<<ln_blocks, 256, 0, stream>>>(x, norm1_w[l], norm1_b[l], T, D, eps, xn, nullptr); }
+        layernorm_kernel<<<ln_blocks, 256, 0, stream>>>(x, norm1_w[l], norm1_b[l], T, D, eps, xn, nullptr, pl_TD); }
       MPA_LAUNCH_CHECK();
     }
     LinearEpilogue e_qkv{in_proj_b[l], nullptr, qkv, nullptr, ACT_NONE};
-    rc = launch_linear(xn, wl, T, 3 * D, D, e_qkv, "linear_qkv", stream);
+    rc = launch_linear(xn, wl, T, 3 * D, D, e_qkv, "linear_qkv", stream, split);
     if (rc != MPA_OK) return rc;
     { ProfScope ps("attention", stream);
       attention_kernel<<<B * H, 32 * (P < ATT_MAX_WARPS ? P : ATT_MAX_WARPS), att_smem, stream>>>(
-          qkv, valid, B, P, H, hd, att, site(l, 0)); }
+          qkv, valid, B, P, H, hd, att, pl_TD, site(l, 0)); }
     MPA_LAUNCH_CHECK();
     // x <- x + dropout1(out_proj(att))  [+ xn <- LayerNorm2(x)]
     LinearEpilogue e_o{out_proj_b[l], (fused && l == 0) ? tokens : x, x, nullptr, ACT_NONE};
     e_o.drop = site(l, 1);
     if (fused) { e_o.ln_gamma = norm2_w[l]; e_o.ln_beta = norm2_b[l]; e_o.ln_eps = eps; e_o.ln_out_bf16 = xn; }
-    rc = launch_linear(att, wl + (size_t)3 * D * D, T, D, D, e_o, "linear_out_proj", stream);
+    e_o.plane = pl_TD;
+    rc = launch_linear(att, wl + o_out, T, D, D, e_o, "linear_out_proj", stream, split);
     if (rc != MPA_OK) return rc;
     if (!fused) {
       { ProfScope ps("layernorm", stream);
-        layernorm_kernel<<<ln_blocks, 256, 0, stream>>>(x, norm2_w[l], norm2_b[l], T, D, eps, xn, nullptr); }
+        layernorm_kernel<<<ln_blocks, 256, 0, stream>>>(x, norm2_w[l], norm2_b[l], T, D, eps, xn, nullptr, pl_TD); }
       MPA_LAUNCH_CHECK();
     }
     LinearEpilogue e_f1{lin1_b[l], nullptr, nullptr, hid, ACT_RELU};
     e_f1.drop = site(l, 2);
-    rc = launch_linear(xn, wl + (size_t)4 * D * D, T, FF, D, e_f1, "linear_ffn1", stream);
+    e_f1.plane = pl_TF;
+    rc = launch_linear(xn, wl + o_l1, T, FF, D, e_f1, "linear_ffn1", stream, split);
     if (rc != MPA_OK) return rc;
     // x <- x + FFN2(hid)  [+ LayerNorm1 of the next layer, or the final encoder norm]
     const bool last = l + 1 == layers;
@@ -777,14 +865,15 @@ int mpa_transformer_forward(const float* tokens, const unsigned char* valid, int
     } else if (fused && final_norm_w != nullptr) {
       e_f2.ln_gamma = final_norm_w; e_f2.ln_beta = final_norm_b; e_f2.ln_eps = eps; e_f2.ln_out_f32 = out;
     }
-    rc = launch_linear(hid, wl + (size_t)4 * D * D + (size_t)FF * D, T, D, FF, e_f2, "linear_ffn2", stream);
+    e_f2.plane = pl_TD;
+    rc = launch_linear(hid, wl + o_l2, T, D, FF, e_f2, "linear_ffn2", stream, split);
     if (rc != MPA_OK) return rc;
   }
   if (fused && layers > 0) return MPA_OK;
   if (final_norm_w != nullptr) {
     { ProfScope ps("layernorm", stream);
       layernorm_kernel<<<ln_blocks, 256, 0, stream>>>(layers > 0 ? x : tokens, final_norm_w, final_norm_b, T, D,
-                                                      eps, nullptr, out); }
+                                                      eps, nullptr, out, 0); }
     MPA_LAUNCH_CHECK();
   } else {
     MPA_CUDA(cudaMemcpyAsync(out, layers > 0 ? x : tokens, (size_t)T * D * 4, cudaMemcpyDeviceToDevice, stream));

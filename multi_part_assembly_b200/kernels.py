@@ -285,8 +285,12 @@ def edge_aggregate(uv, idx, n, N, Co, k, valids=None):
     return ymax, ymin, sums
 
 
-def linear(x, w, bias=None, act=0, residual=None):
-    """act(x @ w.T + bias) (+ residual) on the tcgen05 kernel (bf16 operands)."""
+PRECISION_BF16, PRECISION_FP32 = 0, 1
+
+
+def linear(x, w, bias=None, act=0, residual=None, precision=PRECISION_BF16):
+    """act(x @ w.T + bias) (+ residual) on the tcgen05 kernel: bf16 operands, or the
+    fp32-accurate mode (three bf16 planes per operand, six products per k-step)."""
     M, K = x.shape
     N = w.shape[0]
     if K % 8:
@@ -298,13 +302,13 @@ def linear(x, w, bias=None, act=0, residual=None):
     w = w.float().contiguous()
     out = torch.empty(M, N, dtype=torch.float32, device=x.device)
     L = _lib.lib()
-    ws_bytes = L.mpa_linear_workspace_bytes(M, N, K)
+    ws_bytes = L.mpa_linear_workspace_bytes_ex(M, N, K, precision)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
     with torch.cuda.device(x.device):
-        rc = L.mpa_linear_forward(_lib.ptr(x), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(residual), M,
-                                  N, K, act, _lib.ptr(out), _lib.ptr(ws), ws_bytes,
-                                  _lib.cuda_stream(x.device))
-    _lib.check(rc, 'mpa_linear_forward')
+        rc = L.mpa_linear_forward_ex(_lib.ptr(x), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(residual), M,
+                                     N, K, act, precision, _lib.ptr(out), _lib.ptr(ws), ws_bytes,
+                                     _lib.cuda_stream(x.device))
+    _lib.check(rc, 'mpa_linear_forward_ex')
     return out
 
 
@@ -358,14 +362,9 @@ def lsap_batched(costs):
 
 
 def _dense(x, w, bf16):
-    if bf16:
-        return linear(x, w)
-    prev = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = False
-    try:
-        return x @ w.t()
-    finally:
-        torch.backends.cuda.matmul.allow_tf32 = prev
+    """x @ w.T on the tensor cores in either precision (fp32 mode: three bf16 planes per
+    operand -- an fp32 GEMM to ~1e-6 -- instead of the reference's cuBLAS SGEMM)."""
+    return linear(x, w, precision=PRECISION_BF16 if bf16 else PRECISION_FP32)
 
 
 def _bn_affine(bn, mean, var_biased, count, training):
@@ -595,7 +594,7 @@ class _TransformerFunction(torch.autograd.Function):
     the keep masks the kernels wrote (or the stock module when there is no dropout)."""
 
     @staticmethod
-    def forward(ctx, tokens, valid, encoder, num_heads, dropout_p, *params):
+    def forward(ctx, tokens, valid, encoder, num_heads, dropout_p, precision, *params):
         B, P, D = tokens.shape
         ls = encoder.layers
         FF = ls[0].linear1.out_features
@@ -618,7 +617,7 @@ class _TransformerFunction(torch.autograd.Function):
                 *[_ptr_array([t.detach() for t in g]) for g in groups],
                 _lib.ptr(fn.weight.detach()) if fn is not None else None,
                 _lib.ptr(fn.bias.detach()) if fn is not None else None,
-                float(ls[0].norm1.eps), float(dropout_p), _lib.ptr(rng), _lib.ptr(masks),
+                float(ls[0].norm1.eps), float(dropout_p), _lib.ptr(rng), _lib.ptr(masks), precision,
                 _lib.ptr(out), _lib.ptr(ws), ws_bytes, _lib.cuda_stream(dev))
         _lib.check(rc, 'mpa_transformer_forward')
         ctx.save_for_backward(tokens, valid if valid is not None else tokens.new_empty(0),
@@ -626,6 +625,7 @@ class _TransformerFunction(torch.autograd.Function):
         ctx.encoder = encoder
         ctx.num_heads = num_heads
         ctx.dropout_p = dropout_p
+        ctx.precision = precision
         if _TRANSFORMER_TRACE is not None:
             _TRANSFORMER_TRACE.append(masks)
         return out
@@ -636,7 +636,10 @@ class _TransformerFunction(torch.autograd.Function):
         encoder = ctx.encoder
         params = [p for p in encoder.parameters()]
         B, P, D = tokens.shape
-        with torch.enable_grad(), torch.autocast('cuda', dtype=torch.bfloat16):
+        prev_tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        with torch.enable_grad(), torch.autocast('cuda', dtype=torch.bfloat16,
+                                                 enabled=ctx.precision == PRECISION_BF16):
             t = tokens.detach().requires_grad_(True)
             if ctx.dropout_p > 0.:
                 FF = encoder.layers[0].linear1.out_features
@@ -647,7 +650,8 @@ class _TransformerFunction(torch.autograd.Function):
                 pad = ~valid if valid.numel() else None
                 out = encoder(t, src_key_padding_mask=pad)
             grads = torch.autograd.grad(out, [t] + params, grad.to(out.dtype), allow_unused=True)
-        return (grads[0], None, None, None, None) + tuple(grads[1:])
+        torch.backends.cuda.matmul.allow_tf32 = prev_tf32
+        return (grads[0], None, None, None, None, None) + tuple(grads[1:])
 
 
 # tests set this to a list to receive the dropout keep masks of every native forward
@@ -664,14 +668,17 @@ def transformer_forward(tokens, valid_masks, encoder, num_heads, training, dropo
              for r in (l.dropout.p, l.dropout1.p, l.dropout2.p, l.self_attn.dropout)}
     p = rates.pop() if (training and len(rates) == 1) else 0.0
     ff = layer0.linear1.out_features
-    native = _use_bf16() and layer0.norm_first and (not training or len(rates) == 0) and \
-        tokens.shape[1] <= 32 and tokens.shape[2] % 32 == 0 and \
+    # native in both precisions: bf16 operands under autocast / set_precision('bf16'), the
+    # fp32-accurate three-plane mode otherwise (the reference's default, scripts/train.py:88)
+    precision = PRECISION_BF16 if _use_bf16() else PRECISION_FP32
+    native = layer0.norm_first and (not training or len(rates) == 0) and \
+        tokens.shape[1] <= 32 and tokens.shape[2] % 32 == 0 and ff % 8 == 0 and \
         tokens.shape[2] // num_heads <= 64 and (p == 0. or ff % 32 == 0)
     if native:
         params = [p_ for p_ in encoder.parameters()]
         with torch.autocast('cuda', enabled=False):
             return _TransformerFunction.apply(tokens.float().contiguous(), valid_masks, encoder,
-                                              num_heads, p, *params)
+                                              num_heads, p, precision, *params)
     pad = None if valid_masks is None else ~valid_masks
     prev = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = False

