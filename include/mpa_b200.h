@@ -304,6 +304,26 @@ int mpa_edge_aggregate(const float* uv, const int32_t* idx, const float* valids,
                        int Co, int k, float* ymax, float* ymin, double* sums, void* ws,
                        size_t ws_bytes, void* stream);
 
+/* Second pass of an EdgeConv layer: BatchNorm2d (batch statistics from the aggregate's sums
+ * over n_valid*N*k_edges edges, or running statistics; torch's running update applied) +
+ * LeakyReLU(slope) + the max over the k edges (dgcnn.py:81-95), from ymax / ymin.  Writes the
+ * layer output [n*N,Co] (`out`, nullable) and its slice [.., c0:c0+Co] of the [n*N,ldc]
+ * concatenation conv5 reads (`out_cat`, nullable): no torch.cat. */
+int mpa_edgeconv_finish(const float* ymax, const float* ymin, const double* sums, const float* valids,
+                        int n, int N, int Co, int k_edges, const float* bn_w, const float* bn_b,
+                        float* running_mean, float* running_var, int training, float momentum,
+                        float eps, float slope, float* out, float* out_cat, int ldc, int c0,
+                        void* stream);
+
+/* conv5 epilogue (dgcnn.py:97-107): BatchNorm1d (batch statistics over the valid parts' n_valid*N
+ * points, or running statistics) + LeakyReLU(slope) on y [n*N,F], then max and mean over the N
+ * points of every part: g [n, 2F] = [max | mean] (zeros for padded parts). */
+size_t mpa_bn_pool_workspace_bytes(int n, int F);
+int mpa_bn_pool(const float* y, const float* valids, int n, int N, int F, const float* bn_w,
+                const float* bn_b, float* running_mean, float* running_var, int training,
+                float momentum, float eps, float slope, float* g, void* ws, size_t ws_bytes,
+                void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,6 +68,13 @@ _SIGNATURES = {
     'mpa_edge_aggregate_workspace_bytes': (c_size_t, [ctypes.c_longlong, c_int]),
     'mpa_edge_aggregate': (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p] * 4 +
                            [c_size_t, c_void_p]),
+    'mpa_edgeconv_finish': (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p] * 4 +
+                            [c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, c_void_p, c_void_p,
+                             c_int, c_int, c_void_p]),
+    'mpa_bn_pool_workspace_bytes': (c_size_t, [c_int] * 2),
+    'mpa_bn_pool': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int] + [c_void_p] * 4 +
+                    [c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, c_void_p, c_void_p, c_size_t,
+                     c_void_p]),
     'mpa_pose_chamfer_backward_workspace_bytes': (c_size_t, [c_int] * 3),
     'mpa_pose_chamfer_backward': (c_int, [c_void_p] * 10 + [c_int] * 4 +
                                   [c_void_p] * 5 + [c_size_t, c_void_p]),

@@ -469,6 +469,146 @@ __global__ void column_sum_stage2_kernel(const double* __restrict__ slices, int 
   sums[2 * c + 1] = s2;
 }
 
+
+// ---- BatchNorm + LeakyReLU epilogues of the EdgeConv layers and of conv5 ----------------
+// number of valid parts (valids == nullptr: all n); every thread of the CTA gets the result
+__device__ __forceinline__ float block_valid_parts(const float* __restrict__ valids, int n, float* s_red) {
+  if (valids == nullptr) return (float)n;
+  float c = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) c += valids[i] != 0.0f ? 1.f : 0.f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = c;
+  __syncthreads();
+  float t = 0.f;
+  for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) t += s_red[w];
+  __syncthreads();
+  return t;
+}
+
+// scale / shift of channel c from batch sums (training) or running statistics (eval);
+// CTA 0 also applies torch's running-statistics update (momentum, unbiased variance)
+__device__ __forceinline__ void bn_channel_affine(int c, const double* __restrict__ sums, double count,
+                                                  const float* __restrict__ w, const float* __restrict__ b,
+                                                  float* running_mean, float* running_var, int training,
+                                                  float momentum, float eps, bool update, float& scale,
+                                                  float& shift) {
+  double mean, var;
+  if (training) {
+    mean = sums[2 * c] / count;
+    var = fmax(sums[2 * c + 1] / count - mean * mean, 0.0);
+    if (update) {
+      const double unbias = count / fmax(count - 1.0, 1.0);
+      running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * mean);
+      running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * var * unbias);
+    }
+  } else {
+    mean = (double)running_mean[c];
+    var = (double)running_var[c];
+  }
+  const double sc = (double)w[c] / sqrt(var + (double)eps);
+  scale = (float)sc;
+  shift = (float)((double)b[c] - mean * sc);
+}
+
+// h = LeakyReLU(BN(max over the k edges)) from the aggregate's ymax / ymin (the affine map is
+// monotone per channel: the max over k of scale*y + shift is scale*ymax + shift for scale >= 0,
+// scale*ymin + shift otherwise).  Writes the layer output contiguously (next layer's input)
+// and into its column slice of the [M, ldc] concatenation that conv5 reads.
+constexpr int EF_THREADS = 256;
+__global__ void __launch_bounds__(EF_THREADS)
+edgeconv_finish_kernel(const float* __restrict__ ymax, const float* __restrict__ ymin,
+                       const double* __restrict__ sums, const float* __restrict__ valids, int n, int N,
+                       int Co, int k_edges, const float* __restrict__ bn_w, const float* __restrict__ bn_b,
+                       float* running_mean, float* running_var, int training, float momentum, float eps,
+                       float slope, float* __restrict__ out, float* __restrict__ out_cat, int ldc, int c0) {
+  extern __shared__ float s_aff[];  // [2][Co]
+  __shared__ float s_red[EF_THREADS / 32];
+  const float nv = block_valid_parts(valids, n, s_red);
+  const double count = (double)nv * (double)N * (double)k_edges;
+  for (int c = threadIdx.x; c < Co; c += EF_THREADS)
+    bn_channel_affine(c, sums, count, bn_w, bn_b, running_mean, running_var, training, momentum, eps,
+                      blockIdx.x == 0, s_aff[c], s_aff[Co + c]);
+  __syncthreads();
+  const long long M = (long long)n * N, total4 = M * Co / 4;  // Co % 4 == 0 (checked by the host)
+  for (long long e = (long long)blockIdx.x * EF_THREADS + threadIdx.x; e < total4;
+       e += (long long)gridDim.x * EF_THREADS) {
+    const long long p = e * 4 / Co;
+    const int c = (int)(e * 4 % Co);
+    const float4 a = *reinterpret_cast<const float4*>(ymax + e * 4);
+    const float4 b = *reinterpret_cast<const float4*>(ymin + e * 4);
+    float r[4];
+    const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float sc = s_aff[c + j], sh = s_aff[Co + c + j];
+      const float v = fmaf(sc, sc >= 0.f ? av[j] : bv[j], sh);
+      r[j] = v > 0.f ? v : slope * v;
+    }
+    const float4 o = make_float4(r[0], r[1], r[2], r[3]);
+    if (out != nullptr) *reinterpret_cast<float4*>(out + e * 4) = o;
+    if (out_cat != nullptr) *reinterpret_cast<float4*>(out_cat + p * ldc + c0 + c) = o;
+  }
+}
+
+// conv5 epilogue, pass 1: per part and channel the sum, sum of squares, max and min of
+// y [n*N, F] over the part's N points (padded parts: zeros, outside the statistics)
+__global__ void part_channel_stats_kernel(const float* __restrict__ y, const float* __restrict__ valids, int N,
+                                          int F, float* __restrict__ partial /* [n, F, 2] */,
+                                          float* __restrict__ mm /* [n, F, 2] max, min */) {
+  const int part = blockIdx.x;
+  const bool live = valids == nullptr || valids[part] != 0.0f;
+  for (int c = threadIdx.x; c < F; c += blockDim.x) {
+    float s1 = 0.f, s2 = 0.f, mx = -3.0e38f, mn = 3.0e38f;
+    if (live) {
+      const float* col = y + (long long)part * N * F + c;
+      for (int i = 0; i < N; ++i) {
+        const float v = col[(long long)i * F];
+        s1 += v; s2 = fmaf(v, v, s2);
+        mx = fmaxf(mx, v); mn = fminf(mn, v);
+      }
+    } else {
+      mx = mn = 0.f;
+    }
+    partial[((long long)part * F + c) * 2] = s1;
+    partial[((long long)part * F + c) * 2 + 1] = s2;
+    mm[((long long)part * F + c) * 2] = mx;
+    mm[((long long)part * F + c) * 2 + 1] = mn;
+  }
+}
+
+// pass 2: g[part] = [ max_i a(y_i) | mean_i a(y_i) ], a = LeakyReLU o BatchNorm (dgcnn.py:97-107)
+__global__ void bn_pool_kernel(const float* __restrict__ y, const float* __restrict__ mm,
+                               const double* __restrict__ sums, const float* __restrict__ valids, int n, int N,
+                               int F, const float* __restrict__ bn_w, const float* __restrict__ bn_b,
+                               float* running_mean, float* running_var, int training, float momentum,
+                               float eps, float slope, float* __restrict__ g /* [n, 2F] */) {
+  __shared__ float s_red[32];
+  const int part = blockIdx.x;
+  const float nv = block_valid_parts(valids, n, s_red);
+  const double count = (double)nv * (double)N;
+  const bool live = valids == nullptr || valids[part] != 0.0f;
+  for (int c = threadIdx.x; c < F; c += blockDim.x) {
+    float sc, sh;
+    bn_channel_affine(c, sums, count, bn_w, bn_b, running_mean, running_var, training, momentum, eps,
+                      part == 0, sc, sh);
+    float mx = 0.f, mean = 0.f;
+    if (live) {
+      const float top = fmaf(sc, sc >= 0.f ? mm[((long long)part * F + c) * 2] : mm[((long long)part * F + c) * 2 + 1], sh);
+      mx = top > 0.f ? top : slope * top;
+      const float* col = y + (long long)part * N * F + c;
+      float s = 0.f;
+      for (int i = 0; i < N; ++i) {
+        const float v = fmaf(sc, col[(long long)i * F], sh);
+        s += v > 0.f ? v : slope * v;
+      }
+      mean = s / (float)N;
+    }
+    g[(long long)part * 2 * F + c] = mx;
+    g[(long long)part * 2 * F + F + c] = mean;
+  }
+}
+
 }  // namespace mpa
 
 using namespace mpa;
@@ -575,6 +715,71 @@ int mpa_edge_aggregate(const float* uv, const int32_t* idx, const float* valids,
     column_sum_stage2_kernel<<<(Co + 127) / 128, 128, 0, stream>>>(slices, Co, sums);
   }
   count_launch();
+  MPA_LAUNCH_CHECK();
+  return MPA_OK;
+}
+
+
+int mpa_edgeconv_finish(const float* ymax, const float* ymin, const double* sums, const float* valids, int n,
+                        int N, int Co, int k_edges, const float* bn_w, const float* bn_b, float* running_mean,
+                        float* running_var, int training, float momentum, float eps, float slope, float* out,
+                        float* out_cat, int ldc, int c0, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MPA_CHECK_ARG(n >= 0 && N > 0 && Co > 0 && Co % 4 == 0 && Co <= 4096 && k_edges > 0, "edgeconv_finish: bad sizes");
+  if (n == 0) return MPA_OK;
+  MPA_CHECK_ARG(ymax && ymin && bn_w && bn_b && running_mean && running_var && (out || out_cat) &&
+                    (training == 0 || sums != nullptr),
+                "edgeconv_finish: null pointer");
+  MPA_CHECK_ARG(out_cat == nullptr || (ldc % 4 == 0 && c0 % 4 == 0 && c0 + Co <= ldc),
+                "edgeconv_finish: bad concatenation slice");
+  const long long total4 = (long long)n * N * Co / 4;
+  long long blocks = (total4 + EF_THREADS - 1) / EF_THREADS;
+  const long long cap = (long long)device_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  {
+    ProfScope ps("edgeconv_finish", stream);
+    edgeconv_finish_kernel<<<(unsigned)blocks, EF_THREADS, sizeof(float) * 2 * Co, stream>>>(
+        ymax, ymin, sums, valids, n, N, Co, k_edges, bn_w, bn_b, running_mean, running_var, training, momentum,
+        eps, slope, out, out_cat, ldc, c0);
+  }
+  MPA_LAUNCH_CHECK();
+  return MPA_OK;
+}
+
+size_t mpa_bn_pool_workspace_bytes(int n, int F) {
+  return 2 * align_up(sizeof(float) * 2 * (size_t)n * F, 256) + align_up(sizeof(double) * 2 * (size_t)CS_SLICES * F, 256) +
+         align_up(sizeof(double) * 2 * (size_t)F, 256);
+}
+
+int mpa_bn_pool(const float* y, const float* valids, int n, int N, int F, const float* bn_w, const float* bn_b,
+                float* running_mean, float* running_var, int training, float momentum, float eps, float slope,
+                float* g, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MPA_CHECK_ARG(n >= 0 && N > 0 && F > 0 && F <= 4096, "bn_pool: bad sizes");
+  if (n == 0) return MPA_OK;
+  MPA_CHECK_ARG(y && bn_w && bn_b && running_mean && running_var && g, "bn_pool: null pointer");
+  Scratch scratch;
+  int rc = scratch.acquire(ws, ws_bytes, mpa_bn_pool_workspace_bytes(n, F), stream);
+  if (rc != MPA_OK) return rc;
+  char* p = (char*)scratch.base;
+  float* partial = (float*)p; p += align_up(sizeof(float) * 2 * (size_t)n * F, 256);
+  float* mm = (float*)p; p += align_up(sizeof(float) * 2 * (size_t)n * F, 256);
+  double* slices = (double*)p; p += align_up(sizeof(double) * 2 * (size_t)CS_SLICES * F, 256);
+  double* sums = (double*)p;
+  const int threads = F >= 256 ? 256 : ((F + 31) / 32 * 32);
+  {
+    ProfScope ps("bn_pool_stats", stream);
+    part_channel_stats_kernel<<<n, threads, 0, stream>>>(y, valids, N, F, partial, mm);
+    column_sum_stage1_kernel<<<dim3(F, CS_SLICES), 32, 0, stream>>>(partial, n, F, slices);
+    column_sum_stage2_kernel<<<(F + 127) / 128, 128, 0, stream>>>(slices, F, sums);
+  }
+  count_launch(2);
+  MPA_LAUNCH_CHECK();
+  {
+    ProfScope ps("bn_pool", stream);
+    bn_pool_kernel<<<n, threads, 0, stream>>>(y, mm, sums, valids, n, N, F, bn_w, bn_b, running_mean, running_var,
+                                             training, momentum, eps, slope, g);
+  }
   MPA_LAUNCH_CHECK();
   return MPA_OK;
 }

@@ -361,85 +361,92 @@ def lsap_batched(costs):
     return [out[o:o + p] for o, p in zip(ooff, sizes)]
 
 
-def _dense(x, w, bf16):
-    """x @ w.T on the tensor cores in either precision (fp32 mode: three bf16 planes per
-    operand -- an fp32 GEMM to ~1e-6 -- instead of the reference's cuBLAS SGEMM)."""
-    return linear(x, w, precision=PRECISION_BF16 if bf16 else PRECISION_FP32)
+def _edgeconv_finish(ymax, ymin, sums, valids, n, N, Co, k, bn, training, out, out_cat, c0):
+    """BatchNorm2d + LeakyReLU(0.2) + max over k of one EdgeConv layer (csrc/knn.cu)."""
+    dev = ymax.device
+    with torch.cuda.device(dev):
+        rc = _lib.lib().mpa_edgeconv_finish(
+            _lib.ptr(ymax), _lib.ptr(ymin), _lib.ptr(sums), _lib.ptr(valids), n, N, Co, k,
+            _lib.ptr(bn.weight.detach()), _lib.ptr(bn.bias.detach()), _lib.ptr(bn.running_mean),
+            _lib.ptr(bn.running_var), 1 if training else 0, float(bn.momentum), float(bn.eps), 0.2,
+            _lib.ptr(out), _lib.ptr(out_cat), 0 if out_cat is None else out_cat.shape[1], c0,
+            _lib.cuda_stream(dev))
+    _lib.check(rc, 'mpa_edgeconv_finish')
 
 
-def _bn_affine(bn, mean, var_biased, count, training):
-    """scale/shift of a BatchNorm from batch moments (training: also updates the
-    running statistics like torch, unbiased variance) or running statistics.
-    `count` may be a python number or a device scalar (masked batches)."""
-    if training:
-        with torch.no_grad():
-            m = bn.momentum
-            if isinstance(count, torch.Tensor):
-                unbias = count / (count - 1).clamp_min(1)
-            else:
-                unbias = count / max(count - 1, 1)
-            bn.running_mean.mul_(1 - m).add_(mean.float(), alpha=m)
-            bn.running_var.mul_(1 - m).add_((var_biased * unbias).float(), alpha=m)
-            bn.num_batches_tracked += 1
-    else:
-        mean, var_biased = bn.running_mean.double(), bn.running_var.double()
-    scale = bn.weight.double() / torch.sqrt(var_biased + bn.eps)
-    return scale.float(), (bn.bias.double() - mean * scale).float()
-
-
-# tests set this to a list to receive the k-NN graph of every EdgeConv layer
-_DGCNN_TRACE = None
+def _bn_pool(y, valids, n, N, bn, training):
+    """conv5 epilogue: BatchNorm1d + LeakyReLU(0.2) + [max | mean] over the points -> [n, 2F]."""
+    dev = y.device
+    Fd = y.shape[1]
+    g = torch.empty(n, 2 * Fd, dtype=torch.float32, device=dev)
+    L = _lib.lib()
+    ws_bytes = L.mpa_bn_pool_workspace_bytes(n, Fd)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.mpa_bn_pool(_lib.ptr(y), _lib.ptr(valids), n, N, Fd, _lib.ptr(bn.weight.detach()),
+                           _lib.ptr(bn.bias.detach()), _lib.ptr(bn.running_mean),
+                           _lib.ptr(bn.running_var), 1 if training else 0, float(bn.momentum),
+                           float(bn.eps), 0.2, _lib.ptr(g), _lib.ptr(ws), ws_bytes,
+                           _lib.cuda_stream(dev))
+    _lib.check(rc, 'mpa_bn_pool')
+    return g
 
 
 def _dgcnn_native(x, m, training, k, bf16, valids=None):
-    """`valids` [n] float (optional): padded parts are skipped by the k-NN / EdgeConv kernels
+    """DGCNN.forward (dgcnn.py:77-109) on the native kernels only: per EdgeConv layer
+    k-NN -> one tensor-core GEMM for [W1 ; W2-W1] -> gather/aggregate over the k edges ->
+    BatchNorm + LeakyReLU + max-over-k written straight into the 512-channel concatenation;
+    then conv5 (GEMM), BatchNorm + LeakyReLU + max/mean pooling in two passes, out_fc (GEMM).
+    `valids` [n] float (optional): padded parts are skipped by the k-NN / EdgeConv kernels
     on the device, kept out of every BatchNorm statistic and get zero features -- the
     semantics of the reference's mask gather + scatter (models/dgl/network.py:90-99)
     without its host synchronisation."""
     n, N, _ = x.shape
     M = n * N
-    h = x.reshape(M, 3).float()
-    feats = []
-    nv = None if valids is None else valids.double().sum()  # device scalar: number of valid parts
-    for conv, bn in ((m.conv1, m.bn1), (m.conv2, m.bn2), (m.conv3, m.bn3), (m.conv4, m.bn4)):
+    dev = x.device
+    precision = PRECISION_BF16 if bf16 else PRECISION_FP32
+    h = x.reshape(M, 3).float().contiguous()
+    layers = ((m.conv1, m.bn1), (m.conv2, m.bn2), (m.conv3, m.bn3), (m.conv4, m.bn4))
+    widths = [conv[0].weight.shape[0] for conv, _ in layers]
+    hcat = torch.empty(M, sum(widths), dtype=torch.float32, device=dev)
+    c0 = 0
+    for (conv, bn), Co in zip(layers, widths):
         C = h.shape[1]
-        W = conv[0].weight.reshape(conv[0].weight.shape[0], 2 * C).float()
-        Co = W.shape[0]
+        W = conv[0].weight.detach().reshape(Co, 2 * C).float()
         idx = knn(h.view(n, N, C), k, valids)
         if _DGCNN_TRACE is not None:
             _DGCNN_TRACE.append(idx)
         # W [xj - xi ; xi] = W1 xj + (W2 - W1) xi
         wcat = torch.cat([W[:, :C], W[:, C:] - W[:, :C]], dim=0)
-        uv = _dense(h, wcat, bf16)
+        uv = linear(h, wcat, precision=precision)
         ymax, ymin, sums = edge_aggregate(uv, idx, n, N, Co, k, valids)
-        cnt = M * k if nv is None else nv * (N * k)
-        mean = sums[:, 0] / cnt
-        var = (sums[:, 1] / cnt - mean * mean).clamp_min(0)
-        scale, shift = _bn_affine(bn, mean, var, cnt, training)
-        h = F.leaky_relu(torch.where(scale >= 0, ymax, ymin) * scale + shift, 0.2)
-        feats.append(h)
-    y = _dense(torch.cat(feats, dim=1), m.conv5[0].weight.reshape(m.conv5[0].weight.shape[0], -1).float(), bf16)
-    cnt5 = M
+        h = torch.empty(M, Co, dtype=torch.float32, device=dev)
+        _edgeconv_finish(ymax, ymin, sums, valids, n, N, Co, k, bn, training, h, hcat, c0)
+        c0 += Co
     if training:
-        if valids is None:
-            var, mean = torch.var_mean(y.double(), dim=0, unbiased=False)
-        else:
-            w = valids.double().repeat_interleave(N).unsqueeze(1)  # [M, 1]
-            cnt5 = nv * N
-            yd = y.double()
-            mean = (yd * w).sum(0) / cnt5
-            var = ((yd * yd * w).sum(0) / cnt5 - mean * mean).clamp_min(0)
-    else:
-        mean = var = None
-    scale, shift = _bn_affine(m.bn5, mean, var, cnt5, training)
-    y = F.leaky_relu(y * scale + shift, 0.2)
+        torch._foreach_add_([bn.num_batches_tracked for _, bn in layers] + [m.bn5.num_batches_tracked], 1)
+    w5 = m.conv5[0].weight.detach().reshape(m.conv5[0].weight.shape[0], -1).float()
+    y = linear(hcat, w5, precision=precision)
     if not m.global_feat:
-        y = y.view(n, N, -1)
-        return y if valids is None else y * valids.view(n, 1, 1)
-    y = y.view(n, N, -1)
-    g = torch.cat((y.max(dim=1)[0], y.mean(dim=1)), 1)
-    out = F.linear(g, m.out_fc.weight, m.out_fc.bias)
+        # per-point features: BatchNorm + LeakyReLU only (statistics from the pooled pass)
+        Fd = y.shape[1]
+        sums = _column_stats(y, valids, n, N)
+        out = torch.empty_like(y)
+        _edgeconv_finish(y, y, sums, valids, n, N, Fd, 1, m.bn5, training, out, None, 0)
+        out = out.view(n, N, Fd)
+        return out if valids is None else out * valids.view(n, 1, 1)
+    g = _bn_pool(y, valids, n, N, m.bn5, training)
+    out = linear(g, m.out_fc.weight.detach().float(), m.out_fc.bias.detach().float(),
+                 precision=precision)
     return out if valids is None else out * valids.view(n, 1)
+
+
+def _column_stats(y, valids, n, N):
+    """[Co, 2] fp64 (sum, sum of squares) of y [n*N, F] over the valid parts' points."""
+    yd = y.double().view(n, N, -1)
+    if valids is not None:
+        yd = yd * valids.double().view(n, 1, 1)
+    return torch.stack((yd.sum((0, 1)), (yd * yd).sum((0, 1))), dim=1).contiguous()
 
 
 def _graph_feature(x, k):
