@@ -248,6 +248,10 @@ def pointnet_forward(x, convs, bns, training, global_feat=True, valids=None):
 # ---------------------------------------------------------------------------
 # DGCNN
 # ---------------------------------------------------------------------------
+# tests set this to a list to receive the k-NN graph of every EdgeConv layer
+_DGCNN_TRACE = None
+
+
 def knn(x, k=20, valids=None):
     """x [n, N, C] (points as rows) -> idx [n, N, k] int32, best first
     (replaces dgcnn.py:8-15; native kernel csrc/knn.cu).  `valids` [n]: parts flagged 0
