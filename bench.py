@@ -32,6 +32,7 @@ Keys beyond the base contract:
                  cpu_baseline, none of this repo's kernels on it
   cfg_e_strong   (config C only) cfg E at this N: global batch 256 split over the ranks for
                  512 / 1000 / 2048 points -- strong scaling = value(N) / value(1)
+  other_configs  (config C only) configs B and D, B=32 per rank, a short timed run each
   train_step     secondary figure: forward + loss + backward + gradient
                  all-reduce + Adam as one CUDA graph; `--no-train` skips it
 `--impl reference` times the CPU restatement of the reference path (the reference has no CPU
@@ -464,7 +465,32 @@ def run_native(args):
             del we
             torch.cuda.empty_cache()
 
-    mx, per_rank = max_over_ranks([ms_total, ms_e2e, ms_train] + strong_ms)
+    # BASELINE.json configs B and D on this rank count (weak scaling), so that every named
+    # configuration has a driver-visible number; `--config B|D` gives their full lines
+    others, others_ms = None, []
+    if args.config == 'C' and not args.no_extra:
+        others = []
+        for name in ('B', 'D'):
+            oc = CONFIGS[name]
+            saved = amp
+            amp = torch.bfloat16 if oc['dtype'] == 'bf16' else None  # setup()/eager_step read `amp`
+            try:
+                we = setup(oc['model'], oc['encoder'], oc['batch'], oc['valid'], oc['points'], rank)
+                k_o = max(5, min(args.steps, 20))
+                for _ in range(3):
+                    we['step']()
+                others_ms.append(timed(we['step'], k_o) / k_o)
+                others.append({'config': name, 'workload': workload(oc, world, oc['points']),
+                               'dtype': oc['dtype'], 'steps': k_o, 'cuda_graph': we['graphed'] is not None,
+                               'batch_per_gpu': oc['batch']})
+                del we
+            except Exception as e:
+                others_ms.append(0.0)
+                others.append({'config': name, 'error': repr(e)[:200]})
+            amp = saved
+            torch.cuda.empty_cache()
+
+    mx, per_rank = max_over_ranks([ms_total, ms_e2e, ms_train] + strong_ms + others_ms)
     ms_total, ms_e2e, ms_train = mx[:3]
     if train is not None and 'error' not in train:
         train['ms_per_step'] = ms_train / train['steps']
@@ -474,6 +500,11 @@ def run_native(args):
             e['ms_per_step'] = ms
             e['ms_per_step_ranks'] = ranks
             e['shapes_per_s'] = 256 / (ms / 1e3)
+    if others is not None:
+        for e, ms in zip(others, mx[3 + len(strong_ms):]):
+            if 'error' not in e:
+                e['ms_per_step'] = ms
+                e['shapes_per_s'] = e['batch_per_gpu'] * world / (ms / 1e3)
     if world > 1:
         # last collective done.  The captured graphs hold NCCL resources and tearing the
         # process group down around them can block: ranks leave without the teardown.
@@ -577,6 +608,7 @@ def run_native(args):
         'cpu_baseline': cpu,
         'reference_gpu_build': ref_gpu,
         'cfg_e_strong': strong,
+        'other_configs': others,
     }
     args.emit(line)
     if world > 1:
