@@ -549,6 +549,387 @@ int launch_linear(const __nv_bfloat16* x, const __nv_bfloat16* w, int M, int N, 
   return MPA_OK;
 }
 
+// ======================================================================================
+// Fused second half of a pre-LN encoder layer for d_model = 256 (bf16 operands):
+//     x  <- x + dropout1(att W_o^T + b_o)            (out_proj)
+//     h  <- LayerNorm2(x)
+//     x  <- x + dropout2(dropout(relu(h W_1^T + b_1)) W_2^T + b_2)      (FFN)
+//     xn <- LayerNorm_next(x)        (norm1 of the next layer, or the encoder's final norm)
+// One CTA owns 128 token rows for the whole chain, so the residual stream, LayerNorm2's
+// output and the FFN hidden activations never leave the SM: the att tile and LN2(x) are A
+// operands in shared memory (K-major, 128-byte swizzle, written by the epilogue warps), the
+// hidden layer is produced 128 columns at a time into a double-buffered A operand while the
+// previous chunk is already being contracted with W_2, and the accumulators live in TMEM
+// (256 columns for the two 256-wide results, 2 x 128 for the hidden chunks).  Weights stream
+// through a 2-stage TMA ring of 32 KB tiles.  Replaces three GEMM launches per layer
+// (out_proj, linear1, linear2 of nn.TransformerEncoderLayer, transformer.py:23-34).
+constexpr int FB_D = 256;           // d_model
+constexpr int FB_CH = 128;          // hidden columns per chunk
+constexpr int FB_STAGE = 32 * 1024; // one ring stage: a [256 x 64] weight tile or two [128 x 64] tiles
+constexpr int FB_NST = 2;
+constexpr int FB_KTILE = LN_BM * LN_BK * 2;  // [128 x 64] bf16 A-operand k-block = 16 KB
+constexpr int FB_SMEM = 2 * 4 * FB_KTILE + FB_NST * FB_STAGE + 1024;
+constexpr int FB_EPI = LN_EPI_WARPS * 32;    // 256 epilogue threads
+
+struct FfnBlockArgs {
+  const float* b_o; const float* b1; const float* b2;
+  const float* ln2_g; const float* ln2_b; const float* lnn_g; const float* lnn_b;  // lnn_* may be null
+  const float* x_in;        // [M, 256] residual stream in
+  float* x_out;             // [M, 256] residual stream out (may alias x_in); null: not stored
+  __nv_bfloat16* xn_out;    // [M, 256] LayerNorm_next(x) as the next GEMM's operand (nullable)
+  float* out_f32;           // [M, 256] fp32 result: LayerNorm_next(x) if lnn_g else x (nullable)
+  int M, FF;
+  float eps;
+  DropoutSpec drop1, drop_h, drop2;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+
+// LayerNorm of the 128 rows parked in TMEM columns [0, 256): statistics in two passes
+// (mean, centred variance), the two half-row warps of a row meet in shared memory.
+// `emit(j0, v)` receives 32 normalised columns j0.. of this thread's row.
+template <typename Emit>
+__device__ __forceinline__ void fb_layernorm_rows(uint32_t taddr, int c_begin, int c_end, int half, int row_local,
+                                                  float sum, float (*ln_part)[2][LN_BM], const float* g,
+                                                  const float* b, float eps, Emit emit) {
+  ln_part[0][half][row_local] = sum;
+  tc::group_sync(1, FB_EPI);
+  const float mean = (ln_part[0][0][row_local] + ln_part[0][1][row_local]) * (1.0f / FB_D);
+  float sq = 0.f;
+#pragma unroll 1
+  for (int j0 = c_begin; j0 < c_end; j0 += 32) {
+    float v[32];
+    tc::tmem_ld32(taddr + (uint32_t)j0, v);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { const float d = v[j] - mean; sq = fmaf(d, d, sq); }
+  }
+  ln_part[1][half][row_local] = sq;
+  tc::group_sync(1, FB_EPI);
+  const float rstd = rsqrtf((ln_part[1][0][row_local] + ln_part[1][1][row_local]) * (1.0f / FB_D) + eps);
+#pragma unroll 1
+  for (int j0 = c_begin; j0 < c_end; j0 += 32) {
+    float v[32];
+    tc::tmem_ld32(taddr + (uint32_t)j0, v);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = (v[j] - mean) * rstd * g[j0 + j] + b[j0 + j];
+    emit(j0, v);
+  }
+  tc::group_sync(1, FB_EPI);  // ln_part may be reused
+}
+
+// 32 fp32 values of one row -> bf16 into a K-major SWIZZLE_128B A operand made of [128 x 64]
+// k-block tiles (`tile0` = k-block holding column col0's first element)
+__device__ __forceinline__ void fb_store_operand_row(uint8_t* tiles, int row, int col0, const float* v) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {  // four 16-byte chunks of 8 bf16
+    const int col = col0 + 8 * j;
+    uint8_t* dst = tiles + (col >> 6) * FB_KTILE + tc::sw128_offset(row, col & 63);
+    const uint2 lo = pack_bf16x4(make_float4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]));
+    const uint2 hi = pack_bf16x4(make_float4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]));
+    *reinterpret_cast<uint4*>(dst) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+  }
+}
+
+__global__ void __launch_bounds__(LN_THREADS, 1)
+encoder_ffn_block_kernel(const __grid_constant__ CUtensorMap map_att, const __grid_constant__ CUtensorMap map_wo,
+                         const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2,
+                         FfnBlockArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* A0 = smem;                      // att tile (4 k-blocks), later hid[2] (2 k-blocks each)
+  uint8_t* A1 = smem + 4 * FB_KTILE;       // LayerNorm2(x) (4 k-blocks)
+  uint8_t* ring = smem + 8 * FB_KTILE;
+  __shared__ uint64_t full_bar[FB_NST], empty_bar[FB_NST];
+  __shared__ uint64_t att_full, acc0_o_done, a1_ready, acc0_f2_done;
+  __shared__ uint64_t f1_done[2], acc1_free[2], hid_ready[2], hid_free[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float ln_part[2][2][LN_BM];
+  __shared__ __align__(16) float s_vec[6][FB_D];  // b_o, ln2 g, ln2 b, b2, lnn g, lnn b
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * LN_BM;
+  const int C = a.FF / FB_CH;  // hidden chunks
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < FB_NST; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
+    tc::mbar_init(&att_full, 1);
+    tc::mbar_init(&acc0_o_done, 1);
+    tc::mbar_init(&a1_ready, FB_EPI);
+    tc::mbar_init(&acc0_f2_done, 1);
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&f1_done[i], 1);
+      tc::mbar_init(&acc1_free[i], FB_EPI);
+      tc::mbar_init(&hid_ready[i], FB_EPI);
+      tc::mbar_init(&hid_free[i], 1);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc<512>(&tmem_base_s);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t acc0 = tmem, acc1[2] = {tmem + 256u, tmem + 384u};
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer: tiles in exactly the order the MMA warp consumes them =====
+      mbar_expect_tx(&att_full, 4 * FB_KTILE);
+      for (int kb = 0; kb < 4; ++kb) tma_load_2d(A0 + kb * FB_KTILE, &map_att, kb * LN_BK, m0, &att_full);
+      int it = 0;
+      auto stage = [&](auto&& issue) {
+        const int s = it % FB_NST;
+        if (it >= FB_NST) tc::mbar_wait(&empty_bar[s], ((it / FB_NST) - 1) & 1);
+        mbar_expect_tx(&full_bar[s], FB_STAGE);
+        issue(ring + s * FB_STAGE, &full_bar[s]);
+        ++it;
+      };
+      for (int kb = 0; kb < 4; ++kb)  // W_o [256 x 64] k-blocks
+        stage([&](uint8_t* dst, uint64_t* bar) { tma_load_2d(dst, &map_wo, kb * LN_BK, 0, bar); });
+      auto f1 = [&](int c) {  // W_1 rows [128 c, +128): two stages of two [128 x 64] k-blocks
+        for (int st = 0; st < 2; ++st)
+          stage([&](uint8_t* dst, uint64_t* bar) {
+            tma_load_2d(dst, &map_w1, (2 * st) * LN_BK, c * FB_CH, bar);
+            tma_load_2d(dst + FB_STAGE / 2, &map_w1, (2 * st + 1) * LN_BK, c * FB_CH, bar);
+          });
+      };
+      auto f2 = [&](int c) {  // W_2 [256 x 64] k-blocks of hidden columns [128 c, +128)
+        for (int st = 0; st < 2; ++st)
+          stage([&](uint8_t* dst, uint64_t* bar) { tma_load_2d(dst, &map_w2, c * FB_CH + st * LN_BK, 0, bar); });
+      };
+      f1(0);
+      if (C > 1) f1(1);
+      for (int c = 0; c < C; ++c) {
+        f2(c);
+        if (c + 2 < C) f1(c + 2);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      constexpr uint32_t IDESC_256 = tc::make_idesc_bf16(LN_BM, 256);
+      constexpr uint32_t IDESC_128 = tc::make_idesc_bf16(LN_BM, FB_CH);
+      int it = 0;
+      auto wait_stage = [&]() -> uint32_t {
+        const int s = it % FB_NST;
+        tc::mbar_wait(&full_bar[s], (it / FB_NST) & 1);
+        tc::fence_after_sync();
+        return tc::smem_u32(ring + s * FB_STAGE);
+      };
+      auto release_stage = [&]() { tc::mma_commit(&empty_bar[it % FB_NST]); ++it; };
+      // ---- out_proj: acc0 = att W_o^T ----
+      tc::mbar_wait(&att_full, 0);
+      tc::fence_after_sync();
+      for (int kb = 0; kb < 4; ++kb) {
+        const uint32_t b_addr = wait_stage();
+        const uint32_t a_addr = tc::smem_u32(A0 + kb * FB_KTILE);
+#pragma unroll
+        for (int k = 0; k < LN_BK; k += 16)
+          tc::mma_bf16(acc0, tc::make_desc_sw128(a_addr + k * 2), tc::make_desc_sw128(b_addr + k * 2), IDESC_256,
+                       (kb > 0 || k > 0) ? 1u : 0u);
+        release_stage();
+      }
+      tc::mma_commit(&acc0_o_done);
+      // ---- FFN ----
+      tc::mbar_wait(&a1_ready, 0);  // LayerNorm2(x) is in A1; acc0 and A0 are free again
+      tc::fence_after_sync();
+      auto f1 = [&](int c) {  // acc1[c & 1] = A1 W_1[chunk c]^T
+        for (int st = 0; st < 2; ++st) {
+          const uint32_t b_addr = wait_stage();
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            const uint32_t a_addr = tc::smem_u32(A1 + (2 * st + kk) * FB_KTILE);
+#pragma unroll
+            for (int k = 0; k < LN_BK; k += 16)
+              tc::mma_bf16(acc1[c & 1], tc::make_desc_sw128(a_addr + k * 2),
+                           tc::make_desc_sw128(b_addr + kk * (FB_STAGE / 2) + k * 2), IDESC_128,
+                           (st > 0 || kk > 0 || k > 0) ? 1u : 0u);
+          }
+          release_stage();
+        }
+        tc::mma_commit(&f1_done[c & 1]);
+      };
+      f1(0);
+      if (C > 1) f1(1);
+      for (int c = 0; c < C; ++c) {
+        const int b = c & 1;
+        tc::mbar_wait(&hid_ready[b], (c >> 1) & 1);  // relu(hidden chunk c) is in hid[b]
+        tc::fence_after_sync();
+        for (int st = 0; st < 2; ++st) {           // acc0 += hid[b] W_2[:, chunk c]^T
+          const uint32_t b_addr = wait_stage();
+          const uint32_t a_addr = tc::smem_u32(A0 + (2 * b + st) * FB_KTILE);
+#pragma unroll
+          for (int k = 0; k < LN_BK; k += 16)
+            tc::mma_bf16(acc0, tc::make_desc_sw128(a_addr + k * 2), tc::make_desc_sw128(b_addr + k * 2), IDESC_256,
+                         (c > 0 || st > 0 || k > 0) ? 1u : 0u);
+          release_stage();
+        }
+        tc::mma_commit(&hid_free[b]);
+        if (c + 2 < C) {
+          tc::mbar_wait(&acc1_free[b], (c >> 1) & 1);  // the epilogue has read acc1[b]
+          tc::fence_after_sync();
+          f1(c + 2);
+        }
+      }
+      tc::mma_commit(&acc0_f2_done);
+    }
+  } else {  // ===== epilogue warps 2..9: TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4 =====
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int row_local = q * 32 + lane, row = m0 + row_local;
+    const bool row_ok = row < a.M;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    for (int c = threadIdx.x - 64; c < FB_D; c += FB_EPI) {
+      s_vec[0][c] = __ldg(a.b_o + c);
+      s_vec[1][c] = __ldg(a.ln2_g + c);
+      s_vec[2][c] = __ldg(a.ln2_b + c);
+      s_vec[3][c] = __ldg(a.b2 + c);
+      s_vec[4][c] = a.lnn_g != nullptr ? __ldg(a.lnn_g + c) : 1.f;
+      s_vec[5][c] = a.lnn_g != nullptr ? __ldg(a.lnn_b + c) : 0.f;
+    }
+    tc::group_sync(1, FB_EPI);
+    const int c_begin = half * (FB_D / 2), c_end = c_begin + FB_D / 2;
+    const long long rowoff = (long long)row * FB_D;
+
+    // ---- E1: x = acc0 + b_o (dropout1) + x_in ; LayerNorm2 -> A1 ----
+    tc::mbar_wait(&acc0_o_done, 0);
+    tc::fence_after_sync();
+    float sum = 0.f;
+#pragma unroll 1
+    for (int j0 = c_begin; j0 < c_end; j0 += 32) {
+      float v[32];
+      tc::tmem_ld32(acc0 + lane_off + (uint32_t)j0, v);
+      tc::tmem_ld_wait();
+      add_bias_act(v, s_vec[0], j0, ACT_NONE);
+      if (a.drop1.rng != nullptr && row_ok) dropout32(v, a.drop1, row, j0, FB_D);
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 r = *reinterpret_cast<const float4*>(a.x_in + rowoff + j0 + 4 * j);
+          v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)  // x after attention: FFN residual, re-read in E3 by this thread
+          *reinterpret_cast<float4*>(a.x_out + rowoff + j0 + 4 * j) =
+              make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sum += v[j];
+      tc::tmem_st32(acc0 + lane_off + (uint32_t)j0, v);
+    }
+    tc::tmem_st_wait();
+    fb_layernorm_rows(acc0 + lane_off, c_begin, c_end, half, row_local, sum, ln_part, s_vec[1], s_vec[2], a.eps,
+                      [&](int j0, const float* v) { fb_store_operand_row(A1, row_local, j0, v); });
+    tc::fence_async_smem();        // A1 written through the generic proxy -> visible to the tensor core
+    tc::fence_before_sync();       // ... and the TMEM reads of acc0 are complete
+    mbar_arrive(&a1_ready);
+
+    // ---- E2: hidden chunks: relu(acc1 + b_1) (dropout) -> hid[b] ----
+    for (int c = 0; c < C; ++c) {
+      const int b = c & 1;
+      tc::mbar_wait(&f1_done[b], (c >> 1) & 1);
+      tc::fence_after_sync();
+      float v[2][32];
+      const int h0 = half * (FB_CH / 2);  // this warp's 64 of the chunk's 128 columns
+      tc::tmem_ld32(acc1[b] + lane_off + (uint32_t)h0, v[0]);
+      tc::tmem_ld32(acc1[b] + lane_off + (uint32_t)(h0 + 32), v[1]);
+      tc::tmem_ld_wait();
+      tc::fence_before_sync();
+      mbar_arrive(&acc1_free[b]);  // acc1[b] may be overwritten by chunk c + 2
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int col = c * FB_CH + h0 + 32 * t;  // hidden column of v[t][0]
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[t][j] = fmaxf(v[t][j] + __ldg(a.b1 + col + j), 0.f);
+        if (a.drop_h.rng != nullptr && row_ok) dropout32(v[t], a.drop_h, row, col, a.FF);
+      }
+      if (c >= 2) {  // chunk c - 2's contraction with W_2 must have consumed hid[b]
+        tc::mbar_wait(&hid_free[b], ((c >> 1) - 1) & 1);
+      }
+      fb_store_operand_row(A0 + 2 * b * FB_KTILE, row_local, h0, v[0]);
+      fb_store_operand_row(A0 + 2 * b * FB_KTILE, row_local, h0 + 32, v[1]);
+      tc::fence_async_smem();
+      mbar_arrive(&hid_ready[b]);
+    }
+
+    // ---- E3: x = acc0 + b_2 (dropout2) + x ; LayerNorm_next ----
+    tc::mbar_wait(&acc0_f2_done, 0);
+    tc::fence_after_sync();
+    sum = 0.f;
+    const bool norm = a.lnn_g != nullptr;
+#pragma unroll 1
+    for (int j0 = c_begin; j0 < c_end; j0 += 32) {
+      float v[32];
+      tc::tmem_ld32(acc0 + lane_off + (uint32_t)j0, v);
+      tc::tmem_ld_wait();
+      add_bias_act(v, s_vec[3], j0, ACT_NONE);
+      if (a.drop2.rng != nullptr && row_ok) dropout32(v, a.drop2, row, j0, FB_D);
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 r = *reinterpret_cast<const float4*>(a.x_out + rowoff + j0 + 4 * j);
+          v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          *reinterpret_cast<float4*>(a.x_out + rowoff + j0 + 4 * j) = o;
+          if (!norm && a.out_f32 != nullptr) *reinterpret_cast<float4*>(a.out_f32 + rowoff + j0 + 4 * j) = o;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sum += v[j];
+      if (norm) tc::tmem_st32(acc0 + lane_off + (uint32_t)j0, v);
+    }
+    if (norm) {
+      tc::tmem_st_wait();
+      fb_layernorm_rows(acc0 + lane_off, c_begin, c_end, half, row_local, sum, ln_part, s_vec[4], s_vec[5], a.eps,
+                        [&](int j0, const float* v) {
+                          if (!row_ok) return;
+#pragma unroll
+                          for (int j = 0; j < 8; ++j) {
+                            const float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            if (a.xn_out != nullptr)
+                              *reinterpret_cast<uint2*>(a.xn_out + rowoff + j0 + 4 * j) = pack_bf16x4(o);
+                            if (a.out_f32 != nullptr)
+                              *reinterpret_cast<float4*>(a.out_f32 + rowoff + j0 + 4 * j) = o;
+                          }
+                        });
+    }
+    tc::fence_before_sync();
+  }
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc<512>(tmem);
+}
+
+// host side: tensor maps with a caller-chosen box height
+static int make_map_box(CUtensorMap* map, const void* base, int rows, int cols, int box_rows) {
+  return make_map(map, base, rows, cols, box_rows);
+}
+
+int launch_ffn_block(const __nv_bfloat16* att, const __nv_bfloat16* wo, const __nv_bfloat16* w1,
+                     const __nv_bfloat16* w2, FfnBlockArgs a, cudaStream_t stream) {
+  MPA_CHECK_ARG(a.FF % FB_CH == 0 && a.FF >= FB_CH, "ffn_block: FF must be a multiple of %d", FB_CH);
+  CUtensorMap m_att, m_wo, m_w1, m_w2;
+  int rc = make_map_box(&m_att, att, a.M, FB_D, LN_BM);
+  if (rc == MPA_OK) rc = make_map_box(&m_wo, wo, FB_D, FB_D, 256);
+  if (rc == MPA_OK) rc = make_map_box(&m_w1, w1, a.FF, FB_D, FB_CH);
+  if (rc == MPA_OK) rc = make_map_box(&m_w2, w2, FB_D, a.FF, 256);
+  if (rc != MPA_OK) return rc;
+  static DeviceOnce attr;
+  if (attr.pending()) {
+    MPA_CUDA(cudaFuncSetAttribute(encoder_ffn_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM));
+    attr.done();
+  }
+  {
+    ProfScope ps("encoder_ffn_block", stream);
+    encoder_ffn_block_kernel<<<(a.M + LN_BM - 1) / LN_BM, LN_THREADS, FB_SMEM, stream>>>(m_att, m_wo, m_w1, m_w2, a);
+  }
+  MPA_LAUNCH_CHECK();
+  return MPA_OK;
+}
+
 // ---- small token-level kernels ---------------------------------------------
 // LayerNorm over the last dim (D <= 1024, multiple of 32): one warp per row,
 // fp32 statistics (two-pass in registers), output bf16 (GEMM operand) and/or fp32.
@@ -839,6 +1220,24 @@ int mpa_transformer_forward(const float* tokens, const unsigned char* valid, int
       attention_kernel<<<B * H, 32 * (P < ATT_MAX_WARPS ? P : ATT_MAX_WARPS), att_smem, stream>>>(
           qkv, valid, B, P, H, hd, att, pl_TD, site(l, 0)); }
     MPA_LAUNCH_CHECK();
+    const bool last = l + 1 == layers;
+    if (fused && split == 1 && FF % FB_CH == 0) {
+      // out_proj + LayerNorm2 + FFN + the next LayerNorm in ONE kernel (128 token rows per CTA)
+      FfnBlockArgs fa{};
+      fa.b_o = out_proj_b[l]; fa.b1 = lin1_b[l]; fa.b2 = lin2_b[l];
+      fa.ln2_g = norm2_w[l]; fa.ln2_b = norm2_b[l];
+      fa.lnn_g = last ? final_norm_w : norm1_w[l + 1];
+      fa.lnn_b = last ? final_norm_b : norm1_b[l + 1];
+      fa.x_in = l == 0 ? tokens : x;
+      fa.x_out = x;
+      fa.xn_out = last ? nullptr : xn;
+      fa.out_f32 = last ? out : nullptr;
+      fa.M = T; fa.FF = FF; fa.eps = eps;
+      fa.drop1 = site(l, 1); fa.drop_h = site(l, 2); fa.drop2 = site(l, 3);
+      rc = launch_ffn_block(att, wl + o_out, wl + o_l1, wl + o_l2, fa, stream);
+      if (rc != MPA_OK) return rc;
+      continue;
+    }
     // x <- x + dropout1(out_proj(att))  [+ xn <- LayerNorm2(x)]
     LinearEpilogue e_o{out_proj_b[l], (fused && l == 0) ? tokens : x, x, nullptr, ACT_NONE};
     e_o.drop = site(l, 1);
@@ -857,7 +1256,6 @@ int mpa_transformer_forward(const float* tokens, const unsigned char* valid, int
     rc = launch_linear(xn, wl + o_l1, T, FF, D, e_f1, "linear_ffn1", stream, split);
     if (rc != MPA_OK) return rc;
     // x <- x + FFN2(hid)  [+ LayerNorm1 of the next layer, or the final encoder norm]
-    const bool last = l + 1 == layers;
     LinearEpilogue e_f2{lin2_b[l], x, (fused && last) ? (final_norm_w == nullptr ? out : nullptr) : x, nullptr, ACT_NONE};
     e_f2.drop = site(l, 3);
     if (fused && !last) {
