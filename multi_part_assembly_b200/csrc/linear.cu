@@ -15,6 +15,7 @@
 // (models/pn_transformer/transformer.py:23-34) and PoseRegressor
 // (models/modules/regressor.py:45-68).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "mpa_common.cuh"
 #include "tc05.cuh"
@@ -570,6 +571,7 @@ constexpr int FB_NST = 2;
 constexpr int FB_KTILE = LN_BM * LN_BK * 2;  // [128 x 64] bf16 A-operand k-block = 16 KB
 constexpr int FB_SMEM = 2 * 4 * FB_KTILE + FB_NST * FB_STAGE + 1024;
 constexpr int FB_EPI = LN_EPI_WARPS * 32;    // 256 epilogue threads
+constexpr int FB_MAX_FF = 1024;              // hidden width whose bias fits the static shared memory
 
 struct FfnBlockArgs {
   const float* b_o; const float* b1; const float* b2;
@@ -581,7 +583,9 @@ struct FfnBlockArgs {
   int M, FF;
   float eps;
   DropoutSpec drop1, drop_h, drop2;
+  long long* dbg = nullptr;  // MPA_FFN_DEBUG: cycle stamps of CTA 0 (see tools/profile_transformer.py)
 };
+#define FB_STAMP(i) do { if (a.dbg != nullptr && blockIdx.x == 0) a.dbg[i] = clock64(); } while (0)
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
@@ -649,6 +653,7 @@ encoder_ffn_block_kernel(const __grid_constant__ CUtensorMap map_att, const __gr
   __shared__ uint32_t tmem_base_s;
   __shared__ float ln_part[2][2][LN_BM];
   __shared__ __align__(16) float s_vec[6][FB_D];  // b_o, ln2 g, ln2 b, b2, lnn g, lnn b
+  __shared__ __align__(16) float s_b1[FB_MAX_FF];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * LN_BM;
@@ -720,8 +725,10 @@ encoder_ffn_block_kernel(const __grid_constant__ CUtensorMap map_att, const __gr
       };
       auto release_stage = [&]() { tc::mma_commit(&empty_bar[it % FB_NST]); ++it; };
       // ---- out_proj: acc0 = att W_o^T ----
+      FB_STAMP(0);
       tc::mbar_wait(&att_full, 0);
       tc::fence_after_sync();
+      FB_STAMP(1);
       for (int kb = 0; kb < 4; ++kb) {
         const uint32_t b_addr = wait_stage();
         const uint32_t a_addr = tc::smem_u32(A0 + kb * FB_KTILE);
@@ -732,9 +739,11 @@ encoder_ffn_block_kernel(const __grid_constant__ CUtensorMap map_att, const __gr
         release_stage();
       }
       tc::mma_commit(&acc0_o_done);
+      FB_STAMP(2);
       // ---- FFN ----
       tc::mbar_wait(&a1_ready, 0);  // LayerNorm2(x) is in A1; acc0 and A0 are free again
       tc::fence_after_sync();
+      FB_STAMP(3);
       auto f1 = [&](int c) {  // acc1[c & 1] = A1 W_1[chunk c]^T
         for (int st = 0; st < 2; ++st) {
           const uint32_t b_addr = wait_stage();
@@ -757,6 +766,7 @@ encoder_ffn_block_kernel(const __grid_constant__ CUtensorMap map_att, const __gr
         const int b = c & 1;
         tc::mbar_wait(&hid_ready[b], (c >> 1) & 1);  // relu(hidden chunk c) is in hid[b]
         tc::fence_after_sync();
+        FB_STAMP(8 + c);
         for (int st = 0; st < 2; ++st) {           // acc0 += hid[b] W_2[:, chunk c]^T
           const uint32_t b_addr = wait_stage();
           const uint32_t a_addr = tc::smem_u32(A0 + (2 * b + st) * FB_KTILE);
@@ -774,6 +784,7 @@ encoder_ffn_block_kernel(const __grid_constant__ CUtensorMap map_att, const __gr
         }
       }
       tc::mma_commit(&acc0_f2_done);
+      FB_STAMP(4);
     }
   } else {  // ===== epilogue warps 2..9: TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4 =====
     const int q = warp & 3, half = (warp - 2) >> 2;
@@ -788,13 +799,28 @@ encoder_ffn_block_kernel(const __grid_constant__ CUtensorMap map_att, const __gr
       s_vec[4][c] = a.lnn_g != nullptr ? __ldg(a.lnn_g + c) : 1.f;
       s_vec[5][c] = a.lnn_g != nullptr ? __ldg(a.lnn_b + c) : 0.f;
     }
+    for (int c = threadIdx.x - 64; c < a.FF; c += FB_EPI) s_b1[c] = __ldg(a.b1 + c);
     tc::group_sync(1, FB_EPI);
     const int c_begin = half * (FB_D / 2), c_end = c_begin + FB_D / 2;
-    const long long rowoff = (long long)row * FB_D;
 
     // ---- E1: x = acc0 + b_o (dropout1) + x_in ; LayerNorm2 -> A1 ----
     tc::mbar_wait(&acc0_o_done, 0);
     tc::fence_after_sync();
+    if (threadIdx.x == 64) FB_STAMP(32);
+    // Rows meet global memory through a per-warp [32 x 32] fp32 staging tile (in the A0 region,
+    // idle here): a TMEM lane is a row, a coalesced access wants 4 rows x 128 contiguous bytes.
+    float* tile = reinterpret_cast<float*>(A0) + (warp - 2) * EP_TILE_FLOATS;
+    const int qrow0 = m0 + q * 32 + (lane >> 3), qcol = 4 * (lane & 7);
+    float4 res[8];
+    auto fetch_rows = [&](const float* src, int j0) {  // rows qrow0 + 4 i, columns j0 + qcol .. +3
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = qrow0 + 4 * i;
+        res[i] = r < a.M ? *reinterpret_cast<const float4*>(src + (long long)r * FB_D + j0 + qcol)
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    fetch_rows(a.x_in, c_begin);
     float sum = 0.f;
 #pragma unroll 1
     for (int j0 = c_begin; j0 < c_end; j0 += 32) {
@@ -803,17 +829,24 @@ encoder_ffn_block_kernel(const __grid_constant__ CUtensorMap map_att, const __gr
       tc::tmem_ld_wait();
       add_bias_act(v, s_vec[0], j0, ACT_NONE);
       if (a.drop1.rng != nullptr && row_ok) dropout32(v, a.drop1, row, j0, FB_D);
-      if (row_ok) {
+      tile_put_row(tile, lane, v);
+      __syncwarp();
+      float4 xq[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 r = *reinterpret_cast<const float4*>(a.x_in + rowoff + j0 + 4 * j);
-          v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j)  // x after attention: FFN residual, re-read in E3 by this thread
-          *reinterpret_cast<float4*>(a.x_out + rowoff + j0 + 4 * j) =
-              make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      for (int i = 0; i < 8; ++i) {
+        const float4 t = *tile_quad(tile, lane, i);
+        xq[i] = make_float4(t.x + res[i].x, t.y + res[i].y, t.z + res[i].z, t.w + res[i].w);
       }
+      if (j0 + 32 < c_end) fetch_rows(a.x_in, j0 + 32);  // next slab: before this one's stores (x may alias)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = qrow0 + 4 * i;
+        if (r < a.M) *reinterpret_cast<float4*>(a.x_out + (long long)r * FB_D + j0 + qcol) = xq[i];
+        *tile_quad(tile, lane, i) = xq[i];
+      }
+      __syncwarp();
+      tile_get_row(tile, lane, v);
+      __syncwarp();
 #pragma unroll
       for (int j = 0; j < 32; ++j) sum += v[j];
       tc::tmem_st32(acc0 + lane_off + (uint32_t)j0, v);
@@ -824,12 +857,14 @@ encoder_ffn_block_kernel(const __grid_constant__ CUtensorMap map_att, const __gr
     tc::fence_async_smem();        // A1 written through the generic proxy -> visible to the tensor core
     tc::fence_before_sync();       // ... and the TMEM reads of acc0 are complete
     mbar_arrive(&a1_ready);
+    if (threadIdx.x == 64) FB_STAMP(33);
 
     // ---- E2: hidden chunks: relu(acc1 + b_1) (dropout) -> hid[b] ----
     for (int c = 0; c < C; ++c) {
       const int b = c & 1;
       tc::mbar_wait(&f1_done[b], (c >> 1) & 1);
       tc::fence_after_sync();
+      if (threadIdx.x == 64) FB_STAMP(40 + 2 * c);
       float v[2][32];
       const int h0 = half * (FB_CH / 2);  // this warp's 64 of the chunk's 128 columns
       tc::tmem_ld32(acc1[b] + lane_off + (uint32_t)h0, v[0]);
@@ -841,7 +876,7 @@ encoder_ffn_block_kernel(const __grid_constant__ CUtensorMap map_att, const __gr
       for (int t = 0; t < 2; ++t) {
         const int col = c * FB_CH + h0 + 32 * t;  // hidden column of v[t][0]
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[t][j] = fmaxf(v[t][j] + __ldg(a.b1 + col + j), 0.f);
+        for (int j = 0; j < 32; ++j) v[t][j] = fmaxf(v[t][j] + s_b1[col + j], 0.f);
         if (a.drop_h.rng != nullptr && row_ok) dropout32(v[t], a.drop_h, row, col, a.FF);
       }
       if (c >= 2) {  // chunk c - 2's contraction with W_2 must have consumed hid[b]
@@ -851,13 +886,16 @@ encoder_ffn_block_kernel(const __grid_constant__ CUtensorMap map_att, const __gr
       fb_store_operand_row(A0 + 2 * b * FB_KTILE, row_local, h0 + 32, v[1]);
       tc::fence_async_smem();
       mbar_arrive(&hid_ready[b]);
+      if (threadIdx.x == 64) FB_STAMP(41 + 2 * c);
     }
 
     // ---- E3: x = acc0 + b_2 (dropout2) + x ; LayerNorm_next ----
     tc::mbar_wait(&acc0_f2_done, 0);
     tc::fence_after_sync();
+    if (threadIdx.x == 64) FB_STAMP(34);
     sum = 0.f;
     const bool norm = a.lnn_g != nullptr;
+    fetch_rows(a.x_out, c_begin);  // x after attention (written in E1, re-read coalesced)
 #pragma unroll 1
     for (int j0 = c_begin; j0 < c_end; j0 += 32) {
       float v[32];
@@ -865,38 +903,54 @@ encoder_ffn_block_kernel(const __grid_constant__ CUtensorMap map_att, const __gr
       tc::tmem_ld_wait();
       add_bias_act(v, s_vec[3], j0, ACT_NONE);
       if (a.drop2.rng != nullptr && row_ok) dropout32(v, a.drop2, row, j0, FB_D);
-      if (row_ok) {
+      tile_put_row(tile, lane, v);
+      __syncwarp();
+      float4 xq[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 r = *reinterpret_cast<const float4*>(a.x_out + rowoff + j0 + 4 * j);
-          v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          *reinterpret_cast<float4*>(a.x_out + rowoff + j0 + 4 * j) = o;
-          if (!norm && a.out_f32 != nullptr) *reinterpret_cast<float4*>(a.out_f32 + rowoff + j0 + 4 * j) = o;
-        }
+      for (int i = 0; i < 8; ++i) {
+        const float4 t = *tile_quad(tile, lane, i);
+        xq[i] = make_float4(t.x + res[i].x, t.y + res[i].y, t.z + res[i].z, t.w + res[i].w);
       }
+      if (j0 + 32 < c_end) fetch_rows(a.x_out, j0 + 32);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) sum += v[j];
-      if (norm) tc::tmem_st32(acc0 + lane_off + (uint32_t)j0, v);
+      for (int i = 0; i < 8; ++i) {
+        const int r = qrow0 + 4 * i;
+        if (r < a.M) {
+          const long long o = (long long)r * FB_D + j0 + qcol;
+          *reinterpret_cast<float4*>(a.x_out + o) = xq[i];
+          if (!norm && a.out_f32 != nullptr) *reinterpret_cast<float4*>(a.out_f32 + o) = xq[i];
+        }
+        *tile_quad(tile, lane, i) = xq[i];
+      }
+      __syncwarp();
+      if (norm) {
+        tile_get_row(tile, lane, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sum += v[j];
+        tc::tmem_st32(acc0 + lane_off + (uint32_t)j0, v);
+      }
+      __syncwarp();
     }
     if (norm) {
       tc::tmem_st_wait();
       fb_layernorm_rows(acc0 + lane_off, c_begin, c_end, half, row_local, sum, ln_part, s_vec[4], s_vec[5], a.eps,
                         [&](int j0, const float* v) {
-                          if (!row_ok) return;
+                          tile_put_row(tile, lane, v);
+                          __syncwarp();
 #pragma unroll
-                          for (int j = 0; j < 8; ++j) {
-                            const float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                            if (a.xn_out != nullptr)
-                              *reinterpret_cast<uint2*>(a.xn_out + rowoff + j0 + 4 * j) = pack_bf16x4(o);
-                            if (a.out_f32 != nullptr)
-                              *reinterpret_cast<float4*>(a.out_f32 + rowoff + j0 + 4 * j) = o;
+                          for (int i = 0; i < 8; ++i) {
+                            const int r = qrow0 + 4 * i;
+                            if (r < a.M) {
+                              const float4 y = *tile_quad(tile, lane, i);
+                              const long long o = (long long)r * FB_D + j0 + qcol;
+                              if (a.xn_out != nullptr) *reinterpret_cast<uint2*>(a.xn_out + o) = pack_bf16x4(y);
+                              if (a.out_f32 != nullptr) *reinterpret_cast<float4*>(a.out_f32 + o) = y;
+                            }
                           }
+                          __syncwarp();
                         });
     }
+    if (threadIdx.x == 64) FB_STAMP(35);
     tc::fence_before_sync();
   }
   __syncthreads();
@@ -910,7 +964,8 @@ static int make_map_box(CUtensorMap* map, const void* base, int rows, int cols, 
 
 int launch_ffn_block(const __nv_bfloat16* att, const __nv_bfloat16* wo, const __nv_bfloat16* w1,
                      const __nv_bfloat16* w2, FfnBlockArgs a, cudaStream_t stream) {
-  MPA_CHECK_ARG(a.FF % FB_CH == 0 && a.FF >= FB_CH, "ffn_block: FF must be a multiple of %d", FB_CH);
+  MPA_CHECK_ARG(a.FF % FB_CH == 0 && a.FF >= FB_CH && a.FF <= FB_MAX_FF,
+                "ffn_block: FF must be a multiple of %d, at most %d", FB_CH, FB_MAX_FF);
   CUtensorMap m_att, m_wo, m_w1, m_w2;
   int rc = make_map_box(&m_att, att, a.M, FB_D, LN_BM);
   if (rc == MPA_OK) rc = make_map_box(&m_wo, wo, FB_D, FB_D, 256);
@@ -922,6 +977,7 @@ int launch_ffn_block(const __nv_bfloat16* att, const __nv_bfloat16* wo, const __
     MPA_CUDA(cudaFuncSetAttribute(encoder_ffn_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM));
     attr.done();
   }
+  if (const char* e = getenv("MPA_FFN_DEBUG")) a.dbg = (long long*)strtoull(e, nullptr, 0);  // device pointer
   {
     ProfScope ps("encoder_ffn_block", stream);
     encoder_ffn_block_kernel<<<(a.M + LN_BM - 1) / LN_BM, LN_THREADS, FB_SMEM, stream>>>(m_att, m_wo, m_w1, m_w2, a);
@@ -1221,7 +1277,7 @@ int mpa_transformer_forward(const float* tokens, const unsigned char* valid, int
           qkv, valid, B, P, H, hd, att, pl_TD, site(l, 0)); }
     MPA_LAUNCH_CHECK();
     const bool last = l + 1 == layers;
-    if (fused && split == 1 && FF % FB_CH == 0) {
+    if (fused && split == 1 && FF % FB_CH == 0 && FF <= FB_MAX_FF) {
       // out_proj + LayerNorm2 + FFN + the next LayerNorm in ONE kernel (128 token rows per CTA)
       FfnBlockArgs fa{};
       fa.b_o = out_proj_b[l]; fa.b1 = lin1_b[l]; fa.b2 = lin2_b[l];
