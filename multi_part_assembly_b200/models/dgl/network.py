@@ -88,7 +88,6 @@ class DGLModel(BaseModel):
         part_feats = data_dict.get('part_feats', None)
         if part_feats is None:
             part_feats = self._extract_part_feats(data_dict['part_pcs'], data_dict['part_valids'])
-            self._start_target_prepare()  # ground-truth side of the Chamfer losses: under the GNN
         local_feats = part_feats
         valid_matrix = data_dict['valid_matrix']
         part_label = data_dict['part_label'].type_as(part_feats)

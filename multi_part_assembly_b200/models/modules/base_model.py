@@ -242,7 +242,6 @@ class BaseModel(LightningModule):
         return cache
 
     def _calc_loss_fused(self, out_dict, data_dict, new_trans, new_rot):
-        self._start_target_prepare()
         pred_trans, pred_rot = out_dict['trans'], out_dict['rot']
         part_pcs, valids = data_dict['part_pcs'], data_dict['part_valids']
         terms, pred_trans_pts, gt_trans_pts = fused_geometric_losses(
@@ -295,29 +294,17 @@ class BaseModel(LightningModule):
         # autograd (the fused-loss path) and without matching (which permutes the ground
         # truth), start binning them on side streams now, under the network's forward
         self._prepared = None
-        self._prepare_args = None
         rot = data_dict.get('part_rot', None)
         if not torch.is_grad_enabled() and not self.semantic and rot is not None and \
                 rot.rot_type == 'quat' and data_dict['part_pcs'].is_cuda:
-            self._prepare_args = (data_dict['part_pcs'], data_dict['part_trans'], rot,
-                                  data_dict['part_valids'])
+            self._prepared = prepare_gt_targets(data_dict['part_pcs'], data_dict['part_trans'], rot,
+                                                data_dict['part_valids'])
         try:
             return self._loss_function_samples(data_dict, out_dict, samples, optimizer_idx)
         finally:
-            self._prepare_args = None
             if self._prepared is not None:  # a forked side stream is always joined
                 self._prepared.join(data_dict['part_pcs'].device)
                 self._prepared = None
-
-    def _start_target_prepare(self):
-        """Fork the ground-truth binning of the Chamfer losses onto side streams (once per
-        step).  Models call this right AFTER their part encoder: the encoder kernels fill every
-        SM, the correlation module after it (a few dozen CTAs at batch 32) leaves most of them
-        idle, which is where the binning fits.  `_calc_loss` calls it as a fallback."""
-        args = getattr(self, '_prepare_args', None)
-        if args is not None and self._prepared is None:
-            self._prepared = prepare_gt_targets(*args)
-            self._prepare_args = None
 
     def _loss_function_samples(self, data_dict, out_dict, samples, optimizer_idx):
         for _ in range(self.sample_iter):

@@ -57,7 +57,6 @@ class PNTransformer(BaseModel):
             # side stream while the part encoder runs
             kernels.transformer_prefetch(self.corr_module.transformer_encoder, part_valids.device)
             pc_feats = self._extract_part_feats(data_dict['part_pcs'], part_valids)
-            self._start_target_prepare()  # ground-truth side of the Chamfer losses: under the transformer
             corr_feats = self.corr_module(pc_feats, part_valids == 1)
             feats = torch.cat([corr_feats, data_dict['part_label'].type_as(corr_feats),
                                data_dict['instance_label'].type_as(corr_feats)], dim=-1)

@@ -53,7 +53,6 @@ class PNTransformerRefine(PNTransformer):
         part_pcs, part_valids = data_dict['part_pcs'], data_dict['part_valids']
         if pc_feats is None:
             pc_feats = self._extract_part_feats(part_pcs, part_valids)
-            self._start_target_prepare()  # ground-truth side of the Chamfer losses: under the transformer
         part_feats = pc_feats
         part_label = data_dict['part_label'].type_as(pc_feats)
         inst_label = data_dict['instance_label'].type_as(pc_feats)
