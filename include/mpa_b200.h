@@ -126,19 +126,6 @@ int mpa_pose_chamfer(const float* pts, const float* quat1, const float* trans1,
                      float* dist2, int32_t* idx2, float* pts1, float* pts2, void* ws,
                      size_t ws_bytes, void* stream);
 
-/* mpa_pose_chamfer in two stages that share one caller workspace (same results): `prepare`
- * bins the SECOND cloud -- pose 2, the ground truth in the losses, which does not depend on the
- * prediction -- and may be issued early on a side stream; `finish` bins the first cloud and
- * runs both searches.  One `prepare` can serve several `finish` calls (the per-iteration losses
- * of the DGL / refine models, reference dgl/network.py:284-297). */
-int mpa_pose_chamfer_prepare(const float* pts, const float* quat2, const float* trans2,
-                             const float* valids, int B, int P, int N, int mode, float* dist2,
-                             int32_t* idx2, float* pts2, void* ws, size_t ws_bytes, void* stream);
-int mpa_pose_chamfer_finish(const float* pts, const float* quat1, const float* trans1,
-                            const float* valids, int B, int P, int N, int mode, float* dist1,
-                            int32_t* idx1, float* dist2, int32_t* idx2, float* pts1, void* ws,
-                            size_t ws_bytes, void* stream);
-
 /* Backward of mpa_pose_chamfer w.r.t. the two poses (the points carry no
  * gradient: loss.py:172 detaches them, and part_pcs is data).  Chains
  * ChamferBackward (chamfer_kernel.cu:175-210) into the SE(3) backward.

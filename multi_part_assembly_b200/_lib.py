@@ -38,8 +38,6 @@ _SIGNATURES = {
     'mpa_pose_chamfer_workspace_bytes': (c_size_t, [c_int] * 4),
     'mpa_pose_chamfer': (c_int, [c_void_p] * 6 + [c_int] * 4 + [c_void_p] * 7 +
                          [c_size_t, c_void_p]),
-    'mpa_pose_chamfer_prepare': (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p] * 4 + [c_size_t, c_void_p]),
-    'mpa_pose_chamfer_finish': (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p] * 6 + [c_size_t, c_void_p]),
     'mpa_geometric_losses_workspace_bytes': (c_size_t, [c_int] * 2),
     'mpa_geometric_losses': (c_int, [c_void_p] * 10 + [c_int] * 5 + [c_void_p] * 3 + [c_size_t, c_void_p]),
     'mpa_pointnet_workspace_bytes': (c_size_t, [c_int]),

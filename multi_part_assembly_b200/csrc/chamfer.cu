@@ -207,7 +207,7 @@ __device__ __forceinline__ float warp_max(float v) {
 // K1: one CTA per (cloud, segment): bbox -> grid params -> histogram -> scan -> scatter.
 // dynamic smem: int cnt[dmax^3 + 1]
 template <typename IdxT>
-__global__ void grid_build_kernel(CloudDesc c0, CloudDesc c1, int S, int cloud_base, float4* __restrict__ sorted0,
+__global__ void grid_build_kernel(CloudDesc c0, CloudDesc c1, int S, float4* __restrict__ sorted0,
                                   float4* __restrict__ sorted1, int* __restrict__ cell_start,
                                   int cs_stride, GridParams* __restrict__ params,
                                   float4* __restrict__ far, int* pyr_base, PyrLayout pl,
@@ -220,7 +220,7 @@ __global__ void grid_build_kernel(CloudDesc c0, CloudDesc c1, int S, int cloud_b
   __shared__ GridParams gp;
   __shared__ int s_count, s_nfar;
 
-  const int cloud = cloud_base + blockIdx.x / S;  // cloud_base = 1 with S blocks: only the second cloud
+  const int cloud = blockIdx.x / S;
   const int seg = blockIdx.x % S;
   const CloudDesc& c = cloud ? c1 : c0;
   float4* sorted = (cloud ? sorted1 : sorted0) + (long long)seg * c.Nseg;
@@ -232,7 +232,7 @@ __global__ void grid_build_kernel(CloudDesc c0, CloudDesc c1, int S, int cloud_b
   const bool has_valid = c.valids != nullptr;
 
   if (tid == 0) { s_count = 0; s_nfar = 0; }
-  if (blockIdx.x == 0 && tid == 0 && cloud == 0) { hard_count[0] = 0; hard_count[1] = 0; }  // append list + its read cursor
+  if (blockIdx.x == 0 && tid == 0) { hard_count[0] = 0; hard_count[1] = 0; }  // append list + its read cursor
   __syncthreads();
 
   // ---- pass 1: bbox of the valid points, transformed output, zero-fill ----
@@ -942,10 +942,9 @@ static GridLayout grid_layout(int S, int N0, int N1) {
   return L;
 }
 
-enum { GRID_ALL = 0, GRID_PREPARE_SECOND = 1, GRID_FINISH = 2 };
 template <typename IdxT>
 static int run_grid(CloudDesc c0, CloudDesc c1, int S, float* dist0, IdxT* idx0, float* dist1,
-                    IdxT* idx1, void* ws, size_t ws_bytes, cudaStream_t stream, int stage = GRID_ALL) {
+                    IdxT* idx1, void* ws, size_t ws_bytes, cudaStream_t stream) {
   const GridLayout L = grid_layout(S, c0.Nseg, c1.Nseg);
   Scratch scratch;
   int rc = scratch.acquire(ws, ws_bytes, L.total, stream);
@@ -987,13 +986,11 @@ static int run_grid(CloudDesc c0, CloudDesc c1, int S, float* dist0, IdxT* idx0,
   }
   {
     ProfScope ps(c0.fill_invalid ? "chamfer_grid_build_shape" : (c0.quat ? "chamfer_grid_build_part" : "chamfer_grid_build"), stream);
-    const int nb = stage == GRID_ALL ? 2 * S : S, cloud_base = stage == GRID_PREPARE_SECOND ? 1 : 0;
-    grid_build_kernel<IdxT><<<nb, threads, smem, stream>>>(c0, c1, S, cloud_base, s0, s1, cs, L.cs_stride,
+    grid_build_kernel<IdxT><<<2 * S, threads, smem, stream>>>(c0, c1, S, s0, s1, cs, L.cs_stride,
                                                               params, far, pyr, L.pyr, hard_count, dist0,
                                                               idx0, dist1, idx1);
   }
   MPA_LAUNCH_CHECK();
-  if (stage == GRID_PREPARE_SECOND) return MPA_OK;  // the search follows the first cloud's build
   const long long warps = (long long)S * ((c0.Nseg + 31) / 32 + (c1.Nseg + 31) / 32);
   const long long blocks = (warps + 7) / 8;
   if (blocks > 0) {
@@ -1154,49 +1151,22 @@ size_t mpa_pose_chamfer_workspace_bytes(int B, int P, int N, int mode) {
   return grid_layout(B, P * N, P * N).total;
 }
 
-static int pose_chamfer_impl(const float* pts, const float* quat1, const float* trans1, const float* quat2,
-                             const float* trans2, const float* valids, int B, int P, int N, int mode,
-                             float* dist1, int32_t* idx1, float* dist2, int32_t* idx2, float* pts1,
-                             float* pts2, void* ws, size_t ws_bytes, void* stream_, int stage) {
+int mpa_pose_chamfer(const float* pts, const float* quat1, const float* trans1, const float* quat2,
+                     const float* trans2, const float* valids, int B, int P, int N, int mode,
+                     float* dist1, int32_t* idx1, float* dist2, int32_t* idx2, float* pts1,
+                     float* pts2, void* ws, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   MPA_CHECK_ARG(B >= 0 && P >= 0 && N >= 0, "pose_chamfer: negative size");
   MPA_CHECK_ARG(mode == MPA_CD_PART || mode == MPA_CD_SHAPE, "pose_chamfer: bad mode %d", mode);
   if (B == 0 || P == 0 || N == 0) return MPA_OK;
-  MPA_CHECK_ARG(pts && (stage == GRID_PREPARE_SECOND || (quat1 && dist1)) && (stage == GRID_FINISH || quat2) && dist2,
-                "pose_chamfer: null pointer");
-  MPA_CHECK_ARG(stage == GRID_ALL || ws != nullptr, "pose_chamfer: the staged calls share a caller workspace");
+  MPA_CHECK_ARG(pts && quat1 && quat2 && dist1 && dist2, "pose_chamfer: null pointer");
   MPA_CHECK_ARG(P <= MAX_FAR, "pose_chamfer: at most %d parts per shape", MAX_FAR);
   const bool shape = mode == MPA_CD_SHAPE;
   const int S = shape ? B : B * P;
   const int Nseg = shape ? P * N : N;
   CloudDesc c0{pts, quat1, trans1, valids, pts1, Nseg, N, shape ? 1 : 0, 0, 0.f, 0};
   CloudDesc c1{pts, quat2, trans2, valids, pts2, Nseg, N, shape ? 1 : 0, 0, 0.f, 0};
-  return run_grid<int>(c0, c1, S, dist1, idx1, dist2, idx2, ws, ws_bytes, stream, stage);
-}
-
-int mpa_pose_chamfer(const float* pts, const float* quat1, const float* trans1, const float* quat2,
-                     const float* trans2, const float* valids, int B, int P, int N, int mode,
-                     float* dist1, int32_t* idx1, float* dist2, int32_t* idx2, float* pts1,
-                     float* pts2, void* ws, size_t ws_bytes, void* stream_) {
-  return pose_chamfer_impl(pts, quat1, trans1, quat2, trans2, valids, B, P, N, mode, dist1, idx1, dist2, idx2,
-                           pts1, pts2, ws, ws_bytes, stream_, GRID_ALL);
-}
-
-/* mpa_pose_chamfer in two stages sharing one caller workspace: `prepare` bins the SECOND cloud
- * (pose 2, e.g. the ground truth, which does not depend on the prediction) and may run early on
- * a side stream; `finish` bins the first cloud and runs both searches.  Results are identical. */
-int mpa_pose_chamfer_prepare(const float* pts, const float* quat2, const float* trans2, const float* valids,
-                             int B, int P, int N, int mode, float* dist2, int32_t* idx2, float* pts2, void* ws,
-                             size_t ws_bytes, void* stream_) {
-  return pose_chamfer_impl(pts, nullptr, nullptr, quat2, trans2, valids, B, P, N, mode, nullptr, nullptr, dist2,
-                           idx2, nullptr, pts2, ws, ws_bytes, stream_, GRID_PREPARE_SECOND);
-}
-
-int mpa_pose_chamfer_finish(const float* pts, const float* quat1, const float* trans1, const float* valids,
-                            int B, int P, int N, int mode, float* dist1, int32_t* idx1, float* dist2,
-                            int32_t* idx2, float* pts1, void* ws, size_t ws_bytes, void* stream_) {
-  return pose_chamfer_impl(pts, quat1, trans1, nullptr, nullptr, valids, B, P, N, mode, dist1, idx1, dist2, idx2,
-                           pts1, nullptr, ws, ws_bytes, stream_, GRID_FINISH);
+  return run_grid<int>(c0, c1, S, dist1, idx1, dist2, idx2, ws, ws_bytes, stream);
 }
 
 size_t mpa_pose_chamfer_backward_workspace_bytes(int B, int P, int N) {

@@ -620,7 +620,7 @@ def transformer_prefetch(encoder, dev=None):
     groups = _transformer_params(encoder)
     cur = torch.cuda.current_stream(dev)
     from .utils.loss import _side_stream
-    side = _side_stream(dev, 2)
+    side = _side_stream(dev)
     side.wait_stream(cur)
     with torch.cuda.stream(side), torch.cuda.device(dev):
         rc = L.mpa_transformer_pack_weights(

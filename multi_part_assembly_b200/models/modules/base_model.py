@@ -21,7 +21,7 @@ from ...utils import trans_l2_loss, rot_points_cd_loss, shape_cd_loss, \
     rot_cosine_loss, rot_points_l2_loss, chamfer_distance
 from ...utils import calc_part_acc, calc_connectivity_acc, trans_metrics, \
     rot_metrics
-from ...utils.loss import fused_geometric_losses, prepare_gt_targets
+from ...utils.loss import fused_geometric_losses
 from ...utils.lr import CosineAnnealingWarmupRestarts
 
 
@@ -247,8 +247,7 @@ class BaseModel(LightningModule):
         terms, pred_trans_pts, gt_trans_pts = fused_geometric_losses(
             part_pcs, pred_trans, new_trans, pred_rot, new_rot, valids,
             self._loss_weight_tensor(part_pcs.device), training=self.semantic or self.training,
-            want_rot_l2=bool(self.cfg.loss.use_rot_pt_l2_loss), ret_pts=True,
-            prepared=getattr(self, '_prepared', None))
+            want_rot_l2=bool(self.cfg.loss.use_rot_pt_l2_loss), ret_pts=True)
         loss_dict = {k: terms[k] for k in ('trans_loss', 'rot_pt_cd_loss', 'transform_pt_cd_loss')}
         if self.cfg.loss.use_rot_loss:
             loss_dict['rot_loss'] = terms['rot_loss']
@@ -290,23 +289,6 @@ class BaseModel(LightningModule):
         out_dict = {}
         self._fused_packed = None
         self._calc_loss_calls = 0
-        # The ground-truth clouds of the two Chamfer losses depend on the batch only: without
-        # autograd (the fused-loss path) and without matching (which permutes the ground
-        # truth), start binning them on side streams now, under the network's forward
-        self._prepared = None
-        rot = data_dict.get('part_rot', None)
-        if not torch.is_grad_enabled() and not self.semantic and rot is not None and \
-                rot.rot_type == 'quat' and data_dict['part_pcs'].is_cuda:
-            self._prepared = prepare_gt_targets(data_dict['part_pcs'], data_dict['part_trans'], rot,
-                                                data_dict['part_valids'])
-        try:
-            return self._loss_function_samples(data_dict, out_dict, samples, optimizer_idx)
-        finally:
-            if self._prepared is not None:  # a forked side stream is always joined
-                self._prepared.join(data_dict['part_pcs'].device)
-                self._prepared = None
-
-    def _loss_function_samples(self, data_dict, out_dict, samples, optimizer_idx):
         for _ in range(self.sample_iter):
             sample_loss, out_dict = self._loss_function(data_dict, out_dict,
                                                         optimizer_idx=optimizer_idx)

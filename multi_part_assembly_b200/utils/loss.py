@@ -113,101 +113,19 @@ class FusedLossTerms(dict):
 _SIDE_STREAMS = {}
 
 
-def _side_stream(dev, which=0):
-    s = _SIDE_STREAMS.get((dev, which))
+def _side_stream(dev):
+    s = _SIDE_STREAMS.get(dev)
     if s is None:
-        s = _SIDE_STREAMS[(dev, which)] = torch.cuda.Stream(device=dev)
+        s = _SIDE_STREAMS[dev] = torch.cuda.Stream(device=dev)
     return s
 
 
-class PreparedTargets:
-    """Ground-truth side of the two fused pose-Chamfer searches (shape level and per part),
-    binned ahead of time: it depends on the batch only, not on the prediction, so a model
-    starts it on side streams BEFORE its network runs (`prepare_gt_targets`) and the losses
-    only bin the predicted clouds and search.  One instance serves every loss evaluation of a
-    step (the DGL / refine models score several predictions against the same ground truth)."""
-
-    def __init__(self, pts, gt_trans, gt_quat, valids):
-        B, P, N, _ = pts.shape
-        dev = pts.device
-        self.key = (pts.data_ptr(), valids.data_ptr(), B, P, N)
-        self.pts, self.valids = pts, valids
-        self.q2, self.t2 = gt_quat, gt_trans
-        L = _lib.lib()
-        f32 = dict(dtype=torch.float32, device=dev)
-        cur = torch.cuda.current_stream(dev)
-        self.modes = {}
-        for mode, stream in ((CD_SHAPE, _side_stream(dev)), (CD_PART, _side_stream(dev, 1))):
-            ws_bytes = L.mpa_pose_chamfer_workspace_bytes(B, P, N, mode)
-            m = dict(ws=torch.empty(ws_bytes, dtype=torch.uint8, device=dev), ws_bytes=ws_bytes,
-                     dist2=torch.empty(B, P, N, **f32),
-                     idx2=torch.empty(B, P, N, dtype=torch.int32, device=dev),
-                     pts2=torch.empty(B, P, N, 3, **f32))
-            stream.wait_stream(cur)
-            with torch.cuda.stream(stream), torch.cuda.device(dev):
-                rc = L.mpa_pose_chamfer_prepare(
-                    _lib.ptr(pts), _lib.ptr(gt_quat), _lib.ptr(gt_trans) if mode == CD_SHAPE else None,
-                    _lib.ptr(valids), B, P, N, mode, _lib.ptr(m['dist2']), _lib.ptr(m['idx2']),
-                    _lib.ptr(m['pts2']), _lib.ptr(m['ws']), ws_bytes, stream.cuda_stream)
-                _lib.check(rc, 'mpa_pose_chamfer_prepare')
-                m['ready'] = torch.cuda.Event()
-                m['ready'].record(stream)
-            for t in (m['ws'], m['dist2'], m['idx2'], m['pts2']):
-                t.record_stream(stream)
-            self.modes[mode] = m
-        self.joined = False
-
-    def join(self, dev):
-        """Make the current stream wait for both preparations (once)."""
-        if not self.joined:
-            cur = torch.cuda.current_stream(dev)
-            for m in self.modes.values():
-                cur.wait_event(m['ready'])
-            self.joined = True
-
-    def matches(self, pts, valids):
-        """Same batch tensors?  (The caller guarantees that the ground-truth poses it scores
-        against are the ones given here: BaseModel only prepares when no matching permutes them.)"""
-        B, P, N, _ = pts.shape
-        return self.key == (pts.data_ptr(), valids.data_ptr(), B, P, N)
-
-    def finish(self, mode, q1, t1):
-        """Bin the predicted clouds into the prepared workspace and search: same outputs as
-        `pose_chamfer` (no autograd)."""
-        pts = self.pts
-        B, P, N, _ = pts.shape
-        dev = pts.device
-        m = self.modes[mode]
-        f32 = dict(dtype=torch.float32, device=dev)
-        dist1 = torch.empty(B, P, N, **f32)
-        idx1 = torch.empty(B, P, N, dtype=torch.int32, device=dev)
-        pts1 = torch.empty(B, P, N, 3, **f32)
-        with torch.cuda.device(dev):
-            rc = _lib.lib().mpa_pose_chamfer_finish(
-                _lib.ptr(pts), _lib.ptr(q1), _lib.ptr(t1) if mode == CD_SHAPE else None,
-                _lib.ptr(self.valids), B, P, N, mode, _lib.ptr(dist1), _lib.ptr(idx1), _lib.ptr(m['dist2']),
-                _lib.ptr(m['idx2']), _lib.ptr(pts1), _lib.ptr(m['ws']), m['ws_bytes'],
-                _lib.cuda_stream(dev))
-        _lib.check(rc, 'mpa_pose_chamfer_finish')
-        return dist1, m['dist2'], pts1, m['pts2']
-
-
-def prepare_gt_targets(pts, gt_trans, gt_rot, valids):
-    """Start binning the ground-truth clouds of both Chamfer losses on side streams (see
-    `PreparedTargets`); quaternion rotations on CUDA tensors only, else None."""
-    if not (isinstance(gt_rot, Rotation3D) and gt_rot.rot_type == 'quat' and pts.is_cuda):
-        return None
-    return PreparedTargets(pts.contiguous().float(), gt_trans.contiguous().float(),
-                           gt_rot.rot.contiguous().float(), valids.contiguous().float())
-
-
 def fused_geometric_losses(pts, pred_trans, gt_trans, pred_rot, gt_rot, valids, weights,
-                            training=True, want_rot_l2=True, ret_pts=False, prepared=None):
-    """All geometric loss terms of BaseModel._calc_loss in a handful of launches (two
-    fused pose-Chamfer searches + two reduction kernels), forward only.
+                            training=True, want_rot_l2=True, ret_pts=False):
+    """All geometric loss terms of BaseModel._calc_loss in four launches (two
+    fused pose-Chamfer calls + two reduction kernels), forward only.
 
     weights: [trans, rot_pt_cd, transform_pt_cd, rot, rot_pt_l2] loss weights.
-    prepared: a `PreparedTargets` for this batch (ground-truth side binned earlier), or None.
     Returns a dict of [B] tensors keyed like the reference's loss_dict plus
     'loss' (the weighted total), and optionally the two transformed clouds.
     """
@@ -215,26 +133,16 @@ def fused_geometric_losses(pts, pred_trans, gt_trans, pred_rot, gt_rot, valids, 
     q1, q2 = pred_rot.rot.contiguous().float(), gt_rot.rot.contiguous().float()
     t1, t2 = pred_trans.contiguous().float(), gt_trans.contiguous().float()
     dev = pts.device
-    p = pts.contiguous().float()
-    v = valids.contiguous().float()
     with torch.no_grad():
         # The two searches are independent and each ends in a long tail of slow warps:
         # run the per-part one on a side stream so that it fills the SMs the shape-level
         # one leaves idle (a fork/join that CUDA-graph capture records as parallel branches).
         cur = torch.cuda.current_stream(dev)
         side = _side_stream(dev)
-        use_prep = prepared is not None and prepared.matches(p, v)
-        if prepared is not None:
-            prepared.join(dev)  # joined in every case: a forked stream must not dangle
         side.wait_stream(cur)
-        if use_prep:
-            sd1, sd2, pts1, pts2 = prepared.finish(CD_SHAPE, q1, t1)
-            with torch.cuda.stream(side):
-                pd1, pd2, _, _ = prepared.finish(CD_PART, q1, None)
-        else:
-            sd1, sd2, pts1, pts2 = pose_chamfer(pts, t1, t2, q1, q2, valids, CD_SHAPE)
-            with torch.cuda.stream(side):
-                pd1, pd2, _, _ = pose_chamfer(pts, None, None, q1, q2, valids, CD_PART)
+        sd1, sd2, pts1, pts2 = pose_chamfer(pts, t1, t2, q1, q2, valids, CD_SHAPE)
+        with torch.cuda.stream(side):
+            pd1, pd2, _, _ = pose_chamfer(pts, None, None, q1, q2, valids, CD_PART)
         cur.wait_stream(side)
         for t in (pd1, pd2):
             t.record_stream(cur)
@@ -244,6 +152,8 @@ def fused_geometric_losses(pts, pred_trans, gt_trans, pred_rot, gt_rot, valids, 
     L = _lib.lib()
     ws_bytes = L.mpa_geometric_losses_workspace_bytes(B, P)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    v = valids.contiguous().float()
+    p = pts.contiguous().float()
     with torch.cuda.device(dev):
         rc = L.mpa_geometric_losses(
             _lib.ptr(p), _lib.ptr(q1), _lib.ptr(t1), _lib.ptr(q2), _lib.ptr(t2), _lib.ptr(v),
