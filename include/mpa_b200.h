@@ -277,16 +277,7 @@ int mpa_transformer_forward(const float* tokens, const unsigned char* valid, int
                             const float* const* norm2_b, const float* final_norm_w,
                             const float* final_norm_b, float eps, float dropout_p,
                             unsigned long long* rng_state, unsigned char* masks, int precision,
-                            const void* packed_weights, float* out, void* ws, size_t ws_bytes,
-                            void* stream);
-/* The fp32 -> bf16 operand image of the encoder weights as a separate call: it depends on the
- * parameters only, so a caller can issue it early on a side stream (e.g. while the part
- * encoder runs) and hand the buffer to mpa_transformer_forward (`packed_weights`, else NULL). */
-size_t mpa_transformer_weight_bytes(int D, int FF, int layers, int precision);
-int mpa_transformer_pack_weights(int D, int FF, int layers, const float* const* in_proj_w,
-                                 const float* const* out_proj_w, const float* const* lin1_w,
-                                 const float* const* lin2_w, int precision, void* packed,
-                                 void* stream);
+                            float* out, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- DGCNN: k-NN graph and EdgeConv aggregation -------------------------- */
 /* Replaces knn (models/modules/encoder/dgcnn.py:8-15).  x [n,N,C] fp32 with the

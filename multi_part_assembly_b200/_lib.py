@@ -62,9 +62,7 @@ _SIGNATURES = {
     'mpa_transformer_mask_bytes': (c_size_t, [c_int] * 6),
     'mpa_transformer_forward': (c_int, [c_void_p, c_void_p] + [c_int] * 6 + [c_void_p] * 14 +
                                 [ctypes.c_float, ctypes.c_float, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
-                                 c_void_p, c_size_t, c_void_p]),
-    'mpa_transformer_weight_bytes': (c_size_t, [c_int] * 4),
-    'mpa_transformer_pack_weights': (c_int, [c_int] * 3 + [c_void_p] * 4 + [c_int, c_void_p, c_void_p]),
+                                 c_size_t, c_void_p]),
     'mpa_knn_workspace_bytes': (c_size_t, [c_int] * 2),
     'mpa_knn': (c_int, [c_void_p, c_void_p] + [c_int] * 4 + [c_void_p, c_void_p, c_size_t, c_void_p]),
     'mpa_edge_aggregate_workspace_bytes': (c_size_t, [ctypes.c_longlong, c_int]),

@@ -1154,50 +1154,6 @@ int mpa_linear_forward(const float* x, const float* w, const float* bias, const 
                                stream_);
 }
 
-/* bf16 operand image of the encoder's weight matrices: per layer [in_proj | out_proj |
- * linear1 | linear2], each as `split` planes (1: bf16; 3: hi / mid / lo). */
-static int pack_transformer_weights(int D, int FF, int layers, const float* const* in_proj_w,
-                                    const float* const* out_proj_w, const float* const* lin1_w,
-                                    const float* const* lin2_w, int split, __nv_bfloat16* wts,
-                                    cudaStream_t stream) {
-  MPA_CHECK_ARG(layers * 4 <= 64, "transformer: at most 16 layers");
-  const size_t per_layer = ((size_t)3 * D * D + (size_t)D * D + 2 * (size_t)FF * D) * split;
-  const size_t o_out = (size_t)3 * D * D * split, o_l1 = o_out + (size_t)D * D * split,
-               o_l2 = o_l1 + (size_t)FF * D * split;
-  {
-    ProfScope ps("transformer_weights_to_bf16", stream);
-    CvtBatch cb;
-    for (int l = 0; l < layers; ++l) {
-      __nv_bfloat16* wl = wts + (size_t)l * per_layer;
-      cb.src[4 * l + 0] = in_proj_w[l];  cb.dst[4 * l + 0] = wl;         cb.n[4 * l + 0] = (long long)3 * D * D;
-      cb.src[4 * l + 1] = out_proj_w[l]; cb.dst[4 * l + 1] = wl + o_out; cb.n[4 * l + 1] = (long long)D * D;
-      cb.src[4 * l + 2] = lin1_w[l];     cb.dst[4 * l + 2] = wl + o_l1;  cb.n[4 * l + 2] = (long long)FF * D;
-      cb.src[4 * l + 3] = lin2_w[l];     cb.dst[4 * l + 3] = wl + o_l2;  cb.n[4 * l + 3] = (long long)FF * D;
-      for (int k = 0; k < 4; ++k) cb.plane[4 * l + k] = split == 3 ? cb.n[4 * l + k] : 0;
-    }
-    f32_to_bf16_batch_kernel<<<dim3(32, layers * 4), 256, 0, stream>>>(cb);
-  }
-  MPA_LAUNCH_CHECK();
-  return MPA_OK;
-}
-
-size_t mpa_transformer_weight_bytes(int D, int FF, int layers, int precision) {
-  const size_t split = precision == MPA_PRECISION_FP32 ? 3 : 1;
-  return align_up(split * (size_t)layers * ((size_t)3 * D * D + (size_t)D * D + 2 * (size_t)FF * D) * 2, 256);
-}
-
-/* The weight conversion of mpa_transformer_forward as its own call, so that a caller can run
- * it early on a side stream (it only depends on the parameters) and pass the result in. */
-int mpa_transformer_pack_weights(int D, int FF, int layers, const float* const* in_proj_w,
-                                 const float* const* out_proj_w, const float* const* lin1_w,
-                                 const float* const* lin2_w, int precision, void* packed, void* stream_) {
-  MPA_CHECK_ARG(precision == MPA_PRECISION_BF16 || precision == MPA_PRECISION_FP32, "pack_weights: bad precision");
-  MPA_CHECK_ARG(packed != nullptr, "pack_weights: null pointer");
-  return pack_transformer_weights(D, FF, layers, in_proj_w, out_proj_w, lin1_w, lin2_w,
-                                  precision == MPA_PRECISION_FP32 ? 3 : 1, (__nv_bfloat16*)packed,
-                                  (cudaStream_t)stream_);
-}
-
 /* Pre-LN transformer encoder (nn.TransformerEncoder with norm_first=True,
  * batch_first, ReLU FFN, final LayerNorm), key-padding mask from `valid`.
  * tokens/out [B*P, D] fp32.  Per-layer parameter arrays hold `layers` device pointers each.
@@ -1235,8 +1191,7 @@ int mpa_transformer_forward(const float* tokens, const unsigned char* valid, int
                             const float* const* norm2_b, const float* final_norm_w,
                             const float* final_norm_b, float eps, float dropout_p,
                             unsigned long long* rng_state, unsigned char* masks, int precision,
-                            const void* packed_weights, float* out, void* ws, size_t ws_bytes,
-                            void* stream_) {
+                            float* out, void* ws, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   MPA_CHECK_ARG(precision == MPA_PRECISION_BF16 || precision == MPA_PRECISION_FP32,
                 "transformer_forward: bad precision %d", precision);
@@ -1257,7 +1212,6 @@ int mpa_transformer_forward(const float* tokens, const unsigned char* valid, int
   // every weight matrix is stored as `split` consecutive planes [split][rows][cols]
   const size_t per_layer = ((size_t)3 * D * D + (size_t)D * D + 2 * (size_t)FF * D) * split;
   __nv_bfloat16* wts = (__nv_bfloat16*)p; p += align_up(3 * (size_t)layers * (per_layer / split) * 2, 256);
-  if (packed_weights != nullptr) wts = (__nv_bfloat16*)packed_weights;  // mpa_transformer_pack_weights ran earlier
   float* x = (float*)p; p += align_up((size_t)T * D * 4, 256);
   __nv_bfloat16* xn = (__nv_bfloat16*)p; p += align_up(3 * (size_t)T * D * 2, 256);
   float* qkv = (float*)p; p += align_up((size_t)T * 3 * D * 4, 256);
@@ -1267,10 +1221,21 @@ int mpa_transformer_forward(const float* tokens, const unsigned char* valid, int
   const size_t o_out = (size_t)3 * D * D * split, o_l1 = o_out + (size_t)D * D * split,
                o_l2 = o_l1 + (size_t)FF * D * split;  // offsets of out_proj / linear1 / linear2 in a layer
 
-  if (packed_weights == nullptr) {
-    rc = pack_transformer_weights(D, FF, layers, in_proj_w, out_proj_w, lin1_w, lin2_w, split, wts, stream);
-    if (rc != MPA_OK) return rc;
+  MPA_CHECK_ARG(layers * 4 <= 64, "transformer_forward: at most 16 layers");
+  {
+    ProfScope ps("transformer_weights_to_bf16", stream);
+    CvtBatch cb;
+    for (int l = 0; l < layers; ++l) {
+      __nv_bfloat16* wl = wts + (size_t)l * per_layer;
+      cb.src[4 * l + 0] = in_proj_w[l];  cb.dst[4 * l + 0] = wl;         cb.n[4 * l + 0] = (long long)3 * D * D;
+      cb.src[4 * l + 1] = out_proj_w[l]; cb.dst[4 * l + 1] = wl + o_out; cb.n[4 * l + 1] = (long long)D * D;
+      cb.src[4 * l + 2] = lin1_w[l];     cb.dst[4 * l + 2] = wl + o_l1;  cb.n[4 * l + 2] = (long long)FF * D;
+      cb.src[4 * l + 3] = lin2_w[l];     cb.dst[4 * l + 3] = wl + o_l2;  cb.n[4 * l + 3] = (long long)FF * D;
+      for (int k = 0; k < 4; ++k) cb.plane[4 * l + k] = split == 3 ? cb.n[4 * l + k] : 0;
+    }
+    f32_to_bf16_batch_kernel<<<dim3(32, layers * 4), 256, 0, stream>>>(cb);
   }
+  MPA_LAUNCH_CHECK();
   const int ln_blocks = (T * 32 + 255) / 256;
   const size_t att_smem = (size_t)(2 * P * hd + P * (hd + 1)) * sizeof(float);
   // D == 256 (the reference's d_model): the two GEMMs that finish a residual-stream row

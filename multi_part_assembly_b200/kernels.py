@@ -599,61 +599,13 @@ def split_transformer_masks(masks, B, P, D, H, FF, layers):
     return out
 
 
-_PACKED = {}
-
-
-def transformer_prefetch(encoder, dev=None):
-    """Start converting the encoder's weights to their bf16 operand image on a side stream
-    (the conversion only depends on the parameters): a model calls this before its part encoder
-    runs, and the transformer forward later joins the side stream instead of paying for the
-    conversion on the critical path.  Safe under CUDA-graph capture (a parallel branch)."""
-    if dev is None:
-        dev = next(encoder.parameters()).device
-    if dev.type != 'cuda':
-        return
-    ls = encoder.layers
-    D, FF = ls[0].linear1.in_features, ls[0].linear1.out_features
-    precision = PRECISION_BF16 if _use_bf16() else PRECISION_FP32
-    L = _lib.lib()
-    nbytes = L.mpa_transformer_weight_bytes(D, FF, len(ls), precision)
-    buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    groups = _transformer_params(encoder)
-    cur = torch.cuda.current_stream(dev)
-    from .utils.loss import _side_stream
-    side = _side_stream(dev)
-    side.wait_stream(cur)
-    with torch.cuda.stream(side), torch.cuda.device(dev):
-        rc = L.mpa_transformer_pack_weights(
-            D, FF, len(ls), *[_ptr_array([t.detach() for t in groups[i]]) for i in (0, 2, 4, 6)],
-            precision, _lib.ptr(buf), side.cuda_stream)
-        _lib.check(rc, 'mpa_transformer_pack_weights')
-        ev = torch.cuda.Event()
-        ev.record(side)
-    buf.record_stream(side)
-    _PACKED[id(encoder)] = (buf, ev, precision, tuple(int(p._version) for p in encoder.parameters()))
-
-
-def _take_packed(encoder, precision, dev):
-    """The image `transformer_prefetch` started for this forward, if any (joined on the current
-    stream); None if none is pending or the parameters changed since."""
-    item = _PACKED.pop(id(encoder), None)
-    if item is None:
-        return None
-    buf, ev, prec, versions = item
-    torch.cuda.current_stream(buf.device).wait_event(ev)  # join the side stream in every case
-    if prec != precision or buf.device != dev or \
-            versions != tuple(int(p._version) for p in encoder.parameters()):
-        return None
-    return buf
-
-
 class _TransformerFunction(torch.autograd.Function):
     """Forward: tcgen05 + TMA kernels (csrc/linear.cu), dropout drawn in-kernel (Philox) when
     training with p > 0.  Backward: autograd through the same layer chain in torch ops, with
     the keep masks the kernels wrote (or the stock module when there is no dropout)."""
 
     @staticmethod
-    def forward(ctx, tokens, valid, encoder, num_heads, dropout_p, precision, packed, *params):
+    def forward(ctx, tokens, valid, encoder, num_heads, dropout_p, precision, *params):
         B, P, D = tokens.shape
         ls = encoder.layers
         FF = ls[0].linear1.out_features
@@ -677,7 +629,7 @@ class _TransformerFunction(torch.autograd.Function):
                 _lib.ptr(fn.weight.detach()) if fn is not None else None,
                 _lib.ptr(fn.bias.detach()) if fn is not None else None,
                 float(ls[0].norm1.eps), float(dropout_p), _lib.ptr(rng), _lib.ptr(masks), precision,
-                _lib.ptr(packed), _lib.ptr(out), _lib.ptr(ws), ws_bytes, _lib.cuda_stream(dev))
+                _lib.ptr(out), _lib.ptr(ws), ws_bytes, _lib.cuda_stream(dev))
         _lib.check(rc, 'mpa_transformer_forward')
         ctx.save_for_backward(tokens, valid if valid is not None else tokens.new_empty(0),
                               masks if masks is not None else tokens.new_empty(0))
@@ -710,7 +662,7 @@ class _TransformerFunction(torch.autograd.Function):
                 out = encoder(t, src_key_padding_mask=pad)
             grads = torch.autograd.grad(out, [t] + params, grad.to(out.dtype), allow_unused=True)
         torch.backends.cuda.matmul.allow_tf32 = prev_tf32
-        return (grads[0], None, None, None, None, None, None) + tuple(grads[1:])
+        return (grads[0], None, None, None, None, None) + tuple(grads[1:])
 
 
 # tests set this to a list to receive the dropout keep masks of every native forward
@@ -730,8 +682,6 @@ def transformer_forward(tokens, valid_masks, encoder, num_heads, training, dropo
     # native in both precisions: bf16 operands under autocast / set_precision('bf16'), the
     # fp32-accurate three-plane mode otherwise (the reference's default, scripts/train.py:88)
     precision = PRECISION_BF16 if _use_bf16() else PRECISION_FP32
-    # always join a pending weight prefetch (a forked side stream must not be left dangling)
-    packed = _take_packed(encoder, precision, tokens.device)
     native = layer0.norm_first and (not training or len(rates) == 0) and \
         tokens.shape[1] <= 32 and tokens.shape[2] % 32 == 0 and ff % 8 == 0 and \
         tokens.shape[2] // num_heads <= 64 and (p == 0. or ff % 32 == 0)
@@ -739,7 +689,7 @@ def transformer_forward(tokens, valid_masks, encoder, num_heads, training, dropo
         params = [p_ for p_ in encoder.parameters()]
         with torch.autocast('cuda', enabled=False):
             return _TransformerFunction.apply(tokens.float().contiguous(), valid_masks, encoder,
-                                              num_heads, p, precision, packed, *params)
+                                              num_heads, p, precision, *params)
     pad = None if valid_masks is None else ~valid_masks
     prev = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = False

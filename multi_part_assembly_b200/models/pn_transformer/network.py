@@ -53,9 +53,6 @@ class PNTransformer(BaseModel):
         feats = data_dict.get('pre_pose_feats', None)
         if feats is None:
             part_valids = data_dict['part_valids']
-            # the transformer's weight image only depends on the parameters: convert it on a
-            # side stream while the part encoder runs
-            kernels.transformer_prefetch(self.corr_module.transformer_encoder, part_valids.device)
             pc_feats = self._extract_part_feats(data_dict['part_pcs'], part_valids)
             corr_feats = self.corr_module(pc_feats, part_valids == 1)
             feats = torch.cat([corr_feats, data_dict['part_label'].type_as(corr_feats),
