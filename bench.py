@@ -8,6 +8,7 @@ The default, `--config C`, is the configuration the metric is quoted on (`config
 pn_transformer, B=32 shapes x P=20 valid parts x N=1000 points per GPU, bf16 tensor-core
 GEMMs, Chamfer / SE(3) always fp32).  The other BASELINE.json configs are selectable:
 
+    S  (extra)     pn_transformer on the semantic PartNet config: matching + Min-of-N, eager
     B  configs[1]  global PointNet encoder model, B=32, 8 valid parts, N=1000      (weak)
     C  configs[2]  pn_transformer, B=32 per GPU, 20 valid parts, N=1000            (weak)
     D  configs[3]  dgl + DGCNN (k=20 EdgeConv), B=32 per GPU, 16 valid parts, fp32 (weak)
@@ -61,6 +62,12 @@ CONFIGS = {
     'E': dict(model='pn_transformer', encoder='pointnet', batch=256, valid=20, points=1000,
               dtype='bf16', scaling='strong',
               ref='configs[4]: pn_transformer, global batch 256 split over the ranks'),
+    # not in BASELINE.json: the semantic (PartNet) variant -- Hungarian matching of equivalent
+    # parts + Min-of-N over 5 sampled predictions; eager launches (the step
+    # draws CPU random numbers like the reference, so it is not graph-captured)
+    'S': dict(model='pn_transformer', encoder='pointnet', batch=32, valid=20, points=1000,
+              dtype='bf16', scaling='weak', dataset='partnet_chair',
+              ref='configs/pn_transformer partnet_chair (semantic: matching + Min-of-N)'),
 }
 FP32_PAIR_PEAK = 148 * 128 * 1.965e9 / 9.0  # pair evaluations / s at 9 FP32 issue slots each
 
@@ -104,7 +111,7 @@ def run_reference(args):
     if rank != 0:
         return
     c = CONFIGS[args.config]
-    if c['model'] != 'pn_transformer':
+    if c['model'] != 'pn_transformer' or 'dataset' in c:
         args.emit({'impl': 'reference', 'unavailable':
                    f"the CPU port covers pn_transformer (configs C, E); config {args.config} has none"})
         return
@@ -153,7 +160,7 @@ def run_reference_gpu(args):
     dev = torch.device('cuda', args.device)
     torch.cuda.set_device(dev)
     B = args.batch or c['batch']
-    cfg = get_cfg(c['model'], 'everyday', encoder=c['encoder'])
+    cfg = get_cfg(c['model'], c.get('dataset', 'everyday'), encoder=c['encoder'])
     torch.manual_seed(0)
     model = ref_build_model(cfg).to(dev).train()
     model.trainer = Trainer()
@@ -162,7 +169,8 @@ def run_reference_gpu(args):
             m.p = 0.0
         if isinstance(m, torch.nn.MultiheadAttention):
             m.dropout = 0.0
-    batch = make_batch(B, P=P, N=args.points, num_valid=c['valid'], seed=0, device=dev)
+    batch = make_batch(B, P=P, N=args.points, num_valid=c['valid'], seed=0, device=dev,
+                       semantic=c.get('dataset', 'everyday') != 'everyday')
     flush = torch.empty(192 << 20, dtype=torch.uint8, device=dev)
     out = {'batch': B, 'points': args.points}
     for name, amp in (('fp32', None), ('fp16', torch.float16)):
@@ -332,14 +340,14 @@ def run_native(args):
         stack = torch.stack(allv)  # [world, len]
         return stack.max(0)[0].tolist(), stack.t().tolist()
 
-    def setup(model_name, encoder, per_gpu, valid, points, seed):
+    def setup(model_name, encoder, per_gpu, valid, points, seed, dataset='everyday'):
         """Model + pinned host batches + the stepping functions for one workload."""
         torch.manual_seed(seed)
-        cfg = get_cfg(model_name, 'everyday', encoder=encoder)
+        cfg = get_cfg(model_name, dataset, encoder=encoder)
         model = no_dropout(build_model(cfg)).to(dev).train()
         model.trainer = Trainer()
         hosts = [make_batch(per_gpu, P=P, N=points, num_valid=valid, seed=seed + 1000 * i,
-                            pin_memory=True) for i in range(2)]
+                            semantic=dataset != 'everyday', pin_memory=True) for i in range(2)]
         resident = {k: v.to(dev) for k, v in hosts[0].items()}
 
         def eager_step(batch):
@@ -364,7 +372,8 @@ def run_native(args):
 
     per_gpu = c['batch'] // world if c['scaling'] == 'strong' else c['batch']
     assert per_gpu >= 1, 'more ranks than shapes'
-    w = setup(c['model'], c['encoder'], per_gpu, c['valid'], args.points, rank)
+    w = setup(c['model'], c['encoder'], per_gpu, c['valid'], args.points, rank,
+              c.get('dataset', 'everyday'))
     model, hosts, resident, graphed = w['model'], w['hosts'], w['resident'], w['graphed']
     eager_step, step, graph_error = w['eager_step'], w['step'], w['graph_error']
     h2d_bytes = sum(v.numel() * v.element_size() for v in hosts[0].values())
@@ -432,7 +441,7 @@ def run_native(args):
     # secondary figure: the whole training step as one CUDA graph
     train = None
     ms_train = 0.0
-    if not args.no_train and c['model'] == 'pn_transformer':
+    if not args.no_train and c['model'] == 'pn_transformer' and 'dataset' not in c:
         try:
             from multi_part_assembly_b200.runtime import GraphedTrainStep
             opt = model.configure_optimizers()
@@ -573,7 +582,7 @@ def run_native(args):
 
     threads = os.cpu_count() or 1
     cpu = None
-    if c['model'] == 'pn_transformer':
+    if c['model'] == 'pn_transformer' and 'dataset' not in c:
         cpu_B = 8
         cpu_step(2, 0, threads, args.points)
         cpu_t = cpu_step(cpu_B, 1, threads, args.points)

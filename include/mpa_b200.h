@@ -324,6 +324,23 @@ int mpa_bn_pool(const float* y, const float* valids, int n, int N, int F, const 
                 float momentum, float eps, float slope, float* g, void* ws, size_t ws_bytes,
                 void* stream);
 
+/* BaseModel._match_parts (models/modules/base_model.py:181-238) for a whole batch: for every
+ * group of geometrically equivalent parts the p x p cost matrix of :162-174 (Chamfer distance
+ * between part i under its predicted pose and part j under its ground-truth pose on the group's
+ * n-point random subsample), the min-cost assignment (SciPy's linear_sum_assignment algorithm,
+ * :175) and the permuted ground-truth poses (:229-233), in three launches.  The group table is
+ * built on the host, which also draws the subsamples with the reference's RNG calls
+ * (torch.randperm per group, :165).  table (device int32): shape [G] | size [G] | cost offset
+ * [G] | row offset [G] | members [G,32] | subsample [G,n] | entries (g<<16 | i<<8 | j)
+ * [n_pairs].  new_trans / new_quat [B,P,3/4] must hold copies of the ground truth on entry.
+ * costs_out / col_out (nullable): the cost matrices and assignments for inspection. */
+size_t mpa_match_parts_workspace_bytes(int n_pairs, int total_rows);
+int mpa_match_parts(const float* pts, const float* pred_quat, const float* pred_trans,
+                    const float* gt_quat, const float* gt_trans, int B, int P, int N, int n,
+                    const int32_t* table, int G, int n_pairs, int total_rows, int max_size,
+                    float* new_trans, float* new_quat, float* costs_out, int32_t* col_out, void* ws,
+                    size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

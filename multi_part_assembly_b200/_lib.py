@@ -54,6 +54,9 @@ _SIGNATURES = {
     'mpa_bn_backward': (c_int, [c_void_p] * 9 + [ctypes.c_longlong, c_int, c_int] + [c_void_p] * 4),
     'mpa_pool_argmax': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     'mpa_lsap_batched': (c_int, [c_void_p] * 4 + [c_int, c_int, c_void_p, c_void_p]),
+    'mpa_match_parts_workspace_bytes': (c_size_t, [c_int] * 2),
+    'mpa_match_parts': (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p] + [c_int] * 4 + [c_void_p] * 5 +
+                        [c_size_t, c_void_p]),
     'mpa_linear_workspace_bytes': (c_size_t, [c_int] * 3),
     'mpa_linear_workspace_bytes_ex': (c_size_t, [c_int] * 4),
     'mpa_linear_forward_ex': (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p, c_void_p, c_size_t, c_void_p]),

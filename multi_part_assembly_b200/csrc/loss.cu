@@ -338,6 +338,84 @@ __global__ void lsap_kernel(const float* __restrict__ costs, const int* __restri
   for (int r = 0; r < n; ++r) out[r] = col4row[r];
 }
 
+
+// ---- part matching of the semantic models (reference base_model.py:150-238) ----------------
+// Cost entry (i, j) of one group of geometrically equivalent parts: Chamfer distance between
+// the group's i-th part under its PREDICTED pose and its j-th part under its GROUND-TRUTH pose,
+// on the n points the group's random subsample picked (mean of the nearest squared distances
+// of both directions, :170-174).  One CTA per entry: both clouds (n <= MATCH_MAX_N points) are
+// transformed into shared memory, thread t owns query t of either direction.
+constexpr int MATCH_MAX_N = 128;
+constexpr int MATCH_MAXP = 32;   // parts per group
+__device__ __forceinline__ float block_sum_128(float v, float* s_red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  const float t = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
+  __syncthreads();
+  return t;
+}
+__global__ void __launch_bounds__(MATCH_MAX_N)
+match_cost_kernel(const float* __restrict__ pts, const float* __restrict__ q1, const float* __restrict__ t1,
+                  const float* __restrict__ q2, const float* __restrict__ t2, int P, int N, int n,
+                  const int* __restrict__ g_shape, const int* __restrict__ g_size,
+                  const int* __restrict__ g_cost_off, const int* __restrict__ g_members,
+                  const int* __restrict__ g_sample, const int* __restrict__ pairs,
+                  float* __restrict__ costs) {
+  __shared__ float ax[MATCH_MAX_N], ay[MATCH_MAX_N], az[MATCH_MAX_N];
+  __shared__ float bx[MATCH_MAX_N], by[MATCH_MAX_N], bz[MATCH_MAX_N];
+  __shared__ float s_red[4];
+  const int pr = pairs[blockIdx.x];
+  const int g = pr >> 16, i = (pr >> 8) & 0xff, j = pr & 0xff;
+  const int b = g_shape[g], p = g_size[g];
+  const int part_i = g_members[g * MATCH_MAXP + i], part_j = g_members[g * MATCH_MAXP + j];
+  const int t = threadIdx.x;
+  if (t < n) {
+    const int k = g_sample[g * n + t];
+    const float* pi = pts + ((long long)(b * P + part_i) * N + k) * 3;
+    const float* pj = pts + ((long long)(b * P + part_j) * N + k) * 3;
+    const float* qa = q1 + (long long)(b * P + part_i) * 4;
+    const float* qb = q2 + (long long)(b * P + part_j) * 4;
+    const float qA[4] = {qa[0], qa[1], qa[2], qa[3]}, qB[4] = {qb[0], qb[1], qb[2], qb[3]};
+    const float3 a = se3_apply(qA, t1 + (long long)(b * P + part_i) * 3, make_float3(pi[0], pi[1], pi[2]));
+    const float3 c = se3_apply(qB, t2 + (long long)(b * P + part_j) * 3, make_float3(pj[0], pj[1], pj[2]));
+    ax[t] = a.x; ay[t] = a.y; az[t] = a.z;
+    bx[t] = c.x; by[t] = c.y; bz[t] = c.z;
+  }
+  __syncthreads();
+  float d1 = 0.f, d2 = 0.f;
+  if (t < n) {
+    float m1 = 1e32f, m2 = 1e32f;  // chamfer_kernel.cu:60
+    const float x1 = ax[t], y1 = ay[t], z1 = az[t], x2 = bx[t], y2 = by[t], z2 = bz[t];
+    for (int k = 0; k < n; ++k) {
+      m1 = fminf(m1, sqdist_ref(x1, y1, z1, bx[k], by[k], bz[k]));
+      m2 = fminf(m2, sqdist_ref(x2, y2, z2, ax[k], ay[k], az[k]));
+    }
+    d1 = m1; d2 = m2;
+  }
+  const float s1 = block_sum_128(d1, s_red), s2 = block_sum_128(d2, s_red);
+  if (t == 0) costs[g_cost_off[g] + i * p + j] = s1 / (float)n + s2 / (float)n;
+}
+
+// new_gt[b, members[r]] = gt[b, members[col[r]]] for every group (reference :229-233)
+__global__ void match_permute_kernel(const float* __restrict__ gt_trans, const float* __restrict__ gt_quat, int P,
+                                     const int* __restrict__ g_shape, const int* __restrict__ g_size,
+                                     const int* __restrict__ g_out_off, const int* __restrict__ g_members,
+                                     const int* __restrict__ col_of_row, int G, float* __restrict__ new_trans,
+                                     float* __restrict__ new_quat) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = e / MATCH_MAXP, r = e % MATCH_MAXP;
+  if (g >= G || r >= g_size[g]) return;
+  const int b = g_shape[g];
+  const int dst = b * P + g_members[g * MATCH_MAXP + r];
+  const int src = b * P + g_members[g * MATCH_MAXP + col_of_row[g_out_off[g] + r]];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) new_trans[dst * 3 + k] = gt_trans[src * 3 + k];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) new_quat[dst * 4 + k] = gt_quat[src * 4 + k];
+}
+
 }  // namespace mpa
 
 using namespace mpa;
@@ -431,6 +509,63 @@ int mpa_lsap_batched(const float* costs, const int32_t* cost_offsets, const int3
     ProfScope ps("lsap", stream);
     lsap_kernel<<<(n_problems + 31) / 32, 32, 0, stream>>>(costs, cost_offsets, sizes, out_offsets, n_problems,
                                                            col_of_row);
+  }
+  MPA_LAUNCH_CHECK();
+  return MPA_OK;
+}
+
+
+/* Matching of all groups of equivalent parts of a batch in three launches: cost matrices,
+ * assignments (lsap_kernel), permuted ground-truth poses.  `table` (device int32) holds, for G
+ * groups: shape index [G], size p_g [G], cost offset [G], output offset [G], members
+ * [G, 32] (part indices), subsample [G, n] (point indices) and the (g << 16 | i << 8 | j)
+ * entry list [n_pairs]; new_trans / new_quat must already hold copies of the ground truth. */
+size_t mpa_match_parts_workspace_bytes(int n_pairs, int total_rows) {
+  return align_up(sizeof(float) * (size_t)(n_pairs > 0 ? n_pairs : 1), 256) +
+         align_up(sizeof(int) * (size_t)(total_rows > 0 ? total_rows : 1), 256);
+}
+
+int mpa_match_parts(const float* pts, const float* pred_quat, const float* pred_trans, const float* gt_quat,
+                    const float* gt_trans, int B, int P, int N, int n, const int32_t* table, int G, int n_pairs,
+                    int total_rows, int max_size, float* new_trans, float* new_quat, float* costs_out,
+                    int32_t* col_out, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MPA_CHECK_ARG(B >= 0 && P > 0 && N > 0 && n > 0 && n <= MATCH_MAX_N && n <= N, "match_parts: bad sizes");
+  MPA_CHECK_ARG(G >= 0 && max_size <= MATCH_MAXP && max_size <= LSAP_MAX, "match_parts: groups of at most %d parts",
+                MATCH_MAXP);
+  if (G == 0) return MPA_OK;
+  MPA_CHECK_ARG(pts && pred_quat && pred_trans && gt_quat && gt_trans && table && new_trans && new_quat,
+                "match_parts: null pointer");
+  Scratch scratch;
+  int rc = scratch.acquire(ws, ws_bytes, mpa_match_parts_workspace_bytes(n_pairs, total_rows), stream);
+  if (rc != MPA_OK) return rc;
+  float* costs = costs_out != nullptr ? costs_out : (float*)scratch.base;
+  int* col = col_out != nullptr ? col_out
+                                : (int*)((char*)scratch.base + align_up(sizeof(float) * (size_t)n_pairs, 256));
+  const int* g_shape = table;
+  const int* g_size = table + G;
+  const int* g_cost_off = table + 2 * G;
+  const int* g_out_off = table + 3 * G;
+  const int* g_members = table + 4 * G;
+  const int* g_sample = g_members + (size_t)G * MATCH_MAXP;
+  const int* pairs = g_sample + (size_t)G * n;
+  {
+    ProfScope ps("match_cost", stream);
+    match_cost_kernel<<<n_pairs, MATCH_MAX_N, 0, stream>>>(pts, pred_quat, pred_trans, gt_quat, gt_trans, P, N, n,
+                                                          g_shape, g_size, g_cost_off, g_members, g_sample, pairs,
+                                                          costs);
+  }
+  MPA_LAUNCH_CHECK();
+  {
+    ProfScope ps("lsap", stream);
+    lsap_kernel<<<(G + 31) / 32, 32, 0, stream>>>(costs, g_cost_off, g_size, g_out_off, G, col);
+  }
+  MPA_LAUNCH_CHECK();
+  {
+    ProfScope ps("match_permute", stream);
+    match_permute_kernel<<<(G * MATCH_MAXP + 127) / 128, 128, 0, stream>>>(gt_trans, gt_quat, P, g_shape, g_size,
+                                                                         g_out_off, g_members, col, G, new_trans,
+                                                                         new_quat);
   }
   MPA_LAUNCH_CHECK();
   return MPA_OK;

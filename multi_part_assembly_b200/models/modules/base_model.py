@@ -141,34 +141,99 @@ class BaseModel(LightningModule):
         cind = kernels.lsap_batched([dist_mat])[0]
         return torch.arange(cind.shape[0], device=cind.device), cind
 
+    def _match_groups(self, match_ids):
+        """Groups of equivalent parts of a batch, in the reference's visiting order (shape by
+        shape, group id ascending, :207-218): list of (shape index, member part indices).
+        The group structure comes from the data loader; it is read on the host once per
+        batch (the Min-of-N samples of a step reuse it) because the reference draws one CPU
+        `torch.randperm` per group (:165) -- the number of draws is data dependent."""
+        key = (match_ids.data_ptr(), match_ids._version, tuple(match_ids.shape))
+        cache = getattr(self, '_match_cache', None)
+        if cache is not None and cache[0] == key:
+            return cache[1]
+        ids_host = match_ids.long().cpu().numpy()
+        groups = []
+        for ind in range(ids_host.shape[0]):
+            for g in range(1, int(ids_host[ind].max()) + 1):
+                members = np.nonzero(ids_host[ind] == g)[0]
+                if len(members):
+                    groups.append((ind, members.astype(np.int32)))
+                else:  # an empty group still costs the reference one randperm draw
+                    groups.append((ind, members.astype(np.int32)))
+        self._match_cache = (key, groups)
+        return groups
+
     @torch.no_grad()
     def _match_parts(self, part_pcs, pred_trans, pred_rot, gt_trans, gt_rot, match_ids):
         """Semantic assembly: permute the GT poses inside every group of
         geometrically equivalent parts to the min-cost assignment against the
         predictions (reference :181-238).  `match_ids` [B, P]: 0 = unique or
-        padded, g > 0 = group id."""
-        match_ids = match_ids.long()
+        padded, g > 0 = group id.
+
+        All groups of the batch go through ONE fused call (csrc/loss.cu `mpa_match_parts`:
+        cost matrices, assignments, permutation -- three launches, nothing returns to the
+        host); the host only builds the group table and draws the subsamples with the
+        reference's RNG calls."""
+        from ... import _lib
+        groups = self._match_groups(match_ids)
+        new_gt_trans = gt_trans.detach().clone().float().contiguous()
+        new_gt_quat = gt_rot.rot.detach().clone().float().contiguous()
+        B, P, N, _ = part_pcs.shape
+        n = min(100, N)
+        if self.rot_type != 'quat' or not part_pcs.is_cuda:
+            return self._match_parts_loop(part_pcs, pred_trans, pred_rot, gt_trans, gt_rot, groups)
+        # the reference's RNG consumption: one randperm(N) per group, in visiting order
+        samples = [torch.randperm(N)[:n] for _ in groups]
+        live = [(k, ind, m) for k, (ind, m) in enumerate(groups) if len(m) > 0]
+        if not live:
+            return new_gt_trans.type_as(gt_trans), self._wrap_rotation(new_gt_quat.type_as(gt_rot.rot))
+        G = len(live)
+        MAXP = 32
+        sizes = np.array([len(m) for _, _, m in live], np.int32)
+        assert sizes.max() <= MAXP, 'groups of at most 32 equivalent parts'
+        cost_off = np.concatenate(([0], np.cumsum(sizes.astype(np.int64)**2)[:-1])).astype(np.int32)
+        out_off = np.concatenate(([0], np.cumsum(sizes)[:-1])).astype(np.int32)
+        members = np.zeros((G, MAXP), np.int32)
+        for r, (_, _, m) in enumerate(live):
+            members[r, :len(m)] = m
+        sample = torch.stack([samples[k] for k, _, _ in live]).to(torch.int32).numpy()
+        pairs = np.concatenate([(r << 16) | (np.arange(p)[:, None] << 8) | np.arange(p)[None, :]
+                                for r, p in enumerate(sizes)], axis=None).astype(np.int32)
+        table = np.concatenate([np.array([ind for _, ind, _ in live], np.int32), sizes, cost_off, out_off,
+                                members.ravel(), sample.ravel(), pairs])
+        dev = part_pcs.device
+        table_d = torch.from_numpy(table).to(dev, non_blocking=True)
+        n_pairs, total_rows = int(pairs.size), int(sizes.sum())
+        L = _lib.lib()
+        pts = part_pcs.detach().float().contiguous()
+        q1 = pred_rot.rot.detach().float().contiguous()
+        t1 = pred_trans.detach().float().contiguous()
+        q2 = gt_rot.rot.detach().float().contiguous()
+        t2 = gt_trans.detach().float().contiguous()
+        ws_bytes = L.mpa_match_parts_workspace_bytes(n_pairs, total_rows)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = L.mpa_match_parts(_lib.ptr(pts), _lib.ptr(q1), _lib.ptr(t1), _lib.ptr(q2), _lib.ptr(t2),
+                                   B, P, N, n, _lib.ptr(table_d), G, n_pairs, total_rows, int(sizes.max()),
+                                   _lib.ptr(new_gt_trans), _lib.ptr(new_gt_quat), None, None,
+                                   _lib.ptr(ws), ws_bytes, _lib.cuda_stream(dev))
+        _lib.check(rc, 'mpa_match_parts')
+        return new_gt_trans.type_as(gt_trans), self._wrap_rotation(new_gt_quat.type_as(gt_rot.rot))
+
+    @torch.no_grad()
+    def _match_parts_loop(self, part_pcs, pred_trans, pred_rot, gt_trans, gt_rot, groups):
+        """Per-group formulation (rotation-matrix poses): cost matrices with the generic ops,
+        all assignments in one launch."""
         new_gt_trans = gt_trans.detach().clone()
         new_gt_rot_tensor = gt_rot.detach().clone().rot
         gt_rot_tensor = gt_rot.rot
         pred_rot_tensor = pred_rot.rot
-
-        # one host copy of the ids instead of a sync per (shape, group)
-        ids_host = match_ids.cpu().numpy()
-        groups = []  # (shape index, part indices)
-        for ind in range(part_pcs.shape[0]):
-            for g in range(1, int(ids_host[ind].max()) + 1):
-                members = np.nonzero(ids_host[ind] == g)[0]
-                groups.append((ind, torch.from_numpy(members).to(part_pcs.device)))
-        # cost matrices in group order (keeps the reference's RNG consumption:
-        # one torch.randperm(N) per group), then one batched host copy
+        dev = part_pcs.device
+        groups = [(ind, torch.from_numpy(m.astype(np.int64)).to(dev)) for ind, m in groups]
         costs = [self._match_cost(part_pcs[ind, m], pred_trans[ind, m], pred_rot_tensor[ind, m],
                                   gt_trans[ind, m], new_gt_rot_tensor[ind, m])
                  for ind, m in groups]
         if costs:
-            # all assignments in one launch on the device (same algorithm as SciPy's
-            # linear_sum_assignment: oracle/lsap.py is pinned against it); no cost matrix
-            # travels to the host
             from ... import kernels
             for (ind, m), cind in zip(groups, kernels.lsap_batched(costs)):
                 new_gt_trans[ind, m] = gt_trans[ind, m][cind]
