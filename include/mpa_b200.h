@@ -341,6 +341,30 @@ int mpa_match_parts(const float* pts, const float* pred_quat, const float* pred_
                     float* new_trans, float* new_quat, float* costs_out, int32_t* col_out, void* ws,
                     size_t ws_bytes, void* stream);
 
+/* ---- PointNet++ set abstraction (encoder/pointnet2; pointnet2_ops CUDA extension) ---- */
+/* furthest_point_sampling (_ext-src/src/sampling_gpu.cu:74-177) + gather_operation of the picked
+ * centroids (pointnet2_modules.py:53-61): xyz [B,n,3] -> idx [B,m] int32 (first pick = point 0;
+ * points with |p|^2 <= 1e-3 are skipped; ties follow the reference's strided tree reduction for
+ * its block size opt_n_threads(n)), new_xyz [B,m,3] (nullable). */
+int mpa_furthest_point_sample(const float* xyz, int B, int n, int m, int32_t* idx, float* new_xyz,
+                              void* stream);
+/* ball_query (_ext-src/src/ball_query_gpu.cu:13-48): idx [B,m,nsample] = the first nsample
+ * points (index order) within `radius` of each centroid, padded with the first hit (zeros when
+ * there is none). */
+int mpa_ball_query(const float* xyz, const float* new_xyz, int B, int n, int m, float radius,
+                   int nsample, int32_t* idx, void* stream);
+/* group_points + QueryAndGroup / GroupAll (group_points_gpu.cu:12-32, pointnet2_utils.py:309-392)
+ * as the row matrix of the shared MLP: out [B*m*nsample, ld] rows = [xyz[idx] - centroid |
+ * feats[idx]] (idx == NULL: GroupAll, rows [B*n, ld] = [xyz | feats]); feats channels-last
+ * [B,n,C] (nullable when C == 0); columns >= 3 + C are zero padding. */
+int mpa_group_rows(const float* xyz, const float* new_xyz, const float* feats, const int32_t* idx,
+                   int B, int n, int m, int nsample, int C, int ld, float* out, void* stream);
+/* fp64 (sum, sum of squares) per column of y [n_blocks*R, F]: BatchNorm2d batch statistics of a
+ * shared-MLP layer (pointnet2_modules.py:10-22). */
+size_t mpa_column_stats_workspace_bytes(int n_blocks, int F);
+int mpa_column_stats(const float* y, int n_blocks, int R, int F, double* sums, void* ws,
+                     size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,6 +78,12 @@ _SIGNATURES = {
     'mpa_bn_pool': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int] + [c_void_p] * 4 +
                     [c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, c_void_p, c_void_p, c_size_t,
                      c_void_p]),
+    'mpa_furthest_point_sample': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'mpa_ball_query': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, ctypes.c_float, c_int, c_void_p,
+                               c_void_p]),
+    'mpa_group_rows': (c_int, [c_void_p] * 4 + [c_int] * 6 + [c_void_p, c_void_p]),
+    'mpa_column_stats_workspace_bytes': (c_size_t, [c_int] * 2),
+    'mpa_column_stats': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     'mpa_pose_chamfer_backward_workspace_bytes': (c_size_t, [c_int] * 3),
     'mpa_pose_chamfer_backward': (c_int, [c_void_p] * 10 + [c_int] * 4 +
                                   [c_void_p] * 5 + [c_size_t, c_void_p]),

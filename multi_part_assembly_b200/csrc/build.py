@@ -7,7 +7,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ['mpa_runtime.cu', 'chamfer.cu', 'se3.cu', 'pointnet.cu', 'pointnet_bwd.cu', 'linear.cu', 'knn.cu', 'loss.cu']
+SOURCES = ['mpa_runtime.cu', 'chamfer.cu', 'se3.cu', 'pointnet.cu', 'pointnet_bwd.cu', 'linear.cu', 'knn.cu', 'loss.cu', 'pointnet2.cu']
 HEADERS = ['mpa_common.cuh', 'tc05.cuh', os.path.join('..', '..', 'include', 'mpa_b200.h')]
 TARGET = os.path.join(HERE, 'libmpa_b200.so')
 NVCC = os.environ.get('MPA_NVCC', '/usr/local/cuda/bin/nvcc')

@@ -378,8 +378,8 @@ def _edgeconv_finish(ymax, ymin, sums, valids, n, N, Co, k, bn, training, out, o
     _lib.check(rc, 'mpa_edgeconv_finish')
 
 
-def _bn_pool(y, valids, n, N, bn, training):
-    """conv5 epilogue: BatchNorm1d + LeakyReLU(0.2) + [max | mean] over the points -> [n, 2F]."""
+def _bn_pool(y, valids, n, N, bn, training, slope=0.2):
+    """conv5 epilogue: BatchNorm1d + LeakyReLU(slope) + [max | mean] over the points -> [n, 2F]."""
     dev = y.device
     Fd = y.shape[1]
     g = torch.empty(n, 2 * Fd, dtype=torch.float32, device=dev)
@@ -390,7 +390,7 @@ def _bn_pool(y, valids, n, N, bn, training):
         rc = L.mpa_bn_pool(_lib.ptr(y), _lib.ptr(valids), n, N, Fd, _lib.ptr(bn.weight.detach()),
                            _lib.ptr(bn.bias.detach()), _lib.ptr(bn.running_mean),
                            _lib.ptr(bn.running_var), 1 if training else 0, float(bn.momentum),
-                           float(bn.eps), 0.2, _lib.ptr(g), _lib.ptr(ws), ws_bytes,
+                           float(bn.eps), float(slope), _lib.ptr(g), _lib.ptr(ws), ws_bytes,
                            _lib.cuda_stream(dev))
     _lib.check(rc, 'mpa_bn_pool')
     return g
@@ -519,6 +519,212 @@ def dgcnn_forward(x, m, training, k=20, valids=None):
         return _DGCNNFunction.apply(x.float().contiguous(),
                                     None if valids is None else valids.float().contiguous(),
                                     m, training, k, bf16, *params)
+
+
+# ---------------------------------------------------------------------------
+# PointNet++ (set abstraction)
+# ---------------------------------------------------------------------------
+def furthest_point_sample(xyz, npoint):
+    """xyz [B, n, 3] -> (idx [B, npoint] int32, new_xyz [B, npoint, 3])
+    (pointnet2_utils.py:35-60 + the gather of pointnet2_modules.py:53-61)."""
+    _lib.require_cuda(xyz)
+    xyz = xyz.float().contiguous()
+    B, n, _ = xyz.shape
+    idx = torch.empty(B, npoint, dtype=torch.int32, device=xyz.device)
+    new_xyz = torch.empty(B, npoint, 3, dtype=torch.float32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        rc = _lib.lib().mpa_furthest_point_sample(_lib.ptr(xyz), B, n, npoint, _lib.ptr(idx),
+                                                  _lib.ptr(new_xyz), _lib.cuda_stream(xyz.device))
+    _lib.check(rc, 'mpa_furthest_point_sample')
+    return idx, new_xyz
+
+
+def ball_query(radius, nsample, xyz, new_xyz):
+    """idx [B, m, nsample] int32 (pointnet2_utils.py:254-281)."""
+    _lib.require_cuda(xyz, new_xyz)
+    xyz, new_xyz = xyz.float().contiguous(), new_xyz.float().contiguous()
+    B, n, _ = xyz.shape
+    m = new_xyz.shape[1]
+    idx = torch.empty(B, m, nsample, dtype=torch.int32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        rc = _lib.lib().mpa_ball_query(_lib.ptr(xyz), _lib.ptr(new_xyz), B, n, m, float(radius), nsample,
+                                       _lib.ptr(idx), _lib.cuda_stream(xyz.device))
+    _lib.check(rc, 'mpa_ball_query')
+    return idx
+
+
+def _group_rows(xyz, new_xyz, feats, idx, ld):
+    B, n, _ = xyz.shape
+    C = 0 if feats is None else feats.shape[2]
+    if idx is None:
+        m, nsample, rows = 0, 0, B * n
+    else:
+        m, nsample = idx.shape[1], idx.shape[2]
+        rows = B * m * nsample
+    out = torch.empty(rows, ld, dtype=torch.float32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        rc = _lib.lib().mpa_group_rows(_lib.ptr(xyz), _lib.ptr(new_xyz), _lib.ptr(feats), _lib.ptr(idx),
+                                       B, n, m, nsample, C, ld, _lib.ptr(out), _lib.cuda_stream(xyz.device))
+    _lib.check(rc, 'mpa_group_rows')
+    return out
+
+
+def _column_sums(y, n_blocks, R):
+    dev = y.device
+    Fd = y.shape[1]
+    sums = torch.empty(Fd, 2, dtype=torch.float64, device=dev)
+    L = _lib.lib()
+    ws_bytes = L.mpa_column_stats_workspace_bytes(n_blocks, Fd)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.mpa_column_stats(_lib.ptr(y), n_blocks, R, Fd, _lib.ptr(sums), _lib.ptr(ws), ws_bytes,
+                                _lib.cuda_stream(dev))
+    _lib.check(rc, 'mpa_column_stats')
+    return sums
+
+
+def _bn_relu_rows(y, sums, n_blocks, R, bn, training):
+    """BatchNorm2d + ReLU on the rows of a shared-MLP layer (statistics over all rows)."""
+    dev = y.device
+    Fd = y.shape[1]
+    out = torch.empty_like(y)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().mpa_edgeconv_finish(
+            _lib.ptr(y), _lib.ptr(y), _lib.ptr(sums), None, n_blocks, R, Fd, 1,
+            _lib.ptr(bn.weight.detach()), _lib.ptr(bn.bias.detach()), _lib.ptr(bn.running_mean),
+            _lib.ptr(bn.running_var), 1 if training else 0, float(bn.momentum), float(bn.eps), 0.0,
+            _lib.ptr(out), None, 0, 0, _lib.cuda_stream(dev))
+    _lib.check(rc, 'mpa_edgeconv_finish')
+    return out
+
+
+def _shared_mlp_max(rows, mlp, n_groups, R, training, precision):
+    """rows [n_groups * R, Kp] -> [n_groups, C_out]: the shared MLP (1x1 conv = GEMM on the tensor
+    cores, BatchNorm2d with batch statistics over every row, ReLU) and the max over each group of
+    R rows (pointnet2_modules.py:64-70).  The last layer is never materialised after its
+    activation: ReLU o BatchNorm is monotone per channel, so the group maximum follows from the
+    group max / min of the GEMM output."""
+    convs = [m for m in mlp if isinstance(m, torch.nn.Conv2d)]
+    bns = [m for m in mlp if isinstance(m, torch.nn.BatchNorm2d)]
+    h = rows
+    for li, (conv, bn) in enumerate(zip(convs, bns)):
+        W = conv.weight.detach().reshape(conv.weight.shape[0], -1).float()
+        if W.shape[1] < h.shape[1]:
+            W = F.pad(W, (0, h.shape[1] - W.shape[1]))  # zero columns for the row padding
+        y = linear(h, W, precision=precision)
+        if li + 1 < len(convs):
+            sums = _column_sums(y, n_groups, R) if training else None
+            h = _bn_relu_rows(y, sums, n_groups, R, bn, training)
+        else:
+            g = _bn_pool(y, None, n_groups, R, bn, training, slope=0.0)
+            h = g[:, :y.shape[1]].contiguous()
+        if training:
+            bn.num_batches_tracked += 1
+    return h
+
+
+def _pointnet2_native(x, m, training, bf16, trace=None):
+    precision = PRECISION_BF16 if bf16 else PRECISION_FP32
+    xyz = x.float().contiguous()
+    feats = None  # channels-last [B, n, C]
+    B = xyz.shape[0]
+    for sa in m.SA_modules:
+        n = xyz.shape[1]
+        C = 0 if feats is None else feats.shape[2]
+        ld = (3 + C + 7) // 8 * 8
+        if sa.npoint is None:  # GroupAll: one group of all points per cloud
+            rows = _group_rows(xyz, None, feats, None, ld)
+            out = _shared_mlp_max(rows, sa.mlps[0], B, n, training, precision)
+            xyz, feats = None, out.view(B, 1, -1)
+            continue
+        fps_idx, new_xyz = furthest_point_sample(xyz, sa.npoint)
+        if trace is not None:
+            trace.append(('fps', fps_idx))
+        outs = []
+        for radius, nsample, mlp in zip(sa.radii, sa.nsamples, sa.mlps):
+            idx = ball_query(radius, nsample, xyz, new_xyz)
+            if trace is not None:
+                trace.append(('ball', idx))
+            rows = _group_rows(xyz, new_xyz, feats, idx, ld)
+            outs.append(_shared_mlp_max(rows, mlp, B * sa.npoint, nsample, training, precision))
+        feats = torch.cat(outs, dim=1).view(B, sa.npoint, -1)
+        xyz = new_xyz
+    return feats.reshape(B, -1)
+
+
+def _pointnet2_torch(x, m, trace):
+    """The same network in stock torch ops on the SAME sampling / grouping indices (which are
+    not differentiable): differentiates the native forward, and serves the tests."""
+    xyz = x.float()
+    feats = None
+    B = xyz.shape[0]
+    it = iter(trace)
+    for sa in m.SA_modules:
+        n = xyz.shape[1]
+        if sa.npoint is None:
+            g = xyz if feats is None else torch.cat([xyz, feats], dim=2)  # [B, n, 3 + C]
+            h = sa.mlps[0](g.permute(0, 2, 1).unsqueeze(2))               # [B, C', 1, n]
+            feats = h.max(dim=3)[0].permute(0, 2, 1)                      # [B, 1, C']
+            continue
+        _, fps_idx = next(it)
+        new_xyz = torch.gather(xyz, 1, fps_idx.long().unsqueeze(-1).expand(-1, -1, 3))
+        outs = []
+        for radius, nsample, mlp in zip(sa.radii, sa.nsamples, sa.mlps):
+            _, idx = next(it)
+            ii = idx.long().reshape(B, -1)
+            gx = torch.gather(xyz, 1, ii.unsqueeze(-1).expand(-1, -1, 3)).view(B, sa.npoint, nsample, 3)
+            gx = gx - new_xyz.unsqueeze(2)
+            if feats is not None:
+                gf = torch.gather(feats, 1, ii.unsqueeze(-1).expand(-1, -1, feats.shape[2]))
+                gx = torch.cat([gx, gf.view(B, sa.npoint, nsample, -1)], dim=3)
+            h = mlp(gx.permute(0, 3, 1, 2))                               # [B, C', npoint, nsample]
+            outs.append(h.max(dim=3)[0].permute(0, 2, 1))                 # [B, npoint, C']
+        feats = torch.cat(outs, dim=2)
+        xyz = new_xyz
+    return feats.reshape(B, -1)
+
+
+class _PointNet2Function(torch.autograd.Function):
+    """Forward: native kernels.  Backward: autograd through the stock formulation on the saved
+    sampling / grouping indices (BatchNorm buffers restored so they advance only once)."""
+
+    @staticmethod
+    def forward(ctx, x, m, training, bf16, *params):
+        trace = []
+        out = _pointnet2_native(x, m, training, bf16, trace)
+        ctx.save_for_backward(x, *[t for _, t in trace])
+        ctx.kinds = [k for k, _ in trace]
+        ctx.m = m
+        if _POINTNET2_TRACE is not None:
+            _POINTNET2_TRACE.extend(trace)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        x, *idxs = ctx.saved_tensors
+        m = ctx.m
+        buffers = {n_: b.clone() for n_, b in m.named_buffers()}
+        params = [p for p in m.parameters()]
+        with torch.enable_grad():
+            out = _pointnet2_torch(x.detach(), m, list(zip(ctx.kinds, idxs)))
+            grads = torch.autograd.grad(out, params, grad, allow_unused=True)
+        with torch.no_grad():
+            for n_, b in m.named_buffers():
+                b.copy_(buffers[n_])
+        return (None, None, None, None) + tuple(grads)
+
+
+# tests set this to a list to receive the sampling / grouping indices of a forward
+_POINTNET2_TRACE = None
+
+
+def pointnet2_forward(x, m, training):
+    """x [n, N, 3] -> [n, feat_dim]; `m` is a PointNet2SSG / PointNet2MSG module."""
+    _lib.require_cuda(x)
+    params = [p for p in m.parameters()]
+    bf16 = _use_bf16()
+    with torch.autocast('cuda', enabled=False):
+        return _PointNet2Function.apply(x.float().contiguous(), m, training, bf16, *params)
 
 
 # ---------------------------------------------------------------------------

@@ -1,5 +1,6 @@
 from .pointnet import PointNet
 from .dgcnn import DGCNN
+from .pointnet2 import PointNet2SSG, PointNet2MSG
 
 
 def build_encoder(arch, feat_dim, global_feat=True, **kwargs):
@@ -9,7 +10,10 @@ def build_encoder(arch, feat_dim, global_feat=True, **kwargs):
     if arch == 'dgcnn':
         return DGCNN(feat_dim, global_feat=global_feat)
     if 'pointnet2' in arch:
-        raise NotImplementedError(
-            f'{arch}: the PointNet++ encoders are outside the B200 hot-path scope '
-            '(SURVEY.md 8f rank 3); no shipped config selects them')
+        assert global_feat
+        if 'ssg' in arch:
+            return PointNet2SSG(feat_dim)
+        if 'msg' in arch:
+            return PointNet2MSG(feat_dim)
+        raise NotImplementedError(f'{arch} not supported')
     raise NotImplementedError(f'{arch} is not supported')

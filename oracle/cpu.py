@@ -119,3 +119,23 @@ def knn(x, k=20):
         _p(x, _f32p), ctypes.c_int64(n), ctypes.c_int64(C), ctypes.c_int64(N),
         ctypes.c_int64(k), _p(out, _i64p))
     return out
+
+
+def furthest_point_sample(xyz, m):
+    """xyz [B, n, 3] float32 -> idx [B, m] int64 (pointnet2_ops furthest_point_sampling)."""
+    xyz = _f32(xyz)
+    B, n, _ = xyz.shape
+    out = np.empty((B, m), np.int64)
+    lib().oracle_fps(_p(xyz, _f32p), ctypes.c_int64(B), ctypes.c_int64(n), ctypes.c_int64(m), _p(out, _i64p))
+    return out
+
+
+def ball_query(xyz, new_xyz, radius, nsample):
+    """idx [B, m, nsample] int64 (pointnet2_ops ball_query)."""
+    xyz, new_xyz = _f32(xyz), _f32(new_xyz)
+    B, n, _ = xyz.shape
+    m = new_xyz.shape[1]
+    out = np.empty((B, m, nsample), np.int64)
+    lib().oracle_ball_query(_p(xyz, _f32p), _p(new_xyz, _f32p), ctypes.c_int64(B), ctypes.c_int64(n),
+                            ctypes.c_int64(m), ctypes.c_float(radius), ctypes.c_int64(nsample), _p(out, _i64p))
+    return out

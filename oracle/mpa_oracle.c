@@ -203,6 +203,95 @@ void oracle_knn(const float* x, int64_t n, int64_t C, int64_t N, int64_t k,
   }
 }
 
+/* ---- PointNet++ set abstraction (pointnet2_ops CUDA extension) ---------------------------- */
+/* Squared distance as nvcc contracts the reference's expression (sampling_gpu.cu:103-104,
+ * ball_query_gpu.cu:34-35): t = dy*dy; t = fma(dx,dx,t); t = fma(dz,dz,t). */
+static float sqdist_fused(float x1, float y1, float z1, float x2, float y2, float z2) {
+  const float dx = x1 - x2, dy = y1 - y2, dz = z1 - z2;
+  float t = dy * dy;
+  t = fmaf(dx, dx, t);
+  t = fmaf(dz, dz, t);
+  return t;
+}
+
+/* furthest_point_sampling_kernel (sampling_gpu.cu:74-177), restated thread by thread: `block`
+ * threads (opt_n_threads(n), cuda_utils.h:15-19) each scan a strided slice keeping the first
+ * strict maximum (:106-109), then the shared-memory tree keeps the LOWER slot on ties
+ * (__update, :64-71).  temp starts at 1e10 (sampling.cpp:75); points with |p|^2 <= 1e-3 are
+ * skipped (:100-101). */
+void oracle_fps(const float* xyz, int64_t B, int64_t n, int64_t m, int64_t* idx) {
+  int64_t block = 1;
+  while (block * 2 <= n && block < 512) block *= 2;
+#pragma omp parallel for schedule(dynamic)
+  for (int64_t b = 0; b < B; ++b) {
+    const float* p = xyz + b * n * 3;
+    float* temp = (float*)malloc(sizeof(float) * (size_t)n);
+    float* dists = (float*)malloc(sizeof(float) * (size_t)block);
+    int64_t* dists_i = (int64_t*)malloc(sizeof(int64_t) * (size_t)block);
+    for (int64_t k = 0; k < n; ++k) temp[k] = 1e10f;
+    int64_t old = 0;
+    idx[b * m] = 0;
+    for (int64_t j = 1; j < m; ++j) {
+      const float x1 = p[old * 3], y1 = p[old * 3 + 1], z1 = p[old * 3 + 2];
+      for (int64_t tid = 0; tid < block; ++tid) {
+        int64_t besti = 0;
+        float best = -1.0f;
+        for (int64_t k = tid; k < n; k += block) {
+          const float x2 = p[k * 3], y2 = p[k * 3 + 1], z2 = p[k * 3 + 2];
+          float mag = y2 * y2;
+          mag = fmaf(x2, x2, mag);
+          mag = fmaf(z2, z2, mag);
+          if (mag <= 1e-3f) continue;
+          const float d = sqdist_fused(x2, y2, z2, x1, y1, z1);
+          const float d2 = d < temp[k] ? d : temp[k];
+          temp[k] = d2;
+          besti = d2 > best ? k : besti;
+          best = d2 > best ? d2 : best;
+        }
+        dists[tid] = best;
+        dists_i[tid] = besti;
+      }
+      for (int64_t s = block / 2; s >= 1; s /= 2)
+        for (int64_t tid = 0; tid < s; ++tid) {
+          const float v1 = dists[tid], v2 = dists[tid + s];
+          const int64_t i1 = dists_i[tid], i2 = dists_i[tid + s];
+          dists[tid] = v1 > v2 ? v1 : v2;
+          dists_i[tid] = v2 > v1 ? i2 : i1;
+        }
+      old = dists_i[0];
+      idx[b * m + j] = old;
+    }
+    free(temp);
+    free(dists);
+    free(dists_i);
+  }
+}
+
+/* query_ball_point_kernel (ball_query_gpu.cu:13-48); idx is zero-initialised (ball_query.cpp). */
+void oracle_ball_query(const float* xyz, const float* new_xyz, int64_t B, int64_t n, int64_t m, float radius,
+                       int64_t nsample, int64_t* idx) {
+  const float radius2 = radius * radius;
+#pragma omp parallel for schedule(dynamic)
+  for (int64_t b = 0; b < B; ++b) {
+    const float* p = xyz + b * n * 3;
+    for (int64_t j = 0; j < m; ++j) {
+      const float* c = new_xyz + (b * m + j) * 3;
+      int64_t* out = idx + (b * m + j) * nsample;
+      for (int64_t l = 0; l < nsample; ++l) out[l] = 0;
+      int64_t cnt = 0;
+      for (int64_t k = 0; k < n && cnt < nsample; ++k) {
+        const float d2 = sqdist_fused(c[0], c[1], c[2], p[k * 3], p[k * 3 + 1], p[k * 3 + 2]);
+        if (d2 < radius2) {
+          if (cnt == 0)
+            for (int64_t l = 0; l < nsample; ++l) out[l] = k;
+          out[cnt] = k;
+          ++cnt;
+        }
+      }
+    }
+  }
+}
+
 int oracle_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

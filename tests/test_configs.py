@@ -93,9 +93,29 @@ def test_unsupported_models_raise():
     with pytest.raises(NotImplementedError):
         build_model(cfg)
     cfg.model.name = 'pn_transformer'
-    cfg.model.encoder = 'pointnet2_ssg'
+    cfg.model.encoder = 'pointnet3'
     with pytest.raises(NotImplementedError):
         build_model(cfg)
+
+
+def test_pointnet2_encoders_build():
+    """Encoder registry values 'pointnet2_ssg' / 'pointnet2_msg' (reference encoder/__init__.py:
+    11-19) with the reference's state-dict layout (nn.Sequential of conv / bn / relu per scale)."""
+    from multi_part_assembly_b200.models import build_encoder
+    ssg = build_encoder('pointnet2_ssg', 256)
+    sd = ssg.state_dict()
+    assert tuple(sd['SA_modules.0.mlps.0.0.weight'].shape) == (64, 3, 1, 1)
+    assert tuple(sd['SA_modules.1.mlps.0.6.weight'].shape) == (256, 128, 1, 1)
+    assert tuple(sd['SA_modules.2.mlps.0.6.weight'].shape) == (256, 512, 1, 1)
+    assert 'SA_modules.0.mlps.0.1.running_mean' in sd and 'SA_modules.0.mlps.0.0.bias' not in sd
+    msg = build_encoder('pointnet2_msg', 128)
+    sd = msg.state_dict()
+    assert tuple(sd['SA_modules.0.mlps.2.3.weight'].shape) == (96, 64, 1, 1)
+    assert tuple(sd['SA_modules.1.mlps.1.0.weight'].shape) == (128, 64 + 128 + 128 + 3, 1, 1)
+    assert tuple(sd['SA_modules.2.mlps.0.0.weight'].shape) == (256, 128 + 256 + 256 + 3, 1, 1)
+    cfg = get_cfg('pn_transformer')
+    cfg.model.encoder = 'pointnet2_ssg'
+    assert build_model(cfg) is not None
 
 
 def test_cfgnode_semantics():
