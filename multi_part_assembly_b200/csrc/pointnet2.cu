@@ -21,19 +21,22 @@ namespace mpa {
 // to the last pick lowers its running minimum (initially 1e10, sampling.cpp:75) and the point
 // with the LARGEST minimum is picked; points with |p|^2 <= 1e-3 are skipped (:100-101) --
 // they are never updated nor picked.  Ties: the reference reduces per-thread strided maxima
-// (first maximum of the stride) with a tree that keeps the lower thread on equality, i.e. it
-// picks the smallest (k mod block, k) among the tied points, block = the reference's block size
-// (largest power of two <= n, capped at 512, cuda_utils.h:15-19).  The same order is encoded
-// in the low bits of the reduction key here, so the result does not depend on THIS kernel's
-// thread count.
+// (first maximum of the stride, thread t = k mod block, block = largest power of two <= n
+// capped at 512, cuda_utils.h:15-19) with a shared-memory tree that folds slot t + s onto
+// slot t and keeps slot t on equality (__update, :64-71): two tied slots meet at the stage of
+// their lowest differing bit and the one with a 0 there survives -- the smaller BIT-REVERSED
+// thread index wins, then the smaller k.  That order is encoded in the low bits of the
+// reduction key here, so the result does not depend on THIS kernel's thread count.
 constexpr int FPS_THREADS = 256;
-__device__ __forceinline__ unsigned long long fps_key(float d, int k, int ref_block) {
-  // d >= 0: float bits are order preserving; larger key wins: larger d, then smaller (k % block, k)
-  const unsigned tie = ((unsigned)(k % ref_block) << 16) | (unsigned)k;
+__device__ __forceinline__ unsigned long long fps_key(float d, int k, int ref_bits) {
+  // d >= 0: float bits are order preserving; larger key wins: larger d, then smaller
+  // (bit-reversed k mod block, k)
+  const unsigned t = (unsigned)k & ((1u << ref_bits) - 1u);
+  const unsigned tie = ((ref_bits ? (__brev(t) >> (32 - ref_bits)) : 0u) << 16) | (unsigned)k;
   return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(~tie);
 }
 __global__ void __launch_bounds__(FPS_THREADS)
-fps_kernel(const float* __restrict__ xyz, int n, int m, int ref_block, int* __restrict__ idxs,
+fps_kernel(const float* __restrict__ xyz, int n, int m, int ref_bits, int* __restrict__ idxs,
            float* __restrict__ new_xyz) {
   extern __shared__ float sm[];  // x[n] y[n] z[n] temp[n]
   float* sx = sm;
@@ -64,7 +67,7 @@ fps_kernel(const float* __restrict__ xyz, int n, int m, int ref_block, int* __re
       const float d = sqdist_ref(x2, y2, z2, x1, y1, z1);
       const float d2 = fminf(d, st[k]);
       st[k] = d2;
-      const unsigned long long key = fps_key(d2, k, ref_block);
+      const unsigned long long key = fps_key(d2, k, ref_bits);
       best = key > best ? key : best;
     }
 #pragma unroll
@@ -170,8 +173,8 @@ int mpa_furthest_point_sample(const float* xyz, int B, int n, int m, int32_t* id
   MPA_CHECK_ARG(B >= 0 && n > 0 && m > 0 && n <= 65535, "furthest_point_sample: bad sizes B=%d n=%d m=%d", B, n, m);
   if (B == 0) return MPA_OK;
   MPA_CHECK_ARG(xyz && idx, "furthest_point_sample: null pointer");
-  int ref_block = 1;
-  while (ref_block * 2 <= n && ref_block < 512) ref_block *= 2;  // opt_n_threads(n), cuda_utils.h:15-19
+  int ref_bits = 0;
+  while ((2 << ref_bits) <= n && ref_bits < 9) ++ref_bits;  // block = 1 << ref_bits = opt_n_threads(n), cuda_utils.h:15-19
   const size_t smem = sizeof(float) * 4 * (size_t)n;
   MPA_CHECK_ARG(smem <= 200 * 1024, "furthest_point_sample: clouds of at most %d points", 200 * 1024 / 16);
   static DeviceOnce attr;
@@ -181,7 +184,7 @@ int mpa_furthest_point_sample(const float* xyz, int B, int n, int m, int32_t* id
   }
   {
     ProfScope ps("pointnet2_fps", stream);
-    fps_kernel<<<B, FPS_THREADS, smem, stream>>>(xyz, n, m, ref_block, idx, new_xyz);
+    fps_kernel<<<B, FPS_THREADS, smem, stream>>>(xyz, n, m, ref_bits, idx, new_xyz);
   }
   MPA_LAUNCH_CHECK();
   return MPA_OK;
