@@ -13,9 +13,15 @@ h = rows[0]
 col = {n: i for i, n in enumerate(h)}
 
 
+units = rows[1]
+SCALE = {'nsecond': 1e-3, 'usecond': 1.0, 'msecond': 1e3, 'second': 1e6,   # -> microseconds
+         'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 's': 1e6,
+         'byte': 1e-6, 'Kbyte': 1e-3, 'Mbyte': 1.0, 'Gbyte': 1e3}            # -> megabytes
+
+
 def f(r, name, default=0.0):
     try:
-        return float(r[col[name]].replace(',', ''))
+        return float(r[col[name]].replace(',', '')) * SCALE.get(units[col[name]], 1.0)
     except (KeyError, ValueError):
         return default
 
