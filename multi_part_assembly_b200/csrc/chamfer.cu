@@ -174,11 +174,19 @@ __device__ __forceinline__ int cell_coord(float x, float o, float inv_h, int dim
 }
 
 // load + (optionally) pose-transform point i of segment seg; reports validity
-__device__ __forceinline__ float3 load_point(const CloudDesc& c, int seg, int i, bool& valid) {
+// (`cached`: the transformed point was already written to c.out_pts by pass 1 -- passes 2 and 3
+// re-read 12 bytes instead of repeating the quaternion product)
+__device__ __forceinline__ float3 load_point(const CloudDesc& c, int seg, int i, bool& valid,
+                                             bool cached = false) {
   const long long g = (long long)seg * c.Nseg + i;
-  const long long part = g / c.ppp;
+  // Nseg is a multiple of ppp (whole parts per segment): 32-bit division
+  const long long part = (long long)seg * (c.Nseg / c.ppp) + (unsigned)i / (unsigned)c.ppp;
   valid = (c.valids == nullptr) || (c.valids[part] != 0.0f);
   float3 v;
+  if (cached && c.out_pts != nullptr) {
+    const float* p = c.out_pts + g * 3;
+    return make_float3(p[0], p[1], p[2]);
+  }
   if (!valid && c.fill_invalid) {
     v = make_float3(1e3f, 1e3f, 1e3f);
   } else {
@@ -344,7 +352,7 @@ __global__ void grid_build_kernel(CloudDesc c0, CloudDesc c1, int S, float4* __r
   // ---- pass 2: histogram ----
   for (int i = tid; i < n; i += blockDim.x) {
     bool valid;
-    const float3 v = load_point(c, seg, i, valid);
+    const float3 v = load_point(c, seg, i, valid, true);
     if (valid) {
       const int cell = (cell_coord(v.z, g.oz, g.inv_h, g.dz) * g.dy +
                         cell_coord(v.y, g.oy, g.inv_h, g.dy)) * g.dx +
@@ -394,7 +402,7 @@ __global__ void grid_build_kernel(CloudDesc c0, CloudDesc c1, int S, float4* __r
   // ---- pass 3: scatter (cnt[] doubles as the per-cell cursor) ----
   for (int i = tid; i < n; i += blockDim.x) {
     bool valid;
-    const float3 v = load_point(c, seg, i, valid);
+    const float3 v = load_point(c, seg, i, valid, true);
     if (valid) {
       const int cell = (cell_coord(v.z, g.oz, g.inv_h, g.dz) * g.dy +
                         cell_coord(v.y, g.oy, g.inv_h, g.dy)) * g.dx +
