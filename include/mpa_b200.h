@@ -359,11 +359,12 @@ int mpa_ball_query(const float* xyz, const float* new_xyz, int B, int n, int m, 
  * [B,n,C] (nullable when C == 0); columns >= 3 + C are zero padding. */
 int mpa_group_rows(const float* xyz, const float* new_xyz, const float* feats, const int32_t* idx,
                    int B, int n, int m, int nsample, int C, int ld, float* out, void* stream);
-/* fp64 (sum, sum of squares) per column of y [n_blocks*R, F]: BatchNorm2d batch statistics of a
- * shared-MLP layer (pointnet2_modules.py:10-22). */
+/* fp64 (sum, sum of squares) per column of y [n_blocks*R, F]: BatchNorm batch statistics of a
+ * shared-MLP layer (pointnet2_modules.py:10-22; encoder/pointnet.py:29-41 in fp32 mode);
+ * valids [n_blocks] (nullable): blocks (parts) flagged 0 stay out of the sums. */
 size_t mpa_column_stats_workspace_bytes(int n_blocks, int F);
-int mpa_column_stats(const float* y, int n_blocks, int R, int F, double* sums, void* ws,
-                     size_t ws_bytes, void* stream);
+int mpa_column_stats(const float* y, const float* valids, int n_blocks, int R, int F, double* sums,
+                     void* ws, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

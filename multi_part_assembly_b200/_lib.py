@@ -83,7 +83,7 @@ _SIGNATURES = {
                                c_void_p]),
     'mpa_group_rows': (c_int, [c_void_p] * 4 + [c_int] * 6 + [c_void_p, c_void_p]),
     'mpa_column_stats_workspace_bytes': (c_size_t, [c_int] * 2),
-    'mpa_column_stats': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'mpa_column_stats': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     'mpa_pose_chamfer_backward_workspace_bytes': (c_size_t, [c_int] * 3),
     'mpa_pose_chamfer_backward': (c_int, [c_void_p] * 10 + [c_int] * 4 +
                                   [c_void_p] * 5 + [c_size_t, c_void_p]),

@@ -786,11 +786,12 @@ int mpa_bn_pool(const float* y, const float* valids, int n, int N, int F, const 
 
 
 /* (sum, sum of squares) per column of y [n_blocks * R, F] in fp64, deterministic: the BatchNorm
- * batch statistics of a shared-MLP layer (PointNet++ set abstraction). */
+ * batch statistics of a shared-MLP layer (PointNet++ set abstraction, fp32-mode PointNet);
+ * valids [n_blocks] (nullable): blocks flagged 0 stay out of the sums. */
 size_t mpa_column_stats_workspace_bytes(int n_blocks, int F) { return mpa_bn_pool_workspace_bytes(n_blocks, F); }
 
-int mpa_column_stats(const float* y, int n_blocks, int R, int F, double* sums, void* ws, size_t ws_bytes,
-                     void* stream_) {
+int mpa_column_stats(const float* y, const float* valids, int n_blocks, int R, int F, double* sums, void* ws,
+                     size_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   MPA_CHECK_ARG(n_blocks >= 0 && R > 0 && F > 0 && F <= 4096, "column_stats: bad sizes");
   if (n_blocks == 0) return MPA_OK;
@@ -805,7 +806,7 @@ int mpa_column_stats(const float* y, int n_blocks, int R, int F, double* sums, v
   const int threads = F >= 256 ? 256 : ((F + 31) / 32 * 32);
   {
     ProfScope ps("column_stats", stream);
-    part_channel_stats_kernel<<<n_blocks, threads, 0, stream>>>(y, nullptr, R, F, partial, mm);
+    part_channel_stats_kernel<<<n_blocks, threads, 0, stream>>>(y, valids, R, F, partial, mm);
     column_sum_stage1_kernel<<<dim3(F, CS_SLICES), 32, 0, stream>>>(partial, n_blocks, F, slices);
     column_sum_stage2_kernel<<<(F + 127) / 128, 128, 0, stream>>>(slices, F, sums);
   }

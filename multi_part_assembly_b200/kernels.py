@@ -217,6 +217,78 @@ class _PointNetFunction(torch.autograd.Function):
         return (None, None, None, None) + tuple(grads)
 
 
+def _pointnet_fp32_native(x, convs, bns, training, global_feat, valids):
+    """PointNet.forward in fp32 mode on the generic native kernels: every 1x1 convolution is a
+    tensor-core GEMM over the [n*N, C] point rows in the fp32-accurate three-plane mode,
+    BatchNorm1d statistics come from the deterministic column-sum pass, BatchNorm + ReLU is one
+    streaming kernel, the last layer goes straight into the BatchNorm + max-pool pass.  Padded
+    parts (`valids`) stay out of every statistic and get zero features."""
+    n, N, _ = x.shape
+    h = F.pad(x.reshape(n * N, 3).float(), (0, 5)).contiguous()  # K = 8 for the GEMM
+    v = None if valids is None else valids.float().contiguous()
+    for i, (conv, bn) in enumerate(zip(convs, bns)):
+        W = conv.weight.detach().reshape(conv.weight.shape[0], -1).float()
+        if W.shape[1] < h.shape[1]:
+            W = F.pad(W, (0, h.shape[1] - W.shape[1]))
+        y = linear(h, W, precision=PRECISION_FP32)
+        if i < 4:
+            sums = _column_sums(y, n, N, v) if training else None
+            h = _bn_relu_rows(y, sums, n, N, bn, training, v)
+        elif global_feat:
+            out = _bn_pool(y, v, n, N, bn, training, slope=1.0)[:, :y.shape[1]].contiguous()
+        else:  # per-point features: BatchNorm only (slope 1 = identity activation)
+            sums = _column_sums(y, n, N, v) if training else None
+            dev = y.device
+            out = torch.empty_like(y)
+            with torch.cuda.device(dev):
+                rc = _lib.lib().mpa_edgeconv_finish(
+                    _lib.ptr(y), _lib.ptr(y), _lib.ptr(sums), _lib.ptr(v), n, N, y.shape[1], 1,
+                    _lib.ptr(bn.weight.detach()), _lib.ptr(bn.bias.detach()), _lib.ptr(bn.running_mean),
+                    _lib.ptr(bn.running_var), 1 if training else 0, float(bn.momentum), float(bn.eps),
+                    1.0, _lib.ptr(out), None, 0, 0, _lib.cuda_stream(dev))
+            _lib.check(rc, 'mpa_edgeconv_finish')
+            out = out.view(n, N, -1)
+            if v is not None:
+                out = out * v.view(n, 1, 1)
+    if training:
+        torch._foreach_add_([b.num_batches_tracked for b in bns], 1)
+    return out
+
+
+class _PointNetFp32Function(torch.autograd.Function):
+    """Forward: `_pointnet_fp32_native`.  Backward: autograd through the stock layers
+    (BatchNorm buffers restored so the running statistics advance only once)."""
+
+    @staticmethod
+    def forward(ctx, x, valids, training, global_feat, modules, *params):
+        convs, bns = modules
+        out = _pointnet_fp32_native(x, convs, bns, training, global_feat, valids)
+        ctx.save_for_backward(x, valids if valids is not None else x.new_empty(0))
+        ctx.modules, ctx.training, ctx.global_feat = modules, training, global_feat
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        x, valids = ctx.saved_tensors
+        convs, bns = ctx.modules
+        params = [c.weight for c in convs] + [b.weight for b in bns] + [b.bias for b in bns]
+        prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            with torch.enable_grad():
+                if valids.numel():
+                    idx = (valids != 0).nonzero(as_tuple=True)[0]
+                    xin, g = x.index_select(0, idx), grad.index_select(0, idx)
+                else:
+                    xin, g = x, grad
+                out = _pointnet_torch(xin, convs, bns, ctx.training, ctx.global_feat, track=False)
+                grads = torch.autograd.grad(out, params, g, allow_unused=True)
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+        return (None, None, None, None, None) + tuple(grads)
+
+
 def pointnet_forward(x, convs, bns, training, global_feat=True, valids=None):
     """x [n, N, 3] -> [n, F] (max over points) or [n, N, F].  `valids` [n]
     (optional): parts with 0 are skipped -- zero features, no BatchNorm
@@ -229,20 +301,13 @@ def pointnet_forward(x, convs, bns, training, global_feat=True, valids=None):
             return _PointNetFunction.apply(
                 x.float().contiguous(), None if valids is None else valids.float().contiguous(),
                 training, (convs, bns), *params)
-    # fp32 path: stock torch ops in true fp32 (TF32 off so that it matches the CPU oracle)
-    prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cuda.matmul.allow_tf32 = False
-    try:
-        with torch.autocast('cuda', enabled=False):
-            if valids is not None:
-                idx = (valids != 0).nonzero(as_tuple=True)[0]
-                out = _pointnet_torch(x.float().index_select(0, idx), convs, bns, training, global_feat)
-                full = out.new_zeros((x.shape[0], ) + out.shape[1:])
-                return full.index_copy(0, idx, out)
-            return _pointnet_torch(x.float(), convs, bns, training, global_feat)
-    finally:
-        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+    # fp32 mode (the reference default): the generic native kernels in the fp32-accurate
+    # tensor-core mode
+    params = [c.weight for c in convs] + [b.weight for b in bns] + [b.bias for b in bns]
+    with torch.autocast('cuda', enabled=False):
+        return _PointNetFp32Function.apply(
+            x.float().contiguous(), None if valids is None else valids.float().contiguous(),
+            training, global_feat, (convs, bns), *params)
 
 
 # ---------------------------------------------------------------------------
@@ -569,7 +634,7 @@ def _group_rows(xyz, new_xyz, feats, idx, ld):
     return out
 
 
-def _column_sums(y, n_blocks, R):
+def _column_sums(y, n_blocks, R, valids=None):
     dev = y.device
     Fd = y.shape[1]
     sums = torch.empty(Fd, 2, dtype=torch.float64, device=dev)
@@ -577,20 +642,20 @@ def _column_sums(y, n_blocks, R):
     ws_bytes = L.mpa_column_stats_workspace_bytes(n_blocks, Fd)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        rc = L.mpa_column_stats(_lib.ptr(y), n_blocks, R, Fd, _lib.ptr(sums), _lib.ptr(ws), ws_bytes,
-                                _lib.cuda_stream(dev))
+        rc = L.mpa_column_stats(_lib.ptr(y), _lib.ptr(valids), n_blocks, R, Fd, _lib.ptr(sums), _lib.ptr(ws),
+                                ws_bytes, _lib.cuda_stream(dev))
     _lib.check(rc, 'mpa_column_stats')
     return sums
 
 
-def _bn_relu_rows(y, sums, n_blocks, R, bn, training):
-    """BatchNorm2d + ReLU on the rows of a shared-MLP layer (statistics over all rows)."""
+def _bn_relu_rows(y, sums, n_blocks, R, bn, training, valids=None):
+    """BatchNorm + ReLU on the rows of a shared-MLP layer (statistics over all valid rows)."""
     dev = y.device
     Fd = y.shape[1]
     out = torch.empty_like(y)
     with torch.cuda.device(dev):
         rc = _lib.lib().mpa_edgeconv_finish(
-            _lib.ptr(y), _lib.ptr(y), _lib.ptr(sums), None, n_blocks, R, Fd, 1,
+            _lib.ptr(y), _lib.ptr(y), _lib.ptr(sums), _lib.ptr(valids), n_blocks, R, Fd, 1,
             _lib.ptr(bn.weight.detach()), _lib.ptr(bn.bias.detach()), _lib.ptr(bn.running_mean),
             _lib.ptr(bn.running_var), 1 if training else 0, float(bn.momentum), float(bn.eps), 0.0,
             _lib.ptr(out), None, 0, 0, _lib.cuda_stream(dev))
