@@ -218,7 +218,7 @@ int mpa_pool_argmax(const void* z, const float* scale, int n_parts, int N, int C
 /* Y = act(X W^T + bias) (+ residual): X [M,K], W [N,K] (an nn.Linear weight),
  * bias [N] or NULL, residual [M,N] or NULL, out [M,N]; fp32 in memory, bf16
  * tensor-core operands with fp32 accumulation.  act: 0 none, 1 ReLU,
- * 2 LeakyReLU(0.2).  K must be a multiple of 8.  Replaces the cuBLAS GEMMs of
+ * 2 LeakyReLU(0.2), 3 sigmoid.  K must be a multiple of 8.  Replaces the cuBLAS GEMMs of
  * PoseRegressor (models/modules/regressor.py:45-68). */
 #define MPA_PRECISION_BF16 0 /* bf16 operands, fp32 accumulation */
 #define MPA_PRECISION_FP32 1 /* fp32-accurate: 3 bf16 planes per operand, 6 tensor-core products per k-step */

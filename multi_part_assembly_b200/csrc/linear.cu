@@ -36,7 +36,7 @@ __host__ __device__ constexpr int ln_smem_bytes(int bn, int split = 1) {
   return ln_stages(bn, split) * ln_stage_bytes(bn, split) + 1024;
 }
 
-enum { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY02 = 2 };
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY02 = 2, ACT_SIGMOID = 3 };
 
 // Inverted dropout (torch semantics: keep with probability 1 - p, scale kept values by
 // 1 / (1 - p)) drawn from a counter-based generator: Philox4x32-10 keyed by `rng[0]` (seed) with
@@ -119,6 +119,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == ACT_RELU) return fmaxf(x, 0.f);
   if (act == ACT_LEAKY02) return x > 0.f ? x : 0.2f * x;
+  if (act == ACT_SIGMOID) return 1.0f / (1.0f + expf(-x));
   return x;
 }
 
@@ -1122,7 +1123,7 @@ int mpa_linear_forward_ex(const float* x, const float* w, const float* bias, con
                           void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   MPA_CHECK_ARG(M >= 0 && N > 0 && K > 0, "linear_forward: bad sizes %d %d %d", M, N, K);
-  MPA_CHECK_ARG(act >= ACT_NONE && act <= ACT_LEAKY02, "linear_forward: bad activation %d", act);
+  MPA_CHECK_ARG(act >= ACT_NONE && act <= ACT_SIGMOID, "linear_forward: bad activation %d", act);
   MPA_CHECK_ARG(precision == MPA_PRECISION_BF16 || precision == MPA_PRECISION_FP32,
                 "linear_forward: bad precision %d", precision);
   if (M == 0) return MPA_OK;

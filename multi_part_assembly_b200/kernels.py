@@ -587,6 +587,47 @@ def dgcnn_forward(x, m, training, k=20, valids=None):
 
 
 # ---------------------------------------------------------------------------
+# row-wise MLPs of the DGL model (no-grad passes)
+# ---------------------------------------------------------------------------
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID = 0, 1, 2, 3
+
+
+def _precision():
+    return PRECISION_BF16 if _use_bf16() else PRECISION_FP32
+
+
+def linear_chain(x, layers):
+    """x [..., K] through `layers` = [(nn.Linear, act), ...] on the tensor-core GEMM
+    (bias and activation in its epilogue); no autograd."""
+    shape = x.shape[:-1]
+    h = x.reshape(-1, x.shape[-1])
+    precision = _precision()
+    with torch.autocast('cuda', enabled=False):
+        for lin, act in layers:
+            h = linear(h, lin.weight.detach().float(), lin.bias.detach().float(), act=act,
+                       precision=precision)
+    return h.view(*shape, -1)
+
+
+def conv_bn_relu_rows(x, stages, training):
+    """x [M, P, K] -> [M, P, C]: a chain of 1x1 Conv1d (with bias) + BatchNorm1d + ReLU over the
+    rows (reference models/dgl/modules.py:7-33: statistics over all M*P rows, padding included):
+    GEMM with the bias in its epilogue, deterministic column sums, one BatchNorm + ReLU pass."""
+    M, P, _ = x.shape
+    h = x.reshape(M * P, -1).float().contiguous()
+    precision = _precision()
+    with torch.autocast('cuda', enabled=False):
+        for conv, bn in stages:
+            W = conv.weight.detach().reshape(conv.weight.shape[0], -1).float()
+            y = linear(h, W, conv.bias.detach().float(), precision=precision)
+            sums = _column_sums(y, M, P) if training else None
+            h = _bn_relu_rows(y, sums, M, P, bn, training)
+            if training:
+                bn.num_batches_tracked += 1
+    return h.view(M, P, -1)
+
+
+# ---------------------------------------------------------------------------
 # PointNet++ (set abstraction)
 # ---------------------------------------------------------------------------
 def furthest_point_sample(xyz, npoint):

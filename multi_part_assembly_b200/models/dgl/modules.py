@@ -1,6 +1,15 @@
-"""MLPs of the dynamic-graph-learning model (reference models/dgl/modules.py)."""
+"""MLPs of the dynamic-graph-learning model (reference models/dgl/modules.py).  The modules
+hold the reference's parameters; without autograd (evaluation, benchmarking, CUDA-graph replay)
+their forward runs on the tensor-core GEMM + BatchNorm kernels of `kernels`, with autograd on
+the stock layers."""
 import torch
 import torch.nn as nn
+
+from ... import kernels
+
+
+def _native(x):
+    return x.is_cuda and not torch.is_grad_enabled()
 
 
 class _PointwiseMLP3(nn.Module):
@@ -17,6 +26,9 @@ class _PointwiseMLP3(nn.Module):
         self.bn3 = nn.BatchNorm1d(feat_len)
 
     def forward(self, x):
+        if _native(x):
+            return kernels.conv_bn_relu_rows(
+                x, ((self.conv1, self.bn1), (self.conv2, self.bn2), (self.conv3, self.bn3)), self.training)
         x = x.permute(0, 2, 1)
         x = torch.relu(self.bn1(self.conv1(x)))
         x = torch.relu(self.bn2(self.conv2(x)))
@@ -42,6 +54,9 @@ class RelationNet(nn.Module):
         self.mlp3 = nn.Linear(512, 1)
 
     def forward(self, x):
+        if _native(x):
+            return kernels.linear_chain(x, ((self.mlp1, kernels.ACT_RELU), (self.mlp2, kernels.ACT_RELU),
+                                            (self.mlp3, kernels.ACT_SIGMOID)))
         x = torch.relu(self.mlp1(x))
         x = torch.relu(self.mlp2(x))
         return torch.sigmoid(self.mlp3(x))
@@ -56,4 +71,6 @@ class PoseEncoder(nn.Module):
         self.mlp2 = nn.Linear(256, 128)
 
     def forward(self, x):
+        if _native(x):
+            return kernels.linear_chain(x, ((self.mlp1, kernels.ACT_RELU), (self.mlp2, kernels.ACT_RELU)))
         return torch.relu(self.mlp2(torch.relu(self.mlp1(x))))
