@@ -987,6 +987,256 @@ int launch_ffn_block(const __nv_bfloat16* att, const __nv_bfloat16* wo, const __
   return MPA_OK;
 }
 
+// ======================================================================================
+// Fused first half of a pre-LN encoder layer for d_model = 256, head dim 32 (bf16 operands):
+//     qkv <- LayerNorm1(x) W_in^T + b_in ;  att <- softmax(q k^T / sqrt(32) + key mask) v
+// One CTA owns the tokens of SPT = 128 / P whole shapes (attention never leaves a shape) and
+// AT_HPC of the 8 heads.  Per head the three 32-row slices of W_in (q, k, v rows of that head)
+// are stacked by TMA into one [96 x 256] B operand, so ONE tcgen05 GEMM (M=128, N=96) produces
+// the head's q | k | v in TMEM; the MMA of head h+1 overlaps the attention of head h (two TMEM
+// slots, two weight stages).  The 8 epilogue warps then run the attention on CUDA cores (S=20
+// tokens: a 20x20x32 problem per (shape, head)): k and v rows go to shared
+// memory, each thread of a row pair scores half of the keys, the full score row is exchanged
+// through shared memory, softmax in registers, and each thread accumulates half of the head's
+// 32 output channels.  Replaces the QKV GEMM launch + the attention launch of every layer
+// (nn.MultiheadAttention inside nn.TransformerEncoderLayer, transformer.py:23-34).
+constexpr int AT_HD = 32;                     // head dim
+constexpr int AT_NB = 3 * AT_HD;              // 96 accumulator columns per head: q | k | v
+constexpr int AT_WSTAGE = 4 * AT_NB * 128;    // one head's stacked weight slices: 4 k-blocks of [96 x 64] bf16 = 48 KB
+constexpr int AT_SMEM = 4 * FB_KTILE + 2 * AT_WSTAGE + 2 * LN_BM * AT_HD * 4 + 1024;
+
+struct AttnArgs {
+  const float* b_in;            // [768]
+  const unsigned char* valid;   // [B*P] key-padding mask (1 = valid) or nullptr
+  __nv_bfloat16* att;           // [T, 256] out
+  int B, P, SPT, heads_per_cta;
+  DropoutSpec drop;             // on the attention probabilities; mask [B, 8, P, P]
+};
+
+template <int PT>  // compile-time bound of tokens per shape (P <= PT): score rows live in registers
+__global__ void __launch_bounds__(LN_THREADS, 1)
+encoder_attn_kernel(const __grid_constant__ CUtensorMap map_xn, const __grid_constant__ CUtensorMap map_win,
+                    AttnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* A = smem;                        // LayerNorm1(x) tile, 4 k-blocks
+  uint8_t* wring = smem + 4 * FB_KTILE;     // 2 weight stages
+  __shared__ uint64_t a_full, w_full[2], w_empty[2], acc_full[2], acc_free[2];
+  __shared__ uint32_t tmem_base_s;
+  float (*ks)[AT_HD] = reinterpret_cast<float (*)[AT_HD]>(wring + 2 * AT_WSTAGE);  // k rows of the head, 16 KB
+  float (*vs)[AT_HD] = ks + LN_BM;                                                  // v rows, 16 KB
+  __shared__ float sc[LN_BM][PT + 1];                // score exchange
+  __shared__ float s_bias[3 * 256];
+  __shared__ unsigned char s_valid[LN_BM];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int P = a.P, H = 8;
+  const int shape0 = blockIdx.x * a.SPT;
+  const int nshapes = min(a.SPT, a.B - shape0);
+  const int row0 = shape0 * P;              // first global token row of this tile
+  const int nrows = nshapes * P;
+  const int h_begin = blockIdx.y * a.heads_per_cta;
+  const int nh = a.heads_per_cta;
+
+  if (threadIdx.x == 0) {
+    tc::mbar_init(&a_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&w_full[i], 1);
+      tc::mbar_init(&w_empty[i], 1);
+      tc::mbar_init(&acc_full[i], 1);
+      tc::mbar_init(&acc_free[i], FB_EPI);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc<256>(&tmem_base_s);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer =====
+      mbar_expect_tx(&a_full, 4 * FB_KTILE);
+      for (int kb = 0; kb < 4; ++kb) tma_load_2d(A + kb * FB_KTILE, &map_xn, kb * LN_BK, row0, &a_full);
+      for (int hh = 0; hh < nh; ++hh) {
+        const int s = hh & 1, h = h_begin + hh;
+        if (hh >= 2) tc::mbar_wait(&w_empty[s], ((hh >> 1) - 1) & 1);
+        uint8_t* dst = wring + s * AT_WSTAGE;
+        mbar_expect_tx(&w_full[s], AT_WSTAGE);
+        for (int kb = 0; kb < 4; ++kb)
+          for (int part = 0; part < 3; ++part)  // q, k, v rows of head h -> rows 32 part .. of the stacked tile
+            tma_load_2d(dst + kb * (AT_NB * 128) + part * (AT_HD * 128), &map_win, kb * LN_BK,
+                        part * 256 + h * AT_HD, &w_full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      constexpr uint32_t IDESC = tc::make_idesc_bf16(LN_BM, AT_NB);
+      tc::mbar_wait(&a_full, 0);
+      tc::fence_after_sync();
+      for (int hh = 0; hh < nh; ++hh) {
+        const int s = hh & 1;
+        tc::mbar_wait(&w_full[s], (hh >> 1) & 1);
+        if (hh >= 2) tc::mbar_wait(&acc_free[s], ((hh >> 1) - 1) & 1);
+        tc::fence_after_sync();
+        const uint32_t acc = tmem + (uint32_t)(s * 128);
+        const uint32_t b_base = tc::smem_u32(wring + s * AT_WSTAGE);
+        for (int kb = 0; kb < 4; ++kb) {
+          const uint32_t a_addr = tc::smem_u32(A + kb * FB_KTILE), b_addr = b_base + kb * (AT_NB * 128);
+#pragma unroll
+          for (int k = 0; k < LN_BK; k += 16)
+            tc::mma_bf16(acc, tc::make_desc_sw128(a_addr + k * 2), tc::make_desc_sw128(b_addr + k * 2), IDESC,
+                         (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        tc::mma_commit(&w_empty[s]);
+        tc::mma_commit(&acc_full[s]);
+      }
+    }
+  } else {  // ===== epilogue + attention: warps 2..9 =====
+    const int q4 = warp & 3, half = (warp - 2) >> 2;
+    const int r = q4 * 32 + lane;            // row in the tile = TMEM lane
+    const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
+    for (int c = threadIdx.x - 64; c < 3 * 256; c += FB_EPI) s_bias[c] = __ldg(a.b_in + c);
+    for (int c = threadIdx.x - 64; c < LN_BM; c += FB_EPI)
+      s_valid[c] = (c < nrows && (a.valid == nullptr || a.valid[row0 + c] != 0)) ? 1 : 0;
+    tc::group_sync(1, FB_EPI);
+    const bool live = r < nrows;
+    const int sh = live ? r / P : 0, tok = r - sh * P;  // local shape, token
+    const int kbase = sh * P;                             // first key row of this row's shape
+    const float scale = rsqrtf((float)AT_HD);
+    const int j_lo = half * (PT / 2), j_hi = half ? PT : PT / 2;  // this thread's share of the keys
+
+    for (int hh = 0; hh < nh; ++hh) {
+      const int s = hh & 1, h = h_begin + hh;
+      tc::mbar_wait(&acc_full[s], (hh >> 1) & 1);
+      tc::fence_after_sync();
+      const uint32_t acc = tmem + (uint32_t)(s * 128) + lane_off;
+      float q[AT_HD], kv[AT_HD];
+      tc::tmem_ld32(acc, q);
+      tc::tmem_ld32(acc + (uint32_t)(half ? 64 : 32), kv);  // half 0: k row, half 1: v row
+      tc::tmem_ld_wait();
+      tc::fence_before_sync();
+      mbar_arrive(&acc_free[s]);
+      {
+        const float* bq = s_bias + h * AT_HD;
+        const float* bkv = s_bias + (half ? 512 : 256) + h * AT_HD;
+        float* dst = half ? vs[r] : ks[r];
+#pragma unroll
+        for (int c = 0; c < AT_HD; ++c) { q[c] += bq[c]; kv[c] += bkv[c]; }
+#pragma unroll
+        for (int c = 0; c < AT_HD; c += 4)
+          *reinterpret_cast<float4*>(dst + c) = make_float4(kv[c], kv[c + 1], kv[c + 2], kv[c + 3]);
+      }
+      tc::group_sync(1, FB_EPI);  // k, v of every row are in shared memory
+      // scores of this thread's keys
+#pragma unroll
+      for (int j = j_lo; j < j_hi; ++j) {
+        float d = -3.0e38f;
+        if (j < P && live && s_valid[kbase + j]) {
+          const float4* kr = reinterpret_cast<const float4*>(ks[kbase + j]);
+          float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+          for (int c4 = 0; c4 < AT_HD / 4; ++c4) {
+            const float4 kk = kr[c4];
+            d0 = fmaf(q[4 * c4], kk.x, d0); d1 = fmaf(q[4 * c4 + 1], kk.y, d1);
+            d0 = fmaf(q[4 * c4 + 2], kk.z, d0); d1 = fmaf(q[4 * c4 + 3], kk.w, d1);
+          }
+          d = (d0 + d1) * scale;
+        }
+        sc[r][j] = d;
+      }
+      tc::group_sync(1, FB_EPI);  // the full score row is in shared memory
+      float p[PT];
+      float mx = -3.0e38f;
+#pragma unroll
+      for (int j = 0; j < PT; ++j) { p[j] = sc[r][j]; mx = fmaxf(mx, p[j]); }
+      float den = 0.f;
+#pragma unroll
+      for (int j = 0; j < PT; ++j) { p[j] = p[j] > -1.0e38f ? __expf(p[j] - mx) : 0.f; den += p[j]; }
+      const float inv = den > 0.f ? 1.0f / den : 0.f;  // a shape without a valid key cannot occur; guard anyway
+      if (a.drop.rng != nullptr && live) {  // dropout on the attention probabilities
+        const unsigned rowid = (unsigned)(((shape0 + sh) * H + h) * P + tok);
+        const float keep_scale = 1.0f / (1.0f - a.drop.p);
+#pragma unroll
+        for (int jq = 0; jq < PT; jq += 4) {
+          const uint4 k4 = dropout_quad(a.drop.rng, a.drop.site, rowid, (unsigned)(jq >> 2), a.drop.p);
+          const unsigned kk[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (jq + e < PT) {
+              p[jq + e] = kk[e] ? p[jq + e] * keep_scale : 0.f;
+              if (a.drop.mask != nullptr && half == 0 && jq + e < P)
+                a.drop.mask[(long long)rowid * P + jq + e] = (unsigned char)kk[e];
+            }
+          }
+        }
+      }
+      // this thread's 16 output channels over all keys
+      float o[AT_HD / 2];
+#pragma unroll
+      for (int c = 0; c < AT_HD / 2; ++c) o[c] = 0.f;
+      const int c0 = half * (AT_HD / 2);
+#pragma unroll
+      for (int j = 0; j < PT; ++j) {
+        if (j < P) {
+          const float pj = p[j] * inv;
+          const float4* vr = reinterpret_cast<const float4*>(vs[kbase + j] + c0);
+#pragma unroll
+          for (int c4 = 0; c4 < AT_HD / 8; ++c4) {
+            const float4 vv = vr[c4];
+            o[4 * c4] = fmaf(pj, vv.x, o[4 * c4]); o[4 * c4 + 1] = fmaf(pj, vv.y, o[4 * c4 + 1]);
+            o[4 * c4 + 2] = fmaf(pj, vv.z, o[4 * c4 + 2]); o[4 * c4 + 3] = fmaf(pj, vv.w, o[4 * c4 + 3]);
+          }
+        }
+      }
+      if (live) {
+        __nv_bfloat16* op = a.att + (long long)(row0 + r) * 256 + h * AT_HD + c0;
+#pragma unroll
+        for (int c = 0; c < AT_HD / 2; c += 4)
+          *reinterpret_cast<uint2*>(op + c) = pack_bf16x4(make_float4(o[c], o[c + 1], o[c + 2], o[c + 3]));
+      }
+      tc::group_sync(1, FB_EPI);  // ks / vs / sc are reused by the next head
+    }
+    tc::fence_before_sync();
+  }
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc<256>(tmem);
+}
+
+// tensor map with an arbitrary box height (the weight slices are 32 rows)
+static int make_map_rows(CUtensorMap* map, const void* base, int rows, int cols, int box_rows) {
+  return make_map(map, base, rows, cols, box_rows);
+}
+
+int launch_encoder_attn(const __nv_bfloat16* xn, const __nv_bfloat16* w_in, AttnArgs a, int T, cudaStream_t stream) {
+  MPA_CHECK_ARG(a.P >= 1 && a.P <= 32, "encoder_attn: 1 <= P <= 32");
+  a.SPT = LN_BM / a.P;
+  const int tiles = (a.B + a.SPT - 1) / a.SPT;
+  // few token tiles: split the 8 heads over more CTAs (each re-reads the 64 KB activation tile)
+  int hs = 1;
+  while (hs < 8 && tiles * hs * 2 <= device_sms()) hs *= 2;
+  a.heads_per_cta = 8 / hs;
+  CUtensorMap m_xn, m_w;
+  int rc = make_map_rows(&m_xn, xn, T, 256, LN_BM);
+  if (rc == MPA_OK) rc = make_map_rows(&m_w, w_in, 768, 256, AT_HD);
+  if (rc != MPA_OK) return rc;
+  static DeviceOnce attr;
+  if (attr.pending()) {
+    MPA_CUDA(cudaFuncSetAttribute(encoder_attn_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+    MPA_CUDA(cudaFuncSetAttribute(encoder_attn_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+    attr.done();
+  }
+  {
+    ProfScope ps("encoder_attn", stream);
+    if (a.P <= 20)
+      encoder_attn_kernel<20><<<dim3(tiles, hs), LN_THREADS, AT_SMEM, stream>>>(m_xn, m_w, a);
+    else
+      encoder_attn_kernel<32><<<dim3(tiles, hs), LN_THREADS, AT_SMEM, stream>>>(m_xn, m_w, a);
+  }
+  MPA_LAUNCH_CHECK();
+  return MPA_OK;
+}
+
 // ---- small token-level kernels ---------------------------------------------
 // LayerNorm over the last dim (D <= 1024, multiple of 32): one warp per row,
 // fp32 statistics (two-pass in registers), output bf16 (GEMM operand) and/or fp32.
@@ -1270,6 +1520,16 @@ int mpa_transformer_forward(const float* tokens, const unsigned char* valid, int
         layernorm_kernel<<<ln_blocks, 256, 0, stream>>>(x, norm1_w[l], norm1_b[l], T, D, eps, xn, nullptr, pl_TD); }
       MPA_LAUNCH_CHECK();
     }
+    static const bool no_attn = getenv("MPA_NO_FUSED_ATTN") != nullptr;  // A/B switch (tools/ab_step.sh)
+    const bool fused_attn = fused && split == 1 && hd == AT_HD && H == 8 && !no_attn;
+    if (fused_attn) {
+      // QKV projection + attention in ONE kernel (whole shapes per CTA, heads split over CTAs)
+      AttnArgs aa{};
+      aa.b_in = in_proj_b[l]; aa.valid = valid; aa.att = att; aa.B = B; aa.P = P;
+      aa.drop = site(l, 0);
+      rc = launch_encoder_attn(xn, wl, aa, T, stream);
+      if (rc != MPA_OK) return rc;
+    } else {
     LinearEpilogue e_qkv{in_proj_b[l], nullptr, qkv, nullptr, ACT_NONE};
     rc = launch_linear(xn, wl, T, 3 * D, D, e_qkv, "linear_qkv", stream, split);
     if (rc != MPA_OK) return rc;
@@ -1277,6 +1537,7 @@ int mpa_transformer_forward(const float* tokens, const unsigned char* valid, int
       attention_kernel<<<B * H, 32 * (P < ATT_MAX_WARPS ? P : ATT_MAX_WARPS), att_smem, stream>>>(
           qkv, valid, B, P, H, hd, att, pl_TD, site(l, 0)); }
     MPA_LAUNCH_CHECK();
+    }
     const bool last = l + 1 == layers;
     if (fused && split == 1 && FF % FB_CH == 0 && FF <= FB_MAX_FF) {
       // out_proj + LayerNorm2 + FFN + the next LayerNorm in ONE kernel (128 token rows per CTA)
