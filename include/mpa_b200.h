@@ -103,6 +103,11 @@ int mpa_se3_transform_backward(const float* quat, const float* pts, const float*
                                int n_parts, int N, float* grad_pts, float* grad_quat,
                                float* grad_trans, void* stream);
 
+/* Rotation3D's constructor rule for quaternions (utils/rotation.py:121-128): rows whose
+ * norm is <= 0.5 (the all-zero quaternions of padded parts) become the identity (1,0,0,0).
+ * quat / out [n,4] fp32, 16-byte aligned; out may alias quat. */
+int mpa_quat_fix_zero(const float* quat, long long n, float* out, void* stream);
+
 /* ---- fused pose losses -------------------------------------------------- */
 /* Fused SE(3) + bidirectional Chamfer for the two Chamfer losses of
  * utils/loss.py.  pts [B,P,N,3]; quat1/quat2 [B,P,4]; trans1/trans2 [B,P,3] or

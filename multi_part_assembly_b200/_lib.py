@@ -35,6 +35,7 @@ _SIGNATURES = {
                                          c_int, c_void_p]),
     'mpa_se3_transform': (c_int, [c_void_p] * 3 + [c_int] * 2 + [c_void_p] * 2),
     'mpa_se3_transform_backward': (c_int, [c_void_p] * 3 + [c_int] * 2 + [c_void_p] * 4),
+    'mpa_quat_fix_zero': (c_int, [c_void_p, ctypes.c_longlong, c_void_p, c_void_p]),
     'mpa_pose_chamfer_workspace_bytes': (c_size_t, [c_int] * 4),
     'mpa_pose_chamfer': (c_int, [c_void_p] * 6 + [c_int] * 4 + [c_void_p] * 7 +
                          [c_size_t, c_void_p]),

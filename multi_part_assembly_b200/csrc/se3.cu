@@ -118,6 +118,17 @@ int launch_se3_backward(const float* quat, const float* pts, const float* grad_o
   return MPA_OK;
 }
 
+// zero (padding) quaternions -> identity, everything else untouched: the constructor rule of
+// Rotation3D (utils/rotation.py:121-128 of the reference) as one launch instead of
+// norm / compare / zeros / index-fill / where
+__global__ void quat_fix_zero_kernel(const float4* __restrict__ q, long long n, float4* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 v = q[i];
+  const float nrm = sqrtf(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w);
+  out[i] = nrm > 0.5f ? v : make_float4(1.f, 0.f, 0.f, 0.f);
+}
+
 }  // namespace mpa
 
 using namespace mpa;
@@ -140,6 +151,18 @@ int mpa_se3_transform(const float* quat, const float* trans, const float* pts, i
         quat, trans, (const float4*)pts, n_parts, N, (float4*)out);
   else
     se3_forward_kernel<<<(unsigned)blocks, 256, 0, stream>>>(quat, trans, pts, n_parts, N, out);
+  MPA_LAUNCH_CHECK();
+  return MPA_OK;
+}
+
+int mpa_quat_fix_zero(const float* quat, long long n, float* out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MPA_CHECK_ARG(n >= 0, "quat_fix_zero: negative size");
+  if (n == 0) return MPA_OK;
+  MPA_CHECK_ARG(quat && out, "quat_fix_zero: null pointer");
+  MPA_CHECK_ARG((((uintptr_t)quat | (uintptr_t)out) % 16) == 0, "quat_fix_zero: 16-byte aligned rows");
+  ProfScope ps("quat_fix_zero", stream);
+  quat_fix_zero_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((const float4*)quat, n, (float4*)out);
   MPA_LAUNCH_CHECK();
   return MPA_OK;
 }

@@ -15,7 +15,7 @@ import torch.nn.functional as F
 from . import _lib
 
 
-def encode_parts(encoder, part_pcs, part_valids, feat_dim):
+def encode_parts(encoder, part_pcs, part_valids, feat_dim, valid_mask=None):
     """[B, P, N, 3], [B, P] -> [B, P, C]: run the shared encoder on the valid
     parts only (BatchNorm statistics must exclude padding) and scatter the
     features back; padded parts get zeros.
@@ -27,11 +27,12 @@ def encode_parts(encoder, part_pcs, part_valids, feat_dim):
     semantics but do the compaction with one nonzero() call reused for gather
     and scatter."""
     B, P, N, _ = part_pcs.shape
+    if valid_mask is None:  # callers that also need the mask elsewhere pass it in
+        valid_mask = part_valids == 1
     if getattr(encoder, 'supports_valids', False):
         # device-side skipping of padded parts: no host synchronisation at all
-        feats = encoder(part_pcs.reshape(B * P, N, 3), valids=(part_valids == 1).reshape(-1))
+        feats = encoder(part_pcs.reshape(B * P, N, 3), valids=valid_mask.reshape(-1))
         return feats.view(B, P, -1)
-    valid_mask = part_valids == 1
     if bool(valid_mask.all()):
         feats = encoder(part_pcs.reshape(B * P, N, 3))
         return feats.view(B, P, -1)
@@ -927,7 +928,12 @@ class _TransformerFunction(torch.autograd.Function):
         L = _lib.lib()
         ws_bytes = L.mpa_transformer_workspace_bytes(B, P, D, FF, len(ls))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        vb = None if valid is None else valid.to(torch.uint8).contiguous()
+        if valid is None:
+            vb = None
+        elif valid.dtype == torch.bool and valid.is_contiguous():
+            vb = valid.view(torch.uint8)  # same bytes, no copy
+        else:
+            vb = valid.to(torch.uint8).contiguous()
         fn = encoder.norm
         masks, rng = None, None
         if dropout_p > 0.:

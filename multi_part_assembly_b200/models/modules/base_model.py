@@ -103,7 +103,8 @@ class BaseModel(LightningModule):
         dataset schema; like the reference (:130-132)
         the call replaces `part_quat` by the Rotation3D `part_rot` in place."""
         part_quat = data_dict.pop('part_quat')
-        data_dict['part_rot'] = Rotation3D(part_quat, rot_type='quat').convert(self.rot_type)
+        part_rot = Rotation3D(part_quat, rot_type='quat')  # a fresh tensor: no defensive clone
+        data_dict['part_rot'] = part_rot if self.rot_type == 'quat' else part_rot.convert(self.rot_type)
         loss_dict = self.loss_function(data_dict, optimizer_idx=optimizer_idx)
 
         if mode == 'train' and self.local_rank == 0:
@@ -256,6 +257,9 @@ class BaseModel(LightningModule):
         if self.semantic:
             new_trans, new_rot = self._match_parts(part_pcs, pred_trans, pred_rot, gt_trans,
                                                    gt_rot, data_dict['match_ids'])
+        elif self._can_fuse_losses(pred_rot, gt_rot):
+            # the fused kernels only read the ground-truth poses: no copies
+            return self._calc_loss_fused(out_dict, data_dict, gt_trans, gt_rot)
         else:
             new_trans, new_rot = gt_trans.detach().clone(), gt_rot.detach().clone()
 

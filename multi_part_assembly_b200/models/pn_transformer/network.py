@@ -41,10 +41,11 @@ class PNTransformer(BaseModel):
         return StocasticPoseRegressor(feat_dim=self._pose_in_dim(),
                                       noise_dim=self.cfg.loss.noise_dim, rot_type=self.rot_type)
 
-    def _extract_part_feats(self, part_pcs, part_valids):
+    def _extract_part_feats(self, part_pcs, part_valids, valid_mask=None):
         """[B, P, N, 3] -> [B, P, C]; padded parts get zero features and are
         excluded from the encoder's BatchNorm statistics (reference :59-68)."""
-        return kernels.encode_parts(self.encoder, part_pcs, part_valids, self.pc_feat_dim)
+        return kernels.encode_parts(self.encoder, part_pcs, part_valids, self.pc_feat_dim,
+                                    valid_mask=valid_mask)
 
     def forward(self, data_dict):
         """data_dict: part_pcs [B,P,N,3], part_valids [B,P], part_label
@@ -53,8 +54,9 @@ class PNTransformer(BaseModel):
         feats = data_dict.get('pre_pose_feats', None)
         if feats is None:
             part_valids = data_dict['part_valids']
-            pc_feats = self._extract_part_feats(data_dict['part_pcs'], part_valids)
-            corr_feats = self.corr_module(pc_feats, part_valids == 1)
+            valid_mask = part_valids == 1  # computed once for the encoder and the transformer
+            pc_feats = self._extract_part_feats(data_dict['part_pcs'], part_valids, valid_mask)
+            corr_feats = self.corr_module(pc_feats, valid_mask)
             feats = torch.cat([corr_feats, data_dict['part_label'].type_as(corr_feats),
                                data_dict['instance_label'].type_as(corr_feats)], dim=-1)
         rot, trans = self.pose_predictor(feats)

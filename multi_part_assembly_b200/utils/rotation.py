@@ -94,6 +94,18 @@ class Rotation3D:
         self._check_valid()
 
     def _process_zero_quat(self):
+        r = self._rot
+        if r.is_cuda and r.dtype == torch.float32 and not (torch.is_grad_enabled() and r.requires_grad):
+            # one native launch (csrc/se3.cu) instead of norm / compare / zeros / fill / where
+            from .. import _lib
+            src = r.detach().contiguous()
+            out = torch.empty_like(src)
+            with torch.cuda.device(r.device):
+                rc = _lib.lib().mpa_quat_fix_zero(_lib.ptr(src), src.numel() // 4, _lib.ptr(out),
+                                                  _lib.cuda_stream(r.device))
+            _lib.check(rc, 'mpa_quat_fix_zero')
+            self._rot = out
+            return
         with torch.no_grad():
             keep = torch.norm(self._rot, p=2, dim=-1, keepdim=True) > 0.5
             identity = torch.zeros_like(self._rot)

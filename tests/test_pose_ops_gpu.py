@@ -192,3 +192,22 @@ def test_lsap_kernel_matches_scipy(cuda):
     got = kernels.lsap_batched([torch.from_numpy(m).to(cuda) for m in mats])
     for m, g in zip(mats, got):
         np.testing.assert_array_equal(g.cpu().numpy(), linear_sum_assignment(m)[1])
+
+
+@pytest.mark.gpu
+def test_rotation3d_zero_quat_native(cuda):
+    """Rotation3D's constructor on CUDA (one native launch) vs the reference rule
+    (rotation.py:121-128): zero quaternions -> identity, the rest bit-identical."""
+    from multi_part_assembly_b200.utils.rotation import Rotation3D
+    g = torch.Generator().manual_seed(3)
+    q = torch.nn.functional.normalize(torch.randn(7, 20, 4, generator=g), dim=-1)
+    q[1, 5:] = 0.
+    q[4] = 0.
+    q[6, 0] = torch.tensor([0.3, 0.2, 0.1, 0.1])  # norm < 0.5 -> identity too
+    want = Rotation3D(q.clone(), 'quat').rot                # CPU: the torch formulation
+    got = Rotation3D(q.to(cuda), 'quat').rot
+    assert torch.equal(got.cpu(), want)
+    # a tensor that needs a gradient keeps the differentiable torch path
+    qg = q.to(cuda).requires_grad_(True)
+    r = Rotation3D(qg, 'quat').rot
+    assert r.requires_grad and torch.equal(r.detach().cpu(), want)
