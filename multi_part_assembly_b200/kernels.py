@@ -857,7 +857,37 @@ def _rng_state(dev):
     return torch.randint(0, 2**62, (2, ), dtype=torch.int64, device=dev)
 
 
-def _transformer_masked_torch(tokens, valid, encoder, num_heads, masks, p):
+class _TokenLinear(torch.autograd.Function):
+    """y = x W^T + b on [.., K] token rows for the backward re-run of the encoder.  Same math
+    as F.linear; the difference is the bias gradient, a [1, T] x [T, N] GEMM with fp32 output
+    instead of ATen's column reduction, which runs 640 rows x 1024 columns on two thread
+    blocks (29 us per bias, 16 biases per step: profiles/r02_launches_train_step_summary.txt)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, dt):
+        xc, Wc = x.to(dt), W.to(dt)
+        ctx.save_for_backward(xc, Wc)
+        ctx.in_dtypes = (x.dtype, W.dtype, b.dtype)
+        return F.linear(xc, Wc, b.to(dt))
+
+    @staticmethod
+    def backward(ctx, g):
+        xc, Wc = ctx.saved_tensors
+        dx_t, dw_t, db_t = ctx.in_dtypes
+        N, K = Wc.shape
+        g2 = g.reshape(-1, N).to(Wc.dtype)
+        x2 = xc.reshape(-1, K)
+        dx = (g2 @ Wc).view(xc.shape).to(dx_t)
+        if Wc.dtype == torch.float32:
+            dW = g2.t() @ x2
+            db = (g2.new_ones(1, g2.shape[0]) @ g2).view(N)
+        else:
+            dW = _mm_f32(g2.t(), x2)
+            db = _mm_f32(g2.new_ones(1, g2.shape[0]), g2).view(N)
+        return dx, dW.to(dw_t), db.to(db_t), None
+
+
+def _transformer_masked_torch(tokens, valid, encoder, num_heads, masks, p, fast_bias_grad=False):
     """The encoder in plain torch ops with EXPLICIT dropout keep masks (per layer: attention
     probabilities [B,H,P,P], after out_proj [B,P,D], FFN hidden [B,P,FF], after linear2 [B,P,D];
     None = no dropout) -- nn.TransformerEncoderLayer(norm_first=True) semantics.  Used to
@@ -865,6 +895,11 @@ def _transformer_masked_torch(tokens, valid, encoder, num_heads, masks, p):
     B, P, D = tokens.shape
     hd = D // num_heads
     keep = 1.0 / (1.0 - p) if masks is not None else 1.0
+    if fast_bias_grad:
+        dt = torch.bfloat16 if torch.is_autocast_enabled() else tokens.dtype
+        linear = lambda a, W, b: _TokenLinear.apply(a, W, b, dt)  # noqa: E731
+    else:
+        linear = F.linear
     neg = None
     if valid is not None and valid.numel():
         neg = torch.zeros(B, 1, 1, P, dtype=tokens.dtype, device=tokens.device)
@@ -873,7 +908,7 @@ def _transformer_masked_torch(tokens, valid, encoder, num_heads, masks, p):
     for l, layer in enumerate(encoder.layers):
         m = masks[l] if masks is not None else (None, None, None, None)
         h = F.layer_norm(x, (D, ), layer.norm1.weight, layer.norm1.bias, layer.norm1.eps)
-        qkv = F.linear(h, layer.self_attn.in_proj_weight, layer.self_attn.in_proj_bias)
+        qkv = linear(h, layer.self_attn.in_proj_weight, layer.self_attn.in_proj_bias)
         q, k, v = qkv.view(B, P, 3, num_heads, hd).permute(2, 0, 3, 1, 4)
         sc = torch.matmul(q, k.transpose(-1, -2)) / (hd**0.5)
         if neg is not None:
@@ -882,15 +917,15 @@ def _transformer_masked_torch(tokens, valid, encoder, num_heads, masks, p):
         if m[0] is not None:
             pr = pr * (m[0].to(pr.dtype) * keep)
         o = torch.matmul(pr, v).permute(0, 2, 1, 3).reshape(B, P, D)
-        o = F.linear(o, layer.self_attn.out_proj.weight, layer.self_attn.out_proj.bias)
+        o = linear(o, layer.self_attn.out_proj.weight, layer.self_attn.out_proj.bias)
         if m[1] is not None:
             o = o * (m[1].to(o.dtype) * keep)
         x = x + o
         h = F.layer_norm(x, (D, ), layer.norm2.weight, layer.norm2.bias, layer.norm2.eps)
-        f = F.relu(F.linear(h, layer.linear1.weight, layer.linear1.bias))
+        f = F.relu(linear(h, layer.linear1.weight, layer.linear1.bias))
         if m[2] is not None:
             f = f * (m[2].to(f.dtype) * keep)
-        f = F.linear(f, layer.linear2.weight, layer.linear2.bias)
+        f = linear(f, layer.linear2.weight, layer.linear2.bias)
         if m[3] is not None:
             f = f * (m[3].to(f.dtype) * keep)
         x = x + f
@@ -915,7 +950,7 @@ def split_transformer_masks(masks, B, P, D, H, FF, layers):
 class _TransformerFunction(torch.autograd.Function):
     """Forward: tcgen05 + TMA kernels (csrc/linear.cu), dropout drawn in-kernel (Philox) when
     training with p > 0.  Backward: autograd through the same layer chain in torch ops, with
-    the keep masks the kernels wrote (or the stock module when there is no dropout)."""
+    the keep masks the kernels wrote; bias gradients as GEMMs (`_TokenLinear`)."""
 
     @staticmethod
     def forward(ctx, tokens, valid, encoder, num_heads, dropout_p, precision, *params):
@@ -970,14 +1005,12 @@ class _TransformerFunction(torch.autograd.Function):
         with torch.enable_grad(), torch.autocast('cuda', dtype=torch.bfloat16,
                                                  enabled=ctx.precision == PRECISION_BF16):
             t = tokens.detach().requires_grad_(True)
+            ms = None
             if ctx.dropout_p > 0.:
                 FF = encoder.layers[0].linear1.out_features
                 ms = split_transformer_masks(masks, B, P, D, ctx.num_heads, FF, len(encoder.layers))
-                out = _transformer_masked_torch(t, valid if valid.numel() else None, encoder,
-                                                ctx.num_heads, ms, ctx.dropout_p)
-            else:
-                pad = ~valid if valid.numel() else None
-                out = encoder(t, src_key_padding_mask=pad)
+            out = _transformer_masked_torch(t, valid if valid.numel() else None, encoder,
+                                            ctx.num_heads, ms, ctx.dropout_p, fast_bias_grad=True)
             grads = torch.autograd.grad(out, [t] + params, grad.to(out.dtype), allow_unused=True)
         torch.backends.cuda.matmul.allow_tf32 = prev_tf32
         return (grads[0], None, None, None, None, None) + tuple(grads[1:])

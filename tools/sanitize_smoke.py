@@ -25,5 +25,26 @@ for name, enc in (('pn_transformer', 'pointnet'), ('dgl', 'dgcnn')):
         print(name, float(model.forward_pass(dict(batch), mode='train', optimizer_idx=-1)['loss']))
     loss = model.forward_pass(dict(batch), mode='train', optimizer_idx=-1)['loss']
     loss.backward()
+# reference training configuration: dropout 0.1 inside the native transformer (bf16) and the
+# fp32-accurate three-plane mode
+model = build_model(get_cfg('pn_transformer')).to(dev).train()
+model.trainer = Trainer()
+batch = make_batch(2, P=20, N=200, num_valid=[20, 7], seed=1, device=dev)
+with torch.autocast('cuda', dtype=torch.bfloat16):
+    model.forward_pass(dict(batch), mode='train', optimizer_idx=-1)['loss'].backward()
+kernels.set_precision('fp32')
+with torch.no_grad():
+    print('fp32 mode', float(model.forward_pass(dict(batch), mode='train', optimizer_idx=-1)['loss']))
+kernels.set_precision('auto')
+# PointNet++ ops
+xyz = torch.rand(3, 500, 3, device=dev)
+fi, cen = kernels.furthest_point_sample(xyz, 64)
+kernels.ball_query(0.2, 16, xyz, cen)
+for enc in ('pointnet2_ssg', 'pointnet2_msg'):
+    m2 = build_model(get_cfg('pn_transformer', encoder=enc)).to(dev).train()
+    m2.trainer = Trainer()
+    with torch.no_grad():
+        print(enc, float(m2.forward_pass(dict(make_batch(2, P=20, N=256, num_valid=[4, 3], seed=2, device=dev)),
+                                         mode='train', optimizer_idx=-1)['loss']))
 torch.cuda.synchronize()
 print('sanitize smoke done')
