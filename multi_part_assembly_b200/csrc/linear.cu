@@ -585,6 +585,13 @@ struct FfnBlockArgs {
   float eps;
   DropoutSpec drop1, drop_h, drop2;
   long long* dbg = nullptr;  // MPA_FFN_DEBUG: cycle stamps of CTA 0 (see tools/profile_transformer.py)
+  // hidden-dimension split over a thread-block cluster (few token tiles: 640 tokens are 5 tiles
+  // on 148 SMs): `cl` CTAs share a tile, each contracts FF / cl hidden columns and leaves a
+  // partial [128 x 256] result in `part`; after the cluster barrier every CTA sums, finishes
+  // and normalises its own 128 / cl rows.  cl == 1: one CTA does the whole tile.
+  int cl = 1;
+  float* part = nullptr;     // [tiles, cl, 128, 256] fp32 partial FFN outputs
+  float* x1s = nullptr;      // [tiles, 128, 256] residual stream after attention (owner rows)
 };
 #define FB_STAMP(i) do { if (a.dbg != nullptr && blockIdx.x == 0) a.dbg[i] = clock64(); } while (0)
 
@@ -592,28 +599,21 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
 }
 
-// LayerNorm of the 128 rows parked in TMEM columns [0, 256): statistics in two passes
-// (mean, centred variance), the two half-row warps of a row meet in shared memory.
-// `emit(j0, v)` receives 32 normalised columns j0.. of this thread's row.
+// LayerNorm of the 128 rows parked in TMEM columns [0, 256).  The caller accumulated the row
+// sums and sums of squares of its half while parking (one-pass statistics: the residual stream
+// is O(1) with |mean| << std, and the bf16 operand this feeds has 8 mantissa bits); the two
+// half-row warps of a row meet in shared memory.  `emit(j0, v)` receives 32 normalised columns
+// j0.. of this thread's row.
 template <typename Emit>
 __device__ __forceinline__ void fb_layernorm_rows(uint32_t taddr, int c_begin, int c_end, int half, int row_local,
-                                                  float sum, float (*ln_part)[2][LN_BM], const float* g,
-                                                  const float* b, float eps, Emit emit) {
+                                                  float sum, float sumsq, float (*ln_part)[2][LN_BM],
+                                                  const float* g, const float* b, float eps, Emit emit) {
   ln_part[0][half][row_local] = sum;
+  ln_part[1][half][row_local] = sumsq;
   tc::group_sync(1, FB_EPI);
   const float mean = (ln_part[0][0][row_local] + ln_part[0][1][row_local]) * (1.0f / FB_D);
-  float sq = 0.f;
-#pragma unroll 1
-  for (int j0 = c_begin; j0 < c_end; j0 += 32) {
-    float v[32];
-    tc::tmem_ld32(taddr + (uint32_t)j0, v);
-    tc::tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 32; ++j) { const float d = v[j] - mean; sq = fmaf(d, d, sq); }
-  }
-  ln_part[1][half][row_local] = sq;
-  tc::group_sync(1, FB_EPI);
-  const float rstd = rsqrtf((ln_part[1][0][row_local] + ln_part[1][1][row_local]) * (1.0f / FB_D) + eps);
+  const float ex2 = (ln_part[1][0][row_local] + ln_part[1][1][row_local]) * (1.0f / FB_D);
+  const float rstd = rsqrtf(fmaxf(ex2 - mean * mean, 0.f) + eps);
 #pragma unroll 1
   for (int j0 = c_begin; j0 < c_end; j0 += 32) {
     float v[32];
@@ -639,6 +639,89 @@ __device__ __forceinline__ void fb_store_operand_row(uint8_t* tiles, int row, in
   }
 }
 
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// Cluster mode, after the barrier: rows [rank * 128 / CL, +128 / CL) of the tile belong to this
+// CTA.  2 CL threads per row (consecutive lanes), each 64-float stripe of the row is covered by
+// one coalesced float4 access of the row's threads:  x = sum of the CL partials + b_2 (dropout2)
+// + x_after_attention, then LayerNorm_next with shuffle reductions inside the row's lanes.
+template <int CL>
+__device__ __forceinline__ void fb_reduce_owned_rows(const FfnBlockArgs& a, int tile_i, int rank,
+                                                     const float (*s_vec)[FB_D]) {
+  constexpr int RO = LN_BM / CL, TPR = FB_EPI / RO, NQ = FB_D / 4 / TPR;
+  const int t = threadIdx.x - 64;
+  const int rl = rank * RO + t / TPR, cg = t % TPR;
+  const int row = tile_i * LN_BM + rl;
+  const bool row_ok = row < a.M;
+  float4 acc[NQ];
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) acc[i] = *reinterpret_cast<const float4*>(&s_vec[3][4 * (i * TPR + cg)]);
+#pragma unroll
+  for (int p = 0; p < CL; ++p) {
+    const float* pp = a.part + ((long long)(tile_i * CL + p) * LN_BM + rl) * FB_D;
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+      const float4 u = __ldcg(reinterpret_cast<const float4*>(pp + 4 * (i * TPR + cg)));
+      acc[i].x += u.x; acc[i].y += u.y; acc[i].z += u.z; acc[i].w += u.w;
+    }
+  }
+  if (a.drop2.rng != nullptr && row_ok) {
+    const float scale = 1.0f / (1.0f - a.drop2.p);
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+      const int col = 4 * (i * TPR + cg);
+      const uint4 k = dropout_quad(a.drop2.rng, a.drop2.site, (unsigned)row, (unsigned)(col >> 2), a.drop2.p);
+      acc[i].x = k.x ? acc[i].x * scale : 0.f; acc[i].y = k.y ? acc[i].y * scale : 0.f;
+      acc[i].z = k.z ? acc[i].z * scale : 0.f; acc[i].w = k.w ? acc[i].w * scale : 0.f;
+      if (a.drop2.mask != nullptr)
+        *reinterpret_cast<uchar4*>(a.drop2.mask + (long long)row * FB_D + col) =
+            make_uchar4((unsigned char)k.x, (unsigned char)k.y, (unsigned char)k.z, (unsigned char)k.w);
+    }
+  }
+  const float* xs = a.x1s + ((long long)tile_i * LN_BM + rl) * FB_D;
+  const bool norm = a.lnn_g != nullptr;
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    const int col = 4 * (i * TPR + cg);
+    const float4 x = __ldcg(reinterpret_cast<const float4*>(xs + col));
+    acc[i].x += x.x; acc[i].y += x.y; acc[i].z += x.z; acc[i].w += x.w;
+    sum += (acc[i].x + acc[i].y) + (acc[i].z + acc[i].w);
+    if (row_ok) {
+      const long long o = (long long)row * FB_D + col;
+      if (a.x_out != nullptr) *reinterpret_cast<float4*>(a.x_out + o) = acc[i];
+      if (!norm && a.out_f32 != nullptr) *reinterpret_cast<float4*>(a.out_f32 + o) = acc[i];
+    }
+  }
+  if (!norm) return;  // uniform
+#pragma unroll
+  for (int o = TPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum * (1.0f / FB_D);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    const float dx = acc[i].x - mean, dy = acc[i].y - mean, dz = acc[i].z - mean, dw = acc[i].w - mean;
+    sq = fmaf(dx, dx, sq); sq = fmaf(dy, dy, sq); sq = fmaf(dz, dz, sq); sq = fmaf(dw, dw, sq);
+  }
+#pragma unroll
+  for (int o = TPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq * (1.0f / FB_D) + a.eps);
+  if (!row_ok) return;
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    const int col = 4 * (i * TPR + cg);
+    const float4 g = *reinterpret_cast<const float4*>(&s_vec[4][col]);
+    const float4 b = *reinterpret_cast<const float4*>(&s_vec[5][col]);
+    const float4 y = make_float4((acc[i].x - mean) * rstd * g.x + b.x, (acc[i].y - mean) * rstd * g.y + b.y,
+                                 (acc[i].z - mean) * rstd * g.z + b.z, (acc[i].w - mean) * rstd * g.w + b.w);
+    const long long o = (long long)row * FB_D + col;
+    if (a.xn_out != nullptr) *reinterpret_cast<uint2*>(a.xn_out + o) = pack_bf16x4(y);
+    if (a.out_f32 != nullptr) *reinterpret_cast<float4*>(a.out_f32 + o) = y;
+  }
+}
+
 __global__ void __launch_bounds__(LN_THREADS, 1)
 encoder_ffn_block_kernel(const __grid_constant__ CUtensorMap map_att, const __grid_constant__ CUtensorMap map_wo,
                          const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2,
@@ -657,8 +740,11 @@ encoder_ffn_block_kernel(const __grid_constant__ CUtensorMap map_att, const __gr
   __shared__ __align__(16) float s_b1[FB_MAX_FF];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * LN_BM;
-  const int C = a.FF / FB_CH;  // hidden chunks
+  const int cl = a.cl;
+  const int tile_i = blockIdx.x / cl, rank = blockIdx.x - tile_i * cl;  // cluster = cl consecutive CTAs
+  const int m0 = tile_i * LN_BM;
+  const int C = a.FF / FB_CH / cl;  // hidden chunks of this CTA
+  const int c_lo = rank * C;        // ... starting at this chunk of the hidden layer
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < FB_NST; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
@@ -698,13 +784,15 @@ encoder_ffn_block_kernel(const __grid_constant__ CUtensorMap map_att, const __gr
       auto f1 = [&](int c) {  // W_1 rows [128 c, +128): two stages of two [128 x 64] k-blocks
         for (int st = 0; st < 2; ++st)
           stage([&](uint8_t* dst, uint64_t* bar) {
-            tma_load_2d(dst, &map_w1, (2 * st) * LN_BK, c * FB_CH, bar);
-            tma_load_2d(dst + FB_STAGE / 2, &map_w1, (2 * st + 1) * LN_BK, c * FB_CH, bar);
+            tma_load_2d(dst, &map_w1, (2 * st) * LN_BK, (c_lo + c) * FB_CH, bar);
+            tma_load_2d(dst + FB_STAGE / 2, &map_w1, (2 * st + 1) * LN_BK, (c_lo + c) * FB_CH, bar);
           });
       };
       auto f2 = [&](int c) {  // W_2 [256 x 64] k-blocks of hidden columns [128 c, +128)
         for (int st = 0; st < 2; ++st)
-          stage([&](uint8_t* dst, uint64_t* bar) { tma_load_2d(dst, &map_w2, c * FB_CH + st * LN_BK, 0, bar); });
+          stage([&](uint8_t* dst, uint64_t* bar) {
+            tma_load_2d(dst, &map_w2, (c_lo + c) * FB_CH + st * LN_BK, 0, bar);
+          });
       };
       f1(0);
       if (C > 1) f1(1);
@@ -805,9 +893,6 @@ encoder_ffn_block_kernel(const __grid_constant__ CUtensorMap map_att, const __gr
     const int c_begin = half * (FB_D / 2), c_end = c_begin + FB_D / 2;
 
     // ---- E1: x = acc0 + b_o (dropout1) + x_in ; LayerNorm2 -> A1 ----
-    tc::mbar_wait(&acc0_o_done, 0);
-    tc::fence_after_sync();
-    if (threadIdx.x == 64) FB_STAMP(32);
     // Rows meet global memory through a per-warp [32 x 32] fp32 staging tile (in the A0 region,
     // idle here): a TMEM lane is a row, a coalesced access wants 4 rows x 128 contiguous bytes.
     float* tile = reinterpret_cast<float*>(A0) + (warp - 2) * EP_TILE_FLOATS;
@@ -821,8 +906,11 @@ encoder_ffn_block_kernel(const __grid_constant__ CUtensorMap map_att, const __gr
                          : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    fetch_rows(a.x_in, c_begin);
-    float sum = 0.f;
+    fetch_rows(a.x_in, c_begin);  // issued before the wait: its latency hides behind out_proj
+    tc::mbar_wait(&acc0_o_done, 0);
+    tc::fence_after_sync();
+    if (threadIdx.x == 64) FB_STAMP(32);
+    float sum = 0.f, sumsq = 0.f;
 #pragma unroll 1
     for (int j0 = c_begin; j0 < c_end; j0 += 32) {
       float v[32];
@@ -842,18 +930,26 @@ encoder_ffn_block_kernel(const __grid_constant__ CUtensorMap map_att, const __gr
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = qrow0 + 4 * i;
-        if (r < a.M) *reinterpret_cast<float4*>(a.x_out + (long long)r * FB_D + j0 + qcol) = xq[i];
+        if (cl == 1) {
+          if (r < a.M) *reinterpret_cast<float4*>(a.x_out + (long long)r * FB_D + j0 + qcol) = xq[i];
+        } else {
+          // every CTA of the cluster computes the whole tile (x_out may alias x_in, which the
+          // siblings are still reading): keep only the rows this CTA finishes, in scratch
+          const int rl = r - m0, own0 = rank * (LN_BM / cl);
+          if (rl >= own0 && rl < own0 + LN_BM / cl)
+            *reinterpret_cast<float4*>(a.x1s + ((long long)tile_i * LN_BM + rl) * FB_D + j0 + qcol) = xq[i];
+        }
         *tile_quad(tile, lane, i) = xq[i];
       }
       __syncwarp();
       tile_get_row(tile, lane, v);
       __syncwarp();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) sum += v[j];
+      for (int j = 0; j < 32; ++j) { sum += v[j]; sumsq = fmaf(v[j], v[j], sumsq); }
       tc::tmem_st32(acc0 + lane_off + (uint32_t)j0, v);
     }
     tc::tmem_st_wait();
-    fb_layernorm_rows(acc0 + lane_off, c_begin, c_end, half, row_local, sum, ln_part, s_vec[1], s_vec[2], a.eps,
+    fb_layernorm_rows(acc0 + lane_off, c_begin, c_end, half, row_local, sum, sumsq, ln_part, s_vec[1], s_vec[2], a.eps,
                       [&](int j0, const float* v) { fb_store_operand_row(A1, row_local, j0, v); });
     tc::fence_async_smem();        // A1 written through the generic proxy -> visible to the tensor core
     tc::fence_before_sync();       // ... and the TMEM reads of acc0 are complete
@@ -875,7 +971,7 @@ encoder_ffn_block_kernel(const __grid_constant__ CUtensorMap map_att, const __gr
       mbar_arrive(&acc1_free[b]);  // acc1[b] may be overwritten by chunk c + 2
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
-        const int col = c * FB_CH + h0 + 32 * t;  // hidden column of v[t][0]
+        const int col = (c_lo + c) * FB_CH + h0 + 32 * t;  // hidden column of v[t][0]
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[t][j] = fmaxf(v[t][j] + s_b1[col + j], 0.f);
         if (a.drop_h.rng != nullptr && row_ok) dropout32(v[t], a.drop_h, row, col, a.FF);
@@ -894,7 +990,25 @@ encoder_ffn_block_kernel(const __grid_constant__ CUtensorMap map_att, const __gr
     tc::mbar_wait(&acc0_f2_done, 0);
     tc::fence_after_sync();
     if (threadIdx.x == 64) FB_STAMP(34);
-    sum = 0.f;
+    if (cl > 1) {
+      // cluster mode: this CTA's partial result -> scratch; finished after the cluster barrier
+      float* pbase = a.part + (long long)(tile_i * cl + rank) * LN_BM * FB_D;
+#pragma unroll 1
+      for (int j0 = c_begin; j0 < c_end; j0 += 32) {
+        float v[32];
+        tc::tmem_ld32(acc0 + lane_off + (uint32_t)j0, v);
+        tc::tmem_ld_wait();
+        tile_put_row(tile, lane, v);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = q * 32 + (lane >> 3) + 4 * i;
+          *reinterpret_cast<float4*>(pbase + (long long)rl * FB_D + j0 + qcol) = *tile_quad(tile, lane, i);
+        }
+        __syncwarp();
+      }
+    } else {
+    sum = 0.f; sumsq = 0.f;
     const bool norm = a.lnn_g != nullptr;
     fetch_rows(a.x_out, c_begin);  // x after attention (written in E1, re-read coalesced)
 #pragma unroll 1
@@ -927,14 +1041,14 @@ encoder_ffn_block_kernel(const __grid_constant__ CUtensorMap map_att, const __gr
       if (norm) {
         tile_get_row(tile, lane, v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) sum += v[j];
+        for (int j = 0; j < 32; ++j) { sum += v[j]; sumsq = fmaf(v[j], v[j], sumsq); }
         tc::tmem_st32(acc0 + lane_off + (uint32_t)j0, v);
       }
       __syncwarp();
     }
     if (norm) {
       tc::tmem_st_wait();
-      fb_layernorm_rows(acc0 + lane_off, c_begin, c_end, half, row_local, sum, ln_part, s_vec[4], s_vec[5], a.eps,
+      fb_layernorm_rows(acc0 + lane_off, c_begin, c_end, half, row_local, sum, sumsq, ln_part, s_vec[4], s_vec[5], a.eps,
                         [&](int j0, const float* v) {
                           tile_put_row(tile, lane, v);
                           __syncwarp();
@@ -951,11 +1065,21 @@ encoder_ffn_block_kernel(const __grid_constant__ CUtensorMap map_att, const __gr
                           __syncwarp();
                         });
     }
+    }
     if (threadIdx.x == 64) FB_STAMP(35);
     tc::fence_before_sync();
   }
   __syncthreads();
   if (warp == 1) tc::tmem_dealloc<512>(tmem);
+  if (cl > 1) {
+    cluster_sync_all();  // the partial results of all CTAs of the cluster are in global memory
+    if (warp >= 2) {
+      if (cl == 8) fb_reduce_owned_rows<8>(a, tile_i, rank, s_vec);
+      else if (cl == 4) fb_reduce_owned_rows<4>(a, tile_i, rank, s_vec);
+      else fb_reduce_owned_rows<2>(a, tile_i, rank, s_vec);
+      if (threadIdx.x == 64) FB_STAMP(36);
+    }
+  }
 }
 
 // host side: tensor maps with a caller-chosen box height
@@ -979,12 +1103,39 @@ int launch_ffn_block(const __nv_bfloat16* att, const __nv_bfloat16* wo, const __
     attr.done();
   }
   if (const char* e = getenv("MPA_FFN_DEBUG")) a.dbg = (long long*)strtoull(e, nullptr, 0);  // device pointer
+  const int tiles = (a.M + LN_BM - 1) / LN_BM;
+  if (a.part == nullptr || a.x1s == nullptr) a.cl = 1;
   {
     ProfScope ps("encoder_ffn_block", stream);
-    encoder_ffn_block_kernel<<<(a.M + LN_BM - 1) / LN_BM, LN_THREADS, FB_SMEM, stream>>>(m_att, m_wo, m_w1, m_w2, a);
+    if (a.cl == 1) {
+      encoder_ffn_block_kernel<<<tiles, LN_THREADS, FB_SMEM, stream>>>(m_att, m_wo, m_w1, m_w2, a);
+    } else {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(tiles * a.cl);
+      cfg.blockDim = dim3(LN_THREADS);
+      cfg.dynamicSmemBytes = FB_SMEM;
+      cfg.stream = stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = a.cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      MPA_CUDA(cudaLaunchKernelEx(&cfg, encoder_ffn_block_kernel, m_att, m_wo, m_w1, m_w2, a));
+    }
   }
   MPA_LAUNCH_CHECK();
   return MPA_OK;
+}
+
+// cluster width of the FFN block: split the hidden layer over as many CTAs as keep tiles x cl
+// within one wave of SMs (8 = portable cluster limit); MPA_FFN_CLUSTER overrides (A/B runs)
+static int ffn_cluster_size(int M, int FF) {
+  static const int forced = getenv("MPA_FFN_CLUSTER") ? atoi(getenv("MPA_FFN_CLUSTER")) : 0;
+  const int tiles = (M + LN_BM - 1) / LN_BM, C = FF / FB_CH;
+  if (forced == 1 || forced == 2 || forced == 4 || forced == 8) return (C % forced == 0) ? forced : 1;
+  for (int cl = 8; cl >= 2; cl >>= 1)
+    if (C % cl == 0 && tiles * cl <= device_sms()) return cl;
+  return 1;
 }
 
 // ======================================================================================
@@ -1429,6 +1580,9 @@ size_t mpa_transformer_workspace_bytes(int B, int P, int D, int FF, int layers) 
   o += align_up(T * 3 * D * 4, 256);            // qkv fp32
   o += align_up(planes * T * D * 2, 256);       // attention output (operand)
   o += align_up(planes * T * FF * 2, 256);      // FFN hidden (operand)
+  // cluster mode of the fused block: tiles x cl <= SMs partial results + the owner rows of x
+  const size_t tiles = (T + LN_BM - 1) / LN_BM;
+  o += align_up(((size_t)device_sms() + tiles) * LN_BM * FB_D * 4, 256);
   return o;
 }
 
@@ -1467,7 +1621,9 @@ int mpa_transformer_forward(const float* tokens, const unsigned char* valid, int
   __nv_bfloat16* xn = (__nv_bfloat16*)p; p += align_up(3 * (size_t)T * D * 2, 256);
   float* qkv = (float*)p; p += align_up((size_t)T * 3 * D * 4, 256);
   __nv_bfloat16* att = (__nv_bfloat16*)p; p += align_up(3 * (size_t)T * D * 2, 256);
-  __nv_bfloat16* hid = (__nv_bfloat16*)p;
+  __nv_bfloat16* hid = (__nv_bfloat16*)p; p += align_up(3 * (size_t)T * FF * 2, 256);
+  float* ffn_part = (float*)p;                                     // [<= SMs][128][256]
+  float* ffn_x1 = ffn_part + (size_t)device_sms() * LN_BM * FB_D;  // [tiles][128][256]
   const long long pl_TD = split == 3 ? (long long)T * D : 0, pl_TF = split == 3 ? (long long)T * FF : 0;
   const size_t o_out = (size_t)3 * D * D * split, o_l1 = o_out + (size_t)D * D * split,
                o_l2 = o_l1 + (size_t)FF * D * split;  // offsets of out_proj / linear1 / linear2 in a layer
@@ -1552,6 +1708,7 @@ int mpa_transformer_forward(const float* tokens, const unsigned char* valid, int
       fa.out_f32 = last ? out : nullptr;
       fa.M = T; fa.FF = FF; fa.eps = eps;
       fa.drop1 = site(l, 1); fa.drop_h = site(l, 2); fa.drop2 = site(l, 3);
+      fa.cl = ffn_cluster_size(T, FF); fa.part = ffn_part; fa.x1s = ffn_x1;
       rc = launch_ffn_block(att, wl + o_out, wl + o_l1, wl + o_l2, fa, stream);
       if (rc != MPA_OK) return rc;
       continue;
