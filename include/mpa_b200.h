@@ -184,6 +184,10 @@ int mpa_lsap_batched(const float* costs, const int32_t* cost_offsets, const int3
  * GEMMs run on tcgen05 tensor cores with bf16 operands and fp32 accumulation
  * (the reference's --fp16 autocast analogue); BatchNorm math is fp32. */
 size_t mpa_pointnet_workspace_bytes(int n_parts);
+/* Workspace with room for the activation stash (128 B per point, two buffers): the
+ * training launches then start from the previous launch's last operand tile instead of
+ * recomputing the earlier layers from the points.  Results are identical either way. */
+size_t mpa_pointnet_workspace_bytes_n(int n_parts, int N);
 int mpa_pointnet_forward(const float* pts, const float* valids, int n_parts, int N, int F,
                          const float* const* conv_w, const float* const* bn_gamma,
                          const float* const* bn_beta, float* const* bn_running_mean,

@@ -42,6 +42,7 @@ _SIGNATURES = {
     'mpa_geometric_losses_workspace_bytes': (c_size_t, [c_int] * 2),
     'mpa_geometric_losses': (c_int, [c_void_p] * 10 + [c_int] * 5 + [c_void_p] * 3 + [c_size_t, c_void_p]),
     'mpa_pointnet_workspace_bytes': (c_size_t, [c_int]),
+    'mpa_pointnet_workspace_bytes_n': (c_size_t, [c_int, c_int]),
     'mpa_pointnet_forward': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int] + [c_void_p] * 5 +
                              [c_int, ctypes.c_float, ctypes.c_float, c_void_p, c_void_p, c_size_t,
                               c_void_p]),

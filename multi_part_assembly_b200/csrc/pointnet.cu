@@ -72,6 +72,12 @@ struct PointNetArgs {
   unsigned* pmin;           // [n_parts, 256]
   int n_parts, N, F;        // F = channels of layer 5 (128 or 256)
   long long* dbg;           // optional cycle stamps (MPA_PN_DEBUG), nullptr in production
+  // activation stash (training launches 2..5, optional): launch p leaves the 64-channel bf16
+  // operand tile a_{p-1} it built for its last layer in global memory, as the exact shared
+  // memory image (8 KB per 64-point tile), and launch p+1 starts from it instead of
+  // recomputing layers 1..p-1 from the points.  Same operands, so the results are unchanged.
+  const uint4* stash_in;    // a_{PHASE-2} tiles or nullptr (start from the points)
+  uint4* stash_out;         // a_{PHASE-1} tiles or nullptr
 };
 
 __device__ __forceinline__ int pn_cout(int layer, int F) {  // layer 1..5
@@ -106,11 +112,15 @@ __global__ void __launch_bounds__(PN_THREADS, 1) pointnet_phase_kernel(PointNetA
     tc::fence_barrier_init();
   }
   __syncthreads();
+  // resuming from the stash (launches 4, 5): layers 1..PHASE-2 are not run; the first 32 KB of
+  // the weight region (images of layers 1 and 2) hold the pipelines' prefetch tiles instead
+  const bool resume = PHASE >= 4 && a.stash_in != nullptr;  // uniform
+  const uint32_t w_first = resume ? (uint32_t)(PHASE - 2) * PN_WTILE : 0u;
   if (tid == 0) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(&wbar)),
-                 "r"(W_BYTES)
+                 "r"(W_BYTES - w_first)
                  : "memory");
-    for (uint32_t off = 0; off < W_BYTES; off += PN_WTILE)
+    for (uint32_t off = w_first; off < W_BYTES; off += PN_WTILE)
       asm volatile(
           "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
               tc::smem_u32(wsm + off)),
@@ -195,18 +205,44 @@ __global__ void __launch_bounds__(PN_THREADS, 1) pointnet_phase_kernel(PointNetA
   const int worker = blockIdx.x * PN_GROUPS + g;
   const int n_workers = gridDim.x * PN_GROUPS;
 
-  for (long long tile = worker; tile < n_tiles; tile += n_workers) {
+  // tiles of this pipeline, padded parts skipped (uniform per pipeline)
+  auto next_tile = [&](long long tl) {
+    while (tl < n_tiles && a.valids != nullptr && a.valids[(int)(tl / tiles_per_part)] == 0.0f) tl += n_workers;
+    return tl;
+  };
+  // stash prefetch: the a_{PHASE-2} tile of the NEXT tile streams into this pipeline's 8 KB
+  // buffer (cp.async, 4 x 16 B per thread) while the current tile is in its later layers
+  uint8_t* pf = wsm + g * PN_ACT_KB;
+  static_assert(PN_GROUPS * PN_ACT_KB <= 2 * PN_WTILE, "prefetch tiles fit the images of layers 1 and 2");
+  auto prefetch = [&](long long tl) {
+    const uint4* src = a.stash_in + tl * (PN_ACT_KB / 16);
+#pragma unroll
+    for (int j = 0; j < PN_ACT_KB / 16 / 128; ++j)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(pf + (j * 128 + t) * 16)),
+                   "l"(src + j * 128 + t)
+                   : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  long long tile = next_tile(worker);
+  if (resume && tile < n_tiles) prefetch(tile);
+
+  for (; tile < n_tiles;) {
+    const long long tile_next = next_tile(tile + n_workers);
     const int part = (int)(tile / tiles_per_part);
-    if (a.valids != nullptr && a.valids[part] == 0.0f) continue;  // uniform per pipeline
     const int p0 = (int)(tile % tiles_per_part) * PN_TILE;
     const int npts = min(PN_TILE, a.N - p0);
 
     const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && tid == 0 && tile < 8 * n_workers;
     long long* dbg = a.dbg + (tile / n_workers) * 16;
     if (dbg_on) dbg[0] = clock64();
+    // the previous tile's stash copy read `act` with ordinary loads: all of them are done
+    if (PHASE <= 4 && a.stash_out != nullptr) tc::group_sync(1 + g, 128);
+    if (resume) {
+      // ---- B operand of layer PHASE-1: the prefetched a_{PHASE-2} tile, used in place ----
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else {
     // ---- layer-1 B operand, MN-major: row k = coordinate k of the TILE points
     // (rows 3..15 zero).  Thread i fills one 16-byte chunk: row i>>3, points 8*(i&7).. ----
-    {
       const int row = t >> 3, chunk = t & 7;
       uint32_t w[4] = {0u, 0u, 0u, 0u};
       if (row < 3) {
@@ -229,6 +265,8 @@ __global__ void __launch_bounds__(PN_THREADS, 1) pointnet_phase_kernel(PointNetA
 
 #pragma unroll
     for (int layer = 1; layer <= PHASE; ++layer) {
+      if (resume && layer < PHASE - 1) continue;  // their output came from the stash
+      const uint8_t* bsrc = (resume && layer == PHASE - 1) ? pf : act;
       const int K = layer == 1 ? 16 : (layer == 5 ? 128 : 64);
       const int mblocks = layer == 5 ? mblocks5 : 1;
       // ---- MMA issue (one thread) ----
@@ -239,7 +277,7 @@ __global__ void __launch_bounds__(PN_THREADS, 1) pointnet_phase_kernel(PointNetA
             const int kb = k >> 6, ks = k & 63;
             const uint32_t wa = tc::smem_u32(wsm) + pn_w_off(layer - 1) +
                                 (layer == 5 ? (mb * 2 + kb) * PN_WTILE : 0) + ks * 2;
-            const uint32_t ba = tc::smem_u32(act) + k * 128;  // 16 channel rows per K step
+            const uint32_t ba = tc::smem_u32(bsrc) + k * 128;  // 16 channel rows per K step
             tc::mma_bf16(tmem + (uint32_t)(mb * PN_TILE), tc::make_desc_sw128(wa),
                          tc::make_desc_sw128_mn(ba, 128 * 128), IDESC, k > 0 ? 1u : 0u);
           }
@@ -251,6 +289,7 @@ __global__ void __launch_bounds__(PN_THREADS, 1) pointnet_phase_kernel(PointNetA
       parity ^= 1u;
       tc::fence_after_sync();
       if (dbg_on) dbg[3 * (layer - 1) + 2] = clock64();  // accumulator complete
+      if (resume && layer == PHASE - 1 && tile_next < n_tiles) prefetch(tile_next);  // pf is free again
 
       // ---- epilogue ----
       // 64-channel layers: lanes 64..127 hold a copy of rows 0..63, so warps 2,3 take
@@ -284,6 +323,13 @@ __global__ void __launch_bounds__(PN_THREADS, 1) pointnet_phase_kernel(PointNetA
         tc::fence_async_smem();
         tc::fence_before_sync();
         tc::group_sync(1 + g, 128);
+        if (PHASE <= 4 && layer == PHASE - 1 && a.stash_out != nullptr) {
+          // a_{PHASE-1} (64 channels = K-block 0) -> global, coalesced, while the next MMA reads it
+          uint4* dstg = a.stash_out + tile * (PN_ACT_KB / 16);
+#pragma unroll
+          for (int j = 0; j < PN_ACT_KB / 16 / 128; ++j)
+            __stcs(dstg + j * 128 + t, *reinterpret_cast<const uint4*>(act + (j * 128 + t) * 16));
+        }
       } else {
         // statistics of this layer's pre-activations (+ max/min for layer 5)
 #pragma unroll
@@ -328,6 +374,7 @@ __global__ void __launch_bounds__(PN_THREADS, 1) pointnet_phase_kernel(PointNetA
       }
       if (dbg_on) dbg[3 * (layer - 1) + 3] = clock64();  // epilogue done
     }
+    tile = tile_next;
   }
 
   if (a.dbg != nullptr && blockIdx.x == 0 && tid == 0) {
@@ -476,6 +523,18 @@ using namespace mpa;
 
 extern "C" {
 
+size_t mpa_pointnet_workspace_bytes(int n_parts);
+static size_t pointnet_stash_bytes(int n_parts, int N) {  // one ping-pong buffer of a_k tiles
+  const size_t tiles = (size_t)n_parts * ((N + PN_TILE - 1) / PN_TILE);
+  return align_up(tiles * PN_ACT_KB, 256);
+}
+
+// with room for the activation stash of the training launches (2 buffers of 128 B per point)
+size_t mpa_pointnet_workspace_bytes_n(int n_parts, int N) {
+  if (n_parts <= 0) return 0;
+  return mpa_pointnet_workspace_bytes(n_parts) + 2 * pointnet_stash_bytes(n_parts, N);
+}
+
 size_t mpa_pointnet_workspace_bytes(int n_parts) {
   if (n_parts <= 0) return 0;
   size_t o = 0;
@@ -508,6 +567,10 @@ int mpa_pointnet_forward(const float* pts, const float* valids, int n_parts, int
   if (grid > 160) grid = 160;
   Scratch scratch;
   const size_t need = mpa_pointnet_workspace_bytes(n_parts);
+  // a caller that sized the workspace with mpa_pointnet_workspace_bytes_n gets the stash
+  static const bool no_stash = getenv("MPA_PN_NO_STASH") != nullptr;  // A/B switch
+  const bool stash = training && ws != nullptr && !no_stash &&
+                     ws_bytes >= mpa_pointnet_workspace_bytes_n(n_parts, N);
   int rc = scratch.acquire(ws, ws_bytes, need, stream);
   if (rc != MPA_OK) return rc;
   char* p = (char*)scratch.base;
@@ -516,7 +579,12 @@ int mpa_pointnet_forward(const float* pts, const float* valids, int n_parts, int
   float* shift = scale + 5 * PN_MAXC; p += align_up(sizeof(float) * 2 * 5 * PN_MAXC, 256);
   float* partial = (float*)p; p += align_up(sizeof(float) * 2 * PN_MAXC * 2 * 160 * PN_GROUPS, 256);
   unsigned* pmax = (unsigned*)p; p += align_up(sizeof(unsigned) * (size_t)n_parts * PN_MAXC, 256);
-  unsigned* pmin = (unsigned*)p;
+  unsigned* pmin = (unsigned*)p; p += align_up(sizeof(unsigned) * (size_t)n_parts * PN_MAXC, 256);
+  uint4* stash_buf[2] = {nullptr, nullptr};
+  if (stash) {
+    stash_buf[0] = (uint4*)p;
+    stash_buf[1] = (uint4*)(p + pointnet_stash_bytes(n_parts, N));
+  }
 
   MPA_CUDA(cudaMemsetAsync(image, 0, PN_W_BYTES, stream));
   {
@@ -554,6 +622,11 @@ int mpa_pointnet_forward(const float* pts, const float* valids, int n_parts, int
       a.beta_prev = layer > 0 ? bn_beta[layer - 1] : nullptr;
       a.rmean_prev = layer > 0 ? bn_running_mean[layer - 1] : nullptr;
       a.rvar_prev = layer > 0 ? bn_running_var[layer - 1] : nullptr;
+      // launch 3 stashes a_2 in buffer 0; launch 4 starts from it and stashes a_3 in buffer 1;
+      // launch 5 starts from a_3.  (Launch 3 itself runs from the points: skipping one layer
+      // does not pay for a 128 B/point round trip, measured.)
+      a.stash_out = (stash && (layer == 2 || layer == 3)) ? stash_buf[layer & 1] : nullptr;
+      a.stash_in = (stash && layer >= 3) ? stash_buf[(layer - 1) & 1] : nullptr;
       switch (layer) {
         case 0: rc = launch_phase<1>(a, grid, stream); break;
         case 1: rc = launch_phase<2>(a, grid, stream); break;
@@ -591,6 +664,7 @@ int mpa_pointnet_forward(const float* pts, const float* valids, int n_parts, int
     }
     a.partial = partial_buf[0];
     a.partial_in = partial_buf[1];
+    a.stash_in = nullptr; a.stash_out = nullptr;
     rc = launch_phase<5>(a, grid, stream);
     if (rc != MPA_OK) return rc;
   }

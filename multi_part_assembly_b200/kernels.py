@@ -176,7 +176,7 @@ class _PointNetFunction(torch.autograd.Function):
         dev = x.device
         feats = torch.empty(n, Fdim, dtype=torch.float32, device=dev)
         L = _lib.lib()
-        ws_bytes = L.mpa_pointnet_workspace_bytes(n)
+        ws_bytes = L.mpa_pointnet_workspace_bytes_n(n, N) if training else L.mpa_pointnet_workspace_bytes(n)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         w = [c.weight.detach().reshape(c.weight.shape[0], -1).float().contiguous() for c in convs]
         with torch.cuda.device(dev):
