@@ -62,6 +62,7 @@ struct PointNetArgs {
   float* scale_out;         // same arrays, written by CTA 0 for the layer finished here
   float* shift_out;
   const float* partial_in;  // [ctas, 256, 2] sum / sumsq of layer PHASE-1 (previous launch)
+  int partial_in_rows;      // rows of partial_in to add (0: gridDim.x)
   float* partial;           // [ctas, 256, 2] sum / sumsq of layer PHASE
   const float* gamma_prev;  // BatchNorm parameters of layer PHASE-1 (fused finalize) or nullptr
   const float* beta_prev;
@@ -146,7 +147,8 @@ __global__ void __launch_bounds__(PN_THREADS, 1) pointnet_phase_kernel(PointNetA
     // per-CTA partial sums of the previous launch: group g adds CTAs g, g+GROUPS, ...
     double s1 = 0.0, s2 = 0.0;
     if (t < CP) {
-      for (int b = g; b < (int)gridDim.x; b += PN_GROUPS) {
+      const int rows_in = a.partial_in_rows > 0 ? a.partial_in_rows : (int)gridDim.x;
+      for (int b = g; b < rows_in; b += PN_GROUPS) {
         s1 += (double)a.partial_in[((long long)b * PN_MAXC + t) * 2];
         s2 += (double)a.partial_in[((long long)b * PN_MAXC + t) * 2 + 1];
       }
@@ -404,9 +406,9 @@ __global__ void __launch_bounds__(PN_THREADS, 1) pointnet_phase_kernel(PointNetA
 }
 
 // fp32 conv weights [Cout, Cin] -> pre-swizzled bf16 smem image (zero-filled beforehand)
-__global__ void pointnet_fill_weights_kernel(const float* w1, const float* w2, const float* w3,
-                                             const float* w4, const float* w5, int F,
-                                             uint8_t* image) {
+__device__ __forceinline__ void pointnet_fill_weights(const float* w1, const float* w2, const float* w3,
+                                                      const float* w4, const float* w5, int F,
+                                                      uint8_t* image) {
   // one thread per (layer, out channel, in channel)
   const int cin[5] = {3, 64, 64, 64, 128};
   const int cout[5] = {64, 64, 64, 128, F};
@@ -472,12 +474,118 @@ __global__ void pointnet_eval_affine_kernel(const float* gamma, const float* bet
   shift[layer * PN_MAXC + c] = beta[c] - running_mean[c] * sc;
 }
 
-__global__ void pointnet_init_minmax_kernel(unsigned* pmax, unsigned* pmin, long long n) {
+__device__ __forceinline__ void pointnet_init_minmax(unsigned* pmax, unsigned* pmin, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     pmax[i] = 0u;           // below every encoded float
     pmin[i] = 0xffffffffu;  // above every encoded float
   }
+}
+
+// Statistics of the first layer without running it.  z = W_1 x is linear in the 3 coordinates,
+// so over all valid points  sum_c = w_c . S1  and  sumsq_c = w_c^T S2 w_c  with the first and
+// second moments S1 [3], S2 [3x3] of the (bf16-rounded, as the MMA sees them) points.  One pass
+// over 12 B/point replaces launch 1 (a K=16 MMA + epilogue per tile).  Every CTA writes its
+// partial moments; the last one to finish (ticket) adds them in a fixed order in fp64 and emits
+// the two rows (hi, lo floats of the fp64 sums) launch 2 reads as `partial_in`.
+// The same launch packs the weight image and initialises the pooling extrema (the three
+// preparations are independent; as separate launches they were 22 us in a row).
+constexpr int PN_MOM_THREADS = 256;
+struct PointNetPrepArgs {
+  const float* w[5]; int F; uint8_t* image;        // weight image (zero-filled beforehand)
+  unsigned* pmax; unsigned* pmin; long long n_mm;  // pooling extrema
+  const float* pts; const float* valids; int n_parts, N;
+  double* mom; unsigned* ticket; float* partial_out;  // moments: partial_out == nullptr skips them
+};
+__global__ void __launch_bounds__(PN_MOM_THREADS)
+pointnet_prepare_kernel(PointNetPrepArgs pa) {
+  pointnet_fill_weights(pa.w[0], pa.w[1], pa.w[2], pa.w[3], pa.w[4], pa.F, pa.image);
+  pointnet_init_minmax(pa.pmax, pa.pmin, pa.n_mm);
+  if (pa.partial_out == nullptr) return;
+  const float* __restrict__ pts = pa.pts;
+  const float* __restrict__ valids = pa.valids;
+  const int n_parts = pa.n_parts, N = pa.N;
+  const float* __restrict__ w1 = pa.w[0];
+  double* __restrict__ mom = pa.mom;
+  unsigned* __restrict__ ticket = pa.ticket;
+  float* __restrict__ partial_out = pa.partial_out;
+  __shared__ double red[PN_MOM_THREADS / 32][9];
+  __shared__ double tot[9];
+  __shared__ bool last;
+  float m[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // x y z xx xy xz yy yz zz
+  auto add_point = [&](float fx, float fy, float fz) {
+    const float x = __bfloat162float(__float2bfloat16_rn(fx));
+    const float y = __bfloat162float(__float2bfloat16_rn(fy));
+    const float z = __bfloat162float(__float2bfloat16_rn(fz));
+    m[0] += x; m[1] += y; m[2] += z;
+    m[3] = fmaf(x, x, m[3]); m[4] = fmaf(x, y, m[4]); m[5] = fmaf(x, z, m[5]);
+    m[6] = fmaf(y, y, m[6]); m[7] = fmaf(y, z, m[7]); m[8] = fmaf(z, z, m[8]);
+  };
+  // a CTA takes whole parts (one validity test per part); a thread takes 4 consecutive points =
+  // three 16-byte loads when the part's rows are 16-byte aligned
+  for (int part = blockIdx.x; part < n_parts; part += gridDim.x) {
+    if (valids != nullptr && valids[part] == 0.0f) continue;
+    const float* pp = pts + (long long)part * N * 3;
+    const bool vec = ((N & 3) == 0) && ((reinterpret_cast<uintptr_t>(pp) & 15) == 0);
+    if (vec) {
+      for (int q = threadIdx.x; q < N / 4; q += blockDim.x) {
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(pp) + 3 * q);
+        const float4 a1 = __ldg(reinterpret_cast<const float4*>(pp) + 3 * q + 1);
+        const float4 a2 = __ldg(reinterpret_cast<const float4*>(pp) + 3 * q + 2);
+        add_point(a0.x, a0.y, a0.z);
+        add_point(a0.w, a1.x, a1.y);
+        add_point(a1.z, a1.w, a2.x);
+        add_point(a2.y, a2.z, a2.w);
+      }
+    } else {
+      for (int i = threadIdx.x; i < N; i += blockDim.x) add_point(pp[3 * i], pp[3 * i + 1], pp[3 * i + 2]);
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    double v = (double)m[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    double v = 0.0;
+    for (int w = 0; w < PN_MOM_THREADS / 32; ++w) v += red[w][threadIdx.x];
+    mom[(long long)blockIdx.x * 9 + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  // warp w adds moment w (warp 0 also moment 8) over the CTAs: lanes stride, then a fixed tree
+  for (int k = warp; k < 9; k += PN_MOM_THREADS / 32) {
+    double v = 0.0;
+    for (unsigned b = lane; b < gridDim.x; b += 32) v += __ldcg(mom + (long long)b * 9 + k);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) tot[k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {  // channel of layer 1
+    const int c = threadIdx.x;
+    const double w0 = (double)__bfloat162float(__float2bfloat16_rn(w1[3 * c]));
+    const double wa = (double)__bfloat162float(__float2bfloat16_rn(w1[3 * c + 1]));
+    const double wb = (double)__bfloat162float(__float2bfloat16_rn(w1[3 * c + 2]));
+    const double* S = tot;
+    const double s1 = w0 * S[0] + wa * S[1] + wb * S[2];
+    const double s2 = w0 * w0 * S[3] + wa * wa * S[6] + wb * wb * S[8] +
+                      2.0 * (w0 * wa * S[4] + w0 * wb * S[5] + wa * wb * S[7]);
+    const float h1 = (float)s1, h2 = (float)s2;
+    partial_out[(0 * PN_MAXC + c) * 2] = h1;
+    partial_out[(0 * PN_MAXC + c) * 2 + 1] = h2;
+    partial_out[(1 * PN_MAXC + c) * 2] = (float)(s1 - (double)h1);
+    partial_out[(1 * PN_MAXC + c) * 2 + 1] = (float)(s2 - (double)h2);
+  }
+  if (threadIdx.x == 0) *ticket = 0u;  // ready for the next forward (graph replays included)
 }
 
 // feats[part, c] = max_n BN5(y)[c] = scale*max + shift (scale >= 0) or scale*min + shift
@@ -538,7 +646,7 @@ size_t mpa_pointnet_workspace_bytes_n(int n_parts, int N) {
 size_t mpa_pointnet_workspace_bytes(int n_parts) {
   if (n_parts <= 0) return 0;
   size_t o = 0;
-  o += align_up(PN_W_BYTES, 256);                                   // weight image
+  o += align_up(PN_W_BYTES, 256) + 256;                             // weight image, ticket of the moments kernel
   o += align_up(sizeof(float) * 2 * 5 * PN_MAXC, 256);              // scale, shift
   o += align_up(sizeof(float) * 2 * PN_MAXC * 2 * 160 * PN_GROUPS, 256);  // partial (<=160 CTAs)
   o += 2 * align_up(sizeof(unsigned) * (size_t)n_parts * PN_MAXC, 256);   // pmax, pmin
@@ -575,6 +683,7 @@ int mpa_pointnet_forward(const float* pts, const float* valids, int n_parts, int
   if (rc != MPA_OK) return rc;
   char* p = (char*)scratch.base;
   uint8_t* image = (uint8_t*)p; p += align_up(PN_W_BYTES, 256);
+  unsigned* ticket = (unsigned*)p; p += 256;  // zeroed together with the image
   float* scale = (float*)p;
   float* shift = scale + 5 * PN_MAXC; p += align_up(sizeof(float) * 2 * 5 * PN_MAXC, 256);
   float* partial = (float*)p; p += align_up(sizeof(float) * 2 * PN_MAXC * 2 * 160 * PN_GROUPS, 256);
@@ -586,16 +695,18 @@ int mpa_pointnet_forward(const float* pts, const float* valids, int n_parts, int
     stash_buf[1] = (uint4*)(p + pointnet_stash_bytes(n_parts, N));
   }
 
-  MPA_CUDA(cudaMemsetAsync(image, 0, PN_W_BYTES, stream));
+  MPA_CUDA(cudaMemsetAsync(image, 0, PN_W_BYTES + 256, stream));
+  static const bool run_phase1 = getenv("MPA_PN_PHASE1") != nullptr;  // A/B: layer-1 statistics by the MMA launch
+  PointNetPrepArgs pa{};
+  for (int i = 0; i < 5; ++i) pa.w[i] = conv_w[i];
+  pa.F = F; pa.image = image; pa.pmax = pmax; pa.pmin = pmin; pa.n_mm = (long long)n_parts * PN_MAXC;
+  pa.pts = pts; pa.valids = valids; pa.n_parts = n_parts; pa.N = N;
+  pa.mom = (double*)(partial + (size_t)2 * 2 * PN_MAXC * 160);  // slack of the partial region: [2 sms][9]
+  pa.ticket = ticket;
+  pa.partial_out = (training && !run_phase1) ? partial : nullptr;  // = partial_buf[0], what launch 1 would write
   {
-    ProfScope ps("pointnet_pack_weights", stream);
-    pointnet_fill_weights_kernel<<<64, 256, 0, stream>>>(conv_w[0], conv_w[1], conv_w[2], conv_w[3],
-                                                         conv_w[4], F, image);
-  }
-  MPA_LAUNCH_CHECK();
-  {
-    ProfScope ps("pointnet_init_minmax", stream);
-    pointnet_init_minmax_kernel<<<256, 256, 0, stream>>>(pmax, pmin, (long long)n_parts * PN_MAXC);
+    ProfScope ps("pointnet_prepare", stream);
+    pointnet_prepare_kernel<<<2 * sms, PN_MOM_THREADS, 0, stream>>>(pa);
   }
   MPA_LAUNCH_CHECK();
 
@@ -607,6 +718,7 @@ int mpa_pointnet_forward(const float* pts, const float* valids, int n_parts, int
   }
   // per-CTA partial sums, double buffered: launch l reads what launch l-1 wrote
   float* partial_buf[2] = {partial, partial + (size_t)2 * PN_MAXC * 160};
+
   PointNetArgs a{};
   a.pts = pts; a.valids = valids; a.wimage = (const uint4*)image;
   a.scale = scale; a.shift = shift; a.scale_out = scale; a.shift_out = shift;
@@ -627,6 +739,9 @@ int mpa_pointnet_forward(const float* pts, const float* valids, int n_parts, int
       // does not pay for a 128 B/point round trip, measured.)
       a.stash_out = (stash && (layer == 2 || layer == 3)) ? stash_buf[layer & 1] : nullptr;
       a.stash_in = (stash && layer >= 3) ? stash_buf[(layer - 1) & 1] : nullptr;
+      a.partial_in_rows = 0;
+      if (layer == 0 && !run_phase1) continue;  // layer-1 statistics came from the moments of the points
+      if (layer == 1 && !run_phase1) a.partial_in_rows = 2;
       switch (layer) {
         case 0: rc = launch_phase<1>(a, grid, stream); break;
         case 1: rc = launch_phase<2>(a, grid, stream); break;
