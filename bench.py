@@ -393,7 +393,9 @@ def run_native(args):
 
     # e2e: every step copies ITS batch from pinned host memory and reads its loss back.
     # With the graph runtime the copy of batch k+1 is issued before step k runs (input
-    # prefetch on a side stream, as a data loader does), so it overlaps the compute.
+    # prefetch on a side stream, as a data loader does), so it overlaps the compute, and the
+    # loss of step k lands in pinned host memory asynchronously: the host reads it after it
+    # has enqueued step k+1 (a loop that logs one step late), so the GPU never waits for Python.
     def e2e_loop(steps):
         """K end-to-end steps; returns the summed CUDA-event time of the steps."""
         starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
@@ -403,15 +405,19 @@ def run_native(args):
             flush.zero_()
             starts[0].record()
             graphed.prefetch(hosts[0])
+            pending = None
             for i in range(steps):
-                out = graphed.run_prefetched()
-                if i + 1 < steps:
-                    graphed.prefetch(hosts[(i + 1) % 2])  # next batch's H2D overlaps this step
-                float(out['loss'])                         # D2H of this step's result
+                graphed.run_prefetched()
+                read = graphed.read_async('loss')          # D2H of this step's result (pinned, async)
                 stops[i].record()
                 if i + 1 < steps:
+                    graphed.prefetch(hosts[(i + 1) % 2])  # next batch's H2D overlaps this step
                     flush.zero_()
                     starts[i + 1].record()
+                if pending is not None:
+                    pending.value()                        # the host looks at step i-1's loss now
+                pending = read
+            pending.value()
         else:
             for i in range(steps):
                 flush.zero_()

@@ -30,6 +30,30 @@ def _check_capturable(model):
                              'is drawn from the CPU generator and would be baked into the graph')
 
 
+def _flat_views(example, device):
+    """One contiguous device buffer holding a tensor per entry of `example` (256-byte aligned
+    views): a whole batch then moves between staging and static inputs with ONE copy."""
+    offs, total = {}, 0
+    for k, v in example.items():
+        offs[k] = total
+        total += (v.numel() * v.element_size() + 255) // 256 * 256
+    flat = torch.empty(max(total, 256), dtype=torch.uint8, device=device)
+    views = {k: flat[offs[k]:offs[k] + v.numel() * v.element_size()].view(v.dtype).view(v.shape)
+             for k, v in example.items()}
+    return flat, views
+
+
+class _HostRead:
+    """A device->host copy in flight (pinned destination + event); `value()` waits for it."""
+
+    def __init__(self, host, event):
+        self._host, self._event = host, event
+
+    def value(self):
+        self._event.synchronize()
+        return float(self._host)
+
+
 class GraphedStep:
 
     def __init__(self, model, example_batch, mode='train', autocast_dtype=torch.bfloat16,
@@ -40,7 +64,9 @@ class GraphedStep:
         self.autocast_dtype = autocast_dtype
         dev = next(model.parameters()).device
         self.device = dev
-        self.static_in = {k: v.to(dev).clone() for k, v in example_batch.items()}
+        self._static_flat, self.static_in = _flat_views(example_batch, dev)
+        for k, v in example_batch.items():
+            self.static_in[k].copy_(v)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -81,8 +107,9 @@ class GraphedStep:
         side stream.  Call `run_prefetched()` afterwards to step on it."""
         if not hasattr(self, '_copy_stream'):
             self._copy_stream = torch.cuda.Stream(device=self.device)
-            self._staging = [{k: torch.empty_like(v) for k, v in self.static_in.items()}
-                             for _ in range(2)]
+            flats = [_flat_views(self.static_in, self.device) for _ in range(2)]
+            self._staging_flat = [f for f, _ in flats]
+            self._staging = [v for _, v in flats]
             self._staged = [None, None]
             self._slot = 0
         slot = self._slot
@@ -101,13 +128,26 @@ class GraphedStep:
         slot, ready = self._pending
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(ready)
-        for k, dst in self.static_in.items():
-            dst.copy_(self._staging[slot][k], non_blocking=True)  # device-to-device, a few us
+        self._static_flat.copy_(self._staging_flat[slot], non_blocking=True)  # ONE device-to-device copy
         consumed = torch.cuda.Event()
         consumed.record(cur)
         self._staged[slot] = consumed
         self.graph.replay()
         return self.static_out
+
+    def read_async(self, key='loss'):
+        """Start the device->host copy of one scalar output of the step just replayed and
+        return a handle; `handle.value()` waits for that copy only.  Lets the host enqueue the
+        next step before it looks at this one's loss (a training loop that logs one step late)."""
+        if not hasattr(self, '_host_ring'):
+            self._host_ring = [torch.empty((), dtype=torch.float32, pin_memory=True) for _ in range(4)]
+            self._host_slot = 0
+        host = self._host_ring[self._host_slot]
+        self._host_slot = (self._host_slot + 1) % len(self._host_ring)
+        host.copy_(self.static_out[key].detach().reshape(()).float(), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        return _HostRead(host, ev)
 
 
 def allreduce_gradients(params, group=None):
