@@ -341,8 +341,9 @@ def run_native(args):
         return stack.max(0)[0].tolist(), stack.t().tolist()
 
     def setup(model_name, encoder, per_gpu, valid, points, seed, dataset='everyday'):
-        """Model + pinned host batches + the stepping functions for one workload."""
-        torch.manual_seed(seed)
+        """Model + pinned host batches + the stepping functions for one workload.  The weights
+        are the same on every rank (as under DDP); `seed` selects the rank's data."""
+        torch.manual_seed(0)
         cfg = get_cfg(model_name, dataset, encoder=encoder)
         model = no_dropout(build_model(cfg)).to(dev).train()
         model.trainer = Trainer()
@@ -372,7 +373,13 @@ def run_native(args):
 
     per_gpu = c['batch'] // world if c['scaling'] == 'strong' else c['batch']
     assert per_gpu >= 1, 'more ranks than shapes'
-    w = setup(c['model'], c['encoder'], per_gpu, c['valid'], args.points, rank,
+    # Weak scaling: every rank steps the SAME synthetic batch.  The cost of the exact Chamfer
+    # search depends on the geometry (+-10 % between random batches, profiles/r02_bench_n8.json),
+    # and the max over ranks of N different draws would read as a scaling loss that is not one:
+    # there is no collective in this step.  Strong scaling (cfg E) slices one global batch, so
+    # its ranks necessarily hold different shapes.
+    data_seed = rank if c['scaling'] == 'strong' else 0
+    w = setup(c['model'], c['encoder'], per_gpu, c['valid'], args.points, data_seed,
               c.get('dataset', 'everyday'))
     model, hosts, resident, graphed = w['model'], w['hosts'], w['resident'], w['graphed']
     eager_step, step, graph_error = w['eager_step'], w['step'], w['graph_error']
@@ -490,7 +497,7 @@ def run_native(args):
             saved = amp
             amp = torch.bfloat16 if oc['dtype'] == 'bf16' else None  # setup()/eager_step read `amp`
             try:
-                we = setup(oc['model'], oc['encoder'], oc['batch'], oc['valid'], oc['points'], rank)
+                we = setup(oc['model'], oc['encoder'], oc['batch'], oc['valid'], oc['points'], 0)
                 k_o = max(5, min(args.steps, 20))
                 for _ in range(3):
                     we['step']()
@@ -612,6 +619,9 @@ def run_native(args):
                    'l2': 'flushed (192 MiB memset) before every timed step',
                    'mode': 'training-mode forward (BatchNorm batch statistics) + all loss terms, '
                            'no autograd recording, dropout 0',
+                   'rank_data': ('one global batch sliced over the ranks' if c['scaling'] == 'strong' else
+                                 'same weights and same synthetic batch on every rank (no collective in '
+                                 'fwd+loss; the search cost is data dependent)'),
                    'cuda_graph': graphed is not None, 'graph_error': graph_error},
         'clocks': clocks,
         'e2e': {'value': shapes / (ms_e2e / 1e3), 'unit': 'shapes/s',

@@ -298,6 +298,10 @@ int mpa_transformer_forward(const float* tokens, const unsigned char* valid, int
  * their idx rows are left untouched -- so the caller never compacts on the host
  * (the reference's boolean-mask gather, models/dgl/network.py:90-99). */
 size_t mpa_knn_workspace_bytes(int n, int N);
+/* Workspace that also holds the operand planes and the score slab of the tensor-core
+ * scoring path (tcgen05 candidate filter + exact decision at the k-th boundary, same index
+ * sets); with the smaller size above mpa_knn runs the CUDA-core tile kernel. */
+size_t mpa_knn_workspace_bytes_c(int n, int N, int C);
 int mpa_knn(const float* x, const float* valids, int n, int N, int C, int k, int32_t* idx, void* ws,
             size_t ws_bytes, void* stream);
 

@@ -69,6 +69,7 @@ _SIGNATURES = {
                                 [ctypes.c_float, ctypes.c_float, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                  c_size_t, c_void_p]),
     'mpa_knn_workspace_bytes': (c_size_t, [c_int] * 2),
+    'mpa_knn_workspace_bytes_c': (c_size_t, [c_int] * 3),
     'mpa_knn': (c_int, [c_void_p, c_void_p] + [c_int] * 4 + [c_void_p, c_void_p, c_size_t, c_void_p]),
     'mpa_edge_aggregate_workspace_bytes': (c_size_t, [ctypes.c_longlong, c_int]),
     'mpa_edge_aggregate': (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p] * 4 +

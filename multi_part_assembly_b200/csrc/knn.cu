@@ -393,6 +393,211 @@ knn_tile_kernel(const float* __restrict__ x, const float* __restrict__ xx,
   }
 }
 
+// ---- tensor-core variant: tcgen05 candidate filter + exact decision at the boundary ------
+// The score matrix is a Gram matrix, so the contraction belongs on the tensor cores; what
+// must not change is the RESULT, the oracle's top-k set under its own fp32 arithmetic
+// (sequential-k FMA, dgcnn.py:8-15).  Per chunk of parts:
+//   1. `launch_gram_batched` (csrc/linear.cu, three bf16 planes per operand = fp32-accurate):
+//      t_ij = x_i . x_j - |x_j|^2 / 2, which orders the candidates of row i like the score does;
+//   2. `knn_select_kernel`, one warp per row at full occupancy: lane maxima -> lower bound of
+//      the k-th best -> candidates within `delta` of it (delta bounds twice the worst
+//      difference between t and the oracle's score / 2: tensor-core accumulation, dropped
+//      plane products, the oracle's own roundings, all <= alpha (|x_i|^2 + max_j |x_j|^2)) ->
+//      one 64-key sort.  If the k-th and (k+1)-th approximate scores are more than delta apart
+//      the approximate top k IS the oracle's set.  Otherwise the candidates within delta of the
+//      k-th are re-scored exactly as the oracle scores them and the boundary is decided on
+//      those values (ties -> lower index).  More than 64 candidates: the row is re-scored
+//      exactly as a whole and selected by arg-max rounds.
+// Only the set is contractual (EdgeConv takes a max over the k edges); the order written is
+// approximate-score order with the exactly decided boundary members last.
+// One pass over x: |x|^2 in the oracle's order (sequential-k FMA), -|x|^2 / 2 (the bias of the Gram
+// products), the per-part maximum, and the three bf16 operand planes [3][rows][Kp] (hi, mid, lo;
+// channels >= C zero).  A warp takes 32 rows: coalesced loads into a padded shared-memory tile, the
+// planes leave coalesced as well, then lane r walks row r.
+constexpr int KP_THREADS = 256;
+constexpr int KP_CC = 32;  // channels per tile pass
+__global__ void __launch_bounds__(KP_THREADS)
+knn_prepare_kernel(const float* __restrict__ x, long long rows, int N, int C, int Kp,
+                   float* __restrict__ xx, float* __restrict__ hb, unsigned* __restrict__ xxmax,
+                   __nv_bfloat16* __restrict__ planes) {
+  __shared__ float tile[KP_THREADS / 32][32][KP_CC + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long plane = rows * (long long)Kp;
+  const long long n_blocks = (rows + 31) / 32;
+  for (long long blk = (long long)blockIdx.x * (KP_THREADS / 32) + warp; blk < n_blocks;
+       blk += (long long)gridDim.x * (KP_THREADS / 32)) {
+    const long long r0 = blk * 32;
+    float s = 0.f;
+    for (int c0 = 0; c0 < Kp; c0 += KP_CC) {
+      // rows r0 .. r0+31, channels c0 .. c0+31: 8 lanes x 4 channels per row, 4 rows per instruction
+      const bool vec = (C & 3) == 0 && (Kp & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+      for (int it = 0; it < 8; ++it) {
+        const int rr = it * 4 + (lane >> 3);
+        const long long r = r0 + rr;
+        const int c = c0 + 4 * (lane & 7);
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (r < rows) {
+          if (vec && c + 3 < C) {
+            const float4 q4 = *reinterpret_cast<const float4*>(x + r * C + c);
+            v[0] = q4.x; v[1] = q4.y; v[2] = q4.z; v[3] = q4.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (c + e < C) v[e] = x[r * C + c + e];
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) tile[warp][rr][4 * (lane & 7) + e] = v[e];
+        if (r < rows && c < Kp) {  // Kp is a multiple of 8: the whole quad is inside
+          const long long eo = r * Kp + c;
+#pragma unroll
+          for (int pl = 0; pl < 3; ++pl) {
+            __nv_bfloat16 h[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              h[e] = __float2bfloat16_rn(v[e]);
+              v[e] -= __bfloat162float(h[e]);
+            }
+            *reinterpret_cast<uint2*>(planes + pl * plane + eo) = *reinterpret_cast<const uint2*>(h);
+          }
+        }
+      }
+      __syncwarp();
+      const int cn = min(KP_CC, C - c0);
+      for (int c = 0; c < cn; ++c) s = __fmaf_rn(tile[warp][lane][c], tile[warp][lane][c], s);  // ascending channels
+      __syncwarp();
+    }
+    const long long r = r0 + lane;
+    if (r < rows) {
+      xx[r] = s;
+      hb[r] = -0.5f * s;
+    }
+    // per-part maximum: one atomic per warp and part (a 32-row block touches at most two parts when N >= 32)
+    const int part = r < rows ? (int)(r / N) : -1;
+    const int part0 = __shfl_sync(0xffffffffu, part, 0);
+    const bool uniform = __all_sync(0xffffffffu, part == part0);
+    if (uniform) {
+      float m = s;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (lane == 0 && part0 >= 0) atomicMax(xxmax + part0, __float_as_uint(m));
+    } else if (part >= 0) {
+      atomicMax(xxmax + part, __float_as_uint(s));  // s >= 0: unsigned order = float order
+    }
+  }
+}
+
+// the oracle's score of the pair (i, j): sequential-k FMA, then dgcnn.py:10,12
+__device__ __forceinline__ float knn_exact_score(const float* __restrict__ xi, const float* __restrict__ xj,
+                                                 int C, float xxi, float xxj) {
+  float acc = 0.f;
+  for (int c = 0; c < C; ++c) acc = __fmaf_rn(xi[c], xj[c], acc);
+  const float inner = __fmul_rn(-2.0f, acc);
+  return __fsub_rn(__fsub_rn(-xxj, inner), xxi);
+}
+__device__ __forceinline__ float knn_key_value(unsigned long long key) {
+  const unsigned o = (unsigned)(key >> 32);
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+__device__ __forceinline__ int knn_key_index(unsigned long long key) { return (int)(~(unsigned)(key & 0xffffffffull)); }
+
+constexpr int KS_THREADS = 256;
+__global__ void __launch_bounds__(KS_THREADS)
+knn_select_kernel(float* __restrict__ S, int z0, int items, const float* __restrict__ x,
+                  const float* __restrict__ xx, const unsigned* __restrict__ xxmax,
+                  const float* __restrict__ valids, int N, int C, int k, float alpha, int* __restrict__ idx) {
+  __shared__ unsigned long long cbuf[KS_THREADS / 32][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long row_local = (long long)blockIdx.x * (KS_THREADS / 32) + warp;
+  if (row_local >= (long long)items * N) return;
+  const int part = z0 + (int)(row_local / N), i = (int)(row_local % N);
+  if (valids != nullptr && valids[part] == 0.0f) return;
+  float* Sr = S + row_local * N;
+  const float ninf = -__int_as_float(0x7f800000);
+  unsigned long long* wb = cbuf[warp];
+  float v[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    const int j = lane + 32 * c;
+    v[c] = j < N ? __ldcs(Sr + j) : ninf;
+  }
+  float mv = v[0];
+  int mc = 0;
+#pragma unroll
+  for (int c = 1; c < 32; ++c)
+    if (v[c] > mv) { mv = v[c]; mc = c; }
+  unsigned long long t = (lane + 32 * mc < N) ? knn_key(mv, lane + 32 * mc) : 0ull;
+  knn_sort32(t, lane);
+  const unsigned long long T0 = __shfl_sync(0xffffffffu, t, k - 1);  // <= the k-th best approximate key
+  const float xxi = xx[(long long)part * N + i];
+  const float delta = alpha * (xxi + __uint_as_float(xxmax[part]));
+  const float thr = T0 != 0ull ? knn_key_value(T0) - delta : ninf;  // fewer than k lane maxima: keep all
+  int cnt = 0;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) cnt += (lane + 32 * c < N && v[c] >= thr) ? 1 : 0;
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  int* out = idx + ((long long)part * N + i) * k;
+  const float* xp = x + (long long)part * N * C;
+  const float* xxp = xx + (long long)part * N;
+  if (total <= 64) {
+    int off = incl - cnt;
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      const int j = lane + 32 * c;
+      if (j < N && v[c] >= thr) wb[off++] = knn_key(v[c], j);
+    }
+    __syncwarp();
+    unsigned long long r0 = lane < total ? wb[lane] : 0ull;
+    unsigned long long r1 = lane + 32 < total ? wb[lane + 32] : 0ull;
+    if (total <= 32) knn_sort32(r0, lane);  // warp-uniform; the common case
+    else knn_sort64(r0, r1, lane);          // approximate order, best first
+    const float tk = knn_key_value(__shfl_sync(0xffffffffu, r0, k - 1));
+    const unsigned long long next = k < 32 ? __shfl_sync(0xffffffffu, r0, k & 31) : __shfl_sync(0xffffffffu, r1, 0);
+    const bool clear = total <= k || next == 0ull || tk - knn_key_value(next) > delta;
+    if (clear) {  // the k-th and (k+1)-th are further apart than any rounding can move them
+      if (lane < k) out[lane] = knn_key_index(r0);
+      return;
+    }
+    // boundary decision on exact scores: `sure` = beats the k-th by more than delta (a prefix of
+    // the sorted list, < k long), `band` = within delta of the k-th (the positions after it)
+    const float hi = tk + delta, lo = tk - delta;
+    const bool s0 = r0 != 0ull && knn_key_value(r0) > hi, s1 = r1 != 0ull && knn_key_value(r1) > hi;
+    const bool b0 = r0 != 0ull && !s0 && knn_key_value(r0) >= lo, b1 = r1 != 0ull && !s1 && knn_key_value(r1) >= lo;
+    const int m = __popc(__ballot_sync(0xffffffffu, s0)) + __popc(__ballot_sync(0xffffffffu, s1));
+    const int nb = __popc(__ballot_sync(0xffffffffu, b0)) + __popc(__ballot_sync(0xffffffffu, b1));
+    __syncwarp();
+    wb[lane] = r0;
+    wb[lane + 32] = r1;
+    __syncwarp();
+    unsigned long long e0 = 0ull, e1 = 0ull;
+    if (lane < nb) {
+      const int j = knn_key_index(wb[m + lane]);
+      e0 = knn_key(knn_exact_score(xp + (long long)i * C, xp + (long long)j * C, C, xxi, xxp[j]), j);
+    }
+    if (lane + 32 < nb) {
+      const int j = knn_key_index(wb[m + lane + 32]);
+      e1 = knn_key(knn_exact_score(xp + (long long)i * C, xp + (long long)j * C, C, xxi, xxp[j]), j);
+    }
+    knn_sort64(e0, e1, lane);  // exact order of the band, best first
+    const unsigned long long pick = __shfl_sync(0xffffffffu, e0, (lane - m) & 31);  // k - m <= 32
+    if (lane < m) out[lane] = knn_key_index(r0);
+    else if (lane < k) out[lane] = knn_key_index(pick);
+    return;
+  }
+  // more than 64 candidates (massive ties / adversarial layouts): exact scores for the row
+  for (int j = lane; j < N; j += 32)
+    Sr[j] = knn_exact_score(xp + (long long)i * C, xp + (long long)j * C, C, xxi, xxp[j]);
+  __syncwarp();
+  knn_select_slow(Sr, N, k, lane, out);
+}
+
 // uv [M, 2*Co] (u | v), idx [M, k] (indices local to the part), M = n*N.
 // One CTA per PTS points, thread = channel.  ymax/ymin [M, Co]; partial [gridDim, Co, 2].
 constexpr int EC_PTS = 8;
@@ -625,6 +830,59 @@ size_t mpa_knn_workspace_bytes(int n, int N) {
          sizeof(float) * (size_t)knn_tile_ctas() * KT * Np;   // per-CTA score slabs (L2-resident)
 }
 
+// workspace of the tensor-core path: xx, hb, per-part max, operand planes, score slab of one chunk
+static int knn_kpad(int C) { return (C + 7) & ~7; }
+static int knn_chunk_items(int n, int N) {
+  const size_t per_item = sizeof(float) * (size_t)N * N;
+  size_t items = ((size_t)96 << 20) / per_item;  // ~96 MB of scores in flight: stays in the 126 MB L2
+  if (items < 1) items = 1;
+  if (items > (size_t)n) items = n;
+  return (int)items;
+}
+size_t mpa_knn_workspace_bytes_c(int n, int N, int C) {
+  const size_t rows = (size_t)n * N;
+  return mpa_knn_workspace_bytes(n, N) + 2 * align_up(sizeof(float) * rows, 256) + align_up(sizeof(unsigned) * n, 256) +
+         align_up((size_t)3 * rows * knn_kpad(C) * 2, 256) +
+         align_up(sizeof(float) * (size_t)knn_chunk_items(n, N) * N * N, 256);
+}
+
+static int knn_tensor_core(const float* x, const float* valids, int n, int N, int C, int k, int32_t* idx, char* p,
+                           cudaStream_t stream) {
+  const long long rows = (long long)n * N;
+  const int Kp = knn_kpad(C);
+  float* xx = (float*)p; p += align_up(sizeof(float) * rows, 256);
+  float* hb = (float*)p; p += align_up(sizeof(float) * rows, 256);
+  unsigned* xxmax = (unsigned*)p; p += align_up(sizeof(unsigned) * n, 256);
+  __nv_bfloat16* planes = (__nv_bfloat16*)p; p += align_up((size_t)3 * rows * Kp * 2, 256);
+  float* S = (float*)p;
+  MPA_CUDA(cudaMemsetAsync(xxmax, 0, sizeof(unsigned) * n, stream));
+  {
+    ProfScope ps("knn_prepare", stream);
+    knn_prepare_kernel<<<2 * device_sms(), KP_THREADS, 0, stream>>>(x, rows, N, C, Kp, xx, hb, xxmax, planes);
+  }
+  MPA_LAUNCH_CHECK();
+  // bound of (approximate - exact) / (|x_i|^2 + |x_j|^2), in units of the approximate score:
+  // 6 plane products x Kp/16 accumulation steps of the tensor core (4 ulp each, generous),
+  // the bias subtraction, and the oracle's own C + 8 roundings
+  // (x 2: both sides of a comparison may be off)
+  const float alpha =
+      2.0f * ((6.0f * (float)(Kp / 16 + 1) * 4.0f + 2.0f) * 1.1920929e-7f + (float)(C + 8) * 5.9604645e-8f);
+  const int chunk = knn_chunk_items(n, N);
+  for (int z0 = 0; z0 < n; z0 += chunk) {
+    const int items = n - z0 < chunk ? n - z0 : chunk;
+    int rc = launch_gram_batched(planes, rows, N, Kp, z0, items, hb, S, "knn_gram", stream);
+    if (rc != MPA_OK) return rc;
+    {
+      ProfScope ps("knn_select", stream);
+      const long long nrows = (long long)items * N;
+      knn_select_kernel<<<(unsigned)((nrows + KS_THREADS / 32 - 1) / (KS_THREADS / 32)), KS_THREADS, 0, stream>>>(
+          S, z0, items, x, xx, xxmax, valids, N, C, k, alpha, idx);
+    }
+    MPA_LAUNCH_CHECK();
+  }
+  return MPA_OK;
+}
+
 int mpa_knn(const float* x, const float* valids, int n, int N, int C, int k, int32_t* idx, void* ws,
             size_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -636,13 +894,18 @@ int mpa_knn(const float* x, const float* valids, int n, int N, int C, int k, int
   Scratch scratch;
   int rc = scratch.acquire(ws, ws_bytes, mpa_knn_workspace_bytes(n, N), stream);
   if (rc != MPA_OK) return rc;
+  static const int legacy = getenv("MPA_KNN_LEGACY") ? atoi(getenv("MPA_KNN_LEGACY")) : 0;
+  // tensor-core scoring when the caller sized the workspace for it (mpa_knn_workspace_bytes_c)
+  static const bool force_tile = getenv("MPA_KNN_TILE") != nullptr;  // A/B: the CUDA-core tile kernel
+  if (k <= 32 && N <= 1024 && !legacy && !force_tile && ws != nullptr &&
+      ws_bytes >= mpa_knn_workspace_bytes_c(n, N, C))
+    return knn_tensor_core(x, valids, n, N, C, k, idx, (char*)scratch.base + mpa_knn_workspace_bytes(n, N), stream);
   float* xx = (float*)scratch.base;
   {
     ProfScope ps("knn_sqnorm", stream);
     sqnorm_kernel<<<592, 256, 0, stream>>>(x, (long long)n * N, C, xx);
   }
   MPA_LAUNCH_CHECK();
-  static const int legacy = getenv("MPA_KNN_LEGACY") ? atoi(getenv("MPA_KNN_LEGACY")) : 0;
   if (k <= 32 && N <= 1024 && !legacy) {
     static DeviceOnce attr_t;
     if (attr_t.pending()) {

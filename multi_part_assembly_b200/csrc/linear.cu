@@ -95,6 +95,11 @@ struct LinearEpilogue {
   const float* ln_gamma = nullptr;
   const float* ln_beta = nullptr;
   float ln_eps = 0.f;
+  // batched block-diagonal products (blockIdx.z = item): item z uses rows z * batch_rows .. of
+  // BOTH operands (and of `bias`), M = N = rows of one item, output z * out_batch_stride on
+  int batch_rows = 0;
+  int batch_row0 = 0;  // operand row of item 0 (bias / out are passed already offset)
+  long long out_batch_stride = 0;
   __nv_bfloat16* ln_out_bf16 = nullptr;  // LayerNorm(out) as the next GEMM's operand
   float* ln_out_f32 = nullptr;           // ... and/or in fp32 (final encoder norm)
   int vec = 0;                           // rows are 16-byte aligned: packed loads / stores
@@ -114,6 +119,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)),
                "r"(bytes)
                : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
 }
 
 __device__ __forceinline__ float apply_act(float x, int act) {
@@ -205,7 +214,13 @@ __device__ __forceinline__ void store_operand1(__nv_bfloat16* base, long long o,
 template <int BN, bool FUSE_LN, int SPLIT>
 __global__ void __launch_bounds__(LN_THREADS, 1)
 linear_bf16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-                   int M, int N, int K, int x_plane_rows, int w_plane_rows, LinearEpilogue ep) {
+                   int M, int N, int K, int x_plane_rows, int w_plane_rows, LinearEpilogue ep_in) {
+  LinearEpilogue ep = ep_in;
+  const int zoff = ep.batch_row0 + (int)blockIdx.z * ep.batch_rows;
+  if (ep.batch_rows > 0) {
+    if (ep.out_f32 != nullptr) ep.out_f32 += (long long)blockIdx.z * ep.out_batch_stride;
+    if (ep.bias != nullptr) ep.bias += (int)blockIdx.z * ep.batch_rows;
+  }
   constexpr int LN_STAGES = ln_stages(BN, SPLIT);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -242,8 +257,8 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         mbar_expect_tx(&full_bar[s], STAGE);
 #pragma unroll
         for (int pl = 0; pl < SPLIT; ++pl) {  // plane pl of an operand starts pl * plane_rows rows down
-          tma_load_2d(a_dst + pl * A_TILE, &map_x, kb * LN_BK, pl * x_plane_rows + m0, &full_bar[s]);
-          tma_load_2d(b_dst + pl * B_TILE, &map_w, kb * LN_BK, pl * w_plane_rows + n0, &full_bar[s]);
+          tma_load_2d(a_dst + pl * A_TILE, &map_x, kb * LN_BK, pl * x_plane_rows + zoff + m0, &full_bar[s]);
+          tma_load_2d(b_dst + pl * B_TILE, &map_w, kb * LN_BK, pl * w_plane_rows + zoff + n0, &full_bar[s]);
         }
       }
     }
@@ -551,6 +566,238 @@ int launch_linear(const __nv_bfloat16* x, const __nv_bfloat16* w, int M, int N, 
   return MPA_OK;
 }
 
+// ---- persistent Gram kernel (k-NN scoring) ---------------------------------------------
+// out[z][i][j] = x_{z,i} . x_{z,j} + bias[z R + j] for the R rows of every item z, fp32-accurate
+// (three bf16 planes per operand, six plane products, smallest first).  K <= 128, so a whole
+// [128 x K] operand tile is resident: a CTA walks a contiguous range of [128 x 128] output
+// tiles, keeps the row-tile operand while the column tile changes, and double-buffers the
+// accumulator in TMEM so that the TMA load + MMAs of the next tile run under the epilogue of
+// the current one -- the kernel is bound by the 64 KB fp32 write of each tile, not by per-CTA
+// start-up as the one-tile-per-CTA GEMM is.
+constexpr int GR_KTILE = LN_BM * LN_BK * 2;  // [128 x 64] bf16 = 16 KB
+constexpr int GR_NB = 2;                     // column-tile k-blocks in flight
+// staging tile of an epilogue warp: [32][36] floats (16-byte accesses) when it fits, [32][33]
+// (scalar accesses, conflict-free) for K = 128, where the operands leave 33 KB
+template <int KB>
+__host__ __device__ constexpr int gr_pitch() { return KB == 1 ? EP_PITCH : 33; }
+template <int KB>
+__host__ __device__ constexpr int gr_smem_bytes() {
+  return 3 * KB * GR_KTILE + GR_NB * 3 * GR_KTILE + LN_EPI_WARPS * 32 * gr_pitch<KB>() * 4 + 1024;
+}
+static_assert(gr_smem_bytes<2>() <= 227 * 1024, "K = 128 operands + staging fit one SM");
+
+template <int KB>
+__global__ void __launch_bounds__(LN_THREADS, 1)
+gram_scores_kernel(const __grid_constant__ CUtensorMap map_x, int plane_rows, int R, int row0, int items,
+                   const float* __restrict__ bias, float* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* As = smem;                                   // [3 planes][KB][128 x 64]: row tile, all of K
+  uint8_t* Bs = smem + 3 * KB * GR_KTILE;               // ring of GR_NB x [3 planes][128 x 64]: column-tile k-blocks
+  float* stage = reinterpret_cast<float*>(Bs + GR_NB * 3 * GR_KTILE);
+  constexpr int PITCH = gr_pitch<KB>();
+  __shared__ uint64_t a_full, b_full[GR_NB], b_empty[GR_NB], acc_full[2], acc_free[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = (R + LN_BM - 1) / LN_BM;
+  const int n_tiles = items * T * T;
+  const int per = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int t_begin = (int)blockIdx.x * per, t_end = min(n_tiles, t_begin + per);
+
+  if (threadIdx.x == 0) {
+    tc::mbar_init(&a_full, 1);
+    for (int i = 0; i < GR_NB; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_free[i], LN_EPI_WARPS * 32); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc<256>(&tmem_base_s);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer =====
+      int prev_rt = -1, u = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int rt = t / T, nj = t - rt * T;          // rt = z * T + mi
+        const int z = rt / T, mi = rt - z * T;
+        const int arow = row0 + z * R + mi * LN_BM, brow = row0 + z * R + nj * LN_BM;
+        for (int kb = 0; kb < KB; ++kb, ++u) {
+          const int s = u % GR_NB;
+          if (u >= GR_NB) tc::mbar_wait(&b_empty[s], ((u / GR_NB) - 1) & 1);
+          if (kb == 0 && rt != prev_rt) {
+            // the MMAs that read the old row tile are those of the k-block uses < u: in order,
+            // so the last one's commit covers them all
+            if (u > 0) tc::mbar_wait(&b_empty[(u - 1) % GR_NB], ((u - 1) / GR_NB) & 1);
+            mbar_expect_tx(&a_full, 3 * KB * GR_KTILE);
+            for (int pl = 0; pl < 3; ++pl)
+              for (int k2 = 0; k2 < KB; ++k2)
+                tma_load_2d(As + (pl * KB + k2) * GR_KTILE, &map_x, k2 * LN_BK, pl * plane_rows + arow, &a_full);
+            prev_rt = rt;
+          }
+          mbar_expect_tx(&b_full[s], 3 * GR_KTILE);
+          for (int pl = 0; pl < 3; ++pl)
+            tma_load_2d(Bs + (s * 3 + pl) * GR_KTILE, &map_x, kb * LN_BK, pl * plane_rows + brow, &b_full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      constexpr uint32_t IDESC = tc::make_idesc_bf16(LN_BM, 128);
+      constexpr int PA[6] = {1, 2, 0, 1, 0, 0}, PB[6] = {1, 0, 2, 0, 1, 0};  // smallest terms first
+      int prev_rt = -1, u = 0, a_cnt = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int tl = t - t_begin, buf = tl & 1;
+        const int rt = t / T;
+        if (rt != prev_rt) {
+          tc::mbar_wait(&a_full, a_cnt & 1);
+          ++a_cnt;
+          prev_rt = rt;
+        }
+        if (tl >= 2) tc::mbar_wait(&acc_free[buf], ((tl >> 1) - 1) & 1);
+        const uint32_t acc = tmem + (uint32_t)(buf * 128);
+        for (int kb = 0; kb < KB; ++kb, ++u) {
+          const int s = u % GR_NB;
+          tc::mbar_wait(&b_full[s], (u / GR_NB) & 1);
+          tc::fence_after_sync();
+          const uint32_t a_addr = tc::smem_u32(As), b_addr = tc::smem_u32(Bs + s * 3 * GR_KTILE);
+#pragma unroll
+          for (int k = 0; k < LN_BK; k += 16) {
+#pragma unroll
+            for (int p6 = 0; p6 < 6; ++p6)
+              tc::mma_bf16(acc, tc::make_desc_sw128(a_addr + (PA[p6] * KB + kb) * GR_KTILE + k * 2),
+                           tc::make_desc_sw128(b_addr + PB[p6] * GR_KTILE + k * 2), IDESC,
+                           (kb > 0 || k > 0 || p6 > 0) ? 1u : 0u);
+          }
+          tc::mma_commit(&b_empty[s]);
+        }
+        tc::mma_commit(&acc_full[buf]);
+      }
+    }
+  } else {  // ===== epilogue: warps 2..9 =====
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int row_local = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    float* tile = stage + (warp - 2) * 32 * PITCH;
+    const bool vec = (R & 3) == 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      const int tl = t - t_begin, buf = tl & 1;
+      const int rt = t / T, nj = t - rt * T;
+      const int z = rt / T, mi = rt - z * T;
+      const int m0 = mi * LN_BM, n0 = nj * LN_BM;
+      tc::mbar_wait(&acc_full[buf], (tl >> 1) & 1);
+      tc::fence_after_sync();
+      const uint32_t acc = tmem + (uint32_t)(buf * 128) + lane_off;
+      float* obase = out + (long long)z * R * R;
+#pragma unroll 1
+      for (int j0 = half * 64; j0 < half * 64 + 64; j0 += 32) {
+        float v[32];
+        tc::tmem_ld32(acc + (uint32_t)j0, v);
+        tc::tmem_ld_wait();
+        const int col0 = n0 + j0;
+        if (col0 >= R) continue;  // warp-uniform
+        if (bias != nullptr) {  // the warp's 32 columns: the same address in every lane (broadcast loads)
+          const float* bz = bias + (long long)z * R;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += (col0 + j < R) ? __ldg(bz + col0 + j) : 0.f;
+        }
+        if (vec && col0 + 32 <= R) {
+          // through the warp's staging tile: one instruction then moves 4 rows x 128 contiguous bytes
+          const int qrow0 = m0 + q * 32 + (lane >> 3), qcol = 4 * (lane & 7);
+          if (KB == 1) {
+            tile_put_row(tile, lane, v);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) tile[lane * PITCH + j] = v[j];
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = qrow0 + 4 * i;
+            float4 o4;
+            if (KB == 1) {
+              o4 = *tile_quad(tile, lane, i);
+            } else {
+              const float* src = tile + ((lane >> 3) + 4 * i) * PITCH + qcol;
+              o4 = make_float4(src[0], src[1], src[2], src[3]);
+            }
+            if (row < R) *reinterpret_cast<float4*>(obase + (long long)row * R + col0 + qcol) = o4;
+          }
+          __syncwarp();
+        } else if (m0 + row_local < R) {
+          float* orow = obase + (long long)(m0 + row_local) * R;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < R) orow[col0 + j] = v[j];
+        }
+      }
+      tc::fence_before_sync();
+      mbar_arrive(&acc_free[buf]);
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc<256>(tmem);
+}
+
+// Batched Gram products in the fp32-accurate mode: for every item z of [z0, z0 + items) the
+// [R x R] matrix  out[z - z0][i][j] = x_{z,i} . x_{z,j} + bias[z * R + j]  of the item's R rows
+// of x ([3 planes][total_rows][K] bf16).  Used by the k-NN scoring (csrc/knn.cu).
+int launch_gram_batched(const __nv_bfloat16* x_planes, long long total_rows, int R, int K, int z0, int items,
+                        const float* bias, float* out, const char* name, cudaStream_t stream) {
+  MPA_CHECK_ARG(K % 8 == 0 && total_rows * 3 < (1ll << 31), "gram: K %% 8 == 0 and 3 * rows < 2^31");
+  CUtensorMap mx, mw;
+  int rc = make_map(&mx, x_planes, (int)(3 * total_rows), K, LN_BM);
+  if (rc != MPA_OK) return rc;
+  rc = make_map(&mw, x_planes, (int)(3 * total_rows), K, 128);
+  if (rc != MPA_OK) return rc;
+  static DeviceOnce attr;
+  if (attr.pending()) {
+    MPA_CUDA(cudaFuncSetAttribute(linear_bf16_kernel<128, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  ln_smem_bytes(128, 3)));
+    attr.done();
+  }
+  static const bool generic = getenv("MPA_GRAM_GENERIC") != nullptr;  // A/B: the one-tile-per-CTA kernel
+  if (K <= 2 * LN_BK && !generic) {
+    static DeviceOnce attr2;
+    if (attr2.pending()) {
+      MPA_CUDA(cudaFuncSetAttribute(gram_scores_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, gr_smem_bytes<1>()));
+      MPA_CUDA(cudaFuncSetAttribute(gram_scores_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, gr_smem_bytes<2>()));
+      attr2.done();
+    }
+    const int T = (R + LN_BM - 1) / LN_BM;
+    const int n_tiles = items * T * T;
+    int ctas = device_sms();
+    if (ctas > n_tiles) ctas = n_tiles;
+    const float* b = bias != nullptr ? bias + (long long)z0 * R : nullptr;
+    {
+      ProfScope ps(name, stream);
+      if (K <= LN_BK)
+        gram_scores_kernel<1><<<ctas, LN_THREADS, gr_smem_bytes<1>(), stream>>>(mx, (int)total_rows, R, z0 * R, items, b, out);
+      else
+        gram_scores_kernel<2><<<ctas, LN_THREADS, gr_smem_bytes<2>(), stream>>>(mx, (int)total_rows, R, z0 * R, items, b, out);
+    }
+    MPA_LAUNCH_CHECK();
+    return MPA_OK;
+  }
+  LinearEpilogue ep{bias != nullptr ? bias + (long long)z0 * R : nullptr, nullptr, out, nullptr, ACT_NONE};
+  ep.batch_rows = R;
+  ep.batch_row0 = z0 * R;
+  ep.out_batch_stride = (long long)R * R;
+  ep.vec = (R % 8 == 0) && aligned16(ep.bias) && aligned16(out);
+  // plane pl of item z starts at operand row pl * total_rows + (z0 + z) * R
+  dim3 grid((R + LN_BM - 1) / LN_BM, (R + 127) / 128, items);
+  {
+    ProfScope ps(name, stream);
+    linear_bf16_kernel<128, false, 3><<<grid, LN_THREADS, ln_smem_bytes(128, 3), stream>>>(
+        mx, mw, R, R, K, (int)total_rows, (int)total_rows, ep);
+  }
+  MPA_LAUNCH_CHECK();
+  return MPA_OK;
+}
+
 // ======================================================================================
 // Fused second half of a pre-LN encoder layer for d_model = 256 (bf16 operands):
 //     x  <- x + dropout1(att W_o^T + b_o)            (out_proj)
@@ -595,9 +842,6 @@ struct FfnBlockArgs {
 };
 #define FB_STAMP(i) do { if (a.dbg != nullptr && blockIdx.x == 0) a.dbg[i] = clock64(); } while (0)
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
-}
 
 // LayerNorm of the 128 rows parked in TMEM columns [0, 256).  The caller accumulated the row
 // sums and sums of squares of its half while parking (one-pass statistics: the residual stream
@@ -949,6 +1193,7 @@ encoder_ffn_block_kernel(const __grid_constant__ CUtensorMap map_att, const __gr
       tc::tmem_st32(acc0 + lane_off + (uint32_t)j0, v);
     }
     tc::tmem_st_wait();
+    if (threadIdx.x == 64) FB_STAMP(37);
     fb_layernorm_rows(acc0 + lane_off, c_begin, c_end, half, row_local, sum, sumsq, ln_part, s_vec[1], s_vec[2], a.eps,
                       [&](int j0, const float* v) { fb_store_operand_row(A1, row_local, j0, v); });
     tc::fence_async_smem();        // A1 written through the generic proxy -> visible to the tensor core

@@ -139,7 +139,7 @@ __global__ void pose_outputs_kernel(const float* __restrict__ f, int T, int K,
 // lane 4t ends up with token t's total.
 constexpr int PH_TOK = 8;
 constexpr int PH_THREADS = 384;
-constexpr int PH_OUTS = 4;  // output channels per warp iteration: 32 weight loads in flight per lane
+constexpr int PH_OUTS = 4;  // output channels per warp iteration: 32 weight loads in flight per lane (8: measured slower)
 
 // per-lane partial sums of 8 tokens -> token (lane >> 2)'s total in every lane of its group of 4
 __device__ __forceinline__ float fold8(const float (&a)[8], int lane) {

@@ -1,5 +1,6 @@
 // Shared helpers of libmpa_b200.so (sm_100a only).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -52,6 +53,10 @@ class ProfScope {
 int launch_se3_backward(const float* quat, const float* pts, const float* grad_out,
                         const float* valids, int fill_invalid, int n_parts, int N, float* grad_pts,
                         float* grad_quat, float* grad_trans, cudaStream_t stream);
+
+// csrc/linear.cu: batched [R x R] Gram matrices of the items' rows, fp32-accurate tensor-core mode
+int launch_gram_batched(const __nv_bfloat16* x_planes, long long total_rows, int R, int K, int z0, int items,
+                        const float* bias, float* out, const char* name, cudaStream_t stream);
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

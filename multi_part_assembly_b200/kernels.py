@@ -328,7 +328,7 @@ def knn(x, k=20, valids=None):
     idx = (torch.zeros if valids is not None else torch.empty)(
         n, N, k, dtype=torch.int32, device=x.device)
     L = _lib.lib()
-    ws_bytes = L.mpa_knn_workspace_bytes(n, N)
+    ws_bytes = L.mpa_knn_workspace_bytes_c(n, N, C)  # with room for the tensor-core scoring path
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=x.device)
     with torch.cuda.device(x.device):
         rc = L.mpa_knn(_lib.ptr(x), _lib.ptr(valids), n, N, C, k, _lib.ptr(idx), _lib.ptr(ws),
