@@ -834,7 +834,8 @@ size_t mpa_knn_workspace_bytes(int n, int N) {
 static int knn_kpad(int C) { return (C + 7) & ~7; }
 static int knn_chunk_items(int n, int N) {
   const size_t per_item = sizeof(float) * (size_t)N * N;
-  size_t items = ((size_t)96 << 20) / per_item;  // ~96 MB of scores in flight: stays in the 126 MB L2
+  static const size_t mb = getenv("MPA_KNN_CHUNK_MB") ? (size_t)atoi(getenv("MPA_KNN_CHUNK_MB")) : 256;
+  size_t items = (mb << 20) / per_item;  // scores in flight per Gram + select launch pair (fewer, longer launches measured faster than L2-sized chunks)
   if (items < 1) items = 1;
   if (items > (size_t)n) items = n;
   return (int)items;
@@ -870,7 +871,7 @@ static int knn_tensor_core(const float* x, const float* valids, int n, int N, in
   const int chunk = knn_chunk_items(n, N);
   for (int z0 = 0; z0 < n; z0 += chunk) {
     const int items = n - z0 < chunk ? n - z0 : chunk;
-    int rc = launch_gram_batched(planes, rows, N, Kp, z0, items, hb, S, "knn_gram", stream);
+    int rc = launch_gram_batched(planes, rows, N, Kp, z0, items, hb, valids, S, "knn_gram", stream);
     if (rc != MPA_OK) return rc;
     {
       ProfScope ps("knn_select", stream);

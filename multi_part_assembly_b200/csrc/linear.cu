@@ -589,7 +589,7 @@ static_assert(gr_smem_bytes<2>() <= 227 * 1024, "K = 128 operands + staging fit 
 template <int KB>
 __global__ void __launch_bounds__(LN_THREADS, 1)
 gram_scores_kernel(const __grid_constant__ CUtensorMap map_x, int plane_rows, int R, int row0, int items,
-                   const float* __restrict__ bias, float* __restrict__ out) {
+                   const float* __restrict__ bias, const float* __restrict__ item_valid, float* __restrict__ out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* As = smem;                                   // [3 planes][KB][128 x 64]: row tile, all of K
@@ -601,9 +601,7 @@ gram_scores_kernel(const __grid_constant__ CUtensorMap map_x, int plane_rows, in
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = (R + LN_BM - 1) / LN_BM;
-  const int n_tiles = items * T * T;
-  const int per = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int t_begin = (int)blockIdx.x * per, t_end = min(n_tiles, t_begin + per);
+  const int n_rt = items * T;  // row tiles; a CTA takes every gridDim.x-th one with all its column tiles
 
   if (threadIdx.x == 0) {
     tc::mbar_init(&a_full, 1);
@@ -620,9 +618,9 @@ gram_scores_kernel(const __grid_constant__ CUtensorMap map_x, int plane_rows, in
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer =====
       int prev_rt = -1, u = 0;
-      for (int t = t_begin; t < t_end; ++t) {
-        const int rt = t / T, nj = t - rt * T;          // rt = z * T + mi
-        const int z = rt / T, mi = rt - z * T;
+      for (int rt = blockIdx.x; rt < n_rt; rt += gridDim.x) for (int nj = 0; nj < T; ++nj) {
+        const int z = rt / T, mi = rt - z * T;          // rt = z * T + mi
+        if (item_valid != nullptr && item_valid[z] == 0.0f) continue;  // padded item: every role skips its tiles
         const int arow = row0 + z * R + mi * LN_BM, brow = row0 + z * R + nj * LN_BM;
         for (int kb = 0; kb < KB; ++kb, ++u) {
           const int s = u % GR_NB;
@@ -647,10 +645,11 @@ gram_scores_kernel(const __grid_constant__ CUtensorMap map_x, int plane_rows, in
     if (lane == 0) {  // ===== MMA issuer =====
       constexpr uint32_t IDESC = tc::make_idesc_bf16(LN_BM, 128);
       constexpr int PA[6] = {1, 2, 0, 1, 0, 0}, PB[6] = {1, 0, 2, 0, 1, 0};  // smallest terms first
-      int prev_rt = -1, u = 0, a_cnt = 0;
-      for (int t = t_begin; t < t_end; ++t) {
-        const int tl = t - t_begin, buf = tl & 1;
-        const int rt = t / T;
+      int prev_rt = -1, u = 0, a_cnt = 0, tl = -1;
+      for (int rt = blockIdx.x; rt < n_rt; rt += gridDim.x) for (int nj = 0; nj < T; ++nj) {
+        if (item_valid != nullptr && item_valid[rt / T] == 0.0f) continue;
+        ++tl;  // tiles actually processed: accumulator buffer and barrier phases follow this count
+        const int buf = tl & 1;
         if (rt != prev_rt) {
           tc::mbar_wait(&a_full, a_cnt & 1);
           ++a_cnt;
@@ -682,10 +681,12 @@ gram_scores_kernel(const __grid_constant__ CUtensorMap map_x, int plane_rows, in
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     float* tile = stage + (warp - 2) * 32 * PITCH;
     const bool vec = (R & 3) == 0;
-    for (int t = t_begin; t < t_end; ++t) {
-      const int tl = t - t_begin, buf = tl & 1;
-      const int rt = t / T, nj = t - rt * T;
+    int tl = -1;
+    for (int rt = blockIdx.x; rt < n_rt; rt += gridDim.x) for (int nj = 0; nj < T; ++nj) {
       const int z = rt / T, mi = rt - z * T;
+      if (item_valid != nullptr && item_valid[z] == 0.0f) continue;
+      ++tl;
+      const int buf = tl & 1;
       const int m0 = mi * LN_BM, n0 = nj * LN_BM;
       tc::mbar_wait(&acc_full[buf], (tl >> 1) & 1);
       tc::fence_after_sync();
@@ -746,7 +747,8 @@ gram_scores_kernel(const __grid_constant__ CUtensorMap map_x, int plane_rows, in
 // [R x R] matrix  out[z - z0][i][j] = x_{z,i} . x_{z,j} + bias[z * R + j]  of the item's R rows
 // of x ([3 planes][total_rows][K] bf16).  Used by the k-NN scoring (csrc/knn.cu).
 int launch_gram_batched(const __nv_bfloat16* x_planes, long long total_rows, int R, int K, int z0, int items,
-                        const float* bias, float* out, const char* name, cudaStream_t stream) {
+                        const float* bias, const float* item_valid, float* out, const char* name,
+                        cudaStream_t stream) {
   MPA_CHECK_ARG(K % 8 == 0 && total_rows * 3 < (1ll << 31), "gram: K %% 8 == 0 and 3 * rows < 2^31");
   CUtensorMap mx, mw;
   int rc = make_map(&mx, x_planes, (int)(3 * total_rows), K, LN_BM);
@@ -768,16 +770,18 @@ int launch_gram_batched(const __nv_bfloat16* x_planes, long long total_rows, int
       attr2.done();
     }
     const int T = (R + LN_BM - 1) / LN_BM;
-    const int n_tiles = items * T * T;
     int ctas = device_sms();
-    if (ctas > n_tiles) ctas = n_tiles;
+    if (ctas > items * T) ctas = items * T;
     const float* b = bias != nullptr ? bias + (long long)z0 * R : nullptr;
+    const float* iv = item_valid != nullptr ? item_valid + z0 : nullptr;  // [items]: 0 = skip the item
     {
       ProfScope ps(name, stream);
       if (K <= LN_BK)
-        gram_scores_kernel<1><<<ctas, LN_THREADS, gr_smem_bytes<1>(), stream>>>(mx, (int)total_rows, R, z0 * R, items, b, out);
+        gram_scores_kernel<1><<<ctas, LN_THREADS, gr_smem_bytes<1>(), stream>>>(mx, (int)total_rows, R, z0 * R, items, b,
+                                                                                iv, out);
       else
-        gram_scores_kernel<2><<<ctas, LN_THREADS, gr_smem_bytes<2>(), stream>>>(mx, (int)total_rows, R, z0 * R, items, b, out);
+        gram_scores_kernel<2><<<ctas, LN_THREADS, gr_smem_bytes<2>(), stream>>>(mx, (int)total_rows, R, z0 * R, items, b,
+                                                                                iv, out);
     }
     MPA_LAUNCH_CHECK();
     return MPA_OK;

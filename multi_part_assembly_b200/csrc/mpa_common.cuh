@@ -56,7 +56,8 @@ int launch_se3_backward(const float* quat, const float* pts, const float* grad_o
 
 // csrc/linear.cu: batched [R x R] Gram matrices of the items' rows, fp32-accurate tensor-core mode
 int launch_gram_batched(const __nv_bfloat16* x_planes, long long total_rows, int R, int K, int z0, int items,
-                        const float* bias, float* out, const char* name, cudaStream_t stream);
+                        const float* bias, const float* item_valid, float* out, const char* name,
+                        cudaStream_t stream);
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
