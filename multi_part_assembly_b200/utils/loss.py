@@ -113,10 +113,11 @@ class FusedLossTerms(dict):
 _SIDE_STREAMS = {}
 
 
-def _side_stream(dev):
-    s = _SIDE_STREAMS.get(dev)
+def _side_stream(dev, high=False):
+    key = (dev, high)
+    s = _SIDE_STREAMS.get(key)
     if s is None:
-        s = _SIDE_STREAMS[dev] = torch.cuda.Stream(device=dev)
+        s = _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev, priority=-1 if high else 0)
     return s
 
 
@@ -138,13 +139,16 @@ def fused_geometric_losses(pts, pred_trans, gt_trans, pred_rot, gt_rot, valids, 
         # run the per-part one on a side stream so that it fills the SMs the shape-level
         # one leaves idle (a fork/join that CUDA-graph capture records as parallel branches).
         cur = torch.cuda.current_stream(dev)
-        side = _side_stream(dev)
+        # the shape-level search is the longer branch: it goes to a HIGH-priority stream so that
+        # its blocks are scheduled first and the per-part search fills what it leaves idle
+        # (A/B on one box: 1.194 -> 1.178 ms per cfg C step)
+        side = _side_stream(dev, high=True)
         side.wait_stream(cur)
-        sd1, sd2, pts1, pts2 = pose_chamfer(pts, t1, t2, q1, q2, valids, CD_SHAPE)
         with torch.cuda.stream(side):
-            pd1, pd2, _, _ = pose_chamfer(pts, None, None, q1, q2, valids, CD_PART)
+            sd1, sd2, pts1, pts2 = pose_chamfer(pts, t1, t2, q1, q2, valids, CD_SHAPE)
+        pd1, pd2, _, _ = pose_chamfer(pts, None, None, q1, q2, valids, CD_PART)
         cur.wait_stream(side)
-        for t in (pd1, pd2):
+        for t in (sd1, sd2, pts1, pts2):
             t.record_stream(cur)
     terms = torch.empty(6, B, dtype=torch.float32, device=dev)
     w = torch.tensor([float(x) for x in weights], dtype=torch.float32).to(dev, non_blocking=True) \
