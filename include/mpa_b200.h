@@ -193,6 +193,14 @@ int mpa_pointnet_forward(const float* pts, const float* valids, int n_parts, int
                          const float* const* bn_beta, float* const* bn_running_mean,
                          float* const* bn_running_var, int training, float eps, float momentum,
                          float* feats, void* ws, size_t ws_bytes, void* stream);
+/* Same, and (training, bn_batch_stats != NULL) also returns what a backward pass needs of the
+ * five BatchNorm layers: [5][4][256] floats = batch mean, 1/sqrt(var + eps), scale, shift per
+ * channel, followed by one float = the number of points the statistics were taken over. */
+int mpa_pointnet_forward_ex(const float* pts, const float* valids, int n_parts, int N, int F,
+                            const float* const* conv_w, const float* const* bn_gamma,
+                            const float* const* bn_beta, float* const* bn_running_mean,
+                            float* const* bn_running_var, int training, float eps, float momentum,
+                            float* feats, float* bn_batch_stats, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- PointNet backward: BatchNorm / ReLU / max-pool between the GEMMs ---------- */
 /* Training-step backward of PointNet.forward (models/modules/encoder/pointnet.py:29-41,

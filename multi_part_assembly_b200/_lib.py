@@ -46,6 +46,9 @@ _SIGNATURES = {
     'mpa_pointnet_forward': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int] + [c_void_p] * 5 +
                              [c_int, ctypes.c_float, ctypes.c_float, c_void_p, c_void_p, c_size_t,
                               c_void_p]),
+    'mpa_pointnet_forward_ex': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int] + [c_void_p] * 5 +
+                                [c_int, ctypes.c_float, ctypes.c_float, c_void_p, c_void_p, c_void_p, c_size_t,
+                                 c_void_p]),
     'mpa_pose_outputs': (c_int, [c_void_p, c_int, c_int] + [c_void_p] * 4 + [c_int] + [c_void_p] * 3),
     'mpa_pose_head_forward': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                       c_int] + [c_void_p] * 4 + [c_int] + [c_void_p] * 3),

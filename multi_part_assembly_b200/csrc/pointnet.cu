@@ -77,6 +77,7 @@ struct PointNetArgs {
   // operand tile a_{p-1} it built for its last layer in global memory, as the exact shared
   // memory image (8 KB per 64-point tile), and launch p+1 starts from it instead of
   // recomputing layers 1..p-1 from the points.  Same operands, so the results are unchanged.
+  float* stats_out;         // [5][4][256] batch mean, rstd, scale, shift per layer + [1] point count, or nullptr
   const uint4* stash_in;    // a_{PHASE-2} tiles or nullptr (start from the points)
   uint4* stash_out;         // a_{PHASE-1} tiles or nullptr
 };
@@ -169,6 +170,14 @@ __global__ void __launch_bounds__(PN_THREADS, 1) pointnet_phase_kernel(PointNetA
       if (blockIdx.x == 0 && g == 0) {
         a.scale_out[(PHASE - 2) * PN_MAXC + t] = sc_prev;
         a.shift_out[(PHASE - 2) * PN_MAXC + t] = sh_prev;
+        if (a.stats_out != nullptr) {  // what the backward pass needs of this layer's BatchNorm
+          float* so = a.stats_out + (PHASE - 2) * 4 * PN_MAXC;
+          so[t] = (float)mean;
+          so[PN_MAXC + t] = (float)(1.0 / sqrt(var + (double)a.eps));
+          so[2 * PN_MAXC + t] = sc_prev;
+          so[3 * PN_MAXC + t] = sh_prev;
+          if (t == 0) a.stats_out[5 * 4 * PN_MAXC] = (float)n;
+        }
         if (a.rmean_prev != nullptr) {
           a.rmean_prev[t] = (1.f - a.momentum) * a.rmean_prev[t] + a.momentum * (float)mean;
           const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
@@ -434,7 +443,7 @@ __global__ void pointnet_finalize_kernel(const float* partial, int n_workers, in
                                          const float* valids, int n_parts, int N,
                                          const float* gamma, const float* beta, float eps,
                                          float momentum, float* running_mean, float* running_var,
-                                         float* scale, float* shift) {
+                                         float* scale, float* shift, float* stats_out) {
   // one warp per channel; lanes stride over the workers (fixed order -> deterministic)
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
@@ -457,6 +466,13 @@ __global__ void pointnet_finalize_kernel(const float* partial, int n_workers, in
   const float sc = gamma[c] * (float)(1.0 / sqrt(var + (double)eps));
   scale[layer * PN_MAXC + c] = sc;
   shift[layer * PN_MAXC + c] = beta[c] - (float)mean * sc;
+  if (stats_out != nullptr) {
+    float* so = stats_out + layer * 4 * PN_MAXC;
+    so[c] = (float)mean;
+    so[PN_MAXC + c] = (float)(1.0 / sqrt(var + (double)eps));
+    so[2 * PN_MAXC + c] = sc;
+    so[3 * PN_MAXC + c] = beta[c] - (float)mean * sc;
+  }
   if (running_mean != nullptr) {
     running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
     const double unbiased = cnt > 1.0 ? var * cnt / (cnt - 1.0) : var;
@@ -632,6 +648,11 @@ using namespace mpa;
 extern "C" {
 
 size_t mpa_pointnet_workspace_bytes(int n_parts);
+int mpa_pointnet_forward_ex(const float* pts, const float* valids, int n_parts, int N, int F,
+                            const float* const* conv_w, const float* const* bn_gamma,
+                            const float* const* bn_beta, float* const* bn_running_mean,
+                            float* const* bn_running_var, int training, float eps, float momentum,
+                            float* feats, float* bn_batch_stats, void* ws, size_t ws_bytes, void* stream_);
 static size_t pointnet_stash_bytes(int n_parts, int N) {  // one ping-pong buffer of a_k tiles
   const size_t tiles = (size_t)n_parts * ((N + PN_TILE - 1) / PN_TILE);
   return align_up(tiles * PN_ACT_KB, 256);
@@ -658,6 +679,15 @@ int mpa_pointnet_forward(const float* pts, const float* valids, int n_parts, int
                          const float* const* bn_beta, float* const* bn_running_mean,
                          float* const* bn_running_var, int training, float eps, float momentum,
                          float* feats, void* ws, size_t ws_bytes, void* stream_) {
+  return mpa_pointnet_forward_ex(pts, valids, n_parts, N, F, conv_w, bn_gamma, bn_beta, bn_running_mean,
+                                 bn_running_var, training, eps, momentum, feats, nullptr, ws, ws_bytes, stream_);
+}
+
+int mpa_pointnet_forward_ex(const float* pts, const float* valids, int n_parts, int N, int F,
+                            const float* const* conv_w, const float* const* bn_gamma,
+                            const float* const* bn_beta, float* const* bn_running_mean,
+                            float* const* bn_running_var, int training, float eps, float momentum,
+                            float* feats, float* bn_batch_stats, void* ws, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   MPA_CHECK_ARG(n_parts >= 0 && N >= 0, "pointnet_forward: negative size");
   MPA_CHECK_ARG(F == 128 || F == 256, "pointnet_forward: feat_dim must be 128 or 256 (got %d)", F);
@@ -724,6 +754,7 @@ int mpa_pointnet_forward(const float* pts, const float* valids, int n_parts, int
   a.scale = scale; a.shift = shift; a.scale_out = scale; a.shift_out = shift;
   a.pmax = pmax; a.pmin = pmin; a.n_parts = n_parts; a.N = N; a.F = F; a.dbg = dbg;
   a.eps = eps; a.momentum = momentum;
+  a.stats_out = training ? bn_batch_stats : nullptr;
   const int C[5] = {64, 64, 64, 128, F};
   if (training) {
     for (int layer = 0; layer < 5; ++layer) {
@@ -767,7 +798,7 @@ int mpa_pointnet_forward(const float* pts, const float* valids, int n_parts, int
       ProfScope ps("pointnet_bn_finalize", stream);
       pointnet_finalize_kernel<<<(C[4] * 32 + 255) / 256, 256, 0, stream>>>(
           partial_buf[0], grid, 4, C[4], valids, n_parts, N, bn_gamma[4], bn_beta[4], eps, momentum,
-          bn_running_mean[4], bn_running_var[4], scale, shift);
+          bn_running_mean[4], bn_running_var[4], scale, shift, bn_batch_stats);
     }
     MPA_LAUNCH_CHECK();
   } else {

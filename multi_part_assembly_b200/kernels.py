@@ -92,7 +92,7 @@ def _mm_f32(a, b):
         return torch.mm(a, b).float()
 
 
-def _pointnet_backward_native(x, valids, grad, convs, bns):
+def _pointnet_backward_native(x, valids, grad, convs, bns, stats=None):
     """Gradients of PointNet.forward (global_feat=True, train-mode BatchNorm) w.r.t.
     conv / BatchNorm parameters (reference: autograd through
     models/modules/encoder/pointnet.py:29-41).
@@ -121,15 +121,20 @@ def _pointnet_backward_native(x, valids, grad, convs, bns):
             Ws.append((F.pad(w, (0, 5)) if i == 0 else w).to(bf))
         acts, zs, consts = [a0], [], []
         sums = torch.empty(2 * 256, dtype=torch.float64, device=dev)
-        count = torch.empty(1, **f32)
+        # `stats`: the forward kernels' own batch statistics ([5][mean, rstd, scale, shift][256]
+        # + point count): no second statistics pass over the recomputed pre-activations
+        count = torch.empty(1, **f32) if stats is None else stats[5 * 4 * 256:]
         for i in range(5):
             z = acts[i] @ Ws[i].t()
             C = z.shape[1]
-            _lib.check(L.mpa_bn_stats(ptr(z), M, C, N, ptr(v), ptr(sums), st), 'mpa_bn_stats')
-            cst = torch.empty(4, C, **f32)  # mean, rstd, scale, shift
-            _lib.check(L.mpa_bn_finalize(ptr(sums), C, n, N, ptr(v), ptr(bns[i].weight.detach()),
-                                         ptr(bns[i].bias.detach()), eps, ptr(cst[0]), ptr(cst[1]),
-                                         ptr(cst[2]), ptr(cst[3]), ptr(count), st), 'mpa_bn_finalize')
+            if stats is not None:
+                cst = stats[i * 4 * 256:(i + 1) * 4 * 256].view(4, 256)  # rows contiguous, first C valid
+            else:
+                _lib.check(L.mpa_bn_stats(ptr(z), M, C, N, ptr(v), ptr(sums), st), 'mpa_bn_stats')
+                cst = torch.empty(4, C, **f32)  # mean, rstd, scale, shift
+                _lib.check(L.mpa_bn_finalize(ptr(sums), C, n, N, ptr(v), ptr(bns[i].weight.detach()),
+                                             ptr(bns[i].bias.detach()), eps, ptr(cst[0]), ptr(cst[1]),
+                                             ptr(cst[2]), ptr(cst[3]), ptr(count), st), 'mpa_bn_finalize')
             zs.append(z)
             consts.append(cst)
             if i < 4:
@@ -179,29 +184,35 @@ class _PointNetFunction(torch.autograd.Function):
         ws_bytes = L.mpa_pointnet_workspace_bytes_n(n, N) if training else L.mpa_pointnet_workspace_bytes(n)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         w = [c.weight.detach().reshape(c.weight.shape[0], -1).float().contiguous() for c in convs]
+        # the batch statistics of the five BatchNorm layers, kept for the backward pass
+        # ([5][mean, rstd, scale, shift][256] + the point count) when one will follow
+        want_stats = training and any(ctx.needs_input_grad)
+        stats = torch.empty(5 * 4 * 256 + 1, dtype=torch.float32, device=dev) if want_stats else None
         with torch.cuda.device(dev):
-            rc = L.mpa_pointnet_forward(
+            rc = L.mpa_pointnet_forward_ex(
                 _lib.ptr(x), _lib.ptr(valids), n, N, Fdim, _ptr_array(w),
                 _ptr_array([b.weight.detach() for b in bns]),
                 _ptr_array([b.bias.detach() for b in bns]),
                 _ptr_array([b.running_mean for b in bns]),
                 _ptr_array([b.running_var for b in bns]), 1 if training else 0,
-                float(bns[0].eps), float(bns[0].momentum), _lib.ptr(feats), _lib.ptr(ws),
+                float(bns[0].eps), float(bns[0].momentum), _lib.ptr(feats), _lib.ptr(stats), _lib.ptr(ws),
                 ws_bytes, _lib.cuda_stream(dev))
-        _lib.check(rc, 'mpa_pointnet_forward')
+        _lib.check(rc, 'mpa_pointnet_forward_ex')
         if training:  # one multi-tensor launch instead of five scalar adds
             torch._foreach_add_([b.num_batches_tracked for b in bns], 1)
-        ctx.save_for_backward(x, valids if valids is not None else x.new_empty(0))
+        ctx.save_for_backward(x, valids if valids is not None else x.new_empty(0),
+                              stats if stats is not None else x.new_empty(0))
         ctx.modules = modules
         ctx.training = training
         return feats
 
     @staticmethod
     def backward(ctx, grad):
-        x, valids = ctx.saved_tensors
+        x, valids, stats = ctx.saved_tensors
         convs, bns = ctx.modules
         if ctx.training and _NATIVE_BACKWARD['pointnet']:
-            gW, gG, gB = _pointnet_backward_native(x, valids, grad, convs, bns)
+            gW, gG, gB = _pointnet_backward_native(x, valids, grad, convs, bns,
+                                                   stats if stats.numel() else None)
             return (None, None, None, None) + tuple(gW) + tuple(gG) + tuple(gB)
         # same operand precision as the forward kernels (bf16 GEMMs, fp32 BatchNorm)
         with torch.enable_grad(), torch.autocast('cuda', dtype=torch.bfloat16):
