@@ -113,6 +113,11 @@ class FusedLossTerms(dict):
 _SIDE_STREAMS = {}
 
 
+# set by measurement code: run the two Chamfer searches back to back instead of on parallel streams,
+# so that a kernel's event-timed duration is its own (not stretched by the sibling it shares SMs with)
+SERIAL_SEARCHES = False
+
+
 def _side_stream(dev, high=False):
     key = (dev, high)
     s = _SIDE_STREAMS.get(key)
@@ -142,14 +147,18 @@ def fused_geometric_losses(pts, pred_trans, gt_trans, pred_rot, gt_rot, valids, 
         # the shape-level search is the longer branch: it goes to a HIGH-priority stream so that
         # its blocks are scheduled first and the per-part search fills what it leaves idle
         # (A/B on one box: 1.194 -> 1.178 ms per cfg C step)
-        side = _side_stream(dev, high=True)
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
+        if SERIAL_SEARCHES:  # per-kernel timing (bench.py's roofline pass): one after the other
             sd1, sd2, pts1, pts2 = pose_chamfer(pts, t1, t2, q1, q2, valids, CD_SHAPE)
-        pd1, pd2, _, _ = pose_chamfer(pts, None, None, q1, q2, valids, CD_PART)
-        cur.wait_stream(side)
-        for t in (sd1, sd2, pts1, pts2):
-            t.record_stream(cur)
+            pd1, pd2, _, _ = pose_chamfer(pts, None, None, q1, q2, valids, CD_PART)
+        else:
+            side = _side_stream(dev, high=True)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                sd1, sd2, pts1, pts2 = pose_chamfer(pts, t1, t2, q1, q2, valids, CD_SHAPE)
+            pd1, pd2, _, _ = pose_chamfer(pts, None, None, q1, q2, valids, CD_PART)
+            cur.wait_stream(side)
+            for t in (sd1, sd2, pts1, pts2):
+                t.record_stream(cur)
     terms = torch.empty(6, B, dtype=torch.float32, device=dev)
     w = torch.tensor([float(x) for x in weights], dtype=torch.float32).to(dev, non_blocking=True) \
         if not isinstance(weights, torch.Tensor) else weights
