@@ -16,6 +16,8 @@
 // point it gathers the k neighbours' u rows (coalesced along channels), and
 // keeps max, min, sum and sum of squares of u_j + v_i -- what BatchNorm2d
 // (batch statistics over n*N*k edges) + LeakyReLU + max-over-k need.
+#include <algorithm>
+
 #include "mpa_common.cuh"
 
 namespace mpa {
@@ -213,7 +215,7 @@ __device__ __noinline__ void knn_select_slow(const float* __restrict__ Sr, int N
   for (int s_ = 0; s_ < k; ++s_) {
     unsigned long long best = 0ull;
     for (int j = lane; j < N; j += 32) {
-      const unsigned long long key = knn_key(__ldcg(Sr + j), j);
+      const unsigned long long key = knn_key(Sr[j], j);
       if (key < prev) best = u64max(best, key);
     }
 #pragma unroll
@@ -397,7 +399,7 @@ knn_tile_kernel(const float* __restrict__ x, const float* __restrict__ xx,
 // The score matrix is a Gram matrix, so the contraction belongs on the tensor cores; what
 // must not change is the RESULT, the oracle's top-k set under its own fp32 arithmetic
 // (sequential-k FMA, dgcnn.py:8-15).  Per chunk of parts:
-//   1. `launch_gram_batched` (csrc/linear.cu, three bf16 planes per operand = fp32-accurate):
+//   1. `launch_gram_batched` / `launch_gram_candidates` (csrc/linear.cu, two bf16 planes per operand):
 //      t_ij = x_i . x_j - |x_j|^2 / 2, which orders the candidates of row i like the score does;
 //   2. `knn_select_kernel`, one warp per row at full occupancy: lane maxima -> lower bound of
 //      the k-th best -> candidates within `delta` of it (delta bounds twice the worst
@@ -411,7 +413,7 @@ knn_tile_kernel(const float* __restrict__ x, const float* __restrict__ xx,
 // Only the set is contractual (EdgeConv takes a max over the k edges); the order written is
 // approximate-score order with the exactly decided boundary members last.
 // One pass over x: |x|^2 in the oracle's order (sequential-k FMA), -|x|^2 / 2 (the bias of the Gram
-// products), the per-part maximum, and the three bf16 operand planes [3][rows][Kp] (hi, mid, lo;
+// products), the per-part maximum, and the two bf16 operand planes [2][rows][Kp] (hi, mid;
 // channels >= C zero).  A warp takes 32 rows: coalesced loads into a padded shared-memory tile, the
 // planes leave coalesced as well, then lane r walks row r.
 constexpr int KP_THREADS = 256;
@@ -451,7 +453,7 @@ knn_prepare_kernel(const float* __restrict__ x, long long rows, int N, int C, in
         if (r < rows && c < Kp) {  // Kp is a multiple of 8: the whole quad is inside
           const long long eo = r * Kp + c;
 #pragma unroll
-          for (int pl = 0; pl < 3; ++pl) {
+          for (int pl = 0; pl < 2; ++pl) {
             __nv_bfloat16 h[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -500,6 +502,49 @@ __device__ __forceinline__ float knn_key_value(unsigned long long key) {
   return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
 }
 __device__ __forceinline__ int knn_key_index(unsigned long long key) { return (int)(~(unsigned)(key & 0xffffffffull)); }
+
+// <= 64 candidate keys of one row (r0 = candidate `lane`, r1 = candidate `lane + 32`, 0 = none):
+// sort by approximate score; if the k-th and (k+1)-th are more than `delta` apart the first k are
+// the oracle's set, otherwise the candidates within delta of the k-th are re-scored exactly and
+// the boundary is decided on those values (see the comment above knn_prepare_kernel).
+__device__ __forceinline__ void knn_finish_row(unsigned long long r0, unsigned long long r1, int total, int lane,
+                                               unsigned long long* wb, float delta, int k,
+                                               const float* __restrict__ xp, const float* __restrict__ xxp,
+                                               float xxi, int i, int C, int* __restrict__ out) {
+  if (total <= 32) knn_sort32(r0, lane);  // warp-uniform; the common case
+  else knn_sort64(r0, r1, lane);          // approximate order, best first
+  const float tk = knn_key_value(__shfl_sync(0xffffffffu, r0, k - 1));
+  const unsigned long long next = k < 32 ? __shfl_sync(0xffffffffu, r0, k & 31) : __shfl_sync(0xffffffffu, r1, 0);
+  const bool clear = total <= k || next == 0ull || tk - knn_key_value(next) > delta;
+  if (clear) {  // the k-th and (k+1)-th are further apart than any rounding can move them
+    if (lane < k) out[lane] = knn_key_index(r0);
+    return;
+  }
+  // boundary decision on exact scores: `sure` = beats the k-th by more than delta (a prefix of
+  // the sorted list, < k long), `band` = within delta of the k-th (the positions after it)
+  const float hi = tk + delta, lo = tk - delta;
+  const bool s0 = r0 != 0ull && knn_key_value(r0) > hi, s1 = r1 != 0ull && knn_key_value(r1) > hi;
+  const bool b0 = r0 != 0ull && !s0 && knn_key_value(r0) >= lo, b1 = r1 != 0ull && !s1 && knn_key_value(r1) >= lo;
+  const int m = __popc(__ballot_sync(0xffffffffu, s0)) + __popc(__ballot_sync(0xffffffffu, s1));
+  const int nb = __popc(__ballot_sync(0xffffffffu, b0)) + __popc(__ballot_sync(0xffffffffu, b1));
+  __syncwarp();
+  wb[lane] = r0;
+  wb[lane + 32] = r1;
+  __syncwarp();
+  unsigned long long e0 = 0ull, e1 = 0ull;
+  if (lane < nb) {
+    const int j = knn_key_index(wb[m + lane]);
+    e0 = knn_key(knn_exact_score(xp + (long long)i * C, xp + (long long)j * C, C, xxi, xxp[j]), j);
+  }
+  if (lane + 32 < nb) {
+    const int j = knn_key_index(wb[m + lane + 32]);
+    e1 = knn_key(knn_exact_score(xp + (long long)i * C, xp + (long long)j * C, C, xxi, xxp[j]), j);
+  }
+  knn_sort64(e0, e1, lane);  // exact order of the band, best first
+  const unsigned long long pick = __shfl_sync(0xffffffffu, e0, (lane - m) & 31);  // k - m <= 32
+  if (lane < m) out[lane] = knn_key_index(r0);
+  else if (lane < k) out[lane] = knn_key_index(pick);
+}
 
 constexpr int KS_THREADS = 256;
 __global__ void __launch_bounds__(KS_THREADS)
@@ -556,42 +601,44 @@ knn_select_kernel(float* __restrict__ S, int z0, int items, const float* __restr
     __syncwarp();
     unsigned long long r0 = lane < total ? wb[lane] : 0ull;
     unsigned long long r1 = lane + 32 < total ? wb[lane + 32] : 0ull;
-    if (total <= 32) knn_sort32(r0, lane);  // warp-uniform; the common case
-    else knn_sort64(r0, r1, lane);          // approximate order, best first
-    const float tk = knn_key_value(__shfl_sync(0xffffffffu, r0, k - 1));
-    const unsigned long long next = k < 32 ? __shfl_sync(0xffffffffu, r0, k & 31) : __shfl_sync(0xffffffffu, r1, 0);
-    const bool clear = total <= k || next == 0ull || tk - knn_key_value(next) > delta;
-    if (clear) {  // the k-th and (k+1)-th are further apart than any rounding can move them
-      if (lane < k) out[lane] = knn_key_index(r0);
-      return;
-    }
-    // boundary decision on exact scores: `sure` = beats the k-th by more than delta (a prefix of
-    // the sorted list, < k long), `band` = within delta of the k-th (the positions after it)
-    const float hi = tk + delta, lo = tk - delta;
-    const bool s0 = r0 != 0ull && knn_key_value(r0) > hi, s1 = r1 != 0ull && knn_key_value(r1) > hi;
-    const bool b0 = r0 != 0ull && !s0 && knn_key_value(r0) >= lo, b1 = r1 != 0ull && !s1 && knn_key_value(r1) >= lo;
-    const int m = __popc(__ballot_sync(0xffffffffu, s0)) + __popc(__ballot_sync(0xffffffffu, s1));
-    const int nb = __popc(__ballot_sync(0xffffffffu, b0)) + __popc(__ballot_sync(0xffffffffu, b1));
-    __syncwarp();
-    wb[lane] = r0;
-    wb[lane + 32] = r1;
-    __syncwarp();
-    unsigned long long e0 = 0ull, e1 = 0ull;
-    if (lane < nb) {
-      const int j = knn_key_index(wb[m + lane]);
-      e0 = knn_key(knn_exact_score(xp + (long long)i * C, xp + (long long)j * C, C, xxi, xxp[j]), j);
-    }
-    if (lane + 32 < nb) {
-      const int j = knn_key_index(wb[m + lane + 32]);
-      e1 = knn_key(knn_exact_score(xp + (long long)i * C, xp + (long long)j * C, C, xxi, xxp[j]), j);
-    }
-    knn_sort64(e0, e1, lane);  // exact order of the band, best first
-    const unsigned long long pick = __shfl_sync(0xffffffffu, e0, (lane - m) & 31);  // k - m <= 32
-    if (lane < m) out[lane] = knn_key_index(r0);
-    else if (lane < k) out[lane] = knn_key_index(pick);
+    knn_finish_row(r0, r1, total, lane, wb, delta, k, xp, xxp, xxi, i, C, out);
     return;
   }
   // more than 64 candidates (massive ties / adversarial layouts): exact scores for the row
+  for (int j = lane; j < N; j += 32)
+    Sr[j] = knn_exact_score(xp + (long long)i * C, xp + (long long)j * C, C, xxi, xxp[j]);
+  __syncwarp();
+  knn_select_slow(Sr, N, k, lane, out);
+}
+
+// slab-free path: the Gram kernel left <= 64 candidate keys per row (count > 64: overflow)
+__global__ void __launch_bounds__(KS_THREADS)
+knn_finish_kernel(const unsigned long long* __restrict__ cand, const int* __restrict__ count,
+                  const float* __restrict__ x, const float* __restrict__ xx, const unsigned* __restrict__ xxmax,
+                  const float* __restrict__ valids, long long rows, int N, int C, int k, float alpha,
+                  int* __restrict__ idx) {
+  __shared__ unsigned long long cbuf[KS_THREADS / 32][64];
+  __shared__ float srow[KS_THREADS / 32][1024];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long row = (long long)blockIdx.x * (KS_THREADS / 32) + warp;
+  if (row >= rows) return;
+  const int part = (int)(row / N), i = (int)(row % N);
+  if (valids != nullptr && valids[part] == 0.0f) return;
+  const int total = count[row];
+  const float xxi = xx[row];
+  const float delta = alpha * (xxi + __uint_as_float(xxmax[part]));
+  int* out = idx + row * k;
+  const float* xp = x + (long long)part * N * C;
+  const float* xxp = xx + (long long)part * N;
+  if (total <= 64) {
+    const unsigned long long* cl = cand + row * 64;
+    const unsigned long long r0 = lane < total ? cl[lane] : 0ull;
+    const unsigned long long r1 = lane + 32 < total ? cl[lane + 32] : 0ull;
+    knn_finish_row(r0, r1, total, lane, cbuf[warp], delta, k, xp, xxp, xxi, i, C, out);
+    return;
+  }
+  // overflow (massive ties / adversarial layouts / tiny clouds): exact scores for the whole row
+  float* Sr = srow[warp];
   for (int j = lane; j < N; j += 32)
     Sr[j] = knn_exact_score(xp + (long long)i * C, xp + (long long)j * C, C, xxi, xxp[j]);
   __syncwarp();
@@ -843,8 +890,10 @@ static int knn_chunk_items(int n, int N) {
 size_t mpa_knn_workspace_bytes_c(int n, int N, int C) {
   const size_t rows = (size_t)n * N;
   return mpa_knn_workspace_bytes(n, N) + 2 * align_up(sizeof(float) * rows, 256) + align_up(sizeof(unsigned) * n, 256) +
-         align_up((size_t)3 * rows * knn_kpad(C) * 2, 256) +
-         align_up(sizeof(float) * (size_t)knn_chunk_items(n, N) * N * N, 256);
+         align_up((size_t)2 * rows * knn_kpad(C) * 2, 256) +
+         // the larger of: score slab of one chunk (slab path) / 64 candidate keys + a count per row
+         std::max(align_up(sizeof(float) * (size_t)knn_chunk_items(n, N) * N * N, 256),
+                  align_up(rows * 64 * sizeof(unsigned long long), 256) + align_up(rows * sizeof(int), 256));
 }
 
 static int knn_tensor_core(const float* x, const float* valids, int n, int N, int C, int k, int32_t* idx, char* p,
@@ -854,7 +903,7 @@ static int knn_tensor_core(const float* x, const float* valids, int n, int N, in
   float* xx = (float*)p; p += align_up(sizeof(float) * rows, 256);
   float* hb = (float*)p; p += align_up(sizeof(float) * rows, 256);
   unsigned* xxmax = (unsigned*)p; p += align_up(sizeof(unsigned) * n, 256);
-  __nv_bfloat16* planes = (__nv_bfloat16*)p; p += align_up((size_t)3 * rows * Kp * 2, 256);
+  __nv_bfloat16* planes = (__nv_bfloat16*)p; p += align_up((size_t)2 * rows * Kp * 2, 256);
   float* S = (float*)p;
   MPA_CUDA(cudaMemsetAsync(xxmax, 0, sizeof(unsigned) * n, stream));
   {
@@ -863,11 +912,26 @@ static int knn_tensor_core(const float* x, const float* valids, int n, int N, in
   }
   MPA_LAUNCH_CHECK();
   // bound of (approximate - exact) / (|x_i|^2 + |x_j|^2), in units of the approximate score:
-  // 6 plane products x Kp/16 accumulation steps of the tensor core (4 ulp each, generous),
-  // the bias subtraction, and the oracle's own C + 8 roundings
-  // (x 2: both sides of a comparison may be off)
-  const float alpha =
-      2.0f * ((6.0f * (float)(Kp / 16 + 1) * 4.0f + 2.0f) * 1.1920929e-7f + (float)(C + 8) * 5.9604645e-8f);
+  // the plane products left out (hi.lo, mid.mid, lo.hi, ...: <= 3 * 2^-18 |x_i| |x_j| <= 2^-17 of
+  // the norm sum), 3 products x Kp/16 accumulation steps of the tensor core (4 ulp each, generous),
+  // the bias subtraction, and the oracle's own C + 8 roundings; x 2: both sides of a comparison
+  const float alpha = 2.0f * (7.6293945e-6f + (3.0f * (float)(Kp / 16 + 1) * 4.0f + 2.0f) * 1.1920929e-7f +
+                              (float)(C + 8) * 5.9604645e-8f);
+  // slab-free: candidates straight from the Gram kernel's epilogue (K <= 128, N <= 1024)
+  static const bool use_slab = getenv("MPA_KNN_SLAB") != nullptr;  // A/B: scores through the slab
+  if (!use_slab) {
+    unsigned long long* cand = (unsigned long long*)S;
+    int* count = (int*)((char*)S + align_up((size_t)rows * 64 * sizeof(unsigned long long), 256));
+    const int rc = launch_gram_candidates(planes, rows, N, Kp, n, hb, valids, xx, xxmax, alpha, k, cand, count, stream);
+    if (rc < 0) return rc;
+    if (rc == MPA_OK) {
+      ProfScope ps("knn_select", stream);
+      knn_finish_kernel<<<(unsigned)((rows + KS_THREADS / 32 - 1) / (KS_THREADS / 32)), KS_THREADS, 0, stream>>>(
+          cand, count, x, xx, xxmax, valids, rows, N, C, k, alpha, idx);
+      MPA_LAUNCH_CHECK();
+      return MPA_OK;
+    }
+  }
   const int chunk = knn_chunk_items(n, N);
   for (int z0 = 0; z0 < n; z0 += chunk) {
     const int items = n - z0 < chunk ? n - z0 : chunk;
@@ -898,7 +962,7 @@ int mpa_knn(const float* x, const float* valids, int n, int N, int C, int k, int
   static const int legacy = getenv("MPA_KNN_LEGACY") ? atoi(getenv("MPA_KNN_LEGACY")) : 0;
   // tensor-core scoring when the caller sized the workspace for it (mpa_knn_workspace_bytes_c)
   static const bool force_tile = getenv("MPA_KNN_TILE") != nullptr;  // A/B: the CUDA-core tile kernel
-  if (k <= 32 && N <= 1024 && !legacy && !force_tile && ws != nullptr &&
+  if (k <= 32 && N <= 1024 && knn_kpad(C) <= 128 && !legacy && !force_tile && ws != nullptr &&
       ws_bytes >= mpa_knn_workspace_bytes_c(n, N, C))
     return knn_tensor_core(x, valids, n, N, C, k, idx, (char*)scratch.base + mpa_knn_workspace_bytes(n, N), stream);
   float* xx = (float*)scratch.base;

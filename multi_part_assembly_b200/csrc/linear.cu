@@ -567,34 +567,60 @@ int launch_linear(const __nv_bfloat16* x, const __nv_bfloat16* w, int M, int N, 
 }
 
 // ---- persistent Gram kernel (k-NN scoring) ---------------------------------------------
-// out[z][i][j] = x_{z,i} . x_{z,j} + bias[z R + j] for the R rows of every item z, fp32-accurate
-// (three bf16 planes per operand, six plane products, smallest first).  K <= 128, so a whole
+// out[z][i][j] ~ x_{z,i} . x_{z,j} + bias[z R + j] for the R rows of every item z: two bf16 planes
+// per operand (hi, mid), three plane products, smallest first -- a filter with a known error bound.  K <= 128, so a whole
 // [128 x K] operand tile is resident: a CTA walks a contiguous range of [128 x 128] output
 // tiles, keeps the row-tile operand while the column tile changes, and double-buffers the
 // accumulator in TMEM so that the TMA load + MMAs of the next tile run under the epilogue of
 // the current one -- the kernel is bound by the 64 KB fp32 write of each tile, not by per-CTA
 // start-up as the one-tile-per-CTA GEMM is.
 constexpr int GR_KTILE = LN_BM * LN_BK * 2;  // [128 x 64] bf16 = 16 KB
-constexpr int GR_NB = 2;                     // column-tile k-blocks in flight
+constexpr int GR_NB = 3;                     // column-tile k-blocks in flight
+constexpr int GR_NPL = 2;                    // operand planes (hi, mid): products hi.hi + hi.mid + mid.hi, the
+                                             // dropped ones are <= 3 * 2^-18 |x_i| |x_j| (the caller's delta covers them)
 // staging tile of an epilogue warp: [32][36] floats (16-byte accesses) when it fits, [32][33]
 // (scalar accesses, conflict-free) for K = 128, where the operands leave 33 KB
 template <int KB>
 __host__ __device__ constexpr int gr_pitch() { return KB == 1 ? EP_PITCH : 33; }
 template <int KB>
 __host__ __device__ constexpr int gr_smem_bytes() {
-  return 3 * KB * GR_KTILE + GR_NB * 3 * GR_KTILE + LN_EPI_WARPS * 32 * gr_pitch<KB>() * 4 + 1024;
+  return GR_NPL * KB * GR_KTILE + GR_NB * GR_NPL * GR_KTILE + LN_EPI_WARPS * 32 * gr_pitch<KB>() * 4 + 1024;
 }
 static_assert(gr_smem_bytes<2>() <= 227 * 1024, "K = 128 operands + staging fit one SM");
 
-template <int KB>
+// CAND mode (k-NN without the score slab): every row tile is swept twice over its column tiles.
+// Sweep 0 keeps, per row, the maxima of the 32-column groups; the k-th largest of those is a lower
+// bound of the row's k-th best score (k distinct elements reach it).  Sweep 1 repeats the products
+// (the tensor pipe has the time: the kernel was bound by writing 64 KB per tile) and appends every
+// score within `delta` of that bound to the row's candidate list (<= 64 keys per row in global
+// memory; the count says when a row overflowed).  `knn_finish_kernel` (csrc/knn.cu) then sorts 64
+// keys per row instead of reading 4 KB of scores.
+struct GramCand {
+  const float* xx;          // [items * R] |x|^2 of the rows (for delta)
+  const unsigned* xxmax;    // [items] max |x|^2 of the item, as ordered uint bits
+  float alpha;              // delta = alpha * (|x_i|^2 + max_j |x_j|^2)
+  int k;
+  unsigned long long* cand; // [items * R][64] keys (score, ~column)
+  int* count;               // [items * R]
+};
+__device__ __forceinline__ unsigned long long gram_key(float v, int j) {  // = knn_key of csrc/knn.cu
+  const unsigned b = __float_as_uint(v);
+  const unsigned o = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  return ((unsigned long long)o << 32) | (unsigned long long)(~(unsigned)j);
+}
+constexpr int GC_PITCH = 33;  // floats per row of the group-maxima table (conflict-free per-row walks)
+
+template <int KB, bool CAND>
 __global__ void __launch_bounds__(LN_THREADS, 1)
 gram_scores_kernel(const __grid_constant__ CUtensorMap map_x, int plane_rows, int R, int row0, int items,
-                   const float* __restrict__ bias, const float* __restrict__ item_valid, float* __restrict__ out) {
+                   const float* __restrict__ bias, const float* __restrict__ item_valid, float* __restrict__ out,
+                   GramCand gc) {
+  constexpr int NSWEEP = CAND ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* As = smem;                                   // [3 planes][KB][128 x 64]: row tile, all of K
-  uint8_t* Bs = smem + 3 * KB * GR_KTILE;               // ring of GR_NB x [3 planes][128 x 64]: column-tile k-blocks
-  float* stage = reinterpret_cast<float*>(Bs + GR_NB * 3 * GR_KTILE);
+  uint8_t* As = smem;                                   // [planes][KB][128 x 64]: row tile, all of K
+  uint8_t* Bs = smem + GR_NPL * KB * GR_KTILE;          // ring of GR_NB x [planes][128 x 64]: column-tile k-blocks
+  float* stage = reinterpret_cast<float*>(Bs + GR_NB * GR_NPL * GR_KTILE);
   constexpr int PITCH = gr_pitch<KB>();
   __shared__ uint64_t a_full, b_full[GR_NB], b_empty[GR_NB], acc_full[2], acc_free[2];
   __shared__ uint32_t tmem_base_s;
@@ -618,7 +644,7 @@ gram_scores_kernel(const __grid_constant__ CUtensorMap map_x, int plane_rows, in
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer =====
       int prev_rt = -1, u = 0;
-      for (int rt = blockIdx.x; rt < n_rt; rt += gridDim.x) for (int nj = 0; nj < T; ++nj) {
+      for (int rt = blockIdx.x; rt < n_rt; rt += gridDim.x) for (int sw = 0; sw < NSWEEP; ++sw) for (int nj = 0; nj < T; ++nj) {
         const int z = rt / T, mi = rt - z * T;          // rt = z * T + mi
         if (item_valid != nullptr && item_valid[z] == 0.0f) continue;  // padded item: every role skips its tiles
         const int arow = row0 + z * R + mi * LN_BM, brow = row0 + z * R + nj * LN_BM;
@@ -629,24 +655,24 @@ gram_scores_kernel(const __grid_constant__ CUtensorMap map_x, int plane_rows, in
             // the MMAs that read the old row tile are those of the k-block uses < u: in order,
             // so the last one's commit covers them all
             if (u > 0) tc::mbar_wait(&b_empty[(u - 1) % GR_NB], ((u - 1) / GR_NB) & 1);
-            mbar_expect_tx(&a_full, 3 * KB * GR_KTILE);
-            for (int pl = 0; pl < 3; ++pl)
+            mbar_expect_tx(&a_full, GR_NPL * KB * GR_KTILE);
+            for (int pl = 0; pl < GR_NPL; ++pl)
               for (int k2 = 0; k2 < KB; ++k2)
                 tma_load_2d(As + (pl * KB + k2) * GR_KTILE, &map_x, k2 * LN_BK, pl * plane_rows + arow, &a_full);
             prev_rt = rt;
           }
-          mbar_expect_tx(&b_full[s], 3 * GR_KTILE);
-          for (int pl = 0; pl < 3; ++pl)
-            tma_load_2d(Bs + (s * 3 + pl) * GR_KTILE, &map_x, kb * LN_BK, pl * plane_rows + brow, &b_full[s]);
+          mbar_expect_tx(&b_full[s], GR_NPL * GR_KTILE);
+          for (int pl = 0; pl < GR_NPL; ++pl)
+            tma_load_2d(Bs + (s * GR_NPL + pl) * GR_KTILE, &map_x, kb * LN_BK, pl * plane_rows + brow, &b_full[s]);
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {  // ===== MMA issuer =====
       constexpr uint32_t IDESC = tc::make_idesc_bf16(LN_BM, 128);
-      constexpr int PA[6] = {1, 2, 0, 1, 0, 0}, PB[6] = {1, 0, 2, 0, 1, 0};  // smallest terms first
+      constexpr int NPROD = 3, PA[NPROD] = {1, 0, 0}, PB[NPROD] = {0, 1, 0};  // (plane of A, plane of B), smallest first
       int prev_rt = -1, u = 0, a_cnt = 0, tl = -1;
-      for (int rt = blockIdx.x; rt < n_rt; rt += gridDim.x) for (int nj = 0; nj < T; ++nj) {
+      for (int rt = blockIdx.x; rt < n_rt; rt += gridDim.x) for (int sw = 0; sw < NSWEEP; ++sw) for (int nj = 0; nj < T; ++nj) {
         if (item_valid != nullptr && item_valid[rt / T] == 0.0f) continue;
         ++tl;  // tiles actually processed: accumulator buffer and barrier phases follow this count
         const int buf = tl & 1;
@@ -661,11 +687,11 @@ gram_scores_kernel(const __grid_constant__ CUtensorMap map_x, int plane_rows, in
           const int s = u % GR_NB;
           tc::mbar_wait(&b_full[s], (u / GR_NB) & 1);
           tc::fence_after_sync();
-          const uint32_t a_addr = tc::smem_u32(As), b_addr = tc::smem_u32(Bs + s * 3 * GR_KTILE);
+          const uint32_t a_addr = tc::smem_u32(As), b_addr = tc::smem_u32(Bs + s * GR_NPL * GR_KTILE);
 #pragma unroll
           for (int k = 0; k < LN_BK; k += 16) {
 #pragma unroll
-            for (int p6 = 0; p6 < 6; ++p6)
+            for (int p6 = 0; p6 < NPROD; ++p6)
               tc::mma_bf16(acc, tc::make_desc_sw128(a_addr + (PA[p6] * KB + kb) * GR_KTILE + k * 2),
                            tc::make_desc_sw128(b_addr + PB[p6] * GR_KTILE + k * 2), IDESC,
                            (kb > 0 || k > 0 || p6 > 0) ? 1u : 0u);
@@ -682,9 +708,23 @@ gram_scores_kernel(const __grid_constant__ CUtensorMap map_x, int plane_rows, in
     float* tile = stage + (warp - 2) * 32 * PITCH;
     const bool vec = (R & 3) == 0;
     int tl = -1;
-    for (int rt = blockIdx.x; rt < n_rt; rt += gridDim.x) for (int nj = 0; nj < T; ++nj) {
+    // CAND: per-row tables in the (unused) staging area
+    float* s_mx = stage;                                           // [128][GC_PITCH] group maxima
+    float* s_thr = stage + LN_BM * GC_PITCH;                       // [128]
+    int* s_cnt = reinterpret_cast<int*>(s_thr + LN_BM);            // [128]
+    float* s_bias = reinterpret_cast<float*>(s_cnt + LN_BM);       // [8 * 128] the item's column bias
+    const float ninf = -__int_as_float(0x7f800000);
+    for (int rt = blockIdx.x; rt < n_rt; rt += gridDim.x) for (int sw = 0; sw < NSWEEP; ++sw) for (int nj = 0; nj < T; ++nj) {
       const int z = rt / T, mi = rt - z * T;
       if (item_valid != nullptr && item_valid[z] == 0.0f) continue;
+      if (CAND && sw == 0 && nj == 0) {
+        // new row tile: clear this thread's half of the row's group maxima, stage the item's bias
+#pragma unroll
+        for (int gidx = 0; gidx < 16; ++gidx) s_mx[row_local * GC_PITCH + half * 16 + gidx] = ninf;
+        for (int c = threadIdx.x - 64; c < T * LN_BM; c += LN_EPI_WARPS * 32)
+          s_bias[c] = (bias != nullptr && c < R) ? __ldg(bias + (long long)z * R + c) : 0.f;
+        tc::group_sync(1, LN_EPI_WARPS * 32);
+      }
       ++tl;
       const int buf = tl & 1;
       const int m0 = mi * LN_BM, n0 = nj * LN_BM;
@@ -692,17 +732,85 @@ gram_scores_kernel(const __grid_constant__ CUtensorMap map_x, int plane_rows, in
       tc::fence_after_sync();
       const uint32_t acc = tmem + (uint32_t)(buf * 128) + lane_off;
       float* obase = out + (long long)z * R * R;
+      if (CAND) {
+        // this thread's 64 columns of its row: both 32-column groups at once
+        float v[64];
+        tc::tmem_ld32(acc + (uint32_t)(half * 64), v);
+        tc::tmem_ld32(acc + (uint32_t)(half * 64 + 32), v + 32);
+        tc::tmem_ld_wait();
+        const int colb = n0 + half * 64;
+        const float* sb = s_bias + colb;
+        if (sw == 0) {
+#pragma unroll
+          for (int gq = 0; gq < 2; ++gq) {
+            float m8[8] = {ninf, ninf, ninf, ninf, ninf, ninf, ninf, ninf};  // independent chains
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(sb + 32 * gq + 4 * j4);
+              const float bq[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+              for (int e4 = 0; e4 < 4; ++e4) {
+                const int j = 4 * j4 + e4;
+                const float t = v[32 * gq + j] + bq[e4];
+                m8[j & 7] = (colb + 32 * gq + j < R) ? fmaxf(m8[j & 7], t) : m8[j & 7];
+              }
+            }
+            const float m = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])),
+                                  fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+            const int gidx = 2 * nj + gq;  // group index inside this half: <= 15 for T <= 8
+            s_mx[row_local * GC_PITCH + half * 16 + gidx] = m;
+          }
+        } else if (m0 + row_local < R) {
+          // ~1 of 32 scores passes: one shared-memory atomic per thread and group reserves the
+          // slots, the stores are predicated (a branch per element would serialise the warp)
+          const float thr = s_thr[row_local];
+          unsigned long long* cl = gc.cand + ((long long)z * R + m0 + row_local) * 64;
+#pragma unroll
+          for (int gq = 0; gq < 2; ++gq) {
+            unsigned pass = 0u;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(sb + 32 * gq + 4 * j4);
+              const float bq[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+              for (int e4 = 0; e4 < 4; ++e4) {
+                const int j = 4 * j4 + e4;
+                v[32 * gq + j] += bq[e4];
+                pass |= (colb + 32 * gq + j < R && v[32 * gq + j] >= thr) ? (1u << j) : 0u;
+              }
+            }
+            if (pass != 0u) {
+              int slot = atomicAdd(&s_cnt[row_local], __popc(pass));
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (pass & (1u << j)) {
+                  if (slot < 64) cl[slot] = gram_key(v[32 * gq + j], colb + 32 * gq + j);
+                  ++slot;
+                }
+              }
+            }
+          }
+        }
+      }
 #pragma unroll 1
-      for (int j0 = half * 64; j0 < half * 64 + 64; j0 += 32) {
+      for (int j0 = half * 64; !CAND && j0 < half * 64 + 64; j0 += 32) {
         float v[32];
         tc::tmem_ld32(acc + (uint32_t)j0, v);
         tc::tmem_ld_wait();
         const int col0 = n0 + j0;
         if (col0 >= R) continue;  // warp-uniform
         if (bias != nullptr) {  // the warp's 32 columns: the same address in every lane (broadcast loads)
-          const float* bz = bias + (long long)z * R;
+          const float* bz = bias + (long long)z * R + col0;
+          if (vec && col0 + 32 <= R && (reinterpret_cast<uintptr_t>(bz) & 15) == 0) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += (col0 + j < R) ? __ldg(bz + col0 + j) : 0.f;
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bz) + j4);
+              v[4 * j4] += b4.x; v[4 * j4 + 1] += b4.y; v[4 * j4 + 2] += b4.z; v[4 * j4 + 3] += b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += (col0 + j < R) ? __ldg(bz + j) : 0.f;
+          }
         }
         if (vec && col0 + 32 <= R) {
           // through the warp's staging tile: one instruction then moves 4 rows x 128 contiguous bytes
@@ -736,6 +844,41 @@ gram_scores_kernel(const __grid_constant__ CUtensorMap map_x, int plane_rows, in
       }
       tc::fence_before_sync();
       mbar_arrive(&acc_free[buf]);
+      if (CAND && nj == T - 1) {
+        tc::group_sync(1, LN_EPI_WARPS * 32);  // the sweep's tables are complete
+        if (sw == 0) {
+          // k-th largest of every row's 32 group maxima: warp w sorts the rows 16 w .. 16 w + 15,
+          // one value per lane, bitonic network by shuffles (descending)
+          {
+            const int w8 = warp - 2;
+#pragma unroll 4
+            for (int rr = 0; rr < 16; ++rr) {
+              const int rloc = w8 * 16 + rr;
+              float a = s_mx[rloc * GC_PITCH + lane];
+#pragma unroll
+              for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+                for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+                  const float pa = __shfl_xor_sync(0xffffffffu, a, jj);
+                  const bool lower = (lane & jj) == 0;
+                  const bool desc = (lane & kk) == 0 || kk == 32;
+                  a = (lower == desc) ? fmaxf(a, pa) : fminf(a, pa);
+                }
+              }
+              if (lane == gc.k - 1) {
+                const long long grow = (long long)z * R + m0 + rloc;
+                float thr = ninf;
+                if (m0 + rloc < R && a > ninf) thr = a - gc.alpha * (gc.xx[grow] + __uint_as_float(gc.xxmax[z]));
+                s_thr[rloc] = thr;
+                s_cnt[rloc] = 0;
+              }
+            }
+          }
+        } else if (half == 0 && m0 + row_local < R) {
+          gc.count[(long long)z * R + m0 + row_local] = s_cnt[row_local];
+        }
+        tc::group_sync(1, LN_EPI_WARPS * 32);
+      }
     }
   }
   tc::fence_before_sync();
@@ -749,54 +892,63 @@ gram_scores_kernel(const __grid_constant__ CUtensorMap map_x, int plane_rows, in
 int launch_gram_batched(const __nv_bfloat16* x_planes, long long total_rows, int R, int K, int z0, int items,
                         const float* bias, const float* item_valid, float* out, const char* name,
                         cudaStream_t stream) {
-  MPA_CHECK_ARG(K % 8 == 0 && total_rows * 3 < (1ll << 31), "gram: K %% 8 == 0 and 3 * rows < 2^31");
-  CUtensorMap mx, mw;
-  int rc = make_map(&mx, x_planes, (int)(3 * total_rows), K, LN_BM);
+  MPA_CHECK_ARG(K % 8 == 0 && K <= 2 * LN_BK && total_rows * GR_NPL < (1ll << 31),
+                "gram: K %% 8 == 0, K <= 128 and planes * rows < 2^31");
+  CUtensorMap mx;
+  int rc = make_map(&mx, x_planes, (int)(GR_NPL * total_rows), K, LN_BM);
   if (rc != MPA_OK) return rc;
-  rc = make_map(&mw, x_planes, (int)(3 * total_rows), K, 128);
+  static DeviceOnce attr2;
+  if (attr2.pending()) {
+    MPA_CUDA(cudaFuncSetAttribute(gram_scores_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gr_smem_bytes<1>()));
+    MPA_CUDA(cudaFuncSetAttribute(gram_scores_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gr_smem_bytes<2>()));
+    attr2.done();
+  }
+  const int T = (R + LN_BM - 1) / LN_BM;
+  int ctas = device_sms();
+  if (ctas > items * T) ctas = items * T;
+  const float* b = bias != nullptr ? bias + (long long)z0 * R : nullptr;
+  const float* iv = item_valid != nullptr ? item_valid + z0 : nullptr;  // [items]: 0 = skip the item
+  {
+    ProfScope ps(name, stream);
+    if (K <= LN_BK)
+      gram_scores_kernel<1, false><<<ctas, LN_THREADS, gr_smem_bytes<1>(), stream>>>(mx, (int)total_rows, R, z0 * R,
+                                                                                     items, b, iv, out, GramCand{});
+    else
+      gram_scores_kernel<2, false><<<ctas, LN_THREADS, gr_smem_bytes<2>(), stream>>>(mx, (int)total_rows, R, z0 * R,
+                                                                                     items, b, iv, out, GramCand{});
+  }
+  MPA_LAUNCH_CHECK();
+  return MPA_OK;
+}
+
+// k-NN candidate extraction for ALL items in one launch (no score slab): see GramCand.
+// Returns MPA_ERR_ARG-free "not supported" as 1 when K > 128 (the caller falls back to the slab path).
+int launch_gram_candidates(const __nv_bfloat16* x_planes, long long total_rows, int R, int K, int items,
+                           const float* bias, const float* item_valid, const float* xx, const unsigned* xxmax,
+                           float alpha, int k, unsigned long long* cand, int* count, cudaStream_t stream) {
+  if (K > 2 * LN_BK || (R + LN_BM - 1) / LN_BM > 8) return 1;
+  MPA_CHECK_ARG(K % 8 == 0 && total_rows * GR_NPL < (1ll << 31), "gram: K %% 8 == 0 and planes * rows < 2^31");
+  CUtensorMap mx;
+  int rc = make_map(&mx, x_planes, (int)(GR_NPL * total_rows), K, LN_BM);
   if (rc != MPA_OK) return rc;
   static DeviceOnce attr;
   if (attr.pending()) {
-    MPA_CUDA(cudaFuncSetAttribute(linear_bf16_kernel<128, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  ln_smem_bytes(128, 3)));
+    MPA_CUDA(cudaFuncSetAttribute(gram_scores_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gr_smem_bytes<1>()));
+    MPA_CUDA(cudaFuncSetAttribute(gram_scores_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gr_smem_bytes<2>()));
     attr.done();
   }
-  static const bool generic = getenv("MPA_GRAM_GENERIC") != nullptr;  // A/B: the one-tile-per-CTA kernel
-  if (K <= 2 * LN_BK && !generic) {
-    static DeviceOnce attr2;
-    if (attr2.pending()) {
-      MPA_CUDA(cudaFuncSetAttribute(gram_scores_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, gr_smem_bytes<1>()));
-      MPA_CUDA(cudaFuncSetAttribute(gram_scores_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, gr_smem_bytes<2>()));
-      attr2.done();
-    }
-    const int T = (R + LN_BM - 1) / LN_BM;
-    int ctas = device_sms();
-    if (ctas > items * T) ctas = items * T;
-    const float* b = bias != nullptr ? bias + (long long)z0 * R : nullptr;
-    const float* iv = item_valid != nullptr ? item_valid + z0 : nullptr;  // [items]: 0 = skip the item
-    {
-      ProfScope ps(name, stream);
-      if (K <= LN_BK)
-        gram_scores_kernel<1><<<ctas, LN_THREADS, gr_smem_bytes<1>(), stream>>>(mx, (int)total_rows, R, z0 * R, items, b,
-                                                                                iv, out);
-      else
-        gram_scores_kernel<2><<<ctas, LN_THREADS, gr_smem_bytes<2>(), stream>>>(mx, (int)total_rows, R, z0 * R, items, b,
-                                                                                iv, out);
-    }
-    MPA_LAUNCH_CHECK();
-    return MPA_OK;
-  }
-  LinearEpilogue ep{bias != nullptr ? bias + (long long)z0 * R : nullptr, nullptr, out, nullptr, ACT_NONE};
-  ep.batch_rows = R;
-  ep.batch_row0 = z0 * R;
-  ep.out_batch_stride = (long long)R * R;
-  ep.vec = (R % 8 == 0) && aligned16(ep.bias) && aligned16(out);
-  // plane pl of item z starts at operand row pl * total_rows + (z0 + z) * R
-  dim3 grid((R + LN_BM - 1) / LN_BM, (R + 127) / 128, items);
+  const int T = (R + LN_BM - 1) / LN_BM;
+  int ctas = device_sms();
+  if (ctas > items * T) ctas = items * T;
+  GramCand gc{xx, xxmax, alpha, k, cand, count};
   {
-    ProfScope ps(name, stream);
-    linear_bf16_kernel<128, false, 3><<<grid, LN_THREADS, ln_smem_bytes(128, 3), stream>>>(
-        mx, mw, R, R, K, (int)total_rows, (int)total_rows, ep);
+    ProfScope ps("knn_gram", stream);
+    if (K <= LN_BK)
+      gram_scores_kernel<1, true><<<ctas, LN_THREADS, gr_smem_bytes<1>(), stream>>>(mx, (int)total_rows, R, 0, items, bias,
+                                                                                    item_valid, nullptr, gc);
+    else
+      gram_scores_kernel<2, true><<<ctas, LN_THREADS, gr_smem_bytes<2>(), stream>>>(mx, (int)total_rows, R, 0, items, bias,
+                                                                                    item_valid, nullptr, gc);
   }
   MPA_LAUNCH_CHECK();
   return MPA_OK;

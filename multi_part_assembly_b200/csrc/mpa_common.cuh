@@ -59,6 +59,11 @@ int launch_gram_batched(const __nv_bfloat16* x_planes, long long total_rows, int
                         const float* bias, const float* item_valid, float* out, const char* name,
                         cudaStream_t stream);
 
+// ... and the slab-free variant: <= 64 candidate keys per row (1 = shape not supported, use the slab path)
+int launch_gram_candidates(const __nv_bfloat16* x_planes, long long total_rows, int R, int K, int items,
+                           const float* bias, const float* item_valid, const float* xx, const unsigned* xxmax,
+                           float alpha, int k, unsigned long long* cand, int* count, cudaStream_t stream);
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Function attributes (dynamic shared memory limits) and the SM count are PER DEVICE: a
