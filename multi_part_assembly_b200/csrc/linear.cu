@@ -584,7 +584,9 @@ template <int KB>
 __host__ __device__ constexpr int gr_pitch() { return KB == 1 ? EP_PITCH : 33; }
 template <int KB>
 __host__ __device__ constexpr int gr_smem_bytes() {
-  return GR_NPL * KB * GR_KTILE + GR_NB * GR_NPL * GR_KTILE + LN_EPI_WARPS * 32 * gr_pitch<KB>() * 4 + 1024;
+  // staging / tables: the slab mode needs 8 warp tiles, the candidate mode 128 x 33 group maxima +
+  // thresholds + counters + 1024 biases + 256 x 33 value strips = 55.8 KB
+  return GR_NPL * KB * GR_KTILE + GR_NB * GR_NPL * GR_KTILE + 56 * 1024 + 1024;
 }
 static_assert(gr_smem_bytes<2>() <= 227 * 1024, "K = 128 operands + staging fit one SM");
 
@@ -713,6 +715,7 @@ gram_scores_kernel(const __grid_constant__ CUtensorMap map_x, int plane_rows, in
     float* s_thr = stage + LN_BM * GC_PITCH;                       // [128]
     int* s_cnt = reinterpret_cast<int*>(s_thr + LN_BM);            // [128]
     float* s_bias = reinterpret_cast<float*>(s_cnt + LN_BM);       // [8 * 128] the item's column bias
+    float* s_vst = s_bias + 8 * LN_BM;                             // [256][GC_PITCH] per-thread strips
     const float ninf = -__int_as_float(0x7f800000);
     for (int rt = blockIdx.x; rt < n_rt; rt += gridDim.x) for (int sw = 0; sw < NSWEEP; ++sw) for (int nj = 0; nj < T; ++nj) {
       const int z = rt / T, mi = rt - z * T;
@@ -765,6 +768,7 @@ gram_scores_kernel(const __grid_constant__ CUtensorMap map_x, int plane_rows, in
           // slots, the stores are predicated (a branch per element would serialise the warp)
           const float thr = s_thr[row_local];
           unsigned long long* cl = gc.cand + ((long long)z * R + m0 + row_local) * 64;
+          float* vst = s_vst + (threadIdx.x - 64) * GC_PITCH;
 #pragma unroll
           for (int gq = 0; gq < 2; ++gq) {
             unsigned pass = 0u;
@@ -780,13 +784,17 @@ gram_scores_kernel(const __grid_constant__ CUtensorMap map_x, int plane_rows, in
               }
             }
             if (pass != 0u) {
-              int slot = atomicAdd(&s_cnt[row_local], __popc(pass));
+              // the group goes to this thread's private strip of shared memory, so that the few
+              // set bits can be walked with a dynamic index (32 tests + branches per group were
+              // a third of the kernel's stall samples)
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if (pass & (1u << j)) {
-                  if (slot < 64) cl[slot] = gram_key(v[32 * gq + j], colb + 32 * gq + j);
-                  ++slot;
-                }
+              for (int j = 0; j < 32; ++j) vst[j] = v[32 * gq + j];
+              int slot = atomicAdd(&s_cnt[row_local], __popc(pass));
+              while (pass != 0u) {
+                const int j = __ffs(pass) - 1;
+                pass &= pass - 1u;
+                if (slot < 64) cl[slot] = gram_key(vst[j], colb + 32 * gq + j);
+                ++slot;
               }
             }
           }
