@@ -373,12 +373,12 @@ def run_native(args):
 
     per_gpu = c['batch'] // world if c['scaling'] == 'strong' else c['batch']
     assert per_gpu >= 1, 'more ranks than shapes'
-    # Weak scaling: every rank steps the SAME synthetic batch.  The cost of the exact Chamfer
-    # search depends on the geometry (+-10 % between random batches, profiles/r02_bench_n8.json),
-    # and the max over ranks of N different draws would read as a scaling loss that is not one:
-    # there is no collective in this step.  Strong scaling (cfg E) slices one global batch, so
-    # its ranks necessarily hold different shapes.
-    data_seed = rank if c['scaling'] == 'strong' else 0
+    # Every rank has the same weights (as under DDP) and its own synthetic batch (seed = rank).
+    # With per-rank random WEIGHTS the step time spreads by +-10 % (profiles/
+    # r02_bench_n8_distinct_batches.json: the poses an untrained model predicts decide how many
+    # queries of the exact search are far from the other cloud); with shared weights different
+    # batches step in the same time (cfg_e_strong's per-rank times).
+    data_seed = rank
     w = setup(c['model'], c['encoder'], per_gpu, c['valid'], args.points, data_seed,
               c.get('dataset', 'everyday'))
     model, hosts, resident, graphed = w['model'], w['hosts'], w['resident'], w['graphed']
@@ -502,7 +502,7 @@ def run_native(args):
             saved = amp
             amp = torch.bfloat16 if oc['dtype'] == 'bf16' else None  # setup()/eager_step read `amp`
             try:
-                we = setup(oc['model'], oc['encoder'], oc['batch'], oc['valid'], oc['points'], 0)
+                we = setup(oc['model'], oc['encoder'], oc['batch'], oc['valid'], oc['points'], rank)
                 k_o = max(5, min(args.steps, 20))
                 for _ in range(3):
                     we['step']()
@@ -625,9 +625,7 @@ def run_native(args):
                    'l2': 'flushed (192 MiB memset) before every timed step',
                    'mode': 'training-mode forward (BatchNorm batch statistics) + all loss terms, '
                            'no autograd recording, dropout 0',
-                   'rank_data': ('one global batch sliced over the ranks' if c['scaling'] == 'strong' else
-                                 'same weights and same synthetic batch on every rank (no collective in '
-                                 'fwd+loss; the search cost is data dependent)'),
+                   'rank_data': 'same weights on every rank (as under DDP), a different synthetic batch per rank',
                    'cuda_graph': graphed is not None, 'graph_error': graph_error},
         'clocks': clocks,
         'e2e': {'value': shapes / (ms_e2e / 1e3), 'unit': 'shapes/s',
