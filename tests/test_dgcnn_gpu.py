@@ -13,7 +13,12 @@ GOLD = os.path.join(os.path.dirname(__file__), 'golden')
 
 
 @pytest.mark.parametrize('n,N,C,k', [(3, 64, 3, 20), (4, 1000, 3, 20), (2, 1000, 64, 20),
-                                     (2, 777, 128, 20), (1, 1500, 64, 20), (2, 33, 5, 7)])
+                                     (2, 777, 128, 20), (1, 1500, 64, 20), (2, 33, 5, 7),
+                                     # tensor-core path corners: one / two k-blocks, N % 4 != 0 (scalar
+                                     # epilogue), several row tiles with a ragged tail, k = 32, C > 128
+                                     # (CUDA-core tile kernel), fewer than k column groups (overflow path)
+                                     (3, 130, 72, 20), (2, 1023, 8, 32), (2, 257, 128, 5), (1, 300, 136, 20),
+                                     (5, 200, 64, 20)])
 def test_knn_bit_exact_vs_oracle(cuda, n, N, C, k):
     """north_star: bit-exact k-NN indices.  Contract = the sorted index set per
     row (EdgeConv only sees the set); here even the order matches the oracle's
@@ -123,3 +128,17 @@ def test_dgcnn_valids_mask_equals_compaction(cuda, global_feat):
         a, b = getattr(enc, name), getattr(ref, name)
         np.testing.assert_allclose(a.running_mean.cpu().numpy(), b.running_mean.cpu().numpy(), rtol=1e-5, atol=1e-7)
         np.testing.assert_allclose(a.running_var.cpu().numpy(), b.running_var.cpu().numpy(), rtol=1e-5, atol=1e-7)
+
+
+def test_knn_skips_padded_parts(cuda):
+    """`valids`: padded parts keep zero rows, the others are unaffected (tensor-core path: the
+    Gram kernel skips the tiles of padded items)."""
+    from multi_part_assembly_b200 import kernels
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((6, 300, 64)).astype(np.float32)
+    valids = torch.tensor([1, 0, 1, 1, 0, 1.], device=cuda)
+    got = kernels.knn(torch.from_numpy(x).to(cuda), 20, valids=valids).cpu().numpy().astype(np.int64)
+    want = oracle.knn(np.ascontiguousarray(x.transpose(0, 2, 1)), 20)
+    keep = valids.cpu().numpy() != 0
+    np.testing.assert_array_equal(np.sort(got[keep], -1), want[keep])
+    assert (got[~keep] == 0).all()

@@ -497,3 +497,76 @@ def test_linear_fp32_accurate_mode(cuda, M, N, K, act, res):
     err = float((out.double() - want).abs().max())
     err32 = float((ref32.double() - want).abs().max())
     assert err <= max(8 * err32, 5e-6 * scale), (err, err32, scale)
+
+
+@pytest.mark.parametrize('B', [3, 100, 520])
+def test_transformer_cluster_widths_agree(cuda, B):
+    """The fused FFN block splits the hidden dimension over a thread-block cluster when there are
+    few token tiles (B = 3: 8 CTAs per tile, B = 100: 8, B = 520: one CTA per tile).  All widths
+    compute the same function: compared with the fp32 torch layer chain at the bf16 bar, and
+    the batch-size independence of a shape's output is checked across widths."""
+    from multi_part_assembly_b200 import kernels
+    from multi_part_assembly_b200.models.pn_transformer import TransformerEncoder
+    P, D, H, FF, Lyr = 20, 256, 8, 1024, 4
+    tr = fill_params_(TransformerEncoder(D, H, FF, Lyr), 11).to(cuda).eval()
+    g = torch.Generator().manual_seed(B)
+    tokens = torch.randn(B, P, D, generator=g).to(cuda)
+    valid = torch.ones(B, P, dtype=torch.bool, device=cuda)
+    valid[0, 13:] = False
+    kernels.set_precision('bf16')
+    try:
+        with torch.no_grad():
+            out = tr(tokens, valid)
+            small = tr(tokens[:3].contiguous(), valid[:3].contiguous())  # 8-wide clusters
+    finally:
+        kernels.set_precision('auto')
+    enc = tr.transformer_encoder if hasattr(tr, 'transformer_encoder') else tr
+    enc = next(m for m in tr.modules() if isinstance(m, torch.nn.TransformerEncoder))
+    with torch.no_grad():
+        want = kernels._transformer_masked_torch(tokens, valid, enc, H, None, 0.0)
+    v = valid.cpu().numpy()
+    a, b = out.cpu().numpy(), want.cpu().numpy()
+    assert np.isfinite(a).all()
+    assert np.abs(a[v] - b[v]).max() / np.abs(b[v]).max() < 3e-2
+    # a shape's tokens only see that shape: the first three shapes do not depend on the batch size.
+    # Different cluster widths add the hidden-dimension partial sums in a different order; a last-bit
+    # difference can flip the bf16 rounding of the next layer's operand, so the bar is the bf16 one
+    np.testing.assert_allclose(a[:3][v[:3]], small.cpu().numpy()[v[:3]], rtol=0, atol=1e-2 * np.abs(b).max())
+
+
+def test_pointnet_stash_is_bit_identical(cuda):
+    """mpa_pointnet_forward with the large workspace (launches 4 and 5 resume from stashed operand
+    tiles) and with the small one (every launch recomputes from the points) give the same bits."""
+    from multi_part_assembly_b200 import _lib
+    from multi_part_assembly_b200.kernels import _ptr_array
+    from multi_part_assembly_b200.models import build_encoder
+    enc = fill_params_(build_encoder('pointnet', 256), 3).to(cuda).train()
+    convs = [m for m in enc.modules() if isinstance(m, torch.nn.Conv1d)]
+    bns = [m for m in enc.modules() if isinstance(m, torch.nn.BatchNorm1d)]
+    g = torch.Generator().manual_seed(2)
+    n, N = 37, 500
+    x = (torch.rand(n, N, 3, generator=g) - 0.5).to(cuda).contiguous()
+    valids = torch.ones(n, device=cuda)
+    valids[5] = 0
+    L = _lib.lib()
+    w = [c.weight.detach().reshape(c.weight.shape[0], -1).float().contiguous() for c in convs]
+    outs = []
+    for big in (True, False):
+        rm = [b.running_mean.clone() for b in bns]
+        rv = [b.running_var.clone() for b in bns]
+        nb = L.mpa_pointnet_workspace_bytes_n(n, N) if big else L.mpa_pointnet_workspace_bytes(n)
+        ws = torch.empty(nb, dtype=torch.uint8, device=cuda)
+        feats = torch.empty(n, 256, device=cuda)
+        with torch.cuda.device(cuda):
+            rc = L.mpa_pointnet_forward(_lib.ptr(x), _lib.ptr(valids), n, N, 256, _ptr_array(w),
+                                        _ptr_array([b.weight.detach() for b in bns]),
+                                        _ptr_array([b.bias.detach() for b in bns]), _ptr_array(rm), _ptr_array(rv),
+                                        1, float(bns[0].eps), float(bns[0].momentum), _lib.ptr(feats), _lib.ptr(ws),
+                                        nb, _lib.cuda_stream(cuda))
+        _lib.check(rc, 'mpa_pointnet_forward')
+        torch.cuda.synchronize()
+        outs.append((feats.cpu(), [t.cpu() for t in rm + rv]))
+    assert L.mpa_pointnet_workspace_bytes_n(n, N) > L.mpa_pointnet_workspace_bytes(n)
+    assert torch.equal(outs[0][0], outs[1][0])
+    for a, b in zip(outs[0][1], outs[1][1]):
+        assert torch.equal(a, b)
