@@ -1148,6 +1148,12 @@ encoder_ffn_block_kernel(const __grid_constant__ CUtensorMap map_att, const __gr
   __shared__ __align__(16) float s_b1[FB_MAX_FF];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (a.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 32) {  // kernel entry, wall clock (ns) and cycles
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    a.dbg[60] = (long long)gt;
+    a.dbg[61] = clock64();
+  }
   const int cl = a.cl;
   const int tile_i = blockIdx.x / cl, rank = blockIdx.x - tile_i * cl;  // cluster = cl consecutive CTAs
   const int m0 = tile_i * LN_BM;
@@ -1314,6 +1320,7 @@ encoder_ffn_block_kernel(const __grid_constant__ CUtensorMap map_att, const __gr
                          : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
+    const int own_n = LN_BM / cl, own0 = rank * own_n;  // tile rows this CTA finishes in cluster mode
     fetch_rows(a.x_in, c_begin);  // issued before the wait: its latency hides behind out_proj
     tc::mbar_wait(&acc0_o_done, 0);
     tc::fence_after_sync();
@@ -1343,8 +1350,8 @@ encoder_ffn_block_kernel(const __grid_constant__ CUtensorMap map_att, const __gr
         } else {
           // every CTA of the cluster computes the whole tile (x_out may alias x_in, which the
           // siblings are still reading): keep only the rows this CTA finishes, in scratch
-          const int rl = r - m0, own0 = rank * (LN_BM / cl);
-          if (rl >= own0 && rl < own0 + LN_BM / cl)
+          const int rl = r - m0;
+          if (rl >= own0 && rl < own0 + own_n)
             *reinterpret_cast<float4*>(a.x1s + ((long long)tile_i * LN_BM + rl) * FB_D + j0 + qcol) = xq[i];
         }
         *tile_quad(tile, lane, i) = xq[i];
@@ -1486,7 +1493,14 @@ encoder_ffn_block_kernel(const __grid_constant__ CUtensorMap map_att, const __gr
       if (cl == 8) fb_reduce_owned_rows<8>(a, tile_i, rank, s_vec);
       else if (cl == 4) fb_reduce_owned_rows<4>(a, tile_i, rank, s_vec);
       else fb_reduce_owned_rows<2>(a, tile_i, rank, s_vec);
-      if (threadIdx.x == 64) FB_STAMP(36);
+      if (threadIdx.x == 64) {
+        FB_STAMP(36);
+        if (a.dbg != nullptr && blockIdx.x == 0) {
+          unsigned long long gt;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+          a.dbg[62] = (long long)gt;
+        }
+      }
     }
   }
 }

@@ -43,6 +43,7 @@ del os.environ['MPA_FFN_DEBUG']
 d = dbg.cpu().tolist()
 t0 = d[0]
 rel = lambda i: (d[i] - t0) if d[i] else None
+print('kernel entry -> MMA thread start (cycles):', d[0] - d[61], ' entry -> cluster reduce done (ns):', d[62] - d[60])
 print('MMA thread: att_full', rel(1), 'out_proj issued', rel(2), 'a1_ready', rel(3), 'all issued', rel(4))
 print('MMA thread hid_ready waits done at', [rel(8 + c) for c in range(8)])
 print('epilogue: E1', rel(32), rel(33), '(residual slabs done', rel(37), ')  E3', rel(34), rel(35), ' cluster reduce done', rel(36))
