@@ -212,21 +212,21 @@ __global__ void __launch_bounds__(PN_THREADS, 1) pointnet_phase_kernel(PointNetA
   uint32_t parity = 0;
 
   const int tiles_per_part = (a.N + PN_TILE - 1) / PN_TILE;
-  const long long n_tiles = (long long)a.n_parts * tiles_per_part;
+  const int n_tiles = a.n_parts * tiles_per_part;  // 32-bit tile arithmetic (host checks the range)
   const int worker = blockIdx.x * PN_GROUPS + g;
   const int n_workers = gridDim.x * PN_GROUPS;
 
   // tiles of this pipeline, padded parts skipped (uniform per pipeline)
-  auto next_tile = [&](long long tl) {
-    while (tl < n_tiles && a.valids != nullptr && a.valids[(int)(tl / tiles_per_part)] == 0.0f) tl += n_workers;
+  auto next_tile = [&](int tl) {
+    while (tl < n_tiles && a.valids != nullptr && a.valids[tl / tiles_per_part] == 0.0f) tl += n_workers;
     return tl;
   };
   // stash prefetch: the a_{PHASE-2} tile of the NEXT tile streams into this pipeline's 8 KB
   // buffer (cp.async, 4 x 16 B per thread) while the current tile is in its later layers
   uint8_t* pf = wsm + g * PN_ACT_KB;
   static_assert(PN_GROUPS * PN_ACT_KB <= 2 * PN_WTILE, "prefetch tiles fit the images of layers 1 and 2");
-  auto prefetch = [&](long long tl) {
-    const uint4* src = a.stash_in + tl * (PN_ACT_KB / 16);
+  auto prefetch = [&](int tl) {
+    const uint4* src = a.stash_in + (long long)tl * (PN_ACT_KB / 16);
 #pragma unroll
     for (int j = 0; j < PN_ACT_KB / 16 / 128; ++j)
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(pf + (j * 128 + t) * 16)),
@@ -234,17 +234,17 @@ __global__ void __launch_bounds__(PN_THREADS, 1) pointnet_phase_kernel(PointNetA
                    : "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  long long tile = next_tile(worker);
+  int tile = next_tile(worker);
   if (resume && tile < n_tiles) prefetch(tile);
 
   for (; tile < n_tiles;) {
-    const long long tile_next = next_tile(tile + n_workers);
-    const int part = (int)(tile / tiles_per_part);
-    const int p0 = (int)(tile % tiles_per_part) * PN_TILE;
+    const int tile_next = next_tile(tile + n_workers);
+    const int part = tile / tiles_per_part;
+    const int p0 = (tile - part * tiles_per_part) * PN_TILE;
     const int npts = min(PN_TILE, a.N - p0);
 
     const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && tid == 0 && tile < 8 * n_workers;
-    long long* dbg = a.dbg + (tile / n_workers) * 16;
+    long long* dbg = dbg_on ? a.dbg + (tile / n_workers) * 16 : nullptr;
     if (dbg_on) dbg[0] = clock64();
     // the previous tile's stash copy read `act` with ordinary loads: all of them are done
     if (PHASE <= 4 && a.stash_out != nullptr) tc::group_sync(1 + g, 128);
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(PN_THREADS, 1) pointnet_phase_kernel(PointNetA
         tc::group_sync(1 + g, 128);
         if (PHASE <= 4 && layer == PHASE - 1 && a.stash_out != nullptr) {
           // a_{PHASE-1} (64 channels = K-block 0) -> global, coalesced, while the next MMA reads it
-          uint4* dstg = a.stash_out + tile * (PN_ACT_KB / 16);
+          uint4* dstg = a.stash_out + (long long)tile * (PN_ACT_KB / 16);
 #pragma unroll
           for (int j = 0; j < PN_ACT_KB / 16 / 128; ++j)
             __stcs(dstg + j * 128 + t, *reinterpret_cast<const uint4*>(act + (j * 128 + t) * 16));
@@ -700,6 +700,7 @@ int mpa_pointnet_forward_ex(const float* pts, const float* valids, int n_parts, 
   MPA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int tiles_per_part = (N + PN_TILE - 1) / PN_TILE;
   const long long n_tiles = (long long)n_parts * tiles_per_part;
+  MPA_CHECK_ARG(n_tiles + 4096 < (1ll << 31), "pointnet_forward: n_parts * ceil(N / 64) must fit 31 bits");
   int grid = (int)((n_tiles + PN_GROUPS - 1) / PN_GROUPS);
   if (grid > sms) grid = sms;
   if (grid > 160) grid = 160;
