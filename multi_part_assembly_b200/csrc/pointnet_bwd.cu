@@ -114,7 +114,7 @@ bn_stats_kernel(const __nv_bfloat16* __restrict__ z, long long M, int C, int N,
 #pragma unroll
     for (int u = 0; u < PB_UNROLL; ++u) {  // all loads first: PB_UNROLL packets in flight per thread
       const long long m = m0 + u * stride;
-      ok[u] = m < M && (valids == nullptr || valids[m / N] != 0.f);
+      ok[u] = m < M && (valids == nullptr || valids[(unsigned)m / (unsigned)N] != 0.f);
       raw[u] = ok[u] ? ld_packet(z + (base + u * rstride)) : make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
@@ -174,7 +174,7 @@ bn_act_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ sca
 #pragma unroll
     for (int u = 0; u < PB_UNROLL; ++u) {
       const long long m = m0 + u * stride;
-      ok[u] = m < M && (valids == nullptr || valids[m / N] != 0.f);
+      ok[u] = m < M && (valids == nullptr || valids[(unsigned)m / (unsigned)N] != 0.f);
       raw[u] = ok[u] ? ld_packet(z + (base + u * rstride)) : make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
@@ -207,7 +207,7 @@ __device__ __forceinline__ Bf8 incoming_grad(bool has_da, const uint4& da_raw,
     for (int i = 0; i < 8; ++i)
       if (!(fmaf(zv.v[i], sc[i], sh[i]) > 0.f)) dy.v[i] = 0.f;
   } else {
-    const long long part = m / N;
+    const long long part = (unsigned)m / (unsigned)N;  // rows < 2^31 (checked on the host)
     const int local = (int)(m - part * N);
     const int4 a0 = *reinterpret_cast<const int4*>(arg + part * C + col * 8);
     const int4 a1 = *reinterpret_cast<const int4*>(arg + part * C + col * 8 + 4);
@@ -249,7 +249,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ da, const float* __restri
 #pragma unroll
     for (int u = 0; u < PB_BWD_UNROLL; ++u) {
       const long long m = m0 + u * stride;
-      ok[u] = m < M && (valids == nullptr || valids[m / N] != 0.f);
+      ok[u] = m < M && (valids == nullptr || valids[(unsigned)m / (unsigned)N] != 0.f);
       zr[u] = ok[u] ? ld_packet(z + (base + u * rstride)) : make_uint4(0u, 0u, 0u, 0u);
       dr[u] = (ok[u] && da != nullptr) ? ld_packet(da + (base + u * rstride)) : make_uint4(0u, 0u, 0u, 0u);
     }
@@ -305,7 +305,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ da, const float* __restric
 #pragma unroll
     for (int u = 0; u < PB_BWD_UNROLL; ++u) {
       const long long m = m0 + u * stride;
-      ok[u] = m < M && (valids == nullptr || valids[m / N] != 0.f);
+      ok[u] = m < M && (valids == nullptr || valids[(unsigned)m / (unsigned)N] != 0.f);
       zr[u] = ok[u] ? ld_packet(z + (base + u * rstride)) : make_uint4(0u, 0u, 0u, 0u);
       dr[u] = (ok[u] && da != nullptr) ? ld_packet(da + (base + u * rstride)) : make_uint4(0u, 0u, 0u, 0u);
     }
@@ -383,8 +383,8 @@ static int pb_grid(long long M, int C, int ctas_per_sm) {
 using namespace mpa;
 
 #define PB_CHECK_SHAPE(what)                                                                        \
-  MPA_CHECK_ARG(M >= 0 && N > 0 && (C == 64 || C == 128 || C == 256), what ": unsupported shape M=%lld C=%d N=%d", \
-                M, C, N)
+  MPA_CHECK_ARG(M >= 0 && M < (1ll << 31) && N > 0 && (C == 64 || C == 128 || C == 256),                       \
+                what ": unsupported shape M=%lld C=%d N=%d (rows must fit 31 bits)", M, C, N)
 
 extern "C" {
 
