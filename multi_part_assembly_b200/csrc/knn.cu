@@ -652,31 +652,42 @@ __global__ void edge_aggregate_kernel(const float* __restrict__ uv, const int* _
                                       const float* __restrict__ valids, long long M,
                                       int N, int Co, int k, float* __restrict__ ymax,
                                       float* __restrict__ ymin, float* __restrict__ partial) {
-  extern __shared__ int sidx[];  // [EC_PTS][k]
+  // element offset of every neighbour's u row, worked out once per CTA (the address arithmetic of
+  // the gather used to be half of the kernel's instructions); -1 = point of a padded part
+  extern __shared__ long long soff[];  // [EC_PTS][k]
   const long long p0 = (long long)blockIdx.x * EC_PTS;
+  const int two_co = 2 * Co;
   for (int e = threadIdx.x; e < EC_PTS * k; e += blockDim.x) {
-    const long long p = p0 + e / k;
-    // padded parts have no graph (mpa_knn skipped them): never dereference their slots
-    const bool live = p < M && (valids == nullptr || valids[p / N] != 0.0f);
-    sidx[e] = live ? idx[p * k + e % k] : -1;
+    const int q = e / k, j = e - q * k;
+    const long long p = p0 + q;
+    long long off = -1;
+    if (p < M) {
+      const unsigned part = (unsigned)p / (unsigned)N;  // M < 2^31 (checked on the host)
+      // padded parts have no graph (mpa_knn skipped them): never dereference their slots
+      if (valids == nullptr || valids[part] != 0.0f)
+        off = ((long long)part * N + idx[p * k + j]) * two_co;
+    }
+    soff[e] = off;
   }
   __syncthreads();
   const int c = threadIdx.x;
   float s1 = 0.f, s2 = 0.f;
   if (c < Co) {
+    const float* __restrict__ uc = uv + c;
     for (int q = 0; q < EC_PTS; ++q) {
       const long long p = p0 + q;
       if (p >= M) break;
-      if (sidx[q * k] < 0) {  // point of a padded part: zero features, no BatchNorm contribution
+      const long long* so = soff + q * k;
+      if (so[0] < 0) {  // point of a padded part: zero features, no BatchNorm contribution
         ymax[p * Co + c] = 0.f;
         ymin[p * Co + c] = 0.f;
         continue;
       }
-      const long long base = p / N * N;  // first point of this part
-      const float v = uv[p * 2 * Co + Co + c];
+      const float v = __ldg(uc + p * two_co + Co);
       float mx = -3.0e38f, mn = 3.0e38f;
+#pragma unroll 4
       for (int e = 0; e < k; ++e) {
-        const float y = uv[(base + sidx[q * k + e]) * 2 * Co + c] + v;
+        const float y = __ldg(uc + so[e]) + v;
         mx = fmaxf(mx, y); mn = fminf(mn, y);
         s1 += y; s2 = fmaf(y, y, s2);
       }
@@ -1025,6 +1036,7 @@ int mpa_edge_aggregate(const float* uv, const int32_t* idx, const float* valids,
   MPA_CHECK_ARG(uv && idx && ymax && ymin && sums, "edge_aggregate: null pointer");
   const long long M = (long long)n * N;
   const long long blocks = (M + EC_PTS - 1) / EC_PTS;
+  MPA_CHECK_ARG(M < (1ll << 31), "edge_aggregate: n * N must fit 31 bits");
   Scratch scratch;
   int rc = scratch.acquire(ws, ws_bytes, mpa_edge_aggregate_workspace_bytes(M, Co), stream);
   if (rc != MPA_OK) return rc;
@@ -1032,7 +1044,7 @@ int mpa_edge_aggregate(const float* uv, const int32_t* idx, const float* valids,
   const int threads = (Co + 31) / 32 * 32;
   {
     ProfScope ps("edge_aggregate", stream);
-    edge_aggregate_kernel<<<(unsigned)blocks, threads, sizeof(int) * EC_PTS * k, stream>>>(
+    edge_aggregate_kernel<<<(unsigned)blocks, threads, sizeof(long long) * EC_PTS * k, stream>>>(
         uv, idx, valids, M, N, Co, k, ymax, ymin, partial);
   }
   MPA_LAUNCH_CHECK();
