@@ -875,11 +875,15 @@ class _TokenLinear(torch.autograd.Function):
     blocks (29 us per bias, 16 biases per step: profiles/r02_launches_train_step_summary.txt)."""
 
     @staticmethod
-    def forward(ctx, x, W, b, dt):
-        xc, Wc = x.to(dt), W.to(dt)
+    def forward(ctx, x, W, b, dt, Wc=None, bc=None):
+        # Wc / bc: the parameter already cast to `dt` (all layers' casts done in one multi-tensor
+        # launch by the caller); gradients still go to W and b
+        xc = x.to(dt)
+        if Wc is None:
+            Wc, bc = W.to(dt), b.to(dt)
         ctx.save_for_backward(xc, Wc)
         ctx.in_dtypes = (x.dtype, W.dtype, b.dtype)
-        return F.linear(xc, Wc, b.to(dt))
+        return F.linear(xc, Wc, bc)
 
     @staticmethod
     def backward(ctx, g):
@@ -895,7 +899,7 @@ class _TokenLinear(torch.autograd.Function):
         else:
             dW = _mm_f32(g2.t(), x2)
             db = _mm_f32(g2.new_ones(1, g2.shape[0]), g2).view(N)
-        return dx, dW.to(dw_t), db.to(db_t), None
+        return dx, dW.to(dw_t), db.to(db_t), None, None, None
 
 
 def _transformer_masked_torch(tokens, valid, encoder, num_heads, masks, p, fast_bias_grad=False):
@@ -908,7 +912,18 @@ def _transformer_masked_torch(tokens, valid, encoder, num_heads, masks, p, fast_
     keep = 1.0 / (1.0 - p) if masks is not None else 1.0
     if fast_bias_grad:
         dt = torch.bfloat16 if torch.is_autocast_enabled() else tokens.dtype
-        linear = lambda a, W, b: _TokenLinear.apply(a, W, b, dt)  # noqa: E731
+        cast = {}
+        if dt != tokens.dtype:  # every linear weight / bias of the encoder to `dt` in one launch
+            src = []
+            for layer in encoder.layers:
+                src += [layer.self_attn.in_proj_weight, layer.self_attn.in_proj_bias,
+                        layer.self_attn.out_proj.weight, layer.self_attn.out_proj.bias,
+                        layer.linear1.weight, layer.linear1.bias, layer.linear2.weight, layer.linear2.bias]
+            dst = [torch.empty_like(t, dtype=dt) for t in src]
+            with torch.no_grad():
+                torch._foreach_copy_(dst, [t.detach() for t in src])
+            cast = {id(t): c for t, c in zip(src, dst)}
+        linear = lambda a, W, b: _TokenLinear.apply(a, W, b, dt, cast.get(id(W)), cast.get(id(b)))  # noqa: E731
     else:
         linear = F.linear
     neg = None
