@@ -413,26 +413,29 @@ __global__ void grid_build_kernel(CloudDesc c0, CloudDesc c1, int S, float4* __r
   }
   __syncthreads();
 
-  // ---- occupancy pyramid (cnt[] now holds the cell ENDS): level 1 from the cells, each
-  // further level from the one below (global memory written by this CTA, made visible to
+  // ---- occupancy pyramid of child masks (cnt[] now holds the cell ENDS): level 1 from the cells,
+  // each further level from the one below (global memory written by this CTA, made visible to
   // it by __syncthreads) ----
   {
     int* pyr = pyr_base + (long long)(cloud * S + seg) * pl.stride;
     {
+      // level 1: bit b = dx + 2 dy + 4 dz of a node's entry says that child cell (2x+dx, 2y+dy,
+      // 2z+dz) holds points.  An entry is non-zero iff the node holds points.
       const int D = pl.D[1];
       int* lv = pyr + pl.off[1];
       for (int i = tid; i < D * D * D; i += blockDim.x) {
         const int x = i % D, y = (i / D) % D, z = i / (D * D);
-        int sum = 0;
-        const int xa = 2 * x, xb = min(2 * x + 1, g.dx - 1);
-        if (xa < g.dx) {
-          for (int zc = 2 * z; zc <= min(2 * z + 1, g.dz - 1); ++zc)
-            for (int yc = 2 * y; yc <= min(2 * y + 1, g.dy - 1); ++yc) {
-              const int row = (zc * g.dy + yc) * g.dx;
-              sum += cnt[row + xb] - (row + xa == 0 ? 0 : cnt[row + xa - 1]);
-            }
+        int mask = 0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          const int xc = 2 * x + (b & 1), yc = 2 * y + ((b >> 1) & 1), zc = 2 * z + (b >> 2);
+          if (xc < g.dx && yc < g.dy && zc < g.dz) {
+            const int ci = (zc * g.dy + yc) * g.dx + xc;
+            const int n_in = cnt[ci] - (ci == 0 ? 0 : cnt[ci - 1]);  // cnt[] holds the cell ends
+            mask |= (n_in > 0) ? (1 << b) : 0;
+          }
         }
-        lv[i] = sum;
+        lv[i] = mask;
       }
     }
     for (int L = 2; L <= pl.top; ++L) {
@@ -442,12 +445,13 @@ __global__ void grid_build_kernel(CloudDesc c0, CloudDesc c1, int S, float4* __r
       int* lv = pyr + pl.off[L];
       for (int i = tid; i < D * D * D; i += blockDim.x) {
         const int x = i % D, y = (i / D) % D, z = i / (D * D);
-        int sum = 0;
-        for (int zc = 2 * z; zc <= min(2 * z + 1, Dc - 1); ++zc)
-          for (int yc = 2 * y; yc <= min(2 * y + 1, Dc - 1); ++yc)
-            for (int xc = 2 * x; xc <= min(2 * x + 1, Dc - 1); ++xc)
-              sum += lc[(zc * Dc + yc) * Dc + xc];
-        lv[i] = sum;
+        int mask = 0;  // bit b: child node b of the level below is non-empty
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          const int xc = 2 * x + (b & 1), yc = 2 * y + ((b >> 1) & 1), zc = 2 * z + (b >> 2);
+          if (xc < Dc && yc < Dc && zc < Dc) mask |= (lc[(zc * Dc + yc) * Dc + xc] != 0) ? (1 << b) : 0;
+        }
+        lv[i] = mask;
       }
     }
   }
@@ -609,22 +613,22 @@ __device__ __forceinline__ void nn_pyramid_step(const NNQuery& c, const PyrLayou
   const float gz1 = axis_gap2(q.z, g.oz, g.h, 2 * z + 1, Lc, g.dz, slack);
   if (fminf(gx0, gx1) + fminf(gy0, gy1) + fminf(gz0, gz1) > best) return;  // whole node out of reach
   const int near = (gx1 < gx0 ? 1 : 0) | (gy1 < gy0 ? 2 : 0) | (gz1 < gz0 ? 4 : 0);
+  // ONE load says which children hold points (it was requested when this node was pushed)
+  const int D = pl.D[L];
+  const unsigned kids = (unsigned)(c.pyr + pl.off[L])[(z * D + y) * D + x];
   const int Dc = pl.D[Lc];
   const int* __restrict__ lv = c.pyr + pl.off[Lc];
 #pragma unroll
   for (int o = 7; o >= 0; --o) {  // farthest first: the nearest child ends on top of the stack
     const int b = o ^ near;
+    if (((kids >> b) & 1u) == 0u) continue;  // empty (or outside the grid)
     const int xc = 2 * x + (b & 1), yc = 2 * y + ((b >> 1) & 1), zc = 2 * z + (b >> 2);
     const float lb = ((b & 1) ? gx1 : gx0) + ((b & 2) ? gy1 : gy0) + ((b & 4) ? gz1 : gz0);
-    if (lb > best) continue;  // also drops children outside the grid (infinite gap)
-    int occ;
-    if (Lc == 0) {
-      const int ci = (zc * g.dy + yc) * g.dx + xc;
-      occ = cs[ci + 1] - cs[ci];
-    } else {
-      occ = lv[(zc * Dc + yc) * Dc + xc];
-    }
-    if (occ > 0) stack[sp++] = (Lc << 18) | (zc << 12) | (yc << 6) | xc;
+    if (lb > best) continue;
+    stack[sp++] = (Lc << 18) | (zc << 12) | (yc << 6) | xc;
+    // what the pop of this entry will read first: its own child mask, or the cell's range
+    const int* nextp = Lc == 0 ? cs + ((zc * g.dy + yc) * g.dx + xc) : lv + ((zc * Dc + yc) * Dc + xc);
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(nextp));
   }
 }
 
