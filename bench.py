@@ -446,13 +446,15 @@ def run_native(args):
     n_prof = min(args.steps, 10)
     _loss_mod.SERIAL_SEARCHES = True
     profiler.enable(True)
-    for _ in range(n_prof):
-        flush.zero_()
-        eager_step(resident)  # eager: the library's event pairs cannot be recorded inside a graph
-    torch.cuda.synchronize()
-    prof = profiler.report()
-    profiler.enable(False)
-    _loss_mod.SERIAL_SEARCHES = False
+    try:
+        for _ in range(n_prof):
+            flush.zero_()
+            eager_step(resident)  # eager: the library's event pairs cannot be recorded inside a graph
+        torch.cuda.synchronize()
+        prof = profiler.report()
+    finally:
+        profiler.enable(False)
+        _loss_mod.SERIAL_SEARCHES = False
     pair_stats = profiler.pair_stats(lambda: eager_step(resident)) \
         if hasattr(profiler, 'pair_stats') else None
 

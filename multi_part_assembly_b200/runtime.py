@@ -44,14 +44,18 @@ def _flat_views(example, device):
 
 
 class _HostRead:
-    """A device->host copy in flight (pinned destination + event); `value()` waits for it."""
+    """A device->host copy in flight (pinned destination + event); `value()` waits for it.  The
+    destination is one of a small ring of pinned scalars: a handle that is read only after the
+    ring has wrapped around raises instead of returning a later step's value."""
 
-    def __init__(self, host, event):
-        self._host, self._event = host, event
+    def __init__(self, slot, event):
+        self._slot, self._gen, self._event = slot, slot['gen'], event
 
     def value(self):
         self._event.synchronize()
-        return float(self._host)
+        if self._slot['gen'] != self._gen:
+            raise RuntimeError('read_async: this result was overwritten (more reads in flight than ring slots)')
+        return float(self._slot['host'])
 
 
 class GraphedStep:
@@ -140,14 +144,16 @@ class GraphedStep:
         return a handle; `handle.value()` waits for that copy only.  Lets the host enqueue the
         next step before it looks at this one's loss (a training loop that logs one step late)."""
         if not hasattr(self, '_host_ring'):
-            self._host_ring = [torch.empty((), dtype=torch.float32, pin_memory=True) for _ in range(4)]
+            self._host_ring = [{'host': torch.empty((), dtype=torch.float32, pin_memory=True), 'gen': 0}
+                               for _ in range(8)]
             self._host_slot = 0
-        host = self._host_ring[self._host_slot]
+        slot = self._host_ring[self._host_slot]
         self._host_slot = (self._host_slot + 1) % len(self._host_ring)
-        host.copy_(self.static_out[key].detach().reshape(()).float(), non_blocking=True)
+        slot['gen'] += 1
+        slot['host'].copy_(self.static_out[key].detach().reshape(()).float(), non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.device))
-        return _HostRead(host, ev)
+        return _HostRead(slot, ev)
 
 
 def allreduce_gradients(params, group=None):
