@@ -513,6 +513,195 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 constexpr int LN_FUSED_WIDTH = 256;  // row width the fused-LayerNorm tile supports (d_model of the reference)
 
+constexpr int GR_KTILE_BYTES = LN_BM * LN_BK * 2;  // one [128 x 64] bf16 operand k-block
+
+// ---- persistent variant of the plain GEMM (no fused LayerNorm) for many output tiles ------
+// The one-tile-per-CTA kernel above pays barrier init, TMEM allocation, the first TMA round trip
+// and a cold epilogue for every 128 x 128 tile; with M = 512 k rows (the DGCNN / PointNet++ /
+// fp32-mode GEMMs) that start-up is most of a CTA's life.  Here a CTA walks the tiles
+// blockIdx.x, +gridDim.x, ...: the operand ring keeps running across tiles, the accumulator is
+// double-buffered in TMEM, and the epilogue of tile t (staging tiles outside the ring) overlaps
+// the TMA + MMA of tile t+1.
+template <int SPLIT>
+__host__ __device__ constexpr int lp_stages() { return SPLIT == 1 ? 4 : 2; }
+template <int SPLIT>
+__host__ __device__ constexpr int lp_pitch() { return SPLIT == 1 ? EP_PITCH : 33; }
+template <int SPLIT>
+__host__ __device__ constexpr int lp_smem_bytes() {
+  return lp_stages<SPLIT>() * SPLIT * 2 * GR_KTILE_BYTES + LN_EPI_WARPS * 32 * lp_pitch<SPLIT>() * 4 + 1024;
+}
+
+template <int SPLIT>
+__global__ void __launch_bounds__(LN_THREADS, 1)
+linear_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                         int M, int N, int K, int x_plane_rows, int w_plane_rows, LinearEpilogue ep) {
+  constexpr int NST = lp_stages<SPLIT>();
+  constexpr int A_TILE = GR_KTILE_BYTES, STAGE = SPLIT * 2 * A_TILE;  // [SPLIT A planes | SPLIT B planes]
+  constexpr int PITCH = lp_pitch<SPLIT>();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* stage_tiles = reinterpret_cast<float*>(smem + NST * STAGE);
+  __shared__ uint64_t full_bar[NST], empty_bar[NST], acc_full[2], acc_free[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_k = (K + LN_BK - 1) / LN_BK;
+  const int tiles_n = (N + 127) / 128, tiles_m = (M + LN_BM - 1) / LN_BM;
+  const int n_tiles = tiles_m * tiles_n;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NST; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_free[i], LN_EPI_WARPS * 32); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc<256>(&tmem_base_s);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer =====
+      int it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int m0 = (t / tiles_n) * LN_BM, n0 = (t % tiles_n) * 128;
+        for (int kb = 0; kb < num_k; ++kb, ++it) {
+          const int s = it % NST;
+          if (it >= NST) tc::mbar_wait(&empty_bar[s], ((it / NST) - 1) & 1);
+          uint8_t* a_dst = smem + s * STAGE;
+          uint8_t* b_dst = a_dst + SPLIT * A_TILE;
+          mbar_expect_tx(&full_bar[s], STAGE);
+#pragma unroll
+          for (int pl = 0; pl < SPLIT; ++pl) {
+            tma_load_2d(a_dst + pl * A_TILE, &map_x, kb * LN_BK, pl * x_plane_rows + m0, &full_bar[s]);
+            tma_load_2d(b_dst + pl * A_TILE, &map_w, kb * LN_BK, pl * w_plane_rows + n0, &full_bar[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      constexpr uint32_t IDESC = tc::make_idesc_bf16(LN_BM, 128);
+      int it = 0, tl = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tl) {
+        const int buf = tl & 1;
+        if (tl >= 2) tc::mbar_wait(&acc_free[buf], ((tl >> 1) - 1) & 1);
+        const uint32_t acc = tmem + (uint32_t)(buf * 128);
+        for (int kb = 0; kb < num_k; ++kb, ++it) {
+          const int s = it % NST;
+          tc::mbar_wait(&full_bar[s], (it / NST) & 1);
+          tc::fence_after_sync();
+          const uint32_t a_addr = tc::smem_u32(smem + s * STAGE);
+          const uint32_t b_addr = a_addr + SPLIT * A_TILE;
+#pragma unroll
+          for (int k = 0; k < LN_BK; k += 16) {
+            if (SPLIT == 1) {
+              tc::mma_bf16(acc, tc::make_desc_sw128(a_addr + k * 2), tc::make_desc_sw128(b_addr + k * 2), IDESC,
+                           (kb > 0 || k > 0) ? 1u : 0u);
+            } else {
+              constexpr int PA[6] = {1, 2, 0, 1, 0, 0}, PB[6] = {1, 0, 2, 0, 1, 0};  // smallest terms first
+#pragma unroll
+              for (int p6 = 0; p6 < 6; ++p6)
+                tc::mma_bf16(acc, tc::make_desc_sw128(a_addr + PA[p6] * A_TILE + k * 2),
+                             tc::make_desc_sw128(b_addr + PB[p6] * A_TILE + k * 2), IDESC,
+                             (kb > 0 || k > 0 || p6 > 0) ? 1u : 0u);
+            }
+          }
+          tc::mma_commit(&empty_bar[s]);
+        }
+        tc::mma_commit(&acc_full[buf]);
+      }
+    }
+  } else {  // ===== epilogue: warps 2..9 =====
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int row_local = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    float* tile = stage_tiles + (warp - 2) * 32 * PITCH;
+    const int qcol = 4 * (lane & 7);
+    int tl = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tl) {
+      const int buf = tl & 1;
+      const int m0 = (t / tiles_n) * LN_BM, n0 = (t % tiles_n) * 128;
+      const int qrow0 = m0 + q * 32 + (lane >> 3);
+      tc::mbar_wait(&acc_full[buf], (tl >> 1) & 1);
+      tc::fence_after_sync();
+      const uint32_t acc = tmem + (uint32_t)(buf * 128) + lane_off;
+#pragma unroll 1
+      for (int j0 = half * 64; j0 < half * 64 + 64; j0 += 32) {
+        float v[32];
+        tc::tmem_ld32(acc + (uint32_t)j0, v);
+        tc::tmem_ld_wait();
+        const int col0 = n0 + j0;
+        if (col0 >= N) continue;  // warp-uniform
+        if (ep.vec && col0 + 32 <= N) {
+          float4 res[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = qrow0 + 4 * i;
+            res[i] = (ep.residual != nullptr && row < M)
+                         ? *reinterpret_cast<const float4*>(ep.residual + (long long)row * N + col0 + qcol)
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          if (ep.bias != nullptr) {  // the warp's 32 columns: broadcast 16-byte loads
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + j4);
+              v[4 * j4] += b4.x; v[4 * j4 + 1] += b4.y; v[4 * j4 + 2] += b4.z; v[4 * j4 + 3] += b4.w;
+            }
+          }
+          if (ep.act != ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
+          }
+          if (ep.drop.rng != nullptr && m0 + row_local < M) dropout32(v, ep.drop, m0 + row_local, col0, N);
+          if (SPLIT == 1) {
+            tile_put_row(tile, lane, v);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) tile[lane * PITCH + j] = v[j];
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = qrow0 + 4 * i;
+            float4 x;
+            if (SPLIT == 1) {
+              x = *tile_quad(tile, lane, i);
+            } else {
+              const float* src = tile + ((lane >> 3) + 4 * i) * PITCH + qcol;
+              x = make_float4(src[0], src[1], src[2], src[3]);
+            }
+            if (row < M) {
+              const long long o = (long long)row * N + col0 + qcol;
+              x.x += res[i].x; x.y += res[i].y; x.z += res[i].z; x.w += res[i].w;
+              if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + o) = x;
+              if (ep.out_bf16) store_operand4(ep.out_bf16, o, ep.plane, x);
+            }
+          }
+          __syncwarp();
+        } else if (m0 + row_local < M) {
+          const long long rowoff = (long long)(m0 + row_local) * N;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = col0 + j;
+            if (col >= N) continue;
+            float x = v[j] + (ep.bias ? __ldg(ep.bias + col) : 0.f);
+            x = apply_act(x, ep.act);
+            if (ep.residual) x += ep.residual[rowoff + col];
+            if (ep.out_f32) ep.out_f32[rowoff + col] = x;
+            if (ep.out_bf16) store_operand1(ep.out_bf16, rowoff + col, ep.plane, x);
+          }
+        }
+      }
+      tc::fence_before_sync();
+      mbar_arrive(&acc_free[buf]);
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc<256>(tmem);
+}
+
 // x: [split, M, K] bf16 planes, w: [split, N, K] (split = 1: plain bf16 operands)
 int launch_linear(const __nv_bfloat16* x, const __nv_bfloat16* w, int M, int N, int K,
                   LinearEpilogue ep, const char* name, cudaStream_t stream, int split = 1) {
@@ -544,6 +733,27 @@ int launch_linear(const __nv_bfloat16* x, const __nv_bfloat16* w, int M, int N, 
     attr.done();
   }
   dim3 grid((M + LN_BM - 1) / LN_BM, (N + bn - 1) / bn);
+  // many tiles and no fused LayerNorm: the persistent kernel (every CTA walks several tiles)
+  static const bool no_persist = getenv("MPA_LINEAR_ONE_TILE") != nullptr;  // A/B switch
+  if (!fuse_ln && !no_persist && (long long)grid.x * grid.y >= 2ll * device_sms() && (!ep.vec || aligned16(ep.bias))) {
+    static DeviceOnce attr_p;
+    if (attr_p.pending()) {
+      MPA_CUDA(cudaFuncSetAttribute(linear_persistent_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    lp_smem_bytes<1>()));
+      MPA_CUDA(cudaFuncSetAttribute(linear_persistent_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    lp_smem_bytes<3>()));
+      attr_p.done();
+    }
+    {
+      ProfScope ps(name, stream);
+      if (split == 1)
+        linear_persistent_kernel<1><<<device_sms(), LN_THREADS, lp_smem_bytes<1>(), stream>>>(mx, mw, M, N, K, M, N, ep);
+      else
+        linear_persistent_kernel<3><<<device_sms(), LN_THREADS, lp_smem_bytes<3>(), stream>>>(mx, mw, M, N, K, M, N, ep);
+    }
+    MPA_LAUNCH_CHECK();
+    return MPA_OK;
+  }
   {
     ProfScope ps(name, stream);
     if (split == 1) {
